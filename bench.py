@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registrations/s on B200 (BASELINE.json metric).
+
+A "step" is one registration of the hot path: downsampleCurrentScan (MO:1067-1091) +
+scan2MapOptimization (MO:1329-1350, including the spatial-index build that replaces the two
+kdtree->setInputCloud calls) of one synthetic VLP-16 sweep against a ~100k-point voxel-DS
+local map (BASELINE configs[1]; one independent sequence per GPU, weak scaling, no
+collective on the data path).
+
+  value : device-resident inputs, CUDA events on the context's stream, L2 flushed between
+          timed steps (working set << L2 otherwise), max over ranks.
+  e2e   : the same step through the C ABI with HOST clouds in pcl::PointXYZI layout
+          (H2D of scan + DS map and D2H of the pose inside the timed region), wall clock.
+  roofline : the fused kNN+fit+J^T J kernel, 96 algorithmic bytes per query.
+  cpu_baseline : the CPU oracle (or the reference-linked harness when built) on a bounded
+          sample of the same workload, 1 core.
+  --impl reference : the reference's CPU path on all host cores (one registration per core).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_QUERY = 96          # 16 B query float4 + 5 x 16 B neighbour float4
+WORKLOADS = {
+    # name: (sensor, n_corner_raw, n_surf_raw, corner radius, surf radius)   -> DS map size
+    "vlp16_100k": ("vlp16", 400000, 110000, 120.0, 60.0),
+    "vlp16_50k": ("vlp16", 150000, 50000, 90.0, 45.0),
+    "hdl32e_300k": ("hdl32e", 900000, 420000, 160.0, 110.0),
+}
+
+
+def make_inputs(workload: str, rank: int, n_scans: int):
+    """One local map + n_scans sweeps around it (independent sequence per rank)."""
+    from lego_loam_b200 import synth
+    sensor, ncr, nsr, rad, srad = WORKLOADS[workload]
+    w = synth.make_world(synth.SEED0 + rank)
+    rng = np.random.default_rng(7000 + rank)
+    centre = np.array([rng.uniform(-10, 10), 0.0, rng.uniform(-10, 10)])
+    mc, ms = synth.make_local_map(w, centre, ncr, nsr, seed=11 + rank, radius=rad, surf_radius=srad)
+    scans = []
+    for k in range(n_scans):
+        pose = np.array([rng.uniform(-0.02, 0.02), rng.uniform(-3.1, 3.1), rng.uniform(-0.02, 0.02),
+                         centre[0] + rng.uniform(-8, 8), rng.uniform(-0.03, 0.03), centre[2] + rng.uniform(-8, 8)])
+        sc = synth.make_mapping_scan(w, synth.SENSORS[sensor], pose, seed=100 * rank + k)
+        scans.append((sc, synth.perturb_pose(pose, rng)))
+    return mc, ms, scans
+
+
+def sample_clocks(stop_evt, out, dev):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+    while not stop_evt.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(dev)],
+                               capture_output=True, text=True, timeout=5).stdout.strip()
+            if r:
+                out.append([x.strip() for x in r.split(",")])
+        except Exception:
+            pass
+        stop_evt.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    mx = max(int(s[1]) for s in samples if s[1].isdigit())
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        for k, nme in enumerate(names):
+            if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                reasons.add(nme)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+def cpu_registration_factory(mc_ds, ms_ds, scans):
+    """Returns (fn(i) -> pose, kind) running the reference CPU path on registration i."""
+    kind = "port"
+    try:
+        from oracle import ref_harness                       # reference-linked harness, when built
+        if ref_harness.available():
+            kind = "reference"
+    except Exception:
+        ref_harness = None
+    if kind == "reference":
+        mo = ref_harness.MapOptimization()
+    else:
+        import oracle
+        oracle.set_trig_mode(0)
+        mo = oracle.MapOptimization()
+
+    def run(i):
+        sc, init = scans[i % len(scans)]
+        mo.set_map_ds(mc_ds, ms_ds)
+        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
+        mo.transformTobeMapped = init
+        mo.downsampleCurrentScan()
+        mo.scan2MapOptimization()
+        return mo.transformTobeMapped
+    return run, kind
+
+
+def _ref_worker(args):
+    workload, rank, n_scans, n_regs, start_at = args
+    import oracle
+    mc, ms, scans = make_inputs(workload, rank, n_scans)
+    mc_ds, _ = oracle.voxel_grid(mc, 0.2); ms_ds, _ = oracle.voxel_grid(ms, 0.4)
+    run, kind = cpu_registration_factory(mc_ds, ms_ds, scans)
+    run(0)                                                   # warm-up
+    while time.time() < start_at:
+        time.sleep(0.001)
+    t0 = time.perf_counter()
+    for i in range(n_regs):
+        run(i)
+    return time.perf_counter() - t0, kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path, one registration stream per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    per_core = 3                                             # registrations per core per step
+    K, W = args.steps, args.warmup
+    n_regs = per_core * (K + min(W, 1))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        start_at = time.time() + 30.0                        # every worker builds its inputs first
+        res = pool.map(_ref_worker, [(args.workload, 0, 2, per_core * K, start_at)] * cores)
+    wall = max(r[0] for r in res)
+    kind = res[0][1]
+    total = cores * per_core * K
+    value = total / wall
+    ms_per_step = wall / K * 1e3
+    line = {
+        "impl": "reference", "metric": "scan-to-map registrations/s", "value": value, "unit": "registrations/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: VLP-16 sweep vs ~100k-pt DS local map, downsampleCurrentScan+"
+                               f"scan2MapOptimization, {per_core} registrations/core/step on {cores} cores"},
+        "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": kind,
+                         "sample": f"{total} registrations ({per_core}/core/step x {K} steps x {cores} cores)"},
+        "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_registration_1core": wall / (per_core * K) * 1e3,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vlp16_100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--scans", type=int, default=4, help="distinct sweeps rotated through the steps")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="registrations timed for cpu_baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from lego_loam_b200 import api
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, max(args.warmup, 3)
+
+    mc, ms, scans = make_inputs(args.workload, rank, args.scans)
+    ctx = api.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    # DS map is what the drop-in signature receives (MO:1057-1064 is the caller's tail); produce it once
+    ctx.map_set_raw(mc, ms)
+    mc_ds = ctx.map_get_ds(0); ms_ds = ctx.map_get_ds(1)
+    mc32 = api.to_pcl(mc_ds); ms32 = api.to_pcl(ms_ds)
+    scans32 = [(api.to_pcl(s.corner_last), api.to_pcl(s.surf_last), api.to_pcl(s.outlier_last), init)
+               for s, init in scans]
+
+    # ---------------- device-resident arm (value)
+    dev = torch.device("cuda", local)
+    d_mc = torch.from_numpy(mc_ds).to(dev); d_ms = torch.from_numpy(ms_ds).to(dev)
+    d_scans = [(torch.from_numpy(s.corner_last).to(dev), torch.from_numpy(s.surf_last).to(dev),
+                torch.from_numpy(s.outlier_last).to(dev), torch.from_numpy(init.copy()).to(dev)) for s, init in scans]
+    d_T = torch.zeros(6, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        c, s, o, init = d_scans[i % len(d_scans)]
+        d_T.copy_(init)
+        ctx.scan_set_dev(c.data_ptr(), c.shape[0], s.data_ptr(), s.shape[0], o.data_ptr(), o.shape[0])
+        ctx.downsample_current_scan(want_counts=False)
+        ctx.map_set_ds_dev(d_mc.data_ptr(), d_mc.shape[0], d_ms.data_ptr(), d_ms.shape[0])
+        ctx.s2m_optimize_dev(d_T.data_ptr())
+
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            flush.zero_(); step_dev(i)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk_samples, stop_evt = [], threading.Event()
+        th = threading.Thread(target=sample_clocks, args=(stop_evt, clk_samples, local)); th.start()
+        l0 = ctx.launch_count()
+        evs = []
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                                    # L2 flush between timed steps (not timed)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); step_dev(i); e1.record(stream)
+            evs.append((e0, e1))
+        stream.synchronize()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        launches = ctx.launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        dev_ms = [a.elapsed_time(b) for a, b in evs]
+
+        # ---------------- end-to-end arm (host clouds through the C ABI)
+        def step_host(i):
+            c, s, o, init = scans32[i % len(scans32)]
+            ctx.scan_set_pcl(c, s, o)
+            ctx.downsample_current_scan(want_counts=False)
+            ctx.map_set_ds_pcl(mc32, ms32)
+            T, st = ctx.s2m_optimize(init)
+            return T, st
+        for i in range(W):
+            step_host(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            T_last, st_last = step_host(i)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        stop_evt.set(); th.join()
+
+        # ---------------- roofline of the dominant kernel (timed alone, after the steps)
+        ms_launch, nq = ctx.s2m_time_iteration(scans32[0][3], reps=50)
+
+    total_ms = float(np.sum(dev_ms))
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = total_ms / K
+        value = world * K / (total_ms / 1e3)
+        h2d = sum(a.nbytes for a in scans32[0][:3]) + mc32.nbytes + ms32.nbytes + 24
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = ALG_BYTES_PER_QUERY * nq / (ms_launch * 1e-3) / 1e9
+        # bounded CPU sample on this box's host cores, 1 core
+        run_cpu, kind = cpu_registration_factory(mc_ds, ms_ds, scans)
+        run_cpu(0)
+        t0 = time.perf_counter()
+        for i in range(args.cpu_sample):
+            T_cpu = run_cpu(i)
+        cpu_s = time.perf_counter() - t0
+        line = {
+            "metric": "scan-to-map registrations/s", "value": value, "unit": "registrations/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: VLP-16 16x1800 synthetic sweep vs {mc_ds.shape[0] + ms_ds.shape[0]}-pt "
+                                   f"voxel-DS local map; step = downsampleCurrentScan + scan2MapOptimization "
+                                   f"(index build + <=10 LM iterations); one independent sequence per GPU",
+                       "queries_per_iteration": nq, "map_points": int(mc_ds.shape[0] + ms_ds.shape[0]),
+                       "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "timing": "sum of per-step CUDA-event intervals on the context stream, max over ranks"},
+            "e2e": {"value": world * K / e2e_s, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 24 + 32, "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": summarize_clocks(clk_samples),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "s2m_iter_kernel",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback",
+                         "ms_per_launch": ms_launch, "alg_bytes_per_launch": ALG_BYTES_PER_QUERY * nq},
+            "cpu_baseline": {"value": args.cpu_sample / cpu_s, "unit": "registrations/s", "cores": 1, "kind": kind,
+                             "sample": f"{args.cpu_sample} registrations of the same workload, 1 core",
+                             "ms_per_registration": cpu_s / args.cpu_sample * 1e3},
+            "wall_s_timed_region": t_wall,
+            "last_stats": st_last.as_dict(),
+            "pose_check_max_abs_diff_vs_cpu": float(np.max(np.abs(T_last - run_cpu((K - 1)))))
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,178 @@
+/*
+ * llb200.h — C ABI of lego_loam_b200: the B200-native (sm_100a) drop-in for the
+ * scan-matching hot path of LeGO-LOAM.
+ *
+ * The reference (priseup/LeGO-LOAM) has no plugin / FFI surface: the boundary is
+ * a set of C++ member functions of two monolithic classes.
+ * Each entry point below names the reference member function(s) it replaces
+ * (MO = LeGO-LOAM/src/mapOptmization.cpp, FA = LeGO-LOAM/src/featureAssociation.cpp,
+ * UT = LeGO-LOAM/include/utility.h).  The C++ adapter classes that keep the
+ * reference's own names and signatures on top of this ABI are in
+ * lego_loam_b200/host/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every call returns llb_status;
+ *    on any error the pose passed in is left untouched (the reference's own
+ *    behaviour when a guard fails, MO:1238, MO:1331, FA:1668).
+ *  - host clouds use pcl::PointXYZI's layout (llb_point, 32 B);
+ *    the *_dev family takes device pointers to compact float4 {x,y,z,intensity}.
+ *  - a context owns one CUDA stream and all workspaces; it is not re-entrant
+ *    (the reference runs the path under one mutex, MO:1497).
+ *  - pose T[6] = {rx, ry, rz, tx, ty, tz}, p_map = Ry Rx Rz p + t (MO:513-527).
+ */
+#ifndef LLB200_H_
+#define LLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLB_ABI_VERSION 1
+
+typedef enum {
+    LLB_OK = 0,
+    LLB_ERR_INVALID = 1,      /* bad argument */
+    LLB_ERR_CUDA = 2,         /* CUDA runtime error, see llb_last_error */
+    LLB_ERR_NO_DEVICE = 3,    /* no usable sm_100 device: there is NO CPU fallback */
+    LLB_ERR_CAPACITY = 4,     /* caller buffer too small */
+    LLB_ERR_STATE = 5         /* call order violated (e.g. optimise before map/scan set) */
+} llb_status;
+
+/* pcl::PointXYZI: union{float data[4]; {x,y,z}} + union{{intensity}; float data_c[4]} */
+typedef struct {
+    float x, y, z, w;         /* w = data[3], 1.0f in PCL */
+    float intensity, c1, c2, c3;
+} llb_point;
+
+/* every tunable the hot path reads; defaults = the reference's constants */
+typedef struct {
+    float corner_leaf;            /* 0.2  MO:249 */
+    float surf_leaf;              /* 0.4  MO:250 */
+    float outlier_leaf;           /* 0.4  MO:251 */
+    float knn_max_sqdist;         /* 1.0  MO:1101, MO:1183 */
+    int   s2m_max_iterations;     /* 10   MO:1336 */
+    int   s2m_min_correspondences;/* 50   MO:1238 */
+    float s2m_degeneracy_thresh;  /* 100  MO:1287 */
+    float s2m_converge_deg;       /* 0.05 MO:1323 */
+    float s2m_converge_cm;        /* 0.05 MO:1323 */
+    int   corner_map_min;         /* 10   MO:1331 (strict >) */
+    int   surf_map_min;           /* 100  MO:1331 (strict >) */
+    float odom_nearest_sqdist;    /* 25   UT:125 */
+    int   odom_max_iterations;    /* 25   FA:1671, FA:1683 */
+    int   odom_min_correspondences;/* 10  FA:1677, FA:1690 */
+    float odom_degeneracy_thresh; /* 10   FA:1338, FA:1439 */
+    float odom_converge_deg;      /* 0.1  FA:1373 */
+    float odom_converge_cm;       /* 0.1  FA:1373 */
+    int   max_grid_cells;         /* spatial-index cell budget per map (default 1<<23) */
+} llb_params;
+
+typedef struct {
+    int   iterations;             /* LM iterations executed */
+    int   converged;              /* 1 if the convergence test ended the loop */
+    int   n_correspondences;      /* rows of the last iteration (laserCloudOri size) */
+    int   is_degenerate;          /* isDegenerate after the call */
+    int   skipped;                /* 1 if the map-size guard MO:1331 / FA:1668 skipped the work */
+    int   n_corner_ds, n_surf_ds; /* query counts used */
+    float device_ms;              /* CUDA-event time of the device work of this call */
+} llb_stats;
+
+typedef struct llb_ctx llb_ctx;
+
+/* ---- lifetime ---- */
+int  llb_abi_version(void);
+void llb_params_default(llb_params *p);
+int  llb_create(const llb_params *p /* NULL = defaults */, int device, llb_ctx **out);
+int  llb_destroy(llb_ctx *ctx);
+const char *llb_last_error(const llb_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every call of this context is ordered on */
+void *llb_stream(llb_ctx *ctx);
+int  llb_synchronize(llb_ctx *ctx);
+
+/* ---- pcl::VoxelGrid<PointXYZI>::filter (setLeafSize(leaf,leaf,leaf), defaults)
+ *      call sites MO:1058-1063, MO:1070-1089, FA:779-780 ---- */
+int llb_voxel_downsample(llb_ctx *ctx, const llb_point *in, int n, float leaf,
+                         llb_point *out, int out_capacity, int *m);
+
+/* ---- mapOptimization ---- */
+/* laserCloudCornerFromMapDS / laserCloudSurfFromMapDS hand-over + the two
+ * kdtree->setInputCloud calls of MO:1333-1334 (device spatial index build) */
+int llb_map_set_ds(llb_ctx *ctx, const llb_point *corner_ds, int mc, const llb_point *surf_ds, int ms);
+/* raw local map: tail of extractSurroundingKeyFrames MO:1057-1064 (two voxel
+ * filters) followed by the index build */
+int llb_map_set_raw(llb_ctx *ctx, const llb_point *corner, int rc, const llb_point *surf, int rs);
+/* which: 0 corner, 1 surf.  n receives the size even when out == NULL */
+int llb_map_get_ds(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+/* laserCloudCornerLast / SurfLast / OutlierLast (handlers MO:608-627) */
+int llb_scan_set(llb_ctx *ctx, const llb_point *corner_last, int nc, const llb_point *surf_last, int ns,
+                 const llb_point *outlier_last, int no);
+/* downsampleCurrentScan MO:1067-1091; counts = {cornerDS, surfDS, outlierDS, surfTotalDS}
+ * (counts may be NULL: then no host synchronisation happens) */
+int llb_downsample_current_scan(llb_ctx *ctx, int counts[4]);
+/* which: 0 cornerLastDS, 1 surfLastDS, 2 outlierLastDS, 3 surfTotalLastDS */
+int llb_scan_get_ds(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+/* one iteration of the loop body MO:1338-1345: cornerOptimization + surfOptimization
+ * + LMOptimization(iter).  T is transformTobeMapped in/out. */
+int llb_s2m_iterate(llb_ctx *ctx, float T[6], int iter, int *converged, int *n_correspondences);
+/* scan2MapOptimization MO:1329-1350 without transformUpdate's bookkeeping: guard,
+ * index (already built by llb_map_set_*), <= 10 fused iterations with the
+ * convergence test on device, no host round trip inside. */
+int llb_s2m_optimize(llb_ctx *ctx, float T[6], llb_stats *stats);
+/* laserCloudOri / coeffSel of the last iteration run by llb_s2m_iterate, in the
+ * reference's order (corner rows then surf rows, each in query order) */
+int llb_get_correspondences(llb_ctx *ctx, llb_point *ori, llb_point *coeff, int capacity, int *n);
+/* diagnostics: 5-NN original map indices (-1 where < 5 candidates in range) and
+ * squared distances per query of the last llb_s2m_iterate; which: 0 corner, 1 surf */
+int llb_get_knn(llb_ctx *ctx, int which, int *idx5, float *sqdist5, int capacity, int *n);
+/* AtA (36), AtB (6), X (6) of the last LM step */
+int llb_get_normal_equations(llb_ctx *ctx, float AtA[36], float AtB[6], float X[6]);
+/* isDegenerate / matP persist across registrations (MO:202-203) */
+int llb_get_degeneracy(llb_ctx *ctx, int *is_degenerate, float matP[36]);
+int llb_set_degeneracy(llb_ctx *ctx, int is_degenerate, const float matP[36]);
+
+/* ---- featureAssociation ---- */
+/* laserCloudCornerLast / laserCloudSurfLast + kdtree rebuild (FA:1615-1619, FA:1774-1788) */
+int llb_odom_set_last(llb_ctx *ctx, const llb_point *corner_last, int ncl, const llb_point *surf_last, int nsl);
+/* cornerPointsSharp / surfPointsFlat of the current sweep */
+int llb_odom_set_features(llb_ctx *ctx, const llb_point *corner_sharp, int nsharp, const llb_point *surf_flat, int nflat);
+/* updateTransformation FA:1666-1695: both <= 25-iteration loops on device. T = transformCur in/out */
+int llb_odom_optimize(llb_ctx *ctx, float T[6], llb_stats *stats_surf, llb_stats *stats_corner);
+/* single steps for per-function parity: which 0 = surf (findCorrespondingSurfFeatures +
+ * calculateTransformationSurf), 1 = corner.  *more = the reference's return value
+ * (false = converged, C8); *n_correspondences = laserCloudOri size; the LM step is
+ * skipped when it is < 10 (FA:1677) */
+int llb_odom_iterate(llb_ctx *ctx, int which, float T[6], int iter, int *more, int *n_correspondences);
+int llb_odom_get_correspondences(llb_ctx *ctx, llb_point *ori, llb_point *coeff, int capacity, int *n);
+int llb_odom_get_search_ind(llb_ctx *ctx, int which, float *ind1, float *ind2, float *ind3, int capacity, int *n);
+int llb_odom_get_degeneracy(llb_ctx *ctx, int *is_degenerate, float matP[9]);
+
+/* ---- device-resident family (inputs already in HBM as float4 {x,y,z,intensity}) ---- */
+int llb_map_set_ds_dev(llb_ctx *ctx, const void *corner_ds_f4, int mc, const void *surf_ds_f4, int ms);
+int llb_map_set_raw_dev(llb_ctx *ctx, const void *corner_f4, int rc, const void *surf_f4, int rs);
+int llb_scan_set_dev(llb_ctx *ctx, const void *corner_f4, int nc, const void *surf_f4, int ns,
+                     const void *outlier_f4, int no);
+/* pose in/out in device memory (6 floats); nothing is copied to the host */
+int llb_s2m_optimize_dev(llb_ctx *ctx, float *T_dev);
+/* sharded large-map mode (BASELINE config 4): this rank accumulates the normal
+ * equations of ITS share of the queries into 28 doubles (21 upper-tri AtA, 6 AtB,
+ * count) at a device address the caller all-reduces (NCCL) before llb_s2m_solve */
+int llb_s2m_accumulate(llb_ctx *ctx, int iter, int rank, int world, double **acc28_dev);
+int llb_s2m_solve(llb_ctx *ctx, int iter, int *converged);
+int llb_s2m_pose_set(llb_ctx *ctx, const float T[6]);
+int llb_s2m_pose_get(llb_ctx *ctx, float T[6]);
+
+/* measurement hook for the roofline line of bench.py: launches the fused K3+K4 iteration
+ * kernel `reps` times on the context's stream at pose T with the LM step disabled (the
+ * state is left untouched), bracketed by CUDA events on that stream; *ms_per_launch is the
+ * average device time of one launch, *n_queries the number of queries one launch processes */
+int llb_s2m_time_iteration(llb_ctx *ctx, const float T[6], int reps, float *ms_per_launch, int *n_queries);
+
+/* number of kernels launched by this context since creation (bench.py gpu_launches) */
+long long llb_launch_count(const llb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLB200_H_ */

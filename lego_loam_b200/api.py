@@ -1,0 +1,341 @@
+"""ctypes binding of the C ABI in include/llb200.h (libllb200.so).
+
+This is the Python host-side mirror used by tests/ and bench.py; the C++ adapter
+classes with the reference's own member-function names live in host/.  There is
+no CPU fallback: if the CUDA library is missing or no sm_100 device is present,
+loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libllb200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+LLB_OK, LLB_ERR_INVALID, LLB_ERR_CUDA, LLB_ERR_NO_DEVICE, LLB_ERR_CAPACITY, LLB_ERR_STATE = range(6)
+_STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NO_DEVICE", 4: "CAPACITY", 5: "STATE"}
+
+
+class LlbError(RuntimeError):
+    def __init__(self, status: int, msg: str = ""):
+        super().__init__(f"llb200 status {_STATUS.get(status, status)}: {msg}")
+        self.status = status
+
+
+class Params(ctypes.Structure):
+    _fields_ = [
+        ("corner_leaf", ctypes.c_float), ("surf_leaf", ctypes.c_float), ("outlier_leaf", ctypes.c_float),
+        ("knn_max_sqdist", ctypes.c_float),
+        ("s2m_max_iterations", ctypes.c_int), ("s2m_min_correspondences", ctypes.c_int),
+        ("s2m_degeneracy_thresh", ctypes.c_float), ("s2m_converge_deg", ctypes.c_float),
+        ("s2m_converge_cm", ctypes.c_float),
+        ("corner_map_min", ctypes.c_int), ("surf_map_min", ctypes.c_int),
+        ("odom_nearest_sqdist", ctypes.c_float), ("odom_max_iterations", ctypes.c_int),
+        ("odom_min_correspondences", ctypes.c_int), ("odom_degeneracy_thresh", ctypes.c_float),
+        ("odom_converge_deg", ctypes.c_float), ("odom_converge_cm", ctypes.c_float),
+        ("max_grid_cells", ctypes.c_int),
+    ]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("iterations", ctypes.c_int), ("converged", ctypes.c_int), ("n_correspondences", ctypes.c_int),
+        ("is_degenerate", ctypes.c_int), ("skipped", ctypes.c_int),
+        ("n_corner_ds", ctypes.c_int), ("n_surf_ds", ctypes.c_int), ("device_ms", ctypes.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "llb_abi_version", "llb_params_default", "llb_create", "llb_destroy", "llb_last_error", "llb_stream",
+    "llb_synchronize", "llb_voxel_downsample", "llb_map_set_ds", "llb_map_set_raw", "llb_map_get_ds",
+    "llb_scan_set", "llb_downsample_current_scan", "llb_scan_get_ds", "llb_s2m_iterate", "llb_s2m_optimize",
+    "llb_get_correspondences", "llb_get_knn", "llb_get_normal_equations", "llb_get_degeneracy",
+    "llb_set_degeneracy", "llb_odom_set_last", "llb_odom_set_features", "llb_odom_optimize", "llb_odom_iterate",
+    "llb_odom_get_correspondences", "llb_odom_get_search_ind", "llb_odom_get_degeneracy",
+    "llb_map_set_ds_dev", "llb_map_set_raw_dev", "llb_scan_set_dev", "llb_s2m_optimize_dev",
+    "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
+    "llb_s2m_time_iteration",
+]
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_PKG, "..", "include", "llb200.h"))
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", CSRC, "-s", "-j8"])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LlbError(LLB_ERR_NO_DEVICE, f"{LIB_PATH} is not built (run __graft_entry__.build())")
+        L = ctypes.CDLL(LIB_PATH)
+        L.llb_last_error.restype = ctypes.c_char_p
+        L.llb_stream.restype = ctypes.c_void_p
+        L.llb_launch_count.restype = ctypes.c_longlong
+        for name in EXPORTS:
+            getattr(L, name)   # raises AttributeError if a declared symbol is missing
+        _lib = L
+    return _lib
+
+
+def to_pcl(pts) -> np.ndarray:
+    """(n,4) float32 {x,y,z,intensity} -> (n,8) float32 in pcl::PointXYZI's 32-byte layout."""
+    a = np.ascontiguousarray(pts, np.float32).reshape(-1, 4)
+    out = np.zeros((a.shape[0], 8), np.float32)
+    out[:, :3] = a[:, :3]
+    out[:, 3] = 1.0
+    out[:, 4] = a[:, 3]
+    return out
+
+
+def from_pcl(p32: np.ndarray) -> np.ndarray:
+    out = np.empty((p32.shape[0], 4), np.float32)
+    out[:, :3] = p32[:, :3]
+    out[:, 3] = p32[:, 4]
+    return out
+
+
+def _vp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class Context:
+    """One llb_ctx: one CUDA stream + workspaces on one device."""
+
+    def __init__(self, device: int = 0, params: Params | None = None):
+        L = lib()
+        self._h = ctypes.c_void_p()
+        if params is None:
+            params = default_params()
+        self.params = params
+        rc = L.llb_create(ctypes.byref(params), int(device), ctypes.byref(self._h))
+        if rc != LLB_OK:
+            self._h = ctypes.c_void_p()
+            raise LlbError(rc, "llb_create failed (no CPU fallback exists)")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().llb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != LLB_OK:
+            raise LlbError(rc, (lib().llb_last_error(self._h) or b"").decode())
+
+    @property
+    def stream(self) -> int:
+        return lib().llb_stream(self._h) or 0
+
+    def synchronize(self):
+        self._ck(lib().llb_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib().llb_launch_count(self._h))
+
+    # ---- voxel
+    def voxel_downsample(self, pts, leaf: float) -> np.ndarray:
+        src = to_pcl(pts)
+        n = src.shape[0]
+        out = np.zeros((max(n, 1), 8), np.float32)
+        m = ctypes.c_int(0)
+        self._ck(lib().llb_voxel_downsample(self._h, _vp(src), n, ctypes.c_float(leaf), _vp(out), n, ctypes.byref(m)))
+        return from_pcl(out[:m.value])
+
+    # ---- map
+    def map_set_ds(self, corner_ds, surf_ds):
+        c = to_pcl(corner_ds); s = to_pcl(surf_ds)
+        self._ck(lib().llb_map_set_ds(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    def map_set_ds_pcl(self, c32: np.ndarray, s32: np.ndarray):
+        self._ck(lib().llb_map_set_ds(self._h, _vp(c32), c32.shape[0], _vp(s32), s32.shape[0]))
+
+    def map_set_raw(self, corner, surf):
+        c = to_pcl(corner); s = to_pcl(surf)
+        self._ck(lib().llb_map_set_raw(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    def map_set_raw_pcl(self, c32: np.ndarray, s32: np.ndarray):
+        self._ck(lib().llb_map_set_raw(self._h, _vp(c32), c32.shape[0], _vp(s32), s32.shape[0]))
+
+    def map_get_ds(self, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_map_get_ds(self._h, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_map_get_ds(self._h, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    # ---- scan
+    def scan_set(self, corner_last, surf_last, outlier_last):
+        c = to_pcl(corner_last); s = to_pcl(surf_last); o = to_pcl(outlier_last)
+        self.scan_set_pcl(c, s, o)
+
+    def scan_set_pcl(self, c32, s32, o32):
+        self._ck(lib().llb_scan_set(self._h, _vp(c32), c32.shape[0], _vp(s32), s32.shape[0], _vp(o32), o32.shape[0]))
+
+    def downsample_current_scan(self, want_counts: bool = True):
+        if not want_counts:
+            self._ck(lib().llb_downsample_current_scan(self._h, None))
+            return None
+        cnt = (ctypes.c_int * 4)()
+        self._ck(lib().llb_downsample_current_scan(self._h, cnt))
+        return list(cnt)
+
+    def scan_get_ds(self, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_scan_get_ds(self._h, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_scan_get_ds(self._h, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    # ---- scan-to-map
+    def s2m_iterate(self, T, it: int):
+        t = np.ascontiguousarray(T, np.float32).copy()
+        conv = ctypes.c_int(0); nc = ctypes.c_int(0)
+        self._ck(lib().llb_s2m_iterate(self._h, _fp(t), it, ctypes.byref(conv), ctypes.byref(nc)))
+        return t, bool(conv.value), nc.value
+
+    def s2m_optimize(self, T):
+        t = np.ascontiguousarray(T, np.float32).copy()
+        st = Stats()
+        self._ck(lib().llb_s2m_optimize(self._h, _fp(t), ctypes.byref(st)))
+        return t, st
+
+    def get_correspondences(self):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_get_correspondences(self._h, None, None, 0, ctypes.byref(n)))
+        ori = np.zeros((max(n.value, 1), 8), np.float32); co = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_get_correspondences(self._h, _vp(ori), _vp(co), n.value, ctypes.byref(n)))
+        return from_pcl(ori[:n.value]), from_pcl(co[:n.value])
+
+    def get_knn(self, which: int):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_get_knn(self._h, which, None, None, 0, ctypes.byref(n)))
+        idx = np.zeros((max(n.value, 1), 5), np.int32); d2 = np.zeros((max(n.value, 1), 5), np.float32)
+        self._ck(lib().llb_get_knn(self._h, which, _vp(idx), _vp(d2), n.value, ctypes.byref(n)))
+        return idx[:n.value], d2[:n.value]
+
+    def get_normal_equations(self):
+        A = np.zeros((6, 6), np.float32); B = np.zeros(6, np.float32); X = np.zeros(6, np.float32)
+        self._ck(lib().llb_get_normal_equations(self._h, _fp(A), _fp(B), _fp(X)))
+        return A, B, X
+
+    def get_degeneracy(self):
+        d = ctypes.c_int(0); P = np.zeros((6, 6), np.float32)
+        self._ck(lib().llb_get_degeneracy(self._h, ctypes.byref(d), _fp(P)))
+        return bool(d.value), P
+
+    def set_degeneracy(self, deg: bool, P):
+        P = np.ascontiguousarray(P, np.float32)
+        self._ck(lib().llb_set_degeneracy(self._h, int(deg), _fp(P)))
+
+    # ---- odometry
+    def odom_set_last(self, corner_last, surf_last):
+        c = to_pcl(corner_last); s = to_pcl(surf_last)
+        self._ck(lib().llb_odom_set_last(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    def odom_set_features(self, sharp, flat):
+        c = to_pcl(sharp); s = to_pcl(flat)
+        self._ck(lib().llb_odom_set_features(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    def odom_optimize(self, T):
+        t = np.ascontiguousarray(T, np.float32).copy()
+        s0 = Stats(); s1 = Stats()
+        self._ck(lib().llb_odom_optimize(self._h, _fp(t), ctypes.byref(s0), ctypes.byref(s1)))
+        return t, s0, s1
+
+    def odom_iterate(self, which: int, T, it: int):
+        t = np.ascontiguousarray(T, np.float32).copy()
+        more = ctypes.c_int(0); nc = ctypes.c_int(0)
+        self._ck(lib().llb_odom_iterate(self._h, which, _fp(t), it, ctypes.byref(more), ctypes.byref(nc)))
+        return t, bool(more.value), nc.value
+
+    def odom_get_correspondences(self):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_odom_get_correspondences(self._h, None, None, 0, ctypes.byref(n)))
+        ori = np.zeros((max(n.value, 1), 8), np.float32); co = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_odom_get_correspondences(self._h, _vp(ori), _vp(co), n.value, ctypes.byref(n)))
+        return from_pcl(ori[:n.value]), from_pcl(co[:n.value])
+
+    def odom_get_search_ind(self, which: int):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_odom_get_search_ind(self._h, which, None, None, None, 0, ctypes.byref(n)))
+        a = np.zeros(max(n.value, 1), np.float32); b = a.copy(); c = a.copy()
+        self._ck(lib().llb_odom_get_search_ind(self._h, which, _fp(a), _fp(b), _fp(c), n.value, ctypes.byref(n)))
+        return a[:n.value], b[:n.value], c[:n.value]
+
+    def odom_get_degeneracy(self):
+        d = ctypes.c_int(0); P = np.zeros((3, 3), np.float32)
+        self._ck(lib().llb_odom_get_degeneracy(self._h, ctypes.byref(d), _fp(P)))
+        return bool(d.value), P
+
+    # ---- device-resident family (pointers are raw device addresses, e.g. torch .data_ptr())
+    def map_set_ds_dev(self, corner_ptr: int, mc: int, surf_ptr: int, ms: int):
+        self._ck(lib().llb_map_set_ds_dev(self._h, ctypes.c_void_p(corner_ptr), mc, ctypes.c_void_p(surf_ptr), ms))
+
+    def map_set_raw_dev(self, corner_ptr: int, rc: int, surf_ptr: int, rs: int):
+        self._ck(lib().llb_map_set_raw_dev(self._h, ctypes.c_void_p(corner_ptr), rc, ctypes.c_void_p(surf_ptr), rs))
+
+    def scan_set_dev(self, c_ptr: int, nc: int, s_ptr: int, ns: int, o_ptr: int, no: int):
+        self._ck(lib().llb_scan_set_dev(self._h, ctypes.c_void_p(c_ptr), nc, ctypes.c_void_p(s_ptr), ns,
+                                        ctypes.c_void_p(o_ptr), no))
+
+    def s2m_optimize_dev(self, T_ptr: int):
+        self._ck(lib().llb_s2m_optimize_dev(self._h, ctypes.c_void_p(T_ptr)))
+
+    def s2m_time_iteration(self, T, reps: int = 20):
+        """-> (ms per launch of the fused K3+K4 kernel, queries per launch)"""
+        t = np.ascontiguousarray(T, np.float32)
+        ms = ctypes.c_float(0); nq = ctypes.c_int(0)
+        self._ck(lib().llb_s2m_time_iteration(self._h, _fp(t), reps, ctypes.byref(ms), ctypes.byref(nq)))
+        return float(ms.value), int(nq.value)
+
+    def s2m_pose_set(self, T):
+        t = np.ascontiguousarray(T, np.float32)
+        self._ck(lib().llb_s2m_pose_set(self._h, _fp(t)))
+
+    def s2m_pose_get(self) -> np.ndarray:
+        t = np.zeros(6, np.float32)
+        self._ck(lib().llb_s2m_pose_get(self._h, _fp(t)))
+        return t
+
+    def s2m_accumulate(self, it: int, rank: int, world: int) -> int:
+        p = ctypes.c_void_p()
+        self._ck(lib().llb_s2m_accumulate(self._h, it, rank, world, ctypes.byref(p)))
+        return p.value
+
+    def s2m_solve(self, it: int, want_converged: bool = False):
+        conv = ctypes.c_int(0)
+        self._ck(lib().llb_s2m_solve(self._h, it, ctypes.byref(conv) if want_converged else None))
+        return bool(conv.value)
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().llb_params_default(ctypes.byref(p))
+    return p

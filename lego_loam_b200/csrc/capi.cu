@@ -1,0 +1,778 @@
+// capi.cu — the C ABI of include/llb200.h: context, host<->device staging and the
+// orchestration of K1 (voxel), K2 (grid index), K3+K4 (scan-to-map iteration) and K5
+// (odometry).  There is no CPU fallback anywhere in this file: without a CUDA device
+// llb_create fails with LLB_ERR_NO_DEVICE.
+#include "../../include/llb200.h"
+#include "common.cuh"
+#include "voxel.cuh"
+#include "grid_index.cuh"
+#include "s2m.cuh"
+#include "odom.cuh"
+
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+using namespace llb;
+
+namespace {
+
+__global__ void unpack_points_kernel(const float *__restrict__ src32, int n, float4 *__restrict__ dst)
+{
+    // src: pcl::PointXYZI stride (8 floats): x y z w intensity c1 c2 c3
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src32) + 2 * i);
+        const float inten = __ldg(src32 + 8 * i + 4);
+        dst[i] = make_float4(a.x, a.y, a.z, inten);
+    }
+}
+
+struct Cloud {                    // device cloud with a device-resident length
+    DevBuf<float4> pts;
+    int n_host = 0;               // exact length when known on the host, else upper bound
+    bool exact = true;
+};
+
+}  // namespace
+
+struct llb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    llb_params prm{};
+    std::string err;
+    long long launches = 0;
+
+    // staging: the caller's 32 B-stride clouds are DMA'd as they are and compacted on the device
+    PinnedBuf<float> pin_in[3];
+    DevBuf<float> raw32[3];
+    cudaEvent_t pin_ev[3] = { nullptr, nullptr, nullptr };
+    bool pin_busy[3] = { false, false, false };
+    DevBuf<float4> tmp_in;
+    PinnedBuf<float4> pin_out;
+    PinnedBuf<int> pin_counts;
+    PinnedBuf<S2mState> pin_state;
+    PinnedBuf<OdomState> pin_ostate;
+
+    DevBuf<int> counts;           // device-resident lengths, see enum below
+    enum { C_CORNER_DS = 0, C_SURF_DS, C_OUTLIER_DS, C_SURFTOTAL_DS, C_MAP_CORNER_DS, C_MAP_SURF_DS, C_VOX_TMP, C_N };
+
+    VoxelFilter vox;
+    // scan side (MO:109-118)
+    Cloud cornerLast, surfLast, outlierLast;
+    DevBuf<float4> cornerLastDS, surfLastDS, outlierLastDS, surfTotalLastDS;
+    bool scan_set = false, scan_ds_done = false;
+    // map side (MO:123-126)
+    Cloud mapCornerRaw, mapSurfRaw;
+    DevBuf<float4> mapCornerDS, mapSurfDS;
+    const float4 *mapCornerDS_view = nullptr, *mapSurfDS_view = nullptr;   // own buffer or caller's device memory
+    int mapCornerDS_upper = 0, mapSurfDS_upper = 0;
+    bool map_counts_on_dev = false;
+    GridIndex gridCorner, gridSurf;
+    bool map_set = false;
+
+    S2mSolver s2m;
+    DevBuf<float4> dbg_coeff; DevBuf<int> dbg_valid; DevBuf<int> dbg_knn; DevBuf<float> dbg_d2;
+    int dbg_nc = 0, dbg_ns = 0;
+    bool dbg_ready = false;
+    DevBuf<float4> tmp_vox;
+
+    OdomSolver odom;
+};
+
+namespace {
+
+S2mParams s2m_params(const llb_params &p)
+{
+    S2mParams q;
+    q.knn_max_sqdist = p.knn_max_sqdist; q.min_corr = p.s2m_min_correspondences;
+    q.degeneracy_thresh = p.s2m_degeneracy_thresh; q.converge_deg = p.s2m_converge_deg;
+    q.converge_cm = p.s2m_converge_cm; q.corner_map_min = p.corner_map_min; q.surf_map_min = p.surf_map_min;
+    return q;
+}
+
+OdomParams odom_params(const llb_params &p)
+{
+    OdomParams q;
+    q.nearest_sqdist = p.odom_nearest_sqdist; q.max_iter = p.odom_max_iterations;
+    q.min_corr = p.odom_min_correspondences; q.degeneracy_thresh = p.odom_degeneracy_thresh;
+    q.converge_deg = p.odom_converge_deg; q.converge_cm = p.odom_converge_cm;
+    return q;
+}
+
+template <typename F>
+int guarded(llb_ctx *ctx, F &&f)
+{
+    if (!ctx) return LLB_ERR_INVALID;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return LLB_ERR_CUDA; }
+        return f();
+    } catch (const CudaError &e) {
+        ctx->err = e.what();
+        return LLB_ERR_CUDA;
+    } catch (const std::exception &e) {
+        ctx->err = e.what();
+        return LLB_ERR_INVALID;
+    }
+}
+
+// host (32 B stride) -> device float4.  slot selects the staging pair.
+void upload_cloud(llb_ctx *c, int slot, const llb_point *src, int n, DevBuf<float4> &dst)
+{
+    dst.ensure(std::max(n, 1));
+    if (n <= 0) return;
+    static_assert(sizeof(llb_point) == 32, "pcl::PointXYZI layout");
+    // the staging pair of this slot may still be the source of an earlier DMA
+    if (c->pin_busy[slot]) { LLB_CUDA(cudaEventSynchronize(c->pin_ev[slot])); c->pin_busy[slot] = false; }
+    c->pin_in[slot].ensure((size_t)n * 8);
+    c->raw32[slot].ensure((size_t)n * 8);
+    std::memcpy(c->pin_in[slot].p, src, (size_t)n * sizeof(llb_point));
+    LLB_CUDA(cudaMemcpyAsync(c->raw32[slot].p, c->pin_in[slot].p, (size_t)n * sizeof(llb_point),
+                             cudaMemcpyHostToDevice, c->stream));
+    LLB_CUDA(cudaEventRecord(c->pin_ev[slot], c->stream));
+    c->pin_busy[slot] = true;
+    unpack_points_kernel<<<std::min(div_up(n, 256), 148 * 8), 256, 0, c->stream>>>(c->raw32[slot].p, n, dst.p);
+    LLB_CUDA(cudaGetLastError());
+    c->launches++;
+}
+
+void set_cloud(llb_ctx *c, int slot, Cloud &cl, const llb_point *src, int n)
+{
+    upload_cloud(c, slot, src, n, cl.pts);
+    cl.n_host = n; cl.exact = true;
+}
+
+// device float4 -> host llb_point (blocking)
+void download_cloud(llb_ctx *c, const float4 *src, int n, llb_point *dst)
+{
+    if (n <= 0) return;
+    c->pin_out.ensure(n);
+    LLB_CUDA(cudaMemcpyAsync(c->pin_out.p, src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    LLB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) {
+        const float4 p = c->pin_out.p[i];
+        dst[i].x = p.x; dst[i].y = p.y; dst[i].z = p.z; dst[i].w = 1.0f;
+        dst[i].intensity = p.w; dst[i].c1 = dst[i].c2 = dst[i].c3 = 0.f;
+    }
+}
+
+int read_count(llb_ctx *c, int which)
+{
+    LLB_CUDA(cudaMemcpyAsync(c->pin_counts.p, c->counts.p, sizeof(int) * llb_ctx::C_N, cudaMemcpyDeviceToHost, c->stream));
+    LLB_CUDA(cudaStreamSynchronize(c->stream));
+    return c->pin_counts.p[which];
+}
+
+void build_indices(llb_ctx *c)
+{
+    const float radius = std::sqrt(c->prm.knn_max_sqdist);
+    const int *nc = c->map_counts_on_dev ? c->counts.p + llb_ctx::C_MAP_CORNER_DS : nullptr;
+    const int *ns = c->map_counts_on_dev ? c->counts.p + llb_ctx::C_MAP_SURF_DS : nullptr;
+    c->launches += c->gridCorner.build(c->mapCornerDS_view, nc, c->mapCornerDS_upper, radius, c->stream);
+    c->launches += c->gridSurf.build(c->mapSurfDS_view, ns, c->mapSurfDS_upper, radius, c->stream);
+    c->map_set = true;
+}
+
+void voxel_map_raw(llb_ctx *c, const float4 *corner, int rc, const float4 *surf, int rs)
+{
+    c->mapCornerDS.ensure(std::max(rc, 1)); c->mapSurfDS.ensure(std::max(rs, 1));
+    VoxelInput a; a.a = corner; a.na = rc;
+    VoxelInput b; b.a = surf; b.na = rs;
+    c->launches += c->vox.run(a, c->prm.corner_leaf, c->mapCornerDS.p, c->counts.p + llb_ctx::C_MAP_CORNER_DS, c->stream);
+    c->launches += c->vox.run(b, c->prm.surf_leaf, c->mapSurfDS.p, c->counts.p + llb_ctx::C_MAP_SURF_DS, c->stream);
+    c->mapCornerDS_view = c->mapCornerDS.p; c->mapSurfDS_view = c->mapSurfDS.p;
+    c->mapCornerDS_upper = rc; c->mapSurfDS_upper = rs;
+    c->map_counts_on_dev = true;
+}
+
+S2mQueries s2m_queries(llb_ctx *c)
+{
+    S2mQueries q;
+    q.corner = c->cornerLastDS.p; q.nc_dev = c->counts.p + llb_ctx::C_CORNER_DS; q.nc_upper = c->cornerLast.n_host;
+    q.surf = c->surfTotalLastDS.p; q.ns_dev = c->counts.p + llb_ctx::C_SURFTOTAL_DS;
+    q.ns_upper = c->surfLast.n_host + c->outlierLast.n_host;
+    return q;
+}
+
+void downsample_scan(llb_ctx *c)
+{
+    const int nc = c->cornerLast.n_host, ns = c->surfLast.n_host, no = c->outlierLast.n_host;
+    c->cornerLastDS.ensure(std::max(nc, 1)); c->surfLastDS.ensure(std::max(ns, 1));
+    c->outlierLastDS.ensure(std::max(no, 1)); c->surfTotalLastDS.ensure(std::max(ns + no, 1));
+    VoxelInput in[3];
+    in[0].a = c->cornerLast.pts.p; in[0].na = nc;
+    in[1].a = c->surfLast.pts.p; in[1].na = ns;
+    in[2].a = c->outlierLast.pts.p; in[2].na = no;
+    const float leaf[3] = { c->prm.corner_leaf, c->prm.surf_leaf, c->prm.outlier_leaf };
+    float4 *out[3] = { c->cornerLastDS.p, c->surfLastDS.p, c->outlierLastDS.p };
+    int *cnt[3] = { c->counts.p + llb_ctx::C_CORNER_DS, c->counts.p + llb_ctx::C_SURF_DS, c->counts.p + llb_ctx::C_OUTLIER_DS };
+    c->launches += c->vox.run_batch(in, leaf, out, cnt, 3, c->stream);                 // MO:1069-1082
+    VoxelInput tot;                                                                    // MO:1084-1090 (C12)
+    tot.a = c->surfLastDS.p; tot.na_dev = cnt[1]; tot.na = ns;
+    tot.b = c->outlierLastDS.p; tot.nb_dev = cnt[2]; tot.nb = no;
+    c->launches += c->vox.run(tot, c->prm.surf_leaf, c->surfTotalLastDS.p, c->counts.p + llb_ctx::C_SURFTOTAL_DS, c->stream);
+    c->scan_ds_done = true;
+}
+
+void fill_stats(llb_ctx *c, llb_stats *st, const S2mState &s, float ms)
+{
+    if (!st) return;
+    st->iterations = s.iters; st->converged = s.converged; st->n_correspondences = s.n_corr;
+    st->is_degenerate = s.is_degenerate; st->skipped = s.skipped; st->device_ms = ms;
+    st->n_corner_ds = c->pin_counts.p[llb_ctx::C_CORNER_DS]; st->n_surf_ds = c->pin_counts.p[llb_ctx::C_SURFTOTAL_DS];
+}
+
+}  // namespace
+
+extern "C" {
+
+int llb_abi_version(void) { return LLB_ABI_VERSION; }
+
+void llb_params_default(llb_params *p)
+{
+    if (!p) return;
+    p->corner_leaf = 0.2f; p->surf_leaf = 0.4f; p->outlier_leaf = 0.4f;
+    p->knn_max_sqdist = 1.0f;
+    p->s2m_max_iterations = 10; p->s2m_min_correspondences = 50; p->s2m_degeneracy_thresh = 100.f;
+    p->s2m_converge_deg = 0.05f; p->s2m_converge_cm = 0.05f;
+    p->corner_map_min = 10; p->surf_map_min = 100;
+    p->odom_nearest_sqdist = 25.f; p->odom_max_iterations = 25; p->odom_min_correspondences = 10;
+    p->odom_degeneracy_thresh = 10.f; p->odom_converge_deg = 0.1f; p->odom_converge_cm = 0.1f;
+    p->max_grid_cells = 1 << 23;
+}
+
+int llb_create(const llb_params *p, int device, llb_ctx **out)
+{
+    if (!out) return LLB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LLB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return LLB_ERR_NO_DEVICE;
+    llb_ctx *c = new llb_ctx();
+    c->device = device;
+    if (p) c->prm = *p; else llb_params_default(&c->prm);
+    int rc = guarded(c, [&]() {
+        LLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        LLB_CUDA(cudaEventCreate(&c->ev0)); LLB_CUDA(cudaEventCreate(&c->ev1));
+        for (int i = 0; i < 3; i++) LLB_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
+        c->counts.ensure(llb_ctx::C_N);
+        LLB_CUDA(cudaMemset(c->counts.p, 0, sizeof(int) * llb_ctx::C_N));
+        c->pin_counts.ensure(llb_ctx::C_N);
+        c->pin_state.ensure(1);
+        c->pin_ostate.ensure(1);
+        c->vox.init();
+        c->gridCorner.init(c->prm.max_grid_cells);
+        c->gridSurf.init(c->prm.max_grid_cells);
+        c->s2m.init(s2m_params(c->prm));
+        c->odom.init(odom_params(c->prm));
+        LLB_CUDA(cudaDeviceSynchronize());
+        return (int)LLB_OK;
+    });
+    if (rc != LLB_OK) { delete c; return rc; }
+    *out = c;
+    return LLB_OK;
+}
+
+int llb_destroy(llb_ctx *c)
+{
+    if (!c) return LLB_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 3; i++) { c->pin_in[i].release(); c->raw32[i].release(); if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]); }
+    c->tmp_in.release();
+    c->pin_out.release(); c->pin_counts.release(); c->pin_state.release(); c->pin_ostate.release();
+    c->counts.release(); c->vox.release();
+    c->cornerLast.pts.release(); c->surfLast.pts.release(); c->outlierLast.pts.release();
+    c->cornerLastDS.release(); c->surfLastDS.release(); c->outlierLastDS.release(); c->surfTotalLastDS.release();
+    c->mapCornerRaw.pts.release(); c->mapSurfRaw.pts.release(); c->mapCornerDS.release(); c->mapSurfDS.release();
+    c->gridCorner.release(); c->gridSurf.release(); c->s2m.release(); c->odom.release();
+    c->dbg_coeff.release(); c->dbg_valid.release(); c->dbg_knn.release(); c->dbg_d2.release(); c->tmp_vox.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LLB_OK;
+}
+
+const char *llb_last_error(const llb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+void *llb_stream(llb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+long long llb_launch_count(const llb_ctx *c) { return c ? c->launches : 0; }
+
+int llb_synchronize(llb_ctx *c)
+{
+    return guarded(c, [&]() { LLB_CUDA(cudaStreamSynchronize(c->stream)); return (int)LLB_OK; });
+}
+
+int llb_voxel_downsample(llb_ctx *c, const llb_point *in, int n, float leaf, llb_point *out, int cap, int *m)
+{
+    return guarded(c, [&]() {
+        if (n < 0 || (n > 0 && !in) || !m || !(leaf > 0.f)) return (int)LLB_ERR_INVALID;
+        if (n == 0) { *m = 0; return (int)LLB_OK; }
+        upload_cloud(c, 0, in, n, c->tmp_in);
+        c->tmp_vox.ensure(n);
+        VoxelInput vi; vi.a = c->tmp_in.p; vi.na = n;
+        c->launches += c->vox.run(vi, leaf, c->tmp_vox.p, c->counts.p + llb_ctx::C_VOX_TMP, c->stream);
+        int cnt = read_count(c, llb_ctx::C_VOX_TMP);
+        *m = cnt;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        if (out) download_cloud(c, c->tmp_vox.p, cnt, out);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_set_ds(llb_ctx *c, const llb_point *corner, int mc, const llb_point *surf, int ms)
+{
+    return guarded(c, [&]() {
+        if (mc < 0 || ms < 0 || (mc > 0 && !corner) || (ms > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        upload_cloud(c, 0, corner, mc, c->mapCornerDS);
+        upload_cloud(c, 1, surf, ms, c->mapSurfDS);
+        c->mapCornerDS_view = c->mapCornerDS.p; c->mapSurfDS_view = c->mapSurfDS.p;
+        c->mapCornerDS_upper = mc; c->mapSurfDS_upper = ms;
+        c->map_counts_on_dev = false;
+        build_indices(c);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_set_ds_dev(llb_ctx *c, const void *corner, int mc, const void *surf, int ms)
+{
+    return guarded(c, [&]() {
+        if (mc < 0 || ms < 0 || (mc > 0 && !corner) || (ms > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        c->mapCornerDS_view = (const float4 *)corner; c->mapSurfDS_view = (const float4 *)surf;
+        c->mapCornerDS_upper = mc; c->mapSurfDS_upper = ms;
+        c->map_counts_on_dev = false;
+        build_indices(c);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_set_raw(llb_ctx *c, const llb_point *corner, int rc, const llb_point *surf, int rs)
+{
+    return guarded(c, [&]() {
+        if (rc < 0 || rs < 0 || (rc > 0 && !corner) || (rs > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        set_cloud(c, 0, c->mapCornerRaw, corner, rc);
+        set_cloud(c, 1, c->mapSurfRaw, surf, rs);
+        voxel_map_raw(c, c->mapCornerRaw.pts.p, rc, c->mapSurfRaw.pts.p, rs);
+        build_indices(c);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_set_raw_dev(llb_ctx *c, const void *corner, int rc, const void *surf, int rs)
+{
+    return guarded(c, [&]() {
+        if (rc < 0 || rs < 0 || (rc > 0 && !corner) || (rs > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        voxel_map_raw(c, (const float4 *)corner, rc, (const float4 *)surf, rs);
+        build_indices(c);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_get_ds(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 1) return (int)LLB_ERR_INVALID;
+        if (!c->map_set) return (int)LLB_ERR_STATE;
+        int cnt = which == 0 ? c->mapCornerDS_upper : c->mapSurfDS_upper;
+        if (c->map_counts_on_dev) cnt = read_count(c, which == 0 ? llb_ctx::C_MAP_CORNER_DS : llb_ctx::C_MAP_SURF_DS);
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        download_cloud(c, which == 0 ? c->mapCornerDS_view : c->mapSurfDS_view, cnt, out);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_scan_set(llb_ctx *c, const llb_point *corner, int nc, const llb_point *surf, int ns,
+                 const llb_point *outlier, int no)
+{
+    return guarded(c, [&]() {
+        if (nc < 0 || ns < 0 || no < 0 || (nc > 0 && !corner) || (ns > 0 && !surf) || (no > 0 && !outlier))
+            return (int)LLB_ERR_INVALID;
+        set_cloud(c, 0, c->cornerLast, corner, nc);
+        set_cloud(c, 1, c->surfLast, surf, ns);
+        set_cloud(c, 2, c->outlierLast, outlier, no);
+        c->scan_set = true; c->scan_ds_done = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_scan_set_dev(llb_ctx *c, const void *corner, int nc, const void *surf, int ns, const void *outlier, int no)
+{
+    return guarded(c, [&]() {
+        if (nc < 0 || ns < 0 || no < 0) return (int)LLB_ERR_INVALID;
+        auto cp = [&](Cloud &cl, const void *src, int n) {
+            cl.pts.ensure(std::max(n, 1));
+            if (n > 0) LLB_CUDA(cudaMemcpyAsync(cl.pts.p, src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            cl.n_host = n; cl.exact = true;
+        };
+        cp(c->cornerLast, corner, nc); cp(c->surfLast, surf, ns); cp(c->outlierLast, outlier, no);
+        c->scan_set = true; c->scan_ds_done = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_downsample_current_scan(llb_ctx *c, int counts[4])
+{
+    return guarded(c, [&]() {
+        if (!c->scan_set) return (int)LLB_ERR_STATE;
+        downsample_scan(c);
+        if (counts) {
+            read_count(c, 0);
+            for (int i = 0; i < 4; i++) counts[i] = c->pin_counts.p[i];
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_scan_get_ds(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 3) return (int)LLB_ERR_INVALID;
+        if (!c->scan_ds_done) return (int)LLB_ERR_STATE;
+        int cnt = read_count(c, which);
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        const float4 *src = which == 0 ? c->cornerLastDS.p : which == 1 ? c->surfLastDS.p
+                          : which == 2 ? c->outlierLastDS.p : c->surfTotalLastDS.p;
+        download_cloud(c, src, cnt, out);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_iterate(llb_ctx *c, float T[6], int iter, int *converged, int *n_corr)
+{
+    return guarded(c, [&]() {
+        if (!T || iter < 0) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        const int nq = q.nc_upper + q.ns_upper;
+        c->dbg_coeff.ensure(std::max(nq, 1)); c->dbg_valid.ensure(std::max(nq, 1));
+        c->dbg_knn.ensure((size_t)std::max(nq, 1) * 5); c->dbg_d2.ensure((size_t)std::max(nq, 1) * 5);
+        S2mDebug dbg{ c->dbg_coeff.p, c->dbg_valid.p, c->dbg_knn.p, c->dbg_d2.p };
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        c->launches += c->s2m.iterate(iter, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        read_count(c, 0);                                           // also synchronises
+        const S2mState &s = *c->pin_state.p;
+        c->dbg_nc = c->pin_counts.p[llb_ctx::C_CORNER_DS]; c->dbg_ns = c->pin_counts.p[llb_ctx::C_SURFTOTAL_DS];
+        c->dbg_ready = !s.skipped;
+        for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        if (converged) *converged = s.converged;
+        if (n_corr) *n_corr = s.n_corr;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_optimize(llb_ctx *c, float T[6], llb_stats *stats)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        for (int it = 0; it < c->prm.s2m_max_iterations; it++)
+            c->launches += c->s2m.iterate(it, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        read_count(c, 0);
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const S2mState &s = *c->pin_state.p;
+        if (!s.skipped) for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        fill_stats(c, stats, s, ms);
+        c->dbg_ready = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_optimize_dev(llb_ctx *c, float *T_dev)
+{
+    return guarded(c, [&]() {
+        if (!T_dev) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        c->launches += c->s2m.prepare(nullptr, T_dev, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        for (int it = 0; it < c->prm.s2m_max_iterations; it++)
+            c->launches += c->s2m.iterate(it, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        // S2mState starts with T[6]
+        LLB_CUDA(cudaMemcpyAsync(T_dev, c->s2m.state_dev(), 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        c->dbg_ready = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_pose_set(llb_ctx *c, const float T[6])
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->map_set) return (int)LLB_ERR_STATE;
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_pose_get(llb_ctx *c, float T[6])
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 6; i++) T[i] = c->pin_state.p->T[i];
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_accumulate(llb_ctx *c, int iter, int rank, int world, double **acc)
+{
+    return guarded(c, [&]() {
+        if (!acc || world < 1 || rank < 0 || rank >= world) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        c->launches += c->s2m.iterate(iter, q, c->gridCorner.view(), c->gridSurf.view(), dbg, rank, world, false, c->stream);
+        *acc = c->s2m.acc_dev();
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_time_iteration(llb_ctx *c, const float T[6], int reps, float *ms_per_launch, int *n_queries)
+{
+    return guarded(c, [&]() {
+        if (!T || reps < 1 || !ms_per_launch) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        c->launches += c->s2m.iterate(1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int r = 0; r < reps; r++)
+            c->launches += c->s2m.iterate(1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        read_count(c, 0);
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *ms_per_launch = ms / reps;
+        if (n_queries) *n_queries = c->pin_counts.p[llb_ctx::C_CORNER_DS] + c->pin_counts.p[llb_ctx::C_SURFTOTAL_DS];
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_solve(llb_ctx *c, int iter, int *converged)
+{
+    return guarded(c, [&]() {
+        c->launches += c->s2m.solve(iter, c->stream);
+        if (converged) {
+            LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+            LLB_CUDA(cudaStreamSynchronize(c->stream));
+            *converged = c->pin_state.p->converged;
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_get_correspondences(llb_ctx *c, llb_point *ori, llb_point *coeff, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n) return (int)LLB_ERR_INVALID;
+        if (!c->dbg_ready) { *n = 0; return (int)LLB_ERR_STATE; }
+        const int nq = c->dbg_nc + c->dbg_ns;
+        std::vector<float4> co(std::max(nq, 1)), qc(std::max(c->dbg_nc, 1)), qs(std::max(c->dbg_ns, 1));
+        std::vector<int> va(std::max(nq, 1));
+        // rows live at [0,nc) for corner queries and [nc, nc+ns) for surf queries
+        if (nq > 0) {
+            LLB_CUDA(cudaMemcpyAsync(co.data(), c->dbg_coeff.p, sizeof(float4) * nq, cudaMemcpyDeviceToHost, c->stream));
+            LLB_CUDA(cudaMemcpyAsync(va.data(), c->dbg_valid.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (c->dbg_nc > 0) LLB_CUDA(cudaMemcpyAsync(qc.data(), c->cornerLastDS.p, sizeof(float4) * c->dbg_nc, cudaMemcpyDeviceToHost, c->stream));
+        if (c->dbg_ns > 0) LLB_CUDA(cudaMemcpyAsync(qs.data(), c->surfTotalLastDS.p, sizeof(float4) * c->dbg_ns, cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        int cnt = 0;
+        for (int i = 0; i < nq; i++) cnt += va[i] != 0;
+        *n = cnt;
+        if (!ori || !coeff) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        int k = 0;
+        for (int i = 0; i < nq; i++) {
+            if (!va[i]) continue;
+            const float4 p = i < c->dbg_nc ? qc[i] : qs[i - c->dbg_nc];
+            ori[k] = llb_point{ p.x, p.y, p.z, 1.0f, p.w, 0.f, 0.f, 0.f };
+            coeff[k] = llb_point{ co[i].x, co[i].y, co[i].z, 1.0f, co[i].w, 0.f, 0.f, 0.f };
+            k++;
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_get_knn(llb_ctx *c, int which, int *idx5, float *d2, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 1) return (int)LLB_ERR_INVALID;
+        if (!c->dbg_ready) { *n = 0; return (int)LLB_ERR_STATE; }
+        const int cnt = which == 0 ? c->dbg_nc : c->dbg_ns;
+        const int off = which == 0 ? 0 : c->dbg_nc;
+        *n = cnt;
+        if (!idx5 || !d2) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        if (cnt > 0) {
+            LLB_CUDA(cudaMemcpyAsync(idx5, c->dbg_knn.p + (size_t)off * 5, sizeof(int) * 5 * cnt, cudaMemcpyDeviceToHost, c->stream));
+            LLB_CUDA(cudaMemcpyAsync(d2, c->dbg_d2.p + (size_t)off * 5, sizeof(float) * 5 * cnt, cudaMemcpyDeviceToHost, c->stream));
+            LLB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_get_normal_equations(llb_ctx *c, float AtA[36], float AtB[6], float X[6])
+{
+    return guarded(c, [&]() {
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        if (AtA) std::memcpy(AtA, c->pin_state.p->AtA, sizeof(float) * 36);
+        if (AtB) std::memcpy(AtB, c->pin_state.p->AtB, sizeof(float) * 6);
+        if (X) std::memcpy(X, c->pin_state.p->X, sizeof(float) * 6);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_get_degeneracy(llb_ctx *c, int *deg, float matP[36])
+{
+    return guarded(c, [&]() {
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        if (deg) *deg = c->pin_state.p->is_degenerate;
+        if (matP) std::memcpy(matP, c->pin_state.p->matP, sizeof(float) * 36);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_set_degeneracy(llb_ctx *c, int deg, const float matP[36])
+{
+    return guarded(c, [&]() {
+        if (!matP) return (int)LLB_ERR_INVALID;
+        S2mState *d = c->s2m.state_dev();
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        LLB_CUDA(cudaMemcpy(&d->is_degenerate, &deg, sizeof(int), cudaMemcpyHostToDevice));
+        LLB_CUDA(cudaMemcpy(d->matP, matP, sizeof(float) * 36, cudaMemcpyHostToDevice));
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ featureAssociation
+
+int llb_odom_set_last(llb_ctx *c, const llb_point *corner, int ncl, const llb_point *surf, int nsl)
+{
+    return guarded(c, [&]() {
+        if (ncl < 0 || nsl < 0 || (ncl > 0 && !corner) || (nsl > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        upload_cloud(c, 0, corner, ncl, c->odom.cornerLast());
+        upload_cloud(c, 1, surf, nsl, c->odom.surfLast());
+        c->launches += c->odom.set_last(ncl, nsl, c->stream);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_odom_set_features(llb_ctx *c, const llb_point *sharp, int nsharp, const llb_point *flat, int nflat)
+{
+    return guarded(c, [&]() {
+        if (nsharp < 0 || nflat < 0 || (nsharp > 0 && !sharp) || (nflat > 0 && !flat)) return (int)LLB_ERR_INVALID;
+        upload_cloud(c, 0, sharp, nsharp, c->odom.sharp());
+        upload_cloud(c, 1, flat, nflat, c->odom.flat());
+        c->odom.set_features(nsharp, nflat);
+        return (int)LLB_OK;
+    });
+}
+
+static void fill_odom_stats(llb_stats *st, const OdomState &s, int which, float ms)
+{
+    if (!st) return;
+    std::memset(st, 0, sizeof(*st));
+    st->iterations = s.iters[which]; st->converged = s.converged[which]; st->n_correspondences = s.n_corr;
+    st->is_degenerate = s.is_degenerate; st->skipped = s.skipped; st->device_ms = ms;
+}
+
+int llb_odom_optimize(llb_ctx *c, float T[6], llb_stats *st_surf, llb_stats *st_corner)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->odom.ready()) return (int)LLB_ERR_STATE;
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->odom.optimize(T, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_ostate.p, c->odom.state_dev(), sizeof(OdomState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const OdomState &s = *c->pin_ostate.p;
+        for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        fill_odom_stats(st_surf, s, 0, ms); fill_odom_stats(st_corner, s, 1, ms);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_odom_iterate(llb_ctx *c, int which, float T[6], int iter, int *more, int *n_corr)
+{
+    return guarded(c, [&]() {
+        if (!T || which < 0 || which > 1 || iter < 0) return (int)LLB_ERR_INVALID;
+        if (!c->odom.ready()) return (int)LLB_ERR_STATE;
+        c->launches += c->odom.iterate(which, T, iter, c->stream);
+        LLB_CUDA(cudaMemcpyAsync(c->pin_ostate.p, c->odom.state_dev(), sizeof(OdomState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        const OdomState &s = *c->pin_ostate.p;
+        for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        if (more) *more = s.more;
+        if (n_corr) *n_corr = s.n_corr;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_odom_get_correspondences(llb_ctx *c, llb_point *ori, llb_point *coeff, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n) return (int)LLB_ERR_INVALID;
+        std::vector<float4> o, k;
+        c->odom.download_correspondences(o, k, c->stream);
+        *n = (int)o.size();
+        if (!ori || !coeff) return (int)LLB_OK;
+        if ((int)o.size() > cap) return (int)LLB_ERR_CAPACITY;
+        for (size_t i = 0; i < o.size(); i++) {
+            ori[i] = llb_point{ o[i].x, o[i].y, o[i].z, 1.0f, o[i].w, 0.f, 0.f, 0.f };
+            coeff[i] = llb_point{ k[i].x, k[i].y, k[i].z, 1.0f, k[i].w, 0.f, 0.f, 0.f };
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_odom_get_search_ind(llb_ctx *c, int which, float *i1, float *i2, float *i3, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 1) return (int)LLB_ERR_INVALID;
+        std::vector<float> a, b, d;
+        c->odom.download_search_ind(which, a, b, d, c->stream);
+        *n = (int)a.size();
+        if (!i1 || !i2) return (int)LLB_OK;
+        if ((int)a.size() > cap) return (int)LLB_ERR_CAPACITY;
+        std::copy(a.begin(), a.end(), i1); std::copy(b.begin(), b.end(), i2);
+        if (i3 && which == 1) std::copy(d.begin(), d.end(), i3);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_odom_get_degeneracy(llb_ctx *c, int *deg, float matP[9])
+{
+    return guarded(c, [&]() {
+        LLB_CUDA(cudaMemcpyAsync(c->pin_ostate.p, c->odom.state_dev(), sizeof(OdomState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        if (deg) *deg = c->pin_ostate.p->is_degenerate;
+        if (matP) std::memcpy(matP, c->pin_ostate.p->matP, sizeof(float) * 9);
+        return (int)LLB_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// grid_index.cuh — K2: device-built uniform-grid spatial index that replaces
+// pcl::KdTreeFLANN::setInputCloud (MO:1333-1334) for the radius-bounded 5-NN queries
+// of cornerOptimization / surfOptimization (MO:1099-1101, MO:1181-1183).
+//
+// The reference only uses a 5-NN result when the 5th squared distance is < 1.0, so an
+// exact search inside the ball of radius 1 m is equivalent to the exact kd-tree search.
+// Cells are slightly larger than that radius (x1.001) so the 3x3x3 neighbourhood of the
+// query's cell always contains the whole ball.  Cell ids are x-fastest, which makes the
+// three x-neighbours of a (y,z) row ONE contiguous run in the re-ordered point array:
+// a query reads 9 runs, not 27 cells.  Layout in HBM: `sorted` float4 {x,y,z,bits(original
+// index)} in cell order (coalesced 16 B loads), `cell_begin` int[ncell+1] (exclusive scan
+// of the per-cell counts).
+#pragma once
+#include "common.cuh"
+
+namespace llb {
+
+struct GridDesc {            // device-resident
+    int mn[3], mx[3];        // ordered-int encoded bounds (atomics), reset after use
+    float org[3];
+    float inv_cell;
+    float cell;
+    int dim[3];
+    int ncell;
+    int n;                   // points indexed
+};
+
+struct MapIndexView {        // what the query kernels need (all device pointers)
+    const float4 *sorted;
+    const int *cell_begin;
+    const GridDesc *desc;
+};
+
+class GridIndex {
+public:
+    void init(int max_cells);
+    void release();
+    // points: n_upper is a host upper bound, n_dev (optional) the device-resident length
+    int build(const float4 *pts, const int *n_dev, int n_upper, float radius, cudaStream_t s);
+    MapIndexView view() const { return MapIndexView{ sorted_.p, cell_begin_.p, desc_.p }; }
+    const GridDesc *desc_dev() const { return desc_.p; }
+
+private:
+    int max_cells_ = 1 << 23;
+    DevBuf<GridDesc> desc_;
+    DevBuf<float4> sorted_;
+    DevBuf<int> cell_begin_;   // counts, then scanned in place
+    DevBuf<int> cell_of_;      // per point cell id
+    DevBuf<int> rank_;         // per point rank inside its cell
+    DevBuf<int> blk_;          // scan block sums
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int grid_coord(float p, float org, float inv_cell)
+{
+    return (int)floorf((p - org) * inv_cell);
+}
+#endif
+
+}  // namespace llb

@@ -1,0 +1,68 @@
+// s2m.cuh — K3 + K4: the scan-to-map iteration of mapOptimization on the device.
+//   cornerOptimization MO:1093-1174, surfOptimization MO:1176-1227, LMOptimization
+//   MO:1229-1327, loop scan2MapOptimization MO:1329-1350.
+#pragma once
+#include "common.cuh"
+#include "grid_index.cuh"
+
+namespace llb {
+
+constexpr int S2M_ACC = 28;          // 21 upper-tri AtA + 6 AtB + row count
+
+struct S2mParams {
+    float knn_max_sqdist;            // 1.0
+    int   min_corr;                  // 50
+    float degeneracy_thresh;         // 100
+    float converge_deg, converge_cm; // 0.05, 0.05
+    int   corner_map_min, surf_map_min; // 10, 100
+};
+
+struct S2mState {                    // device-resident, persists across registrations
+    float T[6];                      // transformTobeMapped
+    float cs[6];                     // cRoll sRoll cPitch sPitch cYaw sYaw (MO:498-506)
+    int   converged;
+    int   iters;
+    int   n_corr;
+    int   is_degenerate;             // MO:202 (persists, C6)
+    int   skipped;                   // guard MO:1331 failed
+    float matP[36];                  // MO:203
+    float AtA[36], AtB[6], X[6];     // last LM step (diagnostics)
+    unsigned ticket;                 // last-block election
+};
+
+struct S2mDebug {                    // optional per-query outputs (nullptr = off)
+    float4 *coeff;                   // [nq] coefficient row (valid or not)
+    int *valid;                      // [nq] 1 when the row was accepted (s > 0.1)
+    int *knn_idx;                    // [nq*5] original map indices, -1 if fewer than 5 in range
+    float *knn_d2;                   // [nq*5]
+};
+
+struct S2mQueries {
+    const float4 *corner; const int *nc_dev; int nc_upper;
+    const float4 *surf;   const int *ns_dev; int ns_upper;
+};
+
+class S2mSolver {
+public:
+    void init(const S2mParams &p);
+    void release();
+    S2mState *state_dev() { return state_.p; }
+    double *acc_dev() { return acc_.p; }
+    // upload T, compute its sin/cos on the device, evaluate the map-size guard, reset flags
+    int prepare(const float *T_host, const float *T_dev, const GridDesc *corner_desc, const GridDesc *surf_desc,
+                cudaStream_t s);
+    // one fused iteration.  rank/world shard the queries (world = 1: everything);
+    // do_solve = false stops after the 28 sums are in acc_dev() (for an external all-reduce)
+    int iterate(int iter, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
+                const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s);
+    int solve(int iter, cudaStream_t s);
+
+private:
+    S2mParams prm_{};
+    DevBuf<S2mState> state_;
+    DevBuf<double> partials_;
+    DevBuf<double> acc_;
+    int max_blocks_ = 0;
+};
+
+}  // namespace llb

@@ -1,0 +1,88 @@
+/*
+ * llo_voxel.c — ORACLE (test infrastructure): restatement of
+ * pcl::VoxelGrid<pcl::PointXYZI>::applyFilter with setLeafSize(l,l,l) and every
+ * other setting at its default, as the reference uses it:
+ *   MO:249-251 (leaf 0.2 corner, 0.4 surf / outlier), MO:1058-1063 (local map),
+ *   MO:1070-1089 (current scan, 4 filters), FA:779-780.
+ * PCL is an un-vendored, un-pinned dependency (find_package(PCL),
+ * /root/reference/LeGO-LOAM/CMakeLists.txt:24) and is not present offline, so
+ * this follows the published PCL 1.7/1.8 algorithm:
+ *   inverse_leaf = 1.0f/leaf; getMinMax3D; int64 overflow check -> pass-through;
+ *   min_b = (int)floor(min*inv); ijk = (int)(floor(x*inv) - (float)min_b);
+ *   idx = ijk . (1, div_x, div_x*div_y); sort by idx; one centroid per idx in
+ *   ascending idx order; xyz AND intensity averaged with float sums and a true
+ *   division by (float)count.
+ * Definition chosen where PCL leaves it open: PCL's std::sort is unstable, so
+ * the summation order inside a voxel is implementation-defined there; here it
+ * is ascending input index (stable).  "parity unpinned" for this primitive.
+ */
+#include "llo.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { int32_t idx; int32_t pt; } vox_pair;
+
+static int vox_cmp(const void *a, const void *b)
+{
+    const vox_pair *p = (const vox_pair *)a, *q = (const vox_pair *)b;
+    if (p->idx != q->idx) return p->idx < q->idx ? -1 : 1;
+    return p->pt < q->pt ? -1 : (p->pt > q->pt);   /* stable by input index */
+}
+
+int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *overflow)
+{
+    if (overflow) *overflow = 0;
+    if (n <= 0) return 0;
+
+    const float inv = 1.0f / leaf;
+    float mn[3] = { in[0].x, in[0].y, in[0].z }, mx[3] = { in[0].x, in[0].y, in[0].z };
+    for (int i = 1; i < n; i++) {
+        const float p[3] = { in[i].x, in[i].y, in[i].z };
+        for (int a = 0; a < 3; a++) {
+            if (p[a] < mn[a]) mn[a] = p[a];
+            if (p[a] > mx[a]) mx[a] = p[a];
+        }
+    }
+    int64_t d[3];
+    for (int a = 0; a < 3; a++) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {
+        memcpy(out, in, sizeof(llo_point) * (size_t)n);
+        if (overflow) *overflow = 1;
+        return n;
+    }
+    int min_b[3], max_b[3], div_b[3], mul[3];
+    for (int a = 0; a < 3; a++) {
+        min_b[a] = (int)floorf(mn[a] * inv);
+        max_b[a] = (int)floorf(mx[a] * inv);
+        div_b[a] = max_b[a] - min_b[a] + 1;
+    }
+    mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
+
+    vox_pair *v = (vox_pair *)malloc(sizeof(vox_pair) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        int ijk0 = (int)(floorf(in[i].x * inv) - (float)min_b[0]);
+        int ijk1 = (int)(floorf(in[i].y * inv) - (float)min_b[1]);
+        int ijk2 = (int)(floorf(in[i].z * inv) - (float)min_b[2]);
+        v[i].idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
+        v[i].pt = i;
+    }
+    qsort(v, (size_t)n, sizeof(vox_pair), vox_cmp);
+
+    int m = 0, i = 0;
+    while (i < n) {
+        int j = i;
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        while (j < n && v[j].idx == v[i].idx) {
+            const llo_point *p = &in[v[j].pt];
+            sx += p->x; sy += p->y; sz += p->z; si += p->intensity;
+            j++;
+        }
+        float cnt = (float)(j - i);
+        out[m].x = sx / cnt; out[m].y = sy / cnt; out[m].z = sz / cnt; out[m].intensity = si / cnt;
+        m++;
+        i = j;
+    }
+    free(v);
+    return m;
+}
