@@ -201,7 +201,7 @@ def make_mapping_scan(world: World, sensor: Sensor, pose, seed: int, noise: floa
     r, kind, prim, edge = raycast(world, pose[3:6], d @ R.T, sensor.max_range)
     ok = np.isfinite(r) & (rng.random(r.shape[0]) > dropout)
     r = r + rng.normal(0, noise, r.shape[0])
-    pts = d * r[:, None]
+    pts = d * np.where(np.isfinite(r), r, 0.0)[:, None]
     is_corner = ok & ((kind == 3) | ((kind == 2) & (edge < 0.12)))
     # cap corners at 20 per sector per ring
     sector = (col * 6) // sensor.horizon
@@ -342,7 +342,7 @@ def make_odometry_pair(world: World, sensor: Sensor, pose_start, cur_true, seed:
     r0, k0, _, e0 = raycast(world, tw, d @ Rw.T, sensor.max_range)
     ok0 = np.isfinite(r0)
     r0 = r0 + rng.normal(0, noise, r0.shape[0])
-    p0 = d * r0[:, None]
+    p0 = d * np.where(np.isfinite(r0), r0, 0.0)[:, None]
     c0, s0 = label(k0, e0, ok0)
     c0 = cap(c0, 20)
     s0 = s0 & ((col % 3) == 0)
@@ -363,7 +363,7 @@ def make_odometry_pair(world: World, sensor: Sensor, pose_start, cur_true, seed:
     r1, k1, _, e1 = raycast(world, org, dw, sensor.max_range)
     ok1 = np.isfinite(r1)
     r1 = r1 + rng.normal(0, noise, r1.shape[0])
-    p1 = d * r1[:, None]
+    p1 = d * np.where(np.isfinite(r1), r1, 0.0)[:, None]
     c1, s1 = label(k1, e1, ok1)
     sharp = cap(c1, 2)
     flat = cap(s1 & (k1 == 1) & (ring <= sensor.ground_scan_ind), 4)

@@ -1,0 +1,179 @@
+"""ORACLE tier B (test infrastructure): ctypes view of oracle/_ref/libref_{mo,fa}.so, i.e. the
+UNMODIFIED reference sources (mapOptmization.cpp / featureAssociation.cpp) compiled against shim
+headers (oracle/ref_harness/shim).  The classes mirror oracle.MapOptimization /
+oracle.FeatureAssociation so the same tests drive the restatement and the reference itself.
+The libraries can only be (re)built where /root/reference exists; on the GPU box the prebuilt
+files travel with the snapshot.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_OUT = os.path.join(os.path.dirname(_HERE), "_ref")
+_MO = os.path.join(_OUT, "libref_mo.so")
+_FA = os.path.join(_OUT, "libref_fa.so")
+_libs = {}
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+def build() -> bool:
+    if os.path.isdir("/root/reference/LeGO-LOAM/src"):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return available()
+
+
+def available() -> bool:
+    return os.path.exists(_MO) and os.path.exists(_FA)
+
+
+def _lib(path, create):
+    if path not in _libs:
+        L = ctypes.CDLL(path)
+        getattr(L, create).restype = ctypes.c_void_p
+        _libs[path] = L
+    return _libs[path]
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a.reshape(-1, 4)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+class MapOptimization:
+    """class mapOptimization of the reference (MO:49), driven through its own member functions."""
+
+    def __init__(self):
+        self.L = _lib(_MO, "ref_mo_create")
+        self._h = ctypes.c_void_p(self.L.ref_mo_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_mo_destroy(self._h); self._h = None
+
+    def set_map_ds(self, c, s):
+        c = _pts(c); s = _pts(s)
+        self.L.ref_mo_set_map_ds(self._h, _fp(c), c.shape[0], _fp(s), s.shape[0])
+
+    def set_map_raw(self, c, s):
+        c = _pts(c); s = _pts(s)
+        self.L.ref_mo_set_map_raw(self._h, _fp(c), c.shape[0], _fp(s), s.shape[0])
+
+    def set_scan(self, c, s, o):
+        c = _pts(c); s = _pts(s); o = _pts(o)
+        self.L.ref_mo_set_scan(self._h, _fp(c), c.shape[0], _fp(s), s.shape[0], _fp(o), o.shape[0])
+
+    @property
+    def transformTobeMapped(self):
+        t = np.zeros(6, np.float32); self.L.ref_mo_get_pose(self._h, _fp(t)); return t
+
+    @transformTobeMapped.setter
+    def transformTobeMapped(self, v):
+        t = np.ascontiguousarray(v, np.float32); self.L.ref_mo_set_pose(self._h, _fp(t))
+
+    def set_transform_sum(self, v):
+        t = np.ascontiguousarray(v, np.float32); self.L.ref_mo_set_transform_sum(self._h, _fp(t))
+
+    def bef_aft(self):
+        b = np.zeros(6, np.float32); a = np.zeros(6, np.float32)
+        self.L.ref_mo_get_bef_aft(self._h, _fp(b), _fp(a)); return b, a
+
+    def degenerate(self):
+        d = ctypes.c_int(0); P = np.zeros((6, 6), np.float32)
+        self.L.ref_mo_get_degenerate(self._h, ctypes.byref(d), _fp(P)); return bool(d.value), P
+
+    def downsampleCurrentScan(self): self.L.ref_mo_downsampleCurrentScan(self._h)
+    def build_kdtrees(self): self.L.ref_mo_build_kdtrees(self._h)
+    def clear_correspondences(self): self.L.ref_mo_clear_correspondences(self._h)
+    def cornerOptimization(self, it): self.L.ref_mo_cornerOptimization(self._h, it)
+    def surfOptimization(self, it): self.L.ref_mo_surfOptimization(self._h, it)
+    def LMOptimization(self, it) -> bool: return bool(self.L.ref_mo_LMOptimization(self._h, it))
+    def scan2MapOptimization(self): self.L.ref_mo_scan2MapOptimization(self._h)
+
+    def _cloud(self, fn, which):
+        n = fn(self._h, which, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        fn(self._h, which, _fp(out), n)
+        return out[:n].copy()
+
+    def scan_ds(self, which): return self._cloud(self.L.ref_mo_get_scan_ds, which)
+    def map_ds(self, which): return self._cloud(self.L.ref_mo_get_map_ds, which)
+    def map_raw(self, which): return self._cloud(self.L.ref_mo_get_map_raw, which)
+
+    def correspondences(self):
+        n = self.L.ref_mo_get_correspondences(self._h, None, None, 0)
+        ori = np.zeros((max(n, 1), 4), np.float32); co = np.zeros((max(n, 1), 4), np.float32)
+        self.L.ref_mo_get_correspondences(self._h, _fp(ori), _fp(co), n)
+        return ori[:n].copy(), co[:n].copy()
+
+    # the rest of run() MO:1503-1519 (sequence replays)
+    def set_odometry(self, transform_sum, stamp: float):
+        t = np.ascontiguousarray(transform_sum, np.float32)
+        self.L.ref_mo_set_odometry(self._h, _fp(t), ctypes.c_double(stamp))
+
+    def transformAssociateToMap(self): self.L.ref_mo_transformAssociateToMap(self._h)
+    def extractSurroundingKeyFrames(self): self.L.ref_mo_extractSurroundingKeyFrames(self._h)
+    def saveKeyFramesAndFactor(self): self.L.ref_mo_saveKeyFramesAndFactor(self._h)
+    def correctPoses(self): self.L.ref_mo_correctPoses(self._h)
+    def clearCloud(self): self.L.ref_mo_clearCloud(self._h)
+    def num_keyframes(self) -> int: return self.L.ref_mo_num_keyframes(self._h)
+
+
+class FeatureAssociation:
+    """class FeatureAssociation of the reference (FA:37)."""
+
+    def __init__(self):
+        self.L = _lib(_FA, "ref_fa_create")
+        self._h = ctypes.c_void_p(self.L.ref_fa_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_fa_destroy(self._h); self._h = None
+
+    def set_last(self, c, s, force=False):
+        c = _pts(c); s = _pts(s)
+        self.L.ref_fa_set_last(self._h, _fp(c), c.shape[0], _fp(s), s.shape[0], int(force))
+
+    def set_features(self, sharp, flat):
+        a = _pts(sharp); b = _pts(flat)
+        self.L.ref_fa_set_features(self._h, _fp(a), a.shape[0], _fp(b), b.shape[0])
+
+    @property
+    def transformCur(self):
+        t = np.zeros(6, np.float32); self.L.ref_fa_get_transform(self._h, _fp(t)); return t
+
+    @transformCur.setter
+    def transformCur(self, v):
+        t = np.ascontiguousarray(v, np.float32); self.L.ref_fa_set_transform(self._h, _fp(t))
+
+    def degenerate(self):
+        d = ctypes.c_int(0); P = np.zeros((3, 3), np.float32)
+        self.L.ref_fa_get_degenerate(self._h, ctypes.byref(d), _fp(P)); return bool(d.value), P
+
+    def clear_correspondences(self): self.L.ref_fa_clear_correspondences(self._h)
+    def findCorrespondingCornerFeatures(self, it): self.L.ref_fa_findCorrespondingCornerFeatures(self._h, it)
+    def findCorrespondingSurfFeatures(self, it): self.L.ref_fa_findCorrespondingSurfFeatures(self._h, it)
+    def calculateTransformationSurf(self, it) -> bool: return bool(self.L.ref_fa_calculateTransformationSurf(self._h, it))
+    def calculateTransformationCorner(self, it) -> bool: return bool(self.L.ref_fa_calculateTransformationCorner(self._h, it))
+    def updateTransformation(self): self.L.ref_fa_updateTransformation(self._h)
+
+    def correspondences(self):
+        n = self.L.ref_fa_get_correspondences(self._h, None, None, 0)
+        ori = np.zeros((max(n, 1), 4), np.float32); co = np.zeros((max(n, 1), 4), np.float32)
+        self.L.ref_fa_get_correspondences(self._h, _fp(ori), _fp(co), n)
+        return ori[:n].copy(), co[:n].copy()
+
+    def search_ind(self, which):
+        n = self.L.ref_fa_get_search_ind(self._h, which, None, None, None, 0)
+        a = np.zeros(max(n, 1), np.float32); b = a.copy(); c = a.copy()
+        self.L.ref_fa_get_search_ind(self._h, which, _fp(a), _fp(b), _fp(c), n)
+        return a[:n].copy(), b[:n].copy(), c[:n].copy()

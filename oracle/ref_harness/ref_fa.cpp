@@ -1,0 +1,86 @@
+// ref_fa.cpp — ORACLE tier B (test infrastructure): compiles the UNMODIFIED reference
+// /root/reference/LeGO-LOAM/src/featureAssociation.cpp against shim/llref_shim.hpp (see ref_mo.cpp).
+#include "shim/llref_shim.hpp"
+#define private public
+#define main ref_fa_node_main
+#include "featureAssociation.cpp"
+#undef main
+#undef private
+
+namespace {
+void fill(pcl::PointCloud<PointType>::Ptr &c, const llo_point *p, int n)
+{
+    c->clear();
+    c->points.resize(n);
+    for (int i = 0; i < n; i++) {
+        PointType q;
+        q.x = p[i].x; q.y = p[i].y; q.z = p[i].z; q.intensity = p[i].intensity;
+        c->points[i] = q;
+    }
+    c->width = n; c->height = 1;
+}
+int dump(const pcl::PointCloud<PointType>::Ptr &c, llo_point *out, int cap)
+{
+    int n = (int)c->points.size();
+    for (int i = 0; i < n && i < cap; i++) { out[i].x = c->points[i].x; out[i].y = c->points[i].y; out[i].z = c->points[i].z; out[i].intensity = c->points[i].intensity; }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+void *ref_fa_create() { return new FeatureAssociation(); }
+void ref_fa_destroy(void *h) { delete (FeatureAssociation *)h; }
+// laserCloudCornerLast / SurfLast + the statements of FA:1615-1619 (force) or FA:1782-1788
+void ref_fa_set_last(void *h, const llo_point *c, int nc, const llo_point *s, int ns, int force)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    fill(f->laserCloudCornerLast, c, nc); fill(f->laserCloudSurfLast, s, ns);
+    f->laserCloudCornerLastNum = nc; f->laserCloudSurfLastNum = ns;
+    if (force || (nc > 10 && ns > 100)) {
+        f->kdtreeCornerLast->setInputCloud(f->laserCloudCornerLast);
+        f->kdtreeSurfLast->setInputCloud(f->laserCloudSurfLast);
+    }
+}
+void ref_fa_set_features(void *h, const llo_point *sharp, int nsharp, const llo_point *flat, int nflat)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    fill(f->cornerPointsSharp, sharp, nsharp); fill(f->surfPointsFlat, flat, nflat);
+}
+void ref_fa_set_transform(void *h, const float *t) { memcpy(((FeatureAssociation *)h)->transformCur, t, 24); }
+void ref_fa_get_transform(void *h, float *t) { memcpy(t, ((FeatureAssociation *)h)->transformCur, 24); }
+void ref_fa_get_degenerate(void *h, int *d, float *P)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    *d = f->isDegenerate ? 1 : 0;
+    for (int i = 0; i < 9; i++) P[i] = i < (int)f->matP.d.size() ? f->matP.d[i] : 0.f;
+}
+void ref_fa_clear_correspondences(void *h)
+{   // FA:1672-1673
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    f->laserCloudOri->clear(); f->coeffSel->clear();
+}
+void ref_fa_findCorrespondingCornerFeatures(void *h, int it) { ((FeatureAssociation *)h)->findCorrespondingCornerFeatures(it); }
+void ref_fa_findCorrespondingSurfFeatures(void *h, int it) { ((FeatureAssociation *)h)->findCorrespondingSurfFeatures(it); }
+int ref_fa_calculateTransformationSurf(void *h, int it) { return ((FeatureAssociation *)h)->calculateTransformationSurf(it) ? 1 : 0; }
+int ref_fa_calculateTransformationCorner(void *h, int it) { return ((FeatureAssociation *)h)->calculateTransformationCorner(it) ? 1 : 0; }
+void ref_fa_updateTransformation(void *h) { ((FeatureAssociation *)h)->updateTransformation(); }
+int ref_fa_get_correspondences(void *h, llo_point *ori, llo_point *co, int cap)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    dump(f->laserCloudOri, ori, cap);
+    return dump(f->coeffSel, co, cap);
+}
+int ref_fa_get_search_ind(void *h, int which, float *i1, float *i2, float *i3, int cap)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    int n = which == 0 ? (int)f->cornerPointsSharp->points.size() : (int)f->surfPointsFlat->points.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (which == 0) { i1[i] = f->pointSearchCornerInd1[i]; i2[i] = f->pointSearchCornerInd2[i]; }
+        else { i1[i] = f->pointSearchSurfInd1[i]; i2[i] = f->pointSearchSurfInd2[i]; if (i3) i3[i] = f->pointSearchSurfInd3[i]; }
+    }
+    return n;
+}
+// the per-sweep bookkeeping around the matcher, for sequence replays (FA:1639-1725, FA:1759-1788)
+void ref_fa_integrateTransformation(void *h) { ((FeatureAssociation *)h)->integrateTransformation(); }
+void ref_fa_get_transform_sum(void *h, float *t) { memcpy(t, ((FeatureAssociation *)h)->transformSum, 24); }
+}  // extern "C"

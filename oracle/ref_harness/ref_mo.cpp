@@ -1,0 +1,136 @@
+// ref_mo.cpp — ORACLE tier B (test infrastructure): compiles the UNMODIFIED reference
+// /root/reference/LeGO-LOAM/src/mapOptmization.cpp (included below from where it lies, never
+// copied) against shim/llref_shim.hpp and exposes its own member functions through a C ABI
+// shaped like oracle/llo.h's llo_mapopt_* so the same tests drive both.
+// `private` -> `public` lets the harness reach the class members the ROS callbacks would fill;
+// `main` is renamed so the node's main() does not clash.
+#include "shim/llref_shim.hpp"          // every standard header first, before the keyword hack
+#define private public
+#define main ref_mo_node_main
+#include "mapOptmization.cpp"
+#undef main
+#undef private
+
+namespace {
+void fill(pcl::PointCloud<PointType>::Ptr &c, const llo_point *p, int n)
+{
+    c->clear();
+    c->points.resize(n);
+    for (int i = 0; i < n; i++) {
+        PointType q;
+        q.x = p[i].x; q.y = p[i].y; q.z = p[i].z; q.intensity = p[i].intensity;
+        c->points[i] = q;
+    }
+    c->width = n; c->height = 1;
+}
+sensor_msgs::PointCloud2ConstPtr to_msg(const llo_point *p, int n, double stamp)
+{
+    auto m = std::make_shared<sensor_msgs::PointCloud2>();
+    m->header.stamp = ros::Time(stamp);
+    m->xyzi.resize((size_t)n * 4);
+    for (int i = 0; i < n; i++) { m->xyzi[4 * i] = p[i].x; m->xyzi[4 * i + 1] = p[i].y; m->xyzi[4 * i + 2] = p[i].z; m->xyzi[4 * i + 3] = p[i].intensity; }
+    return m;
+}
+int dump(const pcl::PointCloud<PointType>::Ptr &c, llo_point *out, int cap)
+{
+    int n = (int)c->points.size();
+    for (int i = 0; i < n && i < cap; i++) { out[i].x = c->points[i].x; out[i].y = c->points[i].y; out[i].z = c->points[i].z; out[i].intensity = c->points[i].intensity; }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+void *ref_mo_create() { return new mapOptimization(); }
+void ref_mo_destroy(void *h) { delete (mapOptimization *)h; }
+
+// hand-over of the DS local map (what MO:1057-1064 leaves in the members)
+void ref_mo_set_map_ds(void *h, const llo_point *c, int mc, const llo_point *s, int ms)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    fill(m->laserCloudCornerFromMapDS, c, mc); fill(m->laserCloudSurfFromMapDS, s, ms);
+    m->laserCloudCornerFromMapDSNum = mc; m->laserCloudSurfFromMapDSNum = ms;
+}
+// raw local map + the reference's own filter objects, statements of MO:1058-1064
+void ref_mo_set_map_raw(void *h, const llo_point *c, int rc, const llo_point *s, int rs)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    fill(m->laserCloudCornerFromMap, c, rc); fill(m->laserCloudSurfFromMap, s, rs);
+    m->downSizeFilterCorner.setInputCloud(m->laserCloudCornerFromMap);
+    m->downSizeFilterCorner.filter(*m->laserCloudCornerFromMapDS);
+    m->laserCloudCornerFromMapDSNum = m->laserCloudCornerFromMapDS->points.size();
+    m->downSizeFilterSurf.setInputCloud(m->laserCloudSurfFromMap);
+    m->downSizeFilterSurf.filter(*m->laserCloudSurfFromMapDS);
+    m->laserCloudSurfFromMapDSNum = m->laserCloudSurfFromMapDS->points.size();
+}
+// through the reference's own topic handlers MO:608-627
+void ref_mo_set_scan(void *h, const llo_point *c, int nc, const llo_point *s, int ns, const llo_point *o, int no)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    m->laserCloudCornerLastHandler(to_msg(c, nc, 0.0));
+    m->laserCloudSurfLastHandler(to_msg(s, ns, 0.0));
+    m->laserCloudOutlierLastHandler(to_msg(o, no, 0.0));
+}
+void ref_mo_set_pose(void *h, const float *t) { memcpy(((mapOptimization *)h)->transformTobeMapped, t, 24); }
+void ref_mo_get_pose(void *h, float *t) { memcpy(t, ((mapOptimization *)h)->transformTobeMapped, 24); }
+void ref_mo_set_transform_sum(void *h, const float *t) { memcpy(((mapOptimization *)h)->transformSum, t, 24); }
+void ref_mo_get_bef_aft(void *h, float *b, float *a)
+{
+    memcpy(b, ((mapOptimization *)h)->transformBefMapped, 24); memcpy(a, ((mapOptimization *)h)->transformAftMapped, 24);
+}
+void ref_mo_get_degenerate(void *h, int *d, float *P)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    *d = m->isDegenerate ? 1 : 0;
+    for (int i = 0; i < 36; i++) P[i] = i < (int)m->matP.d.size() ? m->matP.d[i] : 0.f;
+}
+void ref_mo_downsampleCurrentScan(void *h) { ((mapOptimization *)h)->downsampleCurrentScan(); }
+void ref_mo_build_kdtrees(void *h)
+{   // MO:1333-1334
+    mapOptimization *m = (mapOptimization *)h;
+    m->kdtreeCornerFromMap->setInputCloud(m->laserCloudCornerFromMapDS);
+    m->kdtreeSurfFromMap->setInputCloud(m->laserCloudSurfFromMapDS);
+}
+void ref_mo_clear_correspondences(void *h)
+{   // MO:1338-1339
+    mapOptimization *m = (mapOptimization *)h;
+    m->laserCloudOri->clear(); m->coeffSel->clear();
+}
+void ref_mo_cornerOptimization(void *h, int it) { ((mapOptimization *)h)->cornerOptimization(it); }
+void ref_mo_surfOptimization(void *h, int it) { ((mapOptimization *)h)->surfOptimization(it); }
+int ref_mo_LMOptimization(void *h, int it) { return ((mapOptimization *)h)->LMOptimization(it) ? 1 : 0; }
+void ref_mo_scan2MapOptimization(void *h) { ((mapOptimization *)h)->scan2MapOptimization(); }
+int ref_mo_get_scan_ds(void *h, int which, llo_point *out, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    return dump(which == 0 ? m->laserCloudCornerLastDS : which == 1 ? m->laserCloudSurfLastDS
+              : which == 2 ? m->laserCloudOutlierLastDS : m->laserCloudSurfTotalLastDS, out, cap);
+}
+int ref_mo_get_map_ds(void *h, int which, llo_point *out, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    return dump(which == 0 ? m->laserCloudCornerFromMapDS : m->laserCloudSurfFromMapDS, out, cap);
+}
+int ref_mo_get_correspondences(void *h, llo_point *ori, llo_point *co, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    dump(m->laserCloudOri, ori, cap);
+    return dump(m->coeffSel, co, cap);
+}
+// the rest of run() (MO:1503-1519) for sequence replays: key-frame store, local-map assembly
+void ref_mo_set_odometry(void *h, const float *sum, double stamp)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    memcpy(m->transformSum, sum, 24); m->timeLaserOdometry = stamp;
+}
+void ref_mo_transformAssociateToMap(void *h) { ((mapOptimization *)h)->transformAssociateToMap(); }
+void ref_mo_extractSurroundingKeyFrames(void *h) { ((mapOptimization *)h)->extractSurroundingKeyFrames(); }
+void ref_mo_saveKeyFramesAndFactor(void *h) { ((mapOptimization *)h)->saveKeyFramesAndFactor(); }
+void ref_mo_correctPoses(void *h) { ((mapOptimization *)h)->correctPoses(); }
+void ref_mo_clearCloud(void *h) { ((mapOptimization *)h)->clearCloud(); }
+int ref_mo_num_keyframes(void *h) { return (int)((mapOptimization *)h)->cloudKeyPoses3D->points.size(); }
+int ref_mo_get_map_raw(void *h, int which, llo_point *out, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    return dump(which == 0 ? m->laserCloudCornerFromMap : m->laserCloudSurfFromMap, out, cap);
+}
+}  // extern "C"

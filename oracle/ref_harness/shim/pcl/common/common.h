@@ -1,0 +1,3 @@
+// ORACLE tier B shim (test infrastructure): forwards to llref_shim.hpp
+#pragma once
+#include "llref_shim.hpp"
