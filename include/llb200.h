@@ -169,6 +169,11 @@ int llb_s2m_pose_get(llb_ctx *ctx, float T[6]);
  * average device time of one launch, *n_queries the number of queries one launch processes */
 int llb_s2m_time_iteration(llb_ctx *ctx, const float T[6], int reps, float *ms_per_launch, int *n_queries);
 
+/* clock64 stamps taken by CTA 0 during the last iteration of the persistent scan-to-map
+ * kernel: start, end of phase A (kNN), B (fits), C (products), first grid sync, reduction,
+ * LM step, second grid sync (SM clock cycles; diagnostics for profiles/) */
+int llb_s2m_get_profile(llb_ctx *ctx, long long stamps[8]);
+
 /* number of kernels launched by this context since creation (bench.py gpu_launches) */
 long long llb_launch_count(const llb_ctx *ctx);
 

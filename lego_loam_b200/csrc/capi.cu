@@ -455,7 +455,7 @@ int llb_s2m_iterate(llb_ctx *c, float T[6], int iter, int *converged, int *n_cor
         c->dbg_knn.ensure((size_t)std::max(nq, 1) * 5); c->dbg_d2.ensure((size_t)std::max(nq, 1) * 5);
         S2mDebug dbg{ c->dbg_coeff.p, c->dbg_valid.p, c->dbg_knn.p, c->dbg_d2.p };
         c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
-        c->launches += c->s2m.iterate(iter, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        c->launches += c->s2m.run(iter, iter + 1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         read_count(c, 0);                                           // also synchronises
         const S2mState &s = *c->pin_state.p;
@@ -477,8 +477,8 @@ int llb_s2m_optimize(llb_ctx *c, float T[6], llb_stats *stats)
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
         c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
-        for (int it = 0; it < c->prm.s2m_max_iterations; it++)
-            c->launches += c->s2m.iterate(it, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1,
+                                  true, c->stream);
         LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         read_count(c, 0);
@@ -500,8 +500,8 @@ int llb_s2m_optimize_dev(llb_ctx *c, float *T_dev)
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         c->launches += c->s2m.prepare(nullptr, T_dev, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
-        for (int it = 0; it < c->prm.s2m_max_iterations; it++)
-            c->launches += c->s2m.iterate(it, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, true, c->stream);
+        c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1,
+                                  true, c->stream);
         // S2mState starts with T[6]
         LLB_CUDA(cudaMemcpyAsync(T_dev, c->s2m.state_dev(), 6 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
         c->dbg_ready = false;
@@ -537,7 +537,7 @@ int llb_s2m_accumulate(llb_ctx *c, int iter, int rank, int world, double **acc)
         if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
-        c->launches += c->s2m.iterate(iter, q, c->gridCorner.view(), c->gridSurf.view(), dbg, rank, world, false, c->stream);
+        c->launches += c->s2m.run(iter, iter + 1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, rank, world, false, c->stream);
         *acc = c->s2m.acc_dev();
         return (int)LLB_OK;
     });
@@ -551,10 +551,10 @@ int llb_s2m_time_iteration(llb_ctx *c, const float T[6], int reps, float *ms_per
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
-        c->launches += c->s2m.iterate(1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
+        c->launches += c->s2m.run(1, 2, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
         LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
         for (int r = 0; r < reps; r++)
-            c->launches += c->s2m.iterate(1, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
+            c->launches += c->s2m.run(1, 2, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1, false, c->stream);
         LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
         read_count(c, 0);
         float ms = 0.f;
@@ -638,6 +638,17 @@ int llb_get_normal_equations(llb_ctx *c, float AtA[36], float AtB[6], float X[6]
         if (AtA) std::memcpy(AtA, c->pin_state.p->AtA, sizeof(float) * 36);
         if (AtB) std::memcpy(AtB, c->pin_state.p->AtB, sizeof(float) * 6);
         if (X) std::memcpy(X, c->pin_state.p->X, sizeof(float) * 6);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_get_profile(llb_ctx *c, long long stamps[8])
+{
+    return guarded(c, [&]() {
+        if (!stamps) return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 8; i++) stamps[i] = c->pin_state.p->prof[i];
         return (int)LLB_OK;
     });
 }

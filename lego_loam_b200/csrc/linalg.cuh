@@ -13,9 +13,12 @@
 #include <cuda_runtime.h>
 #include <float.h>
 
+// host + device: tests/host_linalg_test.cu runs the very same code on the CPU against the oracle
+#define LLB_HD __host__ __device__
+
 namespace llb {
 
-__device__ __forceinline__ float cv_hypot(float a, float b)
+LLB_HD __forceinline__ float cv_hypot(float a, float b)
 {
     a = fabsf(a);
     b = fabsf(b);
@@ -32,7 +35,7 @@ __device__ __forceinline__ float cv_hypot(float a, float b)
 
 // Symmetric eigen-decomposition, eigenvalues descending in W, eigenvectors as rows of V.
 template <int N>
-__device__ void cv_eigen(float *A, float *W, float *V)
+LLB_HD void cv_eigen(float *A, float *W, float *V)
 {
     const float eps = FLT_EPSILON;
     int indR[N], indC[N];
@@ -129,10 +132,84 @@ __device__ void cv_eigen(float *A, float *W, float *V)
     }
 }
 
+// cv_eigen<3> with everything in registers.  Same arithmetic, same pivot choices (including
+// OpenCV's stale indR/indC bookkeeping: for n = 3 only indR[0] and indC[2] are variable), but
+// the (k,l) pivot is dispatched over its three possible values instead of indexing arrays, so
+// one thread per query runs without local memory.  A = {a00,a01,a02,a11,a12,a22} upper triangle.
+LLB_HD inline void cv_eigen3(float a00, float a01, float a02, float a11, float a12, float a22, float *W, float *V)
+{
+    const float eps = FLT_EPSILON;
+    float w0 = a00, w1 = a11, w2 = a22;
+    float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+    int indR0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;           // indR[1] == 2, indC[1] == 0 always
+    int indC2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+
+    for (int iters = 0; iters < 3 * 3 * 30; iters++) {
+        // pivot search, in OpenCV's order: rows via indR, then columns via indC
+        int k = 0, l;
+        float mv = fabsf(indR0 == 1 ? a01 : a02);
+        {
+            float val = fabsf(a12);
+            if (mv < val) mv = val, k = 1;
+        }
+        l = (k == 0) ? indR0 : 2;
+        {
+            float val = fabsf(a01);                          // i = 1: A[indC[1]][1] = A[0][1]
+            if (mv < val) mv = val, k = 0, l = 1;
+            val = fabsf(indC2 == 0 ? a02 : a12);             // i = 2: A[indC[2]][2]
+            if (mv < val) mv = val, k = indC2, l = 2;
+        }
+        const int code = (k == 0) ? (l == 1 ? 0 : 1) : 2;    // (0,1) (0,2) (1,2)
+        const float p = code == 0 ? a01 : (code == 1 ? a02 : a12);
+        if (fabsf(p) <= eps) break;
+        const float wk = (code == 2) ? w1 : w0, wl = (code == 0) ? w1 : w2;
+        float y = (float)((wl - wk) * 0.5);
+        float t = fabsf(y) + cv_hypot(p, y);
+        float s = cv_hypot(p, t);
+        float c = t / s;
+        s = p / s;
+        t = (p / t) * p;
+        if (y < 0) s = -s, t = -t;
+        float a0, b0;
+#define LLB_ROT(x0, x1) (a0 = (x0), b0 = (x1), (x0) = a0 * c - b0 * s, (x1) = a0 * s + b0 * c)
+        if (code == 0) {
+            a01 = 0; w0 -= t; w1 += t;
+            LLB_ROT(a02, a12);                               // i > l: (A[k][i], A[l][i])
+            LLB_ROT(v00, v10); LLB_ROT(v01, v11); LLB_ROT(v02, v12);
+        } else if (code == 1) {
+            a02 = 0; w0 -= t; w2 += t;
+            LLB_ROT(a01, a12);                               // k < i < l: (A[k][i], A[i][l])
+            LLB_ROT(v00, v20); LLB_ROT(v01, v21); LLB_ROT(v02, v22);
+        } else {
+            a12 = 0; w1 -= t; w2 += t;
+            LLB_ROT(a01, a02);                               // i < k: (A[i][k], A[i][l])
+            LLB_ROT(v10, v20); LLB_ROT(v11, v21); LLB_ROT(v12, v22);
+        }
+#undef LLB_ROT
+        if (k == 0) indR0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+        if (l == 2) indC2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+    }
+    // selection sort, descending, rows of V follow
+    W[0] = w0; W[1] = w1; W[2] = w2;
+    V[0] = v00; V[1] = v01; V[2] = v02; V[3] = v10; V[4] = v11; V[5] = v12; V[6] = v20; V[7] = v21; V[8] = v22;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int m = k;
+#pragma unroll
+        for (int i = k + 1; i < 3; i++)
+            if (W[m] < W[i]) m = i;
+        if (k != m) {
+            float tmp = W[m]; W[m] = W[k]; W[k] = tmp;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { tmp = V[3 * m + i]; V[3 * m + i] = V[3 * k + i]; V[3 * k + i] = tmp; }
+        }
+    }
+}
+
 // Least squares / square solve by Householder QR.  A (M x N, row-major) and b (M) are
 // destroyed; x receives N values.  Returns false (x = 0) for a singular system.
 template <int M, int N>
-__device__ bool cv_solve_qr(float *A, float *b, float *x)
+LLB_HD bool cv_solve_qr(float *A, float *b, float *x)
 {
     const float eps = FLT_EPSILON * 10;
     float vl[M], hF[N];
@@ -189,7 +266,7 @@ __device__ bool cv_solve_qr(float *A, float *b, float *x)
 
 // D (M x Nn) = A (M x K) * B (K x Nn), double accumulation, one rounding (cv::gemm CV_32F)
 template <int M, int K, int Nn>
-__device__ void cv_gemm(const float *A, const float *B, float *D)
+LLB_HD void cv_gemm(const float *A, const float *B, float *D)
 {
     for (int i = 0; i < M; i++)
         for (int j = 0; j < Nn; j++) {
@@ -200,7 +277,7 @@ __device__ void cv_gemm(const float *A, const float *B, float *D)
 }
 
 // Mat::inv() DECOMP_LU, 3x3: closed form in double
-__device__ inline bool cv_inv3(const float *A, float *D)
+LLB_HD inline bool cv_inv3(const float *A, float *D)
 {
 #define S(r, c) ((double)A[(r) * 3 + (c)])
     double d = S(0,0) * (S(1,1) * S(2,2) - S(1,2) * S(2,1)) -
@@ -226,7 +303,7 @@ __device__ inline bool cv_inv3(const float *A, float *D)
 
 // Mat::inv() DECOMP_LU for N > 3: LU with partial pivoting against the identity, float
 template <int N>
-__device__ bool cv_inv_lu(const float *Ain, float *D)
+LLB_HD bool cv_inv_lu(const float *Ain, float *D)
 {
     const float eps = FLT_EPSILON * 10;
     float a[N * N], b[N * N];

@@ -122,8 +122,7 @@ __device__ int solve3(OdomState *st, const double *sum, int iter, int which, con
     cv_solve_qr<3, 3>(A, B, X);
     if (iter == 0) {
         float E[3], V[9], V2[9], Vinv[9];
-        for (int i = 0; i < 9; i++) A[i] = AtA[i];
-        cv_eigen<3>(A, E, V);
+        cv_eigen3(AtA[0], AtA[1], AtA[2], AtA[4], AtA[5], AtA[8], E, V);
         for (int i = 0; i < 9; i++) V2[i] = V[i];
         int deg = 0;
         for (int i = 2; i >= 0; i--) {

@@ -1,31 +1,42 @@
-// s2m.cu — K3 (fused transform -> radius-bounded exact 5-NN -> line / plane fit ->
-// residual + Jacobian row) and K4 (J^T J / J^T r reduction, LM step, degeneracy
-// projection, convergence test) in ONE kernel per LM iteration.
+// s2m.cu — K3 (transform -> radius-bounded exact 5-NN -> line / plane fit -> residual +
+// Jacobian row) and K4 (J^T J / J^T r reduction, LM step, degeneracy projection,
+// convergence test) as ONE persistent cooperative kernel for the whole loop of
+// scan2MapOptimization (MO:1336-1346): an iteration never returns to the host and never
+// pays a launch.
 //
-// Work decomposition: one warp per query.  The 9 contiguous cell runs around the query
-// are read cooperatively (lane = candidate, coalesced float4 loads, all 9 loads in flight
-// before the first use), each lane keeps a private sorted top-5 in registers and five
-// rounds of warp-wide lexicographic (distance, original index) arg-min produce the exact
-// 5-NN with the oracle's tie rule.  The fit is evaluated redundantly by every lane (no
-// divergence, no shuffles) so that lane k can accumulate the k-th of the 27 products of
-// the normal equations in fp64 without any data exchange.  Blocks write deterministic
-// partial sums; the last block to finish (ticket) adds them in a fixed order, rounds to
-// fp32 exactly like cv::gemm does, and one thread performs the 6x6 LM step so the new
-// pose, its sin/cos and the convergence flag are on the device before the next launch.
+// Work decomposition per iteration (each CTA owns a contiguous slice of the queries):
+//   phase A  one WARP per query: the 9 contiguous cell runs around the query are read
+//            cooperatively (lane = candidate, coalesced float4 loads, all loads of the
+//            non-empty runs in flight before the first use), each lane keeps a private
+//            sorted top-5 in registers and five rounds of warp-wide lexicographic
+//            (distance, original index) arg-min give the exact 5-NN with the oracle's tie
+//            rule; the 5 neighbours go to shared memory.
+//   phase B  one THREAD per query: gate, 3x3 Jacobi eigen fit (corner) or 5x3 Householder
+//            least squares (surf), residual, weight, Jacobian row -> shared memory.
+//   phase C  lane k of warp w accumulates product k of the 28 normal-equation terms over
+//            rows w, w+16, ... in fp64 (exact float x float products, like cv::gemm).
+//   then     fixed-order CTA reduction -> global partials -> grid.sync -> CTA 0 adds the
+//            partials in a fixed order, rounds to fp32 exactly like cv::gemm, and performs
+//            the 6x6 LM step (QR solve, iteration-0 eigen degeneracy test, matP projection,
+//            pose update, sin/cos of the new pose, convergence flag) -> grid.sync.
 //
 // Numerics: IEEE fp32 without contraction (-fmad=false) in the reference's association
 // order; the double-promoted sub-expressions of SURVEY.md Appendix B are evaluated in
 // fp64; pose sin/cos are (float)sin((double)x) (correctly rounded float).
 #include "s2m.cuh"
 #include "linalg.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace llb {
 
 namespace {
 
-constexpr int S2M_THREADS = 256;
+constexpr int S2M_THREADS = 512;
 constexpr int S2M_NW = S2M_THREADS / 32;
-constexpr int S2M_MAX_BLOCKS = 148 * 4;
+constexpr int S2M_TILE = 128;            // queries a CTA stages per pass
+constexpr int S2M_QPB = 32;              // target queries per CTA when sizing the grid
 
 __device__ __forceinline__ bool lex_less(float d1, int i1, float d2, int i2)
 {
@@ -72,9 +83,10 @@ __device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const f
 }
 
 // Exact 5-NN of (qx,qy,qz) among the map points inside the 3x3x3 cell neighbourhood.
-// Every lane returns the same result.  nn[k].w carries the original map index bits.
+// Every lane returns the same result: sorted-array positions (or -1), squared distances and
+// original indices in ascending (distance, index) order.
 __device__ __forceinline__ void knn5_warp(const MapIndexView &m, float qx, float qy, float qz, int lane,
-                                          float4 (&nn)[5], float (&nd)[5], int (&ni)[5])
+                                          int (&npos)[5], float (&nd)[5], int (&ni)[5])
 {
     const GridDesc *g = m.desc;
     const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
@@ -130,32 +142,32 @@ __device__ __forceinline__ void knn5_warp(const MapIndexView &m, float qx, float
         const int p = __shfl_sync(FULL, t.S[0], src);
         nd[r] = __uint_as_float(mind);
         ni[r] = (p >= 0) ? (int)mini : -1;
-        if (p >= 0) nn[r] = __ldg(&m.sorted[p]);
-        else nn[r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        npos[r] = p;
         if (lane == src) t.pop();
     }
 }
 
 // cornerOptimization body for one query (MO:1102-1170).  Returns true when the row is accepted.
-__device__ __forceinline__ bool corner_fit(const float4 (&nn)[5], float x0, float y0, float z0, float4 &coeff)
+__device__ __forceinline__ bool corner_fit(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+                                           float x0, float y0, float z0, float4 &coeff)
 {
     float cx = 0, cy = 0, cz = 0;
 #pragma unroll
-    for (int j = 0; j < 5; j++) { cx += nn[j].x; cy += nn[j].y; cz += nn[j].z; }
+    for (int j = 0; j < 5; j++) { cx += nx[j]; cy += ny[j]; cz += nz[j]; }
     cx /= 5; cy /= 5; cz /= 5;
 
     float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
-        float ax = nn[j].x - cx, ay = nn[j].y - cy, az = nn[j].z - cz;
+        float ax = nx[j] - cx, ay = ny[j] - cy, az = nz[j] - cz;
         a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
         a22 += ay * ay; a23 += ay * az;
         a33 += az * az;
     }
     a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
 
-    float A1[9] = { a11, a12, a13, a12, a22, a23, a13, a23, a33 }, D1[3], V1[9];
-    cv_eigen<3>(A1, D1, V1);
+    float D1[3], V1[9];
+    cv_eigen3(a11, a12, a13, a22, a23, a33, D1, V1);
     if (!(D1[0] > 3 * D1[1])) return false;
 
     float x1 = (float)((double)cx + 0.1 * (double)V1[0]);
@@ -181,11 +193,12 @@ __device__ __forceinline__ bool corner_fit(const float4 (&nn)[5], float x0, floa
 }
 
 // surfOptimization body for one query (MO:1184-1223)
-__device__ __forceinline__ bool surf_fit(const float4 (&nn)[5], float x0, float y0, float z0, float4 &coeff)
+__device__ __forceinline__ bool surf_fit(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+                                         float x0, float y0, float z0, float4 &coeff)
 {
     float A0[15], B0[5] = { -1.f, -1.f, -1.f, -1.f, -1.f }, X0[3];
 #pragma unroll
-    for (int j = 0; j < 5; j++) { A0[3 * j] = nn[j].x; A0[3 * j + 1] = nn[j].y; A0[3 * j + 2] = nn[j].z; }
+    for (int j = 0; j < 5; j++) { A0[3 * j] = nx[j]; A0[3 * j + 1] = ny[j]; A0[3 * j + 2] = nz[j]; }
     cv_solve_qr<5, 3>(A0, B0, X0);
 
     float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
@@ -195,21 +208,13 @@ __device__ __forceinline__ bool surf_fit(const float4 (&nn)[5], float x0, float 
     bool planeValid = true;
 #pragma unroll
     for (int j = 0; j < 5; j++)
-        if ((double)fabsf(pa * nn[j].x + pb * nn[j].y + pc * nn[j].z + pd) > 0.2) planeValid = false;
+        if ((double)fabsf(pa * nx[j] + pb * ny[j] + pc * nz[j] + pd) > 0.2) planeValid = false;
     if (!planeValid) return false;
 
     float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
     float s = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
     coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
     return (double)s > 0.1;
-}
-
-__device__ __forceinline__ float sel7(const float (&v)[7], int i)
-{
-    float r = v[0];
-#pragma unroll
-    for (int k = 1; k < 7; k++) r = (i == k) ? v[k] : r;
-    return r;
 }
 
 __device__ void update_sincos(S2mState *st)
@@ -288,125 +293,170 @@ __global__ void s2m_state_init_kernel(S2mState *st)
     st->converged = 0; st->iters = 0; st->n_corr = 0; st->is_degenerate = 0; st->skipped = 0; st->ticket = 0;
 }
 
-__global__ void __launch_bounds__(S2M_THREADS)
-s2m_iter_kernel(S2mParams prm, int iter, S2mQueries q, MapIndexView cmap, MapIndexView smap,
-                S2mState *__restrict__ st, double *__restrict__ partials, double *__restrict__ acc_out,
-                S2mDebug dbg, int rank, int world, int do_solve)
+// index pairs of the 28 accumulated products of v = {arx, ary, arz, cx, cy, cz, b, 1}
+__device__ __forceinline__ void pair_of(int k, int &ia, int &ib)
 {
-    if (st->converged || st->skipped) return;                 // uniform over the grid
+    ia = 7; ib = 7;                                          // k == 27: row count
+    int c = 0;
+    for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++, c++)
+            if (c == k) { ia = i; ib = j; }
+    if (k >= 21 && k < 27) { ia = k - 21; ib = 6; }
+}
 
+__global__ void __launch_bounds__(S2M_THREADS, 1)
+s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexView cmap, MapIndexView smap,
+                S2mState *st, double *partials, double *acc_out, S2mDebug dbg, int rank, int world, int do_solve)
+{
+    cg::grid_group grid = cg::this_grid();
+
+    __shared__ float s_nn[15][S2M_TILE];                      // 5 neighbours x (x,y,z), SoA
+    __shared__ float s_q[7][S2M_TILE];                        // po.xyz, sel.xyz, 5th squared distance (or -1)
+    __shared__ float s_row[8][S2M_TILE];                      // Jacobian row, -residual, valid
     __shared__ double s_acc[S2M_NW][32];
     __shared__ double s_tot[32];
-    __shared__ int s_last;
+
+    if (__ldcg(&st->skipped)) return;                         // uniform over the grid (guard MO:1331)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nc = q.nc_dev ? *q.nc_dev : q.nc_upper;
     const int ns = q.ns_dev ? *q.ns_dev : q.ns_upper;
     const int nq = nc + ns;
+    // this rank's queries are qi = rank + world * j, j in [0, nloc); CTA b owns j in [j0, j1)
+    const int nloc = nq > rank ? (nq - rank + world - 1) / world : 0;
+    const int per = (nloc + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int j0 = min((int)blockIdx.x * per, nloc), j1 = min(j0 + per, nloc);
 
-    const float crx = st->cs[0], srx = st->cs[1], cry = st->cs[2], sry = st->cs[3], crz = st->cs[4], srz = st->cs[5];
-    const float tX = st->T[3], tY = st->T[4], tZ = st->T[5];
+    int ia, ib;
+    pair_of(lane, ia, ib);
 
-    // lane k accumulates product (ia, ib) of v = {arx, ary, arz, cx, cy, cz, b}
-    int ia = 0, ib = 0;
-    {
-        int k = 0;
-        for (int i = 0; i < 6; i++)
-            for (int j = i; j < 6; j++, k++)
-                if (k == lane) { ia = i; ib = j; }
-        if (lane >= 21 && lane < 27) { ia = lane - 21; ib = 6; }
-    }
-    double acc = 0.0;
+    for (int iter = it_begin; iter < it_end; iter++) {
+        const float crx = __ldcg(&st->cs[0]), srx = __ldcg(&st->cs[1]), cry = __ldcg(&st->cs[2]),
+                    sry = __ldcg(&st->cs[3]), crz = __ldcg(&st->cs[4]), srz = __ldcg(&st->cs[5]);
+        const float tX = __ldcg(&st->T[3]), tY = __ldcg(&st->T[4]), tZ = __ldcg(&st->T[5]);
+        double acc = 0.0;
+        long long pa = 0, pb = 0, pc = 0;
+        const bool prof = (blockIdx.x == 0 && tid == 0);
+        if (prof) st->prof[0] = clock64();
 
-    for (int qi = rank + world * (blockIdx.x * S2M_NW + w); qi < nq; qi += world * gridDim.x * S2M_NW) {
-        const bool is_corner = qi < nc;
-        const float4 po = is_corner ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
+        for (int t0 = j0; t0 < j1; t0 += S2M_TILE) {
+            const int tn = min(S2M_TILE, j1 - t0);
+            // ---------------- phase A: warp per query
+            for (int s = w; s < tn; s += S2M_NW) {
+                const int qi = rank + world * (t0 + s);
+                const bool is_corner = qi < nc;
+                const float4 po = is_corner ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
+                // pointAssociateToMap MO:513-527
+                const float x1 = crz * po.x - srz * po.y;
+                const float y1 = srz * po.x + crz * po.y;
+                const float z1 = po.z;
+                const float y2 = crx * y1 - srx * z1;
+                const float z2 = srx * y1 + crx * z1;
+                const float sx = cry * x1 + sry * z2 + tX;
+                const float sy = y2 + tY;
+                const float sz = -sry * x1 + cry * z2 + tZ;
 
-        // pointAssociateToMap MO:513-527
-        const float x1 = crz * po.x - srz * po.y;
-        const float y1 = srz * po.x + crz * po.y;
-        const float z1 = po.z;
-        const float y2 = crx * y1 - srx * z1;
-        const float z2 = srx * y1 + crx * z1;
-        const float sx = cry * x1 + sry * z2 + tX;
-        const float sy = y2 + tY;
-        const float sz = -sry * x1 + cry * z2 + tZ;
-
-        float4 nn[5]; float nd[5]; int ni[5];
-        knn5_warp(is_corner ? cmap : smap, sx, sy, sz, lane, nn, nd, ni);
-
-        if (dbg.knn_idx && lane < 5) {
-            // every lane holds all five; lane j writes entry j
-            int vi = ni[0]; float vd = nd[0];
+                int npos[5]; float nd[5]; int ni[5];
+                const MapIndexView &mv = is_corner ? cmap : smap;
+                knn5_warp(mv, sx, sy, sz, lane, npos, nd, ni);
+                // lane j < 5 fetches neighbour j (an L1/L2 hit: the warp just read it) and stores it
+                int myp = npos[0]; int myi = ni[0]; float myd = nd[0];
 #pragma unroll
-            for (int k = 1; k < 5; k++) { vi = (lane == k) ? ni[k] : vi; vd = (lane == k) ? nd[k] : vd; }
-            dbg.knn_idx[qi * 5 + lane] = vi;
-            dbg.knn_d2[qi * 5 + lane] = vd;
-        }
-
-        bool ok = (ni[4] >= 0) && ((double)nd[4] < (double)prm.knn_max_sqdist);   // MO:1101 / MO:1183
-        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) ok = is_corner ? corner_fit(nn, sx, sy, sz, coeff) : surf_fit(nn, sx, sy, sz, coeff);
-
-        if (dbg.coeff && lane == 0) { dbg.coeff[qi] = coeff; dbg.valid[qi] = ok ? 1 : 0; }
-
-        if (ok) {
-            // Jacobian row MO:1252-1271
-            float v[7];
-            v[0] = (crx * sry * srz * po.x + crx * crz * sry * po.y - srx * sry * po.z) * coeff.x
-                 + (-srx * srz * po.x - crz * srx * po.y - crx * po.z) * coeff.y
-                 + (crx * cry * srz * po.x + crx * cry * crz * po.y - cry * srx * po.z) * coeff.z;
-            v[1] = ((cry * srx * srz - crz * sry) * po.x + (sry * srz + cry * crz * srx) * po.y + crx * cry * po.z) * coeff.x
-                 + ((-cry * crz - srx * sry * srz) * po.x + (cry * srz - crz * srx * sry) * po.y - crx * sry * po.z) * coeff.z;
-            v[2] = ((crz * srx * sry - cry * srz) * po.x + (-cry * crz - srx * sry * srz) * po.y) * coeff.x
-                 + (crx * crz * po.x - crx * srz * po.y) * coeff.y
-                 + ((sry * srz + cry * crz * srx) * po.x + (crz * sry - cry * srx * srz) * po.y) * coeff.z;
-            v[3] = coeff.x; v[4] = coeff.y; v[5] = coeff.z;
-            v[6] = -coeff.w;
-            if (lane < 27) acc += (double)sel7(v, ia) * (double)sel7(v, ib);
-            else if (lane == 27) acc += 1.0;
-        }
-    }
-
-    // ---- block partial (fixed order over warps)
-    s_acc[w][lane] = acc;
-    __syncthreads();
-    if (tid < S2M_ACC) {
-        double s = 0.0;
+                for (int k = 1; k < 5; k++) { myp = (lane == k) ? npos[k] : myp; myi = (lane == k) ? ni[k] : myi; myd = (lane == k) ? nd[k] : myd; }
+                if (lane < 5) {
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (myp >= 0) p = __ldg(&mv.sorted[myp]);
+                    s_nn[lane * 3 + 0][s] = p.x; s_nn[lane * 3 + 1][s] = p.y; s_nn[lane * 3 + 2][s] = p.z;
+                    if (dbg.knn_idx) { dbg.knn_idx[qi * 5 + lane] = myi; dbg.knn_d2[qi * 5 + lane] = myd; }
+                }
+                if (lane == 5) {
+                    s_q[0][s] = po.x; s_q[1][s] = po.y; s_q[2][s] = po.z;
+                    s_q[3][s] = sx; s_q[4][s] = sy; s_q[5][s] = sz;
+                    s_q[6][s] = (ni[4] >= 0) ? nd[4] : -1.f;
+                }
+            }
+            __syncthreads();
+            if (prof) pa = clock64();
+            // ---------------- phase B: thread per query
+            if (tid < tn) {
+                const int s = tid;
+                const int qi = rank + world * (t0 + s);
+                const bool is_corner = qi < nc;
+                const float d5 = s_q[6][s];
+                bool ok = (d5 >= 0.f) && ((double)d5 < (double)prm.knn_max_sqdist);    // MO:1101 / MO:1183
+                float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float px = s_q[0][s], py = s_q[1][s], pz = s_q[2][s];
+                if (ok) {
+                    float nx[5], ny[5], nz[5];
 #pragma unroll
-        for (int k = 0; k < S2M_NW; k++) s += s_acc[k][tid];
-        partials[(size_t)blockIdx.x * S2M_ACC + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+                    for (int k = 0; k < 5; k++) { nx[k] = s_nn[3 * k][s]; ny[k] = s_nn[3 * k + 1][s]; nz[k] = s_nn[3 * k + 2][s]; }
+                    const float sx = s_q[3][s], sy = s_q[4][s], sz = s_q[5][s];
+                    ok = is_corner ? corner_fit(nx, ny, nz, sx, sy, sz, coeff) : surf_fit(nx, ny, nz, sx, sy, sz, coeff);
+                }
+                if (dbg.coeff) { dbg.coeff[qi] = coeff; dbg.valid[qi] = ok ? 1 : 0; }
+                float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+                if (ok) {
+                    // Jacobian row MO:1252-1271
+                    v[0] = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * coeff.x
+                         + (-srx * srz * px - crz * srx * py - crx * pz) * coeff.y
+                         + (crx * cry * srz * px + crx * cry * crz * py - cry * srx * pz) * coeff.z;
+                    v[1] = ((cry * srx * srz - crz * sry) * px + (sry * srz + cry * crz * srx) * py + crx * cry * pz) * coeff.x
+                         + ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * coeff.z;
+                    v[2] = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * coeff.x
+                         + (crx * crz * px - crx * srz * py) * coeff.y
+                         + ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * coeff.z;
+                    v[3] = coeff.x; v[4] = coeff.y; v[5] = coeff.z;
+                    v[6] = -coeff.w;
+                    v[7] = 1.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) s_row[k][s] = v[k];
+            }
+            __syncthreads();
+            if (prof) pb = clock64();
+            // ---------------- phase C: lane k accumulates product k over rows w, w+16, ...
+            if (lane < S2M_ACC)
+                for (int r = w; r < tn; r += S2M_NW) acc += (double)s_row[ia][r] * (double)s_row[ib][r];
+            __syncthreads();
+            if (prof) pc = clock64();
+        }
+        if (prof) { st->prof[1] = pa; st->prof[2] = pb; st->prof[3] = pc; }
 
-    // ---- last block: deterministic grid reduction (8 interleaved slices, fixed order)
-    {
-        double s = 0.0;
-        if (lane < S2M_ACC)
-            for (int b = w; b < (int)gridDim.x; b += S2M_NW) s += __ldcg(&partials[(size_t)b * S2M_ACC + lane]);
-        __syncthreads();
-        s_acc[w][lane] = s;
+        // ---- CTA partial (fixed order over warps)
+        s_acc[w][lane] = acc;
         __syncthreads();
         if (tid < S2M_ACC) {
-            double tsum = 0.0;
+            double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < S2M_NW; k++) tsum += s_acc[k][tid];
-            s_tot[tid] = tsum;
-            if (!do_solve) acc_out[tid] = tsum;
+            for (int k = 0; k < S2M_NW; k++) s += s_acc[k][tid];
+            partials[(size_t)blockIdx.x * S2M_ACC + tid] = s;
         }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        st->ticket = 0;
-        if (do_solve) lm_solve(st, s_tot, iter, prm);
+        grid.sync();
+        if (prof) st->prof[4] = clock64();
+
+        // ---- CTA 0: deterministic grid reduction (16 interleaved slices, fixed order) + LM step
+        if (blockIdx.x == 0) {
+            double s = 0.0;
+            if (lane < S2M_ACC)
+                for (int b = w; b < (int)gridDim.x; b += S2M_NW) s += __ldcg(&partials[(size_t)b * S2M_ACC + lane]);
+            s_acc[w][lane] = s;
+            __syncthreads();
+            if (tid < S2M_ACC) {
+                double tsum = 0.0;
+#pragma unroll
+                for (int k = 0; k < S2M_NW; k++) tsum += s_acc[k][tid];
+                s_tot[tid] = tsum;
+                if (!do_solve) acc_out[tid] = tsum;
+            }
+            __syncthreads();
+            if (prof) st->prof[5] = clock64();
+            if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm);
+            if (prof) st->prof[6] = clock64();
+        }
+        if (!do_solve) break;
+        grid.sync();
+        if (prof) st->prof[7] = clock64();
+        if (__ldcg(&st->converged)) break;                   // MO:1344-1345, uniform over the grid
     }
 }
 
@@ -422,7 +472,12 @@ void S2mSolver::init(const S2mParams &p)
 {
     prm_ = p;
     state_.ensure(1);
-    max_blocks_ = S2M_MAX_BLOCKS;
+    int dev = 0, sms = 0, per_sm = 0;
+    LLB_CUDA(cudaGetDevice(&dev));
+    LLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    LLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2m_loop_kernel, S2M_THREADS, 0));
+    if (per_sm < 1) throw std::runtime_error("s2m_loop_kernel cannot be made resident");
+    max_blocks_ = sms * per_sm;
     partials_.ensure((size_t)max_blocks_ * S2M_ACC);
     acc_.ensure(32);
     s2m_state_init_kernel<<<1, 1>>>(state_.p);
@@ -444,14 +499,17 @@ int S2mSolver::prepare(const float *T_host, const float *T_dev, const GridDesc *
     return 1;
 }
 
-int S2mSolver::iterate(int iter, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
-                       const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s)
+int S2mSolver::run(int it_begin, int it_end, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
+                   const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s)
 {
     const int nq = std::max(1, div_up(q.nc_upper + q.ns_upper, world));
-    const int grid = std::min(max_blocks_, div_up(nq, S2M_NW));
-    s2m_iter_kernel<<<grid, S2M_THREADS, 0, s>>>(prm_, iter, q, cmap, smap, state_.p, partials_.p, acc_.p, dbg,
-                                                 rank, world, do_solve ? 1 : 0);
-    LLB_CUDA(cudaGetLastError());
+    int grid = std::max(1, std::min(max_blocks_, div_up(nq, S2M_QPB)));
+    S2mParams prm = prm_;
+    S2mQueries qq = q; MapIndexView cm = cmap, sm = smap; S2mDebug dg = dbg;
+    S2mState *st = state_.p; double *part = partials_.p, *acc = acc_.p;
+    int ds = do_solve ? 1 : 0;
+    void *args[] = { &prm, &it_begin, &it_end, &qq, &cm, &sm, &st, &part, &acc, &dg, &rank, &world, &ds };
+    LLB_CUDA(cudaLaunchCooperativeKernel((const void *)s2m_loop_kernel, dim3(grid), dim3(S2M_THREADS), args, 0, s));
     return 1;
 }
 

@@ -28,6 +28,7 @@ struct S2mState {                    // device-resident, persists across registr
     float matP[36];                  // MO:203
     float AtA[36], AtB[6], X[6];     // last LM step (diagnostics)
     unsigned ticket;                 // last-block election
+    long long prof[8];               // clock64 stamps of CTA 0, last iteration: start, A, B, C, sync1, reduce, solve, sync2
 };
 
 struct S2mDebug {                    // optional per-query outputs (nullptr = off)
@@ -51,10 +52,11 @@ public:
     // upload T, compute its sin/cos on the device, evaluate the map-size guard, reset flags
     int prepare(const float *T_host, const float *T_dev, const GridDesc *corner_desc, const GridDesc *surf_desc,
                 cudaStream_t s);
-    // one fused iteration.  rank/world shard the queries (world = 1: everything);
-    // do_solve = false stops after the 28 sums are in acc_dev() (for an external all-reduce)
-    int iterate(int iter, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
-                const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s);
+    // iterations [it_begin, it_end) in ONE cooperative launch, stopping early on convergence.
+    // rank/world shard the queries (world = 1: everything); do_solve = false runs exactly one
+    // iteration and stops after the 28 sums are in acc_dev() (for an external all-reduce)
+    int run(int it_begin, int it_end, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
+            const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s);
     int solve(int iter, cudaStream_t s);
 
 private:
