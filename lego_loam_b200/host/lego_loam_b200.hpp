@@ -1,0 +1,266 @@
+// lego_loam_b200.hpp — C++ host adapters: the reference's own class and member-function names
+// on top of the C ABI (include/llb200.h).
+//
+// The reference has no plugin interface; its boundary is the set of member functions of two
+// monolithic classes that communicate through members:
+//   class mapOptimization   (LeGO-LOAM/src/mapOptmization.cpp:49)
+//   class FeatureAssociation (LeGO-LOAM/src/featureAssociation.cpp:37)
+// The classes below keep those method names / signatures and the pcl::PointCloud<PointType>::Ptr
+// members the hot path reads and writes, so a maintainer swaps the bodies of the hot methods for a
+// call into the matching adapter method (INTEGRATION.md shows the exact patch).
+//
+// Error behaviour mirrors the reference: no exceptions, failures are silent skips that leave
+// the pose untouched (guards MO:1331, MO:1238, FA:1668); the last C-ABI status is kept in
+// `last_status` for callers that want to look.  There is no CPU fallback: if the CUDA library
+// cannot create a context the constructor throws std::runtime_error.
+#pragma once
+#include "../../include/llb200.h"
+#include "compat/pcl/llb_pcl_compat.h"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace lego_loam_b200 {
+
+typedef pcl::PointXYZI PointType;                       // UT:51
+typedef pcl::PointCloud<PointType> Cloud;
+
+static_assert(sizeof(PointType) == sizeof(llb_point), "llb_point must alias pcl::PointXYZI");
+
+inline const llb_point *as_llb(const Cloud &c) { return reinterpret_cast<const llb_point *>(c.points.data()); }
+inline llb_point *as_llb(Cloud &c) { return reinterpret_cast<llb_point *>(c.points.data()); }
+
+// ---------------------------------------------------------------------------------------------
+// mapOptimization: downsampleCurrentScan / cornerOptimization / surfOptimization /
+// LMOptimization / scan2MapOptimization (MO:1067-1350) + the map voxel tail MO:1057-1064
+// ---------------------------------------------------------------------------------------------
+class mapOptimization {
+public:
+    // members with the reference's names (MO:109-126, MO:173-178, MO:202-210)
+    Cloud::Ptr laserCloudCornerLast, laserCloudSurfLast, laserCloudOutlierLast;
+    Cloud::Ptr laserCloudCornerLastDS, laserCloudSurfLastDS, laserCloudOutlierLastDS;
+    Cloud::Ptr laserCloudSurfTotalLast, laserCloudSurfTotalLastDS;
+    Cloud::Ptr laserCloudOri, coeffSel;
+    Cloud::Ptr laserCloudCornerFromMap, laserCloudSurfFromMap, laserCloudCornerFromMapDS, laserCloudSurfFromMapDS;
+    float transformTobeMapped[6], transformSum[6], transformBefMapped[6], transformAftMapped[6];
+    bool isDegenerate;
+    float matP[36];
+    int laserCloudCornerFromMapDSNum, laserCloudSurfFromMapDSNum;
+    int laserCloudCornerLastDSNum, laserCloudSurfLastDSNum, laserCloudOutlierLastDSNum, laserCloudSurfTotalLastDSNum;
+    // adapter knobs
+    bool fetch_downsampled_clouds = true;   // copy the *DS clouds back to the host members (key-frame store needs them)
+    int last_status = LLB_OK;
+    llb_stats last_stats;
+
+    explicit mapOptimization(int device = 0, const llb_params *params = nullptr)
+    {
+        for (Cloud::Ptr *p : { &laserCloudCornerLast, &laserCloudSurfLast, &laserCloudOutlierLast, &laserCloudCornerLastDS,
+                               &laserCloudSurfLastDS, &laserCloudOutlierLastDS, &laserCloudSurfTotalLast,
+                               &laserCloudSurfTotalLastDS, &laserCloudOri, &coeffSel, &laserCloudCornerFromMap,
+                               &laserCloudSurfFromMap, &laserCloudCornerFromMapDS, &laserCloudSurfFromMapDS })
+            p->reset(new Cloud());
+        for (int i = 0; i < 6; i++) transformTobeMapped[i] = transformSum[i] = transformBefMapped[i] = transformAftMapped[i] = 0;
+        isDegenerate = false;
+        std::memset(matP, 0, sizeof matP);
+        std::memset(&last_stats, 0, sizeof last_stats);
+        laserCloudCornerFromMapDSNum = laserCloudSurfFromMapDSNum = 0;
+        laserCloudCornerLastDSNum = laserCloudSurfLastDSNum = laserCloudOutlierLastDSNum = laserCloudSurfTotalLastDSNum = 0;
+        int rc = llb_create(params, device, &ctx_);
+        if (rc != LLB_OK) throw std::runtime_error("lego_loam_b200: llb_create failed (no CUDA device / no CPU fallback)");
+    }
+    ~mapOptimization() { llb_destroy(ctx_); }
+    mapOptimization(const mapOptimization &) = delete;
+    mapOptimization &operator=(const mapOptimization &) = delete;
+
+    // tail of extractSurroundingKeyFrames, MO:1057-1064: two voxel filters on the raw local map.
+    // The DS map stays on the device (index built); it is copied back only if asked.
+    void downsampleSurroundingMap(bool fetch = false)
+    {
+        last_status = llb_map_set_raw(ctx_, as_llb(*laserCloudCornerFromMap), (int)laserCloudCornerFromMap->size(),
+                                      as_llb(*laserCloudSurfFromMap), (int)laserCloudSurfFromMap->size());
+        if (last_status != LLB_OK) return;
+        llb_map_get_ds(ctx_, 0, nullptr, 0, &laserCloudCornerFromMapDSNum);
+        llb_map_get_ds(ctx_, 1, nullptr, 0, &laserCloudSurfFromMapDSNum);
+        map_on_device_ = true;
+        if (fetch) {
+            fetch_cloud(&llb_map_get_ds, 0, *laserCloudCornerFromMapDS);
+            fetch_cloud(&llb_map_get_ds, 1, *laserCloudSurfFromMapDS);
+        }
+    }
+
+    void downsampleCurrentScan()                                   // MO:1067
+    {
+        last_status = llb_scan_set(ctx_, as_llb(*laserCloudCornerLast), (int)laserCloudCornerLast->size(),
+                                   as_llb(*laserCloudSurfLast), (int)laserCloudSurfLast->size(),
+                                   as_llb(*laserCloudOutlierLast), (int)laserCloudOutlierLast->size());
+        if (last_status != LLB_OK) return;
+        int counts[4] = { 0, 0, 0, 0 };
+        last_status = llb_downsample_current_scan(ctx_, counts);
+        if (last_status != LLB_OK) return;
+        laserCloudCornerLastDSNum = counts[0]; laserCloudSurfLastDSNum = counts[1];
+        laserCloudOutlierLastDSNum = counts[2]; laserCloudSurfTotalLastDSNum = counts[3];
+        if (fetch_downsampled_clouds) {
+            fetch_cloud(&llb_scan_get_ds, 0, *laserCloudCornerLastDS);
+            fetch_cloud(&llb_scan_get_ds, 1, *laserCloudSurfLastDS);
+            fetch_cloud(&llb_scan_get_ds, 2, *laserCloudOutlierLastDS);
+            fetch_cloud(&llb_scan_get_ds, 3, *laserCloudSurfTotalLastDS);
+        }
+    }
+
+    // cornerOptimization + surfOptimization + LMOptimization are one fused device iteration; the three
+    // reference entry points are kept: the first two stage the iteration, LMOptimization runs it.
+    void cornerOptimization(int /*iterCount*/) { staged_ |= 1; }    // MO:1093
+    void surfOptimization(int /*iterCount*/) { staged_ |= 2; }      // MO:1176
+    bool LMOptimization(int iterCount)                              // MO:1229, returns true when converged
+    {
+        staged_ = 0;
+        if (!ensure_map()) return false;
+        int conv = 0, n = 0;
+        last_status = llb_s2m_iterate(ctx_, transformTobeMapped, iterCount, &conv, &n);
+        if (last_status != LLB_OK) return false;
+        pull_correspondences();
+        pull_degeneracy();
+        return conv != 0;
+    }
+
+    void scan2MapOptimization()                                     // MO:1329
+    {
+        if (laserCloudCornerFromMapDSNum > 10 && laserCloudSurfFromMapDSNum > 100) {
+            if (!ensure_map()) return;                              // MO:1333-1334 (index build)
+            last_status = llb_s2m_optimize(ctx_, transformTobeMapped, &last_stats);   // MO:1336-1346
+            if (last_status != LLB_OK) return;
+            pull_degeneracy();
+            transformUpdate();                                      // MO:1348
+        }
+    }
+
+    void transformUpdate()                                          // MO:463-496 without IMU messages (C15, C23)
+    {
+        for (int i = 0; i < 6; i++) { transformBefMapped[i] = transformSum[i]; transformAftMapped[i] = transformTobeMapped[i]; }
+    }
+
+    // call when laserCloud*FromMapDS were (re)filled on the host by the caller
+    void mapChanged() { map_on_device_ = false; }
+    llb_ctx *context() { return ctx_; }
+
+private:
+    typedef int (*get_fn)(llb_ctx *, int, llb_point *, int, int *);
+    void fetch_cloud(get_fn fn, int which, Cloud &out)
+    {
+        int n = 0;
+        if (fn(ctx_, which, nullptr, 0, &n) != LLB_OK) return;
+        out.resize(n);
+        if (n > 0) fn(ctx_, which, as_llb(out), n, &n);
+    }
+    bool ensure_map()
+    {
+        if (map_on_device_) return true;
+        laserCloudCornerFromMapDSNum = (int)laserCloudCornerFromMapDS->size();
+        laserCloudSurfFromMapDSNum = (int)laserCloudSurfFromMapDS->size();
+        last_status = llb_map_set_ds(ctx_, as_llb(*laserCloudCornerFromMapDS), laserCloudCornerFromMapDSNum,
+                                     as_llb(*laserCloudSurfFromMapDS), laserCloudSurfFromMapDSNum);
+        map_on_device_ = (last_status == LLB_OK);
+        return map_on_device_;
+    }
+    void pull_correspondences()
+    {
+        int n = 0;
+        if (llb_get_correspondences(ctx_, nullptr, nullptr, 0, &n) != LLB_OK) { laserCloudOri->clear(); coeffSel->clear(); return; }
+        laserCloudOri->resize(n); coeffSel->resize(n);
+        if (n > 0) llb_get_correspondences(ctx_, as_llb(*laserCloudOri), as_llb(*coeffSel), n, &n);
+    }
+    void pull_degeneracy()
+    {
+        int d = 0;
+        if (llb_get_degeneracy(ctx_, &d, matP) == LLB_OK) isDegenerate = d != 0;
+    }
+    llb_ctx *ctx_ = nullptr;
+    bool map_on_device_ = false;
+    int staged_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// FeatureAssociation: findCorresponding{Corner,Surf}Features / calculateTransformation{Surf,Corner}
+// / updateTransformation (FA:1044-1478, FA:1666-1695)
+// ---------------------------------------------------------------------------------------------
+class FeatureAssociation {
+public:
+    Cloud::Ptr cornerPointsSharp, surfPointsFlat;                  // FA:56-58
+    Cloud::Ptr laserCloudCornerLast, laserCloudSurfLast;           // FA:161-162
+    Cloud::Ptr laserCloudOri, coeffSel;                            // FA:163-164
+    float transformCur[6];                                         // FA:154
+    int laserCloudCornerLastNum, laserCloudSurfLastNum;            // FA:142-143
+    bool isDegenerate;                                             // FA:179
+    float matP[9];
+    int last_status = LLB_OK;
+    llb_stats stats_surf, stats_corner;
+
+    explicit FeatureAssociation(int device = 0, const llb_params *params = nullptr)
+    {
+        for (Cloud::Ptr *p : { &cornerPointsSharp, &surfPointsFlat, &laserCloudCornerLast, &laserCloudSurfLast, &laserCloudOri, &coeffSel })
+            p->reset(new Cloud());
+        for (int i = 0; i < 6; i++) transformCur[i] = 0;
+        laserCloudCornerLastNum = laserCloudSurfLastNum = 0;
+        isDegenerate = false;
+        std::memset(matP, 0, sizeof matP);
+        std::memset(&stats_surf, 0, sizeof stats_surf); std::memset(&stats_corner, 0, sizeof stats_corner);
+        if (llb_create(params, device, &ctx_) != LLB_OK)
+            throw std::runtime_error("lego_loam_b200: llb_create failed (no CUDA device / no CPU fallback)");
+    }
+    ~FeatureAssociation() { llb_destroy(ctx_); }
+    FeatureAssociation(const FeatureAssociation &) = delete;
+    FeatureAssociation &operator=(const FeatureAssociation &) = delete;
+
+    // replaces the two kdtree->setInputCloud calls of FA:1615-1616 / FA:1786-1787
+    void setLastClouds()
+    {
+        laserCloudCornerLastNum = (int)laserCloudCornerLast->size();
+        laserCloudSurfLastNum = (int)laserCloudSurfLast->size();
+        last_status = llb_odom_set_last(ctx_, as_llb(*laserCloudCornerLast), laserCloudCornerLastNum,
+                                        as_llb(*laserCloudSurfLast), laserCloudSurfLastNum);
+    }
+
+    void findCorrespondingSurfFeatures(int iterCount) { staged_which_ = 0; staged_iter_ = iterCount; push_features(); }     // FA:1155
+    void findCorrespondingCornerFeatures(int iterCount) { staged_which_ = 1; staged_iter_ = iterCount; push_features(); }   // FA:1044
+    // return value as in the reference: FALSE when converged (C8)
+    bool calculateTransformationSurf(int iterCount) { return step(0, iterCount); }       // FA:1270
+    bool calculateTransformationCorner(int iterCount) { return step(1, iterCount); }     // FA:1379
+
+    void updateTransformation()                                                          // FA:1666
+    {
+        if (laserCloudCornerLastNum < 10 || laserCloudSurfLastNum < 100) return;
+        push_features();
+        last_status = llb_odom_optimize(ctx_, transformCur, &stats_surf, &stats_corner);
+        if (last_status != LLB_OK) return;
+        int d = 0;
+        if (llb_odom_get_degeneracy(ctx_, &d, matP) == LLB_OK) isDegenerate = d != 0;
+    }
+    llb_ctx *context() { return ctx_; }
+
+private:
+    void push_features()
+    {
+        last_status = llb_odom_set_features(ctx_, as_llb(*cornerPointsSharp), (int)cornerPointsSharp->size(),
+                                            as_llb(*surfPointsFlat), (int)surfPointsFlat->size());
+    }
+    bool step(int which, int iterCount)
+    {
+        int more = 1, n = 0;
+        last_status = llb_odom_iterate(ctx_, which, transformCur, iterCount, &more, &n);
+        if (last_status != LLB_OK) return true;
+        int m = 0;
+        if (llb_odom_get_correspondences(ctx_, nullptr, nullptr, 0, &m) == LLB_OK) {
+            laserCloudOri->resize(m); coeffSel->resize(m);
+            if (m > 0) llb_odom_get_correspondences(ctx_, as_llb(*laserCloudOri), as_llb(*coeffSel), m, &m);
+        }
+        int d = 0;
+        if (llb_odom_get_degeneracy(ctx_, &d, matP) == LLB_OK) isDegenerate = d != 0;
+        return more != 0;
+    }
+    llb_ctx *ctx_ = nullptr;
+    int staged_which_ = 0, staged_iter_ = 0;
+};
+
+}  // namespace lego_loam_b200

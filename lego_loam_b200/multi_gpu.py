@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing for the hot path (torch.distributed is plumbing, not the product).
+
+Two cases:
+* independent sequences / scans (BASELINE config 5): replicas, one process per GPU, no collective;
+* one registration against a large map (BASELINE config 4): the queries of the scan are sharded
+  round-robin over the ranks (query i belongs to rank i % world), every rank holds the whole
+  voxel-DS map (2M points = 32 MB), and the only exchange per LM iteration is an all-reduce(sum)
+  of 28 fp64 values (21 upper-triangular J^T J terms, 6 J^T r terms, the row count).  Every rank
+  then performs the identical 6x6 LM step redundantly, so no broadcast is needed.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+N_ACC = 28
+
+
+def shard_queries(n_queries: int, rank: int, world: int) -> np.ndarray:
+    """Indices of the queries rank `rank` accumulates (the kernel's qi = rank + world * j)."""
+    return np.arange(rank, n_queries, world)
+
+
+def pair_table():
+    """(ia, ib) of the 28 accumulated products of v = {J0..J5, b, 1} (same order as the kernel)."""
+    pairs = [(i, j) for i in range(6) for j in range(i, 6)]
+    pairs += [(i, 6) for i in range(6)]
+    pairs.append((7, 7))
+    return pairs
+
+
+def normal_equations_from_sums(acc: np.ndarray):
+    """28 fp64 sums -> (AtA float32 6x6, AtB float32 6, n_rows): one rounding, like cv::gemm."""
+    acc = np.asarray(acc, np.float64)
+    A = np.zeros((6, 6), np.float32)
+    k = 0
+    for i in range(6):
+        for j in range(i, 6):
+            A[i, j] = A[j, i] = np.float32(acc[k]); k += 1
+    B = acc[21:27].astype(np.float32)
+    return A, B, int(acc[27])
+
+
+def partial_sums(rows: np.ndarray) -> np.ndarray:
+    """fp64 partial sums of the 28 products over `rows` (n,7) = {J0..J5, b} float32."""
+    v = np.concatenate([rows.astype(np.float64), np.ones((rows.shape[0], 1))], axis=1)
+    return np.array([np.sum(v[:, a] * v[:, b]) for a, b in pair_table()], np.float64)
+
+
+def reduce_normal_equations(acc, group=None):
+    """all-reduce(sum) of the 28-value accumulator (torch tensor on any backend: nccl on GPUs, gloo in tests)."""
+    import torch.distributed as dist
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return acc
+
+
+class _DevView:
+    """CUDA array interface view of a raw device pointer (the context's 28-double accumulator)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def sharded_scan2map(ctx, T_init, rank: int, world: int, group=None, max_iterations: int = 10):
+    """scan2MapOptimization (MO:1329-1350) with the queries sharded over `world` ranks.
+
+    ctx must already hold the (replicated) map and the down-sampled scan.  Returns (pose, iterations).
+    """
+    import torch
+    stream = torch.cuda.ExternalStream(ctx.stream, device=ctx.device)
+    ctx.s2m_pose_set(T_init)
+    iters = 0
+    with torch.cuda.stream(stream):
+        for it in range(max_iterations):
+            ptr = ctx.s2m_accumulate(it, rank, world)
+            acc = torch.as_tensor(_DevView(ptr, N_ACC), device=torch.device("cuda", ctx.device))
+            if world > 1:
+                reduce_normal_equations(acc, group)
+            iters += 1
+            if ctx.s2m_solve(it, want_converged=True):
+                break
+    return ctx.s2m_pose_get(), iters

@@ -1,0 +1,65 @@
+"""The C++ adapter classes (reference member-function names over the C ABI) against the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import data
+from tests.test_gpu_parity import _odom_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_adapter_test(tmp_path):
+    exe = str(tmp_path / "host_adapter_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-o", exe, os.path.join(ROOT, "tests", "host_adapter_test.cpp"),
+                           "-L", os.path.join(ROOT, "lego_loam_b200"), "-lllb200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "lego_loam_b200")])
+    return exe
+
+
+def test_adapter_compiles_without_gpu(tmp_path):
+    build_adapter_test(tmp_path)
+
+
+@pytest.mark.gpu
+def test_adapter_matches_oracle(tmp_path):
+    exe = build_adapter_test(tmp_path)
+    case = data.mapping_case(2)
+    od = _odom_case(2)
+    path = str(tmp_path / "case.bin")
+    with open(path, "wb") as f:
+        def w(c):
+            c = np.ascontiguousarray(c, np.float32)
+            f.write(struct.pack("i", c.shape[0])); f.write(c.tobytes())
+        for c in (case["map_corner_raw"], case["map_surf_raw"], case["corner"], case["surf"], case["outlier"]):
+            w(c)
+        f.write(np.ascontiguousarray(case["init"], np.float32).tobytes())
+        for c in (od.corner_last, od.surf_last, od.corner_sharp, od.surf_flat):
+            w(c)
+    out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
+    mo_line = out[0].split(); fa_line = out[1].split()
+
+    oracle.set_trig_mode(1)
+    mo = oracle.MapOptimization()
+    mo.set_map_raw(case["map_corner_raw"], case["map_surf_raw"])
+    mo.set_scan(case["corner"], case["surf"], case["outlier"])
+    mo.downsampleCurrentScan()
+    mo.transformTobeMapped = case["init"]
+    iters = mo.scan2MapOptimization()
+    assert [int(x) for x in mo_line[1:5]] == [mo.scan_ds(i).shape[0] for i in range(4)]
+    assert int(mo_line[5]) == iters
+    assert np.allclose(np.array(mo_line[7:13], np.float32), mo.transformTobeMapped, atol=1e-6)
+    assert int(mo_line[13]) == mo.scan_ds(3).shape[0]
+
+    fa = oracle.FeatureAssociation()
+    fa.set_last(od.corner_last, od.surf_last, force=True)
+    fa.set_features(od.corner_sharp, od.surf_flat)
+    fa.transformCur = np.zeros(6, np.float32)
+    it1, it2 = fa.updateTransformation()
+    assert (int(fa_line[1]), int(fa_line[2])) == (it1, it2)
+    assert np.allclose(np.array(fa_line[3:9], np.float32), fa.transformCur, atol=1e-5)
+    oracle.set_trig_mode(0)
