@@ -170,8 +170,8 @@ void build_indices(llb_ctx *c)
     const float radius = std::sqrt(c->prm.knn_max_sqdist);
     const int *nc = c->map_counts_on_dev ? c->counts.p + llb_ctx::C_MAP_CORNER_DS : nullptr;
     const int *ns = c->map_counts_on_dev ? c->counts.p + llb_ctx::C_MAP_SURF_DS : nullptr;
-    c->launches += c->gridCorner.build(c->mapCornerDS_view, nc, c->mapCornerDS_upper, radius, c->stream);
-    c->launches += c->gridSurf.build(c->mapSurfDS_view, ns, c->mapSurfDS_upper, radius, c->stream);
+    c->launches += GridIndex::build_pair(c->gridCorner, c->mapCornerDS_view, nc, c->mapCornerDS_upper,
+                                         c->gridSurf, c->mapSurfDS_view, ns, c->mapSurfDS_upper, radius, c->stream);
     c->map_set = true;
 }
 

@@ -1,7 +1,11 @@
-// grid_index.cu — K2 build kernels: bounds -> grid set-up -> per-cell counts (one atomic
-// per point, the returned value is the point's slot inside its cell) -> exclusive scan of
-// the dense cell table -> scatter into cell order.  Everything is sized on the device;
-// the host only knows upper bounds, so nothing synchronises.
+// grid_index.cu — K2 build kernels.  Both maps of a registration (corner, surf) are built by
+// the SAME five launches (blockIdx.y selects the map):
+//   1 bounds           (+ the last CTA to finish derives the grid: origin, cell size, dims)
+//   2 per-cell counts  (one atomic per point; the value it returns is the point's slot in its cell)
+//   3 tile sums of the dense count table (+ the last CTA scans the tile sums)
+//   4 exclusive scan of the count table -> cell_begin
+//   5 scatter into cell order (+ re-zeroes the count table for the next build)
+// Everything is sized on the device; the host only knows upper bounds, so nothing synchronises.
 #include "grid_index.cuh"
 
 namespace llb {
@@ -11,50 +15,24 @@ namespace {
 constexpr int TPB = 256;
 constexpr int SCAN_TILE = 4096;     // 1024 threads x 4
 
+struct GridJob {
+    const float4 *pts; const int *n_dev; int n_host;
+    GridDesc *desc; int *counts; int *cell_begin; int *cell_of; int *rank; int *blk; float4 *sorted;
+};
+struct GridJobs { GridJob j[2]; float radius; int max_cells; };
+
 __global__ void grid_desc_init_kernel(GridDesc *d)
 {
     for (int a = 0; a < 3; a++) { d->mn[a] = INT_MAX; d->mx[a] = INT_MIN; }
-    d->ncell = 0; d->n = 0;
+    d->ncell = 0; d->n = 0; d->ticket = 0;
 }
 
-__global__ void __launch_bounds__(TPB)
-grid_bbox_kernel(const float4 *__restrict__ pts, const int *n_dev, int n_host, GridDesc *__restrict__ d)
+__device__ void grid_setup(GridDesc *d, int n, float radius, int max_cells)
 {
-    __shared__ float s_red[6][TPB / 32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int n = n_dev ? *n_dev : n_host;
-    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (int i = blockIdx.x * TPB + tid; i < n; i += gridDim.x * TPB) {
-        float4 p = __ldg(&pts[i]);
-        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
-        }
-        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
-    }
-    __syncthreads();
-    if (tid < 3 && n > 0) {
-        float m0 = s_red[tid][0], m1 = s_red[3 + tid][0];
-        for (int k = 1; k < TPB / 32; k++) { m0 = fminf(m0, s_red[tid][k]); m1 = fmaxf(m1, s_red[3 + tid][k]); }
-        atomicMin(&d->mn[tid], float_to_ordered(m0));
-        atomicMax(&d->mx[tid], float_to_ordered(m1));
-    }
-}
-
-__global__ void grid_setup_kernel(GridDesc *d, const int *n_dev, int n_host, float radius, int max_cells)
-{
-    const int n = n_dev ? *n_dev : n_host;
     float mn[3], mx[3];
     for (int a = 0; a < 3; a++) {
         mn[a] = ordered_to_float(d->mn[a]); mx[a] = ordered_to_float(d->mx[a]);
-        d->mn[a] = INT_MAX; d->mx[a] = INT_MIN;
+        d->mn[a] = INT_MAX; d->mx[a] = INT_MIN;               // ready for the next build
     }
     d->n = n;
     if (n <= 0) {
@@ -77,112 +55,161 @@ __global__ void grid_setup_kernel(GridDesc *d, const int *n_dev, int n_host, flo
             d->ncell = (int)tot;
             return;
         }
-        cell *= 1.26f;                                   // ~ doubles the cell volume
+        cell *= 1.26f;                                       // ~ doubles the cell volume
     }
-    // unreachable for finite bounds; fall back to one cell (brute force)
-    d->cell = 3.0e38f; d->inv_cell = 0.f; d->ncell = 1;
+    d->cell = 3.0e38f; d->inv_cell = 0.f; d->ncell = 1;      // unreachable for finite bounds: one cell
     for (int a = 0; a < 3; a++) { d->dim[a] = 1; d->org[a] = mn[a]; }
 }
 
 __global__ void __launch_bounds__(TPB)
-grid_clear_kernel(const GridDesc *__restrict__ d, int *__restrict__ table)
+grid_bbox_kernel(GridJobs jobs)
 {
-    const int m = d->ncell + 1;
-    for (int i = blockIdx.x * TPB + threadIdx.x; i < m; i += gridDim.x * TPB) table[i] = 0;
+    const GridJob &jb = jobs.j[blockIdx.y];
+    GridDesc *d = jb.desc;
+    __shared__ float s_red[6][TPB / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n = jb.n_dev ? *jb.n_dev : jb.n_host;
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int i = blockIdx.x * TPB + tid; i < n; i += gridDim.x * TPB) {
+        float4 p = __ldg(&jb.pts[i]);
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+        }
+        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
+    }
+    __syncthreads();
+    if (tid < 3 && n > 0) {
+        float m0 = s_red[tid][0], m1 = s_red[3 + tid][0];
+        for (int k = 1; k < TPB / 32; k++) { m0 = fminf(m0, s_red[tid][k]); m1 = fmaxf(m1, s_red[3 + tid][k]); }
+        atomicMin(&d->mn[tid], float_to_ordered(m0));
+        atomicMax(&d->mx[tid], float_to_ordered(m1));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&d->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        d->ticket = 0;
+        grid_setup(d, n, jobs.radius, jobs.max_cells);
+    }
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __global__ void __launch_bounds__(TPB)
-grid_count_kernel(const float4 *__restrict__ pts, const GridDesc *__restrict__ d, int *__restrict__ counts,
-                  int *__restrict__ cell_of, int *__restrict__ rank)
+grid_count_kernel(GridJobs jobs)
 {
+    const GridJob &jb = jobs.j[blockIdx.y];
+    const GridDesc *d = jb.desc;
     const int n = d->n;
     const float ox = d->org[0], oy = d->org[1], oz = d->org[2], inv = d->inv_cell;
     const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-        float4 p = __ldg(&pts[i]);
+        float4 p = __ldg(&jb.pts[i]);
         int cx = clampi(grid_coord(p.x, ox, inv), 0, dx - 1);
         int cy = clampi(grid_coord(p.y, oy, inv), 0, dy - 1);
         int cz = clampi(grid_coord(p.z, oz, inv), 0, dz - 1);
         int c = (cz * dy + cy) * dx + cx;
-        cell_of[i] = c;
-        rank[i] = atomicAdd(&counts[c], 1);
+        jb.cell_of[i] = c;
+        jb.rank[i] = atomicAdd(&jb.counts[c], 1);
     }
 }
 
+// tile sums of counts[0 .. ncell]; the last CTA turns them into exclusive offsets
 __global__ void __launch_bounds__(1024)
-scan_tile_sum_kernel(const GridDesc *__restrict__ d, const int *__restrict__ data, int *__restrict__ blk)
+scan_tile_sum_kernel(GridJobs jobs)
 {
+    const GridJob &jb = jobs.j[blockIdx.y];
+    GridDesc *d = jb.desc;
+    __shared__ int s_w[33];
+    __shared__ int s_last;
     const int m = d->ncell + 1;
     const int base = blockIdx.x * SCAN_TILE;
-    if (base >= m) {
-        if (threadIdx.x == 0) blk[blockIdx.x] = 0;
-        return;
-    }
     int s = 0;
+    if (base < m) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int i = base + k * 1024 + threadIdx.x;
-        if (i < m) s += data[i];
+        for (int k = 0; k < 4; k++) {
+            int i = base + k * 1024 + threadIdx.x;
+            if (i < m) s += jb.counts[i];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    __shared__ int s_w[32];
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
         int v = s_w[threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (threadIdx.x == 0) blk[blockIdx.x] = v;
+        if (threadIdx.x == 0) {
+            jb.blk[blockIdx.x] = v;
+            __threadfence();
+            s_last = (atomicAdd(&d->ticket, 1u) == gridDim.x - 1);
+        }
     }
-}
-
-__global__ void __launch_bounds__(1024)
-scan_blocks_kernel(int *__restrict__ blk, int count)
-{
-    __shared__ int s_scan[33];
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) d->ticket = 0;
+    // exclusive scan of the gridDim.x tile sums by this CTA
+    const int count = gridDim.x;
     const int per = (count + 1023) / 1024;
     const int lo = min((int)threadIdx.x * per, count), hi = min(lo + per, count);
     int sum = 0;
-    for (int i = lo; i < hi; i++) sum += blk[i];
+    for (int i = lo; i < hi; i++) sum += __ldcg(&jb.blk[i]);
     int total;
-    int base = block_excl_scan(sum, s_scan, total);
-    for (int i = lo; i < hi; i++) { int v = blk[i]; blk[i] = base; base += v; }
+    int ex = block_excl_scan(sum, s_w, total);
+    for (int i = lo; i < hi; i++) { int v = __ldcg(&jb.blk[i]); jb.blk[i] = ex; ex += v; }
 }
 
 __global__ void __launch_bounds__(1024)
-scan_tile_apply_kernel(const GridDesc *__restrict__ d, int *__restrict__ data, const int *__restrict__ blk)
+scan_tile_apply_kernel(GridJobs jobs)
 {
+    const GridJob &jb = jobs.j[blockIdx.y];
     __shared__ int s_scan[33];
-    const int m = d->ncell + 1;
+    const int m = jb.desc->ncell + 1;
     const int base = blockIdx.x * SCAN_TILE;
     if (base >= m) return;
-    // thread owns 4 CONSECUTIVE entries
-    const int i0 = base + threadIdx.x * 4;
+    const int i0 = base + threadIdx.x * 4;                   // thread owns 4 CONSECUTIVE entries
     int v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (i0 + k < m) ? data[i0 + k] : 0;
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < m) ? jb.counts[i0 + k] : 0;
     int total;
-    int ex = blk[blockIdx.x] + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_scan, total);
+    int ex = jb.blk[blockIdx.x] + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_scan, total);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (i0 + k < m) data[i0 + k] = ex;
+        if (i0 + k < m) jb.cell_begin[i0 + k] = ex;
         ex += v[k];
     }
 }
 
 __global__ void __launch_bounds__(TPB)
-grid_scatter_kernel(const float4 *__restrict__ pts, const GridDesc *__restrict__ d, const int *__restrict__ cell_begin,
-                    const int *__restrict__ cell_of, const int *__restrict__ rank, float4 *__restrict__ sorted)
+grid_scatter_kernel(GridJobs jobs)
 {
+    const GridJob &jb = jobs.j[blockIdx.y];
+    const GridDesc *d = jb.desc;
     const int n = d->n;
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-        float4 p = __ldg(&pts[i]);
-        int pos = cell_begin[cell_of[i]] + rank[i];
-        sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        float4 p = __ldg(&jb.pts[i]);
+        const int c = jb.cell_of[i];
+        jb.sorted[jb.cell_begin[c] + jb.rank[i]] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        jb.counts[c] = 0;                                    // leave the count table clean for the next build
     }
+}
+
+__global__ void grid_zero_kernel(int *p, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
 }
 
 }  // namespace
@@ -191,33 +218,49 @@ void GridIndex::init(int max_cells)
 {
     max_cells_ = max_cells > 4096 ? max_cells : 4096;
     desc_.ensure(1);
+    counts_.ensure((size_t)max_cells_ + 1);
     cell_begin_.ensure((size_t)max_cells_ + 1);
     blk_.ensure((size_t)div_up(max_cells_ + 1, SCAN_TILE) + 1);
     grid_desc_init_kernel<<<1, 1>>>(desc_.p);
+    grid_zero_kernel<<<148 * 4, 256>>>(counts_.p, max_cells_ + 1);
     LLB_CUDA(cudaGetLastError());
 }
 
 void GridIndex::release()
 {
-    desc_.release(); sorted_.release(); cell_begin_.release(); cell_of_.release(); rank_.release(); blk_.release();
+    desc_.release(); sorted_.release(); counts_.release(); cell_begin_.release(); cell_of_.release(); rank_.release();
+    blk_.release();
 }
 
-int GridIndex::build(const float4 *pts, const int *n_dev, int n_upper, float radius, cudaStream_t s)
+int GridIndex::build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int na_upper,
+                          GridIndex &b, const float4 *pb, const int *nb_dev, int nb_upper, float radius, cudaStream_t s)
 {
-    const int n = n_upper > 0 ? n_upper : 1;
-    sorted_.ensure(n); cell_of_.ensure(n); rank_.ensure(n);
-    const int grid_pts = std::min(div_up(n, TPB), 148 * 8);
-    const int nblk_scan = div_up(max_cells_ + 1, SCAN_TILE);
-    grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(pts, n_dev, n_upper, desc_.p);
-    grid_setup_kernel<<<1, 1, 0, s>>>(desc_.p, n_dev, n_upper, radius, max_cells_);
-    grid_clear_kernel<<<148 * 8, TPB, 0, s>>>(desc_.p, cell_begin_.p);
-    grid_count_kernel<<<grid_pts, TPB, 0, s>>>(pts, desc_.p, cell_begin_.p, cell_of_.p, rank_.p);
-    scan_tile_sum_kernel<<<nblk_scan, 1024, 0, s>>>(desc_.p, cell_begin_.p, blk_.p);
-    scan_blocks_kernel<<<1, 1024, 0, s>>>(blk_.p, nblk_scan);
-    scan_tile_apply_kernel<<<nblk_scan, 1024, 0, s>>>(desc_.p, cell_begin_.p, blk_.p);
-    grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(pts, desc_.p, cell_begin_.p, cell_of_.p, rank_.p, sorted_.p);
+    GridIndex *g[2] = { &a, &b };
+    const float4 *pts[2] = { pa, pb };
+    const int *ndev[2] = { na_dev, nb_dev };
+    const int nup[2] = { na_upper, nb_upper };
+    GridJobs jobs;
+    jobs.radius = radius;
+    jobs.max_cells = std::min(a.max_cells_, b.max_cells_);
+    int nmax = 1;
+    for (int k = 0; k < 2; k++) {
+        const int n = nup[k] > 0 ? nup[k] : 1;
+        nmax = std::max(nmax, n);
+        g[k]->sorted_.ensure(n); g[k]->cell_of_.ensure(n); g[k]->rank_.ensure(n);
+        GridJob &j = jobs.j[k];
+        j.pts = pts[k]; j.n_dev = ndev[k]; j.n_host = nup[k];
+        j.desc = g[k]->desc_.p; j.counts = g[k]->counts_.p; j.cell_begin = g[k]->cell_begin_.p;
+        j.cell_of = g[k]->cell_of_.p; j.rank = g[k]->rank_.p; j.blk = g[k]->blk_.p; j.sorted = g[k]->sorted_.p;
+    }
+    const dim3 grid_pts(std::min(div_up(nmax, TPB), 148 * 4), 2);
+    const dim3 grid_scan(div_up(jobs.max_cells + 1, SCAN_TILE), 2);
+    grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
+    grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
+    scan_tile_sum_kernel<<<grid_scan, 1024, 0, s>>>(jobs);
+    scan_tile_apply_kernel<<<grid_scan, 1024, 0, s>>>(jobs);
+    grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
     LLB_CUDA(cudaGetLastError());
-    return 8;
+    return 5;
 }
 
 }  // namespace llb

@@ -23,6 +23,7 @@ struct GridDesc {            // device-resident
     int dim[3];
     int ncell;
     int n;                   // points indexed
+    unsigned ticket;         // last-CTA election inside the build kernels
 };
 
 struct MapIndexView {        // what the query kernels need (all device pointers)
@@ -35,8 +36,10 @@ class GridIndex {
 public:
     void init(int max_cells);
     void release();
-    // points: n_upper is a host upper bound, n_dev (optional) the device-resident length
-    int build(const float4 *pts, const int *n_dev, int n_upper, float radius, cudaStream_t s);
+    // Builds the indices of two maps with one set of five launches.  n_upper is a host upper
+    // bound, n_dev (optional) the device-resident length.  Returns the number of launches.
+    static int build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int na_upper,
+                          GridIndex &b, const float4 *pb, const int *nb_dev, int nb_upper, float radius, cudaStream_t s);
     MapIndexView view() const { return MapIndexView{ sorted_.p, cell_begin_.p, desc_.p }; }
     const GridDesc *desc_dev() const { return desc_.p; }
 
@@ -44,7 +47,8 @@ private:
     int max_cells_ = 1 << 23;
     DevBuf<GridDesc> desc_;
     DevBuf<float4> sorted_;
-    DevBuf<int> cell_begin_;   // counts, then scanned in place
+    DevBuf<int> counts_;       // dense per-cell counts (kept zero between builds)
+    DevBuf<int> cell_begin_;   // exclusive scan of the counts
     DevBuf<int> cell_of_;      // per point cell id
     DevBuf<int> rank_;         // per point rank inside its cell
     DevBuf<int> blk_;          // scan block sums

@@ -43,32 +43,35 @@ __device__ __forceinline__ bool lex_less(float d1, int i1, float d2, int i2)
     return d1 < d2 || (d1 == d2 && i1 < i2);
 }
 
+// Per-lane sorted top-5.  A candidate is ONE 64-bit key (distance bits << 32 | original index):
+// squared distances are >= 0, so unsigned integer order of the bits is float order and a single
+// unsigned 64-bit compare is the lexicographic (distance, index) order of the oracle.  The
+// insertion is a branch-free compare-exchange chain (no divergence between lanes).
 struct Top5 {
-    float D[5]; int I[5]; int S[5];
+    unsigned long long K[5]; int S[5];
     __device__ __forceinline__ void init()
     {
 #pragma unroll
-        for (int k = 0; k < 5; k++) { D[k] = __int_as_float(0x7f800000); I[k] = INT_MAX; S[k] = -1; }
+        for (int k = 0; k < 5; k++) { K[k] = ~0ull; S[k] = -1; }
     }
     __device__ __forceinline__ void insert(float d, int oi, int pos)
     {
-        if (lex_less(d, oi, D[4], I[4])) {
-            D[4] = d; I[4] = oi; S[4] = pos;
+        unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)oi;
+        const bool in = key < K[4];
+        K[4] = in ? key : K[4]; S[4] = in ? pos : S[4];
 #pragma unroll
-            for (int k = 4; k > 0; k--) {
-                if (lex_less(D[k], I[k], D[k - 1], I[k - 1])) {
-                    float td = D[k]; D[k] = D[k - 1]; D[k - 1] = td;
-                    int ti = I[k]; I[k] = I[k - 1]; I[k - 1] = ti;
-                    int ts = S[k]; S[k] = S[k - 1]; S[k - 1] = ts;
-                }
-            }
+        for (int k = 4; k > 0; k--) {
+            const bool sw = K[k] < K[k - 1];
+            const unsigned long long a = sw ? K[k] : K[k - 1], b = sw ? K[k - 1] : K[k];
+            const int sa = sw ? S[k] : S[k - 1], sb = sw ? S[k - 1] : S[k];
+            K[k - 1] = a; K[k] = b; S[k - 1] = sa; S[k] = sb;
         }
     }
     __device__ __forceinline__ void pop()
     {
 #pragma unroll
-        for (int k = 0; k < 4; k++) { D[k] = D[k + 1]; I[k] = I[k + 1]; S[k] = S[k + 1]; }
-        D[4] = __int_as_float(0x7f800000); I[4] = INT_MAX; S[4] = -1;
+        for (int k = 0; k < 4; k++) { K[k] = K[k + 1]; S[k] = S[k + 1]; }
+        K[4] = ~0ull; S[4] = -1;
     }
 };
 
@@ -108,22 +111,26 @@ __device__ __forceinline__ void knn5_warp(const MapIndexView &m, float qx, float
     Top5 t;
     t.init();
     float4 c[9];
-    int pos[9];
+    int rbv[9], rev[9];
     bool longrun = false;
+    // empty runs (most of the 9 for a query next to a single surface) cost nothing: b, e are warp-uniform
 #pragma unroll
     for (int r = 0; r < 9; r++) {
-        const int b = __shfl_sync(FULL, rb, r), e = __shfl_sync(FULL, re, r);
-        pos[r] = (b + lane < e) ? b + lane : -1;
-        longrun |= (e - b) > 32;
-        if (pos[r] >= 0) c[r] = __ldg(&m.sorted[pos[r]]);
+        rbv[r] = __shfl_sync(FULL, rb, r); rev[r] = __shfl_sync(FULL, re, r);
+        longrun |= (rev[r] - rbv[r]) > 32;
+        if (rev[r] > rbv[r] && rbv[r] + lane < rev[r]) c[r] = __ldg(&m.sorted[rbv[r] + lane]);
     }
 #pragma unroll
-    for (int r = 0; r < 9; r++)
-        if (pos[r] >= 0) t.insert(l2_simple(qx, qy, qz, c[r]), __float_as_int(c[r].w), pos[r]);
+    for (int r = 0; r < 9; r++) {
+        if (rev[r] > rbv[r]) {                               // warp-uniform
+            const bool v = rbv[r] + lane < rev[r];
+            const float d = v ? l2_simple(qx, qy, qz, c[r]) : __int_as_float(0x7f800000);
+            t.insert(d, v ? __float_as_int(c[r].w) : -1, rbv[r] + lane);
+        }
+    }
     if (longrun) {                                           // warp-uniform
         for (int r = 0; r < 9; r++) {
-            const int b = __shfl_sync(FULL, rb, r), e = __shfl_sync(FULL, re, r);
-            for (int i = b + 32 + lane; i < e; i += 32) {
+            for (int i = rbv[r] + 32 + lane; i < rev[r]; i += 32) {
                 float4 p = __ldg(&m.sorted[i]);
                 t.insert(l2_simple(qx, qy, qz, p), __float_as_int(p.w), i);
             }
@@ -132,17 +139,18 @@ __device__ __forceinline__ void knn5_warp(const MapIndexView &m, float qx, float
     // five rounds of warp-wide lexicographic arg-min over the list heads
 #pragma unroll
     for (int r = 0; r < 5; r++) {
-        const unsigned db = __float_as_uint(t.D[0]);          // d >= 0: uint order == float order
+        const unsigned db = (unsigned)(t.K[0] >> 32), di = (unsigned)t.K[0];
         const unsigned mind = __reduce_min_sync(FULL, db);
-        const unsigned ci = (db == mind) ? (unsigned)t.I[0] : 0xffffffffu;
+        const unsigned ci = (db == mind) ? di : 0xffffffffu;
         const unsigned mini = __reduce_min_sync(FULL, ci);
-        const bool win = (db == mind) && ((unsigned)t.I[0] == mini);
+        const bool win = (db == mind) && (di == mini);
         const unsigned ball = __ballot_sync(FULL, win);
         const int src = __ffs(ball) - 1;
         const int p = __shfl_sync(FULL, t.S[0], src);
+        const bool found = mini != 0xffffffffu;
         nd[r] = __uint_as_float(mind);
-        ni[r] = (p >= 0) ? (int)mini : -1;
-        npos[r] = p;
+        ni[r] = found ? (int)mini : -1;
+        npos[r] = found ? p : -1;
         if (lane == src) t.pop();
     }
 }

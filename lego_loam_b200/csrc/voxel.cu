@@ -8,185 +8,11 @@
 // The float arithmetic that decides membership is written exactly as PCL does it
 // (float multiply, floorf, float subtract, int cast) and this file is compiled with
 // -fmad=false, so voxel membership, order and centroids are bit-identical to the oracle.
-#include "voxel.cuh"
+#include "voxel_dev.cuh"
 
 namespace llb {
 
 namespace {
-
-struct SegIn {
-    const float4 *a; const int *na_dev; int na;
-    const float4 *b; const int *nb_dev; int nb;
-};
-
-__device__ __forceinline__ int seg_len_a(const SegIn &s) { return s.na_dev ? *s.na_dev : s.na; }
-__device__ __forceinline__ int seg_len_b(const SegIn &s) { return s.b ? (s.nb_dev ? *s.nb_dev : s.nb) : 0; }
-__device__ __forceinline__ float4 seg_load(const SegIn &s, int na, int i)
-{
-    return i < na ? __ldg(&s.a[i]) : __ldg(&s.b[i - na]);
-}
-
-__host__ SegIn to_seg(const VoxelInput &in)
-{
-    SegIn s;
-    s.a = in.a; s.na_dev = in.na_dev; s.na = in.na;
-    s.b = in.b; s.nb_dev = in.nb_dev; s.nb = in.nb;
-    return s;
-}
-
-// PCL's grid set-up from the cloud bounds (VoxelGrid::applyFilter, A.1 steps 1-3)
-__device__ void voxel_setup(float inv, const float mn[3], const float mx[3], int n,
-                            int min_b[3], int div_b[3], int mul[3], int &overflow, int &nbits)
-{
-    long long d[3];
-    for (int a = 0; a < 3; a++) d[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
-    overflow = (d[0] * d[1] * d[2] > (long long)INT_MAX) ? 1 : 0;
-    for (int a = 0; a < 3; a++) {
-        min_b[a] = (int)floorf(mn[a] * inv);
-        int max_b = (int)floorf(mx[a] * inv);
-        div_b[a] = max_b - min_b[a] + 1;
-    }
-    mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
-    unsigned long long maxkey;
-    if (overflow) maxkey = n > 0 ? (unsigned long long)(n - 1) : 0;       // pass-through: key = index
-    else maxkey = (unsigned long long)div_b[0] * (unsigned long long)div_b[1] * (unsigned long long)div_b[2] - 1;
-    nbits = 1;
-    while (nbits < 32 && (maxkey >> nbits) != 0) nbits++;
-}
-
-__device__ __forceinline__ unsigned voxel_key(const float4 &p, float inv, const int *min_b, const int *mul)
-{
-    int i0 = (int)(floorf(p.x * inv) - (float)min_b[0]);
-    int i1 = (int)(floorf(p.y * inv) - (float)min_b[1]);
-    int i2 = (int)(floorf(p.z * inv) - (float)min_b[2]);
-    return (unsigned)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]);
-}
-
-// ------------------------------------------------------------------ small path
-
-constexpr int SMALL_THREADS = 1024;
-
-struct SmallJobs {
-    SegIn in[VoxelFilter::MAX_BATCH];
-    float leaf[VoxelFilter::MAX_BATCH];
-    float4 *out[VoxelFilter::MAX_BATCH];
-    int *n_out[VoxelFilter::MAX_BATCH];
-};
-
-// one CTA per job (blockIdx.x): independent filters share a launch
-__global__ void __launch_bounds__(SMALL_THREADS, 1)
-voxel_small_kernel(SmallJobs jobs)
-{
-    const SegIn in = jobs.in[blockIdx.x];
-    const float leaf = jobs.leaf[blockIdx.x];
-    float4 *__restrict__ out = jobs.out[blockIdx.x];
-    int *__restrict__ n_out_dev = jobs.n_out[blockIdx.x];
-    extern __shared__ unsigned long long skey[];          // cap_pow2 entries
-    __shared__ float s_red[6][32];
-    __shared__ int s_scan[33];
-    __shared__ float s_inv;
-    __shared__ int s_min_b[3], s_div_b[3], s_mul[3], s_overflow, s_nbits;
-
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int na = seg_len_a(in), n = na + seg_len_b(in);
-    if (n <= 0) {
-        if (tid == 0) *n_out_dev = 0;
-        return;
-    }
-    // power of two >= n (the host sized the shared memory for its upper bound)
-    int P = 32;
-    while (P < n) P <<= 1;
-
-    // ---- bounds
-    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (int i = tid; i < n; i += SMALL_THREADS) {
-        float4 p = seg_load(in, na, i);
-        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
-        }
-        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float fmn[3], fmx[3];
-        for (int a = 0; a < 3; a++) {
-            fmn[a] = s_red[a][0]; fmx[a] = s_red[3 + a][0];
-            for (int k = 1; k < SMALL_THREADS / 32; k++) {
-                fmn[a] = fminf(fmn[a], s_red[a][k]); fmx[a] = fmaxf(fmx[a], s_red[3 + a][k]);
-            }
-        }
-        float inv = 1.0f / leaf;
-        int ovf, nb;
-        voxel_setup(inv, fmn, fmx, n, s_min_b, s_div_b, s_mul, ovf, nb);
-        s_inv = inv; s_overflow = ovf; s_nbits = nb;
-    }
-    __syncthreads();
-    if (s_overflow) {                                      // PCL: output = input
-        for (int i = tid; i < n; i += SMALL_THREADS) out[i] = seg_load(in, na, i);
-        if (tid == 0) *n_out_dev = n;
-        return;
-    }
-    // ---- keys
-    {
-        const float inv = s_inv;
-        int min_b[3] = { s_min_b[0], s_min_b[1], s_min_b[2] }, mul[3] = { s_mul[0], s_mul[1], s_mul[2] };
-        for (int i = tid; i < P; i += SMALL_THREADS) {
-            unsigned long long k = ~0ull;
-            if (i < n) {
-                float4 p = seg_load(in, na, i);
-                k = ((unsigned long long)voxel_key(p, inv, min_b, mul) << 32) | (unsigned)i;
-            }
-            skey[i] = k;
-        }
-    }
-    __syncthreads();
-    // ---- bitonic sort (keys are unique: the low word is the point index => stable)
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += SMALL_THREADS) {
-                int i = 2 * t - (t & (j - 1));
-                int x = i + j;
-                unsigned long long a = skey[i], b = skey[x];
-                bool up = (i & k) == 0;
-                if ((a > b) == up) { skey[i] = b; skey[x] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    // ---- heads: contiguous chunk per thread
-    const int chunk = (n + SMALL_THREADS - 1) / SMALL_THREADS;
-    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
-    int heads = 0;
-    for (int i = lo; i < hi; i++) {
-        unsigned cur = (unsigned)(skey[i] >> 32);
-        heads += (i == 0) || ((unsigned)(skey[i - 1] >> 32) != cur);
-    }
-    int total;
-    int rank = block_excl_scan(heads, s_scan, total);
-    for (int i = lo; i < hi; i++) {
-        unsigned cur = (unsigned)(skey[i] >> 32);
-        if ((i == 0) || ((unsigned)(skey[i - 1] >> 32) != cur)) {
-            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-            int j = i;
-            while (j < n && (unsigned)(skey[j] >> 32) == cur) {
-                float4 p = seg_load(in, na, (int)(unsigned)skey[j]);
-                sx += p.x; sy += p.y; sz += p.z; si += p.w;
-                j++;
-            }
-            float cnt = (float)(j - i);
-            out[rank++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
-        }
-    }
-    if (tid == 0) *n_out_dev = total;
-}
 
 // ------------------------------------------------------------------ large path
 
@@ -438,20 +264,11 @@ int VoxelFilter::run_batch(const VoxelInput *in, const float *leaf, float4 *cons
         }
         return launches;
     }
-    int P = 32;
-    while (P < upper) P <<= 1;
-    size_t smem = (size_t)P * sizeof(unsigned long long);
-    if (!small_attr_set_) {
-        LLB_CUDA(cudaFuncSetAttribute(voxel_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      SMALL_MAX * (int)sizeof(unsigned long long)));
-        small_attr_set_ = true;
-    }
     SmallJobs jobs{};
     for (int j = 0; j < count; j++) {
         jobs.in[j] = to_seg(in[j]); jobs.leaf[j] = leaf[j]; jobs.out[j] = out[j]; jobs.n_out[j] = n_out_dev[j];
     }
-    voxel_small_kernel<<<count, SMALL_THREADS, smem, s>>>(jobs);
-    LLB_CUDA(cudaGetLastError());
+    launch_voxel_small(jobs, count, s);
     return 1;
 }
 

@@ -1,0 +1,207 @@
+// voxel_small.cu — K1, small path: one thread-block CLUSTER (8 CTAs on 8 SMs, distributed
+// shared memory) per pcl::VoxelGrid filter of up to 16384 points -> one launch for the three
+// independent filters of downsampleCurrentScan (MO:1069-1082) and one for the fourth (MO:1084-1090).
+//
+// Why a cluster: the filter is a sort of (voxel index << 32 | point index) followed by ordered
+// per-voxel sums.  On ONE SM the bitonic network is issue-bound (round-1 profile: ~30 us for 8192
+// keys, 66 us per launch); spread over 8 SMs every CTA owns P/8 keys in its own shared memory, the
+// stages with partner distance < P/8 stay CTA-local, and the 6 stages that cross CTAs read the
+// partner's element through DSMEM between two hardware cluster barriers.  Head detection, the scan
+// of the head counts and the segment walks read neighbouring CTAs' keys the same way.
+//
+// Exactness: PCL's key expression, stable order (the low key word is the input index), strictly
+// sequential float sums per voxel, true division by (float)count, int32-overflow pass-through.
+#include "voxel_dev.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace llb {
+
+namespace {
+
+constexpr int CL = 8;                        // CTAs per cluster
+constexpr int TPB = 1024;
+constexpr int LMAX = VoxelFilter::SMALL_MAX / CL;   // keys per CTA
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, 1)
+voxel_small_kernel(SmallJobs jobs)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int job = blockIdx.x / CL;
+    const int cr = (int)cluster.block_rank();
+    const SegIn in = jobs.in[job];
+    const float leaf = jobs.leaf[job];
+    float4 *__restrict__ out = jobs.out[job];
+    int *__restrict__ n_out_dev = jobs.n_out[job];
+
+    __shared__ unsigned long long skey[LMAX];
+    __shared__ float s_red[6][32];
+    __shared__ float s_mm[6];               // this CTA's min xyz, max xyz
+    __shared__ int s_scan[33];
+    __shared__ int s_heads;                 // head count of this CTA
+    __shared__ float s_inv;
+    __shared__ int s_min_b[3], s_div_b[3], s_mul[3], s_overflow, s_nbits;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int na = seg_len_a(in), n = na + seg_len_b(in);
+    if (n <= 0) {                            // uniform over the cluster
+        if (cr == 0 && tid == 0) *n_out_dev = 0;
+        return;
+    }
+    int P = CL * 32;
+    while (P < n) P <<= 1;
+    const int L = P / CL;                    // keys held by each CTA
+    const int g0 = cr * L;                   // first global position of this CTA
+
+    // ---- bounds: CTA-partial over a strided slice, then all-to-all through DSMEM
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int i = cr * TPB + tid; i < n; i += CL * TPB) {
+        float4 p = seg_load(in, na, i);
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+        }
+        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float m = s_red[tid][0];
+        for (int k = 1; k < TPB / 32; k++) m = tid < 3 ? fminf(m, s_red[tid][k]) : fmaxf(m, s_red[tid][k]);
+        s_mm[tid] = m;
+    }
+    cluster.sync();
+    if (tid == 0) {
+        float fmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, fmx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        for (int r = 0; r < CL; r++) {
+            const float *rm = cluster.map_shared_rank(s_mm, r);
+            for (int a = 0; a < 3; a++) { fmn[a] = fminf(fmn[a], rm[a]); fmx[a] = fmaxf(fmx[a], rm[3 + a]); }
+        }
+        float inv = 1.0f / leaf;
+        int ovf, nb;
+        voxel_setup(inv, fmn, fmx, n, s_min_b, s_div_b, s_mul, ovf, nb);
+        s_inv = inv; s_overflow = ovf; s_nbits = nb;
+    }
+    __syncthreads();
+    if (s_overflow) {                        // PCL: output = input (uniform over the cluster: same inputs)
+        for (int i = cr * TPB + tid; i < n; i += CL * TPB) out[i] = seg_load(in, na, i);
+        if (cr == 0 && tid == 0) *n_out_dev = n;
+        cluster.sync();                      // nobody leaves while s_mm may still be read remotely
+        return;
+    }
+    // ---- keys: global position g = g0 + t
+    {
+        const float inv = s_inv;
+        int min_b[3] = { s_min_b[0], s_min_b[1], s_min_b[2] }, mul[3] = { s_mul[0], s_mul[1], s_mul[2] };
+        for (int t = tid; t < L; t += TPB) {
+            const int g = g0 + t;
+            unsigned long long k = ~0ull;
+            if (g < n) {
+                float4 p = seg_load(in, na, g);
+                k = ((unsigned long long)voxel_key(p, inv, min_b, mul) << 32) | (unsigned)g;
+            }
+            skey[t] = k;
+        }
+    }
+    // ---- bitonic sort over the cluster (keys are unique => the result is the stable order)
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < L) {                                         // partner inside this CTA
+                __syncthreads();
+                for (int t = tid; t < (L >> 1); t += TPB) {
+                    const int li = 2 * t - (t & (j - 1));
+                    const int lx = li + j;
+                    const unsigned long long a = skey[li], b = skey[lx];
+                    const bool up = ((g0 + li) & k) == 0;
+                    if ((a > b) == up) { skey[li] = b; skey[lx] = a; }
+                }
+            } else {                                             // partner in CTA cr ^ (j / L), same local slot
+                cluster.sync();
+                const unsigned long long *rk = cluster.map_shared_rank(skey, cr ^ (j / L));
+                unsigned long long nv[LMAX / TPB];
+#pragma unroll
+                for (int u = 0; u < LMAX / TPB; u++) {
+                    const int t = tid + u * TPB;
+                    if (t < L) {
+                        const unsigned long long mine = skey[t], other = rk[t];
+                        const int g = g0 + t;
+                        const bool up = (g & k) == 0, lower = (g & j) == 0;
+                        const bool keep_min = (lower == up);
+                        nv[u] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+                    }
+                }
+                cluster.sync();
+#pragma unroll
+                for (int u = 0; u < LMAX / TPB; u++) {
+                    const int t = tid + u * TPB;
+                    if (t < L) skey[t] = nv[u];
+                }
+            }
+        }
+    }
+    cluster.sync();
+    // ---- heads of this CTA's slice; key at global position g lives in CTA g / L, slot g % L
+    auto key_hi = [&](int g) -> unsigned {
+        const int r = g / L;
+        const unsigned long long *p = (r == cr) ? skey : cluster.map_shared_rank(skey, r);
+        return (unsigned)(p[g - r * L] >> 32);
+    };
+    auto key_lo = [&](int g) -> unsigned {
+        const int r = g / L;
+        const unsigned long long *p = (r == cr) ? skey : cluster.map_shared_rank(skey, r);
+        return (unsigned)p[g - r * L];
+    };
+    const int lcount = max(0, min(L, n - g0));                   // valid keys in this CTA
+    const int chunk = (lcount + TPB - 1) / TPB;
+    const int lo = min(tid * chunk, lcount), hi = min(lo + chunk, lcount);
+    int heads = 0;
+    for (int t = lo; t < hi; t++) {
+        const int g = g0 + t;
+        heads += (g == 0) || (key_hi(g - 1) != (unsigned)(skey[t] >> 32));
+    }
+    int total;
+    int rank = block_excl_scan(heads, s_scan, total);
+    if (tid == 0) s_heads = total;
+    cluster.sync();
+    int base = 0, grand = 0;
+    for (int r = 0; r < CL; r++) {
+        const int c = *cluster.map_shared_rank(&s_heads, r);
+        if (r < cr) base += c;
+        grand += c;
+    }
+    rank += base;
+    for (int t = lo; t < hi; t++) {
+        const int g = g0 + t;
+        const unsigned cur = (unsigned)(skey[t] >> 32);
+        if ((g == 0) || (key_hi(g - 1) != cur)) {
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            int j = g;
+            while (j < n && key_hi(j) == cur) {
+                float4 p = seg_load(in, na, (int)key_lo(j));
+                sx += p.x; sy += p.y; sz += p.z; si += p.w;
+                j++;
+            }
+            const float cnt = (float)(j - g);
+            out[rank++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        }
+    }
+    if (cr == 0 && tid == 0) *n_out_dev = grand;
+    cluster.sync();                          // keep shared memory alive until every remote read is done
+}
+
+}  // namespace
+
+void launch_voxel_small(const SmallJobs &jobs, int count, cudaStream_t stream)
+{
+    voxel_small_kernel<<<count * CL, TPB, 0, stream>>>(jobs);
+    LLB_CUDA(cudaGetLastError());
+}
+
+}  // namespace llb
