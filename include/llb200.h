@@ -172,7 +172,10 @@ int llb_s2m_time_iteration(llb_ctx *ctx, const float T[6], int reps, float *ms_p
 /* clock64 stamps taken by CTA 0 during the last iteration of the persistent scan-to-map
  * kernel: start, end of phase A (kNN), B (fits), C (products), first grid sync, reduction,
  * LM step, second grid sync (SM clock cycles; diagnostics for profiles/) */
-int llb_s2m_get_profile(llb_ctx *ctx, long long stamps[8]);
+int llb_s2m_get_profile(llb_ctx *ctx, int iter, long long stamps[8]);
+/* per-CTA cycles {phase A, phase B, phase C, wait at the first grid barrier} of the last iteration of the
+ * last run: out[4*cta + k]; *n_ctas receives the grid size (diagnostics for profiles/) */
+int llb_s2m_get_cta_profile(llb_ctx *ctx, double *out, int capacity_ctas, int *n_ctas);
 
 /* number of kernels launched by this context since creation (bench.py gpu_launches) */
 long long llb_launch_count(const llb_ctx *ctx);

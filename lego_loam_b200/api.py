@@ -62,7 +62,7 @@ EXPORTS = [
     "llb_odom_get_correspondences", "llb_odom_get_search_ind", "llb_odom_get_degeneracy",
     "llb_map_set_ds_dev", "llb_map_set_raw_dev", "llb_scan_set_dev", "llb_s2m_optimize_dev",
     "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
-    "llb_s2m_time_iteration", "llb_s2m_get_profile",
+    "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
 ]
 
 _lib = None
@@ -315,13 +315,21 @@ class Context:
         self._ck(lib().llb_s2m_time_iteration(self._h, _fp(t), reps, ctypes.byref(ms), ctypes.byref(nq)))
         return float(ms.value), int(nq.value)
 
-    def s2m_get_profile(self):
-        """clock64 stamps of CTA 0 in the last iteration -> cycle deltas per phase"""
+    def s2m_get_profile(self, it: int = 0):
+        """clock64 stamps of CTA 0 in iteration `it` of the last run -> cycle deltas per phase"""
         st = (ctypes.c_longlong * 8)()
-        self._ck(lib().llb_s2m_get_profile(self._h, st))
+        self._ck(lib().llb_s2m_get_profile(self._h, it, st))
         v = list(st)
         names = ["A_knn", "B_fit", "C_products", "sync1", "reduce", "lm_solve", "sync2"]
         return {n: v[i + 1] - v[i] for i, n in enumerate(names)}
+
+    def s2m_get_cta_profile(self) -> np.ndarray:
+        """(n_ctas, 4) cycles {A, B, C, wait} per CTA for the last iteration of the last run"""
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_s2m_get_cta_profile(self._h, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 4), np.float64)
+        self._ck(lib().llb_s2m_get_cta_profile(self._h, out.ctypes.data_as(ctypes.c_void_p), n.value, ctypes.byref(n)))
+        return out[:n.value]
 
     def s2m_pose_set(self, T):
         t = np.ascontiguousarray(T, np.float32)

@@ -642,13 +642,27 @@ int llb_get_normal_equations(llb_ctx *c, float AtA[36], float AtB[6], float X[6]
     });
 }
 
-int llb_s2m_get_profile(llb_ctx *c, long long stamps[8])
+int llb_s2m_get_cta_profile(llb_ctx *c, double *out, int cap, int *n_ctas)
 {
     return guarded(c, [&]() {
-        if (!stamps) return (int)LLB_ERR_INVALID;
+        if (!n_ctas) return (int)LLB_ERR_INVALID;
+        const int g = c->s2m.last_grid();
+        *n_ctas = g;
+        if (!out) return (int)LLB_OK;
+        if (g > cap) return (int)LLB_ERR_CAPACITY;
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        if (g > 0) LLB_CUDA(cudaMemcpy(out, c->s2m.cta_profile_dev(), sizeof(double) * 4 * g, cudaMemcpyDeviceToHost));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_get_profile(llb_ctx *c, int iter, long long stamps[8])
+{
+    return guarded(c, [&]() {
+        if (!stamps || iter < 0) return (int)LLB_ERR_INVALID;
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         LLB_CUDA(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < 8; i++) stamps[i] = c->pin_state.p->prof[i];
+        for (int i = 0; i < 8; i++) stamps[i] = c->pin_state.p->prof[iter % 10][i];
         return (int)LLB_OK;
     });
 }
@@ -656,6 +670,7 @@ int llb_s2m_get_profile(llb_ctx *c, long long stamps[8])
 int llb_get_degeneracy(llb_ctx *c, int *deg, float matP[36])
 {
     return guarded(c, [&]() {
+        if (matP) c->launches += c->s2m.ensure_matp(c->stream);
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         LLB_CUDA(cudaStreamSynchronize(c->stream));
         if (deg) *deg = c->pin_state.p->is_degenerate;
@@ -672,6 +687,8 @@ int llb_set_degeneracy(llb_ctx *c, int deg, const float matP[36])
         LLB_CUDA(cudaStreamSynchronize(c->stream));
         LLB_CUDA(cudaMemcpy(&d->is_degenerate, &deg, sizeof(int), cudaMemcpyHostToDevice));
         LLB_CUDA(cudaMemcpy(d->matP, matP, sizeof(float) * 36, cudaMemcpyHostToDevice));
+        const int one = 1;
+        LLB_CUDA(cudaMemcpy(&d->matP_valid, &one, sizeof(int), cudaMemcpyHostToDevice));
         return (int)LLB_OK;
     });
 }

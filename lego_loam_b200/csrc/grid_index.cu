@@ -134,35 +134,37 @@ scan_tile_sum_kernel(GridJobs jobs)
     __shared__ int s_w[33];
     __shared__ int s_last;
     const int m = d->ncell + 1;
-    const int base = blockIdx.x * SCAN_TILE;
-    int s = 0;
-    if (base < m) {
+    const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {     // grid-stride: the host does not know ncell
+        const int base = tile * SCAN_TILE;
+        int s = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             int i = base + k * 1024 + threadIdx.x;
             if (i < m) s += jb.counts[i];
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int v = s_w[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int v = s_w[threadIdx.x];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (threadIdx.x == 0) {
-            jb.blk[blockIdx.x] = v;
-            __threadfence();
-            s_last = (atomicAdd(&d->ticket, 1u) == gridDim.x - 1);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            if (threadIdx.x == 0) jb.blk[tile] = v;
         }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&d->ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) d->ticket = 0;
-    // exclusive scan of the gridDim.x tile sums by this CTA
-    const int count = gridDim.x;
+    // exclusive scan of the tile sums by this CTA
+    const int count = ntiles;
     const int per = (count + 1023) / 1024;
     const int lo = min((int)threadIdx.x * per, count), hi = min(lo + per, count);
     int sum = 0;
@@ -178,18 +180,19 @@ scan_tile_apply_kernel(GridJobs jobs)
     const GridJob &jb = jobs.j[blockIdx.y];
     __shared__ int s_scan[33];
     const int m = jb.desc->ncell + 1;
-    const int base = blockIdx.x * SCAN_TILE;
-    if (base >= m) return;
-    const int i0 = base + threadIdx.x * 4;                   // thread owns 4 CONSECUTIVE entries
-    int v[4];
+    const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i0 = tile * SCAN_TILE + threadIdx.x * 4;   // thread owns 4 CONSECUTIVE entries
+        int v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (i0 + k < m) ? jb.counts[i0 + k] : 0;
-    int total;
-    int ex = jb.blk[blockIdx.x] + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_scan, total);
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < m) ? jb.counts[i0 + k] : 0;
+        int total;
+        int ex = jb.blk[tile] + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_scan, total);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (i0 + k < m) jb.cell_begin[i0 + k] = ex;
-        ex += v[k];
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < m) jb.cell_begin[i0 + k] = ex;
+            ex += v[k];
+        }
     }
 }
 
@@ -253,7 +256,7 @@ int GridIndex::build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int
         j.cell_of = g[k]->cell_of_.p; j.rank = g[k]->rank_.p; j.blk = g[k]->blk_.p; j.sorted = g[k]->sorted_.p;
     }
     const dim3 grid_pts(std::min(div_up(nmax, TPB), 148 * 4), 2);
-    const dim3 grid_scan(div_up(jobs.max_cells + 1, SCAN_TILE), 2);
+    const dim3 grid_scan(std::min(div_up(jobs.max_cells + 1, SCAN_TILE), 148 * 2), 2);
     grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
     grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
     scan_tile_sum_kernel<<<grid_scan, 1024, 0, s>>>(jobs);

@@ -25,6 +25,7 @@
 // fp64; pose sin/cos are (float)sin((double)x) (correctly rounded float).
 #include "s2m.cuh"
 #include "linalg.cuh"
+#include "knn.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -33,127 +34,14 @@ namespace llb {
 
 namespace {
 
+// 512 threads x 128 registers = one CTA per SM (an 80-register / two-CTA variant spilled and was slower,
+// profiles/r01_s2m_phases.md); the grid is sized so that every SM gets a CTA before a CTA gets a second
+// round of queries.
 constexpr int S2M_THREADS = 512;
+constexpr int S2M_CTAS_PER_SM = 1;
 constexpr int S2M_NW = S2M_THREADS / 32;
-constexpr int S2M_TILE = 128;            // queries a CTA stages per pass
-constexpr int S2M_QPB = 32;              // target queries per CTA when sizing the grid
-
-__device__ __forceinline__ bool lex_less(float d1, int i1, float d2, int i2)
-{
-    return d1 < d2 || (d1 == d2 && i1 < i2);
-}
-
-// Per-lane sorted top-5.  A candidate is ONE 64-bit key (distance bits << 32 | original index):
-// squared distances are >= 0, so unsigned integer order of the bits is float order and a single
-// unsigned 64-bit compare is the lexicographic (distance, index) order of the oracle.  The
-// insertion is a branch-free compare-exchange chain (no divergence between lanes).
-struct Top5 {
-    unsigned long long K[5]; int S[5];
-    __device__ __forceinline__ void init()
-    {
-#pragma unroll
-        for (int k = 0; k < 5; k++) { K[k] = ~0ull; S[k] = -1; }
-    }
-    __device__ __forceinline__ void insert(float d, int oi, int pos)
-    {
-        unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)oi;
-        const bool in = key < K[4];
-        K[4] = in ? key : K[4]; S[4] = in ? pos : S[4];
-#pragma unroll
-        for (int k = 4; k > 0; k--) {
-            const bool sw = K[k] < K[k - 1];
-            const unsigned long long a = sw ? K[k] : K[k - 1], b = sw ? K[k - 1] : K[k];
-            const int sa = sw ? S[k] : S[k - 1], sb = sw ? S[k - 1] : S[k];
-            K[k - 1] = a; K[k] = b; S[k - 1] = sa; S[k] = sb;
-        }
-    }
-    __device__ __forceinline__ void pop()
-    {
-#pragma unroll
-        for (int k = 0; k < 4; k++) { K[k] = K[k + 1]; S[k] = S[k + 1]; }
-        K[4] = ~0ull; S[4] = -1;
-    }
-};
-
-// flann::L2_Simple<float>: sequential float sum of squared differences
-__device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const float4 &p)
-{
-    float diff = qx - p.x;
-    float d = diff * diff;
-    diff = qy - p.y; d += diff * diff;
-    diff = qz - p.z; d += diff * diff;
-    return d;
-}
-
-// Exact 5-NN of (qx,qy,qz) among the map points inside the 3x3x3 cell neighbourhood.
-// Every lane returns the same result: sorted-array positions (or -1), squared distances and
-// original indices in ascending (distance, index) order.
-__device__ __forceinline__ void knn5_warp(const MapIndexView &m, float qx, float qy, float qz, int lane,
-                                          int (&npos)[5], float (&nd)[5], int (&ni)[5])
-{
-    const GridDesc *g = m.desc;
-    const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
-    const float inv = g->inv_cell;
-    const int cx = grid_coord(qx, g->org[0], inv), cy = grid_coord(qy, g->org[1], inv), cz = grid_coord(qz, g->org[2], inv);
-
-    int rb = 0, re = 0;
-    if (lane < 9) {
-        const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
-        if (y >= 0 && y < dimy && z >= 0 && z < dimz) {
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
-            if (x0 <= x1) {
-                const int row = (z * dimy + y) * dimx;
-                rb = __ldg(&m.cell_begin[row + x0]);
-                re = __ldg(&m.cell_begin[row + x1 + 1]);
-            }
-        }
-    }
-    Top5 t;
-    t.init();
-    float4 c[9];
-    int rbv[9], rev[9];
-    bool longrun = false;
-    // empty runs (most of the 9 for a query next to a single surface) cost nothing: b, e are warp-uniform
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        rbv[r] = __shfl_sync(FULL, rb, r); rev[r] = __shfl_sync(FULL, re, r);
-        longrun |= (rev[r] - rbv[r]) > 32;
-        if (rev[r] > rbv[r] && rbv[r] + lane < rev[r]) c[r] = __ldg(&m.sorted[rbv[r] + lane]);
-    }
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        if (rev[r] > rbv[r]) {                               // warp-uniform
-            const bool v = rbv[r] + lane < rev[r];
-            const float d = v ? l2_simple(qx, qy, qz, c[r]) : __int_as_float(0x7f800000);
-            t.insert(d, v ? __float_as_int(c[r].w) : -1, rbv[r] + lane);
-        }
-    }
-    if (longrun) {                                           // warp-uniform
-        for (int r = 0; r < 9; r++) {
-            for (int i = rbv[r] + 32 + lane; i < rev[r]; i += 32) {
-                float4 p = __ldg(&m.sorted[i]);
-                t.insert(l2_simple(qx, qy, qz, p), __float_as_int(p.w), i);
-            }
-        }
-    }
-    // five rounds of warp-wide lexicographic arg-min over the list heads
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const unsigned db = (unsigned)(t.K[0] >> 32), di = (unsigned)t.K[0];
-        const unsigned mind = __reduce_min_sync(FULL, db);
-        const unsigned ci = (db == mind) ? di : 0xffffffffu;
-        const unsigned mini = __reduce_min_sync(FULL, ci);
-        const bool win = (db == mind) && (di == mini);
-        const unsigned ball = __ballot_sync(FULL, win);
-        const int src = __ffs(ball) - 1;
-        const int p = __shfl_sync(FULL, t.S[0], src);
-        const bool found = mini != 0xffffffffu;
-        nd[r] = __uint_as_float(mind);
-        ni[r] = found ? (int)mini : -1;
-        npos[r] = found ? p : -1;
-        if (lane == src) t.pop();
-    }
-}
+constexpr int S2M_TILE = 64;             // queries a CTA stages per pass
+constexpr int S2M_QPB = S2M_NW;          // target queries per CTA when sizing the grid (one per warp)
 
 // cornerOptimization body for one query (MO:1102-1170).  Returns true when the row is accepted.
 __device__ __forceinline__ bool corner_fit(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
@@ -233,7 +121,53 @@ __device__ void update_sincos(S2mState *st)
 }
 
 // LMOptimization tail MO:1273-1326 on the 28 reduced sums (one thread)
-__device__ void lm_solve(S2mState *st, const double *sum, int iter, const S2mParams &prm)
+// Certificate that every eigenvalue of the symmetric matrix A (6x6, float) exceeds `bound`:
+// Cholesky of (A - bound*I) in fp64 succeeds iff that matrix is positive definite.
+__device__ bool all_eigenvalues_above(const float *A, double bound)
+{
+    double L[36];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = (double)A[j * 6 + j] - bound;
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 0.0)) return false;
+        const double r = sqrt(d);
+        L[j * 6 + j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double s = (double)A[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = s / r;
+        }
+    }
+    return true;
+}
+
+// iteration-0 degeneracy analysis MO:1278-1299 on AtA: cv::eigen, zero the rows of the small
+// eigenvalues, matP = V^-1 * V2.  ~80 us for one thread (Jacobi in local memory): only run when the
+// cheap certificate below cannot rule degeneracy out, or when matP is asked for.
+__device__ void degeneracy_full(S2mState *st, const float *AtA, float thresh)
+{
+    float A[36], E[6], V[36], V2[36], Vinv[36];
+    for (int i = 0; i < 36; i++) A[i] = AtA[i];
+    cv_eigen<6>(A, E, V);
+    for (int i = 0; i < 36; i++) V2[i] = V[i];
+    int deg = 0;
+    for (int i = 5; i >= 0; i--) {
+        if (E[i] < thresh) {
+            for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f;
+            deg = 1;
+        } else break;
+    }
+    st->is_degenerate = deg;
+    cv_inv_lu<6>(V, Vinv);
+    cv_gemm<6, 6, 6>(Vinv, V2, st->matP);
+    st->matP_valid = 1;
+}
+
+__device__ void lm_solve(S2mState *st, const double *sum, int iter, const S2mParams &prm, bool do_trig)
 {
     const int n_corr = (int)sum[27];
     st->n_corr = n_corr;
@@ -250,20 +184,19 @@ __device__ void lm_solve(S2mState *st, const double *sum, int iter, const S2mPar
     cv_solve_qr<6, 6>(A, B, X);
 
     if (iter == 0) {
-        float E[6], V[36], V2[36], Vinv[36];
-        for (int i = 0; i < 36; i++) A[i] = AtA[i];
-        cv_eigen<6>(A, E, V);
-        for (int i = 0; i < 36; i++) V2[i] = V[i];
-        int deg = 0;
-        for (int i = 5; i >= 0; i--) {
-            if (E[i] < prm.degeneracy_thresh) {
-                for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f;
-                deg = 1;
-            } else break;
+        // isDegenerate <=> the float Jacobi reports an eigenvalue < thresh.  Jacobi's absolute eigenvalue
+        // error is O(n eps ||A||) <= ~1e-5 trace(A); if A - (thresh + 1e-4 trace) I is positive definite
+        // every Jacobi eigenvalue is >= thresh for sure: not degenerate, and matP is never read
+        // (MO:1301), so the eigen-decomposition is deferred until somebody asks for matP.
+        double tr = 0.0;
+        for (int i = 0; i < 6; i++) { tr += (double)AtA[i * 6 + i]; }
+        for (int i = 0; i < 36; i++) st->AtA0[i] = AtA[i];
+        if (all_eigenvalues_above(AtA, (double)prm.degeneracy_thresh + 1e-4 * tr + 1.0)) {
+            st->is_degenerate = 0;
+            st->matP_valid = 0;
+        } else {
+            degeneracy_full(st, AtA, prm.degeneracy_thresh);
         }
-        st->is_degenerate = deg;
-        cv_inv_lu<6>(V, Vinv);
-        cv_gemm<6, 6, 6>(Vinv, V2, st->matP);
     }
     if (st->is_degenerate) {
         float X2[6];
@@ -271,7 +204,7 @@ __device__ void lm_solve(S2mState *st, const double *sum, int iter, const S2mPar
         cv_gemm<6, 6, 1>(st->matP, X2, X);
     }
     for (int i = 0; i < 6; i++) { st->T[i] += X[i]; st->X[i] = X[i]; }
-    update_sincos(st);
+    if (do_trig) update_sincos(st);
 
     double r0 = (double)(X[0] * 57.29578f), r1 = (double)(X[1] * 57.29578f), r2 = (double)(X[2] * 57.29578f);
     double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
@@ -297,7 +230,8 @@ __global__ void s2m_prepare_kernel(S2mState *st, PoseArg pose, const float *T_de
 __global__ void s2m_state_init_kernel(S2mState *st)
 {
     for (int i = 0; i < 6; i++) { st->T[i] = 0.f; st->cs[i] = (i & 1) ? 0.f : 1.f; st->AtB[i] = 0.f; st->X[i] = 0.f; }
-    for (int i = 0; i < 36; i++) { st->matP[i] = 0.f; st->AtA[i] = 0.f; }
+    for (int i = 0; i < 36; i++) { st->matP[i] = 0.f; st->AtA[i] = 0.f; st->AtA0[i] = 0.f; }
+    st->matP_valid = 1;                                      // the reference starts with matP = 0 (MO:361)
     st->converged = 0; st->iters = 0; st->n_corr = 0; st->is_degenerate = 0; st->skipped = 0; st->ticket = 0;
 }
 
@@ -312,9 +246,10 @@ __device__ __forceinline__ void pair_of(int k, int &ia, int &ib)
     if (k >= 21 && k < 27) { ia = k - 21; ib = 6; }
 }
 
-__global__ void __launch_bounds__(S2M_THREADS, 1)
+__global__ void __launch_bounds__(S2M_THREADS, S2M_CTAS_PER_SM)
 s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexView cmap, MapIndexView smap,
-                S2mState *st, double *partials, double *acc_out, S2mDebug dbg, int rank, int world, int do_solve)
+                S2mState *st, double *partials, double *acc_out, S2mDebug dbg, int rank, int world, int do_solve,
+                int prof_off)
 {
     cg::grid_group grid = cg::this_grid();
 
@@ -323,6 +258,9 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
     __shared__ float s_row[8][S2M_TILE];                      // Jacobian row, -residual, valid
     __shared__ double s_acc[S2M_NW][32];
     __shared__ double s_tot[32];
+    __shared__ unsigned long long s_wkey[S2M_NW][KNN_CAP];    // per-warp in-gate candidate lists (phase A)
+    __shared__ int s_wpos[S2M_NW][KNN_CAP];
+    __shared__ int s_rb[9][S2M_TILE], s_re[9][S2M_TILE];      // cell-run ranges per query (phase A1 -> A2)
 
     if (__ldcg(&st->skipped)) return;                         // uniform over the grid (guard MO:1331)
 
@@ -330,10 +268,20 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
     const int nc = q.nc_dev ? *q.nc_dev : q.nc_upper;
     const int ns = q.ns_dev ? *q.ns_dev : q.ns_upper;
     const int nq = nc + ns;
-    // this rank's queries are qi = rank + world * j, j in [0, nloc); CTA b owns j in [j0, j1)
+    // this rank's queries are qi = rank + world * j, j in [0, nloc): the first ncl are corner queries.
+    // CTA b owns a contiguous range [j0, j1) (spatial locality of the cell reads) of equal WEIGHT: a corner
+    // query counts 3x (dense 0.2 m cells -> long runs, Jacobi fit), see profiles/r01_s2m_phases.md
     const int nloc = nq > rank ? (nq - rank + world - 1) / world : 0;
-    const int per = (nloc + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int j0 = min((int)blockIdx.x * per, nloc), j1 = min(j0 + per, nloc);
+    const int ncl = nc > rank ? (nc - rank + world - 1) / world : 0;
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+    constexpr long long CW = 3;
+    const long long Wt = CW * ncl + (nloc - ncl);
+    auto boundary = [&](int b) -> int {
+        const long long p = Wt * b / G;
+        return p < CW * ncl ? (int)(p / CW) : (int)(ncl + (p - CW * ncl));
+    };
+    const int j0 = boundary(bx), j1 = boundary(bx + 1);
+    const int cnt = j1 - j0;
 
     int ia, ib;
     pair_of(lane, ia, ib);
@@ -345,13 +293,17 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
         double acc = 0.0;
         long long pa = 0, pb = 0, pc = 0;
         const bool prof = (blockIdx.x == 0 && tid == 0);
-        if (prof) st->prof[0] = clock64();
+        const long long t_start = clock64();
+        if (prof) st->prof[iter % 10][0] = t_start;
 
-        for (int t0 = j0; t0 < j1; t0 += S2M_TILE) {
-            const int tn = min(S2M_TILE, j1 - t0);
-            // ---------------- phase A: warp per query
-            for (int s = w; s < tn; s += S2M_NW) {
-                const int qi = rank + world * (t0 + s);
+        for (int t0 = 0; t0 < cnt; t0 += S2M_TILE) {
+            const int tn = min(S2M_TILE, cnt - t0);
+            // slots [0, ncs) of this tile are corner queries, [ncs, tn) surf queries
+            const int ncs = max(0, min(tn, ncl - (j0 + t0)));
+            // ---------------- phase A1: thread per query: transform + the 9 cell-run ranges (18 independent loads)
+            if (tid < tn) {
+                const int s = tid;
+                const int qi = rank + world * (j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float4 po = is_corner ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
                 // pointAssociateToMap MO:513-527
@@ -363,10 +315,26 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 const float sx = cry * x1 + sry * z2 + tX;
                 const float sy = y2 + tY;
                 const float sz = -sry * x1 + cry * z2 + tZ;
+                s_q[0][s] = po.x; s_q[1][s] = po.y; s_q[2][s] = po.z;
+                s_q[3][s] = sx; s_q[4][s] = sy; s_q[5][s] = sz;
+                int rb[9], re[9];
+                knn_ranges(is_corner ? cmap : smap, sx, sy, sz, rb, re);
+#pragma unroll
+                for (int r = 0; r < 9; r++) { s_rb[r][s] = rb[r]; s_re[r][s] = re[r]; }
+            }
+            __syncthreads();
+            // ---------------- phase A2: warp per query: candidates -> in-gate list -> 5 smallest
+            for (int s = w; s < tn; s += S2M_NW) {
+                const int qi = rank + world * (j0 + t0 + s);
+                const bool is_corner = qi < nc;
+                const float sx = s_q[3][s], sy = s_q[4][s], sz = s_q[5][s];
+                int rbv[9], rev[9];
+#pragma unroll
+                for (int r = 0; r < 9; r++) { rbv[r] = s_rb[r][s]; rev[r] = s_re[r][s]; }
 
                 int npos[5]; float nd[5]; int ni[5];
                 const MapIndexView &mv = is_corner ? cmap : smap;
-                knn5_warp(mv, sx, sy, sz, lane, npos, nd, ni);
+                const int found = knn5_warp(mv, sx, sy, sz, prm.knn_max_sqdist, lane, rbv, rev, s_wkey[w], s_wpos[w], npos, nd, ni);
                 // lane j < 5 fetches neighbour j (an L1/L2 hit: the warp just read it) and stores it
                 int myp = npos[0]; int myi = ni[0]; float myd = nd[0];
 #pragma unroll
@@ -377,18 +345,17 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                     s_nn[lane * 3 + 0][s] = p.x; s_nn[lane * 3 + 1][s] = p.y; s_nn[lane * 3 + 2][s] = p.z;
                     if (dbg.knn_idx) { dbg.knn_idx[qi * 5 + lane] = myi; dbg.knn_d2[qi * 5 + lane] = myd; }
                 }
-                if (lane == 5) {
-                    s_q[0][s] = po.x; s_q[1][s] = po.y; s_q[2][s] = po.z;
-                    s_q[3][s] = sx; s_q[4][s] = sy; s_q[5][s] = sz;
-                    s_q[6][s] = (ni[4] >= 0) ? nd[4] : -1.f;
-                }
+                if (lane == 5) s_q[6][s] = (found == 5) ? nd[4] : -1.f;
             }
             __syncthreads();
-            if (prof) pa = clock64();
+            if (tid == 0) pa = clock64();
             // ---------------- phase B: thread per query
-            if (tid < tn) {
-                const int s = tid;
-                const int qi = rank + world * (t0 + s);
+            // corner slots are served by warp 0, surf slots by warps 1..: the Jacobi and the QR code paths
+            // never diverge inside a warp (TILE <= THREADS - 32 surf slots always fit)
+            const int c32 = min(ncs, 32);                    // corner slots beyond 32 ride with the surf warps
+            const int s = tid < 32 ? (tid < c32 ? tid : -1) : (c32 + tid - 32);
+            if (s >= 0 && s < tn) {
+                const int qi = rank + world * (j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float d5 = s_q[6][s];
                 bool ok = (d5 >= 0.f) && ((double)d5 < (double)prm.knn_max_sqdist);    // MO:1101 / MO:1183
@@ -421,14 +388,14 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 for (int k = 0; k < 8; k++) s_row[k][s] = v[k];
             }
             __syncthreads();
-            if (prof) pb = clock64();
+            if (tid == 0) pb = clock64();
             // ---------------- phase C: lane k accumulates product k over rows w, w+16, ...
             if (lane < S2M_ACC)
                 for (int r = w; r < tn; r += S2M_NW) acc += (double)s_row[ia][r] * (double)s_row[ib][r];
             __syncthreads();
-            if (prof) pc = clock64();
+            if (tid == 0) pc = clock64();
         }
-        if (prof) { st->prof[1] = pa; st->prof[2] = pb; st->prof[3] = pc; }
+        if (prof) { st->prof[iter % 10][1] = pa; st->prof[iter % 10][2] = pb; st->prof[iter % 10][3] = pc; }
 
         // ---- CTA partial (fixed order over warps)
         s_acc[w][lane] = acc;
@@ -440,7 +407,12 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             partials[(size_t)blockIdx.x * S2M_ACC + tid] = s;
         }
         grid.sync();
-        if (prof) st->prof[4] = clock64();
+        if (prof) st->prof[iter % 10][4] = clock64();
+        if (tid == 0) {                                      // per-CTA phase cycles of this iteration (diagnostics)
+            double *cp = partials + (size_t)prof_off + (size_t)blockIdx.x * 4;
+            cp[0] = (double)(pa - t_start); cp[1] = (double)(pb - pa); cp[2] = (double)(pc - pb);
+            cp[3] = (double)(clock64() - pc);
+        }
 
         // ---- CTA 0: deterministic grid reduction (16 interleaved slices, fixed order) + LM step
         if (blockIdx.x == 0) {
@@ -457,13 +429,19 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 if (!do_solve) acc_out[tid] = tsum;
             }
             __syncthreads();
-            if (prof) st->prof[5] = clock64();
-            if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm);
-            if (prof) st->prof[6] = clock64();
+            if (prof) st->prof[iter % 10][5] = clock64();
+            if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm, false);
+            __syncthreads();
+            // the six sin/cos of the new pose, one per thread (fp64 libm calls are the long pole of the step)
+            if (tid < 6 && do_solve) {
+                const double a = (double)st->T[tid >> 1];
+                st->cs[tid] = (tid & 1) ? (float)sin(a) : (float)cos(a);
+            }
+            if (prof) st->prof[iter % 10][6] = clock64();
         }
         if (!do_solve) break;
         grid.sync();
-        if (prof) st->prof[7] = clock64();
+        if (prof) st->prof[iter % 10][7] = clock64();
         if (__ldcg(&st->converged)) break;                   // MO:1344-1345, uniform over the grid
     }
 }
@@ -471,7 +449,16 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
 __global__ void s2m_solve_kernel(S2mParams prm, int iter, S2mState *st, const double *acc)
 {
     if (st->converged || st->skipped) return;
-    lm_solve(st, acc, iter, prm);
+    lm_solve(st, acc, iter, prm, true);
+}
+
+// matP on demand (see lm_solve): recompute the iteration-0 analysis from the saved AtA
+__global__ void s2m_matp_kernel(S2mParams prm, S2mState *st)
+{
+    if (st->matP_valid) return;
+    const int deg = st->is_degenerate;
+    degeneracy_full(st, st->AtA0, prm.degeneracy_thresh);
+    st->is_degenerate = deg;                                 // the decision was already made, keep it
 }
 
 }  // namespace
@@ -486,7 +473,7 @@ void S2mSolver::init(const S2mParams &p)
     LLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2m_loop_kernel, S2M_THREADS, 0));
     if (per_sm < 1) throw std::runtime_error("s2m_loop_kernel cannot be made resident");
     max_blocks_ = sms * per_sm;
-    partials_.ensure((size_t)max_blocks_ * S2M_ACC);
+    partials_.ensure((size_t)max_blocks_ * (S2M_ACC + 4));     // + 4 profile doubles per CTA
     acc_.ensure(32);
     s2m_state_init_kernel<<<1, 1>>>(state_.p);
     LLB_CUDA(cudaGetLastError());
@@ -516,8 +503,17 @@ int S2mSolver::run(int it_begin, int it_end, const S2mQueries &q, const MapIndex
     S2mQueries qq = q; MapIndexView cm = cmap, sm = smap; S2mDebug dg = dbg;
     S2mState *st = state_.p; double *part = partials_.p, *acc = acc_.p;
     int ds = do_solve ? 1 : 0;
-    void *args[] = { &prm, &it_begin, &it_end, &qq, &cm, &sm, &st, &part, &acc, &dg, &rank, &world, &ds };
+    int prof_off = max_blocks_ * S2M_ACC;
+    last_grid_ = grid;
+    void *args[] = { &prm, &it_begin, &it_end, &qq, &cm, &sm, &st, &part, &acc, &dg, &rank, &world, &ds, &prof_off };
     LLB_CUDA(cudaLaunchCooperativeKernel((const void *)s2m_loop_kernel, dim3(grid), dim3(S2M_THREADS), args, 0, s));
+    return 1;
+}
+
+int S2mSolver::ensure_matp(cudaStream_t s)
+{
+    s2m_matp_kernel<<<1, 1, 0, s>>>(prm_, state_.p);
+    LLB_CUDA(cudaGetLastError());
     return 1;
 }
 

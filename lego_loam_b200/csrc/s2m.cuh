@@ -25,10 +25,12 @@ struct S2mState {                    // device-resident, persists across registr
     int   n_corr;
     int   is_degenerate;             // MO:202 (persists, C6)
     int   skipped;                   // guard MO:1331 failed
-    float matP[36];                  // MO:203
+    float matP[36];                  // MO:203 (valid when matP_valid; else derived on demand from AtA0)
+    float AtA0[36];                  // AtA of the last executed iteration 0
+    int   matP_valid;
     float AtA[36], AtB[6], X[6];     // last LM step (diagnostics)
     unsigned ticket;                 // last-block election
-    long long prof[8];               // clock64 stamps of CTA 0, last iteration: start, A, B, C, sync1, reduce, solve, sync2
+    long long prof[10][8];           // clock64 stamps of CTA 0 per iteration: start, A, B, C, sync1, reduce, solve, sync2
 };
 
 struct S2mDebug {                    // optional per-query outputs (nullptr = off)
@@ -58,6 +60,8 @@ public:
     int run(int it_begin, int it_end, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
             const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s);
     int solve(int iter, cudaStream_t s);
+    // makes S2mState::matP valid (it is computed lazily when the registration was not degenerate)
+    int ensure_matp(cudaStream_t s);
 
 private:
     S2mParams prm_{};
@@ -65,6 +69,11 @@ private:
     DevBuf<double> partials_;
     DevBuf<double> acc_;
     int max_blocks_ = 0;
+    int last_grid_ = 0;
+public:
+    // per-CTA phase cycles {A, B, C, wait at the grid barrier} of the last iteration of the last run
+    const double *cta_profile_dev() const { return partials_.p + (size_t)max_blocks_ * S2M_ACC; }
+    int last_grid() const { return last_grid_; }
 };
 
 }  // namespace llb

@@ -66,7 +66,16 @@ def main():
     for name, (dms, wall) in rows:
         print(f"{name:62s} device {dms * 1e3:9.1f} us   host-wall {wall * 1e3:9.1f} us")
     print(f"one accumulate-only iteration: {ms_it * 1e3:.1f} us for {nq} queries; full optimize stats: {st.as_dict()}")
-    print("CTA-0 cycles per phase, last iteration:", ctx.s2m_get_profile())
+    cp = ctx.s2m_get_cta_profile()
+    if cp.shape[0]:
+        nc_ctas = int(np.ceil(st.n_corner_ds / max(1, int(np.ceil((st.n_corner_ds + st.n_surf_ds) / cp.shape[0])))))
+        for name, sel in (("corner CTAs", slice(0, max(nc_ctas - 1, 1))), ("surf CTAs", slice(nc_ctas, None))):
+            q = cp[sel]
+            if q.shape[0]:
+                print(f"per-CTA cycles, last iteration, {name} ({q.shape[0]}): "
+                      + ", ".join(f"{n} med {np.median(q[:, k]):.0f} max {q[:, k].max():.0f}" for k, n in enumerate("ABCW")))
+    for it in range(st.iterations):
+        print(f"CTA-0 cycles per phase, iteration {it}:", ctx.s2m_get_profile(it))
     # odometry
     from lego_loam_b200 import synth
     w = synth.make_world()
