@@ -159,6 +159,13 @@ __device__ int solve3(OdomState *st, const double *sum, int iter, int which, con
 }
 
 // mode 0: full updateTransformation; mode 1: one surf iteration `iter0`; mode 2: one corner iteration
+//
+// Per iteration, over tiles of 1024 features:
+//   P1 thread/feature : TransformToStart (six fp64 sin/cos per point, FA:871-881) -> shared memory
+//   P2 warp/feature   : only when iter % 5 == 0 (C4): exact 1-NN + the two ring-window scans -> index arrays
+//   P3 thread/feature : line / plane coefficients from the stored indices, weight, Jacobian row -> shared memory
+//   P4 lane k of warp w accumulates product k of the 10 normal-equation terms over rows w, w+32, ...
+// then a fixed-order reduction and the 3x3 LM step by thread 0.
 __global__ void __launch_bounds__(OD_THREADS, 1)
 odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, int iter0)
 {
@@ -166,7 +173,9 @@ odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, 
     __shared__ double s_tot[OD_ACC];
     __shared__ float s_T[6];
     __shared__ Trig s_trig;
-    __shared__ int s_more, s_ncorr;
+    __shared__ int s_more;
+    __shared__ float s_sel[3][OD_THREADS];                  // de-skewed feature of the tile
+    __shared__ float s_row[5][OD_THREADS];                  // J0 J1 J2 b valid
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
@@ -177,9 +186,9 @@ odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, 
     }
     if (dat.ncl < 10 || dat.nsl < 100) return;
 
-    const int ia_tab[9] = { 0, 0, 0, 1, 1, 2, 0, 1, 2 };
-    const int ib_tab[9] = { 0, 1, 2, 1, 2, 2, 3, 3, 3 };
-    const int ia = lane < 9 ? ia_tab[lane] : 0, ib = lane < 9 ? ib_tab[lane] : 0;
+    const int ia_tab[10] = { 0, 0, 0, 1, 1, 2, 0, 1, 2, 4 };
+    const int ib_tab[10] = { 0, 1, 2, 1, 2, 2, 3, 3, 3, 4 };
+    const int ia = lane < OD_ACC ? ia_tab[lane] : 0, ib = lane < OD_ACC ? ib_tab[lane] : 0;
 
     for (int which = 0; which < 2; which++) {
         if (mode == 1 && which != 0) continue;
@@ -195,126 +204,147 @@ odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, 
             __syncthreads();
             if (tid == 0) {
                 for (int i = 0; i < 6; i++) s_T[i] = st->T[i];
-                Trig t;
-                t.srx = (float)sin((double)s_T[0]); t.crx = (float)cos((double)s_T[0]);
-                t.sry = (float)sin((double)s_T[1]); t.cry = (float)cos((double)s_T[1]);
-                t.srz = (float)sin((double)s_T[2]); t.crz = (float)cos((double)s_T[2]);
-                t.tx = s_T[3]; t.ty = s_T[4]; t.tz = s_T[5];
-                s_trig = t;
+                s_trig.tx = s_T[3]; s_trig.ty = s_T[4]; s_trig.tz = s_T[5];
+            }
+            __syncthreads();
+            if (tid < 6) {                                                   // six threads, one fp64 libm call each
+                const double a = (double)s_T[tid >> 1];
+                const float v = (tid & 1) ? (float)cos(a) : (float)sin(a);
+                if (tid == 0) s_trig.srx = v; if (tid == 1) s_trig.crx = v;
+                if (tid == 2) s_trig.sry = v; if (tid == 3) s_trig.cry = v;
+                if (tid == 4) s_trig.srz = v; if (tid == 5) s_trig.crz = v;
             }
             __syncthreads();
             const float srx = s_trig.srx, crx = s_trig.crx, sry = s_trig.sry, cry = s_trig.cry,
                         srz = s_trig.srz, crz = s_trig.crz, tx = s_trig.tx, ty = s_trig.ty, tz = s_trig.tz;
             double acc = 0.0;
 
-            for (int i = w; i < nq; i += OD_NW) {
-                const float4 pi = __ldg(&qpts[i]);
-                float x0, y0, z0;
-                transform_to_start(s_T, pi, x0, y0, z0);
-
+            for (int t0 = 0; t0 < nq; t0 += OD_THREADS) {
+                const int tn = min(OD_THREADS, nq - t0);
+                // ---- P1
+                float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tid < tn) {
+                    pi = __ldg(&qpts[t0 + tid]);
+                    float x0, y0, z0;
+                    transform_to_start(s_T, pi, x0, y0, z0);
+                    s_sel[0][tid] = x0; s_sel[1][tid] = y0; s_sel[2][tid] = z0;
+                }
+                __syncthreads();
+                // ---- P2
                 if (iter % 5 == 0) {                                          // C4
-                    float d1; int closest;
-                    nn1_warp(last, nlast, x0, y0, z0, lane, d1, closest);
-                    float bd[2] = { prm.nearest_sqdist, prm.nearest_sqdist };
-                    int bj[2] = { -1, -1 };
-                    if (d1 < prm.nearest_sqdist) {
-                        const int closestScan = (int)__ldg(&last[closest]).w;
+                    for (int s = w; s < tn; s += OD_NW) {
+                        const int i = t0 + s;
+                        const float x0 = s_sel[0][s], y0 = s_sel[1][s], z0 = s_sel[2][s];
+                        float d1; int closest;
+                        nn1_warp(last, nlast, x0, y0, z0, lane, d1, closest);
+                        float bd[2] = { prm.nearest_sqdist, prm.nearest_sqdist };
+                        int bj[2] = { -1, -1 };
+                        if (d1 < prm.nearest_sqdist) {
+                            const int closestScan = (int)__ldg(&last[closest]).w;
+                            if (which == 0) {
+                                window_scan<true>(last, closest + 1, +1, 0, fwdEnd, closestScan, x0, y0, z0, lane, bd, bj);
+                                window_scan<true>(last, closest - 1, -1, 0, nlast, closestScan, x0, y0, z0, lane, bd, bj);
+                            } else {
+                                window_scan<false>(last, closest + 1, +1, 0, fwdEnd, closestScan, x0, y0, z0, lane, bd, bj);
+                                window_scan<false>(last, closest - 1, -1, 0, nlast, closestScan, x0, y0, z0, lane, bd, bj);
+                            }
+                        } else closest = -1;
+                        if (lane == 0) {
+                            if (which == 0) { dat.sInd1[i] = (float)closest; dat.sInd2[i] = (float)bj[0]; dat.sInd3[i] = (float)bj[1]; }
+                            else { dat.cInd1[i] = (float)closest; dat.cInd2[i] = (float)bj[0]; }
+                        }
+                    }
+                    __syncthreads();
+                }
+                // ---- P3
+                {
+                    float v[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+                    if (tid < tn) {
+                        const int i = t0 + tid;
+                        const float x0 = s_sel[0][tid], y0 = s_sel[1][tid], z0 = s_sel[2][tid];
+                        bool ok = false;
+                        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (which == 0) {
-                            window_scan<true>(last, closest + 1, +1, 0, fwdEnd, closestScan, x0, y0, z0, lane, bd, bj);
-                            window_scan<true>(last, closest - 1, -1, 0, nlast, closestScan, x0, y0, z0, lane, bd, bj);
+                            const float f1 = dat.sInd1[i], f2 = dat.sInd2[i], f3 = dat.sInd3[i];
+                            if (f2 >= 0 && f3 >= 0) {
+                                const float4 t1 = __ldg(&last[(int)f1]), t2 = __ldg(&last[(int)f2]), t3 = __ldg(&last[(int)f3]);
+                                float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+                                float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+                                float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+                                float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+                                const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+                                pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+                                const float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
+                                float s = 1;
+                                if (iter >= 5)
+                                    s = (float)(1.0 - 1.8 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
+                                if ((double)s > 0.1 && pd2 != 0) {
+                                    coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+                                    ok = true;
+                                }
+                            }
                         } else {
-                            window_scan<false>(last, closest + 1, +1, 0, fwdEnd, closestScan, x0, y0, z0, lane, bd, bj);
-                            window_scan<false>(last, closest - 1, -1, 0, nlast, closestScan, x0, y0, z0, lane, bd, bj);
+                            const float f1 = dat.cInd1[i], f2 = dat.cInd2[i];
+                            if (f2 >= 0) {
+                                const float4 t1 = __ldg(&last[(int)f1]), t2 = __ldg(&last[(int)f2]);
+                                const float x1 = t1.x, y1 = t1.y, z1 = t1.z, x2 = t2.x, y2 = t2.y, z2 = t2.z;
+                                const float m11 = ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1));
+                                const float m22 = ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1));
+                                const float m33 = ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1));
+                                const float a012 = sqrtf(m11 * m11 + m22 * m22 + m33 * m33);
+                                const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+                                const float la = ((y1 - y2) * m11 + (z1 - z2) * m22) / a012 / l12;
+                                const float lb = -((x1 - x2) * m11 - (z1 - z2) * m33) / a012 / l12;
+                                const float lc = -((x1 - x2) * m22 + (y1 - y2) * m33) / a012 / l12;
+                                const float ld2 = a012 / l12;
+                                float s = 1;
+                                if (iter >= 5) s = (float)(1.0 - 1.8 * (double)fabsf(ld2));
+                                if ((double)s > 0.1 && ld2 != 0) {
+                                    coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
+                                    ok = true;
+                                }
+                            }
                         }
-                    } else closest = -1;
-                    if (lane == 0) {
-                        if (which == 0) { dat.sInd1[i] = (float)closest; dat.sInd2[i] = (float)bj[0]; dat.sInd3[i] = (float)bj[1]; }
-                        else { dat.cInd1[i] = (float)closest; dat.cInd2[i] = (float)bj[0]; }
-                    }
-                    __syncwarp();
-                }
-
-                bool ok = false;
-                float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (which == 0) {
-                    const float f1 = dat.sInd1[i], f2 = dat.sInd2[i], f3 = dat.sInd3[i];
-                    if (f2 >= 0 && f3 >= 0) {
-                        const float4 t1 = __ldg(&last[(int)f1]), t2 = __ldg(&last[(int)f2]), t3 = __ldg(&last[(int)f3]);
-                        float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
-                        float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
-                        float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
-                        float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
-                        const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
-                        pa /= ps; pb /= ps; pc /= ps; pd /= ps;
-                        const float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
-                        float s = 1;
-                        if (iter >= 5)
-                            s = (float)(1.0 - 1.8 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
-                        if ((double)s > 0.1 && pd2 != 0) {
-                            coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
-                            ok = true;
+                        if (dat.dbg_coeff) { dat.dbg_coeff[i] = coeff; dat.dbg_valid[i] = ok ? 1 : 0; }
+                        if (ok) {
+                            if (which == 0) {                                         // FA:1291-1321
+                                const float a1 = crx * sry * srz, a2 = crx * crz * sry, a3 = srx * sry, a4 = tx * a1 - ty * a2 - tz * a3;
+                                const float a5 = srx * srz, a6 = crz * srx, a7 = ty * a6 - tz * crx - tx * a5;
+                                const float a8 = crx * cry * srz, a9 = crx * cry * crz, a10 = cry * srx, a11 = tz * a10 + ty * a9 - tx * a8;
+                                const float b1 = -crz * sry - cry * srx * srz, b2 = cry * crz * srx - sry * srz;
+                                const float b5 = cry * crz - srx * sry * srz, b6 = cry * srz + crz * srx * sry;
+                                const float c1 = -b6, c2 = b5, c3 = tx * b6 - ty * b5, c4 = -crx * crz, c5 = crx * srz, c6 = ty * c5 + tx * -c4;
+                                const float c7 = b2, c8 = -b1, c9 = tx * -b2 - ty * -b1;
+                                v[0] = (-a1 * pi.x + a2 * pi.y + a3 * pi.z + a4) * coeff.x
+                                     + (a5 * pi.x - a6 * pi.y + crx * pi.z + a7) * coeff.y
+                                     + (a8 * pi.x - a9 * pi.y - a10 * pi.z + a11) * coeff.z;
+                                v[1] = (c1 * pi.x + c2 * pi.y + c3) * coeff.x
+                                     + (c4 * pi.x - c5 * pi.y + c6) * coeff.y
+                                     + (c7 * pi.x + c8 * pi.y + c9) * coeff.z;
+                                v[2] = -b6 * coeff.x + c4 * coeff.y + b2 * coeff.z;
+                            } else {                                                  // FA:1400-1422
+                                const float b1 = -crz * sry - cry * srx * srz, b2 = cry * crz * srx - sry * srz, b3 = crx * cry,
+                                            b4 = tx * -b1 + ty * -b2 + tz * b3;
+                                const float b5 = cry * crz - srx * sry * srz, b6 = cry * srz + crz * srx * sry, b7 = crx * sry,
+                                            b8 = tz * b7 - ty * b6 - tx * b5;
+                                const float c5 = crx * srz;
+                                v[0] = (b1 * pi.x + b2 * pi.y - b3 * pi.z + b4) * coeff.x
+                                     + (b5 * pi.x + b6 * pi.y - b7 * pi.z + b8) * coeff.z;
+                                v[1] = -b5 * coeff.x + c5 * coeff.y + b1 * coeff.z;
+                                v[2] = b7 * coeff.x - srx * coeff.y - b3 * coeff.z;
+                            }
+                            v[3] = (float)(-0.05 * (double)coeff.w);
+                            v[4] = 1.f;
                         }
                     }
-                } else {
-                    const float f1 = dat.cInd1[i], f2 = dat.cInd2[i];
-                    if (f2 >= 0) {
-                        const float4 t1 = __ldg(&last[(int)f1]), t2 = __ldg(&last[(int)f2]);
-                        const float x1 = t1.x, y1 = t1.y, z1 = t1.z, x2 = t2.x, y2 = t2.y, z2 = t2.z;
-                        const float m11 = ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1));
-                        const float m22 = ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1));
-                        const float m33 = ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1));
-                        const float a012 = sqrtf(m11 * m11 + m22 * m22 + m33 * m33);
-                        const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
-                        const float la = ((y1 - y2) * m11 + (z1 - z2) * m22) / a012 / l12;
-                        const float lb = -((x1 - x2) * m11 - (z1 - z2) * m33) / a012 / l12;
-                        const float lc = -((x1 - x2) * m22 + (y1 - y2) * m33) / a012 / l12;
-                        const float ld2 = a012 / l12;
-                        float s = 1;
-                        if (iter >= 5) s = (float)(1.0 - 1.8 * (double)fabsf(ld2));
-                        if ((double)s > 0.1 && ld2 != 0) {
-                            coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
-                            ok = true;
-                        }
-                    }
-                }
-                if (dat.dbg_coeff && lane == 0) { dat.dbg_coeff[i] = coeff; dat.dbg_valid[i] = ok ? 1 : 0; }
-
-                if (ok) {
-                    float v[4];
-                    if (which == 0) {                                         // FA:1291-1321
-                        const float a1 = crx * sry * srz, a2 = crx * crz * sry, a3 = srx * sry, a4 = tx * a1 - ty * a2 - tz * a3;
-                        const float a5 = srx * srz, a6 = crz * srx, a7 = ty * a6 - tz * crx - tx * a5;
-                        const float a8 = crx * cry * srz, a9 = crx * cry * crz, a10 = cry * srx, a11 = tz * a10 + ty * a9 - tx * a8;
-                        const float b1 = -crz * sry - cry * srx * srz, b2 = cry * crz * srx - sry * srz;
-                        const float b5 = cry * crz - srx * sry * srz, b6 = cry * srz + crz * srx * sry;
-                        const float c1 = -b6, c2 = b5, c3 = tx * b6 - ty * b5, c4 = -crx * crz, c5 = crx * srz, c6 = ty * c5 + tx * -c4;
-                        const float c7 = b2, c8 = -b1, c9 = tx * -b2 - ty * -b1;
-                        v[0] = (-a1 * pi.x + a2 * pi.y + a3 * pi.z + a4) * coeff.x
-                             + (a5 * pi.x - a6 * pi.y + crx * pi.z + a7) * coeff.y
-                             + (a8 * pi.x - a9 * pi.y - a10 * pi.z + a11) * coeff.z;
-                        v[1] = (c1 * pi.x + c2 * pi.y + c3) * coeff.x
-                             + (c4 * pi.x - c5 * pi.y + c6) * coeff.y
-                             + (c7 * pi.x + c8 * pi.y + c9) * coeff.z;
-                        v[2] = -b6 * coeff.x + c4 * coeff.y + b2 * coeff.z;
-                    } else {                                                  // FA:1400-1422
-                        const float b1 = -crz * sry - cry * srx * srz, b2 = cry * crz * srx - sry * srz, b3 = crx * cry,
-                                    b4 = tx * -b1 + ty * -b2 + tz * b3;
-                        const float b5 = cry * crz - srx * sry * srz, b6 = cry * srz + crz * srx * sry, b7 = crx * sry,
-                                    b8 = tz * b7 - ty * b6 - tx * b5;
-                        const float c5 = crx * srz;
-                        v[0] = (b1 * pi.x + b2 * pi.y - b3 * pi.z + b4) * coeff.x
-                             + (b5 * pi.x + b6 * pi.y - b7 * pi.z + b8) * coeff.z;
-                        v[1] = -b5 * coeff.x + c5 * coeff.y + b1 * coeff.z;
-                        v[2] = b7 * coeff.x - srx * coeff.y - b3 * coeff.z;
-                    }
-                    v[3] = (float)(-0.05 * (double)coeff.w);
-                    if (lane < 9) {
-                        float a = v[0], b = v[0];
 #pragma unroll
-                        for (int k = 1; k < 4; k++) { a = (ia == k) ? v[k] : a; b = (ib == k) ? v[k] : b; }
-                        acc += (double)a * (double)b;
-                    } else if (lane == 9) acc += 1.0;
+                    for (int k = 0; k < 5; k++) s_row[k][tid] = v[k];
                 }
+                __syncthreads();
+                // ---- P4
+                if (lane < OD_ACC)
+                    for (int r = w; r < tn; r += OD_NW) acc += (double)s_row[ia][r] * (double)s_row[ib][r];
+                __syncthreads();
             }
 
             if (lane < OD_ACC) s_acc[w][lane] = acc;
@@ -335,7 +365,7 @@ odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, 
                     if (!more) st->converged[which] = 1;
                 }
                 st->more = more;
-                s_more = more; s_ncorr = n_corr;
+                s_more = more;
             }
             __syncthreads();
             if (!s_more) break;
