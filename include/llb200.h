@@ -67,6 +67,17 @@ typedef struct {
     float odom_converge_deg;      /* 0.1  FA:1373 */
     float odom_converge_cm;       /* 0.1  FA:1373 */
     int   max_grid_cells;         /* spatial-index cell budget per map (default 1<<23) */
+    int   pin_host_clouds;        /* 0 (default): host clouds are copied into the context's pinned staging during the
+                                     call and may be reused as soon as it returns.  1: the caller's buffers are
+                                     page-locked once (cudaHostRegister, cached per pointer) and DMA'd in place:
+                                     no host copy, but the caller must keep a cloud unchanged until the next
+                                     blocking call on this context (llb_s2m_optimize / llb_s2m_result / llb_synchronize
+                                     / any getter).  The reference's clouds are long-lived class members, so the
+                                     adapters can enable it. */
+    int   s2m_max_ctas;           /* cap on the CTAs of the persistent scan-to-map kernel; 0 (default) = one per SM:
+                                     lowest latency for ONE registration.  When several contexts (sequences) share a
+                                     GPU a cap of ~1/4 of the SMs lets their registrations overlap instead of queueing
+                                     behind each other's cooperative launches (throughput mode). */
 } llb_params;
 
 typedef struct {
@@ -120,6 +131,11 @@ int llb_s2m_iterate(llb_ctx *ctx, float T[6], int iter, int *converged, int *n_c
  * index (already built by llb_map_set_*), <= 10 fused iterations with the
  * convergence test on device, no host round trip inside. */
 int llb_s2m_optimize(llb_ctx *ctx, float T[6], llb_stats *stats);
+/* the same, split so that several contexts (independent sequences on one GPU) can be kept in flight
+ * from one host thread: _async enqueues the whole registration and returns without synchronising,
+ * _result waits for it and returns pose + stats */
+int llb_s2m_optimize_async(llb_ctx *ctx, const float T[6]);
+int llb_s2m_result(llb_ctx *ctx, float T[6], llb_stats *stats);
 /* laserCloudOri / coeffSel of the last iteration run by llb_s2m_iterate, in the
  * reference's order (corner rows then surf rows, each in query order) */
 int llb_get_correspondences(llb_ctx *ctx, llb_point *ori, llb_point *coeff, int capacity, int *n);

@@ -39,6 +39,8 @@ class Params(ctypes.Structure):
         ("odom_min_correspondences", ctypes.c_int), ("odom_degeneracy_thresh", ctypes.c_float),
         ("odom_converge_deg", ctypes.c_float), ("odom_converge_cm", ctypes.c_float),
         ("max_grid_cells", ctypes.c_int),
+        ("pin_host_clouds", ctypes.c_int),
+        ("s2m_max_ctas", ctypes.c_int),
     ]
 
 
@@ -63,6 +65,7 @@ EXPORTS = [
     "llb_map_set_ds_dev", "llb_map_set_raw_dev", "llb_scan_set_dev", "llb_s2m_optimize_dev",
     "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
+    "llb_s2m_optimize_async", "llb_s2m_result",
 ]
 
 _lib = None
@@ -224,6 +227,17 @@ class Context:
         t = np.ascontiguousarray(T, np.float32).copy()
         st = Stats()
         self._ck(lib().llb_s2m_optimize(self._h, _fp(t), ctypes.byref(st)))
+        return t, st
+
+    def s2m_optimize_async(self, T):
+        t = np.ascontiguousarray(T, np.float32)
+        self._async_T = t.copy()
+        self._ck(lib().llb_s2m_optimize_async(self._h, _fp(t)))
+
+    def s2m_result(self):
+        t = self._async_T.copy()          # left untouched when the map-size guard skips the registration
+        st = Stats()
+        self._ck(lib().llb_s2m_result(self._h, _fp(t), ctypes.byref(st)))
         return t, st
 
     def get_correspondences(self):

@@ -49,6 +49,9 @@ struct llb_ctx {
     DevBuf<float> raw32[3];
     cudaEvent_t pin_ev[3] = { nullptr, nullptr, nullptr };
     bool pin_busy[3] = { false, false, false };
+    struct Reg { const void *p; size_t bytes; bool ours; };
+    std::vector<Reg> regs;        // caller buffers page-locked by this context (pin_host_clouds)
+    bool async_pending = false;   // llb_s2m_optimize_async issued, llb_s2m_result not yet called
     DevBuf<float4> tmp_in;
     PinnedBuf<float4> pin_out;
     PinnedBuf<int> pin_counts;
@@ -89,6 +92,7 @@ S2mParams s2m_params(const llb_params &p)
     q.knn_max_sqdist = p.knn_max_sqdist; q.min_corr = p.s2m_min_correspondences;
     q.degeneracy_thresh = p.s2m_degeneracy_thresh; q.converge_deg = p.s2m_converge_deg;
     q.converge_cm = p.s2m_converge_cm; q.corner_map_min = p.corner_map_min; q.surf_map_min = p.surf_map_min;
+    q.max_ctas = p.s2m_max_ctas;
     return q;
 }
 
@@ -118,12 +122,46 @@ int guarded(llb_ctx *ctx, F &&f)
     }
 }
 
+// page-lock the caller's buffer once (pin_host_clouds); false => fall back to the staging copy
+bool ensure_registered(llb_ctx *c, const void *p, size_t bytes)
+{
+    for (auto &r : c->regs)
+        if (r.p == p && r.bytes >= bytes) return true;
+    for (size_t i = 0; i < c->regs.size(); i++)
+        if (c->regs[i].p == p) {                              // same buffer grew: register the larger range
+            if (c->regs[i].ours) { cudaStreamSynchronize(c->stream); cudaHostUnregister(const_cast<void *>(p)); }
+            c->regs.erase(c->regs.begin() + i);
+            break;
+        }
+    if (c->regs.size() >= 64) {                               // bounded cache: drop the oldest entry
+        if (c->regs[0].ours) { cudaStreamSynchronize(c->stream); cudaHostUnregister(const_cast<void *>(c->regs[0].p)); }
+        c->regs.erase(c->regs.begin());
+    }
+    cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {          // another context of this process pinned it
+        cudaGetLastError();
+        c->regs.push_back({ p, bytes, false });
+        return true;
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    c->regs.push_back({ p, bytes, true });
+    return true;
+}
+
 // host (32 B stride) -> device float4.  slot selects the staging pair.
 void upload_cloud(llb_ctx *c, int slot, const llb_point *src, int n, DevBuf<float4> &dst)
 {
     dst.ensure(std::max(n, 1));
     if (n <= 0) return;
     static_assert(sizeof(llb_point) == 32, "pcl::PointXYZI layout");
+    if (c->prm.pin_host_clouds && ensure_registered(c, src, (size_t)n * sizeof(llb_point))) {
+        c->raw32[slot].ensure((size_t)n * 8);
+        LLB_CUDA(cudaMemcpyAsync(c->raw32[slot].p, src, (size_t)n * sizeof(llb_point), cudaMemcpyHostToDevice, c->stream));
+        unpack_points_kernel<<<std::min(div_up(n, 256), 148 * 8), 256, 0, c->stream>>>(c->raw32[slot].p, n, dst.p);
+        LLB_CUDA(cudaGetLastError());
+        c->launches++;
+        return;
+    }
     // the staging pair of this slot may still be the source of an earlier DMA
     if (c->pin_busy[slot]) { LLB_CUDA(cudaEventSynchronize(c->pin_ev[slot])); c->pin_busy[slot] = false; }
     c->pin_in[slot].ensure((size_t)n * 8);
@@ -241,6 +279,8 @@ void llb_params_default(llb_params *p)
     p->odom_nearest_sqdist = 25.f; p->odom_max_iterations = 25; p->odom_min_correspondences = 10;
     p->odom_degeneracy_thresh = 10.f; p->odom_converge_deg = 0.1f; p->odom_converge_cm = 0.1f;
     p->max_grid_cells = 1 << 23;
+    p->pin_host_clouds = 0;
+    p->s2m_max_ctas = 0;
 }
 
 int llb_create(const llb_params *p, int device, llb_ctx **out)
@@ -283,6 +323,8 @@ int llb_destroy(llb_ctx *c)
     cudaDeviceSynchronize();
     for (int i = 0; i < 3; i++) { c->pin_in[i].release(); c->raw32[i].release(); if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]); }
     c->tmp_in.release();
+    for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
+    c->regs.clear();
     c->pin_out.release(); c->pin_counts.release(); c->pin_state.release(); c->pin_ostate.release();
     c->counts.release(); c->vox.release();
     c->cornerLast.pts.release(); c->surfLast.pts.release(); c->outlierLast.pts.release();
@@ -488,6 +530,42 @@ int llb_s2m_optimize(llb_ctx *c, float T[6], llb_stats *stats)
         if (!s.skipped) for (int i = 0; i < 6; i++) T[i] = s.T[i];
         fill_stats(c, stats, s, ms);
         c->dbg_ready = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_optimize_async(llb_ctx *c, const float T[6])
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg, 0, 1,
+                                  true, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_counts.p, c->counts.p, sizeof(int) * llb_ctx::C_N, cudaMemcpyDeviceToHost, c->stream));
+        c->async_pending = true;
+        c->dbg_ready = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_result(llb_ctx *c, float T[6], llb_stats *stats)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->async_pending) return (int)LLB_ERR_STATE;
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        c->async_pending = false;
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const S2mState &s = *c->pin_state.p;
+        if (!s.skipped) for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        fill_stats(c, stats, s, ms);
         return (int)LLB_OK;
     });
 }

@@ -499,6 +499,7 @@ int S2mSolver::run(int it_begin, int it_end, const S2mQueries &q, const MapIndex
 {
     const int nq = std::max(1, div_up(q.nc_upper + q.ns_upper, world));
     int grid = std::max(1, std::min(max_blocks_, div_up(nq, S2M_QPB)));
+    if (prm_.max_ctas > 0) grid = std::min(grid, prm_.max_ctas);
     S2mParams prm = prm_;
     S2mQueries qq = q; MapIndexView cm = cmap, sm = smap; S2mDebug dg = dbg;
     S2mState *st = state_.p; double *part = partials_.p, *acc = acc_.p;

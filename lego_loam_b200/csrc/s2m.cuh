@@ -15,6 +15,7 @@ struct S2mParams {
     float degeneracy_thresh;         // 100
     float converge_deg, converge_cm; // 0.05, 0.05
     int   corner_map_min, surf_map_min; // 10, 100
+    int   max_ctas;                  // 0 = one per SM
 };
 
 struct S2mState {                    // device-resident, persists across registrations

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Config-4 style check (run under torchrun on >= 2 GPUs): one registration with the queries sharded over the
+ranks and a 28-value fp64 NCCL all-reduce per LM iteration must reproduce the single-GPU pose.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lego_loam_b200 import api, multi_gpu, synth  # noqa: E402
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sensor = synth.SENSORS[os.environ.get("LLB_SENSOR", "hdl32e")]
+    n_c, n_s = int(os.environ.get("LLB_RAW_CORNER", "900000")), int(os.environ.get("LLB_RAW_SURF", "420000"))
+    w = synth.make_world(synth.SEED0)                       # identical inputs on every rank (same seeds)
+    pose = np.array([0.01, 0.7, -0.01, 4.0, 0.0, -3.0])
+    sc = synth.make_mapping_scan(w, sensor, pose, seed=5)
+    mc, ms = synth.make_local_map(w, pose[3:6], n_c, n_s, seed=6, radius=160.0, surf_radius=110.0)
+    init = synth.perturb_pose(pose, np.random.default_rng(9))
+    ctx = api.Context(local)
+    ctx.map_set_raw(mc, ms)                                 # the voxel-DS map is replicated (bit-identical on all ranks)
+    ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
+    counts = ctx.downsample_current_scan()
+    T_single, st = ctx.s2m_optimize(init)                   # every rank: the whole registration alone
+    res = []
+    for rep in range(5):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        T_shard, iters = multi_gpu.sharded_scan2map(ctx, init, rank, world)
+        torch.cuda.synchronize()
+        res.append((time.perf_counter() - t0) * 1e3)
+    ok = bool(np.allclose(T_shard, T_single, atol=1e-6)) and iters == st.iterations
+    gathered = [None] * world
+    dist.all_gather_object(gathered, T_shard.tolist())
+    same = all(g == gathered[0] for g in gathered)          # the redundant LM steps stayed bit-identical
+    if rank == 0:
+        print(json.dumps({"world": world, "queries": counts[0] + counts[3], "map_ds": [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])],
+                          "iterations_single": st.iterations, "iterations_sharded": iters, "pose_match": ok,
+                          "bit_identical_across_ranks": same, "max_abs_diff": float(np.max(np.abs(T_shard - T_single))),
+                          "single_gpu_device_ms": st.device_ms, "sharded_wall_ms_median": float(np.median(res))}))
+    dist.destroy_process_group()
+    ctx.close()
+    return 0 if (ok and same) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
