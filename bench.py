@@ -41,6 +41,7 @@ WORKLOADS = {
     "vlp16_100k": ("vlp16", 400000, 110000, 120.0, 60.0),
     "vlp16_50k": ("vlp16", 150000, 50000, 90.0, 45.0),
     "hdl32e_300k": ("hdl32e", 900000, 420000, 160.0, 110.0),
+    "vls128_2m": ("vls128", 1500000, 6500000, 260.0, 200.0),
 }
 
 
