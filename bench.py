@@ -359,6 +359,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = ALG_BYTES_PER_QUERY * nq / (ms_launch * 1e-3) / 1e9
+        traffic = None
+        try:                                                 # dram bytes per launch from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if args.workload == "vlp16_100k":
+                traffic = int(tj["dram_bytes_per_launch"])
+        except Exception:
+            pass
         # bounded CPU sample on this box's host cores, 1 core; also the pose check of the e2e result
         tsel = seqs[0::T][-1]                                # the sequence whose result thread 0 reported last
         run_cpu, kind = cpu_registration_factory(tsel["mc_ds"], tsel["ms_ds"], tsel["scans"])
@@ -393,7 +400,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk_samples),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "s2m_loop_kernel (one accumulate-only iteration)",
+                         "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_traffic.json (same workload)",
+                         "kernel": "s2m_loop_kernel (one accumulate-only iteration)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "ms_per_launch": ms_launch, "alg_bytes_per_launch": ALG_BYTES_PER_QUERY * nq,
                          "note": "latency/instruction-bound by construction at this size (DESIGN.md section 3)"},
