@@ -121,6 +121,15 @@ class MapOptimization:
         self.L.ref_mo_set_odometry(self._h, _fp(t), ctypes.c_double(stamp))
 
     def transformAssociateToMap(self): self.L.ref_mo_transformAssociateToMap(self._h)
+    def transformUpdate(self): self.L.ref_mo_transformUpdate(self._h)
+
+    @property
+    def transformAftMapped(self):
+        t = np.zeros(6, np.float32); self.L.ref_mo_get_aft_mapped(self._h, _fp(t)); return t
+
+    def map_ds_sizes(self):
+        a = ctypes.c_int(0); b = ctypes.c_int(0)
+        self.L.ref_mo_map_ds_sizes(self._h, ctypes.byref(a), ctypes.byref(b)); return a.value, b.value
     def extractSurroundingKeyFrames(self): self.L.ref_mo_extractSurroundingKeyFrames(self._h)
     def saveKeyFramesAndFactor(self): self.L.ref_mo_saveKeyFramesAndFactor(self._h)
     def correctPoses(self): self.L.ref_mo_correctPoses(self._h)

@@ -123,6 +123,14 @@ void ref_mo_set_odometry(void *h, const float *sum, double stamp)
     memcpy(m->transformSum, sum, 24); m->timeLaserOdometry = stamp;
 }
 void ref_mo_transformAssociateToMap(void *h) { ((mapOptimization *)h)->transformAssociateToMap(); }
+void ref_mo_transformUpdate(void *h) { ((mapOptimization *)h)->transformUpdate(); }
+void ref_mo_get_aft_mapped(void *h, float *t) { memcpy(t, ((mapOptimization *)h)->transformAftMapped, 24); }
+int ref_mo_map_ds_sizes(void *h, int *nc, int *ns)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    *nc = m->laserCloudCornerFromMapDSNum; *ns = m->laserCloudSurfFromMapDSNum;
+    return 0;
+}
 void ref_mo_extractSurroundingKeyFrames(void *h) { ((mapOptimization *)h)->extractSurroundingKeyFrames(); }
 void ref_mo_saveKeyFramesAndFactor(void *h) { ((mapOptimization *)h)->saveKeyFramesAndFactor(); }
 void ref_mo_correctPoses(void *h) { ((mapOptimization *)h)->correctPoses(); }

@@ -1,0 +1,80 @@
+"""Sequence replay (BASELINE configs[1]): the REFERENCE mapOptimization node logic (oracle/_ref: the unmodified
+mapOptmization.cpp -- key-frame store, extractSurroundingKeyFrames, transformAssociateToMap, iSAM2 stand-in)
+is run twice over the same synthetic VLP-16 sequence: once pure, once with its hot path
+(map voxel tail MO:1057-1064 + downsampleCurrentScan + scan2MapOptimization) replaced by the CUDA library
+through the C ABI.  Bars of the north star: per-scan pose within 1e-4 m / 1e-4 rad, accumulated drift within 0.1 %."""
+import numpy as np
+import pytest
+
+from lego_loam_b200 import synth
+from oracle import ref_harness
+from tests import data
+
+pytestmark = pytest.mark.gpu
+
+N_SCANS = 36
+
+
+def make_sequence(n, seed=77):
+    rng = np.random.default_rng(seed)
+    w = data.world()
+    pose = np.array([0.0, 0.3, 0.0, -6.0, 0.0, -8.0])
+    poses, odo, scans = [], [], []
+    drift = np.zeros(6)
+    for k in range(n):
+        # ~0.6 m per mapping step (1.5 m/s, one registration every 0.4 s), gentle turn, small roll/pitch
+        yaw = pose[1] + 0.02
+        step = 0.6
+        pose = np.array([0.01 * np.sin(0.3 * k), yaw, 0.01 * np.cos(0.2 * k),
+                         pose[3] + step * np.sin(yaw), 0.0, pose[5] + step * np.cos(yaw)])
+        drift += rng.normal(0, [0.0005, 0.001, 0.0005, 0.01, 0.004, 0.01])     # odometry random walk
+        poses.append(pose.copy()); odo.append((pose + drift).astype(np.float32))
+        scans.append(synth.make_mapping_scan(w, synth.VLP16, pose, seed=1000 + k))
+    return poses, odo, scans
+
+
+def replay(ctx, poses, odo, scans):
+    mo = ref_harness.MapOptimization()
+    traj, used_gpu, ds_equal = [], 0, True
+    for k, (sum_k, sc) in enumerate(zip(odo, scans)):
+        mo.set_odometry(sum_k, 0.4 * k)
+        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
+        mo.transformAssociateToMap()                 # MO:1503
+        mo.extractSurroundingKeyFrames()             # MO:1505 (includes the reference's own map voxel tail)
+        mo.downsampleCurrentScan()                   # MO:1507 (the key-frame store keeps these clouds)
+        if ctx is None:
+            mo.scan2MapOptimization()                # MO:1509
+        else:
+            nc, ns = mo.map_ds_sizes()
+            if nc > 10 and ns > 100:                 # guard MO:1331
+                ctx.map_set_raw(mo.map_raw(0), mo.map_raw(1))          # MO:1057-1064 on the device
+                ds_equal &= np.array_equal(ctx.map_get_ds(0).view(np.uint32), mo.map_ds(0).view(np.uint32))
+                ds_equal &= np.array_equal(ctx.map_get_ds(1).view(np.uint32), mo.map_ds(1).view(np.uint32))
+                ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
+                ctx.downsample_current_scan()
+                T, st = ctx.s2m_optimize(mo.transformTobeMapped)
+                mo.transformTobeMapped = T
+                mo.transformUpdate()                 # MO:1348
+                used_gpu += 1
+        mo.saveKeyFramesAndFactor()                  # MO:1511
+        mo.correctPoses()
+        mo.clearCloud()                              # MO:1519
+        traj.append(mo.transformAftMapped.copy())
+    return np.array(traj), used_gpu, ds_equal, mo.num_keyframes()
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="oracle/_ref not built")
+def test_sequence_replay_drift_parity(ctx):
+    poses, odo, scans = make_sequence(N_SCANS)
+    ref, _, _, kf_ref = replay(None, poses, odo, scans)
+    gpu, used, ds_equal, kf_gpu = replay(ctx, poses, odo, scans)
+    assert used >= N_SCANS - 2 and kf_ref == kf_gpu and kf_ref > 10
+    assert ds_equal                                                   # voxel DS of the growing local map: bit-exact
+    d = np.abs(gpu - ref)
+    assert d[:, :3].max() < 1e-4 and d[:, 3:].max() < 1e-4            # per-scan bars of the north star
+    path = np.sum(np.linalg.norm(np.diff(ref[:, 3:], axis=0), axis=1))
+    drift = np.linalg.norm(gpu[-1, 3:] - ref[-1, 3:]) / path
+    assert path > 15.0 and drift < 1e-3                               # 0.1 % of the path length
+    # and the mapping tracks the true trajectory of the synthetic world
+    truth = np.array(poses)
+    assert np.linalg.norm(gpu[-1, 3:] - truth[-1, 3:]) < 0.5
