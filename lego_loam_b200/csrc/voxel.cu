@@ -148,18 +148,35 @@ radix_scatter_kernel(const VoxelDesc *__restrict__ d, int shift, unsigned *__res
     s_base[tid] = hist[tid * gridDim.x + blockIdx.x];
     int lo, hi;
     radix_tile(d->n, gridDim.x, blockIdx.x, lo, hi);
-    for (int r = lo; r < hi; r += LG_THREADS) {
+    // Sub-tiles of 2048 keys: warp w owns the contiguous keys [w*256, (w+1)*256) of the sub-tile and ranks them
+    // in 8 rounds of 32 against its PRIVATE digit counters (warp-level sync only), so a sub-tile costs two block
+    // barriers instead of three per 256 keys.  Order of ranks = (sub-tile, warp, round, lane) = input order: stable.
+    constexpr int ITEMS = 8, SUB = LG_THREADS * ITEMS;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int sub = lo; sub < hi; sub += SUB) {
 #pragma unroll
         for (int k = 0; k < NW; k++) s_wcnt[k][tid] = 0;
         __syncthreads();
-        const int i = r + tid;
-        const bool valid = i < hi;
-        unsigned key = valid ? kin[i] : 0;
-        int val = valid ? vin[i] : 0;
-        unsigned dig = valid ? ((key >> shift) & 255) : (256 + lane);   // invalid lanes never match
-        unsigned m = __match_any_sync(FULL, dig);
-        int rank = __popc(m & ((1u << lane) - 1));
-        if (valid && rank == 0) s_wcnt[w][dig] = __popc(m);
+        unsigned key[ITEMS]; int val[ITEMS]; int rk[ITEMS]; unsigned dg[ITEMS];
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const int i = sub + w * (32 * ITEMS) + r * 32 + lane;
+            const bool valid = i < hi;
+            key[r] = valid ? kin[i] : 0u;
+            val[r] = valid ? vin[i] : 0;
+            dg[r] = valid ? ((key[r] >> shift) & 255u) : (256u + lane);    // invalid lanes never match
+        }
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const unsigned m = __match_any_sync(FULL, dg[r]);
+            const int pr = __popc(m & lt);
+            int cnt = 0;
+            if (dg[r] < 256u) cnt = s_wcnt[w][dg[r]];
+            rk[r] = cnt + pr;
+            __syncwarp();
+            if (dg[r] < 256u && pr == 0) s_wcnt[w][dg[r]] = cnt + __popc(m);
+            __syncwarp();
+        }
         __syncthreads();
         {   // thread tid owns digit tid: turn per-warp counts into offsets
             int run = s_base[tid];
@@ -168,9 +185,12 @@ radix_scatter_kernel(const VoxelDesc *__restrict__ d, int shift, unsigned *__res
             s_base[tid] = run;
         }
         __syncthreads();
-        if (valid) {
-            int pos = s_wcnt[w][dig] + rank;
-            kout[pos] = key; vout[pos] = val;
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            if (dg[r] < 256u) {
+                const int pos = s_wcnt[w][dg[r]] + rk[r];
+                kout[pos] = key[r]; vout[pos] = val[r];
+            }
         }
         __syncthreads();
     }
