@@ -196,6 +196,45 @@ int llb_s2m_get_cta_profile(llb_ctx *ctx, double *out, int capacity_ctas, int *n
 /* number of kernels launched by this context since creation (bench.py gpu_launches) */
 long long llb_launch_count(const llb_ctx *ctx);
 
+/* ---- batched multi-registration engine (BASELINE config 5: batches of independent sequences) ----
+ * n_slots independent sequences share one GPU and one stream; llb_batch_register performs, for EVERY slot,
+ * downsampleCurrentScan (MO:1067-1091) + the two kdtree->setInputCloud replacements (MO:1333-1334, only for
+ * slots whose map was set since the last step) + scan2MapOptimization (MO:1329-1350) with a number of kernel
+ * launches that does not depend on n_slots.  Each slot keeps its own isDegenerate / matP across steps (C6).
+ * Results are bit-identical to n_slots separate llb_ctx registrations up to the fp64 summation order of the
+ * normal equations.  max_scan_points bounds every one of the three scan clouds of a slot (<= 8192: the four
+ * filters of downsampleCurrentScan run on the 8-CTA cluster voxel kernel); max_map_points bounds each DS map. */
+typedef struct llb_batch llb_batch;
+int  llb_batch_create(const llb_params *p /* NULL = defaults */, int device, int n_slots, int max_scan_points,
+                      int max_map_points, llb_batch **out);
+int  llb_batch_destroy(llb_batch *b);
+const char *llb_batch_last_error(const llb_batch *b);
+void *llb_batch_stream(llb_batch *b);
+int  llb_batch_slots(const llb_batch *b);
+long long llb_batch_launch_count(const llb_batch *b);
+/* laserCloudCornerLast / SurfLast / OutlierLast of one slot (handlers MO:608-627); host clouds are DMA'd
+ * asynchronously and must stay unchanged until the next llb_batch_result (params.pin_host_clouds as for llb_ctx) */
+int  llb_batch_scan_set(llb_batch *b, int slot, const llb_point *corner_last, int nc, const llb_point *surf_last,
+                        int ns, const llb_point *outlier_last, int no);
+/* laserCloudCornerFromMapDS / SurfFromMapDS of one slot; a slot whose map is not set again keeps its index */
+int  llb_batch_map_set_ds(llb_batch *b, int slot, const llb_point *corner_ds, int mc, const llb_point *surf_ds, int ms);
+/* device-resident inputs (float4 {x,y,z,intensity}); the pointers are borrowed until the step has finished */
+int  llb_batch_scan_set_dev(llb_batch *b, int slot, const void *corner_f4, int nc, const void *surf_f4, int ns,
+                            const void *outlier_f4, int no);
+int  llb_batch_map_set_ds_dev(llb_batch *b, int slot, const void *corner_ds_f4, int mc, const void *surf_ds_f4, int ms);
+/* T: n_slots x 6 transformTobeMapped in/out; stats: n_slots entries (device_ms = the whole step) or NULL */
+int  llb_batch_register(llb_batch *b, float *T, llb_stats *stats);
+int  llb_batch_register_async(llb_batch *b, const float *T);
+int  llb_batch_result(llb_batch *b, float *T, llb_stats *stats);
+/* which: 0 cornerLastDS, 1 surfLastDS, 2 outlierLastDS, 3 surfTotalLastDS of the slot's last step */
+int  llb_batch_scan_get_ds(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
+int  llb_batch_get_degeneracy(llb_batch *b, int slot, int *is_degenerate);
+/* per-stage CUDA-event times of the last step when enabled: ms[6] = {host-cloud unpack, downsampleCurrentScan,
+ * index build, kNN kernels, fit kernels, LM-step + prepare + collect kernels}; geometry[4] = {kNN CTAs per slot,
+ * fit CTAs per slot, index-build CTAs per map, query capacity per slot} */
+int  llb_batch_set_profile(llb_batch *b, int on);
+int  llb_batch_get_profile(llb_batch *b, float ms[6], int geometry[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,10 @@ EXPORTS = [
     "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
+    "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
+    "llb_batch_launch_count", "llb_batch_scan_set", "llb_batch_map_set_ds", "llb_batch_scan_set_dev",
+    "llb_batch_map_set_ds_dev", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
+    "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
 ]
 
 _lib = None
@@ -91,6 +95,9 @@ def lib() -> ctypes.CDLL:
         L.llb_last_error.restype = ctypes.c_char_p
         L.llb_stream.restype = ctypes.c_void_p
         L.llb_launch_count.restype = ctypes.c_longlong
+        L.llb_batch_last_error.restype = ctypes.c_char_p
+        L.llb_batch_stream.restype = ctypes.c_void_p
+        L.llb_batch_launch_count.restype = ctypes.c_longlong
         for name in EXPORTS:
             getattr(L, name)   # raises AttributeError if a declared symbol is missing
         _lib = L
@@ -363,6 +370,109 @@ class Context:
         conv = ctypes.c_int(0)
         self._ck(lib().llb_s2m_solve(self._h, it, ctypes.byref(conv) if want_converged else None))
         return bool(conv.value)
+
+
+class Batch:
+    """One llb_batch: n_slots independent sequences registered per step with a slot-count-independent number of
+    launches (BASELINE config 5).  Mirrors Context's scan/map/optimise calls with a leading slot index."""
+
+    def __init__(self, device: int, n_slots: int, max_scan_points: int, max_map_points: int, params: Params | None = None):
+        L = lib()
+        self._h = ctypes.c_void_p()
+        if params is None:
+            params = default_params()
+        self.params = params
+        rc = L.llb_batch_create(ctypes.byref(params), int(device), int(n_slots), int(max_scan_points),
+                                int(max_map_points), ctypes.byref(self._h))
+        if rc != LLB_OK:
+            self._h = ctypes.c_void_p()
+            raise LlbError(rc, "llb_batch_create failed (no CPU fallback exists)")
+        self.n_slots = n_slots
+        self._keep = {}                   # host clouds stay alive (and unchanged) until the step has finished
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().llb_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != LLB_OK:
+            raise LlbError(rc, (lib().llb_batch_last_error(self._h) or b"").decode())
+
+    @property
+    def stream(self) -> int:
+        return lib().llb_batch_stream(self._h) or 0
+
+    def launch_count(self) -> int:
+        return int(lib().llb_batch_launch_count(self._h))
+
+    def scan_set(self, slot: int, corner_last, surf_last, outlier_last):
+        self.scan_set_pcl(slot, to_pcl(corner_last), to_pcl(surf_last), to_pcl(outlier_last))
+
+    def scan_set_pcl(self, slot: int, c32, s32, o32):
+        self._keep[("scan", slot)] = (c32, s32, o32)
+        self._ck(lib().llb_batch_scan_set(self._h, slot, _vp(c32), c32.shape[0], _vp(s32), s32.shape[0],
+                                          _vp(o32), o32.shape[0]))
+
+    def map_set_ds(self, slot: int, corner_ds, surf_ds):
+        self.map_set_ds_pcl(slot, to_pcl(corner_ds), to_pcl(surf_ds))
+
+    def map_set_ds_pcl(self, slot: int, c32, s32):
+        self._keep[("map", slot)] = (c32, s32)
+        self._ck(lib().llb_batch_map_set_ds(self._h, slot, _vp(c32), c32.shape[0], _vp(s32), s32.shape[0]))
+
+    def scan_set_dev(self, slot: int, c_ptr: int, nc: int, s_ptr: int, ns: int, o_ptr: int, no: int):
+        self._ck(lib().llb_batch_scan_set_dev(self._h, slot, ctypes.c_void_p(c_ptr), nc, ctypes.c_void_p(s_ptr), ns,
+                                              ctypes.c_void_p(o_ptr), no))
+
+    def map_set_ds_dev(self, slot: int, c_ptr: int, mc: int, s_ptr: int, ms: int):
+        self._ck(lib().llb_batch_map_set_ds_dev(self._h, slot, ctypes.c_void_p(c_ptr), mc, ctypes.c_void_p(s_ptr), ms))
+
+    def register(self, T):
+        """T: (n_slots, 6) initial transformTobeMapped -> (poses (n_slots, 6), [Stats] * n_slots)"""
+        t = np.ascontiguousarray(T, np.float32).reshape(self.n_slots, 6).copy()
+        st = (Stats * self.n_slots)()
+        self._ck(lib().llb_batch_register(self._h, _fp(t), st))
+        return t, list(st)
+
+    def register_async(self, T):
+        t = np.ascontiguousarray(T, np.float32).reshape(self.n_slots, 6)
+        self._async_T = t.copy()
+        self._ck(lib().llb_batch_register_async(self._h, _fp(t)))
+
+    def result(self):
+        t = self._async_T.copy()
+        st = (Stats * self.n_slots)()
+        self._ck(lib().llb_batch_result(self._h, _fp(t), st))
+        return t, list(st)
+
+    def scan_get_ds(self, slot: int, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_batch_scan_get_ds(self._h, slot, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_batch_scan_get_ds(self._h, slot, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    def get_degeneracy(self, slot: int) -> bool:
+        d = ctypes.c_int(0)
+        self._ck(lib().llb_batch_get_degeneracy(self._h, slot, ctypes.byref(d)))
+        return bool(d.value)
+
+    def set_profile(self, on: bool):
+        self._ck(lib().llb_batch_set_profile(self._h, int(on)))
+
+    def get_profile(self):
+        ms = (ctypes.c_float * 6)(); geo = (ctypes.c_int * 4)()
+        self._ck(lib().llb_batch_get_profile(self._h, ms, geo))
+        names = ["unpack", "downsample", "index_build", "knn", "fit", "lm_step"]
+        return dict(zip(names, [float(x) for x in ms])), {"knn_ctas_per_slot": geo[0], "fit_ctas_per_slot": geo[1],
+                                                          "index_ctas_per_map": geo[2], "query_capacity": geo[3]}
 
 
 def default_params() -> Params:

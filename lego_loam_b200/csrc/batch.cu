@@ -1,0 +1,278 @@
+// batch.cu — kernels of the batched multi-registration engine (see batch.cuh): every launch covers
+// ALL slots of the batch (blockIdx.y = slot), so a step costs the same number of launches for 1 or
+// 64 independent sequences.  The arithmetic is the single-registration path's (s2m_dev.cuh, knn.cuh):
+// same expressions, same association order, fp64 accumulation of exact float products in a fixed order.
+#include "batch.cuh"
+#include "s2m_dev.cuh"
+#include "knn.cuh"
+
+namespace llb {
+
+namespace {
+
+constexpr int KNN_NW = BATCH_KNN_THREADS / 32;
+constexpr int FIT_NW = BATCH_FIT_THREADS / 32;
+
+__global__ void __launch_bounds__(256)
+batch_unpack_kernel(const BatchUnpack *__restrict__ jobs)
+{
+    const BatchUnpack jb = jobs[blockIdx.y];
+    // src: pcl::PointXYZI stride (8 floats): x y z w intensity c1 c2 c3
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(jb.src32) + 2 * i);
+        const float inten = __ldg(jb.src32 + 8 * i + 4);
+        jb.dst[i] = make_float4(a.x, a.y, a.z, inten);
+    }
+}
+
+__global__ void batch_state_init_kernel(S2mState *st, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    S2mState *s = st + b;
+    for (int i = 0; i < 6; i++) { s->T[i] = 0.f; s->cs[i] = (i & 1) ? 0.f : 1.f; s->AtB[i] = 0.f; s->X[i] = 0.f; }
+    for (int i = 0; i < 36; i++) { s->matP[i] = 0.f; s->AtA[i] = 0.f; s->AtA0[i] = 0.f; }
+    s->matP_valid = 1;                                       // the reference starts with matP = 0 (MO:361)
+    s->converged = 0; s->iters = 0; s->n_corr = 0; s->is_degenerate = 0; s->skipped = 0; s->ticket = 0;
+}
+
+// pose hand-over, sin/cos of MO:498-506, guard MO:1331, flags: one thread per slot
+__global__ void batch_prepare_kernel(const BatchReg *__restrict__ regs, const float *__restrict__ poses, int B, S2mParams prm)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const BatchReg r = regs[b];
+    S2mState *st = r.st;
+    for (int i = 0; i < 6; i++) st->T[i] = poses[6 * b + i];
+    update_sincos(st);
+    st->converged = 0;
+    st->iters = 0;
+    st->n_corr = 0;
+    st->ticket = 0;
+    st->skipped = !(r.cmap.desc->n > prm.corner_map_min && r.smap.desc->n > prm.surf_map_min);
+}
+
+// ---- iteration, step 1: pointAssociateToMap + radius-bounded exact 5-NN, one THREAD per query.
+// Throughput form of knn.cuh's search: a thread walks the (up to) nine cell runs around its query and keeps the five
+// smallest (distance, original index) pairs inside the gate in registers - ~10 instructions per candidate instead of
+// a warp-wide ballot / compaction / arg-min per 32 candidates (measured 4.5x fewer warp instructions per query).
+// Consecutive queries are voxel-ordered DS points, i.e. spatial neighbours: the lanes of a warp read the same cells
+// and the float4 candidate loads hit L1.  Rows whose slab is farther than the gate radius are skipped (1 % margin:
+// cell membership is decided by the same floorf expression for map points and queries, rounding differences are
+// orders of magnitude below the margin).
+__global__ void __launch_bounds__(BATCH_KNN_THREADS, 4)
+batch_knn_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
+{
+    const BatchReg r = regs[blockIdx.y];
+    const S2mState *st = r.st;
+    if (__ldcg(&st->skipped) || __ldcg(&st->converged)) return;
+    const float crx = __ldcg(&st->cs[0]), srx = __ldcg(&st->cs[1]), cry = __ldcg(&st->cs[2]),
+                sry = __ldcg(&st->cs[3]), crz = __ldcg(&st->cs[4]), srz = __ldcg(&st->cs[5]);
+    const float tX = __ldcg(&st->T[3]), tY = __ldcg(&st->T[4]), tZ = __ldcg(&st->T[5]);
+    const int nc = *r.nc_dev, ns = *r.ns_dev;
+    const int nq = min(nc + ns, r.cap);
+    const float max_sq = prm.knn_max_sqdist;
+    const float prune_sq = max_sq * 1.01f;
+    for (int q = blockIdx.x * BATCH_KNN_THREADS + threadIdx.x; q < nq; q += gridDim.x * BATCH_KNN_THREADS) {
+        const bool is_corner = q < nc;
+        const float4 po = is_corner ? __ldg(&r.corner[q]) : __ldg(&r.surf[q - nc]);
+        float sx, sy, sz;
+        associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
+        const GridDesc *g = is_corner ? r.cmap.desc : r.smap.desc;
+        const int *__restrict__ cell_begin = is_corner ? r.cmap.cell_begin : r.smap.cell_begin;
+        const int *__restrict__ row_begin = is_corner ? r.cmap.row_begin : r.smap.row_begin;
+        const float4 *__restrict__ sorted = is_corner ? r.cmap.sorted : r.smap.sorted;
+        const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
+        const float inv = g->inv_cell, cell = g->cell;
+        const float fy = (sy - g->org[1]) * inv, fz = (sz - g->org[2]) * inv;
+        const int cx = grid_coord(sx, g->org[0], inv), cy = (int)floorf(fy), cz = (int)floorf(fz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
+        // distance from the query to the neighbouring rows' slabs, in metres (0 for the query's own row)
+        const float ly = (fy - (float)cy) * cell, lz = (fz - (float)cz) * cell;
+        float bd[5]; int bi[5], bp[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) { bd[k] = __int_as_float(0x7f800000); bi[k] = 0x7fffffff; bp[k] = -1; }
+        int found = 0;
+        if (x0 <= x1) {
+#pragma unroll 1
+            for (int rr = 0; rr < 9; rr++) {
+                const int dy = (rr % 3) - 1, dz = (rr / 3) - 1;
+                const int y = cy + dy, z = cz + dz;
+                if (y < 0 || y >= dimy || z < 0 || z >= dimz) continue;
+                const float gy = dy < 0 ? ly : (dy > 0 ? cell - ly : 0.f);
+                const float gz = dz < 0 ? lz : (dz > 0 ? cell - lz : 0.f);
+                if (gy * gy + gz * gz > prune_sq) continue;
+                const int ry = z * dimy + y;
+                if (__ldg(&row_begin[ry + 1]) == __ldg(&row_begin[ry])) continue;     // empty row: no cell table there
+                const int row = ry * dimx;
+                const int rb = __ldg(&cell_begin[row + x0]), re = __ldg(&cell_begin[row + x1 + 1]);
+#pragma unroll 2
+                for (int i = rb; i < re; i++) {
+                    const float4 p = __ldg(&sorted[i]);
+                    const float d = l2_simple(sx, sy, sz, p);
+                    if (d < max_sq) {
+                        found++;
+                        const int oi = __float_as_int(p.w);
+                        if (d < bd[4] || (d == bd[4] && oi < bi[4])) {
+                            // insert (d, oi) into the ascending list, dropping the last entry
+                            bd[4] = d; bi[4] = oi; bp[4] = i;
+#pragma unroll
+                            for (int k = 4; k > 0; k--) {
+                                const bool sw = bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1]);
+                                if (sw) {
+                                    const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                                    const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                                    const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = found >= 5 ? bp[k] : -1;
+        r.d5[q] = found >= 5 ? bd[4] : -1.f;
+    }
+}
+
+// ---- iteration, step 2: gate, line / plane fit, residual, Jacobian row (one THREAD per query; corner and
+// surf queries live in different warps), then the 28 fp64 products of the rows of this CTA
+__global__ void __launch_bounds__(BATCH_FIT_THREADS)
+batch_fit_kernel(const BatchReg *__restrict__ regs, int iter, S2mParams prm)
+{
+    __shared__ float s_row[8][BATCH_FIT_THREADS];
+    __shared__ double s_acc[FIT_NW][32];
+    const BatchReg r = regs[blockIdx.y];
+    const S2mState *st = r.st;
+    if (__ldcg(&st->skipped) || __ldcg(&st->converged)) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float crx = __ldcg(&st->cs[0]), srx = __ldcg(&st->cs[1]), cry = __ldcg(&st->cs[2]),
+                sry = __ldcg(&st->cs[3]), crz = __ldcg(&st->cs[4]), srz = __ldcg(&st->cs[5]);
+    const float tX = __ldcg(&st->T[3]), tY = __ldcg(&st->T[4]), tZ = __ldcg(&st->T[5]);
+    const int nc = *r.nc_dev, ns = *r.ns_dev;
+    const int nq = min(nc + ns, r.cap);
+    const int nc_pad = (nc + 31) & ~31;                      // surf rows start on a warp boundary
+    const int total = nc_pad + (nq - min(nc, nq));
+    int ia, ib;
+    pair_of(lane, ia, ib);
+    double acc = 0.0;
+    for (int base = blockIdx.x * BATCH_FIT_THREADS; base < total; base += gridDim.x * BATCH_FIT_THREADS) {
+        const int s = base + tid;
+        const bool is_corner = s < nc_pad;
+        const int q = is_corner ? s : s - nc_pad + nc;
+        const bool live = is_corner ? (s < nc && s < nq) : (q < nq);
+        float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+        if (live) {
+            const float d5 = r.d5[q];
+            if ((d5 >= 0.f) && ((double)d5 < (double)prm.knn_max_sqdist)) {       // MO:1101 / MO:1183
+                const float4 po = is_corner ? __ldg(&r.corner[q]) : __ldg(&r.surf[q - nc]);
+                float sx, sy, sz;
+                associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
+                const float4 *sorted = is_corner ? r.cmap.sorted : r.smap.sorted;
+                float nx[5], ny[5], nz[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const float4 p = __ldg(&sorted[r.nn[(size_t)k * r.cap + q]]);
+                    nx[k] = p.x; ny[k] = p.y; nz[k] = p.z;
+                }
+                float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool ok = is_corner ? corner_fit(nx, ny, nz, sx, sy, sz, coeff) : surf_fit(nx, ny, nz, sx, sy, sz, coeff);
+                if (ok) jacobian_row(crx, srx, cry, sry, crz, srz, po.x, po.y, po.z, coeff, v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_row[k][tid] = v[k];
+        __syncthreads();
+        if (lane < S2M_ACC)
+            for (int rr = w; rr < BATCH_FIT_THREADS; rr += FIT_NW) acc += (double)s_row[ia][rr] * (double)s_row[ib][rr];
+        __syncthreads();
+    }
+    s_acc[w][lane] = acc;
+    __syncthreads();
+    if (tid < S2M_ACC) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < FIT_NW; k++) sum += s_acc[k][tid];
+        r.partials[(size_t)blockIdx.x * S2M_ACC + tid] = sum;
+    }
+    // ---- the LAST CTA of this slot to get here adds the CTA partials in a fixed order and performs the
+    // LMOptimization tail (MO:1273-1326): no separate launch, no host round trip
+    __shared__ int s_last;
+    __shared__ double s_tot[32];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&r.st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 32) {
+        double s = 0.0;
+        if (lane < S2M_ACC)
+            for (int b = 0; b < (int)gridDim.x; b++) s += __ldcg(&r.partials[(size_t)b * S2M_ACC + lane]);
+        s_tot[lane] = s;
+        __syncwarp();
+        S2mState *stw = r.st;
+        if (lane == 0) { stw->ticket = 0; lm_solve(stw, s_tot, iter, prm, false); }
+        __syncwarp();
+        if (lane < 6) {                                      // sin/cos of the new pose, one per lane
+            const double a = (double)stw->T[lane >> 1];
+            stw->cs[lane] = (lane & 1) ? (float)sin(a) : (float)cos(a);
+        }
+    }
+}
+
+__global__ void batch_collect_kernel(const BatchReg *__restrict__ regs, int B, BatchResult *__restrict__ out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const BatchReg r = regs[b];
+    const S2mState *st = r.st;
+    BatchResult o;
+    for (int i = 0; i < 6; i++) o.T[i] = st->T[i];
+    o.iters = st->iters; o.converged = st->converged; o.n_corr = st->n_corr; o.is_degenerate = st->is_degenerate;
+    o.skipped = st->skipped; o.nc = *r.nc_dev; o.ns = *r.ns_dev; o.pad = 0;
+    out[b] = o;
+}
+
+}  // namespace
+
+void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s)
+{
+    if (count <= 0) return;
+    const dim3 grid(std::max(1, std::min(div_up(std::max(n_max, 1), 256), 64)), count);
+    batch_unpack_kernel<<<grid, 256, 0, s>>>(jobs_dev);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_batch_state_init(S2mState *st, int B, cudaStream_t s)
+{
+    batch_state_init_kernel<<<div_up(B, 128), 128, 0, s>>>(st, B);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, cudaStream_t s)
+{
+    batch_prepare_kernel<<<div_up(B, 128), 128, 0, s>>>(regs, poses_dev, B, prm);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s)
+{
+    batch_knn_kernel<<<dim3(std::max(1, ctas_per_slot), B), BATCH_KNN_THREADS, 0, s>>>(regs, prm);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_batch_fit(const BatchReg *regs, int B, int fit_blocks, int iter, const S2mParams &prm, cudaStream_t s)
+{
+    batch_fit_kernel<<<dim3(std::max(1, fit_blocks), B), BATCH_FIT_THREADS, 0, s>>>(regs, iter, prm);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_batch_collect(const BatchReg *regs, int B, BatchResult *out, cudaStream_t s)
+{
+    batch_collect_kernel<<<div_up(B, 128), 128, 0, s>>>(regs, B, out);
+    LLB_CUDA(cudaGetLastError());
+}
+
+}  // namespace llb

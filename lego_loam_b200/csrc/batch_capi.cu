@@ -1,0 +1,517 @@
+// batch_capi.cu — C ABI of the batched multi-registration engine (llb_batch_* in include/llb200.h):
+// B independent sequences on one GPU, one stream, a fixed number of launches per step (batch.cuh).
+// No CPU fallback: llb_batch_create fails with LLB_ERR_NO_DEVICE without an sm_100 device.
+#include "../../include/llb200.h"
+#include "batch.cuh"
+
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+using namespace llb;
+
+namespace {
+
+// everything the kernels of one step read that the host decides: uploaded with ONE H2D copy per step
+struct StepLayout {
+    size_t off_scan_n, off_map_n, off_poses, off_small1, off_small2, off_grid, off_regs, off_unpack, bytes;
+    explicit StepLayout(int B)
+    {
+        size_t o = 0;
+        auto take = [&](size_t n) { size_t r = o; o = (o + n + 255) & ~(size_t)255; return r; };
+        off_scan_n = take(sizeof(int) * 3 * B);
+        off_map_n = take(sizeof(int) * 2 * B);
+        off_poses = take(sizeof(float) * 6 * B);
+        off_small1 = take(sizeof(SmallJob) * 3 * B);
+        off_small2 = take(sizeof(SmallJob) * B);
+        off_grid = take(sizeof(GridJob) * 2 * B);
+        off_regs = take(sizeof(BatchReg) * B);
+        off_unpack = take(sizeof(BatchUnpack) * 5 * B);
+        bytes = o;
+    }
+};
+
+constexpr int RING = 3;
+constexpr int PROF_N = 6;      // unpack+copies, downsample, index, knn, fit, solve(+prepare/collect)
+
+}  // namespace
+
+struct llb_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    llb_params prm{};
+    S2mParams sprm{};
+    std::string err;
+    long long launches = 0;
+    int vox_cap1 = 1024, vox_cap2 = 1024;
+    int B = 0, cap_scan = 0, cap_map = 0, qcap = 0, fit_blocks = 0, knn_ctas = 0, grid_ctas = 0;
+    StepLayout lay{ 1 };
+
+    // per-slot device buffers, sliced out of big allocations
+    DevBuf<float4> scan_in;      // [B][3][cap_scan]  own copies of host uploads
+    DevBuf<float> scan_raw;      // [B][3][cap_scan*8]
+    DevBuf<float4> scan_ds;      // [B][5*cap_scan]: cornerDS | surfDS | outlierDS | surfTotalDS (2*cap_scan)
+    DevBuf<float4> map_in;       // [B][2][cap_map]
+    DevBuf<float> map_raw;       // [B][2][cap_map*8]
+    DevBuf<int> ds_n;            // [B][4]
+    std::vector<GridIndex> grids;   // 2B
+    DevBuf<S2mState> states;
+    DevBuf<int> nn; DevBuf<float> d5; DevBuf<double> partials;
+    DevBuf<BatchResult> results;
+    PinnedBuf<BatchResult> pin_results;
+    DevBuf<unsigned char> step_dev;
+    PinnedBuf<unsigned char> step_pin[RING];
+    cudaEvent_t step_ev[RING] = {};
+    bool step_busy[RING] = {};
+    int ring_pos = 0;
+
+    // host-side slot state
+    struct Slot {
+        const float4 *scan[3] = { nullptr, nullptr, nullptr }; int scan_n[3] = { 0, 0, 0 };
+        const float4 *map[2] = { nullptr, nullptr }; int map_n[2] = { 0, 0 };
+        bool scan_set = false, map_set = false, map_dirty = false;
+    };
+    std::vector<Slot> slots;
+    std::vector<BatchUnpack> pending_unpack;
+    int pending_unpack_max = 0;
+    struct Reg { const void *p; size_t bytes; bool ours; };
+    std::vector<Reg> regs;
+    std::vector<PinnedBuf<float>> stage;     // [B*5] lazily allocated staging (pin_host_clouds == 0)
+    std::vector<cudaEvent_t> stage_ev; std::vector<char> stage_busy;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool pending = false;
+    bool profile = false;
+    cudaEvent_t pev[64] = {};
+    int n_pev = 0;
+    int pev_kind[64] = {};
+    float prof_ms[PROF_N] = {};
+};
+
+namespace {
+
+template <typename F>
+int guarded(llb_batch *b, F &&f)
+{
+    if (!b) return LLB_ERR_INVALID;
+    try {
+        cudaError_t e = cudaSetDevice(b->device);
+        if (e != cudaSuccess) { b->err = cudaGetErrorString(e); return LLB_ERR_CUDA; }
+        return f();
+    } catch (const CudaError &e) {
+        b->err = e.what();
+        return LLB_ERR_CUDA;
+    } catch (const std::exception &e) {
+        b->err = e.what();
+        return LLB_ERR_INVALID;
+    }
+}
+
+bool ensure_registered(llb_batch *c, const void *p, size_t bytes)
+{
+    for (auto &r : c->regs)
+        if (r.p == p && r.bytes >= bytes) return true;
+    for (size_t i = 0; i < c->regs.size(); i++)
+        if (c->regs[i].p == p) {
+            if (c->regs[i].ours) { cudaStreamSynchronize(c->stream); cudaHostUnregister(const_cast<void *>(p)); }
+            c->regs.erase(c->regs.begin() + i);
+            break;
+        }
+    if (c->regs.size() >= 1024) {
+        if (c->regs[0].ours) { cudaStreamSynchronize(c->stream); cudaHostUnregister(const_cast<void *>(c->regs[0].p)); }
+        c->regs.erase(c->regs.begin());
+    }
+    cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); c->regs.push_back({ p, bytes, false }); return true; }
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    c->regs.push_back({ p, bytes, true });
+    return true;
+}
+
+// host cloud (32 B stride) -> raw device slice (async DMA) + a pending unpack job into dst
+void upload(llb_batch *c, int stage_id, const llb_point *src, int n, float *raw_dev, float4 *dst)
+{
+    if (n <= 0) return;
+    const size_t bytes = (size_t)n * sizeof(llb_point);
+    if (c->prm.pin_host_clouds && ensure_registered(c, src, bytes)) {
+        LLB_CUDA(cudaMemcpyAsync(raw_dev, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if (c->stage_busy[stage_id]) { LLB_CUDA(cudaEventSynchronize(c->stage_ev[stage_id])); c->stage_busy[stage_id] = 0; }
+        c->stage[stage_id].ensure((size_t)n * 8);
+        std::memcpy(c->stage[stage_id].p, src, bytes);
+        LLB_CUDA(cudaMemcpyAsync(raw_dev, c->stage[stage_id].p, bytes, cudaMemcpyHostToDevice, c->stream));
+        LLB_CUDA(cudaEventRecord(c->stage_ev[stage_id], c->stream));
+        c->stage_busy[stage_id] = 1;
+    }
+    c->pending_unpack.push_back(BatchUnpack{ raw_dev, dst, n });
+    c->pending_unpack_max = std::max(c->pending_unpack_max, n);
+}
+
+void prof_mark(llb_batch *c, int kind)
+{
+    if (!c->profile || c->n_pev >= 64) return;
+    LLB_CUDA(cudaEventRecord(c->pev[c->n_pev], c->stream));
+    c->pev_kind[c->n_pev] = kind;
+    c->n_pev++;
+}
+
+int enqueue_step(llb_batch *c, const float *T)
+{
+    const int B = c->B;
+    for (int s = 0; s < B; s++)
+        if (!c->slots[s].scan_set || !c->slots[s].map_set) return LLB_ERR_STATE;
+    // ---- build this step's tables in the next pinned block
+    const int rp = c->ring_pos;
+    c->ring_pos = (rp + 1) % RING;
+    if (c->step_busy[rp]) { LLB_CUDA(cudaEventSynchronize(c->step_ev[rp])); c->step_busy[rp] = false; }
+    unsigned char *hp = c->step_pin[rp].p, *dp = c->step_dev.p;
+    const StepLayout &L = c->lay;
+    int *h_scan_n = (int *)(hp + L.off_scan_n), *h_map_n = (int *)(hp + L.off_map_n);
+    float *h_poses = (float *)(hp + L.off_poses);
+    SmallJob *h_s1 = (SmallJob *)(hp + L.off_small1), *h_s2 = (SmallJob *)(hp + L.off_small2);
+    GridJob *h_grid = (GridJob *)(hp + L.off_grid);
+    BatchReg *h_regs = (BatchReg *)(hp + L.off_regs);
+    BatchUnpack *h_unp = (BatchUnpack *)(hp + L.off_unpack);
+    const int *d_scan_n = (const int *)(dp + L.off_scan_n), *d_map_n = (const int *)(dp + L.off_map_n);
+    const float leaf[3] = { c->prm.corner_leaf, c->prm.surf_leaf, c->prm.outlier_leaf };
+    int ngrid = 0, map_n_max = 1;
+    int vmax1 = 1, vmax2 = 1;
+    for (int s = 0; s < B; s++) {
+        llb_batch::Slot &sl = c->slots[s];
+        float4 *ds = c->scan_ds.p + (size_t)s * 5 * c->cap_scan;
+        float4 *ds_out[4] = { ds, ds + c->cap_scan, ds + 2 * (size_t)c->cap_scan, ds + 3 * (size_t)c->cap_scan };
+        int *dsn = c->ds_n.p + 4 * s;
+        for (int k = 0; k < 3; k++) {
+            h_scan_n[3 * s + k] = sl.scan_n[k];
+            SmallJob &j = h_s1[3 * s + k];                   // MO:1069-1082
+            j.in.a = sl.scan[k]; j.in.na_dev = d_scan_n + 3 * s + k; j.in.na = sl.scan_n[k];
+            j.in.b = nullptr; j.in.nb_dev = nullptr; j.in.nb = 0;
+            j.leaf = leaf[k]; j.out = ds_out[k]; j.n_out = dsn + k;
+        }
+        vmax1 = std::max(vmax1, std::max(sl.scan_n[0], std::max(sl.scan_n[1], sl.scan_n[2])));
+        vmax2 = std::max(vmax2, sl.scan_n[1] + sl.scan_n[2]);
+        SmallJob &t = h_s2[s];                               // MO:1084-1090 (C12): surfDS + outlierDS -> DS again
+        t.in.a = ds_out[1]; t.in.na_dev = dsn + 1; t.in.na = sl.scan_n[1];
+        t.in.b = ds_out[2]; t.in.nb_dev = dsn + 2; t.in.nb = sl.scan_n[2];
+        t.leaf = c->prm.surf_leaf; t.out = ds_out[3]; t.n_out = dsn + 3;
+        for (int k = 0; k < 2; k++) {
+            h_map_n[2 * s + k] = sl.map_n[k];
+            if (sl.map_dirty) {
+                h_grid[ngrid++] = c->grids[2 * s + k].job(sl.map[k], d_map_n + 2 * s + k, sl.map_n[k]);
+                map_n_max = std::max(map_n_max, sl.map_n[k]);
+            }
+        }
+        sl.map_dirty = false;
+        BatchReg &r = h_regs[s];
+        r.corner = ds_out[0]; r.surf = ds_out[3]; r.nc_dev = dsn + 0; r.ns_dev = dsn + 3;
+        r.cmap = c->grids[2 * s].view(); r.smap = c->grids[2 * s + 1].view();
+        r.st = c->states.p + s;
+        r.nn = c->nn.p + (size_t)s * 5 * c->qcap; r.d5 = c->d5.p + (size_t)s * c->qcap;
+        r.partials = c->partials.p + (size_t)s * c->fit_blocks * S2M_ACC;
+        r.cap = c->qcap;
+        for (int i = 0; i < 6; i++) h_poses[6 * s + i] = T[6 * s + i];
+    }
+    // shared-memory capacity of the two voxel launches: this step's largest filter, rounded to 1024 points
+    c->vox_cap1 = (vmax1 + 1023) & ~1023; c->vox_cap2 = (vmax2 + 1023) & ~1023;
+    const int nunp = (int)c->pending_unpack.size();
+    if (nunp > 5 * B) return LLB_ERR_STATE;
+    for (int i = 0; i < nunp; i++) h_unp[i] = c->pending_unpack[i];
+    const int unp_max = c->pending_unpack_max;
+    c->pending_unpack.clear(); c->pending_unpack_max = 0;
+
+    // ---- enqueue
+    c->n_pev = 0;
+    LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    prof_mark(c, -1);
+    LLB_CUDA(cudaMemcpyAsync(dp, hp, L.bytes, cudaMemcpyHostToDevice, c->stream));
+    LLB_CUDA(cudaEventRecord(c->step_ev[rp], c->stream));
+    c->step_busy[rp] = true;
+    if (nunp > 0) {
+        launch_batch_unpack((const BatchUnpack *)(dp + L.off_unpack), nunp, unp_max, c->stream);
+        c->launches++;
+    }
+    prof_mark(c, 0);
+    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream);
+    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream);
+    c->launches += 2;
+    prof_mark(c, 1);
+    if (ngrid > 0)
+        c->launches += GridIndex::build_table((const GridJob *)(dp + L.off_grid), ngrid, map_n_max,
+                                              std::sqrt(c->prm.knn_max_sqdist), c->grids[0].max_cells(), c->grid_ctas, c->stream);
+    prof_mark(c, 2);
+    const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
+    launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
+    c->launches++;
+    prof_mark(c, 5);
+    for (int it = 0; it < c->prm.s2m_max_iterations; it++) {
+        launch_batch_knn(regs, B, c->knn_ctas, c->sprm, c->stream);
+        prof_mark(c, 3);
+        launch_batch_fit(regs, B, c->fit_blocks, it, c->sprm, c->stream);
+        prof_mark(c, 4);
+        c->launches += 2;
+    }
+    launch_batch_collect(regs, B, c->results.p, c->stream);
+    c->launches++;
+    prof_mark(c, 5);
+    LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    LLB_CUDA(cudaMemcpyAsync(c->pin_results.p, c->results.p, sizeof(BatchResult) * B, cudaMemcpyDeviceToHost, c->stream));
+    c->pending = true;
+    return LLB_OK;
+}
+
+int fetch_result(llb_batch *c, float *T, llb_stats *stats)
+{
+    if (!c->pending) return LLB_ERR_STATE;
+    LLB_CUDA(cudaStreamSynchronize(c->stream));
+    c->pending = false;
+    float ms = 0.f;
+    LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    for (int s = 0; s < c->B; s++) {
+        const BatchResult &r = c->pin_results.p[s];
+        if (T && !r.skipped) for (int i = 0; i < 6; i++) T[6 * s + i] = r.T[i];
+        if (stats) {
+            llb_stats &st = stats[s];
+            st.iterations = r.iters; st.converged = r.converged; st.n_correspondences = r.n_corr;
+            st.is_degenerate = r.is_degenerate; st.skipped = r.skipped; st.n_corner_ds = r.nc; st.n_surf_ds = r.ns;
+            st.device_ms = ms;
+        }
+    }
+    if (c->profile) {
+        for (int k = 0; k < PROF_N; k++) c->prof_ms[k] = 0.f;
+        for (int i = 1; i < c->n_pev; i++) {
+            float d = 0.f;
+            LLB_CUDA(cudaEventElapsedTime(&d, c->pev[i - 1], c->pev[i]));
+            if (c->pev_kind[i] >= 0 && c->pev_kind[i] < PROF_N) c->prof_ms[c->pev_kind[i]] += d;
+        }
+    }
+    return LLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_points, int max_map_points, llb_batch **out)
+{
+    if (!out) return LLB_ERR_INVALID;
+    *out = nullptr;
+    if (n_slots < 1 || n_slots > 4096 || max_scan_points < 1 || max_map_points < 1) return LLB_ERR_INVALID;
+    // every filter of downsampleCurrentScan must fit the cluster voxel kernel (surf + outlier are concatenated)
+    if (max_scan_points > VoxelFilter::SMALL_MAX / 2) return LLB_ERR_CAPACITY;   // 8192
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LLB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return LLB_ERR_NO_DEVICE;
+    llb_batch *c = new llb_batch();
+    c->device = device;
+    if (p) c->prm = *p; else llb_params_default(&c->prm);
+    int rc = guarded(c, [&]() {
+        const int B = n_slots;
+        c->B = B; c->cap_scan = max_scan_points; c->cap_map = max_map_points;
+        c->qcap = 3 * max_scan_points;
+        c->lay = StepLayout(B);
+        S2mParams &q = c->sprm;
+        q.knn_max_sqdist = c->prm.knn_max_sqdist; q.min_corr = c->prm.s2m_min_correspondences;
+        q.degeneracy_thresh = c->prm.s2m_degeneracy_thresh; q.converge_deg = c->prm.s2m_converge_deg;
+        q.converge_cm = c->prm.s2m_converge_cm; q.corner_map_min = c->prm.corner_map_min;
+        q.surf_map_min = c->prm.surf_map_min; q.max_ctas = 0;
+        LLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        LLB_CUDA(cudaEventCreate(&c->ev0)); LLB_CUDA(cudaEventCreate(&c->ev1));
+        for (int i = 0; i < 64; i++) LLB_CUDA(cudaEventCreate(&c->pev[i]));
+        for (int i = 0; i < RING; i++) {
+            LLB_CUDA(cudaEventCreateWithFlags(&c->step_ev[i], cudaEventDisableTiming));
+            c->step_pin[i].ensure(c->lay.bytes);
+        }
+        c->step_dev.ensure(c->lay.bytes);
+        c->scan_in.ensure((size_t)B * 3 * c->cap_scan);
+        c->scan_raw.ensure((size_t)B * 3 * c->cap_scan * 8);
+        c->scan_ds.ensure((size_t)B * 5 * c->cap_scan);
+        c->map_in.ensure((size_t)B * 2 * c->cap_map);
+        c->map_raw.ensure((size_t)B * 2 * c->cap_map * 8);
+        c->ds_n.ensure((size_t)B * 4);
+        LLB_CUDA(cudaMemset(c->ds_n.p, 0, sizeof(int) * 4 * B));
+        c->states.ensure(B);
+        c->nn.ensure((size_t)B * 5 * c->qcap); c->d5.ensure((size_t)B * c->qcap);
+        // launch geometry: enough CTAs to fill 148 SMs several times over, independent of B
+        c->fit_blocks = std::max(1, std::min(div_up(c->qcap, BATCH_FIT_THREADS), std::max(2, 148 * 8 / B)));
+        c->knn_ctas = std::max(1, std::min(div_up(c->qcap, BATCH_KNN_THREADS), std::max(2, 148 * 8 / B)));
+        c->grid_ctas = std::max(2, std::min(148 * 4, 148 * 8 / (2 * B)));
+        c->partials.ensure((size_t)B * c->fit_blocks * S2M_ACC);
+        c->results.ensure(B); c->pin_results.ensure(B);
+        const int cells = std::min(c->prm.max_grid_cells, 1 << 22);
+        c->grids.resize(2 * (size_t)B);
+        for (auto &g : c->grids) { g.init(cells); g.job(nullptr, nullptr, c->cap_map); }
+        c->slots.resize(B);
+        c->stage.resize((size_t)B * 5); c->stage_ev.assign((size_t)B * 5, nullptr); c->stage_busy.assign((size_t)B * 5, 0);
+        for (auto &e : c->stage_ev) LLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        launch_batch_state_init(c->states.p, B, c->stream);
+        LLB_CUDA(cudaDeviceSynchronize());
+        return (int)LLB_OK;
+    });
+    if (rc != LLB_OK) { llb_batch_destroy(c); return rc; }
+    *out = c;
+    return LLB_OK;
+}
+
+int llb_batch_destroy(llb_batch *c)
+{
+    if (!c) return LLB_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
+    c->scan_in.release(); c->scan_raw.release(); c->scan_ds.release(); c->map_in.release(); c->map_raw.release();
+    c->ds_n.release(); c->states.release(); c->nn.release(); c->d5.release(); c->partials.release();
+    c->results.release(); c->pin_results.release(); c->step_dev.release();
+    for (int i = 0; i < RING; i++) { c->step_pin[i].release(); if (c->step_ev[i]) cudaEventDestroy(c->step_ev[i]); }
+    for (auto &g : c->grids) g.release();
+    for (auto &s : c->stage) s.release();
+    for (auto &e : c->stage_ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 64; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LLB_OK;
+}
+
+const char *llb_batch_last_error(const llb_batch *c) { return c ? c->err.c_str() : "null batch"; }
+void *llb_batch_stream(llb_batch *c) { return c ? (void *)c->stream : nullptr; }
+long long llb_batch_launch_count(const llb_batch *c) { return c ? c->launches : 0; }
+int llb_batch_slots(const llb_batch *c) { return c ? c->B : 0; }
+
+int llb_batch_scan_set(llb_batch *c, int slot, const llb_point *corner, int nc, const llb_point *surf, int ns,
+                       const llb_point *outlier, int no)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || nc < 0 || ns < 0 || no < 0 || (nc > 0 && !corner) || (ns > 0 && !surf) ||
+            (no > 0 && !outlier)) return (int)LLB_ERR_INVALID;
+        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan) return (int)LLB_ERR_CAPACITY;
+        const llb_point *src[3] = { corner, surf, outlier };
+        const int n[3] = { nc, ns, no };
+        llb_batch::Slot &sl = c->slots[slot];
+        for (int k = 0; k < 3; k++) {
+            float4 *dst = c->scan_in.p + ((size_t)slot * 3 + k) * c->cap_scan;
+            upload(c, slot * 5 + k, src[k], n[k], c->scan_raw.p + ((size_t)slot * 3 + k) * c->cap_scan * 8, dst);
+            sl.scan[k] = dst; sl.scan_n[k] = n[k];
+        }
+        sl.scan_set = true;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_scan_set_dev(llb_batch *c, int slot, const void *corner, int nc, const void *surf, int ns,
+                           const void *outlier, int no)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || nc < 0 || ns < 0 || no < 0) return (int)LLB_ERR_INVALID;
+        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan) return (int)LLB_ERR_CAPACITY;
+        llb_batch::Slot &sl = c->slots[slot];
+        sl.scan[0] = (const float4 *)corner; sl.scan[1] = (const float4 *)surf; sl.scan[2] = (const float4 *)outlier;
+        sl.scan_n[0] = nc; sl.scan_n[1] = ns; sl.scan_n[2] = no;
+        sl.scan_set = true;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_map_set_ds(llb_batch *c, int slot, const llb_point *corner, int mc, const llb_point *surf, int ms)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || mc < 0 || ms < 0 || (mc > 0 && !corner) || (ms > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        if (mc > c->cap_map || ms > c->cap_map) return (int)LLB_ERR_CAPACITY;
+        const llb_point *src[2] = { corner, surf };
+        const int n[2] = { mc, ms };
+        llb_batch::Slot &sl = c->slots[slot];
+        for (int k = 0; k < 2; k++) {
+            float4 *dst = c->map_in.p + ((size_t)slot * 2 + k) * c->cap_map;
+            upload(c, slot * 5 + 3 + k, src[k], n[k], c->map_raw.p + ((size_t)slot * 2 + k) * c->cap_map * 8, dst);
+            sl.map[k] = dst; sl.map_n[k] = n[k];
+        }
+        sl.map_set = true; sl.map_dirty = true;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_map_set_ds_dev(llb_batch *c, int slot, const void *corner, int mc, const void *surf, int ms)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || mc < 0 || ms < 0) return (int)LLB_ERR_INVALID;
+        if (mc > c->cap_map || ms > c->cap_map) return (int)LLB_ERR_CAPACITY;
+        llb_batch::Slot &sl = c->slots[slot];
+        sl.map[0] = (const float4 *)corner; sl.map[1] = (const float4 *)surf;
+        sl.map_n[0] = mc; sl.map_n[1] = ms;
+        sl.map_set = true; sl.map_dirty = true;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_register_async(llb_batch *c, const float *T)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (c->pending) return (int)LLB_ERR_STATE;
+        return enqueue_step(c, T);
+    });
+}
+
+int llb_batch_result(llb_batch *c, float *T, llb_stats *stats)
+{
+    return guarded(c, [&]() { return fetch_result(c, T, stats); });
+}
+
+int llb_batch_register(llb_batch *c, float *T, llb_stats *stats)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (c->pending) return (int)LLB_ERR_STATE;
+        int rc = enqueue_step(c, T);
+        if (rc != LLB_OK) return rc;
+        return fetch_result(c, T, stats);
+    });
+}
+
+int llb_batch_scan_get_ds(llb_batch *c, int slot, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || slot < 0 || slot >= c->B || which < 0 || which > 3) return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        int cnt[4];
+        LLB_CUDA(cudaMemcpy(cnt, c->ds_n.p + 4 * slot, sizeof(cnt), cudaMemcpyDeviceToHost));
+        *n = cnt[which];
+        if (!out) return (int)LLB_OK;
+        if (cnt[which] > cap) return (int)LLB_ERR_CAPACITY;
+        std::vector<float4> tmp(std::max(cnt[which], 1));
+        const float4 *src = c->scan_ds.p + (size_t)slot * 5 * c->cap_scan + (size_t)which * c->cap_scan;
+        if (cnt[which] > 0) LLB_CUDA(cudaMemcpy(tmp.data(), src, sizeof(float4) * cnt[which], cudaMemcpyDeviceToHost));
+        for (int i = 0; i < cnt[which]; i++)
+            out[i] = llb_point{ tmp[i].x, tmp[i].y, tmp[i].z, 1.0f, tmp[i].w, 0.f, 0.f, 0.f };
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_get_degeneracy(llb_batch *c, int slot, int *deg)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || !deg) return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        LLB_CUDA(cudaMemcpy(deg, &c->states.p[slot].is_degenerate, sizeof(int), cudaMemcpyDeviceToHost));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_set_profile(llb_batch *c, int on)
+{
+    if (!c) return LLB_ERR_INVALID;
+    c->profile = on != 0;
+    return LLB_OK;
+}
+
+int llb_batch_get_profile(llb_batch *c, float ms[6], int geometry[4])
+{
+    if (!c) return LLB_ERR_INVALID;
+    if (ms) for (int k = 0; k < PROF_N; k++) ms[k] = c->prof_ms[k];
+    if (geometry) { geometry[0] = c->knn_ctas; geometry[1] = c->fit_blocks; geometry[2] = c->grid_ctas; geometry[3] = c->qcap; }
+    return LLB_OK;
+}
+
+}  // extern "C"

@@ -2,9 +2,11 @@
 // the SAME five launches (blockIdx.y selects the map):
 //   1 bounds           (+ the last CTA to finish derives the grid: origin, cell size, dims)
 //   2 per-cell counts  (one atomic per point; the value it returns is the point's slot in its cell)
-//   3 tile sums of the dense count table (+ the last CTA scans the tile sums)
-//   4 exclusive scan of the count table -> cell_begin
-//   5 scatter into cell order (+ re-zeroes the count table for the next build)
+//   3 exclusive scan of the per-ROW point counts (a row = the dimx cells of one (y,z); one CTA per map)
+//   4 cell_begin of the OCCUPIED rows (one warp per row: warp scan of the row's cell counts); empty rows are
+//     skipped - queries consult row_begin first - so the dense tables are only touched where points are
+//     (a 100k-point local map occupies ~1 % of its ~1M cells, profiles/r01c_batch.md)
+//   5 scatter into cell order (+ re-zeroes the touched cell / row counts for the next build)
 // Everything is sized on the device; the host only knows upper bounds, so nothing synchronises.
 #include "grid_index.cuh"
 
@@ -13,12 +15,7 @@ namespace llb {
 namespace {
 
 constexpr int TPB = 256;
-constexpr int SCAN_TILE = 4096;     // 1024 threads x 4
 
-struct GridJob {
-    const float4 *pts; const int *n_dev; int n_host;
-    GridDesc *desc; int *counts; int *cell_begin; int *cell_of; int *rank; int *blk; float4 *sorted;
-};
 struct GridJobs { GridJob j[2]; float radius; int max_cells; };
 
 __global__ void grid_desc_init_kernel(GridDesc *d)
@@ -62,9 +59,9 @@ __device__ void grid_setup(GridDesc *d, int n, float radius, int max_cells)
 }
 
 __global__ void __launch_bounds__(TPB)
-grid_bbox_kernel(GridJobs jobs)
+grid_bbox_kernel(GridJobs jobs, const GridJob *__restrict__ table)
 {
-    const GridJob &jb = jobs.j[blockIdx.y];
+    const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
     GridDesc *d = jb.desc;
     __shared__ float s_red[6][TPB / 32];
     __shared__ int s_last;
@@ -107,106 +104,111 @@ grid_bbox_kernel(GridJobs jobs)
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __global__ void __launch_bounds__(TPB)
-grid_count_kernel(GridJobs jobs)
+grid_count_kernel(GridJobs jobs, const GridJob *__restrict__ table)
 {
-    const GridJob &jb = jobs.j[blockIdx.y];
+    const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
     const GridDesc *d = jb.desc;
     const int n = d->n;
     const float ox = d->org[0], oy = d->org[1], oz = d->org[2], inv = d->inv_cell;
     const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
-    for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-        float4 p = __ldg(&jb.pts[i]);
-        int cx = clampi(grid_coord(p.x, ox, inv), 0, dx - 1);
-        int cy = clampi(grid_coord(p.y, oy, inv), 0, dy - 1);
-        int cz = clampi(grid_coord(p.z, oz, inv), 0, dz - 1);
-        int c = (cz * dy + cy) * dx + cx;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i0 = blockIdx.x * TPB; i0 < n; i0 += gridDim.x * TPB) {
+        const int i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        int c = -1 - lane, row = -1 - lane;                  // invalid lanes match nobody
+        if (valid) {
+            float4 p = __ldg(&jb.pts[i]);
+            int cx = clampi(grid_coord(p.x, ox, inv), 0, dx - 1);
+            int cy = clampi(grid_coord(p.y, oy, inv), 0, dy - 1);
+            int cz = clampi(grid_coord(p.z, oz, inv), 0, dz - 1);
+            row = cz * dy + cy;
+            c = row * dx + cx;
+        }
+        // map clouds arrive in voxel order, so neighbouring lanes mostly share a cell (and almost always a row):
+        // ONE atomic per distinct cell / row per warp; the leader's return value + the lane's rank among its
+        // peers is the point's slot inside its cell
+        const unsigned mc = __match_any_sync(FULL, c);
+        const int lead = __ffs(mc) - 1;
+        int base = 0;
+        if (valid && lane == lead) base = atomicAdd(&jb.counts[c], __popc(mc));
+        base = __shfl_sync(FULL, base, lead);
+        const unsigned mr = __match_any_sync(FULL, row);
+        if (valid && lane == __ffs(mr) - 1) atomicAdd(&jb.row_cnt[row], __popc(mr));
+        if (!valid) continue;
         jb.cell_of[i] = c;
-        jb.rank[i] = atomicAdd(&jb.counts[c], 1);
+        jb.rank[i] = base + __popc(mc & lt);
     }
 }
 
-// tile sums of counts[0 .. ncell]; the last CTA turns them into exclusive offsets
+// exclusive scan of the per-row point counts -> row_begin[0 .. nrows]; ONE CTA per map (blockIdx.y)
 __global__ void __launch_bounds__(1024)
-scan_tile_sum_kernel(GridJobs jobs)
+grid_row_scan_kernel(GridJobs jobs, const GridJob *__restrict__ table)
 {
-    const GridJob &jb = jobs.j[blockIdx.y];
-    GridDesc *d = jb.desc;
+    const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
+    const GridDesc *d = jb.desc;
     __shared__ int s_w[33];
-    __shared__ int s_last;
-    const int m = d->ncell + 1;
-    const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {     // grid-stride: the host does not know ncell
-        const int base = tile * SCAN_TILE;
-        int s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int i = base + k * 1024 + threadIdx.x;
-            if (i < m) s += jb.counts[i];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int v = s_w[threadIdx.x];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-            if (threadIdx.x == 0) jb.blk[tile] = v;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(&d->ticket, 1u) == gridDim.x - 1);
-    }
+    __shared__ int s_carry;
+    const int nrows = d->dim[1] * d->dim[2];
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) d->ticket = 0;
-    // exclusive scan of the tile sums by this CTA
-    const int count = ntiles;
-    const int per = (count + 1023) / 1024;
-    const int lo = min((int)threadIdx.x * per, count), hi = min(lo + per, count);
-    int sum = 0;
-    for (int i = lo; i < hi; i++) sum += __ldcg(&jb.blk[i]);
-    int total;
-    int ex = block_excl_scan(sum, s_w, total);
-    for (int i = lo; i < hi; i++) { int v = __ldcg(&jb.blk[i]); jb.blk[i] = ex; ex += v; }
-}
-
-__global__ void __launch_bounds__(1024)
-scan_tile_apply_kernel(GridJobs jobs)
-{
-    const GridJob &jb = jobs.j[blockIdx.y];
-    __shared__ int s_scan[33];
-    const int m = jb.desc->ncell + 1;
-    const int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i0 = tile * SCAN_TILE + threadIdx.x * 4;   // thread owns 4 CONSECUTIVE entries
+    for (int base = 0; base < nrows; base += 4096) {         // 1024 threads x 4 consecutive rows
+        const int i0 = base + threadIdx.x * 4;
         int v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (i0 + k < m) ? jb.counts[i0 + k] : 0;
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < nrows) ? jb.row_cnt[i0 + k] : 0;
         int total;
-        int ex = jb.blk[tile] + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_scan, total);
+        int ex = s_carry + block_excl_scan(v[0] + v[1] + v[2] + v[3], s_w, total);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (i0 + k < m) jb.cell_begin[i0 + k] = ex;
+            if (i0 + k < nrows) jb.row_begin[i0 + k] = ex;
             ex += v[k];
         }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) jb.row_begin[nrows] = s_carry;
+}
+
+// cell_begin of every row: one warp per row
+__global__ void __launch_bounds__(TPB)
+grid_row_apply_kernel(GridJobs jobs, const GridJob *__restrict__ table)
+{
+    const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
+    const GridDesc *d = jb.desc;
+    const int dx = d->dim[0], nrows = d->dim[1] * d->dim[2];
+    const int lane = threadIdx.x & 31;
+    const int wpb = TPB / 32;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += gridDim.x * wpb) {
+        const int rb = jb.row_begin[r], rn = jb.row_begin[r + 1] - rb;
+        if (rn == 0) continue;                               // empty rows are never read by a query
+        int *__restrict__ cb = jb.cell_begin + (size_t)r * dx;
+        const int *__restrict__ cnt = jb.counts + (size_t)r * dx;
+        int run = rb;
+        for (int x0 = 0; x0 < dx; x0 += 32) {
+            const int x = x0 + lane;
+            const int v = x < dx ? cnt[x] : 0;
+            const int inc = warp_incl_scan(v);
+            if (x < dx) cb[x] = run + inc - v;
+            run += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) cb[dx] = run;                         // end of the row's last cell (= next row's first entry)
     }
 }
 
 __global__ void __launch_bounds__(TPB)
-grid_scatter_kernel(GridJobs jobs)
+grid_scatter_kernel(GridJobs jobs, const GridJob *__restrict__ table)
 {
-    const GridJob &jb = jobs.j[blockIdx.y];
+    const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
     const GridDesc *d = jb.desc;
     const int n = d->n;
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
         float4 p = __ldg(&jb.pts[i]);
         const int c = jb.cell_of[i];
         jb.sorted[jb.cell_begin[c] + jb.rank[i]] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-        jb.counts[c] = 0;                                    // leave the count table clean for the next build
+        jb.counts[c] = 0;                                    // leave the count tables clean for the next build
+        jb.row_cnt[c / d->dim[0]] = 0;
     }
 }
 
@@ -223,16 +225,18 @@ void GridIndex::init(int max_cells)
     desc_.ensure(1);
     counts_.ensure((size_t)max_cells_ + 1);
     cell_begin_.ensure((size_t)max_cells_ + 1);
-    blk_.ensure((size_t)div_up(max_cells_ + 1, SCAN_TILE) + 1);
+    row_cnt_.ensure((size_t)max_cells_ + 1);
+    row_begin_.ensure((size_t)max_cells_ + 2);
     grid_desc_init_kernel<<<1, 1>>>(desc_.p);
     grid_zero_kernel<<<148 * 4, 256>>>(counts_.p, max_cells_ + 1);
+    grid_zero_kernel<<<148 * 4, 256>>>(row_cnt_.p, max_cells_ + 1);
     LLB_CUDA(cudaGetLastError());
 }
 
 void GridIndex::release()
 {
     desc_.release(); sorted_.release(); counts_.release(); cell_begin_.release(); cell_of_.release(); rank_.release();
-    blk_.release();
+    row_cnt_.release(); row_begin_.release();
 }
 
 int GridIndex::build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int na_upper,
@@ -253,15 +257,44 @@ int GridIndex::build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int
         GridJob &j = jobs.j[k];
         j.pts = pts[k]; j.n_dev = ndev[k]; j.n_host = nup[k];
         j.desc = g[k]->desc_.p; j.counts = g[k]->counts_.p; j.cell_begin = g[k]->cell_begin_.p;
-        j.cell_of = g[k]->cell_of_.p; j.rank = g[k]->rank_.p; j.blk = g[k]->blk_.p; j.sorted = g[k]->sorted_.p;
+        j.cell_of = g[k]->cell_of_.p; j.rank = g[k]->rank_.p; j.row_cnt = g[k]->row_cnt_.p; j.row_begin = g[k]->row_begin_.p;
+        j.sorted = g[k]->sorted_.p;
     }
     const dim3 grid_pts(std::min(div_up(nmax, TPB), 148 * 4), 2);
-    const dim3 grid_scan(std::min(div_up(jobs.max_cells + 1, SCAN_TILE), 148 * 2), 2);
-    grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
-    grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
-    scan_tile_sum_kernel<<<grid_scan, 1024, 0, s>>>(jobs);
-    scan_tile_apply_kernel<<<grid_scan, 1024, 0, s>>>(jobs);
-    grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(jobs);
+    grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs, nullptr);
+    grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs, nullptr);
+    grid_row_scan_kernel<<<dim3(1, 2), 1024, 0, s>>>(jobs, nullptr);
+    grid_row_apply_kernel<<<dim3(148 * 2, 2), TPB, 0, s>>>(jobs, nullptr);
+    grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(jobs, nullptr);
+    LLB_CUDA(cudaGetLastError());
+    return 5;
+}
+
+GridJob GridIndex::job(const float4 *pts, const int *n_dev, int n_upper)
+{
+    const int n = n_upper > 0 ? n_upper : 1;
+    sorted_.ensure(n); cell_of_.ensure(n); rank_.ensure(n);
+    GridJob j;
+    j.pts = pts; j.n_dev = n_dev; j.n_host = n_upper;
+    j.desc = desc_.p; j.counts = counts_.p; j.cell_begin = cell_begin_.p;
+    j.cell_of = cell_of_.p; j.rank = rank_.p; j.row_cnt = row_cnt_.p; j.row_begin = row_begin_.p; j.sorted = sorted_.p;
+    return j;
+}
+
+int GridIndex::build_table(const GridJob *table_dev, int count, int n_upper_max, float radius, int max_cells,
+                           int ctas_per_map, cudaStream_t s)
+{
+    if (count <= 0) return 0;
+    GridJobs jobs{};
+    jobs.radius = radius; jobs.max_cells = max_cells;
+    // the whole table shares each launch: a few CTAs per map keep the grid near one wave on 148 SMs
+    const int per = std::max(1, ctas_per_map);
+    const dim3 grid_pts(std::min(div_up(std::max(n_upper_max, 1), TPB), per), count);
+    grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
+    grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
+    grid_row_scan_kernel<<<dim3(1, count), 1024, 0, s>>>(jobs, table_dev);
+    grid_row_apply_kernel<<<dim3(per, count), TPB, 0, s>>>(jobs, table_dev);
+    grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
     LLB_CUDA(cudaGetLastError());
     return 5;
 }

@@ -8,8 +8,10 @@
 // query's cell always contains the whole ball.  Cell ids are x-fastest, which makes the
 // three x-neighbours of a (y,z) row ONE contiguous run in the re-ordered point array:
 // a query reads 9 runs, not 27 cells.  Layout in HBM: `sorted` float4 {x,y,z,bits(original
-// index)} in cell order (coalesced 16 B loads), `cell_begin` int[ncell+1] (exclusive scan
-// of the per-cell counts).
+// index)} in cell order (coalesced 16 B loads), `row_begin` int[rows+1] (exclusive scan of the
+// points per (y,z) row) and `cell_begin` int[ncell+1] (exclusive scan of the per-cell counts),
+// which is only materialised inside occupied rows: a 100k-point local map occupies ~1 % of its
+// ~1M cells, so the build never touches (and the queries never read) the empty 99 %.
 #pragma once
 #include "common.cuh"
 
@@ -28,8 +30,15 @@ struct GridDesc {            // device-resident
 
 struct MapIndexView {        // what the query kernels need (all device pointers)
     const float4 *sorted;
-    const int *cell_begin;
+    const int *cell_begin;   // valid ONLY inside occupied rows (+ the entry right after such a row)
+    const int *row_begin;    // [dimy*dimz + 1] exclusive scan of the points per (y,z) row: row r is empty iff
+                             // row_begin[r] == row_begin[r+1]; a query looks here first and skips empty rows
     const GridDesc *desc;
+};
+
+struct GridJob {             // one index build: input cloud + the buffers of the GridIndex that receives it
+    const float4 *pts; const int *n_dev; int n_host;
+    GridDesc *desc; int *counts; int *cell_begin; int *cell_of; int *rank; int *row_cnt; int *row_begin; float4 *sorted;
 };
 
 class GridIndex {
@@ -40,7 +49,13 @@ public:
     // bound, n_dev (optional) the device-resident length.  Returns the number of launches.
     static int build_pair(GridIndex &a, const float4 *pa, const int *na_dev, int na_upper,
                           GridIndex &b, const float4 *pb, const int *nb_dev, int nb_upper, float radius, cudaStream_t s);
-    MapIndexView view() const { return MapIndexView{ sorted_.p, cell_begin_.p, desc_.p }; }
+    // batched form: job() sizes this index's buffers for n_upper points and returns the job record; a
+    // device-resident table of such records (any number of maps) is then built by ONE set of five launches
+    GridJob job(const float4 *pts, const int *n_dev, int n_upper);
+    static int build_table(const GridJob *table_dev, int count, int n_upper_max, float radius, int max_cells,
+                           int ctas_per_map, cudaStream_t s);
+    int max_cells() const { return max_cells_; }
+    MapIndexView view() const { return MapIndexView{ sorted_.p, cell_begin_.p, row_begin_.p, desc_.p }; }
     const GridDesc *desc_dev() const { return desc_.p; }
 
 private:
@@ -51,7 +66,8 @@ private:
     DevBuf<int> cell_begin_;   // exclusive scan of the counts
     DevBuf<int> cell_of_;      // per point cell id
     DevBuf<int> rank_;         // per point rank inside its cell
-    DevBuf<int> blk_;          // scan block sums
+    DevBuf<int> row_cnt_;      // points per (y,z) row (kept zero between builds)
+    DevBuf<int> row_begin_;    // exclusive scan of the row counts
 };
 
 #ifdef __CUDACC__

@@ -72,9 +72,12 @@ __device__ __forceinline__ void knn_ranges(const MapIndexView &m, float qx, floa
         const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
         rb[r] = 0; re[r] = 0;
         if (y >= 0 && y < dimy && z >= 0 && z < dimz && x0 <= x1) {
-            const int row = (z * dimy + y) * dimx;
-            rb[r] = __ldg(&m.cell_begin[row + x0]);
-            re[r] = __ldg(&m.cell_begin[row + x1 + 1]);
+            const int ry = z * dimy + y;
+            if (__ldg(&m.row_begin[ry + 1]) > __ldg(&m.row_begin[ry])) {   // cell_begin only exists in occupied rows
+                const int row = ry * dimx;
+                rb[r] = __ldg(&m.cell_begin[row + x0]);
+                re[r] = __ldg(&m.cell_begin[row + x1 + 1]);
+            }
         }
     }
 }
@@ -156,6 +159,80 @@ __device__ __forceinline__ int knn5_warp(const MapIndexView &m, float qx, float 
         knn_select5_general(wkey, wpos, cnt, lane, ck, cp);
 #pragma unroll
         for (int r = 0; r < 5; r++) { npos[r] = cp[r]; nd[r] = __uint_as_float((unsigned)(ck[r] >> 32)); ni[r] = (int)(unsigned)ck[r]; }
+    }
+    __syncwarp();
+    return 5;
+}
+
+// Lean variant for the batched, high-occupancy kNN kernel (batch.cu): the same exact result as knn5_warp, but the
+// cell runs are visited one after the other (bounds broadcast from lanes 0..8 on demand) instead of holding all nine
+// first tiles in registers: ~half the registers, so 2-3x the warps per SM hide the load latency instead of ILP.
+// b0 / e0: lane r < 9 holds the [begin, end) of run r.
+__device__ __forceinline__ int knn5_warp_lean(const MapIndexView &m, float qx, float qy, float qz, float max_sq, int lane,
+                                              int b0, int e0, unsigned long long *wkey, int *wpos,
+                                              int (&npos)[5], float &d5th)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;                                             // warp-uniform
+#pragma unroll 1
+    for (int r = 0; r < 9; r++) {
+        const int rb = __shfl_sync(FULL, b0, r), re = __shfl_sync(FULL, e0, r);
+#pragma unroll 1
+        for (int base = rb; base < re; base += 32) {
+            const int i = base + lane;
+            const bool v = i < re;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v) p = __ldg(&m.sorted[i]);
+            const float d = l2_simple(qx, qy, qz, p);
+            const bool ok = v && d < max_sq;
+            const unsigned mask = __ballot_sync(FULL, ok);
+            if (mask) {                                      // warp-uniform
+                if (cnt + 32 > KNN_CAP) {                    // list full: keep its best five and go on
+                    unsigned long long ck[5]; int cp[5];
+                    __syncwarp();
+                    knn_select5_general(wkey, wpos, cnt, lane, ck, cp);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) if (lane == k) { wkey[k] = ck[k]; wpos[k] = cp[k]; }
+                    cnt = 5;
+                    __syncwarp();
+                }
+                if (ok) {
+                    const int off = cnt + __popc(mask & lt);
+                    wkey[off] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                    wpos[off] = i;
+                }
+                cnt += __popc(mask);
+            }
+        }
+    }
+    __syncwarp();
+    d5th = -1.f;
+    if (cnt < 5) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) npos[r] = -1;
+        return cnt;
+    }
+    if (cnt <= 32) {                                         // one candidate per lane, registers only
+        unsigned long long key = lane < cnt ? wkey[lane] : ~0ull;
+        const int pos = lane < cnt ? wpos[lane] : -1;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+            const unsigned mhi = __reduce_min_sync(FULL, hi);
+            const unsigned clo = (hi == mhi) ? lo : 0xffffffffu;
+            const unsigned mlo = __reduce_min_sync(FULL, clo);
+            const bool win = (hi == mhi) && (lo == mlo);
+            const int src = __ffs(__ballot_sync(FULL, win)) - 1;
+            npos[r] = __shfl_sync(FULL, pos, src);
+            if (r == 4) d5th = __uint_as_float(mhi);
+            if (win) key = ~0ull;
+        }
+    } else {
+        unsigned long long ck[5]; int cp[5];
+        knn_select5_general(wkey, wpos, cnt, lane, ck, cp);
+#pragma unroll
+        for (int r = 0; r < 5; r++) npos[r] = cp[r];
+        d5th = __uint_as_float((unsigned)(ck[4] >> 32));
     }
     __syncwarp();
     return 5;

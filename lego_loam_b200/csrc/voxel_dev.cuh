@@ -60,6 +60,14 @@ struct SmallJobs {
     int *n_out[VoxelFilter::MAX_BATCH];
 };
 
+struct SmallJob { SegIn in; float leaf; float4 *out; int *n_out; };
+// the same with a device-resident job table of any length (batched multi-registration path)
+void launch_voxel_small_jobs(const SmallJob *jobs_dev, int count, cudaStream_t stream);
+
+// throughput form: ONE CTA per job (shared-memory radix sort); every job must have at most `cap` points
+// (cap <= VoxelFilter::SMALL_MAX, dynamic shared memory = 12 B x cap)
+void launch_voxel_cta_jobs(const SmallJob *jobs_dev, int count, int cap, cudaStream_t stream);
+
 // one 8-CTA cluster per job; every job must have at most VoxelFilter::SMALL_MAX points
 void launch_voxel_small(const SmallJobs &jobs, int count, cudaStream_t stream);
 

@@ -24,16 +24,12 @@ constexpr int CL = 8;                        // CTAs per cluster
 constexpr int TPB = 1024;
 constexpr int LMAX = VoxelFilter::SMALL_MAX / CL;   // keys per CTA
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, 1)
-voxel_small_kernel(SmallJobs jobs)
+// one filter by one cluster; called by the two kernel wrappers below
+__device__ __forceinline__ void voxel_small_body(const SegIn in, const float leaf, float4 *__restrict__ out,
+                                                 int *__restrict__ n_out_dev)
 {
     cg::cluster_group cluster = cg::this_cluster();
-    const int job = blockIdx.x / CL;
     const int cr = (int)cluster.block_rank();
-    const SegIn in = jobs.in[job];
-    const float leaf = jobs.leaf[job];
-    float4 *__restrict__ out = jobs.out[job];
-    int *__restrict__ n_out_dev = jobs.n_out[job];
 
     __shared__ unsigned long long skey[LMAX];
     __shared__ float s_red[6][32];
@@ -196,7 +192,199 @@ voxel_small_kernel(SmallJobs jobs)
     cluster.sync();                          // keep shared memory alive until every remote read is done
 }
 
+// ------------------------------------------------------------------------------------------------
+// Throughput form (batched multi-registration path): ONE CTA per filter, stable LSD radix sort of the 32-bit voxel
+// keys in shared memory (8-bit digits, only the significant key bits; per-warp digit counters + __match_any ranking
+// keep equal keys in input order, which is what the 64-bit bitonic keys of the cluster kernel encode explicitly).
+// ~5x fewer instructions per filter than the bitonic network and one SM instead of eight, so the 4B filters of a
+// B-slot batch fill the GPU in about one wave.  Dynamic shared memory: cap x (2 x 4 B keys + 2 x 2 B indices).
+constexpr int VC_THREADS = 512;
+constexpr int VC_NW = VC_THREADS / 32;
+constexpr int VC_ITEMS = 4;
+constexpr int VC_SUB = VC_THREADS * VC_ITEMS;
+
+__global__ void __launch_bounds__(VC_THREADS)
+voxel_cta_kernel(const SmallJob *__restrict__ jobs, int cap)
+{
+    extern __shared__ __align__(16) unsigned char vc_smem[];
+    unsigned *kin = reinterpret_cast<unsigned *>(vc_smem), *kout = kin + cap;
+    unsigned short *vin = reinterpret_cast<unsigned short *>(kout + cap), *vout = vin + cap;
+    __shared__ int s_wcnt[VC_NW][256];
+    __shared__ int s_base[256];
+    __shared__ float s_red[6][VC_NW];
+    __shared__ int s_scan[33];
+    __shared__ float s_inv;
+    __shared__ int s_min_b[3], s_div_b[3], s_mul[3], s_overflow, s_nbits;
+
+    const SmallJob jb = jobs[blockIdx.x];
+    const SegIn in = jb.in;
+    float4 *__restrict__ out = jb.out;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int na = seg_len_a(in), n = na + seg_len_b(in);
+    if (n <= 0 || n > cap) {                 // n > cap cannot happen (the host sizes cap from the upper bounds)
+        if (tid == 0) *jb.n_out = 0;
+        return;
+    }
+    // ---- bounds
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int i = tid; i < n; i += VC_THREADS) {
+        const float4 p = seg_load(in, na, i);
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+        }
+        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float fmn[3], fmx[3];
+        for (int a = 0; a < 3; a++) {
+            fmn[a] = s_red[a][0]; fmx[a] = s_red[3 + a][0];
+            for (int k = 1; k < VC_NW; k++) { fmn[a] = fminf(fmn[a], s_red[a][k]); fmx[a] = fmaxf(fmx[a], s_red[3 + a][k]); }
+        }
+        const float inv = 1.0f / jb.leaf;
+        int ovf, nb;
+        voxel_setup(inv, fmn, fmx, n, s_min_b, s_div_b, s_mul, ovf, nb);
+        s_inv = inv; s_overflow = ovf; s_nbits = nb;
+    }
+    __syncthreads();
+    if (s_overflow) {                        // PCL: output = input (C18)
+        for (int i = tid; i < n; i += VC_THREADS) out[i] = seg_load(in, na, i);
+        if (tid == 0) *jb.n_out = n;
+        return;
+    }
+    // ---- keys
+    {
+        const float inv = s_inv;
+        const int min_b[3] = { s_min_b[0], s_min_b[1], s_min_b[2] }, mul[3] = { s_mul[0], s_mul[1], s_mul[2] };
+        for (int i = tid; i < n; i += VC_THREADS) {
+            kin[i] = voxel_key(seg_load(in, na, i), inv, min_b, mul);
+            vin[i] = (unsigned short)i;
+        }
+    }
+    // ---- stable LSD radix sort, 8 bits per pass
+    const int nbits = s_nbits;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int shift = 0; shift < nbits; shift += 8) {
+        if (tid < 256) s_base[tid] = 0;
+        __syncthreads();                                     // also orders the previous pass's scatter / the key pass
+        for (int i = tid; i < n; i += VC_THREADS) atomicAdd(&s_base[(kin[i] >> shift) & 255u], 1);
+        __syncthreads();
+        {
+            const int v = tid < 256 ? s_base[tid] : 0;
+            int total;
+            const int ex = block_excl_scan(v, s_scan, total);
+            if (tid < 256) s_base[tid] = ex;
+        }
+        for (int sub = 0; sub < n; sub += VC_SUB) {
+            for (int k = tid; k < VC_NW * 256; k += VC_THREADS) (&s_wcnt[0][0])[k] = 0;
+            __syncthreads();
+            unsigned key[VC_ITEMS]; unsigned short val[VC_ITEMS]; int rk[VC_ITEMS]; unsigned dg[VC_ITEMS];
+#pragma unroll
+            for (int r = 0; r < VC_ITEMS; r++) {
+                const int i = sub + w * (32 * VC_ITEMS) + r * 32 + lane;
+                const bool valid = i < n;
+                key[r] = valid ? kin[i] : 0u;
+                val[r] = valid ? vin[i] : (unsigned short)0;
+                dg[r] = valid ? ((key[r] >> shift) & 255u) : (256u + lane);    // invalid lanes never match
+            }
+#pragma unroll
+            for (int r = 0; r < VC_ITEMS; r++) {
+                const unsigned m = __match_any_sync(FULL, dg[r]);
+                const int pr = __popc(m & lt);
+                int cnt = 0;
+                if (dg[r] < 256u) cnt = s_wcnt[w][dg[r]];
+                rk[r] = cnt + pr;
+                __syncwarp();
+                if (dg[r] < 256u && pr == 0) s_wcnt[w][dg[r]] = cnt + __popc(m);
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < 256) {                                 // digit tid: per-warp counts -> scatter offsets
+                int run = s_base[tid];
+#pragma unroll
+                for (int k = 0; k < VC_NW; k++) { const int c = s_wcnt[k][tid]; s_wcnt[k][tid] = run; run += c; }
+                s_base[tid] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < VC_ITEMS; r++)
+                if (dg[r] < 256u) {
+                    const int pos = s_wcnt[w][dg[r]] + rk[r];
+                    kout[pos] = key[r]; vout[pos] = val[r];
+                }
+            __syncthreads();
+        }
+        unsigned *tk = kin; kin = kout; kout = tk;
+        unsigned short *tv = vin; vin = vout; vout = tv;
+    }
+    __syncthreads();
+    // ---- heads, scan, ordered per-voxel sums
+    const int chunk = (n + VC_THREADS - 1) / VC_THREADS;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int heads = 0;
+    for (int t = lo; t < hi; t++) heads += (t == 0) || (kin[t - 1] != kin[t]);
+    int total;
+    int rank = block_excl_scan(heads, s_scan, total);
+    for (int t = lo; t < hi; t++) {
+        const unsigned cur = kin[t];
+        if ((t == 0) || (kin[t - 1] != cur)) {
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            int j = t;
+            while (j < n && kin[j] == cur) {
+                const float4 p = seg_load(in, na, (int)vin[j]);
+                sx += p.x; sy += p.y; sz += p.z; si += p.w;
+                j++;
+            }
+            const float cnt = (float)(j - t);
+            out[rank++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        }
+    }
+    if (tid == 0) *jb.n_out = total;
+}
+
+// jobs by value (<= MAX_BATCH filters: the single-context path)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, 1)
+voxel_small_kernel(SmallJobs jobs)
+{
+    const int job = blockIdx.x / CL;
+    voxel_small_body(jobs.in[job], jobs.leaf[job], jobs.out[job], jobs.n_out[job]);
+}
+
+// device-resident job table (any number of filters: the batched multi-registration path)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, 1)
+voxel_small_jobs_kernel(const SmallJob *__restrict__ jobs)
+{
+    const SmallJob jb = jobs[blockIdx.x / CL];
+    voxel_small_body(jb.in, jb.leaf, jb.out, jb.n_out);
+}
+
 }  // namespace
+
+void launch_voxel_cta_jobs(const SmallJob *jobs_dev, int count, int cap, cudaStream_t stream)
+{
+    static int attr_cap = 0;                                 // largest dynamic shared memory opted into so far
+    const int bytes = cap * 12;
+    if (bytes > attr_cap) {
+        LLB_CUDA(cudaFuncSetAttribute(voxel_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        attr_cap = bytes;
+    }
+    voxel_cta_kernel<<<count, VC_THREADS, bytes, stream>>>(jobs_dev, cap);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_voxel_small_jobs(const SmallJob *jobs_dev, int count, cudaStream_t stream)
+{
+    voxel_small_jobs_kernel<<<count * CL, TPB, 0, stream>>>(jobs_dev);
+    LLB_CUDA(cudaGetLastError());
+}
 
 void launch_voxel_small(const SmallJobs &jobs, int count, cudaStream_t stream)
 {

@@ -1,0 +1,115 @@
+"""Batched multi-registration engine (llb_batch_*, BASELINE config 5) through the C ABI: every slot of a
+batch must reproduce what the CPU oracle and the single-registration path give for the same inputs.
+Bars: DS scan clouds bit-exact; poses identical to the oracle in correctly-rounded-trig mode and within the
+north-star tolerance (1e-4 m / 1e-4 rad) in libm mode; iteration counts, convergence flags and row counts equal.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from lego_loam_b200 import api, synth
+from tests import data
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-4
+
+
+def _oracle_registration(case, mc_ds, ms_ds, trig_mode):
+    oracle.set_trig_mode(trig_mode)
+    mo = oracle.MapOptimization()
+    mo.set_map_ds(mc_ds, ms_ds)
+    mo.set_scan(case["corner"], case["surf"], case["outlier"])
+    mo.downsampleCurrentScan()
+    mo.transformTobeMapped = case["init"]
+    iters = mo.scan2MapOptimization()
+    ds = [mo.scan_ds(i) for i in range(4)]
+    oracle.set_trig_mode(0)
+    return mo.transformTobeMapped.copy(), iters, ds
+
+
+@pytest.fixture(scope="module")
+def cases(ctx):
+    out = []
+    for seed in (1, 2, 3, 4, 5):
+        c = data.mapping_case(seed, 15000, 90000)
+        ctx.map_set_raw(c["map_corner_raw"], c["map_surf_raw"])
+        out.append(dict(c, mc_ds=ctx.map_get_ds(0), ms_ds=ctx.map_get_ds(1)))
+    return out
+
+
+def test_batch_matches_oracle_and_single(ctx, cases):
+    B = len(cases)
+    b = api.Batch(0, B, 8192, 120000)
+    for s, c in enumerate(cases):
+        b.scan_set(s, c["corner"], c["surf"], c["outlier"])
+        b.map_set_ds(s, c["mc_ds"], c["ms_ds"])
+    T, st = b.register(np.stack([c["init"] for c in cases]))
+    for s, c in enumerate(cases):
+        Tr, iters, ds = _oracle_registration(c, c["mc_ds"], c["ms_ds"], 1)        # correctly rounded sin/cos
+        for which in range(4):
+            got = b.scan_get_ds(s, which)
+            assert got.shape == ds[which].shape
+            assert np.array_equal(got.view(np.uint32), ds[which].view(np.uint32)), f"slot {s} DS cloud {which}"
+        assert st[s].iterations == iters, (s, st[s].as_dict(), iters)
+        assert st[s].skipped == 0 and st[s].n_corner_ds == ds[0].shape[0] and st[s].n_surf_ds == ds[3].shape[0]
+        assert np.array_equal(T[s].view(np.uint32), Tr.astype(np.float32).view(np.uint32)), (s, T[s], Tr)
+        Tl, _, _ = _oracle_registration(c, c["mc_ds"], c["ms_ds"], 0)             # host libm sinf/cosf
+        assert np.max(np.abs(T[s] - Tl)) < POSE_TOL
+        # the single-registration path on the same inputs
+        ctx.map_set_ds(c["mc_ds"], c["ms_ds"]); ctx.scan_set(c["corner"], c["surf"], c["outlier"])
+        ctx.downsample_current_scan()
+        Ts, sts = ctx.s2m_optimize(c["init"])
+        assert np.array_equal(T[s].view(np.uint32), Ts.view(np.uint32))
+        assert sts.iterations == st[s].iterations and sts.n_correspondences == st[s].n_correspondences
+    b.close()
+
+
+def test_batch_resident_map_and_repeat(cases):
+    """A slot whose map is not set again keeps its index; a second step with new scans and device-resident
+    inputs gives the same poses as the host-cloud path."""
+    import torch
+    B = 3
+    b = api.Batch(0, B, 8192, 120000)
+    for s in range(B):
+        c = cases[s]
+        b.scan_set(s, c["corner"], c["surf"], c["outlier"]); b.map_set_ds(s, c["mc_ds"], c["ms_ds"])
+    T0, st0 = b.register(np.stack([cases[s]["init"] for s in range(B)]))
+    l0 = b.launch_count()
+    # step 2: same scans, maps untouched (no index build), inputs from device memory
+    dev = torch.device("cuda", 0)
+    keep = []
+    for s in range(B):
+        c = cases[s]
+        t = [torch.from_numpy(np.ascontiguousarray(c[k], np.float32)).to(dev) for k in ("corner", "surf", "outlier")]
+        keep.append(t)
+        b.scan_set_dev(s, t[0].data_ptr(), t[0].shape[0], t[1].data_ptr(), t[1].shape[0], t[2].data_ptr(), t[2].shape[0])
+    torch.cuda.synchronize()
+    T1, st1 = b.register(np.stack([cases[s]["init"] for s in range(B)]))
+    assert np.array_equal(T0.view(np.uint32), T1.view(np.uint32))
+    assert [x.iterations for x in st0] == [x.iterations for x in st1]
+    # launches of a step do not depend on the slot count and exclude the 5 index-build launches here
+    assert b.launch_count() - l0 == 2 + 1 + 2 * b.params.s2m_max_iterations + 1
+    b.close()
+
+
+def test_batch_guard_and_errors(cases):
+    b = api.Batch(0, 2, 8192, 120000)
+    c = cases[0]
+    with pytest.raises(api.LlbError) as e:
+        b.register(np.zeros((2, 6), np.float32))              # nothing set yet
+    assert e.value.status == api.LLB_ERR_STATE
+    with pytest.raises(api.LlbError) as e:
+        b.scan_set(0, np.zeros((9000, 4), np.float32), c["surf"], c["outlier"])
+    assert e.value.status == api.LLB_ERR_CAPACITY
+    # slot 1 gets a map below the reference's guard (MO:1331: > 10 corner and > 100 surf points): skipped,
+    # pose untouched; slot 0 registers normally
+    b.scan_set(0, c["corner"], c["surf"], c["outlier"]); b.map_set_ds(0, c["mc_ds"], c["ms_ds"])
+    b.scan_set(1, c["corner"], c["surf"], c["outlier"]); b.map_set_ds(1, c["mc_ds"][:10], c["ms_ds"][:500])
+    init = np.stack([c["init"], c["init"]]).astype(np.float32)
+    T, st = b.register(init)
+    assert st[1].skipped == 1 and st[1].iterations == 0 and np.array_equal(T[1], init[1])
+    assert st[0].skipped == 0 and st[0].iterations > 0 and not np.array_equal(T[0], init[0])
+    b.close()
+    with pytest.raises(api.LlbError):
+        api.Batch(0, 2, 9000, 1000)                            # scan capacity beyond the cluster voxel kernel
