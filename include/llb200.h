@@ -148,6 +148,26 @@ int llb_get_normal_equations(llb_ctx *ctx, float AtA[36], float AtB[6], float X[
 int llb_get_degeneracy(llb_ctx *ctx, int *is_degenerate, float matP[36]);
 int llb_set_degeneracy(llb_ctx *ctx, int is_degenerate, const float matP[36]);
 
+/* ---- device-resident key-frame store ----
+ * cornerCloudKeyFrames / surfCloudKeyFrames / outlierCloudKeyFrames (MO:128-130) kept in HBM, so that a registration
+ * moves only the new sweep over PCIe and the raw local map never exists on the host. */
+/* saveKeyFramesAndFactor's cloud part MO:1443-1453: stores the CURRENT laserCloudCornerLastDS / SurfLastDS /
+ * OutlierLastDS (already on the device after llb_downsample_current_scan); *id = index in the store */
+int llb_keyframe_add(llb_ctx *ctx, int *id);
+/* the same from host clouds (replaying / restoring a store) */
+int llb_keyframe_add_clouds(llb_ctx *ctx, const llb_point *corner_ds, int nc, const llb_point *surf_ds, int ns,
+                            const llb_point *outlier_ds, int no, int *id);
+int llb_keyframe_count(llb_ctx *ctx, int *n);
+int llb_keyframe_clear(llb_ctx *ctx);
+/* cloud part of extractSurroundingKeyFrames: for the n key-frames ids[] IN ORDER (surroundingExistingKeyPosesID,
+ * MO:1033-1049, or the recent-frames queue MO:962-1001) with their cloudKeyPoses6D entries poses[n][6] =
+ * {roll, pitch, yaw, x, y, z}: transformPointCloud (MO:545-575) + concatenation (MO:1050-1054) in ONE launch,
+ * then the two map voxel filters (MO:1057-1064) and the index build (MO:1333-1334).  The sin/cos of the poses are
+ * taken on the host with the float libm overloads, as the reference does (MO:529-543). */
+int llb_map_assemble(llb_ctx *ctx, const int *ids, const float *poses, int n);
+/* laserCloudCornerFromMap (0) / laserCloudSurfFromMap (1) of the last llb_map_assemble (parity checks) */
+int llb_map_get_raw(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+
 /* ---- featureAssociation ---- */
 /* laserCloudCornerLast / laserCloudSurfLast + kdtree rebuild (FA:1615-1619, FA:1774-1788) */
 int llb_odom_set_last(llb_ctx *ctx, const llb_point *corner_last, int ncl, const llb_point *surf_last, int nsl);

@@ -66,6 +66,8 @@ EXPORTS = [
     "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
+    "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
+    "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
     "llb_batch_launch_count", "llb_batch_scan_set", "llb_batch_map_set_ds", "llb_batch_scan_set_dev",
     "llb_batch_map_set_ds_dev", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
@@ -198,6 +200,41 @@ class Context:
         self._ck(lib().llb_map_get_ds(self._h, which, None, 0, ctypes.byref(n)))
         out = np.zeros((max(n.value, 1), 8), np.float32)
         self._ck(lib().llb_map_get_ds(self._h, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    # ---- device-resident key-frame store
+    def keyframe_add(self) -> int:
+        k = ctypes.c_int(-1)
+        self._ck(lib().llb_keyframe_add(self._h, ctypes.byref(k)))
+        return k.value
+
+    def keyframe_add_clouds(self, corner_ds, surf_ds, outlier_ds) -> int:
+        c = to_pcl(corner_ds); s = to_pcl(surf_ds); o = to_pcl(outlier_ds)
+        k = ctypes.c_int(-1)
+        self._ck(lib().llb_keyframe_add_clouds(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0], _vp(o), o.shape[0],
+                                               ctypes.byref(k)))
+        return k.value
+
+    def keyframe_count(self) -> int:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_keyframe_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def keyframe_clear(self):
+        self._ck(lib().llb_keyframe_clear(self._h))
+
+    def map_assemble(self, ids, poses6d):
+        """ids: key-frame indices in order; poses6d: (n, 6) {roll, pitch, yaw, x, y, z} (cloudKeyPoses6D)"""
+        i = np.ascontiguousarray(ids, np.int32)
+        p = np.ascontiguousarray(poses6d, np.float32).reshape(-1, 6)
+        assert p.shape[0] == i.shape[0]
+        self._ck(lib().llb_map_assemble(self._h, i.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(p), int(i.shape[0])))
+
+    def map_get_raw(self, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_map_get_raw(self._h, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_map_get_raw(self._h, which, _vp(out), n.value, ctypes.byref(n)))
         return from_pcl(out[:n.value])
 
     # ---- scan

@@ -8,6 +8,7 @@
 #include "grid_index.cuh"
 #include "s2m.cuh"
 #include "odom.cuh"
+#include "keyframes.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -82,6 +83,15 @@ struct llb_ctx {
     DevBuf<float4> tmp_vox;
 
     OdomSolver odom;
+
+    // device-resident key-frame store + assembled raw local map
+    KeyFrameStore kfs;
+    DevBuf<float4> asmCorner, asmSurf;
+    DevBuf<AsmSeg> asm_segs;
+    PinnedBuf<AsmSeg> pin_segs;
+    cudaEvent_t asm_ev = nullptr;
+    bool asm_busy = false;
+    int asm_rc = 0, asm_rs = 0;
 };
 
 namespace {
@@ -298,6 +308,7 @@ int llb_create(const llb_params *p, int device, llb_ctx **out)
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         LLB_CUDA(cudaEventCreate(&c->ev0)); LLB_CUDA(cudaEventCreate(&c->ev1));
         for (int i = 0; i < 3; i++) LLB_CUDA(cudaEventCreateWithFlags(&c->pin_ev[i], cudaEventDisableTiming));
+        LLB_CUDA(cudaEventCreateWithFlags(&c->asm_ev, cudaEventDisableTiming));
         c->counts.ensure(llb_ctx::C_N);
         LLB_CUDA(cudaMemset(c->counts.p, 0, sizeof(int) * llb_ctx::C_N));
         c->pin_counts.ensure(llb_ctx::C_N);
@@ -332,6 +343,8 @@ int llb_destroy(llb_ctx *c)
     c->mapCornerRaw.pts.release(); c->mapSurfRaw.pts.release(); c->mapCornerDS.release(); c->mapSurfDS.release();
     c->gridCorner.release(); c->gridSurf.release(); c->s2m.release(); c->odom.release();
     c->dbg_coeff.release(); c->dbg_valid.release(); c->dbg_knn.release(); c->dbg_d2.release(); c->tmp_vox.release();
+    c->kfs.release(); c->asmCorner.release(); c->asmSurf.release(); c->asm_segs.release(); c->pin_segs.release();
+    if (c->asm_ev) cudaEventDestroy(c->asm_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -767,6 +780,123 @@ int llb_set_degeneracy(llb_ctx *c, int deg, const float matP[36])
         LLB_CUDA(cudaMemcpy(d->matP, matP, sizeof(float) * 36, cudaMemcpyHostToDevice));
         const int one = 1;
         LLB_CUDA(cudaMemcpy(&d->matP_valid, &one, sizeof(int), cudaMemcpyHostToDevice));
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ key-frame store
+
+int llb_keyframe_add(llb_ctx *c, int *id)
+{
+    return guarded(c, [&]() {
+        if (!c->scan_ds_done) return (int)LLB_ERR_STATE;
+        read_count(c, 0);                                     // sizes of the DS clouds (synchronises the stream)
+        const int n[3] = { c->pin_counts.p[llb_ctx::C_CORNER_DS], c->pin_counts.p[llb_ctx::C_SURF_DS],
+                           c->pin_counts.p[llb_ctx::C_OUTLIER_DS] };
+        const float4 *src[3] = { c->cornerLastDS.p, c->surfLastDS.p, c->outlierLastDS.p };
+        float4 *dst[3];
+        const int k = c->kfs.add(n, dst);
+        for (int j = 0; j < 3; j++)
+            if (n[j] > 0) LLB_CUDA(cudaMemcpyAsync(dst[j], src[j], sizeof(float4) * n[j], cudaMemcpyDeviceToDevice, c->stream));
+        if (id) *id = k;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_keyframe_add_clouds(llb_ctx *c, const llb_point *corner, int nc, const llb_point *surf, int ns,
+                            const llb_point *outlier, int no, int *id)
+{
+    return guarded(c, [&]() {
+        if (nc < 0 || ns < 0 || no < 0 || (nc > 0 && !corner) || (ns > 0 && !surf) || (no > 0 && !outlier))
+            return (int)LLB_ERR_INVALID;
+        const int n[3] = { nc, ns, no };
+        const llb_point *src[3] = { corner, surf, outlier };
+        float4 *dst[3];
+        const int k = c->kfs.add(n, dst);
+        for (int j = 0; j < 3; j++) {
+            if (n[j] <= 0) continue;
+            upload_cloud(c, j, src[j], n[j], c->tmp_in);       // staged + unpacked, then placed into the arena
+            LLB_CUDA(cudaMemcpyAsync(dst[j], c->tmp_in.p, sizeof(float4) * n[j], cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (id) *id = k;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_keyframe_count(llb_ctx *c, int *n)
+{
+    if (!c || !n) return LLB_ERR_INVALID;
+    *n = c->kfs.size();
+    return LLB_OK;
+}
+
+int llb_keyframe_clear(llb_ctx *c)
+{
+    return guarded(c, [&]() {
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        c->kfs.clear();
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_assemble(llb_ctx *c, const int *ids, const float *poses, int n)
+{
+    return guarded(c, [&]() {
+        if (n < 0 || (n > 0 && (!ids || !poses))) return (int)LLB_ERR_INVALID;
+        size_t rc = 0, rs = 0;
+        for (int k = 0; k < n; k++) {
+            if (ids[k] < 0 || ids[k] >= c->kfs.size()) return (int)LLB_ERR_INVALID;
+            const KeyFrameRec &r = c->kfs.rec(ids[k]);
+            rc += r.n[0]; rs += (size_t)r.n[1] + r.n[2];
+        }
+        if (rc > (size_t)INT_MAX || rs > (size_t)INT_MAX) return (int)LLB_ERR_CAPACITY;
+        c->asmCorner.ensure(std::max<size_t>(rc, 1)); c->asmSurf.ensure(std::max<size_t>(rs, 1));
+        c->asm_segs.ensure(std::max(3 * n, 1));
+        if (c->asm_busy) { LLB_CUDA(cudaEventSynchronize(c->asm_ev)); c->asm_busy = false; }
+        c->pin_segs.ensure(std::max(3 * n, 1));
+        size_t oc = 0, os = 0;
+        int nseg = 0, nmax = 1;
+        for (int k = 0; k < n; k++) {
+            const KeyFrameRec &r = c->kfs.rec(ids[k]);
+            const float *p = poses + 6 * k;                  // PointTypePose: roll, pitch, yaw, x, y, z
+            AsmSeg sg{};
+            // updateTransformPointCloudSinCos MO:529-543: float overloads of cos / sin of the host libm, as the
+            // reference (std::cos(float)); the device only multiplies and adds
+            sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]);
+            sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
+            sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]);
+            sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
+            // MO:1050-1054: corner map += corner_k; surf map += surf_k; surf map += outlier_k
+            sg.src = r.cloud[0]; sg.n = r.n[0]; sg.dst = c->asmCorner.p + oc; oc += r.n[0];
+            if (sg.n > 0) { c->pin_segs.p[nseg++] = sg; nmax = std::max(nmax, sg.n); }
+            sg.src = r.cloud[1]; sg.n = r.n[1]; sg.dst = c->asmSurf.p + os; os += r.n[1];
+            if (sg.n > 0) { c->pin_segs.p[nseg++] = sg; nmax = std::max(nmax, sg.n); }
+            sg.src = r.cloud[2]; sg.n = r.n[2]; sg.dst = c->asmSurf.p + os; os += r.n[2];
+            if (sg.n > 0) { c->pin_segs.p[nseg++] = sg; nmax = std::max(nmax, sg.n); }
+        }
+        if (nseg > 0) {
+            LLB_CUDA(cudaMemcpyAsync(c->asm_segs.p, c->pin_segs.p, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
+            LLB_CUDA(cudaEventRecord(c->asm_ev, c->stream));
+            c->asm_busy = true;
+            launch_kf_assemble(c->asm_segs.p, nseg, nmax, c->stream);
+            c->launches++;
+        }
+        c->asm_rc = (int)rc; c->asm_rs = (int)rs;
+        voxel_map_raw(c, c->asmCorner.p, (int)rc, c->asmSurf.p, (int)rs);      // MO:1057-1064
+        build_indices(c);                                                      // MO:1333-1334
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_get_raw(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 1) return (int)LLB_ERR_INVALID;
+        const int cnt = which == 0 ? c->asm_rc : c->asm_rs;
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        download_cloud(c, which == 0 ? c->asmCorner.p : c->asmSurf.p, cnt, out);
         return (int)LLB_OK;
     });
 }

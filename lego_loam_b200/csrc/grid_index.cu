@@ -113,31 +113,42 @@ grid_count_kernel(GridJobs jobs, const GridJob *__restrict__ table)
     const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    for (int i0 = blockIdx.x * TPB; i0 < n; i0 += gridDim.x * TPB) {
-        const int i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        int c = -1 - lane, row = -1 - lane;                  // invalid lanes match nobody
-        if (valid) {
-            float4 p = __ldg(&jb.pts[i]);
-            int cx = clampi(grid_coord(p.x, ox, inv), 0, dx - 1);
-            int cy = clampi(grid_coord(p.y, oy, inv), 0, dy - 1);
-            int cz = clampi(grid_coord(p.z, oz, inv), 0, dz - 1);
-            row = cz * dy + cy;
-            c = row * dx + cx;
+    constexpr int U = 4;                                     // independent load -> atomic chains per thread
+    for (int i0 = blockIdx.x * TPB * U; i0 < n; i0 += gridDim.x * TPB * U) {
+        int c[U], row[U], base[U]; unsigned mc[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const int i = i0 + k * TPB + threadIdx.x;
+            c[k] = -1 - lane; row[k] = -1 - lane;            // invalid lanes match nobody
+            if (i < n) {
+                const float4 p = __ldg(&jb.pts[i]);
+                const int cx = clampi(grid_coord(p.x, ox, inv), 0, dx - 1);
+                const int cy = clampi(grid_coord(p.y, oy, inv), 0, dy - 1);
+                const int cz = clampi(grid_coord(p.z, oz, inv), 0, dz - 1);
+                row[k] = cz * dy + cy;
+                c[k] = row[k] * dx + cx;
+            }
         }
         // map clouds arrive in voxel order, so neighbouring lanes mostly share a cell (and almost always a row):
         // ONE atomic per distinct cell / row per warp; the leader's return value + the lane's rank among its
         // peers is the point's slot inside its cell
-        const unsigned mc = __match_any_sync(FULL, c);
-        const int lead = __ffs(mc) - 1;
-        int base = 0;
-        if (valid && lane == lead) base = atomicAdd(&jb.counts[c], __popc(mc));
-        base = __shfl_sync(FULL, base, lead);
-        const unsigned mr = __match_any_sync(FULL, row);
-        if (valid && lane == __ffs(mr) - 1) atomicAdd(&jb.row_cnt[row], __popc(mr));
-        if (!valid) continue;
-        jb.cell_of[i] = c;
-        jb.rank[i] = base + __popc(mc & lt);
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            mc[k] = __match_any_sync(FULL, c[k]);
+            base[k] = 0;
+            if (c[k] >= 0 && lane == __ffs(mc[k]) - 1) base[k] = atomicAdd(&jb.counts[c[k]], __popc(mc[k]));
+            const unsigned mr = __match_any_sync(FULL, row[k]);
+            if (row[k] >= 0 && lane == __ffs(mr) - 1) atomicAdd(&jb.row_cnt[row[k]], __popc(mr));
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const int i = i0 + k * TPB + threadIdx.x;
+            const int b = __shfl_sync(FULL, base[k], __ffs(mc[k]) - 1);
+            if (i < n) {
+                jb.cell_of[i] = c[k];
+                jb.rank[i] = b + __popc(mc[k] & lt);
+            }
+        }
     }
 }
 
@@ -186,12 +197,17 @@ grid_row_apply_kernel(GridJobs jobs, const GridJob *__restrict__ table)
         int *__restrict__ cb = jb.cell_begin + (size_t)r * dx;
         const int *__restrict__ cnt = jb.counts + (size_t)r * dx;
         int run = rb;
-        for (int x0 = 0; x0 < dx; x0 += 32) {
-            const int x = x0 + lane;
-            const int v = x < dx ? cnt[x] : 0;
-            const int inc = warp_incl_scan(v);
-            if (x < dx) cb[x] = run + inc - v;
-            run += __shfl_sync(FULL, inc, 31);
+        for (int x0 = 0; x0 < dx; x0 += 256) {              // 8 independent loads per lane, then 8 warp scans
+            int v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const int x = x0 + j * 32 + lane; v[j] = x < dx ? cnt[x] : 0; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int x = x0 + j * 32 + lane;
+                const int inc = warp_incl_scan(v[j]);
+                if (x < dx) cb[x] = run + inc - v[j];
+                run += __shfl_sync(FULL, inc, 31);
+            }
         }
         if (lane == 0) cb[dx] = run;                         // end of the row's last cell (= next row's first entry)
     }
@@ -203,12 +219,27 @@ grid_scatter_kernel(GridJobs jobs, const GridJob *__restrict__ table)
     const GridJob &jb = table ? table[blockIdx.y] : jobs.j[blockIdx.y];
     const GridDesc *d = jb.desc;
     const int n = d->n;
-    for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-        float4 p = __ldg(&jb.pts[i]);
-        const int c = jb.cell_of[i];
-        jb.sorted[jb.cell_begin[c] + jb.rank[i]] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-        jb.counts[c] = 0;                                    // leave the count tables clean for the next build
-        jb.row_cnt[c / d->dim[0]] = 0;
+    const int dimx = d->dim[0];
+    constexpr int U = 4;
+    for (int i0 = blockIdx.x * TPB * U; i0 < n; i0 += gridDim.x * TPB * U) {
+        float4 p[U]; int c[U], rk[U], cb[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const int i = i0 + k * TPB + threadIdx.x;
+            c[k] = -1;
+            if (i < n) { p[k] = __ldg(&jb.pts[i]); c[k] = jb.cell_of[i]; rk[k] = jb.rank[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) if (c[k] >= 0) cb[k] = jb.cell_begin[c[k]];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const int i = i0 + k * TPB + threadIdx.x;
+            if (c[k] >= 0) {
+                jb.sorted[cb[k] + rk[k]] = make_float4(p[k].x, p[k].y, p[k].z, __int_as_float(i));
+                jb.counts[c[k]] = 0;                         // leave the count tables clean for the next build
+                jb.row_cnt[c[k] / dimx] = 0;
+            }
+        }
     }
 }
 

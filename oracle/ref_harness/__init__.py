@@ -136,6 +136,21 @@ class MapOptimization:
     def clearCloud(self): self.L.ref_mo_clearCloud(self._h)
     def num_keyframes(self) -> int: return self.L.ref_mo_num_keyframes(self._h)
 
+    def surrounding_ids(self) -> np.ndarray:
+        n = self.L.ref_mo_get_surrounding_ids(self._h, None, 0)
+        out = np.zeros(max(n, 1), np.int32)
+        self.L.ref_mo_get_surrounding_ids(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n)
+        return out[:n].copy()
+
+    def keypose6d(self, idx: int) -> np.ndarray:
+        t = np.zeros(6, np.float32); self.L.ref_mo_get_keypose6d(self._h, int(idx), _fp(t)); return t
+
+    def keyframe_cloud(self, idx: int, which: int) -> np.ndarray:
+        n = self.L.ref_mo_get_keyframe_cloud(self._h, int(idx), which, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self.L.ref_mo_get_keyframe_cloud(self._h, int(idx), which, _fp(out), n)
+        return out[:n].copy()
+
 
 class FeatureAssociation:
     """class FeatureAssociation of the reference (FA:37)."""

@@ -136,6 +136,26 @@ void ref_mo_saveKeyFramesAndFactor(void *h) { ((mapOptimization *)h)->saveKeyFra
 void ref_mo_correctPoses(void *h) { ((mapOptimization *)h)->correctPoses(); }
 void ref_mo_clearCloud(void *h) { ((mapOptimization *)h)->clearCloud(); }
 int ref_mo_num_keyframes(void *h) { return (int)((mapOptimization *)h)->cloudKeyPoses3D->points.size(); }
+// key-frame bookkeeping the reference keeps on the host (inputs of the device key-frame store's parity test)
+int ref_mo_get_surrounding_ids(void *h, int *out, int cap)
+{   // surroundingExistingKeyPosesID in order (MO:1033-1049; loopClosureEnableFlag is false, UT:104)
+    mapOptimization *m = (mapOptimization *)h;
+    int n = (int)m->surroundingExistingKeyPosesID.size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = m->surroundingExistingKeyPosesID[i];
+    return n;
+}
+void ref_mo_get_keypose6d(void *h, int idx, float *out6)
+{   // cloudKeyPoses6D[idx]: roll, pitch, yaw, x, y, z
+    mapOptimization *m = (mapOptimization *)h;
+    const PointTypePose &p = m->cloudKeyPoses6D->points[idx];
+    out6[0] = p.roll; out6[1] = p.pitch; out6[2] = p.yaw; out6[3] = p.x; out6[4] = p.y; out6[5] = p.z;
+}
+int ref_mo_get_keyframe_cloud(void *h, int idx, int which, llo_point *out, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    return dump(which == 0 ? m->cornerCloudKeyFrames[idx] : which == 1 ? m->surfCloudKeyFrames[idx]
+                                                                       : m->outlierCloudKeyFrames[idx], out, cap);
+}
 int ref_mo_get_map_raw(void *h, int which, llo_point *out, int cap)
 {
     mapOptimization *m = (mapOptimization *)h;

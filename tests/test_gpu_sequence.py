@@ -78,3 +78,57 @@ def test_sequence_replay_drift_parity(ctx):
     # and the mapping tracks the true trajectory of the synthetic world
     truth = np.array(poses)
     assert np.linalg.norm(gpu[-1, 3:] - truth[-1, 3:]) < 0.5
+
+
+def replay_keyframe_store(ctx, poses, odo, scans):
+    """The same replay with the key-frame clouds kept on the DEVICE (llb_keyframe_add) and the local map assembled
+    there (llb_map_assemble) from the ids / poses the reference's own host bookkeeping selects: the raw and the DS
+    local map never exist on the host, only the new sweep crosses PCIe."""
+    mo = ref_harness.MapOptimization()
+    ctx.keyframe_clear()
+    traj, raw_equal, ds_equal, n_asm = [], True, True, 0
+    for k, (sum_k, sc) in enumerate(zip(odo, scans)):
+        mo.set_odometry(sum_k, 0.4 * k)
+        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
+        mo.transformAssociateToMap()
+        mo.extractSurroundingKeyFrames()             # host bookkeeping (ids) + the reference's own clouds to compare with
+        mo.downsampleCurrentScan()
+        ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
+        ctx.downsample_current_scan()
+        ids = mo.surrounding_ids()
+        nc, ns = mo.map_ds_sizes()
+        if ids.shape[0] > 0:
+            ctx.map_assemble(ids, np.stack([mo.keypose6d(i) for i in ids]))
+            n_asm += 1
+            raw_equal &= np.array_equal(ctx.map_get_raw(0).view(np.uint32), mo.map_raw(0).view(np.uint32))
+            raw_equal &= np.array_equal(ctx.map_get_raw(1).view(np.uint32), mo.map_raw(1).view(np.uint32))
+            ds_equal &= np.array_equal(ctx.map_get_ds(0).view(np.uint32), mo.map_ds(0).view(np.uint32))
+            ds_equal &= np.array_equal(ctx.map_get_ds(1).view(np.uint32), mo.map_ds(1).view(np.uint32))
+        if nc > 10 and ns > 100:                     # guard MO:1331
+            T, st = ctx.s2m_optimize(mo.transformTobeMapped)
+            mo.transformTobeMapped = T
+            mo.transformUpdate()
+        n_before = mo.num_keyframes()
+        mo.saveKeyFramesAndFactor()
+        if mo.num_keyframes() > n_before:            # MO:1443-1453: the DS clouds of this sweep become a key-frame
+            kid = ctx.keyframe_add()
+            assert kid == mo.num_keyframes() - 1
+        mo.correctPoses()
+        mo.clearCloud()
+        traj.append(mo.transformAftMapped.copy())
+    return np.array(traj), raw_equal, ds_equal, n_asm
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="oracle/_ref not built")
+def test_sequence_replay_device_keyframe_store(ctx):
+    poses, odo, scans = make_sequence(N_SCANS)
+    ref, _, _, kf_ref = replay(None, poses, odo, scans)
+    gpu, raw_equal, ds_equal, n_asm = replay_keyframe_store(ctx, poses, odo, scans)
+    assert n_asm >= N_SCANS - 2 and ctx.keyframe_count() == kf_ref
+    assert raw_equal                                  # transformPointCloud + concatenation: bit-exact
+    assert ds_equal                                   # map voxel filters on the assembled map: bit-exact
+    d = np.abs(gpu - ref)
+    assert d[:, :3].max() < 1e-4 and d[:, 3:].max() < 1e-4
+    # a stored key-frame equals the reference's copy of the DS clouds (MO:1447-1449)
+    ctx.keyframe_clear()
+    assert ctx.keyframe_count() == 0
