@@ -4,17 +4,20 @@
 Workload (BASELINE configs[1]/[4]): VLP-16 synthetic sequences replayed against their ~100k-point
 voxel-DS local maps.  A registration = downsampleCurrentScan (MO:1067-1091) + scan2MapOptimization
 (MO:1329-1350, including the spatial-index build that replaces the two kdtree->setInputCloud calls).
-One registration is ~0.2 ms of mostly latency-bound device work, so -- exactly like the reference arm,
-which runs one registration stream per host core -- the GPU arm keeps S independent sequences in flight
-per GPU (one llb context = one CUDA stream per sequence).  A "step" = one registration for each of the
-S sequences; ranks are replicas (weak scaling, no data-path collective).
+One registration is ~0.2 ms of latency-bound device work, so -- exactly like the reference arm, which
+runs one registration stream per host core -- the GPU arm registers S independent sequences per step
+with the batched engine (llb_batch_*: every kernel launch covers all slots; NB batches of S/NB slots
+alternate so that the host work / H2D of one overlaps the kernels of the other).  A "step" = one
+registration for each of the S sequences; ranks are replicas (weak scaling, no data-path collective).
 
-  value : device-resident inputs, CUDA events (first start -> last end over the S streams), max over
-          ranks.  The S resident maps + indices exceed the 126 MB L2 (config.l2), no flush needed.
+  value : device-resident inputs, CUDA events (first start -> last end over the NB batch streams),
+          max over ranks.  The resident maps + indices exceed the 126 MB L2 (config.l2), no flush needed.
   e2e   : the same steps through the C ABI with HOST clouds in pcl::PointXYZI layout (H2D of scan + DS
-          map and D2H of pose + stats inside the timed region), wall clock, T host threads.
-  latency : single sequence, L2 flushed between registrations (ms/scan of the metric).
-  roofline : the persistent K3+K4 kernel, 96 algorithmic bytes per query-iteration.
+          map and D2H of pose + stats inside the timed region), wall clock, one host thread per batch.
+  latency : single sequence through the single-registration path (one persistent kernel), L2 flushed
+          between registrations (ms/scan of the metric).
+  roofline : the kNN + fit kernels of one LM iteration over all slots (K3+K4), 96 algorithmic bytes per
+          query-iteration, timed with CUDA events on the batch stream.
   cpu_baseline : the reference-linked harness (oracle/_ref, kind "reference"; else the oracle port)
           on a bounded sample of the same workload, 1 core.
   --impl reference : the reference's CPU path on all host cores (one registration stream per core).
@@ -173,9 +176,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vlp16_100k", choices=sorted(WORKLOADS))
-    ap.add_argument("--seqs", type=int, default=16, help="independent sequences in flight per GPU")
-    ap.add_argument("--threads", type=int, default=8, help="host threads driving the e2e arm")
-    ap.add_argument("--s2m-ctas", type=int, default=37, help="CTA cap of the persistent scan-to-map kernel (0 = all SMs)")
+    ap.add_argument("--seqs", type=int, default=64, help="independent sequences registered per step per GPU")
+    ap.add_argument("--batches", type=int, default=2, help="batch objects (streams) the sequences are split over")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic sequences generated (slots beyond copy them)")
     ap.add_argument("--scans", type=int, default=2, help="distinct sweeps per sequence rotated through the steps")
     ap.add_argument("--cpu-sample", type=int, default=12, help="registrations timed for cpu_baseline")
     args = ap.parse_args()
@@ -194,138 +197,170 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W, S = args.steps, max(args.warmup, 3), args.seqs
+    NB = max(1, min(args.batches, S))
     dev = torch.device("cuda", local)
 
-    # ---------------- S independent sequences: own map, own sweeps, own context (= own stream)
-    prm = api.default_params()
-    prm.pin_host_clouds = 1                                  # e2e: DMA straight from the (long-lived) host clouds
-    prm.s2m_max_ctas = args.s2m_ctas                         # throughput mode: registrations of different sequences overlap
-    seqs = []
-    setup_ctx = api.Context(local)                           # staging-copy context for the one-off set-up work
-    for s in range(S):
-        mc, ms, scans = make_inputs(args.workload, 1000 * rank + s, args.scans)
+    # ---------------- S independent sequences: own DS map, own sweeps, own slot (own resident index + LM state)
+    D = max(1, min(args.distinct, S))
+    base = []
+    setup_ctx = api.Context(local)                           # one-off set-up work (untimed)
+    for d in range(D):
+        mc, ms, scans = make_inputs(args.workload, 1000 * rank + d, args.scans)
         setup_ctx.map_set_raw(mc, ms)                        # DS map = what the drop-in signature receives (MO:1057-1064
-        mc_ds = setup_ctx.map_get_ds(0); ms_ds = setup_ctx.map_get_ds(1)   # is the caller's tail); once, untimed
-        ctx = api.Context(local, prm)                        # only ever sees the persistent arrays below
-        q = {"ctx": ctx, "stream": torch.cuda.ExternalStream(ctx.stream, device=local), "scans": scans,
-             "mc_ds": mc_ds, "ms_ds": ms_ds, "mc32": api.to_pcl(mc_ds), "ms32": api.to_pcl(ms_ds),
+        base.append((setup_ctx.map_get_ds(0), setup_ctx.map_get_ds(1), scans))   # is the caller's tail); once, untimed
+    setup_ctx.close()
+    seqs = []
+    for s in range(S):
+        mc_ds, ms_ds, scans = base[s % D]
+        q = {"scans": scans, "mc_ds": mc_ds, "ms_ds": ms_ds,
+             # every slot gets its OWN host and device copies: no artificial sharing in L2 or over PCIe
+             "mc32": api.to_pcl(mc_ds), "ms32": api.to_pcl(ms_ds),
              "scans32": [(api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), init)
                          for sc, init in scans],
              "d_mc": torch.from_numpy(mc_ds).to(dev), "d_ms": torch.from_numpy(ms_ds).to(dev),
              "d_scans": [(torch.from_numpy(sc.corner_last).to(dev), torch.from_numpy(sc.surf_last).to(dev),
-                          torch.from_numpy(sc.outlier_last).to(dev), torch.from_numpy(init.copy()).to(dev))
-                         for sc, init in scans],
-             "d_T": torch.zeros(6, dtype=torch.float32, device=dev)}
+                          torch.from_numpy(sc.outlier_last).to(dev)) for sc, init in scans]}
         seqs.append(q)
-    setup_ctx.close()
     torch.cuda.synchronize()
     map_pts = int(np.mean([q["mc_ds"].shape[0] + q["ms_ds"].shape[0] for q in seqs]))
-    # resident bytes per sequence that a registration touches: DS map + re-ordered copy + cell tables (estimate)
-    ws_mb = S * (map_pts * 16 * 2 + 2 * 4 * 2.0e6) / 1e6
+    max_map = max(max(q["mc_ds"].shape[0], q["ms_ds"].shape[0]) for q in seqs) + 1024
+    max_scan = max(max(c.shape[0] for c in sc[:3]) for q in seqs for sc in q["scans32"]) + 256
+    # resident bytes a step touches: per slot the DS map + its re-ordered copy + cell/row tables (estimate)
+    ws_mb = S * (map_pts * 16 * 2 + 2 * 4 * 1.2e6) / 1e6
 
-    def step_dev(q, i):
-        c, s_, o, init = q["d_scans"][i % len(q["d_scans"])]
-        ctx = q["ctx"]
-        with torch.cuda.stream(q["stream"]):
-            q["d_T"].copy_(init, non_blocking=True)
-        ctx.scan_set_dev(c.data_ptr(), c.shape[0], s_.data_ptr(), s_.shape[0], o.data_ptr(), o.shape[0])
-        ctx.downsample_current_scan(want_counts=False)
-        ctx.map_set_ds_dev(q["d_mc"].data_ptr(), q["d_mc"].shape[0], q["d_ms"].data_ptr(), q["d_ms"].shape[0])
-        ctx.s2m_optimize_dev(q["d_T"].data_ptr())
+    prm = api.default_params()
+    prm.pin_host_clouds = 1                                  # e2e: DMA straight from the (long-lived) host clouds
+    groups = [list(range(b, S, NB)) for b in range(NB)]
+    batches = []
+    for g in groups:
+        b = api.Batch(local, len(g), min(max_scan, 8192), max_map, prm)
+        P = api.Batch.pack
+        tabs = {"T": [np.stack([seqs[s]["scans"][i][1] for s in g]).astype(np.float32) for i in range(args.scans)]}
+        for kind, dev_side in (("dev", True), ("host", False)):
+            ptr = (lambda a: a.data_ptr()) if dev_side else (lambda a: a.ctypes.data)
+            mk, sk = ("d_mc", "d_ms") if dev_side else ("mc32", "ms32")
+            tabs[kind + "_map"] = (P([ptr(seqs[s][mk]) for s in g], [seqs[s][mk].shape[0] for s in g]),
+                                   P([ptr(seqs[s][sk]) for s in g], [seqs[s][sk].shape[0] for s in g]))
+            sckey = "d_scans" if dev_side else "scans32"
+            tabs[kind + "_scan"] = [tuple(P([ptr(seqs[s][sckey][i][k]) for s in g], [seqs[s][sckey][i][k].shape[0] for s in g])
+                                          for k in range(3)) for i in range(args.scans)]
+        batches.append({"b": b, "g": g, "tabs": tabs, "stream": torch.cuda.ExternalStream(b.stream, device=local)})
 
-    def sync_all():
-        for q in seqs:
-            q["stream"].synchronize()
-        torch.cuda.synchronize()
+    def enqueue(bt, i, kind):
+        """one step of one batch: hand-over of every slot's sweep + DS map, then all registrations, asynchronously"""
+        b, tabs = bt["b"], bt["tabs"]
+        c, s_, o = tabs[kind + "_scan"][i % args.scans]
+        b.scan_set_all(c, s_, o, dev=(kind == "dev"))
+        mc, ms = tabs[kind + "_map"]
+        b.map_set_ds_all(mc, ms, dev=(kind == "dev"))        # index rebuilt every registration, like the kd-trees MO:1333-1334
+        b.register_async(tabs["T"][i % args.scans])
 
-    for i in range(W):
-        for q in seqs:
-            step_dev(q, i)
-    sync_all()
+    def run_steps(kind, n):
+        """n steps of every batch, software-pipelined from one host thread: while batch A computes, B is prepared"""
+        last = None
+        for i in range(n):
+            for bt in batches:
+                if bt.get("pending"):
+                    last = bt["b"].result(); bt["pending"] = False
+                enqueue(bt, i, kind); bt["pending"] = True
+        for bt in batches:
+            if bt.get("pending"):
+                last = bt["b"].result(); bt["pending"] = False
+        return last
+
+    run_steps("dev", W)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sync_all()
+    torch.cuda.synchronize()
     clk_samples, stop_evt = [], threading.Event()
     th = threading.Thread(target=sample_clocks, args=(stop_evt, clk_samples, local)); th.start()
-    l0 = sum(q["ctx"].launch_count() for q in seqs)
+    l0 = sum(bt["b"].launch_count() for bt in batches)
     e_start = torch.cuda.Event(enable_timing=True)
-    e_ends = [torch.cuda.Event(enable_timing=True) for _ in seqs]
+    e_ends = [torch.cuda.Event(enable_timing=True) for _ in batches]
     t_wall0 = time.perf_counter()
-    e_start.record(seqs[0]["stream"])
-    Td = max(1, min(args.threads, S))                        # host threads enqueueing (launch-rate bound otherwise)
-
-    def dev_worker(t):
-        torch.cuda.set_device(local)
-        for i in range(K):
-            for q in seqs[t::Td]:
-                step_dev(q, i)
-        for q, e in list(zip(seqs, e_ends))[t::Td]:
-            e.record(q["stream"])
-
-    dths = [threading.Thread(target=dev_worker, args=(t,)) for t in range(Td)]
-    for x in dths:
-        x.start()
-    for x in dths:
-        x.join()
-    sync_all()
+    e_start.record(batches[0]["stream"])
+    run_steps("dev", K)
+    for bt, e in zip(batches, e_ends):
+        e.record(bt["stream"])
+    torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    launches = sum(q["ctx"].launch_count() for q in seqs) - l0
+    launches = sum(bt["b"].launch_count() for bt in batches) - l0
     if world > 1:
         dist.barrier()
     total_ms = max(e_start.elapsed_time(e) for e in e_ends)
 
-    # ---------------- single-sequence latency, L2 flushed between registrations
+    # ---------------- roofline of the dominant kernels (kNN + fit of the LM iterations), timed with CUDA events on the
+    # batch stream during extra steps after the timed region (per-stage events perturb the pipelining)
+    b0 = batches[0]
+    b0["b"].set_profile(True)
+    prof_acc, geo, qi_acc, it_max_acc = {}, None, 0, 0
+    NPROF = 5
+    for i in range(NPROF):
+        enqueue(b0, i, "dev"); Tp, stp = b0["b"].result()
+        pr, geo = b0["b"].get_profile()
+        for k, v in pr.items():
+            prof_acc[k] = prof_acc.get(k, 0.0) + v / NPROF
+        qi_acc += sum((x.n_corner_ds + x.n_surf_ds) * x.iterations for x in stp) / NPROF
+        it_max_acc += max(x.iterations for x in stp) / NPROF
+    b0["b"].set_profile(False)
+
+    # ---------------- single-sequence latency (single-registration path, one persistent kernel), L2 flushed
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    lat_ctx = api.Context(local)                             # latency mode: default parameters (one CTA per SM)
-    q0 = dict(seqs[0], ctx=lat_ctx, stream=torch.cuda.ExternalStream(lat_ctx.stream, device=local))
+    lat_ctx = api.Context(local)                             # default parameters: one CTA per SM
+    lat_stream = torch.cuda.ExternalStream(lat_ctx.stream, device=local)
+    q0 = seqs[0]
+    d_T = torch.zeros(6, dtype=torch.float32, device=dev)
+    d_init = [torch.from_numpy(init.copy()).to(dev) for _, init in q0["scans"]]
     lat, lat_host = [], []
-    with torch.cuda.stream(q0["stream"]):
+
+    def step_single(i):
+        c, s_, o = q0["d_scans"][i % args.scans]
+        with torch.cuda.stream(lat_stream):
+            d_T.copy_(d_init[i % args.scans], non_blocking=True)
+        lat_ctx.scan_set_dev(c.data_ptr(), c.shape[0], s_.data_ptr(), s_.shape[0], o.data_ptr(), o.shape[0])
+        lat_ctx.downsample_current_scan(want_counts=False)
+        lat_ctx.map_set_ds_dev(q0["d_mc"].data_ptr(), q0["d_mc"].shape[0], q0["d_ms"].data_ptr(), q0["d_ms"].shape[0])
+        lat_ctx.s2m_optimize_dev(d_T.data_ptr())
+
+    with torch.cuda.stream(lat_stream):
         for i in range(W + 20):
             flush.zero_()
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(q0["stream"]); step_dev(q0, i); b.record(q0["stream"])
-            q0["stream"].synchronize()
+            a.record(lat_stream); step_single(i); b.record(lat_stream)
+            lat_stream.synchronize()
             if i >= W:
                 lat.append(a.elapsed_time(b))
         for i in range(W + 20):                              # the same through the C ABI with host clouds, wall clock
-            c, s_, o, init = q0["scans32"][i % len(q0["scans32"])]
-            flush.zero_(); q0["stream"].synchronize()
+            c, s_, o, init = q0["scans32"][i % args.scans]
+            flush.zero_(); lat_stream.synchronize()
             t0 = time.perf_counter()
             lat_ctx.scan_set_pcl(c, s_, o); lat_ctx.downsample_current_scan(want_counts=False)
             lat_ctx.map_set_ds_pcl(q0["mc32"], q0["ms32"]); lat_ctx.s2m_optimize(init)
             if i >= W:
                 lat_host.append((time.perf_counter() - t0) * 1e3)
     del flush
+    lat_ctx.close()
 
-    # ---------------- end-to-end arm: host clouds through the C ABI, T host threads
-    T = max(1, min(args.threads, S))
-    barrier = threading.Barrier(T + 1)
+    # ---------------- end-to-end arm: host clouds through the C ABI, one host thread per batch (the H2D of one batch
+    # overlaps the kernels of the other)
+    barrier = threading.Barrier(NB + 1)
     last = {}
 
-    def worker(t):
-        mine = seqs[t::T]
+    def worker(k):
+        torch.cuda.set_device(local)
+        bt = batches[k]
         for i in range(W):
-            for q in mine:
-                c, s_, o, init = q["scans32"][i % len(q["scans32"])]
-                q["ctx"].scan_set_pcl(c, s_, o); q["ctx"].downsample_current_scan(want_counts=False)
-                q["ctx"].map_set_ds_pcl(q["mc32"], q["ms32"]); q["ctx"].s2m_optimize_async(init)
-            for q in mine:
-                q["ctx"].s2m_result()
+            enqueue(bt, i, "host"); bt["b"].result()
         barrier.wait()
         for i in range(K):
-            for q in mine:
-                c, s_, o, init = q["scans32"][i % len(q["scans32"])]
-                q["ctx"].scan_set_pcl(c, s_, o)
-                q["ctx"].downsample_current_scan(want_counts=False)
-                q["ctx"].map_set_ds_pcl(q["mc32"], q["ms32"])
-                q["ctx"].s2m_optimize_async(init)
-            for q in mine:
-                res = q["ctx"].s2m_result()
-            if t == 0:
-                last["T"], last["st"] = res
+            enqueue(bt, i, "host")
+            res = bt["b"].result()
+        if k == 0:
+            last["T"], last["st"] = res
         barrier.wait()
 
-    ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(NB)]
     for x in ths:
         x.start()
     barrier.wait()
@@ -340,9 +375,6 @@ def main():
         dist.barrier()
     stop_evt.set(); th.join()
 
-    # ---------------- roofline of the dominant kernel (timed alone, after the steps)
-    ms_launch, nq = q0["ctx"].s2m_time_iteration(q0["scans32"][0][3], reps=50)
-
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -351,31 +383,41 @@ def main():
     if rank == 0:
         ms_per_step = total_ms / K
         value = world * S * K / (total_ms / 1e3)
-        h2d_reg = sum(a.nbytes for a in q0["scans32"][0][:3]) + q0["mc32"].nbytes + q0["ms32"].nbytes + 24
+        h2d_reg = [sum(a.nbytes for a in q["scans32"][0][:3]) + q["mc32"].nbytes + q["ms32"].nbytes + 24 for q in seqs]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = ALG_BYTES_PER_QUERY * nq / (ms_launch * 1e-3) / 1e9
+        # K3+K4 of one LM iteration over all slots of a batch = one kNN launch + one fit launch
+        nb0 = len(b0["g"])
+        kern_ms = prof_acc["knn"] + prof_acc["fit"]
+        ms_launch = kern_ms / max(it_max_acc, 1e-9)
+        alg_bytes_launch = ALG_BYTES_PER_QUERY * qi_acc / max(it_max_acc, 1e-9)
+        achieved = ALG_BYTES_PER_QUERY * qi_acc / (kern_ms * 1e-3) / 1e9
         traffic = None
-        try:                                                 # dram bytes per launch from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        try:                                                 # dram bytes per launch pair from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
             if args.workload == "vlp16_100k":
-                traffic = int(tj["dram_bytes_per_launch"])
+                traffic = int(tj["dram_bytes_per_launch"] * nb0 / tj["slots"])
         except Exception:
             pass
         # bounded CPU sample on this box's host cores, 1 core; also the pose check of the e2e result
-        tsel = seqs[0::T][-1]                                # the sequence whose result thread 0 reported last
-        run_cpu, kind = cpu_registration_factory(tsel["mc_ds"], tsel["ms_ds"], tsel["scans"])
+        g0 = batches[0]["g"]
         n_cpu = max(args.cpu_sample, 1)
+        run_cpu, kind = cpu_registration_factory(seqs[g0[0]]["mc_ds"], seqs[g0[0]]["ms_ds"], seqs[g0[0]]["scans"])
         run_cpu(0)
         t0 = time.perf_counter()
         for i in range(n_cpu):
             run_cpu(i)
         cpu_s = time.perf_counter() - t0
-        pose_diff = float(np.max(np.abs(last["T"] - run_cpu(K - 1)))) if "T" in last else None
+        pose_diff = None
+        if "T" in last:                                      # every DISTINCT sequence of batch 0 against the CPU reference
+            pose_diff = 0.0
+            for j, s in enumerate(g0[:D]):
+                rc, _ = cpu_registration_factory(seqs[s]["mc_ds"], seqs[s]["ms_ds"], seqs[s]["scans"])
+                pose_diff = max(pose_diff, float(np.max(np.abs(last["T"][j] - rc(K - 1)))))
         line = {
             "metric": "scan-to-map registrations/s", "value": value, "unit": "registrations/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -383,40 +425,46 @@ def main():
             "config": {"workload": f"{args.workload}: {S} independent VLP-16 (16x1800) synthetic sequences per GPU, each "
                                    f"sweep vs its own ~{map_pts}-pt voxel-DS local map; registration = "
                                    f"downsampleCurrentScan + scan2MapOptimization (index build + <=10 LM iterations); "
-                                   f"step = one registration per sequence",
-                       "sequences_per_gpu": S, "registrations_per_step": S * world, "queries_per_iteration": nq,
+                                   f"step = one registration per sequence, batched engine ({NB} batches x {S // NB} slots)",
+                       "sequences_per_gpu": S, "batches": NB, "distinct_sequences": D,
+                       "registrations_per_step": S * world, "queries_per_registration": int(np.mean([x.n_corner_ds + x.n_surf_ds for x in stp])),
                        "map_points": map_pts,
-                       "l2": f"no flush in the throughput arms: the {S} resident maps+indices touch ~{ws_mb:.0f} MB "
-                             f"per step (> 126 MB L2); the latency arm flushes L2 (256 MiB write) before every registration",
-                       "timing": "CUDA events, first start to last end over the per-sequence streams, max over ranks",
-                       "e2e_host_threads": T, "pin_host_clouds": 1, "s2m_max_ctas": args.s2m_ctas},
+                       "l2": f"no flush in the throughput arms: every slot has its own map, index and clouds, ~{ws_mb:.0f} MB "
+                             f"touched per step (> 126 MB L2); the latency arm flushes L2 (256 MiB write) before every registration",
+                       "timing": "CUDA events, first start to last end over the batch streams (host gaps included), max over ranks",
+                       "e2e_host_threads": NB, "pin_host_clouds": 1},
             "e2e": {"value": world * S * K / e2e_s, "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(h2d_reg * S), "d2h_bytes_per_step": int((6 * 4 + 72 + 28) * S),
-                    "ms_per_step": e2e_s / K * 1e3},
+                    "h2d_bytes_per_step": int(sum(h2d_reg)), "d2h_bytes_per_step": int(64 * S),
+                    "ms_per_step": e2e_s / K * 1e3,
+                    "note": "scan AND voxel-DS map cross PCIe for every registration (the drop-in signature hands both over); "
+                            "PCIe-bound"},
             "latency": {"ms_per_scan_device": float(np.median(lat)), "ms_per_scan_device_max": float(np.max(lat)),
                         "ms_per_scan_e2e_host": float(np.median(lat_host)), "ms_per_scan_e2e_host_max": float(np.max(lat_host)),
-                        "note": "one sequence alone, default parameters (one CTA per SM), L2 flushed before each "
-                                "registration; e2e_host = host PCL clouds in, pose out, wall clock, staging copy (no pinning)"},
+                        "note": "one sequence alone on the single-registration path (one persistent kernel, one CTA per SM), L2 "
+                                "flushed before each registration; e2e_host = host PCL clouds in, pose out, wall clock"},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk_samples),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r01_traffic.json (same workload)",
-                         "kernel": "s2m_loop_kernel (one accumulate-only iteration)",
+                         "traffic": traffic,
+                         "traffic_source": "ncu --set full captures of both kernels, profiles/r01c_traffic.json (same workload)",
+                         "kernel": "batch_knn_kernel + batch_fit_kernel (K3+K4 of one LM iteration over all slots of a batch)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "ms_per_launch": ms_launch, "alg_bytes_per_launch": ALG_BYTES_PER_QUERY * nq,
-                         "note": "latency/instruction-bound by construction at this size (DESIGN.md section 3)"},
+                         "ms_per_launch": ms_launch, "alg_bytes_per_launch": alg_bytes_launch,
+                         "slots_per_launch": nb0, "stage_ms_per_step": prof_acc, "geometry": geo,
+                         "note": "instruction/latency-bound, not bandwidth-bound: ~1.8k thread instructions per query-iteration "
+                                 "for 96 algorithmic bytes (DESIGN.md section 3)"},
             "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "registrations/s", "cores": 1, "kind": kind,
                              "sample": f"{n_cpu} registrations of the same workload, 1 core",
                              "ms_per_registration": cpu_s / n_cpu * 1e3},
             "wall_s_timed_region": t_wall,
-            "last_stats": last["st"].as_dict() if "st" in last else None,
+            "last_stats": last["st"][0].as_dict() if "st" in last else None,
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    for q in seqs:
-        q["ctx"].close()
+    for bt in batches:
+        bt["b"].close()
     return 0
 
 

@@ -242,6 +242,15 @@ int  llb_batch_map_set_ds(llb_batch *b, int slot, const llb_point *corner_ds, in
 int  llb_batch_scan_set_dev(llb_batch *b, int slot, const void *corner_f4, int nc, const void *surf_f4, int ns,
                             const void *outlier_f4, int no);
 int  llb_batch_map_set_ds_dev(llb_batch *b, int slot, const void *corner_ds_f4, int mc, const void *surf_ds_f4, int ms);
+/* the same for ALL slots with one call: arrays of n_slots pointers / counts */
+int  llb_batch_scan_set_all(llb_batch *b, const llb_point *const *corner_last, const int *nc,
+                            const llb_point *const *surf_last, const int *ns, const llb_point *const *outlier_last, const int *no);
+int  llb_batch_map_set_ds_all(llb_batch *b, const llb_point *const *corner_ds, const int *mc,
+                              const llb_point *const *surf_ds, const int *ms);
+int  llb_batch_scan_set_dev_all(llb_batch *b, const void *const *corner_f4, const int *nc, const void *const *surf_f4,
+                                const int *ns, const void *const *outlier_f4, const int *no);
+int  llb_batch_map_set_ds_dev_all(llb_batch *b, const void *const *corner_ds_f4, const int *mc,
+                                  const void *const *surf_ds_f4, const int *ms);
 /* T: n_slots x 6 transformTobeMapped in/out; stats: n_slots entries (device_ms = the whole step) or NULL */
 int  llb_batch_register(llb_batch *b, float *T, llb_stats *stats);
 int  llb_batch_register_async(llb_batch *b, const float *T);

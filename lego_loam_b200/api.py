@@ -70,7 +70,8 @@ EXPORTS = [
     "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
     "llb_batch_launch_count", "llb_batch_scan_set", "llb_batch_map_set_ds", "llb_batch_scan_set_dev",
-    "llb_batch_map_set_ds_dev", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
+    "llb_batch_map_set_ds_dev", "llb_batch_scan_set_all", "llb_batch_map_set_ds_all", "llb_batch_scan_set_dev_all",
+    "llb_batch_map_set_ds_dev_all", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
     "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
 ]
 
@@ -470,6 +471,24 @@ class Batch:
 
     def map_set_ds_dev(self, slot: int, c_ptr: int, mc: int, s_ptr: int, ms: int):
         self._ck(lib().llb_batch_map_set_ds_dev(self._h, slot, ctypes.c_void_p(c_ptr), mc, ctypes.c_void_p(s_ptr), ms))
+
+    @staticmethod
+    def pack(ptrs, counts):
+        """-> (uint64 pointer array, int32 count array) for the *_all calls (build once, reuse every step)"""
+        return np.ascontiguousarray(ptrs, np.uint64), np.ascontiguousarray(counts, np.int32)
+
+    @staticmethod
+    def _pa(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def scan_set_all(self, c, s, o, dev: bool):
+        """c, s, o: (pointer array, count array) pairs from pack(); dev selects device float4 / host PCL clouds"""
+        fn = lib().llb_batch_scan_set_dev_all if dev else lib().llb_batch_scan_set_all
+        self._ck(fn(self._h, self._pa(c[0]), self._pa(c[1]), self._pa(s[0]), self._pa(s[1]), self._pa(o[0]), self._pa(o[1])))
+
+    def map_set_ds_all(self, c, s, dev: bool):
+        fn = lib().llb_batch_map_set_ds_dev_all if dev else lib().llb_batch_map_set_ds_all
+        self._ck(fn(self._h, self._pa(c[0]), self._pa(c[1]), self._pa(s[0]), self._pa(s[1])))
 
     def register(self, T):
         """T: (n_slots, 6) initial transformTobeMapped -> (poses (n_slots, 6), [Stats] * n_slots)"""

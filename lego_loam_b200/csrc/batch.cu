@@ -5,6 +5,8 @@
 #include "batch.cuh"
 #include "s2m_dev.cuh"
 #include "knn.cuh"
+#include "cta_radix.cuh"
+#include <cstdlib>
 
 namespace llb {
 
@@ -52,16 +54,195 @@ __global__ void batch_prepare_kernel(const BatchReg *__restrict__ regs, const fl
     st->skipped = !(r.cmap.desc->n > prm.corner_map_min && r.smap.desc->n > prm.surf_map_min);
 }
 
-// ---- iteration, step 1: pointAssociateToMap + radius-bounded exact 5-NN, one THREAD per query.
-// Throughput form of knn.cuh's search: a thread walks the (up to) nine cell runs around its query and keeps the five
-// smallest (distance, original index) pairs inside the gate in registers - ~10 instructions per candidate instead of
-// a warp-wide ballot / compaction / arg-min per 32 candidates (measured 4.5x fewer warp instructions per query).
+// ---- query binning, once per registration: the queries of a slot are ordered by the MAP cell they fall into at the
+// initial pose (stable radix sort in shared memory, one CTA per slot and query kind).  The kNN kernel hands thread j
+// the j-th query of that order, so the lanes of a warp search the same cell runs: uniform loop trip counts and
+// warp-broadcast candidate loads.  The pose moves by centimetres between LM iterations - far less than a cell - so
+// the order stays good for the whole registration; it only affects speed, never results.
+constexpr int QS_THREADS = 512;
+constexpr int QS_ITEMS = 4;
+
+__global__ void __launch_bounds__(QS_THREADS)
+batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap)
+{
+    extern __shared__ __align__(16) unsigned char qs_smem[];
+    unsigned *kin = reinterpret_cast<unsigned *>(qs_smem), *kout = kin + cap;
+    unsigned short *vin = reinterpret_cast<unsigned short *>(kout + cap), *vout = vin + cap;
+    __shared__ int s_wcnt[QS_THREADS / 32][256];
+    __shared__ int s_base[256];
+    __shared__ int s_scan[33];
+    const BatchReg r = regs[blockIdx.y];
+    const S2mState *st = r.st;
+    if (st->skipped) return;
+    const int which = blockIdx.x;                            // 0: corner queries, 1: surf queries
+    const int nc = *r.nc_dev, ns = *r.ns_dev;
+    const int n = which == 0 ? nc : ns;
+    if (n <= 0 || nc + ns > r.cap) return;
+    int *__restrict__ perm = r.qperm + (which == 0 ? 0 : nc);
+    const int tid = threadIdx.x;
+    if (n > cap || n > 65535) {                              // does not fit the shared-memory sort: keep scan order
+        for (int i = tid; i < n; i += QS_THREADS) perm[i] = i;
+        return;
+    }
+    const float crx = st->cs[0], srx = st->cs[1], cry = st->cs[2], sry = st->cs[3], crz = st->cs[4], srz = st->cs[5];
+    const float tX = st->T[3], tY = st->T[4], tZ = st->T[5];
+    const GridDesc *g = which == 0 ? r.cmap.desc : r.smap.desc;
+    const float4 *__restrict__ qs = which == 0 ? r.corner : r.surf;
+    const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
+    const float inv = g->inv_cell, ox = g->org[0], oy = g->org[1], oz = g->org[2];
+    for (int i = tid; i < n; i += QS_THREADS) {
+        float sx, sy, sz;
+        associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, __ldg(&qs[i]), sx, sy, sz);
+        const int cx = min(max(grid_coord(sx, ox, inv), 0), dimx - 1);
+        const int cy = min(max(grid_coord(sy, oy, inv), 0), dimy - 1);
+        const int cz = min(max(grid_coord(sz, oz, inv), 0), dimz - 1);
+        kin[i] = (unsigned)((cz * dimy + cy) * dimx + cx);
+        vin[i] = (unsigned short)i;
+    }
+    int nbits = 1;
+    while (nbits < 32 && ((unsigned)(g->ncell - 1) >> nbits) != 0u) nbits++;
+    cta_radix_sort<QS_THREADS, QS_ITEMS>(kin, kout, vin, vout, n, nbits, s_wcnt, s_base, s_scan);
+    for (int i = tid; i < n; i += QS_THREADS) perm[i] = (int)vin[i];
+}
+
+// ---- iteration, step 1: pointAssociateToMap + radius-bounded exact 5-NN, one THREAD per query, two phases.
+// Throughput form of knn.cuh's search.  Phase 1 walks the (up to) nine cell runs around the query and appends every
+// candidate INSIDE the gate (d2 < 1, ~15 % of them) to a per-thread list in shared memory: ~14 straight-line
+// instructions per candidate, no divergent path.  Phase 2 pushes the ~20 listed candidates through a branch-free
+// sorted insertion and keeps the five smallest (distance, original index) pairs - the oracle's tie rule.  (A first
+// single-phase version kept the top five while scanning: its rarely-taken insertion path ran with 1-3 active lanes
+// and ncu showed 8.5 active lanes per instruction on average; profiles/r01c_batch.md.)
 // Consecutive queries are voxel-ordered DS points, i.e. spatial neighbours: the lanes of a warp read the same cells
-// and the float4 candidate loads hit L1.  Rows whose slab is farther than the gate radius are skipped (1 % margin:
-// cell membership is decided by the same floorf expression for map points and queries, rounding differences are
-// orders of magnitude below the margin).
+// and the float4 candidate loads hit L1 (81 %).  Rows whose slab is farther than the gate radius are skipped (1 %
+// margin: cell membership is decided by the same floorf expression for map points and queries, rounding
+// differences are orders of magnitude below the margin); empty rows are skipped through the row directory.
+constexpr int KNN_LCAP = 32;                                 // list entries per thread (compressed to 5 when full)
+
+// five smallest (d, original index) of the thread's list, ascending, by branch-free sorted insertion.  The list holds
+// positions in `sorted` only (4 B per entry keeps shared memory small and L1 large); distance and original index (the
+// tie-breaker) are re-derived from the candidate itself - the same float expression, hence the same bits.
+__device__ __forceinline__ void knn_select5_thread(const int (*li)[BATCH_KNN_THREADS], int cnt, int tid,
+                                                   const float4 *__restrict__ sorted, float qx, float qy, float qz,
+                                                   float (&bd)[5], int (&bi)[5], int (&bp)[5])
+{
+#pragma unroll
+    for (int k = 0; k < 5; k++) { bd[k] = __int_as_float(0x7f800000); bi[k] = 0x7fffffff; bp[k] = -1; }
+    for (int j = 0; j < cnt; j++) {
+        int pos = li[j][tid];
+        const float4 p = __ldg(&sorted[pos]);
+        float d = l2_simple(qx, qy, qz, p);
+        int oi = __float_as_int(p.w);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {                        // (d, oi, pos) sinks to its place, the rest shifts down
+            const bool lt = d < bd[k] || (d == bd[k] && oi < bi[k]);
+            const float td = lt ? bd[k] : d; const int ti = lt ? bi[k] : oi; const int tp = lt ? bp[k] : pos;
+            bd[k] = lt ? d : bd[k]; bi[k] = lt ? oi : bi[k]; bp[k] = lt ? pos : bp[k];
+            d = td; oi = ti; pos = tp;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(BATCH_KNN_THREADS, 4)
 batch_knn_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
+{
+    __shared__ int s_li[KNN_LCAP][BATCH_KNN_THREADS];
+    const BatchReg r = regs[blockIdx.y];
+    const S2mState *st = r.st;
+    if (__ldcg(&st->skipped) || __ldcg(&st->converged)) return;
+    const int tid = threadIdx.x;
+    const float crx = __ldcg(&st->cs[0]), srx = __ldcg(&st->cs[1]), cry = __ldcg(&st->cs[2]),
+                sry = __ldcg(&st->cs[3]), crz = __ldcg(&st->cs[4]), srz = __ldcg(&st->cs[5]);
+    const float tX = __ldcg(&st->T[3]), tY = __ldcg(&st->T[4]), tZ = __ldcg(&st->T[5]);
+    const int nc = *r.nc_dev, ns = *r.ns_dev;
+    const int nq = min(nc + ns, r.cap);
+    const float max_sq = prm.knn_max_sqdist;
+    const float prune_sq = max_sq * 1.01f;
+    for (int j = blockIdx.x * BATCH_KNN_THREADS + tid; j < nq; j += gridDim.x * BATCH_KNN_THREADS) {
+        const bool is_corner = j < nc;
+        const int q = (is_corner ? 0 : nc) + __ldg(&r.qperm[j]);      // cell-ordered query (batch_qsort_kernel)
+        const float4 po = is_corner ? __ldg(&r.corner[q]) : __ldg(&r.surf[q - nc]);
+        float sx, sy, sz;
+        associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
+        const GridDesc *g = is_corner ? r.cmap.desc : r.smap.desc;
+        const int *__restrict__ cell_begin = is_corner ? r.cmap.cell_begin : r.smap.cell_begin;
+        const int *__restrict__ row_begin = is_corner ? r.cmap.row_begin : r.smap.row_begin;
+        const float4 *__restrict__ sorted = is_corner ? r.cmap.sorted : r.smap.sorted;
+        const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
+        const float inv = g->inv_cell, cell = g->cell;
+        const float fy = (sy - g->org[1]) * inv, fz = (sz - g->org[2]) * inv;
+        const int cx = grid_coord(sx, g->org[0], inv), cy = (int)floorf(fy), cz = (int)floorf(fz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
+        // distance from the query to the neighbouring rows' slabs, in metres (0 for the query's own row)
+        const float ly = (fy - (float)cy) * cell, lz = (fz - (float)cz) * cell;
+        int found = 0;
+        int *my_list = &s_li[0][tid];
+        if (x0 <= x1) {
+#pragma unroll 1
+            for (int rr = 0; rr < 9; rr++) {
+                const int dy = (rr % 3) - 1, dz = (rr / 3) - 1;
+                const int y = cy + dy, z = cz + dz;
+                if (y < 0 || y >= dimy || z < 0 || z >= dimz) continue;
+                const float gy = dy < 0 ? ly : (dy > 0 ? cell - ly : 0.f);
+                const float gz = dz < 0 ? lz : (dz > 0 ? cell - lz : 0.f);
+                if (gy * gy + gz * gz > prune_sq) continue;
+                const int ry = z * dimy + y;
+                if (__ldg(&row_begin[ry + 1]) == __ldg(&row_begin[ry])) continue;     // empty row: no cell table there
+                const int row = ry * dimx;
+                const int rb = __ldg(&cell_begin[row + x0]), re = __ldg(&cell_begin[row + x1 + 1]);
+#pragma unroll 4
+                for (int i = rb; i < re; i++) {
+                    const float4 p = __ldg(&sorted[i]);
+                    const float d = l2_simple(sx, sy, sz, p);
+                    const bool in = d < max_sq;
+                    if (in && found < KNN_LCAP) my_list[found * BATCH_KNN_THREADS] = i;   // predicated store
+                    found += in ? 1 : 0;
+                }
+            }
+        }
+        int cnt = min(found, KNN_LCAP);
+        if (found > KNN_LCAP) {
+            // more in-gate candidates than list entries (dense corner clusters, rare): second walk that keeps the list
+            // compressed to its best five whenever it fills up
+            cnt = 0;
+#pragma unroll 1
+            for (int rr = 0; rr < 9; rr++) {
+                const int y = cy + (rr % 3) - 1, z = cz + (rr / 3) - 1;
+                if (y < 0 || y >= dimy || z < 0 || z >= dimz) continue;
+                const int ry = z * dimy + y;
+                if (__ldg(&row_begin[ry + 1]) == __ldg(&row_begin[ry])) continue;
+                const int row = ry * dimx;
+                const int rb = __ldg(&cell_begin[row + x0]), re = __ldg(&cell_begin[row + x1 + 1]);
+#pragma unroll 1
+                for (int i = rb; i < re; i++) {
+                    const float d = l2_simple(sx, sy, sz, __ldg(&sorted[i]));
+                    if (d < max_sq) {
+                        if (cnt == KNN_LCAP) {
+                            float cd[5]; int ci[5], cp[5];
+                            knn_select5_thread(s_li, cnt, tid, sorted, sx, sy, sz, cd, ci, cp);
+#pragma unroll
+                            for (int k = 0; k < 5; k++) s_li[k][tid] = cp[k];
+                            cnt = 5;
+                        }
+                        s_li[cnt][tid] = i;
+                        cnt++;
+                    }
+                }
+            }
+        }
+        float bd[5]; int bi[5], bp[5];
+        knn_select5_thread(s_li, cnt, tid, sorted, sx, sy, sz, bd, bi, bp);
+#pragma unroll
+        for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = found >= 5 ? bp[k] : -1;
+        r.d5[q] = found >= 5 ? bd[4] : -1.f;
+    }
+}
+
+// DEFAULT kNN kernel: single phase, the five best (distance, original index) pairs live in registers while the thread
+// scans its candidates.  Measured on B200 (64 slots x ~3.5k queries, profiles/r01c_batch.md): 118 us per iteration vs
+// 157 us for the two-phase list variant above (LLB_KNN_VARIANT=2), with or without cell-ordered queries: both are bound
+// by unequal candidate counts of neighbouring lanes (8-14 active lanes per instruction), not by the insertion path.
+__global__ void __launch_bounds__(256, 4)
+batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
 {
     const BatchReg r = regs[blockIdx.y];
     const S2mState *st = r.st;
@@ -73,8 +254,9 @@ batch_knn_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
     const int nq = min(nc + ns, r.cap);
     const float max_sq = prm.knn_max_sqdist;
     const float prune_sq = max_sq * 1.01f;
-    for (int q = blockIdx.x * BATCH_KNN_THREADS + threadIdx.x; q < nq; q += gridDim.x * BATCH_KNN_THREADS) {
-        const bool is_corner = q < nc;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < nq; j += gridDim.x * 256) {
+        const bool is_corner = j < nc;
+        const int q = j;                                     // scan order (cell-ordered queries measured no faster)
         const float4 po = is_corner ? __ldg(&r.corner[q]) : __ldg(&r.surf[q - nc]);
         float sx, sy, sz;
         associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
@@ -93,7 +275,7 @@ batch_knn_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
 #pragma unroll
         for (int k = 0; k < 5; k++) { bd[k] = __int_as_float(0x7f800000); bi[k] = 0x7fffffff; bp[k] = -1; }
         int found = 0;
-        if (x0 <= x1) {
+                if (x0 <= x1) {
 #pragma unroll 1
             for (int rr = 0; rr < 9; rr++) {
                 const int dy = (rr % 3) - 1, dz = (rr / 3) - 1;
@@ -257,8 +439,31 @@ void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, c
     LLB_CUDA(cudaGetLastError());
 }
 
+int batch_knn_variant()
+{
+    static const int variant = getenv("LLB_KNN_VARIANT") ? atoi(getenv("LLB_KNN_VARIANT")) : 1;
+    return variant;
+}
+
+void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s)
+{
+    static int attr_cap = 0;
+    const int bytes = cap * 12;
+    if (bytes > attr_cap) {
+        LLB_CUDA(cudaFuncSetAttribute(batch_qsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        attr_cap = bytes;
+    }
+    batch_qsort_kernel<<<dim3(2, B), QS_THREADS, bytes, s>>>(regs, cap);
+    LLB_CUDA(cudaGetLastError());
+}
+
 void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s)
 {
+    if (batch_knn_variant() != 2) {
+        batch_knn1_kernel<<<dim3(std::max(1, ctas_per_slot * BATCH_KNN_THREADS / 256), B), 256, 0, s>>>(regs, prm);
+        LLB_CUDA(cudaGetLastError());
+        return;
+    }
     batch_knn_kernel<<<dim3(std::max(1, ctas_per_slot), B), BATCH_KNN_THREADS, 0, s>>>(regs, prm);
     LLB_CUDA(cudaGetLastError());
 }

@@ -29,6 +29,7 @@ struct BatchReg {                    // device-resident record of one slot, read
     MapIndexView cmap, smap;
     S2mState *st;
     int *nn;                         // [5][cap] positions of the 5 neighbours in the map's sorted array
+    int *qperm;                      // [cap] cell-ordered query permutation (corner part, then surf part)
     float *d5;                       // [cap] 5th squared distance, -1 when fewer than 5 candidates inside the gate
     double *partials;                // [fit blocks][S2M_ACC]
     int cap;                         // query slots of nn / d5
@@ -49,6 +50,8 @@ constexpr int BATCH_KNN_THREADS = 256;
 // kernels (batch.cu)
 void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s);
 void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, cudaStream_t s);
+int batch_knn_variant();   // 1 (default): single-phase register top-5; 2: cell-ordered queries + two-phase list
+void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s);
 void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s);
 void launch_batch_fit(const BatchReg *regs, int B, int fit_blocks, int iter, const S2mParams &prm, cudaStream_t s);
 void launch_batch_collect(const BatchReg *regs, int B, BatchResult *out, cudaStream_t s);

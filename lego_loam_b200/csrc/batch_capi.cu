@@ -57,7 +57,7 @@ struct llb_batch {
     DevBuf<int> ds_n;            // [B][4]
     std::vector<GridIndex> grids;   // 2B
     DevBuf<S2mState> states;
-    DevBuf<int> nn; DevBuf<float> d5; DevBuf<double> partials;
+    DevBuf<int> nn; DevBuf<int> qperm; DevBuf<float> d5; DevBuf<double> partials;
     DevBuf<BatchResult> results;
     PinnedBuf<BatchResult> pin_results;
     DevBuf<unsigned char> step_dev;
@@ -208,6 +208,7 @@ int enqueue_step(llb_batch *c, const float *T)
         r.cmap = c->grids[2 * s].view(); r.smap = c->grids[2 * s + 1].view();
         r.st = c->states.p + s;
         r.nn = c->nn.p + (size_t)s * 5 * c->qcap; r.d5 = c->d5.p + (size_t)s * c->qcap;
+        r.qperm = c->qperm.p + (size_t)s * c->qcap;
         r.partials = c->partials.p + (size_t)s * c->fit_blocks * S2M_ACC;
         r.cap = c->qcap;
         for (int i = 0; i < 6; i++) h_poses[6 * s + i] = T[6 * s + i];
@@ -243,6 +244,10 @@ int enqueue_step(llb_batch *c, const float *T)
     const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
     launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
     c->launches++;
+    if (batch_knn_variant() == 2) {                          // experimental kNN variant: cell-ordered queries
+        launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);
+        c->launches++;
+    }
     prof_mark(c, 5);
     for (int it = 0; it < c->prm.s2m_max_iterations; it++) {
         launch_batch_knn(regs, B, c->knn_ctas, c->sprm, c->stream);
@@ -332,10 +337,10 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
         c->ds_n.ensure((size_t)B * 4);
         LLB_CUDA(cudaMemset(c->ds_n.p, 0, sizeof(int) * 4 * B));
         c->states.ensure(B);
-        c->nn.ensure((size_t)B * 5 * c->qcap); c->d5.ensure((size_t)B * c->qcap);
+        c->nn.ensure((size_t)B * 5 * c->qcap); c->d5.ensure((size_t)B * c->qcap); c->qperm.ensure((size_t)B * c->qcap);
         // launch geometry: enough CTAs to fill 148 SMs several times over, independent of B
         c->fit_blocks = std::max(1, std::min(div_up(c->qcap, BATCH_FIT_THREADS), std::max(2, 148 * 8 / B)));
-        c->knn_ctas = std::max(1, std::min(div_up(c->qcap, BATCH_KNN_THREADS), std::max(2, 148 * 8 / B)));
+        c->knn_ctas = std::max(1, std::min(div_up(c->qcap, BATCH_KNN_THREADS), std::max(2, 148 * 12 / B)));
         c->grid_ctas = std::max(2, std::min(148 * 4, 148 * 8 / (2 * B)));
         c->partials.ensure((size_t)B * c->fit_blocks * S2M_ACC);
         c->results.ensure(B); c->pin_results.ensure(B);
@@ -361,7 +366,7 @@ int llb_batch_destroy(llb_batch *c)
     cudaDeviceSynchronize();
     for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
     c->scan_in.release(); c->scan_raw.release(); c->scan_ds.release(); c->map_in.release(); c->map_raw.release();
-    c->ds_n.release(); c->states.release(); c->nn.release(); c->d5.release(); c->partials.release();
+    c->ds_n.release(); c->states.release(); c->nn.release(); c->qperm.release(); c->d5.release(); c->partials.release();
     c->results.release(); c->pin_results.release(); c->step_dev.release();
     for (int i = 0; i < RING; i++) { c->step_pin[i].release(); if (c->step_ev[i]) cudaEventDestroy(c->step_ev[i]); }
     for (auto &g : c->grids) g.release();
@@ -443,6 +448,52 @@ int llb_batch_map_set_ds_dev(llb_batch *c, int slot, const void *corner, int mc,
         sl.map_set = true; sl.map_dirty = true;
         return (int)LLB_OK;
     });
+}
+
+// bulk setters: one call for all slots (arrays of n_slots pointers / counts); a NULL pointer array entry with a zero
+// count is an empty cloud
+int llb_batch_scan_set_all(llb_batch *c, const llb_point *const *corner, const int *nc, const llb_point *const *surf,
+                           const int *ns, const llb_point *const *outlier, const int *no)
+{
+    if (!c || !corner || !nc || !surf || !ns || !outlier || !no) return LLB_ERR_INVALID;
+    for (int s = 0; s < c->B; s++) {
+        const int rc = llb_batch_scan_set(c, s, corner[s], nc[s], surf[s], ns[s], outlier[s], no[s]);
+        if (rc != LLB_OK) return rc;
+    }
+    return LLB_OK;
+}
+
+int llb_batch_map_set_ds_all(llb_batch *c, const llb_point *const *corner_ds, const int *mc, const llb_point *const *surf_ds,
+                             const int *ms)
+{
+    if (!c || !corner_ds || !mc || !surf_ds || !ms) return LLB_ERR_INVALID;
+    for (int s = 0; s < c->B; s++) {
+        const int rc = llb_batch_map_set_ds(c, s, corner_ds[s], mc[s], surf_ds[s], ms[s]);
+        if (rc != LLB_OK) return rc;
+    }
+    return LLB_OK;
+}
+
+int llb_batch_scan_set_dev_all(llb_batch *c, const void *const *corner, const int *nc, const void *const *surf,
+                               const int *ns, const void *const *outlier, const int *no)
+{
+    if (!c || !corner || !nc || !surf || !ns || !outlier || !no) return LLB_ERR_INVALID;
+    for (int s = 0; s < c->B; s++) {
+        const int rc = llb_batch_scan_set_dev(c, s, corner[s], nc[s], surf[s], ns[s], outlier[s], no[s]);
+        if (rc != LLB_OK) return rc;
+    }
+    return LLB_OK;
+}
+
+int llb_batch_map_set_ds_dev_all(llb_batch *c, const void *const *corner_ds, const int *mc, const void *const *surf_ds,
+                                 const int *ms)
+{
+    if (!c || !corner_ds || !mc || !surf_ds || !ms) return LLB_ERR_INVALID;
+    for (int s = 0; s < c->B; s++) {
+        const int rc = llb_batch_map_set_ds_dev(c, s, corner_ds[s], mc[s], surf_ds[s], ms[s]);
+        if (rc != LLB_OK) return rc;
+    }
+    return LLB_OK;
 }
 
 int llb_batch_register_async(llb_batch *c, const float *T)

@@ -12,6 +12,7 @@
 // Exactness: PCL's key expression, stable order (the low key word is the input index), strictly
 // sequential float sums per voxel, true division by (float)count, int32-overflow pass-through.
 #include "voxel_dev.cuh"
+#include "cta_radix.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -201,7 +202,6 @@ __device__ __forceinline__ void voxel_small_body(const SegIn in, const float lea
 constexpr int VC_THREADS = 512;
 constexpr int VC_NW = VC_THREADS / 32;
 constexpr int VC_ITEMS = 4;
-constexpr int VC_SUB = VC_THREADS * VC_ITEMS;
 
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_cta_kernel(const SmallJob *__restrict__ jobs, int cap)
@@ -269,63 +269,8 @@ voxel_cta_kernel(const SmallJob *__restrict__ jobs, int cap)
             vin[i] = (unsigned short)i;
         }
     }
-    // ---- stable LSD radix sort, 8 bits per pass
-    const int nbits = s_nbits;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int shift = 0; shift < nbits; shift += 8) {
-        if (tid < 256) s_base[tid] = 0;
-        __syncthreads();                                     // also orders the previous pass's scatter / the key pass
-        for (int i = tid; i < n; i += VC_THREADS) atomicAdd(&s_base[(kin[i] >> shift) & 255u], 1);
-        __syncthreads();
-        {
-            const int v = tid < 256 ? s_base[tid] : 0;
-            int total;
-            const int ex = block_excl_scan(v, s_scan, total);
-            if (tid < 256) s_base[tid] = ex;
-        }
-        for (int sub = 0; sub < n; sub += VC_SUB) {
-            for (int k = tid; k < VC_NW * 256; k += VC_THREADS) (&s_wcnt[0][0])[k] = 0;
-            __syncthreads();
-            unsigned key[VC_ITEMS]; unsigned short val[VC_ITEMS]; int rk[VC_ITEMS]; unsigned dg[VC_ITEMS];
-#pragma unroll
-            for (int r = 0; r < VC_ITEMS; r++) {
-                const int i = sub + w * (32 * VC_ITEMS) + r * 32 + lane;
-                const bool valid = i < n;
-                key[r] = valid ? kin[i] : 0u;
-                val[r] = valid ? vin[i] : (unsigned short)0;
-                dg[r] = valid ? ((key[r] >> shift) & 255u) : (256u + lane);    // invalid lanes never match
-            }
-#pragma unroll
-            for (int r = 0; r < VC_ITEMS; r++) {
-                const unsigned m = __match_any_sync(FULL, dg[r]);
-                const int pr = __popc(m & lt);
-                int cnt = 0;
-                if (dg[r] < 256u) cnt = s_wcnt[w][dg[r]];
-                rk[r] = cnt + pr;
-                __syncwarp();
-                if (dg[r] < 256u && pr == 0) s_wcnt[w][dg[r]] = cnt + __popc(m);
-                __syncwarp();
-            }
-            __syncthreads();
-            if (tid < 256) {                                 // digit tid: per-warp counts -> scatter offsets
-                int run = s_base[tid];
-#pragma unroll
-                for (int k = 0; k < VC_NW; k++) { const int c = s_wcnt[k][tid]; s_wcnt[k][tid] = run; run += c; }
-                s_base[tid] = run;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < VC_ITEMS; r++)
-                if (dg[r] < 256u) {
-                    const int pos = s_wcnt[w][dg[r]] + rk[r];
-                    kout[pos] = key[r]; vout[pos] = val[r];
-                }
-            __syncthreads();
-        }
-        unsigned *tk = kin; kin = kout; kout = tk;
-        unsigned short *tv = vin; vin = vout; vout = tv;
-    }
-    __syncthreads();
+    // ---- stable LSD radix sort, 8 bits per pass (cta_radix.cuh)
+    cta_radix_sort<VC_THREADS, VC_ITEMS>(kin, kout, vin, vout, n, s_nbits, s_wcnt, s_base, s_scan);
     // ---- heads, scan, ordered per-voxel sums
     const int chunk = (n + VC_THREADS - 1) / VC_THREADS;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
