@@ -196,6 +196,15 @@ int llb_s2m_optimize_dev(llb_ctx *ctx, float *T_dev);
  * count) at a device address the caller all-reduces (NCCL) before llb_s2m_solve */
 int llb_s2m_accumulate(llb_ctx *ctx, int iter, int rank, int world, double **acc28_dev);
 int llb_s2m_solve(llb_ctx *ctx, int iter, int *converged);
+/* the same exchange FUSED into the persistent kernel (no NCCL call, no host round trip per iteration): every rank's
+ * CTA 0 stores its 28 sums into every peer's mailbox over NVLink (P2P stores into cudaIpc-mapped memory), waits for
+ * the peers' flags, adds the contributions in rank order - bit-identical normal equations on all ranks - and takes the
+ * identical 6x6 LM step.  Set-up: each rank exports its mailbox handle, the 64-byte handles are all-gathered by the
+ * caller (torch.distributed / MPI: plumbing) and imported.  llb_s2m_optimize_sharded must then be called by every rank
+ * with the same map, scan and pose; a peer that never arrives is reported as LLB_ERR_STATE after ~2 s, not a hang. */
+int llb_p2p_export(llb_ctx *ctx, unsigned char handle[64]);
+int llb_p2p_import(llb_ctx *ctx, int rank, int world, const unsigned char *handles /* world x 64 bytes */);
+int llb_s2m_optimize_sharded(llb_ctx *ctx, float T[6], llb_stats *stats);
 int llb_s2m_pose_set(llb_ctx *ctx, const float T[6]);
 int llb_s2m_pose_get(llb_ctx *ctx, float T[6]);
 

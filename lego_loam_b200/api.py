@@ -66,6 +66,7 @@ EXPORTS = [
     "llb_s2m_accumulate", "llb_s2m_solve", "llb_s2m_pose_set", "llb_s2m_pose_get", "llb_launch_count",
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
+    "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
     "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
     "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
@@ -398,6 +399,23 @@ class Context:
         t = np.zeros(6, np.float32)
         self._ck(lib().llb_s2m_pose_get(self._h, _fp(t)))
         return t
+
+    def p2p_export(self) -> bytes:
+        h = (ctypes.c_ubyte * 64)()
+        self._ck(lib().llb_p2p_export(self._h, h))
+        return bytes(h)
+
+    def p2p_import(self, rank: int, world: int, handles):
+        buf = b"".join(handles)
+        assert len(buf) == 64 * world
+        arr = (ctypes.c_ubyte * len(buf)).from_buffer_copy(buf)
+        self._ck(lib().llb_p2p_import(self._h, rank, world, arr))
+
+    def s2m_optimize_sharded(self, T):
+        t = np.ascontiguousarray(T, np.float32).copy()
+        st = Stats()
+        self._ck(lib().llb_s2m_optimize_sharded(self._h, _fp(t), ctypes.byref(st)))
+        return t, st
 
     def s2m_accumulate(self, it: int, rank: int, world: int) -> int:
         p = ctypes.c_void_p()

@@ -92,6 +92,12 @@ struct llb_ctx {
     cudaEvent_t asm_ev = nullptr;
     bool asm_busy = false;
     int asm_rc = 0, asm_rs = 0;
+
+    // fused multi-GPU exchange (sharded registration): this rank's mailbox + the peers' mailboxes mapped through cudaIpc
+    unsigned char *p2p_mem = nullptr;
+    S2mPeers peers{};
+    void *p2p_opened[S2M_MAX_PEERS] = {};
+    bool p2p_ready = false;
 };
 
 namespace {
@@ -343,6 +349,8 @@ int llb_destroy(llb_ctx *c)
     c->mapCornerRaw.pts.release(); c->mapSurfRaw.pts.release(); c->mapCornerDS.release(); c->mapSurfDS.release();
     c->gridCorner.release(); c->gridSurf.release(); c->s2m.release(); c->odom.release();
     c->dbg_coeff.release(); c->dbg_valid.release(); c->dbg_knn.release(); c->dbg_d2.release(); c->tmp_vox.release();
+    for (int r = 0; r < S2M_MAX_PEERS; r++) if (c->p2p_opened[r]) cudaIpcCloseMemHandle(c->p2p_opened[r]);
+    if (c->p2p_mem) cudaFree(c->p2p_mem);
     c->kfs.release(); c->asmCorner.release(); c->asmSurf.release(); c->asm_segs.release(); c->pin_segs.release();
     if (c->asm_ev) cudaEventDestroy(c->asm_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -780,6 +788,82 @@ int llb_set_degeneracy(llb_ctx *c, int deg, const float matP[36])
         LLB_CUDA(cudaMemcpy(d->matP, matP, sizeof(float) * 36, cudaMemcpyHostToDevice));
         const int one = 1;
         LLB_CUDA(cudaMemcpy(&d->matP_valid, &one, sizeof(int), cudaMemcpyHostToDevice));
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ fused multi-GPU exchange (BASELINE config 4)
+
+namespace {
+constexpr size_t P2P_DATA_BYTES = sizeof(double) * 2 * S2M_MAX_PEERS * 32;
+constexpr size_t P2P_BYTES = P2P_DATA_BYTES + sizeof(unsigned long long) * 2 * S2M_MAX_PEERS;
+}
+
+int llb_p2p_export(llb_ctx *c, unsigned char handle[64])
+{
+    return guarded(c, [&]() {
+        if (!handle) return (int)LLB_ERR_INVALID;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        if (!c->p2p_mem) {
+            LLB_CUDA(cudaMalloc(&c->p2p_mem, P2P_BYTES));
+            LLB_CUDA(cudaMemset(c->p2p_mem, 0, P2P_BYTES));
+            LLB_CUDA(cudaDeviceSynchronize());
+        }
+        cudaIpcMemHandle_t h;
+        LLB_CUDA(cudaIpcGetMemHandle(&h, c->p2p_mem));
+        std::memcpy(handle, &h, 64);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_p2p_import(llb_ctx *c, int rank, int world, const unsigned char *handles)
+{
+    return guarded(c, [&]() {
+        if (!handles || world < 1 || world > S2M_MAX_PEERS || rank < 0 || rank >= world) return (int)LLB_ERR_INVALID;
+        if (!c->p2p_mem) return (int)LLB_ERR_STATE;
+        for (int r = 0; r < world; r++) {
+            unsigned char *base = c->p2p_mem;
+            if (r != rank) {
+                if (c->p2p_opened[r]) { cudaIpcCloseMemHandle(c->p2p_opened[r]); c->p2p_opened[r] = nullptr; }
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, handles + 64 * r, 64);
+                void *p = nullptr;
+                LLB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                c->p2p_opened[r] = p;
+                base = (unsigned char *)p;
+            }
+            c->peers.box[r] = (double *)base;
+            c->peers.flag[r] = (unsigned long long *)(base + P2P_DATA_BYTES);
+        }
+        c->peers.rank = rank; c->peers.world = world;
+        c->p2p_ready = true;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_s2m_optimize_sharded(llb_ctx *c, float T[6], llb_stats *stats)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->map_set || !c->scan_ds_done || !c->p2p_ready) return (int)LLB_ERR_STATE;
+        S2mQueries q = s2m_queries(c);
+        S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg,
+                                  c->peers.rank, c->peers.world, true, c->stream, &c->peers);
+        c->peers.seq_base += (unsigned long long)c->prm.s2m_max_iterations + 1ull;   // the same on every rank
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
+        read_count(c, 0);
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const S2mState &s = *c->pin_state.p;
+        if (s.peer_timeout) { c->err = "a peer rank did not deliver its normal equations (llb_s2m_optimize_sharded must be "
+                                       "called by every rank with the same inputs)"; return (int)LLB_ERR_STATE; }
+        if (!s.skipped) for (int i = 0; i < 6; i++) T[i] = s.T[i];
+        fill_stats(c, stats, s, ms);
+        c->dbg_ready = false;
         return (int)LLB_OK;
     });
 }

@@ -72,12 +72,15 @@ __device__ __forceinline__ void knn_ranges(const MapIndexView &m, float qx, floa
         const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
         rb[r] = 0; re[r] = 0;
         if (y >= 0 && y < dimy && z >= 0 && z < dimz && x0 <= x1) {
+            // cell_begin only holds valid offsets inside occupied rows; the four loads are issued together (no
+            // dependent round trip) and the cell offsets are simply discarded when the row directory says "empty"
             const int ry = z * dimy + y;
-            if (__ldg(&m.row_begin[ry + 1]) > __ldg(&m.row_begin[ry])) {   // cell_begin only exists in occupied rows
-                const int row = ry * dimx;
-                rb[r] = __ldg(&m.cell_begin[row + x0]);
-                re[r] = __ldg(&m.cell_begin[row + x1 + 1]);
-            }
+            const int row = ry * dimx;
+            const int r0 = __ldg(&m.row_begin[ry]), r1 = __ldg(&m.row_begin[ry + 1]);
+            const int b = __ldg(&m.cell_begin[row + x0]), e = __ldg(&m.cell_begin[row + x1 + 1]);
+            const bool occ = r1 > r0;
+            rb[r] = occ ? b : 0;
+            re[r] = occ ? e : 0;
         }
     }
 }

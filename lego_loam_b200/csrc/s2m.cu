@@ -64,13 +64,14 @@ __global__ void s2m_state_init_kernel(S2mState *st)
     for (int i = 0; i < 36; i++) { st->matP[i] = 0.f; st->AtA[i] = 0.f; st->AtA0[i] = 0.f; }
     st->matP_valid = 1;                                      // the reference starts with matP = 0 (MO:361)
     st->converged = 0; st->iters = 0; st->n_corr = 0; st->is_degenerate = 0; st->skipped = 0; st->ticket = 0;
+    st->queue = 0; st->peer_timeout = 0;
 }
 
 
 __global__ void __launch_bounds__(S2M_THREADS, S2M_CTAS_PER_SM)
 s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexView cmap, MapIndexView smap,
                 S2mState *st, double *partials, double *acc_out, S2mDebug dbg, int rank, int world, int do_solve,
-                int prof_off)
+                int prof_off, S2mPeers peers)
 {
     cg::grid_group grid = cg::this_grid();
 
@@ -239,6 +240,39 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 if (!do_solve) acc_out[tid] = tsum;
             }
             __syncthreads();
+            if (peers.world > 1) {
+                // ---- fused exchange of the 28 sums over NVLink (BASELINE config 4): one-shot all-to-all of P2P
+                // stores into every peer's mailbox + flag, then every rank adds the contributions in RANK ORDER, so
+                // all ranks hold bit-identical normal equations and take the identical LM step - no NCCL call, no host.
+                // Mailboxes are double-buffered by iteration parity: a rank can be at most one iteration ahead of a
+                // peer (it needs the peer's sums of iteration i to leave iteration i).
+                const int par = iter & 1;
+                const unsigned long long seq = peers.seq_base + (unsigned long long)iter + 1ull;
+                if (tid < S2M_ACC)
+                    for (int r = 0; r < peers.world; r++)
+                        reinterpret_cast<volatile double *>(peers.box[r])[(par * S2M_MAX_PEERS + peers.rank) * 32 + tid] = s_tot[tid];
+                __threadfence_system();
+                __syncthreads();
+                if (tid < peers.world) {
+                    volatile unsigned long long *f = peers.flag[tid] + par * S2M_MAX_PEERS + peers.rank;
+                    *f = seq;                                // after the fence: the data is visible before the flag
+                    __threadfence_system();
+                    volatile unsigned long long *mine = peers.flag[peers.rank] + par * S2M_MAX_PEERS + tid;
+                    const long long t_wait = clock64();
+                    while (*mine < seq) {                    // a peer that never arrives must not hang the GPU: ~2 s
+                        if (clock64() - t_wait > 4000000000ll) { st->peer_timeout = 1; break; }
+                    }
+                    __threadfence_system();
+                }
+                __syncthreads();
+                if (tid < S2M_ACC) {
+                    const volatile double *box = reinterpret_cast<const volatile double *>(peers.box[peers.rank]);
+                    double tsum = 0.0;
+                    for (int r = 0; r < peers.world; r++) tsum += box[(par * S2M_MAX_PEERS + r) * 32 + tid];
+                    s_tot[tid] = tsum;
+                }
+                __syncthreads();
+            }
             if (prof) st->prof[iter % 10][5] = clock64();
             if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm, false);
             __syncthreads();
@@ -305,8 +339,10 @@ int S2mSolver::prepare(const float *T_host, const float *T_dev, const GridDesc *
 }
 
 int S2mSolver::run(int it_begin, int it_end, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
-                   const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s)
+                   const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s, const S2mPeers *peers_in)
 {
+    S2mPeers peers{};
+    if (peers_in) peers = *peers_in;
     const int nq = std::max(1, div_up(q.nc_upper + q.ns_upper, world));
     int grid = std::max(1, std::min(max_blocks_, div_up(nq, S2M_QPB)));
     if (prm_.max_ctas > 0) grid = std::min(grid, prm_.max_ctas);
@@ -315,8 +351,9 @@ int S2mSolver::run(int it_begin, int it_end, const S2mQueries &q, const MapIndex
     S2mState *st = state_.p; double *part = partials_.p, *acc = acc_.p;
     int ds = do_solve ? 1 : 0;
     int prof_off = max_blocks_ * S2M_ACC;
+    last_prof_off_ = prof_off;
     last_grid_ = grid;
-    void *args[] = { &prm, &it_begin, &it_end, &qq, &cm, &sm, &st, &part, &acc, &dg, &rank, &world, &ds, &prof_off };
+    void *args[] = { &prm, &it_begin, &it_end, &qq, &cm, &sm, &st, &part, &acc, &dg, &rank, &world, &ds, &prof_off, &peers };
     LLB_CUDA(cudaLaunchCooperativeKernel((const void *)s2m_loop_kernel, dim3(grid), dim3(S2M_THREADS), args, 0, s));
     return 1;
 }

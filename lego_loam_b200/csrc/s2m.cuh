@@ -31,6 +31,8 @@ struct S2mState {                    // device-resident, persists across registr
     int   matP_valid;
     float AtA[36], AtB[6], X[6];     // last LM step (diagnostics)
     unsigned ticket;                 // last-block election
+    int peer_timeout;                // fused multi-GPU exchange: a peer's sums did not arrive within ~2 s
+    unsigned queue;                  // chunk queue of the persistent kernel (zero between iterations)
     long long prof[10][8];           // clock64 stamps of CTA 0 per iteration: start, A, B, C, sync1, reduce, solve, sync2
 };
 
@@ -39,6 +41,16 @@ struct S2mDebug {                    // optional per-query outputs (nullptr = of
     int *valid;                      // [nq] 1 when the row was accepted (s > 0.1)
     int *knn_idx;                    // [nq*5] original map indices, -1 if fewer than 5 in range
     float *knn_d2;                   // [nq*5]
+};
+
+constexpr int S2M_MAX_PEERS = 8;     // one NVSwitch domain
+// peer mailboxes of the fused multi-GPU exchange (sharded registration, BASELINE config 4): box[r] / flag[r] are rank
+// r's mailbox mapped into THIS process (cudaIpc); layout double[2][S2M_MAX_PEERS][32] / unsigned long long[2][S2M_MAX_PEERS]
+struct S2mPeers {
+    double *box[S2M_MAX_PEERS];
+    unsigned long long *flag[S2M_MAX_PEERS];
+    int world, rank;
+    unsigned long long seq_base;     // flags carry seq_base + iteration + 1: monotonic over the context's lifetime
 };
 
 struct S2mQueries {
@@ -59,7 +71,7 @@ public:
     // rank/world shard the queries (world = 1: everything); do_solve = false runs exactly one
     // iteration and stops after the 28 sums are in acc_dev() (for an external all-reduce)
     int run(int it_begin, int it_end, const S2mQueries &q, const MapIndexView &cmap, const MapIndexView &smap,
-            const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s);
+            const S2mDebug &dbg, int rank, int world, bool do_solve, cudaStream_t s, const S2mPeers *peers = nullptr);
     int solve(int iter, cudaStream_t s);
     // makes S2mState::matP valid (it is computed lazily when the registration was not degenerate)
     int ensure_matp(cudaStream_t s);
@@ -71,9 +83,10 @@ private:
     DevBuf<double> acc_;
     int max_blocks_ = 0;
     int last_grid_ = 0;
+    int last_prof_off_ = 0;
 public:
     // per-CTA phase cycles {A, B, C, wait at the grid barrier} of the last iteration of the last run
-    const double *cta_profile_dev() const { return partials_.p + (size_t)max_blocks_ * S2M_ACC; }
+    const double *cta_profile_dev() const { return partials_.p + (size_t)last_prof_off_; }
     int last_grid() const { return last_grid_; }
 };
 

@@ -79,3 +79,23 @@ def sharded_scan2map(ctx, T_init, rank: int, world: int, group=None, max_iterati
             if ctx.s2m_solve(it, want_converged=True):
                 break
     return ctx.s2m_pose_get(), iters
+
+
+def setup_fused_exchange(ctx, rank: int, world: int, group=None):
+    """One-off set-up of the fused NVLink exchange: all-gather the cudaIpc handles of the ranks' mailboxes
+    (torch.distributed is the plumbing) and map the peers' mailboxes into this context."""
+    import torch.distributed as dist
+    mine = ctx.p2p_export()
+    handles = [None] * world
+    if world > 1:
+        dist.all_gather_object(handles, mine, group=group)
+    else:
+        handles = [mine]
+    ctx.p2p_import(rank, world, handles)
+
+
+def sharded_scan2map_fused(ctx, T_init):
+    """scan2MapOptimization with the queries sharded over the ranks and the 28-value exchange fused into the persistent
+    kernel (P2P stores over NVLink, no NCCL call inside the loop).  Needs setup_fused_exchange() once.
+    Returns (pose, Stats)."""
+    return ctx.s2m_optimize_sharded(T_init)

@@ -41,7 +41,16 @@ def main():
         T_shard, iters = multi_gpu.sharded_scan2map(ctx, init, rank, world)
         torch.cuda.synchronize()
         res.append((time.perf_counter() - t0) * 1e3)
-    ok = bool(np.allclose(T_shard, T_single, atol=1e-6)) and iters == st.iterations
+    # the same with the exchange fused into the persistent kernel (P2P stores over NVLink, no NCCL in the loop)
+    multi_gpu.setup_fused_exchange(ctx, rank, world)
+    fused_wall, fused_dev = [], []
+    for rep in range(8):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        T_fused, st_f = multi_gpu.sharded_scan2map_fused(ctx, init)
+        fused_wall.append((time.perf_counter() - t0) * 1e3); fused_dev.append(st_f.device_ms)
+    ok_fused = bool(np.array_equal(T_fused, T_shard)) and st_f.iterations == st.iterations
+    ok = bool(np.allclose(T_shard, T_single, atol=1e-6)) and iters == st.iterations and ok_fused
     gathered = [None] * world
     dist.all_gather_object(gathered, T_shard.tolist())
     same = all(g == gathered[0] for g in gathered)          # the redundant LM steps stayed bit-identical
@@ -49,7 +58,9 @@ def main():
         print(json.dumps({"world": world, "queries": counts[0] + counts[3], "map_ds": [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])],
                           "iterations_single": st.iterations, "iterations_sharded": iters, "pose_match": ok,
                           "bit_identical_across_ranks": same, "max_abs_diff": float(np.max(np.abs(T_shard - T_single))),
-                          "single_gpu_device_ms": st.device_ms, "sharded_wall_ms_median": float(np.median(res))}))
+                          "single_gpu_device_ms": st.device_ms, "sharded_nccl_wall_ms_median": float(np.median(res)),
+                          "fused_matches_nccl_bitwise": ok_fused, "fused_wall_ms_median": float(np.median(fused_wall[2:])),
+                          "fused_device_ms_median": float(np.median(fused_dev[2:]))}))
     dist.destroy_process_group()
     ctx.close()
     return 0 if (ok and same) else 1
