@@ -169,6 +169,127 @@ def run_reference(args):
     return 0
 
 
+def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_sample):
+    """Secondary arm (SURVEY 8(f)-1 + row a2): the mapping cycle with the DEVICE-RESIDENT key-frame store.  Per
+    registration only the new sweep crosses PCIe; the raw local map is assembled from the resident key-frames
+    (transformPointCloud + concatenation, MO:1033-1056), voxel-filtered (MO:1057-1064) and indexed on the device, then
+    downsampleCurrentScan + scan2MapOptimization as in the main arm.  The CPU figure runs the reference's own
+    statements for the same work (its two map voxel filters + downsampleCurrentScan + scan2MapOptimization) on 1 core."""
+    from lego_loam_b200 import synth
+    D = 2
+    seq = []
+    for d in range(D):
+        w = synth.make_world(synth.SEED0 + 500 + d)
+        yaw0 = 0.4 + 0.9 * d
+        poses, scans = [], []
+        for k in range(n_keyframes + 2):
+            # key-frames every ~1 m along a gently turning path (the reference thins key poses to 1 m, MO:1011-1012)
+            j = min(k, n_keyframes - 1) if k < n_keyframes else n_keyframes // 2 + (k - n_keyframes)
+            yaw = yaw0 + 0.01 * j
+            pose = np.array([0.004 * np.sin(0.3 * j), yaw, 0.004 * np.cos(0.2 * j),
+                             -20.0 + 1.0 * j * np.sin(yaw0 + 0.005 * j), 0.0, -25.0 + 1.0 * j * np.cos(yaw0 + 0.005 * j)])
+            if k >= n_keyframes:
+                pose[3] += 0.35; pose[5] += 0.2                    # the new sweeps are not on a key-frame
+            poses.append(pose.astype(np.float32))
+            scans.append(synth.make_mapping_scan(w, synth.VLP16, pose, seed=9000 + 100 * d + k))
+        seq.append((poses, scans))
+    prm = api.default_params(); prm.pin_host_clouds = 1; prm.s2m_max_ctas = 37
+    ctxs = []
+    for s in range(n_ctx):
+        poses, scans = seq[s % D]
+        c = api.Context(local, prm)
+        hold = []                                                 # pinned in place (pin_host_clouds): must outlive the context
+        for k in range(n_keyframes):                              # saveKeyFramesAndFactor's cloud part, MO:1443-1453
+            sc = scans[k]
+            h = (api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last)); hold.append(h)
+            c.scan_set_pcl(*h); c.downsample_current_scan(); c.keyframe_add()
+        new = [(api.to_pcl(scans[n_keyframes + i].corner_last), api.to_pcl(scans[n_keyframes + i].surf_last),
+                api.to_pcl(scans[n_keyframes + i].outlier_last),
+                synth.perturb_pose(poses[n_keyframes + i].astype(np.float64), np.random.default_rng(s * 10 + i)).astype(np.float32))
+               for i in range(2)]
+        ctxs.append({"ctx": c, "hold": hold, "new": new, "ids": np.arange(n_keyframes, dtype=np.int32),
+                     "kposes": np.stack(poses[:n_keyframes]).astype(np.float32), "seq": s % D})
+    T = max(1, min(threads, n_ctx))
+    barrier = threading.Barrier(T + 1)
+    out = {}
+
+    def cycle(q, i):
+        c = q["ctx"]
+        cc, ss, oo, init = q["new"][i % 2]
+        c.scan_set_pcl(cc, ss, oo)                                # H2D: the new sweep only
+        c.downsample_current_scan(want_counts=False)
+        c.map_assemble(q["ids"], q["kposes"])                     # resident key-frames -> raw map -> DS map -> index
+        c.s2m_optimize_async(init)
+
+    def worker(tix):
+        mine = ctxs[tix::T]
+        for i in range(warm):
+            for q in mine:
+                cycle(q, i)
+            for q in mine:
+                q["ctx"].s2m_result()
+        barrier.wait()
+        for i in range(steps):
+            for q in mine:
+                cycle(q, i)
+            for q in mine:
+                res = q["ctx"].s2m_result()
+            if tix == 0:
+                out["T"], out["st"] = res
+        barrier.wait()
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(T)]
+    for x in ths:
+        x.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    barrier.wait()
+    wall = time.perf_counter() - t0
+    for x in ths:
+        x.join()
+    # the reference's own statements for the same cycle on 1 core (bounded sample) + pose check
+    q = ctxs[0::T][-1]
+    raw_c, raw_s = q["ctx"].map_get_raw(0), q["ctx"].map_get_raw(1)
+    ds_sizes = (int(q["ctx"].map_get_ds(0).shape[0]), int(q["ctx"].map_get_ds(1).shape[0]))
+    kind, mo = "port", None
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            kind = "reference"; mo = ref_harness.MapOptimization()
+    except Exception:
+        pass
+    if mo is None:
+        import oracle
+        oracle.set_trig_mode(0); mo = oracle.MapOptimization()
+    poses, scans = seq[q["seq"]]
+
+    def cpu_cycle(i):
+        sc = scans[n_keyframes + i % 2]
+        mo.set_map_raw(raw_c, raw_s)                              # MO:1057-1064: the two map voxel filters
+        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
+        mo.transformTobeMapped = q["new"][i % 2][3]
+        mo.downsampleCurrentScan()
+        mo.scan2MapOptimization()
+        return mo.transformTobeMapped
+    cpu_cycle(0)
+    t0 = time.perf_counter()
+    for i in range(cpu_sample):
+        Tc = cpu_cycle(i)
+    cpu_s = time.perf_counter() - t0
+    diff = float(np.max(np.abs(out["T"] - cpu_cycle(steps - 1)))) if "T" in out else None
+    h2d = int(sum(a.nbytes for a in ctxs[0]["new"][0][:3]) + ctxs[0]["kposes"].nbytes + ctxs[0]["ids"].nbytes + 24)
+    for qq in ctxs:
+        qq["ctx"].close()
+    return {"value": n_ctx * steps / wall, "unit": "registrations/s", "contexts": n_ctx, "host_threads": T,
+            "key_frames": n_keyframes, "raw_map_points": [int(raw_c.shape[0]), int(raw_s.shape[0])], "ds_map_points": list(ds_sizes),
+            "h2d_bytes_per_registration": h2d, "ms_per_registration_wall": wall / (n_ctx * steps) * 1e3,
+            "cpu_1core": {"value": cpu_sample / cpu_s, "ms_per_registration": cpu_s / cpu_sample * 1e3, "kind": kind,
+                          "sample": f"{cpu_sample} cycles"},
+            "pose_check_max_abs_diff_vs_cpu": diff,
+            "note": "registration = local-map assembly from device-resident key-frames + map voxel filters + index + "
+                    "downsampleCurrentScan + scan2MapOptimization; host clouds in (new sweep only), pose out, wall clock"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +302,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic sequences generated (slots beyond copy them)")
     ap.add_argument("--scans", type=int, default=2, help="distinct sweeps per sequence rotated through the steps")
     ap.add_argument("--cpu-sample", type=int, default=12, help="registrations timed for cpu_baseline")
+    ap.add_argument("--mapping-cycle", type=int, default=1, help="1: also run the key-frame-store mapping-cycle arm (rank 0)")
+    ap.add_argument("--key-frames", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -374,6 +497,14 @@ def main():
     if world > 1:
         dist.barrier()
     stop_evt.set(); th.join()
+    mc_arm = None
+    if args.mapping_cycle and rank == 0:
+        try:
+            mc_arm = mapping_cycle_arm(api, local, 16, args.key_frames, max(4, K // 4), 2, 8, 4)
+        except Exception as e:                                # secondary arm: never hides the main line
+            mc_arm = {"error": repr(e)}
+    if world > 1:
+        dist.barrier()
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -459,6 +590,7 @@ def main():
             "wall_s_timed_region": t_wall,
             "last_stats": last["st"][0].as_dict() if "st" in last else None,
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
+            "mapping_cycle": mc_arm,
         }
         print(json.dumps(line))
     if world > 1:
