@@ -323,7 +323,7 @@ batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
 __global__ void __launch_bounds__(BATCH_FIT_THREADS)
 batch_fit_kernel(const BatchReg *__restrict__ regs, int iter, S2mParams prm)
 {
-    __shared__ float s_row[8][BATCH_FIT_THREADS];
+    __shared__ float s_row[8][BATCH_FIT_THREADS + 1];        // +1: lane k reads row ia(k), same column -> distinct banks
     __shared__ double s_acc[FIT_NW][32];
     const BatchReg r = regs[blockIdx.y];
     const S2mState *st = r.st;

@@ -77,7 +77,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
 
     __shared__ float s_nn[15][S2M_TILE];                      // 5 neighbours x (x,y,z), SoA
     __shared__ float s_q[7][S2M_TILE];                        // po.xyz, sel.xyz, 5th squared distance (or -1)
-    __shared__ float s_row[8][S2M_TILE];                      // Jacobian row, -residual, valid
+    __shared__ float s_row[8][S2M_TILE + 1];                  // Jacobian row, -residual, valid (+1: bank spread in phase C)
     __shared__ double s_acc[S2M_NW][32];
     __shared__ double s_tot[32];
     __shared__ unsigned long long s_wkey[S2M_NW][KNN_CAP];    // per-warp in-gate candidate lists (phase A)

@@ -90,6 +90,27 @@ public:
         }
     }
 
+    // ---- device-resident key-frame store ----
+    // cloud part of saveKeyFramesAndFactor, MO:1443-1453: the DS clouds of the current sweep (already in HBM after
+    // downsampleCurrentScan) become key-frame number `return value`; nothing is copied to the host
+    int saveKeyFrameClouds()
+    {
+        int id = -1;
+        last_status = llb_keyframe_add(ctx_, &id);
+        return last_status == LLB_OK ? id : -1;
+    }
+    // cloud part of extractSurroundingKeyFrames, MO:1033-1064 (or the recent-frames branch MO:962-1001): ids in the
+    // order of surroundingExistingKeyPosesID, poses6d[6*i ..] = cloudKeyPoses6D[ids[i]] {roll, pitch, yaw, x, y, z}.
+    // transformPointCloud + concatenation + the two map voxel filters + the index build, all on the device.
+    void assembleSurroundingMap(const std::vector<int> &ids, const std::vector<float> &poses6d)
+    {
+        last_status = llb_map_assemble(ctx_, ids.data(), poses6d.data(), (int)ids.size());
+        if (last_status != LLB_OK) return;
+        llb_map_get_ds(ctx_, 0, nullptr, 0, &laserCloudCornerFromMapDSNum);
+        llb_map_get_ds(ctx_, 1, nullptr, 0, &laserCloudSurfFromMapDSNum);
+        map_on_device_ = true;
+    }
+
     void downsampleCurrentScan()                                   // MO:1067
     {
         last_status = llb_scan_set(ctx_, as_llb(*laserCloudCornerLast), (int)laserCloudCornerLast->size(),
