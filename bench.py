@@ -356,7 +356,7 @@ def main():
     groups = [list(range(b, S, NB)) for b in range(NB)]
     batches = []
     for g in groups:
-        b = api.Batch(local, len(g), min(max_scan, 8192), max_map, prm)
+        b = api.Batch(local, len(g), min(max_scan, 16384), max_map, prm)
         P = api.Batch.pack
         tabs = {"T": [np.stack([seqs[s]["scans"][i][1] for s in g]).astype(np.float32) for i in range(args.scans)]}
         for kind, dev_side in (("dev", True), ("host", False)):

@@ -231,8 +231,9 @@ long long llb_launch_count(const llb_ctx *ctx);
  * slots whose map was set since the last step) + scan2MapOptimization (MO:1329-1350) with a number of kernel
  * launches that does not depend on n_slots.  Each slot keeps its own isDegenerate / matP across steps (C6).
  * Results are bit-identical to n_slots separate llb_ctx registrations up to the fp64 summation order of the
- * normal equations.  max_scan_points bounds every one of the three scan clouds of a slot (<= 8192: the four
- * filters of downsampleCurrentScan run on the 8-CTA cluster voxel kernel); max_map_points bounds each DS map. */
+ * normal equations.  max_scan_points bounds every one of the three scan clouds of a slot (<= 16384, and surf + outlier
+ * of one sweep <= 16384: the four filters of downsampleCurrentScan sort in shared memory; VLP-16 / HDL-32E sweeps fit,
+ * VLS-128 sweeps use llb_ctx); max_map_points bounds each DS map. */
 typedef struct llb_batch llb_batch;
 int  llb_batch_create(const llb_params *p /* NULL = defaults */, int device, int n_slots, int max_scan_points,
                       int max_map_points, llb_batch **out);

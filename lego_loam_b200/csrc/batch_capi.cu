@@ -302,8 +302,9 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
     if (!out) return LLB_ERR_INVALID;
     *out = nullptr;
     if (n_slots < 1 || n_slots > 4096 || max_scan_points < 1 || max_map_points < 1) return LLB_ERR_INVALID;
-    // every filter of downsampleCurrentScan must fit the cluster voxel kernel (surf + outlier are concatenated)
-    if (max_scan_points > VoxelFilter::SMALL_MAX / 2) return LLB_ERR_CAPACITY;   // 8192
+    // every filter of downsampleCurrentScan must fit the one-CTA voxel kernel (shared-memory sort of <= 16384 points);
+    // surf + outlier are concatenated for the fourth filter: checked per sweep in llb_batch_scan_set
+    if (max_scan_points > VoxelFilter::SMALL_MAX) return LLB_ERR_CAPACITY;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LLB_ERR_NO_DEVICE;
     cudaDeviceProp prop;
@@ -391,7 +392,8 @@ int llb_batch_scan_set(llb_batch *c, int slot, const llb_point *corner, int nc, 
     return guarded(c, [&]() {
         if (slot < 0 || slot >= c->B || nc < 0 || ns < 0 || no < 0 || (nc > 0 && !corner) || (ns > 0 && !surf) ||
             (no > 0 && !outlier)) return (int)LLB_ERR_INVALID;
-        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan) return (int)LLB_ERR_CAPACITY;
+        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan || ns + no > VoxelFilter::SMALL_MAX)
+            return (int)LLB_ERR_CAPACITY;
         const llb_point *src[3] = { corner, surf, outlier };
         const int n[3] = { nc, ns, no };
         llb_batch::Slot &sl = c->slots[slot];
@@ -410,7 +412,8 @@ int llb_batch_scan_set_dev(llb_batch *c, int slot, const void *corner, int nc, c
 {
     return guarded(c, [&]() {
         if (slot < 0 || slot >= c->B || nc < 0 || ns < 0 || no < 0) return (int)LLB_ERR_INVALID;
-        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan) return (int)LLB_ERR_CAPACITY;
+        if (nc > c->cap_scan || ns > c->cap_scan || no > c->cap_scan || ns + no > VoxelFilter::SMALL_MAX)
+            return (int)LLB_ERR_CAPACITY;
         llb_batch::Slot &sl = c->slots[slot];
         sl.scan[0] = (const float4 *)corner; sl.scan[1] = (const float4 *)surf; sl.scan[2] = (const float4 *)outlier;
         sl.scan_n[0] = nc; sl.scan_n[1] = ns; sl.scan_n[2] = no;

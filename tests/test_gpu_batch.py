@@ -100,7 +100,7 @@ def test_batch_guard_and_errors(cases):
         b.register(np.zeros((2, 6), np.float32))              # nothing set yet
     assert e.value.status == api.LLB_ERR_STATE
     with pytest.raises(api.LlbError) as e:
-        b.scan_set(0, np.zeros((9000, 4), np.float32), c["surf"], c["outlier"])
+        b.scan_set(0, np.zeros((9000, 4), np.float32), c["surf"], c["outlier"])          # beyond max_scan_points
     assert e.value.status == api.LLB_ERR_CAPACITY
     # slot 1 gets a map below the reference's guard (MO:1331: > 10 corner and > 100 surf points): skipped,
     # pose untouched; slot 0 registers normally
@@ -112,4 +112,68 @@ def test_batch_guard_and_errors(cases):
     assert st[0].skipped == 0 and st[0].iterations > 0 and not np.array_equal(T[0], init[0])
     b.close()
     with pytest.raises(api.LlbError):
-        api.Batch(0, 2, 9000, 1000)                            # scan capacity beyond the cluster voxel kernel
+        api.Batch(0, 2, 20000, 1000)                           # scan capacity beyond the shared-memory voxel kernel
+    b2 = api.Batch(0, 1, 16384, 1000)
+    with pytest.raises(api.LlbError) as e:                     # surf + outlier of one sweep must fit the fourth filter
+        b2.scan_set(0, c["corner"], np.zeros((9000, 4), np.float32), np.zeros((9000, 4), np.float32))
+    assert e.value.status == api.LLB_ERR_CAPACITY
+    b2.close()
+
+
+def test_batch_ragged_and_empty_clouds(ctx, cases):
+    """Slots with very different sizes in one step: an empty outlier cloud, an empty corner cloud (registration runs on
+    surf rows only), a tiny sweep (< 50 correspondences: LMOptimization returns early every iteration, MO:1238) - each
+    slot must equal the single-registration path on the same inputs."""
+    c = cases[0]
+    empty = np.zeros((0, 4), np.float32)
+    variants = [
+        (c["corner"], c["surf"], empty),
+        (empty, c["surf"], c["outlier"]),
+        (c["corner"][:12], c["surf"][:40], c["outlier"][:5]),
+        (c["corner"], c["surf"], c["outlier"]),
+    ]
+    b = api.Batch(0, len(variants), 8192, 120000)
+    for s, (co, su, ou) in enumerate(variants):
+        b.scan_set(s, co, su, ou); b.map_set_ds(s, c["mc_ds"], c["ms_ds"])
+    init = np.stack([c["init"]] * len(variants)).astype(np.float32)
+    T, st = b.register(init)
+    for s, (co, su, ou) in enumerate(variants):
+        ctx.map_set_ds(c["mc_ds"], c["ms_ds"]); ctx.scan_set(co, su, ou)
+        counts = ctx.downsample_current_scan()
+        Ts, sts = ctx.s2m_optimize(c["init"])
+        assert np.array_equal(T[s].view(np.uint32), Ts.view(np.uint32)), (s, T[s], Ts)
+        assert (st[s].iterations, st[s].converged, st[s].n_correspondences) == (sts.iterations, sts.converged, sts.n_correspondences)
+        assert (st[s].n_corner_ds, st[s].n_surf_ds) == (counts[0], counts[3])
+    assert st[2].iterations == 10 and st[2].converged == 0 and np.array_equal(T[2], init[2])   # too few rows: pose untouched
+    b.close()
+
+
+def test_keyframe_store_edge_cases(ctx, cases):
+    c = cases[0]
+    ctx.keyframe_clear()
+    with pytest.raises(api.LlbError):                          # unknown key-frame id
+        ctx.map_assemble([0], np.zeros((1, 6), np.float32))
+    k0 = ctx.keyframe_add_clouds(c["corner"], c["surf"], c["outlier"])
+    k1 = ctx.keyframe_add_clouds(np.zeros((0, 4), np.float32), c["surf"][:10], np.zeros((0, 4), np.float32))
+    assert (k0, k1) == (0, 1) and ctx.keyframe_count() == 2
+    pose = np.array([[0.01, 0.5, -0.02, 1.0, 0.2, -3.0], [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]], np.float32)
+    ctx.map_assemble([1, 0, 1], pose[[1, 0, 1]])               # repeated ids, an empty corner cloud in the middle
+    raw_c, raw_s = ctx.map_get_raw(0), ctx.map_get_raw(1)
+    assert raw_c.shape[0] == c["corner"].shape[0] and raw_s.shape[0] == 20 + c["surf"].shape[0] + c["outlier"].shape[0]
+    # identity pose: the first surf segment is the stored cloud itself; transformed segment: reference formula in float32
+    assert np.array_equal(raw_s[:10].view(np.uint32), np.ascontiguousarray(c["surf"][:10], np.float32).view(np.uint32))
+    f = np.float32
+    r, p, y = pose[0, :3]
+    cr, sr, cp, sp, cy, sy = (f(np.cos(r, dtype=f)), f(np.sin(r, dtype=f)), f(np.cos(p, dtype=f)), f(np.sin(p, dtype=f)),
+                              f(np.cos(y, dtype=f)), f(np.sin(y, dtype=f)))
+    q = np.ascontiguousarray(c["corner"], f)
+    x1 = cy * q[:, 0] - sy * q[:, 1]; y1 = sy * q[:, 0] + cy * q[:, 1]; z1 = q[:, 2]
+    y2 = cr * y1 - sr * z1; z2 = sr * y1 + cr * z1
+    exp = np.stack([cp * x1 + sp * z2 + pose[0, 3], y2 + pose[0, 4], -sp * x1 + cp * z2 + pose[0, 5], q[:, 3]], 1).astype(f)
+    assert np.allclose(raw_c, exp, atol=2e-6, rtol=0)          # numpy's cosf/sinf may differ from libm by an ulp
+    ctx.map_assemble([], np.zeros((0, 6), np.float32))         # empty selection: empty maps, guard MO:1331 skips
+    assert ctx.map_get_raw(0).shape[0] == 0 and ctx.map_get_ds(1).shape[0] == 0
+    ctx.scan_set(c["corner"], c["surf"], c["outlier"]); ctx.downsample_current_scan()
+    T, st = ctx.s2m_optimize(c["init"])
+    assert st.skipped == 1 and np.array_equal(T, np.asarray(c["init"], np.float32))
+    ctx.keyframe_clear()
