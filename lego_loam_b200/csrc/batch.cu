@@ -271,13 +271,17 @@ batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
         // distance from the query to the neighbouring rows' slabs, in metres (0 for the query's own row)
         const float ly = (fy - (float)cy) * cell, lz = (fz - (float)cz) * cell;
+        // the list starts as five sentinels (gate distance, index -1): "d < bd[4]" is then the gate test AND the top-5
+        // test in one compare, and five real neighbours were found iff the last sentinel has been pushed out
         float bd[5]; int bi[5], bp[5];
 #pragma unroll
-        for (int k = 0; k < 5; k++) { bd[k] = __int_as_float(0x7f800000); bi[k] = 0x7fffffff; bp[k] = -1; }
-        int found = 0;
-                if (x0 <= x1) {
+        for (int k = 0; k < 5; k++) { bd[k] = max_sq; bi[k] = -1; bp[k] = -1; }
+        if (x0 <= x1) {
 #pragma unroll 1
-            for (int rr = 0; rr < 9; rr++) {
+            for (int ro = 0; ro < 9; ro++) {
+                // own row first, then the four face neighbours, then the corners: the 5th-best distance tightens early
+                // and most later candidates fail the single compare (fewer trips through the insertion path)
+                const int rr = (int)((0x862075314ull >> (4 * ro)) & 15ull);
                 const int dy = (rr % 3) - 1, dz = (rr / 3) - 1;
                 const int y = cy + dy, z = cz + dz;
                 if (y < 0 || y >= dimy || z < 0 || z >= dimz) continue;
@@ -292,20 +296,17 @@ batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
                 for (int i = rb; i < re; i++) {
                     const float4 p = __ldg(&sorted[i]);
                     const float d = l2_simple(sx, sy, sz, p);
-                    if (d < max_sq) {
-                        found++;
-                        const int oi = __float_as_int(p.w);
-                        if (d < bd[4] || (d == bd[4] && oi < bi[4])) {
-                            // insert (d, oi) into the ascending list, dropping the last entry
-                            bd[4] = d; bi[4] = oi; bp[4] = i;
+                    const int oi = __float_as_int(p.w);
+                    if (d < bd[4] || (d == bd[4] && oi < bi[4])) {   // sentinels have index -1: never beaten on a tie
+                        // insert (d, oi) into the ascending list, dropping the last entry
+                        bd[4] = d; bi[4] = oi; bp[4] = i;
 #pragma unroll
-                            for (int k = 4; k > 0; k--) {
-                                const bool sw = bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1]);
-                                if (sw) {
-                                    const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-                                    const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
-                                    const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
-                                }
+                        for (int k = 4; k > 0; k--) {
+                            const bool sw = bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1]);
+                            if (sw) {
+                                const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                                const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                                const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
                             }
                         }
                     }
@@ -313,14 +314,14 @@ batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
             }
         }
 #pragma unroll
-        for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = found >= 5 ? bp[k] : -1;
-        r.d5[q] = found >= 5 ? bd[4] : -1.f;
+        for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = bp[4] >= 0 ? bp[k] : -1;
+        r.d5[q] = bp[4] >= 0 ? bd[4] : -1.f;
     }
 }
 
 // ---- iteration, step 2: gate, line / plane fit, residual, Jacobian row (one THREAD per query; corner and
 // surf queries live in different warps), then the 28 fp64 products of the rows of this CTA
-__global__ void __launch_bounds__(BATCH_FIT_THREADS)
+__global__ void __launch_bounds__(BATCH_FIT_THREADS, 3)
 batch_fit_kernel(const BatchReg *__restrict__ regs, int iter, S2mParams prm)
 {
     __shared__ float s_row[8][BATCH_FIT_THREADS + 1];        // +1: lane k reads row ia(k), same column -> distinct banks
