@@ -102,6 +102,12 @@ const char *llb_last_error(const llb_ctx *ctx);
 void *llb_stream(llb_ctx *ctx);
 int  llb_synchronize(llb_ctx *ctx);
 
+/* Optional: pre-size every workspace (sweep clouds of up to max_scan_points each, raw local maps of up to
+ * max_raw_map_points each, a surrounding set of up to max_keyframes key-frames) so that no call below those bounds
+ * allocates: workspaces otherwise grow on demand (cudaMalloc / cudaFree, a device synchronisation and a latency
+ * spike of milliseconds whenever a cloud outgrows its buffer - the reference's own vectors reallocate the same way). */
+int  llb_reserve(llb_ctx *ctx, int max_scan_points, int max_raw_map_points, int max_keyframes);
+
 /* ---- pcl::VoxelGrid<PointXYZI>::filter (setLeafSize(leaf,leaf,leaf), defaults)
  *      call sites MO:1058-1063, MO:1070-1089, FA:779-780 ---- */
 int llb_voxel_downsample(llb_ctx *ctx, const llb_point *in, int n, float leaf,

@@ -57,7 +57,7 @@ class Stats(ctypes.Structure):
 
 EXPORTS = [
     "llb_abi_version", "llb_params_default", "llb_create", "llb_destroy", "llb_last_error", "llb_stream",
-    "llb_synchronize", "llb_voxel_downsample", "llb_map_set_ds", "llb_map_set_raw", "llb_map_get_ds",
+    "llb_synchronize", "llb_reserve", "llb_voxel_downsample", "llb_map_set_ds", "llb_map_set_raw", "llb_map_get_ds",
     "llb_scan_set", "llb_downsample_current_scan", "llb_scan_get_ds", "llb_s2m_iterate", "llb_s2m_optimize",
     "llb_get_correspondences", "llb_get_knn", "llb_get_normal_equations", "llb_get_degeneracy",
     "llb_set_degeneracy", "llb_odom_set_last", "llb_odom_set_features", "llb_odom_optimize", "llb_odom_iterate",
@@ -172,6 +172,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().llb_launch_count(self._h))
+
+    def reserve(self, max_scan_points: int, max_raw_map_points: int, max_keyframes: int = 0):
+        self._ck(lib().llb_reserve(self._h, int(max_scan_points), int(max_raw_map_points), int(max_keyframes)))
 
     # ---- voxel
     def voxel_downsample(self, pts, leaf: float) -> np.ndarray:

@@ -369,6 +369,31 @@ int llb_synchronize(llb_ctx *c)
     return guarded(c, [&]() { LLB_CUDA(cudaStreamSynchronize(c->stream)); return (int)LLB_OK; });
 }
 
+int llb_reserve(llb_ctx *c, int max_scan_points, int max_raw_map_points, int max_keyframes)
+{
+    return guarded(c, [&]() {
+        if (max_scan_points < 0 || max_raw_map_points < 0 || max_keyframes < 0) return (int)LLB_ERR_INVALID;
+        const size_t ns = (size_t)std::max(max_scan_points, 1), nm = (size_t)std::max(max_raw_map_points, 1);
+        // scan side: the three sweeps clouds, their staging and the four DS clouds
+        for (int i = 0; i < 3; i++) { c->pin_in[i].ensure(std::max(ns, nm) * 8); c->raw32[i].ensure(std::max(ns, nm) * 8); }
+        c->cornerLast.pts.ensure(ns); c->surfLast.pts.ensure(ns); c->outlierLast.pts.ensure(ns);
+        c->cornerLastDS.ensure(ns); c->surfLastDS.ensure(ns); c->outlierLastDS.ensure(ns); c->surfTotalLastDS.ensure(2 * ns);
+        // map side: raw map (host hand-over and key-frame assembly), DS map, voxel scratch, both spatial indices
+        c->mapCornerRaw.pts.ensure(nm); c->mapSurfRaw.pts.ensure(nm);
+        c->asmCorner.ensure(nm); c->asmSurf.ensure(nm);
+        c->mapCornerDS.ensure(nm); c->mapSurfDS.ensure(nm);
+        c->vox.reserve((int)std::max(nm, 2 * ns));
+        c->gridCorner.job(nullptr, nullptr, (int)nm); c->gridSurf.job(nullptr, nullptr, (int)nm);
+        c->tmp_in.ensure(std::max(ns, nm)); c->tmp_vox.ensure(std::max(ns, nm)); c->pin_out.ensure(std::max(ns, nm));
+        const int nq = 3 * (int)ns;
+        c->dbg_coeff.ensure(nq); c->dbg_valid.ensure(nq); c->dbg_knn.ensure((size_t)nq * 5); c->dbg_d2.ensure((size_t)nq * 5);
+        c->asm_segs.ensure(3 * (size_t)std::max(max_keyframes, 1)); c->pin_segs.ensure(3 * (size_t)std::max(max_keyframes, 1));
+        if (max_keyframes > 0) c->kfs.reserve((size_t)max_keyframes * 3 * ns / 2);   // DS clouds are well below the raw sweep size
+        LLB_CUDA(cudaDeviceSynchronize());
+        return (int)LLB_OK;
+    });
+}
+
 int llb_voxel_downsample(llb_ctx *c, const llb_point *in, int n, float leaf, llb_point *out, int cap, int *m)
 {
     return guarded(c, [&]() {

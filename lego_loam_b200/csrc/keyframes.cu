@@ -52,6 +52,15 @@ float4 *KeyFrameStore::alloc(size_t n)
     return r;
 }
 
+void KeyFrameStore::reserve(size_t n_points)
+{
+    if (!chunks_.empty() && cap_ - used_ >= n_points) return;
+    float4 *p = nullptr;
+    LLB_CUDA(cudaMalloc(&p, std::max(n_points, CHUNK) * sizeof(float4)));
+    chunks_.push_back(p);
+    used_ = 0; cap_ = std::max(n_points, CHUNK);
+}
+
 int KeyFrameStore::add(const int n[3], float4 *dst[3])
 {
     KeyFrameRec r;

@@ -25,6 +25,8 @@ public:
     const KeyFrameRec &rec(int i) const { return recs_[i]; }
     // reserves room for the three clouds of a new key-frame and returns where to copy them
     int add(const int n[3], float4 *dst[3]);
+    // makes room for n_points more key-frame points without a further allocation
+    void reserve(size_t n_points);
 private:
     static constexpr size_t CHUNK = (size_t)4 << 20;                    // points per arena chunk (64 MB)
     float4 *alloc(size_t n);

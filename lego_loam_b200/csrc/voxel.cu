@@ -255,6 +255,14 @@ void VoxelFilter::init()
     LLB_CUDA(cudaGetLastError());
 }
 
+void VoxelFilter::reserve(int n)
+{
+    if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
+    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
+    hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
+    blk_.ensure(div_up(n, HEAD_TILE) + 1);
+}
+
 void VoxelFilter::release()
 {
     desc_.release(); keys_[0].release(); keys_[1].release(); vals_[0].release(); vals_[1].release();

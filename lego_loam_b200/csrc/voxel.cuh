@@ -31,6 +31,8 @@ public:
     static constexpr int MAX_BATCH = 4;         // independent small filters sharing one launch
     void init();
     void release();
+    // pre-sizes the scratch of the multi-kernel path for inputs of up to n points (no allocation at run time below n)
+    void reserve(int n);
     // out must have room for in.upper() points; n_out_dev receives the output count.
     // All work is enqueued on `stream`; nothing synchronises. Returns kernels launched.
     int run(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t stream);

@@ -3,10 +3,14 @@ mapOptmization.cpp -- key-frame store, extractSurroundingKeyFrames, transformAss
 is run twice over the same synthetic VLP-16 sequence: once pure, once with its hot path
 (map voxel tail MO:1057-1064 + downsampleCurrentScan + scan2MapOptimization) replaced by the CUDA library
 through the C ABI.  Bars of the north star: per-scan pose within 1e-4 m / 1e-4 rad, accumulated drift within 0.1 %."""
+import json
+import os
+import time
+
 import numpy as np
 import pytest
 
-from lego_loam_b200 import synth
+from lego_loam_b200 import api, synth
 from oracle import ref_harness
 from tests import data
 
@@ -80,7 +84,7 @@ def test_sequence_replay_drift_parity(ctx):
     assert np.linalg.norm(gpu[-1, 3:] - truth[-1, 3:]) < 0.5
 
 
-def replay_keyframe_store(ctx, poses, odo, scans):
+def replay_keyframe_store(ctx, poses, odo, scans, lat=None):
     """The same replay with the key-frame clouds kept on the DEVICE (llb_keyframe_add) and the local map assembled
     there (llb_map_assemble) from the ids / poses the reference's own host bookkeeping selects: the raw and the DS
     local map never exist on the host, only the new sweep crosses PCIe."""
@@ -93,13 +97,20 @@ def replay_keyframe_store(ctx, poses, odo, scans):
         mo.transformAssociateToMap()
         mo.extractSurroundingKeyFrames()             # host bookkeeping (ids) + the reference's own clouds to compare with
         mo.downsampleCurrentScan()
-        ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
-        ctx.downsample_current_scan()
         ids = mo.surrounding_ids()
+        kposes = np.stack([mo.keypose6d(i) for i in ids]) if ids.shape[0] else np.zeros((0, 6), np.float32)
+        c32, s32, o32 = api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last)
+        t0 = time.perf_counter()
+        ctx.scan_set_pcl(c32, s32, o32)
+        ctx.downsample_current_scan(want_counts=False)
         nc, ns = mo.map_ds_sizes()
         if ids.shape[0] > 0:
-            ctx.map_assemble(ids, np.stack([mo.keypose6d(i) for i in ids]))
+            ctx.map_assemble(ids, kposes)
             n_asm += 1
+        if lat is not None and nc > 10 and ns > 100:
+            T_, st_ = ctx.s2m_optimize(mo.transformTobeMapped)   # timed copy of the registration below (same inputs)
+            lat.append(((time.perf_counter() - t0) * 1e3, int(ids.shape[0]), int(mo.map_raw(0).shape[0] + mo.map_raw(1).shape[0])))
+        if ids.shape[0] > 0:
             raw_equal &= np.array_equal(ctx.map_get_raw(0).view(np.uint32), mo.map_raw(0).view(np.uint32))
             raw_equal &= np.array_equal(ctx.map_get_raw(1).view(np.uint32), mo.map_raw(1).view(np.uint32))
             ds_equal &= np.array_equal(ctx.map_get_ds(0).view(np.uint32), mo.map_ds(0).view(np.uint32))
@@ -132,3 +143,26 @@ def test_sequence_replay_device_keyframe_store(ctx):
     # a stored key-frame equals the reference's copy of the DS clouds (MO:1447-1449)
     ctx.keyframe_clear()
     assert ctx.keyframe_count() == 0
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="oracle/_ref not built")
+def test_sequence_replay_latency_histogram(ctx):
+    """BASELINE configs[1] shape: per-scan latency of the mapping hot path over a replayed sequence with the device
+    key-frame store (host sweep in -> assemble local map from resident key-frames -> voxel -> index -> downsample ->
+    scan2MapOptimization -> pose out, wall clock).  LLB_REPLAY_SCANS sets the length (default 36); the summary is
+    written to gpurun_out/sequence_replay.json for profiles/."""
+    n = int(os.environ.get("LLB_REPLAY_SCANS", str(N_SCANS)))
+    poses, odo, scans = make_sequence(n)
+    lat = []
+    ctx.reserve(16384, 600000, 256)                              # steady state: no workspace grows during the replay
+    gpu, raw_equal, ds_equal, n_asm = replay_keyframe_store(ctx, poses, odo, scans, lat)
+    assert raw_equal and ds_equal and len(lat) >= n - 3
+    ms = np.array([x[0] for x in lat[2:]])
+    out = {"scans": n, "registrations": int(ms.shape[0]), "ms_p50": float(np.percentile(ms, 50)), "ms_p99": float(np.percentile(ms, 99)),
+           "ms_max": float(ms.max()), "ms_mean": float(ms.mean()), "key_frames_last": lat[-1][1], "raw_map_points_last": lat[-1][2],
+           "note": "wall clock per scan through the C ABI: H2D sweep + map assembly from resident key-frames + 2 map voxel "
+                   "filters + index build + downsampleCurrentScan + scan2MapOptimization + D2H pose; one context"}
+    assert out["ms_p99"] < 5.0                                   # north star: < 1 ms per scan for the registration itself
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        json.dump(out, open(os.path.join(d, "sequence_replay.json"), "w"), indent=1)
