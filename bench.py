@@ -290,6 +290,55 @@ def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_
                     "downsampleCurrentScan + scan2MapOptimization; host clouds in (new sweep only), pose out, wall clock"}
 
 
+def odometry_arm(api, local, reps, cpu_sample):
+    """Secondary arm for the featureAssociation rows of the path: updateTransformation (FA:1666-1695:
+    both <= 25-iteration LM loops with their correspondence searches) for one VLP-16 sweep pair, device time and wall
+    time through the C ABI with host clouds, beside the reference's own function on one core."""
+    from lego_loam_b200 import synth
+    w = synth.make_world(synth.SEED0)
+    od = synth.make_odometry_pair(w, synth.VLP16, np.array([0, 1.0, 0, 3.0, 0, -4.0]),
+                                  np.array([0.002, 0.015, -0.001, 0.01, 0.005, -0.15]), seed=1)
+    c = api.Context(local)
+    dev_ms, wall_ms = [], []
+    for i in range(reps + 3):
+        t0 = time.perf_counter()
+        c.odom_set_last(od.corner_last, od.surf_last)            # FA:1615-1619 / FA:1774-1788 (index of the last sweep)
+        c.odom_set_features(od.corner_sharp, od.surf_flat)
+        T, s0, s1 = c.odom_optimize(np.zeros(6, np.float32))
+        if i >= 3:
+            wall_ms.append((time.perf_counter() - t0) * 1e3); dev_ms.append(s0.device_ms)
+    c.close()
+    kind, fa = "port", None
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            kind = "reference"; fa = ref_harness.FeatureAssociation()
+    except Exception:
+        pass
+    if fa is None:
+        import oracle
+        oracle.set_trig_mode(0); fa = oracle.FeatureAssociation()
+
+    def cpu_once():
+        fa.set_last(od.corner_last, od.surf_last, True)
+        fa.set_features(od.corner_sharp, od.surf_flat)
+        fa.transformCur = np.zeros(6, np.float32)
+        fa.updateTransformation()
+        return fa.transformCur
+    cpu_once()
+    t0 = time.perf_counter()
+    for _ in range(cpu_sample):
+        Tc = cpu_once()
+    cpu_ms = (time.perf_counter() - t0) / cpu_sample * 1e3
+    return {"ms_per_scan_device": float(np.median(dev_ms)), "ms_per_scan_e2e_host": float(np.median(wall_ms)),
+            "iterations": [int(s0.iterations), int(s1.iterations)],
+            "features": {"sharp": int(od.corner_sharp.shape[0]), "flat": int(od.surf_flat.shape[0]),
+                         "corner_last": int(od.corner_last.shape[0]), "surf_last": int(od.surf_last.shape[0])},
+            "cpu_1core": {"ms_per_scan": cpu_ms, "kind": kind, "sample": f"{cpu_sample} calls"},
+            "pose_max_abs_diff_vs_cpu": float(np.max(np.abs(np.asarray(T) - np.asarray(Tc)))),
+            "note": "updateTransformation (FA:1666-1695) of one VLP-16 sweep pair: one persistent CTA on the device"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -503,6 +552,12 @@ def main():
             mc_arm = mapping_cycle_arm(api, local, 16, args.key_frames, max(4, K // 4), 2, 8, 4)
         except Exception as e:                                # secondary arm: never hides the main line
             mc_arm = {"error": repr(e)}
+    od_arm = None
+    if rank == 0:
+        try:
+            od_arm = odometry_arm(api, local, 20, 10)
+        except Exception as e:
+            od_arm = {"error": repr(e)}
     if world > 1:
         dist.barrier()
 
@@ -591,6 +646,7 @@ def main():
             "last_stats": last["st"][0].as_dict() if "st" in last else None,
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
             "mapping_cycle": mc_arm,
+            "odometry": od_arm,
         }
         print(json.dumps(line))
     if world > 1:
