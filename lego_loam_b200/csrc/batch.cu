@@ -63,7 +63,7 @@ constexpr int QS_THREADS = 512;
 constexpr int QS_ITEMS = 4;
 
 __global__ void __launch_bounds__(QS_THREADS)
-batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap)
+batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap, int by_count)
 {
     extern __shared__ __align__(16) unsigned char qs_smem[];
     unsigned *kin = reinterpret_cast<unsigned *>(qs_smem), *kout = kin + cap;
@@ -96,11 +96,32 @@ batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap)
         const int cx = min(max(grid_coord(sx, ox, inv), 0), dimx - 1);
         const int cy = min(max(grid_coord(sy, oy, inv), 0), dimy - 1);
         const int cz = min(max(grid_coord(sz, oz, inv), 0), dimz - 1);
-        kin[i] = (unsigned)((cz * dimy + cy) * dimx + cx);
+        unsigned key = (unsigned)((cz * dimy + cy) * dimx + cx);
+        if (by_count) {
+            // key = number of candidates in the 3x3x3 cell neighbourhood (what the kNN thread of this query will walk):
+            // threads of a warp then get queries of (nearly) equal cost
+            const int *__restrict__ cell_begin = which == 0 ? r.cmap.cell_begin : r.smap.cell_begin;
+            const int *__restrict__ row_begin = which == 0 ? r.cmap.row_begin : r.smap.row_begin;
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
+            int tot = 0;
+            // the three rows of the query's own z-slab (12 independent loads): a cheap proxy of the 9-row total
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int y = cy + dy;
+                if (y < 0 || y >= dimy) continue;
+                const int ry = cz * dimy + y;
+                const int r0 = __ldg(&row_begin[ry]), r1 = __ldg(&row_begin[ry + 1]);
+                const int c0 = __ldg(&cell_begin[ry * dimx + x0]), c1 = __ldg(&cell_begin[ry * dimx + x1 + 1]);
+                tot += (r1 > r0) ? (c1 - c0) : 0;
+            }
+            key = (unsigned)min(tot >> 1, 255);               // one 8-bit radix pass is enough to equalise warps
+        }
+        kin[i] = key;
         vin[i] = (unsigned short)i;
     }
     int nbits = 1;
-    while (nbits < 32 && ((unsigned)(g->ncell - 1) >> nbits) != 0u) nbits++;
+    if (by_count) nbits = 8;
+    else while (nbits < 32 && ((unsigned)(g->ncell - 1) >> nbits) != 0u) nbits++;
     cta_radix_sort<QS_THREADS, QS_ITEMS>(kin, kout, vin, vout, n, nbits, s_wcnt, s_base, s_scan);
     for (int i = tid; i < n; i += QS_THREADS) perm[i] = (int)vin[i];
 }
@@ -237,10 +258,11 @@ batch_knn_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
     }
 }
 
-// DEFAULT kNN kernel: single phase, the five best (distance, original index) pairs live in registers while the thread
-// scans its candidates.  Measured on B200 (64 slots x ~3.5k queries, profiles/r01c_batch.md): 118 us per iteration vs
-// 157 us for the two-phase list variant above (LLB_KNN_VARIANT=2), with or without cell-ordered queries: both are bound
-// by unequal candidate counts of neighbouring lanes (8-14 active lanes per instruction), not by the insertion path.
+// kNN variant 1 (LLB_KNN_VARIANT=1): single phase, the five best (distance, original index) pairs live in registers
+// while the thread scans its candidates row by row, queries in scan order.  Measured on B200 (64 slots x ~3.5k
+// queries, profiles/r01c_batch.md): 118 us per iteration vs 157 us for the two-phase list variant above
+// (LLB_KNN_VARIANT=2), with or without cell-ordered queries: both are bound by unequal candidate counts of neighbouring
+// lanes (8-14 active lanes per instruction).  Variant 3 below (the default) removes that imbalance.
 __global__ void __launch_bounds__(256, 4)
 batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
 {
@@ -312,6 +334,94 @@ batch_knn1_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
                     }
                 }
             }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = bp[4] >= 0 ? bp[k] : -1;
+        r.d5[q] = bp[4] >= 0 ? bd[4] : -1.f;
+    }
+}
+
+// DEFAULT kNN kernel, variant 3 (LLB_KNN_VARIANT=3): the register top-5 search of batch_knn1_kernel with the two causes of its low lane
+// utilisation (8.7 active lanes per instruction) removed: (a) the queries are handed out in order of their candidate
+// count (batch_qsort_kernel, by_count) so the threads of a warp have equal work, (b) the nine cell runs of a query are
+// compacted into a per-thread list in shared memory and walked as ONE flattened loop with the next candidate's load
+// issued before the current one is processed, so a warp iterates max(total) times instead of sum over rows of max(row).
+__global__ void __launch_bounds__(256, 4)
+batch_knn3_kernel(const BatchReg *__restrict__ regs, S2mParams prm)
+{
+    __shared__ int s_rb[9][256], s_re[9][256];
+    const BatchReg r = regs[blockIdx.y];
+    const S2mState *st = r.st;
+    if (__ldcg(&st->skipped) || __ldcg(&st->converged)) return;
+    const int tid = threadIdx.x;
+    const float crx = __ldcg(&st->cs[0]), srx = __ldcg(&st->cs[1]), cry = __ldcg(&st->cs[2]),
+                sry = __ldcg(&st->cs[3]), crz = __ldcg(&st->cs[4]), srz = __ldcg(&st->cs[5]);
+    const float tX = __ldcg(&st->T[3]), tY = __ldcg(&st->T[4]), tZ = __ldcg(&st->T[5]);
+    const int nc = *r.nc_dev, ns = *r.ns_dev;
+    const int nq = min(nc + ns, r.cap);
+    const float max_sq = prm.knn_max_sqdist;
+    const float prune_sq = max_sq * 1.01f;
+    for (int j = blockIdx.x * 256 + tid; j < nq; j += gridDim.x * 256) {
+        const bool is_corner = j < nc;
+        const int q = (is_corner ? 0 : nc) + __ldg(&r.qperm[j]);
+        const float4 po = is_corner ? __ldg(&r.corner[q]) : __ldg(&r.surf[q - nc]);
+        float sx, sy, sz;
+        associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
+        const GridDesc *g = is_corner ? r.cmap.desc : r.smap.desc;
+        const int *__restrict__ cell_begin = is_corner ? r.cmap.cell_begin : r.smap.cell_begin;
+        const int *__restrict__ row_begin = is_corner ? r.cmap.row_begin : r.smap.row_begin;
+        const float4 *__restrict__ sorted = is_corner ? r.cmap.sorted : r.smap.sorted;
+        const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
+        const float inv = g->inv_cell, cell = g->cell;
+        const float fy = (sy - g->org[1]) * inv, fz = (sz - g->org[2]) * inv;
+        const int cx = grid_coord(sx, g->org[0], inv), cy = (int)floorf(fy), cz = (int)floorf(fz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
+        const float ly = (fy - (float)cy) * cell, lz = (fz - (float)cz) * cell;
+        // ---- the non-empty, non-pruned runs of this query, own row first (see batch_knn1_kernel)
+        int nr = 0;
+        if (x0 <= x1) {
+#pragma unroll
+            for (int ro = 0; ro < 9; ro++) {
+                const int rr = (int)((0x862075314ull >> (4 * ro)) & 15ull);
+                const int dy = (rr % 3) - 1, dz = (rr / 3) - 1;
+                const int y = cy + dy, z = cz + dz;
+                const float gy = dy < 0 ? ly : (dy > 0 ? cell - ly : 0.f);
+                const float gz = dz < 0 ? lz : (dz > 0 ? cell - lz : 0.f);
+                if (y >= 0 && y < dimy && z >= 0 && z < dimz && gy * gy + gz * gz <= prune_sq) {
+                    const int ry = z * dimy + y;
+                    const int r0 = __ldg(&row_begin[ry]), r1 = __ldg(&row_begin[ry + 1]);
+                    const int rb = __ldg(&cell_begin[ry * dimx + x0]), re = __ldg(&cell_begin[ry * dimx + x1 + 1]);
+                    if (r1 > r0 && re > rb) { s_rb[nr][tid] = rb; s_re[nr][tid] = re; nr++; }
+                }
+            }
+        }
+        float bd[5]; int bi[5], bp[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) { bd[k] = max_sq; bi[k] = -1; bp[k] = -1; }
+        // ---- flattened walk, software-pipelined by one candidate
+        int run = 0, i = 0, e = 0;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nr > 0) { i = s_rb[0][tid]; e = s_re[0][tid]; p = __ldg(&sorted[i]); }
+        while (run < nr) {
+            int ni = i + 1, nrun = run, ne = e;
+            if (ni >= e) { nrun = run + 1; if (nrun < nr) { ni = s_rb[nrun][tid]; ne = s_re[nrun][tid]; } }
+            float4 pn = p;
+            if (nrun < nr) pn = __ldg(&sorted[ni]);
+            const float d = l2_simple(sx, sy, sz, p);
+            const int oi = __float_as_int(p.w);
+            if (d < bd[4] || (d == bd[4] && oi < bi[4])) {
+                bd[4] = d; bi[4] = oi; bp[4] = i;
+#pragma unroll
+                for (int k = 4; k > 0; k--) {
+                    const bool sw = bd[k] < bd[k - 1] || (bd[k] == bd[k - 1] && bi[k] < bi[k - 1]);
+                    if (sw) {
+                        const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+                        const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+                        const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
+                    }
+                }
+            }
+            p = pn; i = ni; run = nrun; e = ne;
         }
 #pragma unroll
         for (int k = 0; k < 5; k++) r.nn[(size_t)k * r.cap + q] = bp[4] >= 0 ? bp[k] : -1;
@@ -442,7 +552,7 @@ void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, c
 
 int batch_knn_variant()
 {
-    static const int variant = getenv("LLB_KNN_VARIANT") ? atoi(getenv("LLB_KNN_VARIANT")) : 1;
+    static const int variant = getenv("LLB_KNN_VARIANT") ? atoi(getenv("LLB_KNN_VARIANT")) : 3;
     return variant;
 }
 
@@ -454,12 +564,17 @@ void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s)
         LLB_CUDA(cudaFuncSetAttribute(batch_qsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         attr_cap = bytes;
     }
-    batch_qsort_kernel<<<dim3(2, B), QS_THREADS, bytes, s>>>(regs, cap);
+    batch_qsort_kernel<<<dim3(2, B), QS_THREADS, bytes, s>>>(regs, cap, batch_knn_variant() == 3 ? 1 : 0);
     LLB_CUDA(cudaGetLastError());
 }
 
 void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s)
 {
+    if (batch_knn_variant() == 3) {
+        batch_knn3_kernel<<<dim3(std::max(1, ctas_per_slot * BATCH_KNN_THREADS / 256), B), 256, 0, s>>>(regs, prm);
+        LLB_CUDA(cudaGetLastError());
+        return;
+    }
     if (batch_knn_variant() != 2) {
         batch_knn1_kernel<<<dim3(std::max(1, ctas_per_slot * BATCH_KNN_THREADS / 256), B), 256, 0, s>>>(regs, prm);
         LLB_CUDA(cudaGetLastError());

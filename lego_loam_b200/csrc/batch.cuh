@@ -7,8 +7,8 @@
 //     1   unpack of every host cloud uploaded this step (PCL 32 B stride -> float4)
 //     2   downsampleCurrentScan, MO:1067-1091: 3B filters in one cluster launch, then the B "total" filters
 //     5   spatial-index build of every map that changed (replaces 2B kdtree->setInputCloud, MO:1333-1334)
-//     1   prepare (pose, sin/cos, guard MO:1331)
-//   2xI   per LM iteration (MO:1336-1346): kNN (thread per query, 32 warps/SM), then fit + Jacobian rows + fp64
+//     2   prepare (pose, sin/cos, guard MO:1331) + ordering of the queries by kNN cost (speed only)
+//   2xI   per LM iteration (MO:1336-1346): kNN (thread per query, cost-balanced warps), then fit + Jacobian rows + fp64
 //         products (thread per query) whose last CTA per slot also performs the LM step; converged slots drop out
 //     1   collect (pose + stats of all slots -> one D2H)
 // whereas the single-registration path (s2m.cu) is ONE persistent kernel tuned for latency.  Throughput
@@ -50,7 +50,7 @@ constexpr int BATCH_KNN_THREADS = 256;
 // kernels (batch.cu)
 void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s);
 void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, cudaStream_t s);
-int batch_knn_variant();   // 1 (default): single-phase register top-5; 2: cell-ordered queries + two-phase list
+int batch_knn_variant();   // 3 (default): cost-ordered queries + flattened walk; 1: row-by-row walk in scan order; 2: two-phase list
 void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s);
 void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s);
 void launch_batch_fit(const BatchReg *regs, int B, int fit_blocks, int iter, const S2mParams &prm, cudaStream_t s);

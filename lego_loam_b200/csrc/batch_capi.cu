@@ -244,7 +244,7 @@ int enqueue_step(llb_batch *c, const float *T)
     const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
     launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
     c->launches++;
-    if (batch_knn_variant() == 2) {                          // experimental kNN variant: cell-ordered queries
+    if (batch_knn_variant() >= 2) {                          // kNN variants 2 / 3: queries ordered by cell / by cost
         launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);
         c->launches++;
     }

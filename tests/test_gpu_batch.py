@@ -89,7 +89,7 @@ def test_batch_resident_map_and_repeat(cases):
     assert np.array_equal(T0.view(np.uint32), T1.view(np.uint32))
     assert [x.iterations for x in st0] == [x.iterations for x in st1]
     # launches of a step do not depend on the slot count and exclude the 5 index-build launches here
-    assert b.launch_count() - l0 == 2 + 1 + 2 * b.params.s2m_max_iterations + 1
+    assert b.launch_count() - l0 == 2 + 2 + 2 * b.params.s2m_max_iterations + 1
     b.close()
 
 
