@@ -324,7 +324,8 @@ int GridIndex::build_table(const GridJob *table_dev, int count, int n_upper_max,
     grid_bbox_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
     grid_count_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
     grid_row_scan_kernel<<<dim3(1, count), 1024, 0, s>>>(jobs, table_dev);
-    grid_row_apply_kernel<<<dim3(per, count), TPB, 0, s>>>(jobs, table_dev);
+    // one warp per row with two dependent round trips each: 4x the CTAs of the streaming kernels keeps the chains short
+    grid_row_apply_kernel<<<dim3(per * 4, count), TPB, 0, s>>>(jobs, table_dev);
     grid_scatter_kernel<<<grid_pts, TPB, 0, s>>>(jobs, table_dev);
     LLB_CUDA(cudaGetLastError());
     return 5;
