@@ -558,12 +558,9 @@ int batch_knn_variant()
 
 void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s)
 {
-    static int attr_cap = 0;
     const int bytes = cap * 12;
-    if (bytes > attr_cap) {
-        LLB_CUDA(cudaFuncSetAttribute(batch_qsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        attr_cap = bytes;
-    }
+    if (bytes > 48 * 1024)                                   // opt-in above the default limit (idempotent, per device)
+        LLB_CUDA(cudaFuncSetAttribute(batch_qsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
     batch_qsort_kernel<<<dim3(2, B), QS_THREADS, bytes, s>>>(regs, cap, batch_knn_variant() == 3 ? 1 : 0);
     LLB_CUDA(cudaGetLastError());
 }

@@ -315,12 +315,10 @@ voxel_small_jobs_kernel(const SmallJob *__restrict__ jobs)
 
 void launch_voxel_cta_jobs(const SmallJob *jobs_dev, int count, int cap, cudaStream_t stream)
 {
-    static int attr_cap = 0;                                 // largest dynamic shared memory opted into so far
     const int bytes = cap * 12;
-    if (bytes > attr_cap) {
-        LLB_CUDA(cudaFuncSetAttribute(voxel_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        attr_cap = bytes;
-    }
+    if (bytes > 48 * 1024)                                   // opt-in above the default limit (idempotent, per device)
+        LLB_CUDA(cudaFuncSetAttribute(voxel_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      VoxelFilter::SMALL_MAX * 12));
     voxel_cta_kernel<<<count, VC_THREADS, bytes, stream>>>(jobs_dev, cap);
     LLB_CUDA(cudaGetLastError());
 }
