@@ -274,6 +274,19 @@ int  llb_batch_result(llb_batch *b, float *T, llb_stats *stats);
 /* which: 0 cornerLastDS, 1 surfLastDS, 2 outlierLastDS, 3 surfTotalLastDS of the slot's last step */
 int  llb_batch_scan_get_ds(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
 int  llb_batch_get_degeneracy(llb_batch *b, int slot, int *is_degenerate);
+/* ---- device-resident key-frame stores for the slots of a batch (the llb_ctx calls llb_keyframe_add / llb_map_assemble
+ * with a leading slot index).  llb_batch_enable_keyframes sizes the per-slot arenas and the scratch of the batched
+ * map voxel filters: raw local maps of up to max_raw_map_points points each, up to max_keyframes key-frames per
+ * assembled map.  llb_batch_keyframe_add stores the DS clouds of the slot's LAST completed step (MO:1443-1453);
+ * llb_batch_map_assemble (MO:1033-1064) takes effect in the NEXT step, where the raw maps of all requesting slots are
+ * assembled by one launch and voxel-filtered by one set of 18 launches; a slot's map then stays as it is until the
+ * next llb_batch_map_assemble / llb_batch_map_set_ds. */
+int  llb_batch_enable_keyframes(llb_batch *b, int max_raw_map_points, int max_keyframes);
+int  llb_batch_keyframe_add(llb_batch *b, int slot, int *id);
+int  llb_batch_keyframe_count(llb_batch *b, int slot, int *n);
+int  llb_batch_map_assemble(llb_batch *b, int slot, const int *ids, const float *poses, int n);
+/* which: 0 / 1 raw corner / surf map, 2 / 3 DS corner / surf map of the slot's last assembled map (parity checks) */
+int  llb_batch_map_get(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
 /* per-stage CUDA-event times of the last step when enabled: ms[6] = {host-cloud unpack, downsampleCurrentScan,
  * index build, kNN kernels, fit kernels, LM-step + prepare + collect kernels}; geometry[4] = {kNN CTAs per slot,
  * fit CTAs per slot, index-build CTAs per map, query capacity per slot} */

@@ -73,7 +73,8 @@ EXPORTS = [
     "llb_batch_launch_count", "llb_batch_scan_set", "llb_batch_map_set_ds", "llb_batch_scan_set_dev",
     "llb_batch_map_set_ds_dev", "llb_batch_scan_set_all", "llb_batch_map_set_ds_all", "llb_batch_scan_set_dev_all",
     "llb_batch_map_set_ds_dev_all", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
-    "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
+    "llb_batch_enable_keyframes", "llb_batch_keyframe_add", "llb_batch_keyframe_count", "llb_batch_map_assemble",
+    "llb_batch_map_get", "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
 ]
 
 _lib = None
@@ -534,6 +535,34 @@ class Batch:
         self._ck(lib().llb_batch_scan_get_ds(self._h, slot, which, None, 0, ctypes.byref(n)))
         out = np.zeros((max(n.value, 1), 8), np.float32)
         self._ck(lib().llb_batch_scan_get_ds(self._h, slot, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    # ---- per-slot device-resident key-frame stores
+    def enable_keyframes(self, max_raw_map_points: int, max_keyframes: int):
+        self._ck(lib().llb_batch_enable_keyframes(self._h, int(max_raw_map_points), int(max_keyframes)))
+
+    def keyframe_add(self, slot: int) -> int:
+        k = ctypes.c_int(-1)
+        self._ck(lib().llb_batch_keyframe_add(self._h, slot, ctypes.byref(k)))
+        return k.value
+
+    def keyframe_count(self, slot: int) -> int:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_batch_keyframe_count(self._h, slot, ctypes.byref(n)))
+        return n.value
+
+    def map_assemble(self, slot: int, ids, poses6d):
+        i = np.ascontiguousarray(ids, np.int32)
+        p = np.ascontiguousarray(poses6d, np.float32).reshape(-1, 6)
+        assert p.shape[0] == i.shape[0]
+        self._ck(lib().llb_batch_map_assemble(self._h, slot, i.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(p),
+                                              int(i.shape[0])))
+
+    def map_get(self, slot: int, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_batch_map_get(self._h, slot, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_batch_map_get(self._h, slot, which, _vp(out), n.value, ctypes.byref(n)))
         return from_pcl(out[:n.value])
 
     def get_degeneracy(self, slot: int) -> bool:

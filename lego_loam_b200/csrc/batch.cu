@@ -27,6 +27,13 @@ batch_unpack_kernel(const BatchUnpack *__restrict__ jobs)
     }
 }
 
+__global__ void __launch_bounds__(256)
+batch_copy_kernel(const BatchCopy *__restrict__ jobs)
+{
+    const BatchCopy jb = jobs[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) jb.dst[i] = __ldg(&jb.src[i]);
+}
+
 __global__ void batch_state_init_kernel(S2mState *st, int B)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -525,10 +532,19 @@ __global__ void batch_collect_kernel(const BatchReg *__restrict__ regs, int B, B
     for (int i = 0; i < 6; i++) o.T[i] = st->T[i];
     o.iters = st->iters; o.converged = st->converged; o.n_corr = st->n_corr; o.is_degenerate = st->is_degenerate;
     o.skipped = st->skipped; o.nc = *r.nc_dev; o.ns = *r.ns_dev; o.pad = 0;
+    for (int k = 0; k < 4; k++) o.ds[k] = r.nc_dev[k];       // nc_dev points at the slot's four DS counts
     out[b] = o;
 }
 
 }  // namespace
+
+void launch_batch_copy(const BatchCopy *jobs_dev, int count, int n_max, cudaStream_t s)
+{
+    if (count <= 0) return;
+    const dim3 grid(std::max(1, std::min(div_up(std::max(n_max, 1), 256), 32)), count);
+    batch_copy_kernel<<<grid, 256, 0, s>>>(jobs_dev);
+    LLB_CUDA(cudaGetLastError());
+}
 
 void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s)
 {

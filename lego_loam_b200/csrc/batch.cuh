@@ -19,6 +19,7 @@
 #include "grid_index.cuh"
 #include "s2m.cuh"
 #include "voxel_dev.cuh"
+#include "keyframes.cuh"
 #include <vector>
 
 namespace llb {
@@ -42,12 +43,18 @@ struct BatchUnpack {                 // one host cloud to compact: raw PCL point
 struct BatchResult {                 // per slot, gathered into one contiguous D2H block
     float T[6];
     int iters, converged, n_corr, is_degenerate, skipped, nc, ns, pad;
+    int ds[4];                       // sizes of cornerLastDS, surfLastDS, outlierLastDS, surfTotalLastDS
+};
+
+struct BatchCopy {                   // float4 cloud copy (DS clouds of a sweep -> key-frame arena)
+    const float4 *src; float4 *dst; int n;
 };
 
 constexpr int BATCH_FIT_THREADS = 256;
 constexpr int BATCH_KNN_THREADS = 256;
 
 // kernels (batch.cu)
+void launch_batch_copy(const BatchCopy *jobs_dev, int count, int n_max, cudaStream_t s);
 void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s);
 void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, cudaStream_t s);
 int batch_knn_variant();   // 3 (default): cost-ordered queries + flattened walk; 1: row-by-row walk in scan order; 2: two-phase list

@@ -15,7 +15,7 @@ namespace {
 
 // everything the kernels of one step read that the host decides: uploaded with ONE H2D copy per step
 struct StepLayout {
-    size_t off_scan_n, off_map_n, off_poses, off_small1, off_small2, off_grid, off_regs, off_unpack, bytes;
+    size_t off_scan_n, off_map_n, off_poses, off_small1, off_small2, off_grid, off_regs, off_unpack, off_vox, off_copy, bytes;
     explicit StepLayout(int B)
     {
         size_t o = 0;
@@ -28,6 +28,8 @@ struct StepLayout {
         off_grid = take(sizeof(GridJob) * 2 * B);
         off_regs = take(sizeof(BatchReg) * B);
         off_unpack = take(sizeof(BatchUnpack) * 5 * B);
+        off_vox = take(sizeof(LargeVoxelJob) * 2 * B);
+        off_copy = take(sizeof(BatchCopy) * 3 * B);
         bytes = o;
     }
 };
@@ -79,6 +81,24 @@ struct llb_batch {
     std::vector<Reg> regs;
     std::vector<PinnedBuf<float>> stage;     // [B*5] lazily allocated staging (pin_host_clouds == 0)
     std::vector<cudaEvent_t> stage_ev; std::vector<char> stage_busy;
+
+    // device-resident key-frame stores (llb_batch_enable_keyframes): per slot an arena of key-frame clouds, the assembled
+    // raw local map, the voxel scratch of its two map filters and the DS maps they produce
+    bool kf_enabled = false;
+    int cap_raw = 0, max_kf = 0;
+    std::vector<KeyFrameStore> kfs;
+    std::vector<VoxelFilter> vox;            // 2B (corner, surf)
+    DevBuf<float4> raw_map;                  // [B][2][cap_raw]
+    DevBuf<float4> ds_map;                   // [B][2][cap_raw]
+    DevBuf<int> ds_map_n;                    // [B][2]
+    DevBuf<AsmSeg> seg_dev;
+    PinnedBuf<AsmSeg> seg_pin[RING];
+    struct AsmReq { std::vector<int> ids; std::vector<float> poses; bool pending = false; int rc = 0, rs = 0; };
+    std::vector<AsmReq> asm_req;
+    std::vector<char> map_from_kf;           // the slot's current map is the assembled one (counts live on the device)
+    std::vector<BatchCopy> pending_copy;
+    int pending_copy_max = 0;
+    bool have_results = false;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool pending = false;
@@ -160,7 +180,7 @@ int enqueue_step(llb_batch *c, const float *T)
 {
     const int B = c->B;
     for (int s = 0; s < B; s++)
-        if (!c->slots[s].scan_set || !c->slots[s].map_set) return LLB_ERR_STATE;
+        if (!c->slots[s].scan_set || !(c->slots[s].map_set || (c->kf_enabled && c->asm_req[s].pending))) return LLB_ERR_STATE;
     // ---- build this step's tables in the next pinned block
     const int rp = c->ring_pos;
     c->ring_pos = (rp + 1) % RING;
@@ -177,6 +197,10 @@ int enqueue_step(llb_batch *c, const float *T)
     const float leaf[3] = { c->prm.corner_leaf, c->prm.surf_leaf, c->prm.outlier_leaf };
     int ngrid = 0, map_n_max = 1;
     int vmax1 = 1, vmax2 = 1;
+    LargeVoxelJob *h_vox = (LargeVoxelJob *)(hp + L.off_vox);
+    BatchCopy *h_copy = (BatchCopy *)(hp + L.off_copy);
+    int nvox = 0, nseg = 0, seg_max = 1, raw_max = 1;
+    AsmSeg *h_seg = c->kf_enabled ? c->seg_pin[rp].p : nullptr;
     for (int s = 0; s < B; s++) {
         llb_batch::Slot &sl = c->slots[s];
         float4 *ds = c->scan_ds.p + (size_t)s * 5 * c->cap_scan;
@@ -195,10 +219,42 @@ int enqueue_step(llb_batch *c, const float *T)
         t.in.a = ds_out[1]; t.in.na_dev = dsn + 1; t.in.na = sl.scan_n[1];
         t.in.b = ds_out[2]; t.in.nb_dev = dsn + 2; t.in.nb = sl.scan_n[2];
         t.leaf = c->prm.surf_leaf; t.out = ds_out[3]; t.n_out = dsn + 3;
+        if (c->kf_enabled && c->asm_req[s].pending) {
+            // cloud part of extractSurroundingKeyFrames for this slot: segments of the fused transform + concatenation
+            // launch, then its two map voxel filters (MO:1057-1064) as jobs of the batched multi-kernel path
+            llb_batch::AsmReq &rq = c->asm_req[s];
+            float4 *rawc = c->raw_map.p + (size_t)(2 * s) * c->cap_raw, *raws = rawc + c->cap_raw;
+            float4 *dsc = c->ds_map.p + (size_t)(2 * s) * c->cap_raw, *dss = dsc + c->cap_raw;
+            size_t oc = 0, os = 0;
+            for (size_t k = 0; k < rq.ids.size(); k++) {
+                const KeyFrameRec &kr = c->kfs[s].rec(rq.ids[k]);
+                const float *p = rq.poses.data() + 6 * k;
+                AsmSeg sg{};
+                sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]); sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
+                sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]); sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
+                sg.src = kr.cloud[0]; sg.n = kr.n[0]; sg.dst = rawc + oc; oc += kr.n[0];
+                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
+                sg.src = kr.cloud[1]; sg.n = kr.n[1]; sg.dst = raws + os; os += kr.n[1];
+                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
+                sg.src = kr.cloud[2]; sg.n = kr.n[2]; sg.dst = raws + os; os += kr.n[2];
+                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
+            }
+            VoxelInput vc; vc.a = rawc; vc.na = (int)oc;
+            VoxelInput vs; vs.a = raws; vs.na = (int)os;
+            int *dn = c->ds_map_n.p + 2 * s;
+            h_vox[nvox++] = c->vox[2 * s].large_job(vc, c->prm.corner_leaf, dsc, dn);
+            h_vox[nvox++] = c->vox[2 * s + 1].large_job(vs, c->prm.surf_leaf, dss, dn + 1);
+            raw_max = std::max(raw_max, (int)std::max(oc, os));
+            sl.map[0] = dsc; sl.map[1] = dss; sl.map_n[0] = (int)oc; sl.map_n[1] = (int)os;   // upper bounds
+            sl.map_set = true; sl.map_dirty = true;
+            c->map_from_kf[s] = 1;
+            rq.pending = false;
+        }
         for (int k = 0; k < 2; k++) {
             h_map_n[2 * s + k] = sl.map_n[k];
             if (sl.map_dirty) {
-                h_grid[ngrid++] = c->grids[2 * s + k].job(sl.map[k], d_map_n + 2 * s + k, sl.map_n[k]);
+                const int *n_dev = (c->kf_enabled && c->map_from_kf[s]) ? c->ds_map_n.p + 2 * s + k : d_map_n + 2 * s + k;
+                h_grid[ngrid++] = c->grids[2 * s + k].job(sl.map[k], n_dev, sl.map_n[k]);
                 map_n_max = std::max(map_n_max, sl.map_n[k]);
             }
         }
@@ -220,6 +276,11 @@ int enqueue_step(llb_batch *c, const float *T)
     for (int i = 0; i < nunp; i++) h_unp[i] = c->pending_unpack[i];
     const int unp_max = c->pending_unpack_max;
     c->pending_unpack.clear(); c->pending_unpack_max = 0;
+    const int ncopy = (int)c->pending_copy.size();
+    if (ncopy > 3 * B) return LLB_ERR_STATE;
+    for (int i = 0; i < ncopy; i++) h_copy[i] = c->pending_copy[i];
+    const int copy_max = c->pending_copy_max;
+    c->pending_copy.clear(); c->pending_copy_max = 0;
 
     // ---- enqueue
     c->n_pev = 0;
@@ -232,6 +293,18 @@ int enqueue_step(llb_batch *c, const float *T)
         launch_batch_unpack((const BatchUnpack *)(dp + L.off_unpack), nunp, unp_max, c->stream);
         c->launches++;
     }
+    if (ncopy > 0) {                                         // key-frames saved since the last step: DS clouds -> arenas,
+        launch_batch_copy((const BatchCopy *)(dp + L.off_copy), ncopy, copy_max, c->stream);   // before they are overwritten
+        c->launches++;
+    }
+    if (nseg > 0) {
+        LLB_CUDA(cudaMemcpyAsync(c->seg_dev.p, h_seg, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
+        launch_kf_assemble(c->seg_dev.p, nseg, seg_max, c->stream);
+        c->launches++;
+    }
+    if (nvox > 0)
+        c->launches += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
+                                                 std::max(raw_max, c->cap_raw), c->stream);
     prof_mark(c, 0);
     launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream);
     launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream);
@@ -270,6 +343,7 @@ int fetch_result(llb_batch *c, float *T, llb_stats *stats)
     if (!c->pending) return LLB_ERR_STATE;
     LLB_CUDA(cudaStreamSynchronize(c->stream));
     c->pending = false;
+    c->have_results = true;
     float ms = 0.f;
     LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     for (int s = 0; s < c->B; s++) {
@@ -371,6 +445,10 @@ int llb_batch_destroy(llb_batch *c)
     c->results.release(); c->pin_results.release(); c->step_dev.release();
     for (int i = 0; i < RING; i++) { c->step_pin[i].release(); if (c->step_ev[i]) cudaEventDestroy(c->step_ev[i]); }
     for (auto &g : c->grids) g.release();
+    for (auto &k : c->kfs) k.release();
+    for (auto &v : c->vox) v.release();
+    c->raw_map.release(); c->ds_map.release(); c->ds_map_n.release(); c->seg_dev.release();
+    for (int i = 0; i < RING; i++) c->seg_pin[i].release();
     for (auto &s : c->stage) s.release();
     for (auto &e : c->stage_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 64; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
@@ -436,6 +514,7 @@ int llb_batch_map_set_ds(llb_batch *c, int slot, const llb_point *corner, int mc
             sl.map[k] = dst; sl.map_n[k] = n[k];
         }
         sl.map_set = true; sl.map_dirty = true;
+        if (c->kf_enabled) c->map_from_kf[slot] = 0;
         return (int)LLB_OK;
     });
 }
@@ -449,6 +528,7 @@ int llb_batch_map_set_ds_dev(llb_batch *c, int slot, const void *corner, int mc,
         sl.map[0] = (const float4 *)corner; sl.map[1] = (const float4 *)surf;
         sl.map_n[0] = mc; sl.map_n[1] = ms;
         sl.map_set = true; sl.map_dirty = true;
+        if (c->kf_enabled) c->map_from_kf[slot] = 0;
         return (int)LLB_OK;
     });
 }
@@ -549,6 +629,98 @@ int llb_batch_get_degeneracy(llb_batch *c, int slot, int *deg)
         if (slot < 0 || slot >= c->B || !deg) return (int)LLB_ERR_INVALID;
         LLB_CUDA(cudaStreamSynchronize(c->stream));
         LLB_CUDA(cudaMemcpy(deg, &c->states.p[slot].is_degenerate, sizeof(int), cudaMemcpyDeviceToHost));
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ key-frame stores of the slots
+
+int llb_batch_enable_keyframes(llb_batch *c, int max_raw_map_points, int max_keyframes)
+{
+    return guarded(c, [&]() {
+        if (max_raw_map_points < 1 || max_keyframes < 1) return (int)LLB_ERR_INVALID;
+        if (c->kf_enabled) return (int)LLB_ERR_STATE;
+        const int B = c->B;
+        c->cap_raw = std::max(max_raw_map_points, VoxelFilter::SMALL_MAX + 1);
+        c->max_kf = max_keyframes;
+        c->kfs.resize(B); c->vox.resize(2 * (size_t)B);
+        for (auto &v : c->vox) { v.init(); v.reserve(c->cap_raw); }
+        for (auto &k : c->kfs) k.reserve((size_t)max_keyframes * 3 * c->cap_scan / 2);
+        c->raw_map.ensure((size_t)B * 2 * c->cap_raw); c->ds_map.ensure((size_t)B * 2 * c->cap_raw);
+        c->ds_map_n.ensure((size_t)B * 2);
+        LLB_CUDA(cudaMemset(c->ds_map_n.p, 0, sizeof(int) * 2 * B));
+        c->seg_dev.ensure((size_t)B * 3 * max_keyframes);
+        for (int i = 0; i < RING; i++) c->seg_pin[i].ensure((size_t)B * 3 * max_keyframes);
+        for (auto &g : c->grids) g.job(nullptr, nullptr, c->cap_raw);       // an assembled DS map is bounded by its raw size
+        c->asm_req.resize(B); c->map_from_kf.assign(B, 0);
+        c->kf_enabled = true;
+        LLB_CUDA(cudaDeviceSynchronize());
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_keyframe_add(llb_batch *c, int slot, int *id)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B) return (int)LLB_ERR_INVALID;
+        if (!c->kf_enabled || c->pending || !c->have_results) return (int)LLB_ERR_STATE;
+        const BatchResult &r = c->pin_results.p[slot];       // DS cloud sizes of the slot's last step
+        const int n[3] = { r.ds[0], r.ds[1], r.ds[2] };
+        float4 *dst[3];
+        const int k = c->kfs[slot].add(n, dst);
+        const float4 *ds = c->scan_ds.p + (size_t)slot * 5 * c->cap_scan;
+        const float4 *src[3] = { ds, ds + c->cap_scan, ds + 2 * (size_t)c->cap_scan };
+        for (int j = 0; j < 3; j++)
+            if (n[j] > 0) { c->pending_copy.push_back(BatchCopy{ src[j], dst[j], n[j] }); c->pending_copy_max = std::max(c->pending_copy_max, n[j]); }
+        if (id) *id = k;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_keyframe_count(llb_batch *c, int slot, int *n)
+{
+    if (!c || !n || slot < 0 || slot >= c->B || !c->kf_enabled) return LLB_ERR_INVALID;
+    *n = c->kfs[slot].size();
+    return LLB_OK;
+}
+
+int llb_batch_map_assemble(llb_batch *c, int slot, const int *ids, const float *poses, int n)
+{
+    return guarded(c, [&]() {
+        if (slot < 0 || slot >= c->B || n < 0 || (n > 0 && (!ids || !poses))) return (int)LLB_ERR_INVALID;
+        if (!c->kf_enabled) return (int)LLB_ERR_STATE;
+        if (n > c->max_kf) return (int)LLB_ERR_CAPACITY;
+        size_t rc = 0, rs = 0;
+        for (int k = 0; k < n; k++) {
+            if (ids[k] < 0 || ids[k] >= c->kfs[slot].size()) return (int)LLB_ERR_INVALID;
+            const KeyFrameRec &kr = c->kfs[slot].rec(ids[k]);
+            rc += kr.n[0]; rs += (size_t)kr.n[1] + kr.n[2];
+        }
+        if (rc > (size_t)c->cap_raw || rs > (size_t)c->cap_raw) return (int)LLB_ERR_CAPACITY;
+        llb_batch::AsmReq &rq = c->asm_req[slot];
+        rq.ids.assign(ids, ids + n); rq.poses.assign(poses, poses + 6 * (size_t)n);
+        rq.rc = (int)rc; rq.rs = (int)rs; rq.pending = true;
+        return (int)LLB_OK;
+    });
+}
+
+// which: 0 raw corner map, 1 raw surf map, 2 DS corner map, 3 DS surf map of the slot's last assembled map
+int llb_batch_map_get(llb_batch *c, int slot, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || slot < 0 || slot >= c->B || which < 0 || which > 3) return (int)LLB_ERR_INVALID;
+        if (!c->kf_enabled || !c->map_from_kf[slot]) return (int)LLB_ERR_STATE;
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        int cnt = 0;
+        if (which < 2) cnt = which == 0 ? c->asm_req[slot].rc : c->asm_req[slot].rs;
+        else LLB_CUDA(cudaMemcpy(&cnt, c->ds_map_n.p + 2 * slot + (which - 2), sizeof(int), cudaMemcpyDeviceToHost));
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        const float4 *src = (which < 2 ? c->raw_map.p : c->ds_map.p) + (size_t)(2 * slot + (which & 1)) * c->cap_raw;
+        std::vector<float4> tmp(std::max(cnt, 1));
+        if (cnt > 0) LLB_CUDA(cudaMemcpy(tmp.data(), src, sizeof(float4) * cnt, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < cnt; i++) out[i] = llb_point{ tmp[i].x, tmp[i].y, tmp[i].z, 1.0f, tmp[i].w, 0.f, 0.f, 0.f };
         return (int)LLB_OK;
     });
 }

@@ -9,6 +9,7 @@
 // (float multiply, floorf, float subtract, int cast) and this file is compiled with
 // -fmad=false, so voxel membership, order and centroids are bit-identical to the oracle.
 #include "voxel_dev.cuh"
+#include <cstdlib>
 
 namespace llb {
 
@@ -19,14 +20,20 @@ namespace {
 constexpr int LG_THREADS = 256;
 constexpr int RADIX_MAX_BLOCKS = 256;
 
+// every kernel of the large path serves job blockIdx.y of a device-resident table: one entry for a single filter
+// (llb_ctx), 2B entries when the map filters of a batched step share each launch
+#define LG_JOB(table) const LargeVoxelJob jb = (table)[blockIdx.y]
+
 __global__ void voxel_desc_init_kernel(VoxelDesc *d)
 {
     for (int a = 0; a < 3; a++) { d->mn[a] = INT_MAX; d->mx[a] = INT_MIN; }
 }
 
 __global__ void __launch_bounds__(LG_THREADS)
-voxel_minmax_kernel(SegIn in, VoxelDesc *__restrict__ d)
+voxel_minmax_kernel(const LargeVoxelJob *__restrict__ table)
 {
+    LG_JOB(table);
+    const SegIn in = jb.in; VoxelDesc *__restrict__ d = jb.desc;
     __shared__ float s_red[6][LG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int na = seg_len_a(in), n = na + seg_len_b(in);
@@ -57,8 +64,10 @@ voxel_minmax_kernel(SegIn in, VoxelDesc *__restrict__ d)
     }
 }
 
-__global__ void voxel_setup_kernel(SegIn in, float leaf, VoxelDesc *d)
+__global__ void voxel_setup_kernel(const LargeVoxelJob *__restrict__ table)
 {
+    LG_JOB(table);
+    const SegIn in = jb.in; const float leaf = jb.leaf; VoxelDesc *d = jb.desc;
     const int n = seg_len_a(in) + seg_len_b(in);
     float mn[3], mx[3];
     for (int a = 0; a < 3; a++) {
@@ -75,8 +84,11 @@ __global__ void voxel_setup_kernel(SegIn in, float leaf, VoxelDesc *d)
 }
 
 __global__ void __launch_bounds__(LG_THREADS)
-voxel_keys_kernel(SegIn in, const VoxelDesc *__restrict__ d, unsigned *__restrict__ keys, int *__restrict__ vals)
+voxel_keys_kernel(const LargeVoxelJob *__restrict__ table)
 {
+    LG_JOB(table);
+    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc;
+    unsigned *__restrict__ keys = jb.kA; int *__restrict__ vals = jb.vA;
     const int n = d->n;
     const int na = seg_len_a(in);
     const float inv = d->inv;
@@ -101,9 +113,11 @@ __device__ __forceinline__ void radix_tile(int n, int nblocks, int b, int &lo, i
 }
 
 __global__ void __launch_bounds__(LG_THREADS)
-radix_hist_kernel(const VoxelDesc *__restrict__ d, int shift, const unsigned *__restrict__ kA,
-                  const unsigned *__restrict__ kB, int *__restrict__ hist)
+radix_hist_kernel(const LargeVoxelJob *__restrict__ table, int shift)
 {
+    LG_JOB(table);
+    const VoxelDesc *__restrict__ d = jb.desc; const unsigned *__restrict__ kA = jb.kA, *__restrict__ kB = jb.kB;
+    int *__restrict__ hist = jb.hist;
     if (shift >= d->nbits) return;
     const unsigned *keys = ((shift >> 3) & 1) ? kB : kA;
     __shared__ int s_h[256];
@@ -118,8 +132,13 @@ radix_hist_kernel(const VoxelDesc *__restrict__ d, int shift, const unsigned *__
 
 // exclusive scan of `count` ints in place by ONE block of 1024 threads
 __global__ void __launch_bounds__(1024)
-scan_single_block_kernel(int *__restrict__ data, int count, const VoxelDesc *d, int shift, int *total_out)
+scan_single_block_kernel(const LargeVoxelJob *__restrict__ table, int what, int count, int shift)
 {
+    // what 0: the radix histograms of pass `shift`; what 1: the per-block head counts (total -> output length)
+    LG_JOB(table);
+    int *__restrict__ data = what == 0 ? jb.hist : jb.blk;
+    const VoxelDesc *d = what == 0 ? jb.desc : nullptr;
+    int *total_out = what == 0 ? nullptr : jb.n_out;
     if (d && shift >= 0 && shift >= d->nbits) return;
     __shared__ int s_scan[33];
     const int per = (count + 1023) / 1024;
@@ -133,9 +152,11 @@ scan_single_block_kernel(int *__restrict__ data, int count, const VoxelDesc *d, 
 }
 
 __global__ void __launch_bounds__(LG_THREADS)
-radix_scatter_kernel(const VoxelDesc *__restrict__ d, int shift, unsigned *__restrict__ kA, unsigned *__restrict__ kB,
-                     int *__restrict__ vA, int *__restrict__ vB, const int *__restrict__ hist)
+radix_scatter_kernel(const LargeVoxelJob *__restrict__ table, int shift)
 {
+    LG_JOB(table);
+    const VoxelDesc *__restrict__ d = jb.desc; unsigned *__restrict__ kA = jb.kA, *__restrict__ kB = jb.kB;
+    int *__restrict__ vA = jb.vA, *__restrict__ vB = jb.vB; const int *__restrict__ hist = jb.hist;
     if (shift >= d->nbits) return;
     const bool odd = ((shift >> 3) & 1) != 0;
     const unsigned *kin = odd ? kB : kA; unsigned *kout = odd ? kA : kB;
@@ -208,8 +229,10 @@ __device__ __forceinline__ void sorted_bufs(const VoxelDesc *d, const unsigned *
 constexpr int HEAD_TILE = 1024;
 
 __global__ void __launch_bounds__(HEAD_TILE)
-voxel_heads_kernel(const VoxelDesc *__restrict__ d, const unsigned *kA, const unsigned *kB, int *__restrict__ blk)
+voxel_heads_kernel(const LargeVoxelJob *__restrict__ table)
 {
+    LG_JOB(table);
+    const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB; int *__restrict__ blk = jb.blk;
     const unsigned *k; const int *v;
     sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
     const int n = d->n;
@@ -220,9 +243,11 @@ voxel_heads_kernel(const VoxelDesc *__restrict__ d, const unsigned *kA, const un
 }
 
 __global__ void __launch_bounds__(HEAD_TILE)
-voxel_centroid_kernel(SegIn in, const VoxelDesc *__restrict__ d, const unsigned *kA, const unsigned *kB,
-                      const int *vA, const int *vB, const int *__restrict__ blk, float4 *__restrict__ out)
+voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
+    LG_JOB(table);
+    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB;
+    const int *vA = jb.vA, *vB = jb.vB; const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
     __shared__ int s_scan[33];
     const unsigned *k; const int *v;
     sorted_bufs(d, kA, kB, vA, vB, k, v);
@@ -266,7 +291,7 @@ void VoxelFilter::reserve(int n)
 void VoxelFilter::release()
 {
     desc_.release(); keys_[0].release(); keys_[1].release(); vals_[0].release(); vals_[1].release();
-    hist_.release(); blk_.release();
+    hist_.release(); blk_.release(); job_raw_.release();
 }
 
 int VoxelFilter::run(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t stream)
@@ -300,35 +325,52 @@ int VoxelFilter::run_batch(const VoxelInput *in, const float *leaf, float4 *cons
     return 1;
 }
 
-int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s)
+LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev)
 {
-    const int n = in.upper();
-    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
-    const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, 4096));
-    hist_.ensure((size_t)256 * nblk_radix);
-    const int nblk_head = div_up(n, HEAD_TILE);
-    blk_.ensure(nblk_head + 1);
-    SegIn seg = to_seg(in);
-    int launches = 0;
-    const int grid_stream = std::min(div_up(n, LG_THREADS), 148 * 8);
+    const int n = std::max(in.upper(), 1);
+    reserve(std::max(n, SMALL_MAX + 1));
+    LargeVoxelJob j;
+    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p;
+    j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
+    j.hist = hist_.p; j.blk = blk_.p; j.out = out; j.n_out = n_out_dev;
+    return j;
+}
 
-    voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(seg, desc_.p); launches++;
-    voxel_setup_kernel<<<1, 1, 0, s>>>(seg, leaf, desc_.p); launches++;
-    voxel_keys_kernel<<<grid_stream, LG_THREADS, 0, s>>>(seg, desc_.p, keys_[0].p, vals_[0].p); launches++;
+// `count` jobs of a device-resident table; n_upper bounds the input length of every job
+int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s)
+{
+    const int n = std::max(n_upper, 1);
+    // the histogram layout depends on the radix grid: it must be the same for sizing (reserve) and launching
+    const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, 4096));
+    const int nblk_head = div_up(n, HEAD_TILE);
+    const unsigned ny = (unsigned)std::max(count, 1);
+    const int per = count > 1 ? std::max(8, 148 * 8 / count) : 148 * 8;
+    const dim3 grid_stream(std::min(div_up(n, LG_THREADS), per), ny);
+    int launches = 0;
+    voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
+    voxel_setup_kernel<<<dim3(1, ny), 1, 0, s>>>(table_dev); launches++;
+    voxel_keys_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     for (int pass = 0; pass < 4; pass++) {
         const int shift = pass * 8;
-        radix_hist_kernel<<<nblk_radix, LG_THREADS, 0, s>>>(desc_.p, shift, keys_[0].p, keys_[1].p, hist_.p);
-        scan_single_block_kernel<<<1, 1024, 0, s>>>(hist_.p, 256 * nblk_radix, desc_.p, shift, nullptr);
-        radix_scatter_kernel<<<nblk_radix, LG_THREADS, 0, s>>>(desc_.p, shift, keys_[0].p, keys_[1].p,
-                                                               vals_[0].p, vals_[1].p, hist_.p);
+        radix_hist_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
+        scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 0, 256 * nblk_radix, shift);
+        radix_scatter_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
         launches += 3;
     }
-    voxel_heads_kernel<<<nblk_head, HEAD_TILE, 0, s>>>(desc_.p, keys_[0].p, keys_[1].p, blk_.p); launches++;
-    scan_single_block_kernel<<<1, 1024, 0, s>>>(blk_.p, nblk_head, nullptr, -1, n_out_dev); launches++;
-    voxel_centroid_kernel<<<nblk_head, HEAD_TILE, 0, s>>>(seg, desc_.p, keys_[0].p, keys_[1].p, vals_[0].p,
-                                                          vals_[1].p, blk_.p, out); launches++;
+    voxel_heads_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+    scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
+    voxel_centroid_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
     LLB_CUDA(cudaGetLastError());
     return launches;
+}
+
+int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s)
+{
+    const LargeVoxelJob j = large_job(in, leaf, out, n_out_dev);
+    job_raw_.ensure(sizeof(LargeVoxelJob));
+    // pageable source: the runtime stages these 136 bytes before the call returns, so `j` may die right away
+    LLB_CUDA(cudaMemcpyAsync(job_raw_.p, &j, sizeof(j), cudaMemcpyHostToDevice, s));
+    return launch_large(reinterpret_cast<const LargeVoxelJob *>(job_raw_.p), 1, in.upper(), s);
 }
 
 }  // namespace llb

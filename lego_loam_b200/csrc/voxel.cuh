@@ -25,12 +25,18 @@ struct VoxelDesc {           // device-resident, written by the setup step
     int n_out;
 };
 
+struct LargeVoxelJob;        // one filter of the multi-kernel path (voxel_dev.cuh)
+
 class VoxelFilter {
 public:
     static constexpr int SMALL_MAX = 16384;     // single-CTA path up to this many points
     static constexpr int MAX_BATCH = 4;         // independent small filters sharing one launch
     void init();
     void release();
+    // batched form of the multi-kernel path: large_job() sizes this filter's scratch for the input's upper bound and
+    // returns the job record; a device-resident table of such records is run by ONE set of 18 launches
+    LargeVoxelJob large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev);
+    static int launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s);
     // pre-sizes the scratch of the multi-kernel path for inputs of up to n points (no allocation at run time below n)
     void reserve(int n);
     // out must have room for in.upper() points; n_out_dev receives the output count.
@@ -47,6 +53,7 @@ private:
     DevBuf<int> vals_[2];
     DevBuf<int> hist_;          // radix histograms: 256 bins x nblocks
     DevBuf<int> blk_;           // per-block head counts / offsets
+    DevBuf<unsigned char> job_raw_;
     bool small_attr_set_ = false;
 };
 

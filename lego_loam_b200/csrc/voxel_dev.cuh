@@ -16,6 +16,12 @@ __device__ __forceinline__ float4 seg_load(const SegIn &s, int na, int i)
     return i < na ? __ldg(&s.a[i]) : __ldg(&s.b[i - na]);
 }
 
+struct LargeVoxelJob {       // one filter of the multi-kernel (radix) path: input, parameters, scratch, output
+    SegIn in; float leaf; VoxelDesc *desc;
+    unsigned *kA, *kB; int *vA, *vB; int *hist; int *blk;
+    float4 *out; int *n_out;
+};
+
 inline __host__ SegIn to_seg(const VoxelInput &in)
 {
     SegIn s;

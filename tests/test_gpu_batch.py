@@ -177,3 +177,55 @@ def test_keyframe_store_edge_cases(ctx, cases):
     T, st = ctx.s2m_optimize(c["init"])
     assert st.skipped == 1 and np.array_equal(T, np.asarray(c["init"], np.float32))
     ctx.keyframe_clear()
+
+
+def test_batch_keyframe_stores(ctx, cases):
+    """Per-slot device key-frame stores of the batch engine against the single-context store (which is pinned against
+    the reference's node logic in test_gpu_sequence.py): key-frames saved from the slots' own DS clouds, local maps
+    assembled in different orders, voxel-filtered by the BATCHED multi-kernel path (the context uses the cluster kernel
+    below 16384 points), then a registration against them - raw maps, DS maps and poses bit-identical."""
+    B, K = 2, 6
+    b = api.Batch(0, B, 8192, 120000)
+    with pytest.raises(api.LlbError):
+        b.map_assemble(0, [0], np.zeros((1, 6), np.float32))   # not enabled yet
+    b.enable_keyframes(400000, 16)
+    for k in range(K):
+        for s in range(B):
+            c = cases[(s + k) % len(cases)]
+            b.scan_set(s, c["corner"], c["surf"], c["outlier"]); b.map_set_ds(s, c["mc_ds"], c["ms_ds"])
+        b.register(np.stack([cases[(s + k) % len(cases)]["init"] for s in range(B)]))
+        for s in range(B):
+            assert b.keyframe_add(s) == k
+    orders = [list(range(K)), [4, 0, 5, 2, 1, 3]]
+    rng = np.random.default_rng(3)
+    kposes = [np.concatenate([rng.uniform(-0.03, 0.03, (K, 1)), rng.uniform(-3, 3, (K, 1)), rng.uniform(-0.03, 0.03, (K, 1)),
+                              rng.uniform(-15, 15, (K, 1)), rng.uniform(-0.1, 0.1, (K, 1)), rng.uniform(-15, 15, (K, 1))], 1).astype(np.float32)
+              for _ in range(B)]
+    new = [cases[(s + 2) % len(cases)] for s in range(B)]
+    for s in range(B):
+        b.map_assemble(s, orders[s], kposes[s][orders[s]])
+        b.scan_set(s, new[s]["corner"], new[s]["surf"], new[s]["outlier"])
+    init = np.stack([kposes[s][0] for s in range(B)]).astype(np.float32)
+    T, st = b.register(init)
+    assert b.keyframe_count(0) == K
+    for s in range(B):
+        ctx.keyframe_clear()
+        for k in range(K):
+            c = cases[(s + k) % len(cases)]
+            ctx.scan_set(c["corner"], c["surf"], c["outlier"]); ctx.downsample_current_scan(); ctx.keyframe_add()
+        ctx.map_assemble(orders[s], kposes[s][orders[s]])
+        for which in range(2):
+            assert np.array_equal(b.map_get(s, which).view(np.uint32), ctx.map_get_raw(which).view(np.uint32)), (s, which)
+            assert np.array_equal(b.map_get(s, 2 + which).view(np.uint32), ctx.map_get_ds(which).view(np.uint32)), (s, which)
+        assert b.map_get(s, 1).shape[0] > 16384                 # the surf map is beyond the cluster kernel's range
+        ctx.scan_set(new[s]["corner"], new[s]["surf"], new[s]["outlier"]); ctx.downsample_current_scan()
+        Ts, sts = ctx.s2m_optimize(init[s])
+        assert np.array_equal(T[s].view(np.uint32), Ts.view(np.uint32)), (s, T[s], Ts)
+        assert (st[s].iterations, st[s].skipped, st[s].n_correspondences) == (sts.iterations, sts.skipped, sts.n_correspondences)
+    # the assembled map stays until it is replaced: a second step without a new request registers against it again
+    for s in range(B):
+        b.scan_set(s, new[s]["corner"], new[s]["surf"], new[s]["outlier"])
+    T2, _ = b.register(init)
+    assert np.array_equal(T.view(np.uint32), T2.view(np.uint32))
+    ctx.keyframe_clear()
+    b.close()
