@@ -169,12 +169,13 @@ def run_reference(args):
     return 0
 
 
-def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_sample):
-    """Secondary arm (SURVEY 8(f)-1 + row a2): the mapping cycle with the DEVICE-RESIDENT key-frame store.  Per
-    registration only the new sweep crosses PCIe; the raw local map is assembled from the resident key-frames
-    (transformPointCloud + concatenation, MO:1033-1056), voxel-filtered (MO:1057-1064) and indexed on the device, then
-    downsampleCurrentScan + scan2MapOptimization as in the main arm.  The CPU figure runs the reference's own
-    statements for the same work (its two map voxel filters + downsampleCurrentScan + scan2MapOptimization) on 1 core."""
+def mapping_cycle_arm(api, local, n_slots, n_batches, n_keyframes, steps, warm, cpu_sample):
+    """Secondary arm (SURVEY 8(f)-1 + row a2): the mapping cycle with DEVICE-RESIDENT key-frame stores on the batched
+    engine.  Per registration only the new sweep crosses PCIe; the raw local map of every slot is assembled from its
+    resident key-frames (transformPointCloud + concatenation, MO:1033-1056) by one launch, the 2 x slots map voxel
+    filters (MO:1057-1064) share one set of 18 launches, then index build + downsampleCurrentScan +
+    scan2MapOptimization as in the main arm.  The CPU figure runs the reference's own statements for the same cycle
+    (its two map voxel filters + downsampleCurrentScan + scan2MapOptimization) on 1 core."""
     from lego_loam_b200 import synth
     D = 2
     seq = []
@@ -184,61 +185,63 @@ def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_
         poses, scans = [], []
         for k in range(n_keyframes + 2):
             # key-frames every ~1 m along a gently turning path (the reference thins key poses to 1 m, MO:1011-1012)
-            j = min(k, n_keyframes - 1) if k < n_keyframes else n_keyframes // 2 + (k - n_keyframes)
+            j = k if k < n_keyframes else n_keyframes // 2 + (k - n_keyframes)
             yaw = yaw0 + 0.01 * j
             pose = np.array([0.004 * np.sin(0.3 * j), yaw, 0.004 * np.cos(0.2 * j),
                              -20.0 + 1.0 * j * np.sin(yaw0 + 0.005 * j), 0.0, -25.0 + 1.0 * j * np.cos(yaw0 + 0.005 * j)])
             if k >= n_keyframes:
                 pose[3] += 0.35; pose[5] += 0.2                    # the new sweeps are not on a key-frame
             poses.append(pose.astype(np.float32))
-            scans.append(synth.make_mapping_scan(w, synth.VLP16, pose, seed=9000 + 100 * d + k))
+            sc = synth.make_mapping_scan(w, synth.VLP16, pose, seed=9000 + 100 * d + k)
+            scans.append((api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), sc))
         seq.append((poses, scans))
-    prm = api.default_params(); prm.pin_host_clouds = 1; prm.s2m_max_ctas = 37
-    ctxs = []
-    for s in range(n_ctx):
-        poses, scans = seq[s % D]
-        c = api.Context(local, prm)
-        hold = []                                                 # pinned in place (pin_host_clouds): must outlive the context
+    prm = api.default_params(); prm.pin_host_clouds = 1
+    P = api.Batch.pack
+    per = n_slots // n_batches
+    bts = []
+    for bi in range(n_batches):
+        b = api.Batch(local, per, 8192, 4096, prm)
+        b.enable_keyframes(400000, n_keyframes)
+        slot_seq = [(bi * per + s) % D for s in range(per)]
+        dummy = api.to_pcl(np.zeros((16, 4), np.float32))          # placeholder map for the key-frame collection steps
+        for s in range(per):
+            b.map_set_ds_pcl(s, dummy, dummy)
+        tabs = [tuple(P([seq[d][1][k][j].ctypes.data for d in slot_seq], [seq[d][1][k][j].shape[0] for d in slot_seq])
+                      for j in range(3)) for k in range(n_keyframes + 2)]
         for k in range(n_keyframes):                              # saveKeyFramesAndFactor's cloud part, MO:1443-1453
-            sc = scans[k]
-            h = (api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last)); hold.append(h)
-            c.scan_set_pcl(*h); c.downsample_current_scan(); c.keyframe_add()
-        new = [(api.to_pcl(scans[n_keyframes + i].corner_last), api.to_pcl(scans[n_keyframes + i].surf_last),
-                api.to_pcl(scans[n_keyframes + i].outlier_last),
-                synth.perturb_pose(poses[n_keyframes + i].astype(np.float64), np.random.default_rng(s * 10 + i)).astype(np.float32))
-               for i in range(2)]
-        ctxs.append({"ctx": c, "hold": hold, "new": new, "ids": np.arange(n_keyframes, dtype=np.int32),
-                     "kposes": np.stack(poses[:n_keyframes]).astype(np.float32), "seq": s % D})
-    T = max(1, min(threads, n_ctx))
-    barrier = threading.Barrier(T + 1)
+            b.scan_set_all(*tabs[k], dev=False)
+            b.register(np.zeros((per, 6), np.float32))             # (skipped by the guard MO:1331: only the DS clouds matter)
+            for s in range(per):
+                b.keyframe_add(s)
+        kposes = [np.stack(seq[d][0][:n_keyframes]).astype(np.float32) for d in slot_seq]
+        rng = np.random.default_rng(100 + bi)
+        init = [np.stack([synth.perturb_pose(seq[d][0][n_keyframes + i].astype(np.float64), rng) for d in slot_seq]).astype(np.float32)
+                for i in range(2)]
+        bts.append({"b": b, "tabs": tabs, "kposes": kposes, "init": init, "slot_seq": slot_seq, "dummy": dummy})
+    ids = np.arange(n_keyframes, dtype=np.int32)
+
+    def cycle(bt, i):
+        b = bt["b"]
+        b.scan_set_all(*bt["tabs"][n_keyframes + i % 2], dev=False)    # H2D: the new sweeps only
+        for s in range(per):
+            b.map_assemble(s, ids, bt["kposes"][s])               # resident key-frames -> raw map -> DS map -> index
+        b.register_async(bt["init"][i % 2])
+
+    barrier = threading.Barrier(n_batches + 1)
     out = {}
 
-    def cycle(q, i):
-        c = q["ctx"]
-        cc, ss, oo, init = q["new"][i % 2]
-        c.scan_set_pcl(cc, ss, oo)                                # H2D: the new sweep only
-        c.downsample_current_scan(want_counts=False)
-        c.map_assemble(q["ids"], q["kposes"])                     # resident key-frames -> raw map -> DS map -> index
-        c.s2m_optimize_async(init)
-
-    def worker(tix):
-        mine = ctxs[tix::T]
+    def worker(k):
+        bt = bts[k]
         for i in range(warm):
-            for q in mine:
-                cycle(q, i)
-            for q in mine:
-                q["ctx"].s2m_result()
+            cycle(bt, i); bt["b"].result()
         barrier.wait()
         for i in range(steps):
-            for q in mine:
-                cycle(q, i)
-            for q in mine:
-                res = q["ctx"].s2m_result()
-            if tix == 0:
-                out["T"], out["st"] = res
+            cycle(bt, i); res = bt["b"].result()
+        if k == 0:
+            out["T"], out["st"] = res
         barrier.wait()
 
-    ths = [threading.Thread(target=worker, args=(k,)) for k in range(T)]
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(n_batches)]
     for x in ths:
         x.start()
     barrier.wait()
@@ -247,10 +250,14 @@ def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_
     wall = time.perf_counter() - t0
     for x in ths:
         x.join()
-    # the reference's own statements for the same cycle on 1 core (bounded sample) + pose check
-    q = ctxs[0::T][-1]
-    raw_c, raw_s = q["ctx"].map_get_raw(0), q["ctx"].map_get_raw(1)
-    ds_sizes = (int(q["ctx"].map_get_ds(0).shape[0]), int(q["ctx"].map_get_ds(1).shape[0]))
+    b0 = bts[0]["b"]
+    b0.set_profile(True)
+    cycle(bts[0], steps - 1); b0.result()
+    prof, _ = b0.get_profile()
+    b0.set_profile(False)
+    # the reference's own statements for the same cycle on 1 core (bounded sample) + pose check of slot 0
+    raw_c, raw_s = b0.map_get(0, 0), b0.map_get(0, 1)
+    ds_sizes = (int(b0.map_get(0, 2).shape[0]), int(b0.map_get(0, 3).shape[0]))
     kind, mo = "port", None
     try:
         from oracle import ref_harness
@@ -261,33 +268,37 @@ def mapping_cycle_arm(api, local, n_ctx, n_keyframes, steps, warm, threads, cpu_
     if mo is None:
         import oracle
         oracle.set_trig_mode(0); mo = oracle.MapOptimization()
-    poses, scans = seq[q["seq"]]
+    d0 = bts[0]["slot_seq"][0]
 
     def cpu_cycle(i):
-        sc = scans[n_keyframes + i % 2]
+        sc = seq[d0][1][n_keyframes + i % 2][3]
         mo.set_map_raw(raw_c, raw_s)                              # MO:1057-1064: the two map voxel filters
         mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
-        mo.transformTobeMapped = q["new"][i % 2][3]
+        mo.transformTobeMapped = bts[0]["init"][i % 2][0]
         mo.downsampleCurrentScan()
         mo.scan2MapOptimization()
         return mo.transformTobeMapped
     cpu_cycle(0)
     t0 = time.perf_counter()
     for i in range(cpu_sample):
-        Tc = cpu_cycle(i)
+        cpu_cycle(i)
     cpu_s = time.perf_counter() - t0
-    diff = float(np.max(np.abs(out["T"] - cpu_cycle(steps - 1)))) if "T" in out else None
-    h2d = int(sum(a.nbytes for a in ctxs[0]["new"][0][:3]) + ctxs[0]["kposes"].nbytes + ctxs[0]["ids"].nbytes + 24)
-    for qq in ctxs:
-        qq["ctx"].close()
-    return {"value": n_ctx * steps / wall, "unit": "registrations/s", "contexts": n_ctx, "host_threads": T,
-            "key_frames": n_keyframes, "raw_map_points": [int(raw_c.shape[0]), int(raw_s.shape[0])], "ds_map_points": list(ds_sizes),
-            "h2d_bytes_per_registration": h2d, "ms_per_registration_wall": wall / (n_ctx * steps) * 1e3,
+    diff = float(np.max(np.abs(out["T"][0] - cpu_cycle(steps - 1)))) if "T" in out else None
+    h2d = int(sum(seq[d0][1][n_keyframes][j].nbytes for j in range(3)) + n_keyframes * 28 + 24)
+    st0 = out["st"][0].as_dict() if "st" in out else None
+    for bt in bts:
+        bt["b"].close()
+    return {"value": n_slots * steps / wall, "unit": "registrations/s", "slots": n_slots, "batches": n_batches,
+            "host_threads": n_batches, "key_frames": n_keyframes,
+            "raw_map_points": [int(raw_c.shape[0]), int(raw_s.shape[0])], "ds_map_points": list(ds_sizes),
+            "h2d_bytes_per_registration": h2d, "ms_per_step_wall": wall / steps * 1e3,
+            "stage_ms_per_step": prof, "last_stats_slot0": st0,
             "cpu_1core": {"value": cpu_sample / cpu_s, "ms_per_registration": cpu_s / cpu_sample * 1e3, "kind": kind,
                           "sample": f"{cpu_sample} cycles"},
             "pose_check_max_abs_diff_vs_cpu": diff,
             "note": "registration = local-map assembly from device-resident key-frames + map voxel filters + index + "
-                    "downsampleCurrentScan + scan2MapOptimization; host clouds in (new sweep only), pose out, wall clock"}
+                    "downsampleCurrentScan + scan2MapOptimization on the batched engine; host clouds in (new sweep only), "
+                    "pose out, wall clock; stage_ms: 'unpack' = key-frame copies + assembly + map voxel filters"}
 
 
 def odometry_arm(api, local, reps, cpu_sample):
@@ -549,7 +560,7 @@ def main():
     mc_arm = None
     if args.mapping_cycle and rank == 0:
         try:
-            mc_arm = mapping_cycle_arm(api, local, 16, args.key_frames, max(4, K // 4), 2, 8, 4)
+            mc_arm = mapping_cycle_arm(api, local, 64, 2, args.key_frames, max(4, K // 2), 2, 4)
         except Exception as e:                                # secondary arm: never hides the main line
             mc_arm = {"error": repr(e)}
     od_arm = None
@@ -620,7 +631,7 @@ def main():
                        "timing": "CUDA events, first start to last end over the batch streams (host gaps included), max over ranks",
                        "e2e_host_threads": NB, "pin_host_clouds": 1},
             "e2e": {"value": world * S * K / e2e_s, "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(sum(h2d_reg)), "d2h_bytes_per_step": int(64 * S),
+                    "h2d_bytes_per_step": int(sum(h2d_reg)), "d2h_bytes_per_step": int(72 * S),
                     "ms_per_step": e2e_s / K * 1e3,
                     "note": "scan AND voxel-DS map cross PCIe for every registration (the drop-in signature hands both over); "
                             "PCIe-bound"},

@@ -304,7 +304,7 @@ int enqueue_step(llb_batch *c, const float *T)
     }
     if (nvox > 0)
         c->launches += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
-                                                 std::max(raw_max, c->cap_raw), c->stream);
+                                                 raw_max, c->stream);      // scratch is sized for cap_raw >= raw_max
     prof_mark(c, 0);
     launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream);
     launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream);

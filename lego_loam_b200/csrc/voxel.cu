@@ -242,17 +242,32 @@ voxel_heads_kernel(const LargeVoxelJob *__restrict__ table)
     if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
 }
 
+// points in sorted order: psorted[i] = in[v[i]] (fully parallel gather, coalesced writes), so that the ordered per-voxel
+// sums below walk CONTIGUOUS memory instead of chasing one random 16-byte load per point
+__global__ void __launch_bounds__(LG_THREADS)
+voxel_gather_kernel(const LargeVoxelJob *__restrict__ table)
+{
+    LG_JOB(table);
+    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc;
+    const unsigned *k; const int *v;
+    sorted_bufs(d, jb.kA, jb.kB, jb.vA, jb.vB, k, v);
+    const int n = d->n;
+    const int na = seg_len_a(in);
+    for (int i = blockIdx.x * LG_THREADS + threadIdx.x; i < n; i += gridDim.x * LG_THREADS)
+        jb.psorted[i] = seg_load(in, na, __ldg(&v[i]));
+}
+
 __global__ void __launch_bounds__(HEAD_TILE)
 voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
-    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB;
-    const int *vA = jb.vA, *vB = jb.vB; const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
+    const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB;
+    const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
+    const float4 *__restrict__ ps = jb.psorted;
     __shared__ int s_scan[33];
     const unsigned *k; const int *v;
-    sorted_bufs(d, kA, kB, vA, vB, k, v);
+    sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
     const int n = d->n;
-    const int na = seg_len_a(in);
     const int i = blockIdx.x * HEAD_TILE + threadIdx.x;
     int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
     int total;
@@ -262,7 +277,7 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         int j = i;
         while (j < n && k[j] == cur) {
-            float4 p = seg_load(in, na, v[j]);
+            const float4 p = ps[j];
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             j++;
         }
@@ -283,7 +298,7 @@ void VoxelFilter::init()
 void VoxelFilter::reserve(int n)
 {
     if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
-    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
+    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n); psorted_.ensure(n);
     hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
     blk_.ensure(div_up(n, HEAD_TILE) + 1);
 }
@@ -291,7 +306,7 @@ void VoxelFilter::reserve(int n)
 void VoxelFilter::release()
 {
     desc_.release(); keys_[0].release(); keys_[1].release(); vals_[0].release(); vals_[1].release();
-    hist_.release(); blk_.release(); job_raw_.release();
+    hist_.release(); blk_.release(); job_raw_.release(); psorted_.release();
 }
 
 int VoxelFilter::run(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t stream)
@@ -332,7 +347,7 @@ LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *o
     LargeVoxelJob j;
     j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p;
     j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
-    j.hist = hist_.p; j.blk = blk_.p; j.out = out; j.n_out = n_out_dev;
+    j.hist = hist_.p; j.blk = blk_.p; j.psorted = psorted_.p; j.out = out; j.n_out = n_out_dev;
     return j;
 }
 
@@ -359,6 +374,7 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     }
     voxel_heads_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
+    voxel_gather_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     voxel_centroid_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
     LLB_CUDA(cudaGetLastError());
     return launches;

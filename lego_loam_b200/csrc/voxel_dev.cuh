@@ -18,7 +18,7 @@ __device__ __forceinline__ float4 seg_load(const SegIn &s, int na, int i)
 
 struct LargeVoxelJob {       // one filter of the multi-kernel (radix) path: input, parameters, scratch, output
     SegIn in; float leaf; VoxelDesc *desc;
-    unsigned *kA, *kB; int *vA, *vB; int *hist; int *blk;
+    unsigned *kA, *kB; int *vA, *vB; int *hist; int *blk; float4 *psorted;
     float4 *out; int *n_out;
 };
 

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""A few mapping-cycle steps of the batched engine with device key-frame stores (for ncu launch lists)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lego_loam_b200 import api, synth  # noqa: E402
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    w = synth.make_world(synth.SEED0 + 500)
+    poses, scans = [], []
+    for k in range(K + 1):
+        j = k if k < K else K // 2
+        yaw = 0.4 + 0.01 * j
+        pose = np.array([0.004 * np.sin(0.3 * j), yaw, 0.004 * np.cos(0.2 * j), -20.0 + j * np.sin(0.4 + 0.005 * j), 0.0,
+                         -25.0 + j * np.cos(0.4 + 0.005 * j)])
+        if k == K:
+            pose[3] += 0.35; pose[5] += 0.2
+        poses.append(pose.astype(np.float32))
+        sc = synth.make_mapping_scan(w, synth.VLP16, pose, seed=9000 + k)
+        scans.append((api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last)))
+    b = api.Batch(0, B, 8192, 4096)
+    b.enable_keyframes(400000, K)
+    dummy = api.to_pcl(np.zeros((16, 4), np.float32))
+    for s in range(B):
+        b.map_set_ds_pcl(s, dummy, dummy)
+    for k in range(K):
+        for s in range(B):
+            b.scan_set_pcl(s, *scans[k])
+        b.register(np.zeros((B, 6), np.float32))
+        for s in range(B):
+            b.keyframe_add(s)
+    ids = np.arange(K, dtype=np.int32); kp = np.stack(poses[:K])
+    init = np.stack([synth.perturb_pose(poses[K].astype(np.float64), np.random.default_rng(s)) for s in range(B)]).astype(np.float32)
+    b.set_profile(True)
+    for i in range(steps):
+        for s in range(B):
+            b.scan_set_pcl(s, *scans[K]); b.map_assemble(s, ids, kp)
+        T, st = b.register(init)
+    print("iters", [x.iterations for x in st][:4], "device_ms", st[0].device_ms, b.get_profile()[0])
+    b.close()
+
+
+if __name__ == "__main__":
+    main()
