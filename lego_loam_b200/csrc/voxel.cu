@@ -257,6 +257,10 @@ voxel_gather_kernel(const LargeVoxelJob *__restrict__ table)
         jb.psorted[i] = seg_load(in, na, __ldg(&v[i]));
 }
 
+// GATHERED: the points were put into sorted order by voxel_gather_kernel (batched launches: thousands of segment walks
+// in flight, contiguous reads pay); otherwise each walk fetches its points through the sorted index list (one filter
+// alone: one launch less on the latency path)
+template <bool GATHERED>
 __global__ void __launch_bounds__(HEAD_TILE)
 voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
@@ -264,9 +268,11 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
     const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB;
     const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
     const float4 *__restrict__ ps = jb.psorted;
+    const SegIn in = jb.in;
+    const int na = seg_len_a(in);
     __shared__ int s_scan[33];
     const unsigned *k; const int *v;
-    sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
+    sorted_bufs(d, kA, kB, jb.vA, jb.vB, k, v);
     const int n = d->n;
     const int i = blockIdx.x * HEAD_TILE + threadIdx.x;
     int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
@@ -277,7 +283,7 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         int j = i;
         while (j < n && k[j] == cur) {
-            const float4 p = ps[j];
+            const float4 p = GATHERED ? ps[j] : seg_load(in, na, v[j]);
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             j++;
         }
@@ -374,8 +380,12 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     }
     voxel_heads_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
-    voxel_gather_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
-    voxel_centroid_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+    if (count > 1) {
+        voxel_gather_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
+        voxel_centroid_kernel<true><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+    } else {
+        voxel_centroid_kernel<false><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+    }
     LLB_CUDA(cudaGetLastError());
     return launches;
 }
