@@ -10,6 +10,7 @@
 // -fmad=false, so voxel membership, order and centroids are bit-identical to the oracle.
 #include "voxel_dev.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace llb {
 
@@ -312,7 +313,8 @@ void VoxelFilter::reserve(int n)
 void VoxelFilter::release()
 {
     desc_.release(); keys_[0].release(); keys_[1].release(); vals_[0].release(); vals_[1].release();
-    hist_.release(); blk_.release(); job_raw_.release(); psorted_.release();
+    hist_.release(); blk_.release(); job_raw_.release(); psorted_.release(); job_pin_.release();
+    if (job_ev_) { cudaEventDestroy(job_ev_); job_ev_ = nullptr; }
 }
 
 int VoxelFilter::run(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t stream)
@@ -394,8 +396,12 @@ int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n
 {
     const LargeVoxelJob j = large_job(in, leaf, out, n_out_dev);
     job_raw_.ensure(sizeof(LargeVoxelJob));
-    // pageable source: the runtime stages these 136 bytes before the call returns, so `j` may die right away
-    LLB_CUDA(cudaMemcpyAsync(job_raw_.p, &j, sizeof(j), cudaMemcpyHostToDevice, s));
+    job_pin_.ensure(sizeof(LargeVoxelJob));
+    if (!job_ev_) LLB_CUDA(cudaEventCreateWithFlags(&job_ev_, cudaEventDisableTiming));
+    else LLB_CUDA(cudaEventSynchronize(job_ev_));            // the previous upload has left the pinned record (long ago)
+    std::memcpy(job_pin_.p, &j, sizeof(j));
+    LLB_CUDA(cudaMemcpyAsync(job_raw_.p, job_pin_.p, sizeof(j), cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaEventRecord(job_ev_, s));
     return launch_large(reinterpret_cast<const LargeVoxelJob *>(job_raw_.p), 1, in.upper(), s);
 }
 

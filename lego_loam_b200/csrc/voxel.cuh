@@ -54,6 +54,8 @@ private:
     DevBuf<int> hist_;          // radix histograms: 256 bins x nblocks
     DevBuf<int> blk_;           // per-block head counts / offsets
     DevBuf<unsigned char> job_raw_;
+    PinnedBuf<unsigned char> job_pin_;
+    cudaEvent_t job_ev_ = nullptr;
     DevBuf<float4> psorted_;    // points in sorted order (multi-kernel path)
     bool small_attr_set_ = false;
 };
