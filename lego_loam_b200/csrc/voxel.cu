@@ -227,9 +227,11 @@ __device__ __forceinline__ void sorted_bufs(const VoxelDesc *d, const unsigned *
     v = (passes & 1) ? vB : vA;
 }
 
-constexpr int HEAD_TILE = 1024;
+constexpr int HEAD_TILE = 1024;         // one filter alone: few, large CTAs (short block-count scan)
+constexpr int HEAD_TILE_BATCH = 256;    // batched: small CTAs, 8 resident per SM overlap the load -> scan -> walk chains
 
-__global__ void __launch_bounds__(HEAD_TILE)
+template <int TILE>
+__global__ void __launch_bounds__(TILE)
 voxel_heads_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
@@ -237,7 +239,7 @@ voxel_heads_kernel(const LargeVoxelJob *__restrict__ table)
     const unsigned *k; const int *v;
     sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
     const int n = d->n;
-    const int i = blockIdx.x * HEAD_TILE + threadIdx.x;
+    const int i = blockIdx.x * TILE + threadIdx.x;
     int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
     int cnt = __syncthreads_count(head);
     if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
@@ -261,8 +263,8 @@ voxel_gather_kernel(const LargeVoxelJob *__restrict__ table)
 // GATHERED: the points were put into sorted order by voxel_gather_kernel (batched launches: thousands of segment walks
 // in flight, contiguous reads pay); otherwise each walk fetches its points through the sorted index list (one filter
 // alone: one launch less on the latency path)
-template <bool GATHERED>
-__global__ void __launch_bounds__(HEAD_TILE)
+template <bool GATHERED, int TILE>
+__global__ void __launch_bounds__(TILE)
 voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
@@ -275,7 +277,7 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
     const unsigned *k; const int *v;
     sorted_bufs(d, kA, kB, jb.vA, jb.vB, k, v);
     const int n = d->n;
-    const int i = blockIdx.x * HEAD_TILE + threadIdx.x;
+    const int i = blockIdx.x * TILE + threadIdx.x;
     int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
     int total;
     int rank = blk[blockIdx.x] + block_excl_scan(head, s_scan, total);
@@ -307,7 +309,7 @@ void VoxelFilter::reserve(int n)
     if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
     keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n); psorted_.ensure(n);
     hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
-    blk_.ensure(div_up(n, HEAD_TILE) + 1);
+    blk_.ensure(div_up(n, HEAD_TILE_BATCH) + 1);
 }
 
 void VoxelFilter::release()
@@ -365,7 +367,8 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     const int n = std::max(n_upper, 1);
     // the histogram layout depends on the radix grid: it must be the same for sizing (reserve) and launching
     const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, 4096));
-    const int nblk_head = div_up(n, HEAD_TILE);
+    const int head_tile = count > 1 ? HEAD_TILE_BATCH : HEAD_TILE;
+    const int nblk_head = div_up(n, head_tile);
     const unsigned ny = (unsigned)std::max(count, 1);
     const int per = count > 1 ? std::max(8, 148 * 8 / count) : 148 * 8;
     const dim3 grid_stream(std::min(div_up(n, LG_THREADS), per), ny);
@@ -380,13 +383,15 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
         radix_scatter_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
         launches += 3;
     }
-    voxel_heads_kernel<<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+    if (count > 1) voxel_heads_kernel<HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev);
+    else voxel_heads_kernel<HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev);
+    launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
     if (count > 1) {
         voxel_gather_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
-        voxel_centroid_kernel<true><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+        voxel_centroid_kernel<true, HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev); launches++;
     } else {
-        voxel_centroid_kernel<false><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
+        voxel_centroid_kernel<false, HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
     }
     LLB_CUDA(cudaGetLastError());
     return launches;
