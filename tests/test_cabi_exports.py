@@ -61,3 +61,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "llo.h" not in txt, f
+
+
+def test_batch_engine_needs_a_device_too():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lego_loam_b200 import api
+    with pytest.raises(api.LlbError) as e:
+        api.Batch(0, 4, 8192, 100000)
+    assert e.value.status == api.LLB_ERR_NO_DEVICE
