@@ -644,7 +644,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "traffic_source": "ncu --set full captures of both kernels, profiles/r01c_traffic.json (same workload)",
-                         "kernel": "batch_knn_kernel + batch_fit_kernel (K3+K4 of one LM iteration over all slots of a batch)",
+                         "kernel": "batch_knn3_kernel + batch_fit_kernel (K3+K4 of one LM iteration over all slots of a batch)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "ms_per_launch": ms_launch, "alg_bytes_per_launch": alg_bytes_launch,
                          "slots_per_launch": nb0, "stage_ms_per_step": prof_acc, "geometry": geo,
