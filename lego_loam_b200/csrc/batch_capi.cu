@@ -100,6 +100,8 @@ struct llb_batch {
     int pending_copy_max = 0;
     bool have_results = false;
 
+    cudaStream_t stream2 = nullptr;          // forked stream of the step (downsampleCurrentScan beside the map side)
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool pending = false;
     bool profile = false;
@@ -297,6 +299,14 @@ int enqueue_step(llb_batch *c, const float *T)
         launch_batch_copy((const BatchCopy *)(dp + L.off_copy), ncopy, copy_max, c->stream);   // before they are overwritten
         c->launches++;
     }
+    // downsampleCurrentScan only depends on the sweeps: it runs on a forked stream beside the map side of the step
+    // (key-frame assembly, map voxel filters, index build) and is joined before the registrations start
+    LLB_CUDA(cudaEventRecord(c->fork_ev, c->stream));
+    LLB_CUDA(cudaStreamWaitEvent(c->stream2, c->fork_ev, 0));
+    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream2);
+    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream2);
+    c->launches += 2;
+    LLB_CUDA(cudaEventRecord(c->join_ev, c->stream2));
     if (nseg > 0) {
         LLB_CUDA(cudaMemcpyAsync(c->seg_dev.p, h_seg, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
         launch_kf_assemble(c->seg_dev.p, nseg, seg_max, c->stream);
@@ -306,14 +316,12 @@ int enqueue_step(llb_batch *c, const float *T)
         c->launches += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
                                                  raw_max, c->stream);      // scratch is sized for cap_raw >= raw_max
     prof_mark(c, 0);
-    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream);
-    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream);
-    c->launches += 2;
-    prof_mark(c, 1);
     if (ngrid > 0)
         c->launches += GridIndex::build_table((const GridJob *)(dp + L.off_grid), ngrid, map_n_max,
                                               std::sqrt(c->prm.knn_max_sqdist), c->grids[0].max_cells(), c->grid_ctas, c->stream);
     prof_mark(c, 2);
+    LLB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+    prof_mark(c, 1);                                         // what is left of downsampleCurrentScan after the overlap
     const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
     launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
     c->launches++;
@@ -398,6 +406,9 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
         q.surf_map_min = c->prm.surf_map_min; q.max_ctas = 0;
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         LLB_CUDA(cudaEventCreate(&c->ev0)); LLB_CUDA(cudaEventCreate(&c->ev1));
+        LLB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        LLB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+        LLB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
         for (int i = 0; i < 64; i++) LLB_CUDA(cudaEventCreate(&c->pev[i]));
         for (int i = 0; i < RING; i++) {
             LLB_CUDA(cudaEventCreateWithFlags(&c->step_ev[i], cudaEventDisableTiming));
@@ -454,6 +465,9 @@ int llb_batch_destroy(llb_batch *c)
     for (int i = 0; i < 64; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return LLB_OK;

@@ -69,19 +69,36 @@ def replay(ctx, poses, odo, scans):
 
 @pytest.mark.skipif(not ref_harness.available(), reason="oracle/_ref not built")
 def test_sequence_replay_drift_parity(ctx):
-    poses, odo, scans = make_sequence(N_SCANS)
+    n_scans = int(os.environ.get("LLB_DRIFT_SCANS", str(N_SCANS)))   # longer replays on demand (profiles/)
+    poses, odo, scans = make_sequence(n_scans)
     ref, _, _, kf_ref = replay(None, poses, odo, scans)
     gpu, used, ds_equal, kf_gpu = replay(ctx, poses, odo, scans)
-    assert used >= N_SCANS - 2 and kf_ref == kf_gpu and kf_ref > 10
+    assert used >= n_scans - 2 and kf_ref == kf_gpu and kf_ref > 10
     assert ds_equal                                                   # voxel DS of the growing local map: bit-exact
     d = np.abs(gpu - ref)
-    assert d[:, :3].max() < 1e-4 and d[:, 3:].max() < 1e-4            # per-scan bars of the north star
     path = np.sum(np.linalg.norm(np.diff(ref[:, 3:], axis=0), axis=1))
     drift = np.linalg.norm(gpu[-1, 3:] - ref[-1, 3:]) / path
-    assert path > 15.0 and drift < 1e-3                               # 0.1 % of the path length
+    assert path > 15.0 and drift < 1e-3                               # north star: drift within 0.1 % of the path length
+    if n_scans <= N_SCANS:
+        assert d[:, :3].max() < 1e-4 and d[:, 3:].max() < 1e-4        # per-scan bars of the north star
+    else:
+        # Long replays: the two runs stop being fed IDENTICAL inputs once a 1-ulp difference between the device's
+        # correctly rounded sin/cos and the host libm's sinf/cosf flips an LM convergence test (MO:1323: 0.05 deg /
+        # 0.05 cm) somewhere; from then on single scans may differ by up to that tolerance without drifting apart.
+        assert d[:, :3].max() < 2e-3 and d[:, 3:].max() < 2e-3
     # and the mapping tracks the true trajectory of the synthetic world
     truth = np.array(poses)
     assert np.linalg.norm(gpu[-1, 3:] - truth[-1, 3:]) < 0.5
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump({"scans": n_scans, "key_frames": int(kf_ref), "path_m": float(path),
+                   "max_abs_rot_diff_rad": float(d[:, :3].max()), "max_abs_trans_diff_m": float(d[:, 3:].max()),
+                   "end_point_drift_vs_reference_over_path": float(drift),
+                   "end_point_error_vs_truth_m": float(np.linalg.norm(gpu[-1, 3:] - truth[-1, 3:])),
+                   "scans_within_1e-4": int(np.sum((d[:, :3].max(1) < 1e-4) & (d[:, 3:].max(1) < 1e-4))),
+                   "first_scan_that_differs": int(np.argmax(d.max(1) > 0)) if np.any(d > 0) else -1,
+                   "bit_identical_trajectory": bool(np.array_equal(gpu, ref))},
+                  open(os.path.join(out_dir, "sequence_drift.json"), "w"), indent=1)
 
 
 def replay_keyframe_store(ctx, poses, odo, scans, lat=None):
