@@ -319,6 +319,22 @@ def odometry_arm(api, local, reps, cpu_sample):
         if i >= 3:
             wall_ms.append((time.perf_counter() - t0) * 1e3); dev_ms.append(s0.device_ms)
     c.close()
+    # throughput form: 64 sweep pairs per launch on the batched engine (one persistent CTA per pair)
+    NBO = 64
+    b = api.Batch(local, NBO, 8192, 64)
+    pcl = tuple(api.to_pcl(x) for x in (od.corner_last, od.surf_last, od.corner_sharp, od.surf_flat))
+    bt_wall = []
+    for i in range(reps + 3):
+        t0 = time.perf_counter()
+        for s in range(NBO):
+            b._ck(api.lib().llb_batch_odom_set(b._h, s, api._vp(pcl[0]), pcl[0].shape[0], api._vp(pcl[1]), pcl[1].shape[0],
+                                               api._vp(pcl[2]), pcl[2].shape[0], api._vp(pcl[3]), pcl[3].shape[0]))
+        Tb, b0, b1 = b.odom_optimize(np.zeros((NBO, 6), np.float32))
+        if i >= 3:
+            bt_wall.append((time.perf_counter() - t0) * 1e3)
+    batch_dev_ms = float(b0[0].device_ms)
+    batch_equal = bool(np.array_equal(Tb[0], np.asarray(T, np.float32)) and np.array_equal(Tb[NBO - 1], np.asarray(T, np.float32)))
+    b.close()
     kind, fa = "port", None
     try:
         from oracle import ref_harness
@@ -347,6 +363,9 @@ def odometry_arm(api, local, reps, cpu_sample):
                          "corner_last": int(od.corner_last.shape[0]), "surf_last": int(od.surf_last.shape[0])},
             "cpu_1core": {"ms_per_scan": cpu_ms, "kind": kind, "sample": f"{cpu_sample} calls"},
             "pose_max_abs_diff_vs_cpu": float(np.max(np.abs(np.asarray(T) - np.asarray(Tc)))),
+            "batched": {"pairs_per_launch": NBO, "ms_per_launch_device": batch_dev_ms,
+                        "pairs_per_s_e2e_host": NBO / (float(np.median(bt_wall)) * 1e-3),
+                        "equal_to_single": batch_equal},
             "note": "updateTransformation (FA:1666-1695) of one VLP-16 sweep pair: one persistent CTA on the device"}
 
 

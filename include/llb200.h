@@ -287,6 +287,13 @@ int  llb_batch_keyframe_count(llb_batch *b, int slot, int *n);
 int  llb_batch_map_assemble(llb_batch *b, int slot, const int *ids, const float *poses, int n);
 /* which: 0 / 1 raw corner / surf map, 2 / 3 DS corner / surf map of the slot's last assembled map (parity checks) */
 int  llb_batch_map_get(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
+/* ---- featureAssociation of the slots: llb_odom_set_last + llb_odom_set_features + llb_odom_optimize with a leading slot
+ * index; updateTransformation (FA:1666-1695) of ALL slots is one launch (one persistent CTA per slot).  T: n_slots x 6
+ * transformCur in/out; stats arrays of n_slots entries or NULL.  isDegenerate / matP and the neighbour indices kept
+ * between iterations persist per slot, as in the reference. */
+int  llb_batch_odom_set(llb_batch *b, int slot, const llb_point *corner_last, int ncl, const llb_point *surf_last, int nsl,
+                        const llb_point *corner_sharp, int nsharp, const llb_point *surf_flat, int nflat);
+int  llb_batch_odom_optimize(llb_batch *b, float *T, llb_stats *stats_surf, llb_stats *stats_corner);
 /* per-stage CUDA-event times of the last step when enabled: ms[6] = {host-cloud unpack, downsampleCurrentScan,
  * index build, kNN kernels, fit kernels, LM-step + prepare + collect kernels}; geometry[4] = {kNN CTAs per slot,
  * fit CTAs per slot, index-build CTAs per map, query capacity per slot} */

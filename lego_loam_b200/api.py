@@ -74,7 +74,7 @@ EXPORTS = [
     "llb_batch_map_set_ds_dev", "llb_batch_scan_set_all", "llb_batch_map_set_ds_all", "llb_batch_scan_set_dev_all",
     "llb_batch_map_set_ds_dev_all", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
     "llb_batch_enable_keyframes", "llb_batch_keyframe_add", "llb_batch_keyframe_count", "llb_batch_map_assemble",
-    "llb_batch_map_get", "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
+    "llb_batch_map_get", "llb_batch_odom_set", "llb_batch_odom_optimize", "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
 ]
 
 _lib = None
@@ -564,6 +564,22 @@ class Batch:
         out = np.zeros((max(n.value, 1), 8), np.float32)
         self._ck(lib().llb_batch_map_get(self._h, slot, which, _vp(out), n.value, ctypes.byref(n)))
         return from_pcl(out[:n.value])
+
+    # ---- featureAssociation of the slots
+    def odom_set(self, slot: int, corner_last, surf_last, corner_sharp, surf_flat):
+        arrs = tuple(to_pcl(x) for x in (corner_last, surf_last, corner_sharp, surf_flat))
+        self._keep[("odom", slot)] = arrs
+        args = []
+        for a in arrs:
+            args += [_vp(a), a.shape[0]]
+        self._ck(lib().llb_batch_odom_set(self._h, slot, *args))
+
+    def odom_optimize(self, T):
+        """T: (n_slots, 6) transformCur -> (poses, [surf Stats], [corner Stats])"""
+        t = np.ascontiguousarray(T, np.float32).reshape(self.n_slots, 6).copy()
+        s0 = (Stats * self.n_slots)(); s1 = (Stats * self.n_slots)()
+        self._ck(lib().llb_batch_odom_optimize(self._h, _fp(t), s0, s1))
+        return t, list(s0), list(s1)
 
     def get_degeneracy(self, slot: int) -> bool:
         d = ctypes.c_int(0)

@@ -3,6 +3,7 @@
 // No CPU fallback: llb_batch_create fails with LLB_ERR_NO_DEVICE without an sm_100 device.
 #include "../../include/llb200.h"
 #include "batch.cuh"
+#include "odom.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -100,6 +101,20 @@ struct llb_batch {
     int pending_copy_max = 0;
     bool have_results = false;
 
+    // featureAssociation of the slots (llb_batch_odom_*): one persistent CTA per slot in one launch
+    bool od_ready = false;
+    OdomParams oprm{};
+    DevBuf<float4> od_clouds;                // [B][4][cap_scan]: cornerLast, surfLast, cornerPointsSharp, surfPointsFlat
+    DevBuf<float> od_raw;                    // [B][4][cap_scan * 8]
+    DevBuf<float> od_ind;                    // [B][5 * cap_scan]
+    DevBuf<OdomState> od_states;
+    PinnedBuf<OdomState> od_pin_states;
+    DevBuf<OdomBatchJob> od_jobs_dev; PinnedBuf<OdomBatchJob> od_jobs_pin;
+    DevBuf<BatchUnpack> od_unp_dev; PinnedBuf<BatchUnpack> od_unp_pin;
+    DevBuf<float> od_poses_dev; PinnedBuf<float> od_poses_pin;
+    std::vector<int> od_n;                   // [B][4] lengths; -1 = not set
+    std::vector<BatchUnpack> od_pending; int od_pending_max = 0;
+
     cudaStream_t stream2 = nullptr;          // forked stream of the step (downsampleCurrentScan beside the map side)
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -152,7 +167,8 @@ bool ensure_registered(llb_batch *c, const void *p, size_t bytes)
 }
 
 // host cloud (32 B stride) -> raw device slice (async DMA) + a pending unpack job into dst
-void upload(llb_batch *c, int stage_id, const llb_point *src, int n, float *raw_dev, float4 *dst)
+void upload(llb_batch *c, int stage_id, const llb_point *src, int n, float *raw_dev, float4 *dst,
+            std::vector<BatchUnpack> *list = nullptr, int *list_max = nullptr)
 {
     if (n <= 0) return;
     const size_t bytes = (size_t)n * sizeof(llb_point);
@@ -166,6 +182,7 @@ void upload(llb_batch *c, int stage_id, const llb_point *src, int n, float *raw_
         LLB_CUDA(cudaEventRecord(c->stage_ev[stage_id], c->stream));
         c->stage_busy[stage_id] = 1;
     }
+    if (list) { list->push_back(BatchUnpack{ raw_dev, dst, n }); *list_max = std::max(*list_max, n); return; }
     c->pending_unpack.push_back(BatchUnpack{ raw_dev, dst, n });
     c->pending_unpack_max = std::max(c->pending_unpack_max, n);
 }
@@ -434,7 +451,7 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
         c->grids.resize(2 * (size_t)B);
         for (auto &g : c->grids) { g.init(cells); g.job(nullptr, nullptr, c->cap_map); }
         c->slots.resize(B);
-        c->stage.resize((size_t)B * 5); c->stage_ev.assign((size_t)B * 5, nullptr); c->stage_busy.assign((size_t)B * 5, 0);
+        c->stage.resize((size_t)B * 9); c->stage_ev.assign((size_t)B * 9, nullptr); c->stage_busy.assign((size_t)B * 9, 0);
         for (auto &e : c->stage_ev) LLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         launch_batch_state_init(c->states.p, B, c->stream);
         LLB_CUDA(cudaDeviceSynchronize());
@@ -456,6 +473,9 @@ int llb_batch_destroy(llb_batch *c)
     c->results.release(); c->pin_results.release(); c->step_dev.release();
     for (int i = 0; i < RING; i++) { c->step_pin[i].release(); if (c->step_ev[i]) cudaEventDestroy(c->step_ev[i]); }
     for (auto &g : c->grids) g.release();
+    c->od_clouds.release(); c->od_raw.release(); c->od_ind.release(); c->od_states.release(); c->od_pin_states.release();
+    c->od_jobs_dev.release(); c->od_jobs_pin.release(); c->od_unp_dev.release(); c->od_unp_pin.release();
+    c->od_poses_dev.release(); c->od_poses_pin.release();
     for (auto &k : c->kfs) k.release();
     for (auto &v : c->vox) v.release();
     c->raw_map.release(); c->ds_map.release(); c->ds_map_n.release(); c->seg_dev.release();
@@ -735,6 +755,105 @@ int llb_batch_map_get(llb_batch *c, int slot, int which, llb_point *out, int cap
         std::vector<float4> tmp(std::max(cnt, 1));
         if (cnt > 0) LLB_CUDA(cudaMemcpy(tmp.data(), src, sizeof(float4) * cnt, cudaMemcpyDeviceToHost));
         for (int i = 0; i < cnt; i++) out[i] = llb_point{ tmp[i].x, tmp[i].y, tmp[i].z, 1.0f, tmp[i].w, 0.f, 0.f, 0.f };
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ featureAssociation of the slots
+
+namespace {
+void odom_ensure(llb_batch *c)
+{
+    if (c->od_ready) return;
+    const int B = c->B;
+    const llb_params &p = c->prm;
+    c->oprm.nearest_sqdist = p.odom_nearest_sqdist; c->oprm.max_iter = p.odom_max_iterations;
+    c->oprm.min_corr = p.odom_min_correspondences; c->oprm.degeneracy_thresh = p.odom_degeneracy_thresh;
+    c->oprm.converge_deg = p.odom_converge_deg; c->oprm.converge_cm = p.odom_converge_cm;
+    c->od_clouds.ensure((size_t)B * 4 * c->cap_scan); c->od_raw.ensure((size_t)B * 4 * c->cap_scan * 8);
+    c->od_ind.ensure((size_t)B * 5 * c->cap_scan);
+    c->od_states.ensure(B); c->od_pin_states.ensure(B);
+    c->od_jobs_dev.ensure(B); c->od_jobs_pin.ensure(B);
+    c->od_unp_dev.ensure((size_t)B * 4); c->od_unp_pin.ensure((size_t)B * 4);
+    c->od_poses_dev.ensure((size_t)B * 6); c->od_poses_pin.ensure((size_t)B * 6);
+    c->od_n.assign((size_t)B * 4, -1);
+    launch_odom_state_init(c->od_states.p, B, c->stream);
+    launch_odom_fill(c->od_ind.p, B * 5 * c->cap_scan, -1.f, c->stream);
+    LLB_CUDA(cudaStreamSynchronize(c->stream));
+    c->od_ready = true;
+}
+}  // namespace
+
+int llb_batch_odom_set(llb_batch *c, int slot, const llb_point *corner_last, int ncl, const llb_point *surf_last, int nsl,
+                       const llb_point *corner_sharp, int nsharp, const llb_point *surf_flat, int nflat)
+{
+    return guarded(c, [&]() {
+        const llb_point *src[4] = { corner_last, surf_last, corner_sharp, surf_flat };
+        const int n[4] = { ncl, nsl, nsharp, nflat };
+        if (slot < 0 || slot >= c->B) return (int)LLB_ERR_INVALID;
+        for (int k = 0; k < 4; k++) {
+            if (n[k] < 0 || (n[k] > 0 && !src[k])) return (int)LLB_ERR_INVALID;
+            if (n[k] > c->cap_scan) return (int)LLB_ERR_CAPACITY;
+        }
+        odom_ensure(c);
+        for (int k = 0; k < 4; k++) {
+            const size_t o = ((size_t)slot * 4 + k) * c->cap_scan;
+            upload(c, c->B * 5 + slot * 4 + k, src[k], n[k], c->od_raw.p + o * 8, c->od_clouds.p + o, &c->od_pending, &c->od_pending_max);
+            c->od_n[(size_t)slot * 4 + k] = n[k];
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_odom_optimize(llb_batch *c, float *T, llb_stats *stats_surf, llb_stats *stats_corner)
+{
+    return guarded(c, [&]() {
+        if (!T) return (int)LLB_ERR_INVALID;
+        if (!c->od_ready || c->pending) return (int)LLB_ERR_STATE;
+        const int B = c->B;
+        for (int s = 0; s < B; s++)
+            for (int k = 0; k < 4; k++) if (c->od_n[(size_t)s * 4 + k] < 0) return (int)LLB_ERR_STATE;
+        for (int s = 0; s < B; s++) {
+            OdomBatchJob &j = c->od_jobs_pin.p[s];
+            const float4 *base = c->od_clouds.p + (size_t)s * 4 * c->cap_scan;
+            j.cornerLast = base; j.surfLast = base + c->cap_scan; j.sharp = base + 2 * (size_t)c->cap_scan;
+            j.flat = base + 3 * (size_t)c->cap_scan;
+            j.ncl = c->od_n[4 * s]; j.nsl = c->od_n[4 * s + 1]; j.nsharp = c->od_n[4 * s + 2]; j.nflat = c->od_n[4 * s + 3];
+            j.ind = c->od_ind.p + (size_t)s * 5 * c->cap_scan; j.cap = c->cap_scan;
+            j.st = c->od_states.p + s;
+            for (int i = 0; i < 6; i++) c->od_poses_pin.p[6 * s + i] = T[6 * s + i];
+        }
+        const int nunp = (int)c->od_pending.size();
+        for (int i = 0; i < nunp; i++) c->od_unp_pin.p[i] = c->od_pending[i];
+        const int unp_max = c->od_pending_max;
+        c->od_pending.clear(); c->od_pending_max = 0;
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->od_jobs_dev.p, c->od_jobs_pin.p, sizeof(OdomBatchJob) * B, cudaMemcpyHostToDevice, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->od_poses_dev.p, c->od_poses_pin.p, sizeof(float) * 6 * B, cudaMemcpyHostToDevice, c->stream));
+        if (nunp > 0) {
+            LLB_CUDA(cudaMemcpyAsync(c->od_unp_dev.p, c->od_unp_pin.p, sizeof(BatchUnpack) * nunp, cudaMemcpyHostToDevice, c->stream));
+            launch_batch_unpack(c->od_unp_dev.p, nunp, unp_max, c->stream);
+            c->launches++;
+        }
+        launch_odom_batch_set_pose(c->od_jobs_dev.p, c->od_poses_dev.p, B, c->stream);
+        launch_odom_batch(c->oprm, c->od_jobs_dev.p, B, c->stream);      // updateTransformation FA:1666-1695 for every slot
+        c->launches += 2;
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->od_pin_states.p, c->od_states.p, sizeof(OdomState) * B, cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        LLB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        for (int s = 0; s < B; s++) {
+            const OdomState &st = c->od_pin_states.p[s];
+            for (int i = 0; i < 6; i++) T[6 * s + i] = st.T[i];
+            for (int w = 0; w < 2; w++) {
+                llb_stats *o = w == 0 ? stats_surf : stats_corner;
+                if (!o) continue;
+                std::memset(&o[s], 0, sizeof(llb_stats));
+                o[s].iterations = st.iters[w]; o[s].converged = st.converged[w]; o[s].n_correspondences = st.n_corr;
+                o[s].is_degenerate = st.is_degenerate; o[s].skipped = st.skipped; o[s].device_ms = ms;
+            }
+        }
         return (int)LLB_OK;
     });
 }

@@ -166,8 +166,8 @@ __device__ int solve3(OdomState *st, const double *sum, int iter, int which, con
 //   P3 thread/feature : line / plane coefficients from the stored indices, weight, Jacobian row -> shared memory
 //   P4 lane k of warp w accumulates product k of the 10 normal-equation terms over rows w, w+32, ...
 // then a fixed-order reduction and the 3x3 LM step by thread 0.
-__global__ void __launch_bounds__(OD_THREADS, 1)
-odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, int iter0)
+__device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData &dat, OdomState *__restrict__ st, int mode,
+                                          int iter0)
 {
     __shared__ double s_acc[OD_NW][OD_ACC];
     __shared__ double s_tot[OD_ACC];
@@ -373,6 +373,28 @@ odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, 
     }
 }
 
+// one sweep pair (llb_ctx)
+__global__ void __launch_bounds__(OD_THREADS, 1)
+odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, int iter0)
+{
+    odom_body(prm, dat, st, mode, iter0);
+}
+
+// B independent sweep pairs, one CTA each (llb_batch): the <= 50 sequential iterations of a pair cannot be spread
+// over more than one CTA, but 148 SMs run 148 pairs side by side
+__global__ void __launch_bounds__(OD_THREADS, 1)
+odom_batch_kernel(OdomParams prm, const OdomBatchJob *__restrict__ jobs)
+{
+    const OdomBatchJob jb = jobs[blockIdx.x];
+    OdomData dat;
+    dat.sharp = jb.sharp; dat.flat = jb.flat; dat.cornerLast = jb.cornerLast; dat.surfLast = jb.surfLast;
+    dat.nsharp = jb.nsharp; dat.nflat = jb.nflat; dat.ncl = jb.ncl; dat.nsl = jb.nsl;
+    dat.cInd1 = jb.ind; dat.cInd2 = jb.ind + jb.cap; dat.sInd1 = jb.ind + 2 * jb.cap; dat.sInd2 = jb.ind + 3 * jb.cap;
+    dat.sInd3 = jb.ind + 4 * jb.cap;
+    dat.dbg_coeff = nullptr; dat.dbg_valid = nullptr;
+    odom_body(prm, dat, jb.st, 0, 0);
+}
+
 __global__ void odom_state_init_kernel(OdomState *st)
 {
     for (int i = 0; i < 6; i++) st->T[i] = 0.f;
@@ -387,6 +409,39 @@ __global__ void fill_float_kernel(float *p, int n, float v)
 }
 
 }  // namespace
+
+void launch_odom_batch(const OdomParams &prm, const OdomBatchJob *jobs_dev, int count, cudaStream_t s)
+{
+    if (count <= 0) return;
+    odom_batch_kernel<<<count, OD_THREADS, 0, s>>>(prm, jobs_dev);
+    LLB_CUDA(cudaGetLastError());
+}
+
+__global__ void odom_batch_set_pose_kernel(const OdomBatchJob *__restrict__ jobs, const float *__restrict__ poses, int count)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    OdomState *st = jobs[b].st;
+    for (int i = 0; i < 6; i++) st->T[i] = poses[6 * b + i];
+}
+
+void launch_odom_batch_set_pose(const OdomBatchJob *jobs_dev, const float *poses_dev, int count, cudaStream_t s)
+{
+    odom_batch_set_pose_kernel<<<div_up(count, 128), 128, 0, s>>>(jobs_dev, poses_dev, count);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_odom_state_init(OdomState *st, int count, cudaStream_t s)
+{
+    for (int i = 0; i < count; i++) odom_state_init_kernel<<<1, 1, 0, s>>>(st + i);
+    LLB_CUDA(cudaGetLastError());
+}
+
+void launch_odom_fill(float *p, int n, float v, cudaStream_t s)
+{
+    fill_float_kernel<<<div_up(n, 256), 256, 0, s>>>(p, n, v);
+    LLB_CUDA(cudaGetLastError());
+}
 
 void OdomSolver::init(const OdomParams &p)
 {

@@ -30,6 +30,18 @@ struct OdomState {               // device-resident, persists across sweeps
     int   more;                  // return value of the last calculateTransformation* (C8)
 };
 
+struct OdomBatchJob {            // one sweep pair of a batched launch (device-resident table entry)
+    const float4 *sharp, *flat, *cornerLast, *surfLast;
+    int nsharp, nflat, ncl, nsl;
+    float *ind;                  // 5 x cap floats: cInd1, cInd2, sInd1, sInd2, sInd3 (kept between sweeps, C3 / C4)
+    int cap;
+    OdomState *st;               // T in / out, isDegenerate / matP persist per slot
+};
+void launch_odom_batch(const OdomParams &prm, const OdomBatchJob *jobs_dev, int count, cudaStream_t s);
+void launch_odom_batch_set_pose(const OdomBatchJob *jobs_dev, const float *poses_dev, int count, cudaStream_t s);
+void launch_odom_state_init(OdomState *st, int count, cudaStream_t s);
+void launch_odom_fill(float *p, int n, float v, cudaStream_t s);
+
 class OdomSolver {
 public:
     void init(const OdomParams &p);

@@ -229,3 +229,36 @@ def test_batch_keyframe_stores(ctx, cases):
     assert np.array_equal(T.view(np.uint32), T2.view(np.uint32))
     ctx.keyframe_clear()
     b.close()
+
+
+def test_batch_odometry_matches_single_and_oracle(ctx):
+    """updateTransformation (FA:1666-1695) of several slots in ONE launch against the single-context path and the
+    oracle: poses bit-identical (correctly rounded trig), iteration counts equal; a second sweep on the same slots
+    re-uses the per-slot state exactly like the context does (isDegenerate / matP, C6)."""
+    from tests.test_gpu_parity import _odom_case
+    ods = [_odom_case(s) for s in (1, 2, 3)]
+    B = len(ods)
+    b = api.Batch(0, B, 8192, 1000)
+    with pytest.raises(api.LlbError):
+        b.odom_optimize(np.zeros((B, 6), np.float32))              # nothing set
+    for rep in range(2):
+        for s, od in enumerate(ods):
+            b.odom_set(s, od.corner_last, od.surf_last, od.corner_sharp, od.surf_flat)
+        T, s0, s1 = b.odom_optimize(np.zeros((B, 6), np.float32))
+        for s, od in enumerate(ods):
+            c1 = api.Context(0)
+            for _ in range(rep + 1):                               # same history as the slot
+                c1.odom_set_last(od.corner_last, od.surf_last); c1.odom_set_features(od.corner_sharp, od.surf_flat)
+                Ts, t0, t1 = c1.odom_optimize(np.zeros(6, np.float32))
+            c1.close()
+            assert np.array_equal(T[s].view(np.uint32), Ts.view(np.uint32)), (rep, s, T[s], Ts)
+            assert (s0[s].iterations, s1[s].iterations) == (t0.iterations, t1.iterations)
+            if rep == 0:
+                oracle.set_trig_mode(1)
+                fa = oracle.FeatureAssociation()
+                fa.set_last(od.corner_last, od.surf_last, force=True); fa.set_features(od.corner_sharp, od.surf_flat)
+                fa.transformCur = np.zeros(6, np.float32)
+                fa.updateTransformation()
+                oracle.set_trig_mode(0)
+                assert np.array_equal(T[s].view(np.uint32), np.asarray(fa.transformCur, np.float32).view(np.uint32))
+    b.close()
