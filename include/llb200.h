@@ -193,6 +193,7 @@ int llb_odom_get_degeneracy(llb_ctx *ctx, int *is_degenerate, float matP[9]);
 /* ---- device-resident family (inputs already in HBM as float4 {x,y,z,intensity}) ---- */
 int llb_map_set_ds_dev(llb_ctx *ctx, const void *corner_ds_f4, int mc, const void *surf_ds_f4, int ms);
 int llb_map_set_raw_dev(llb_ctx *ctx, const void *corner_f4, int rc, const void *surf_f4, int rs);
+/* the sweep clouds are borrowed, not copied: keep them valid and unchanged until the registration has finished */
 int llb_scan_set_dev(llb_ctx *ctx, const void *corner_f4, int nc, const void *surf_f4, int ns,
                      const void *outlier_f4, int no);
 /* pose in/out in device memory (6 floats); nothing is copied to the host */

@@ -31,6 +31,7 @@ __global__ void unpack_points_kernel(const float *__restrict__ src32, int n, flo
 
 struct Cloud {                    // device cloud with a device-resident length
     DevBuf<float4> pts;
+    const float4 *view = nullptr; // where the points are: pts.p (uploaded from the host) or the caller's device memory
     int n_host = 0;               // exact length when known on the host, else upper bound
     bool exact = true;
 };
@@ -198,6 +199,7 @@ void upload_cloud(llb_ctx *c, int slot, const llb_point *src, int n, DevBuf<floa
 void set_cloud(llb_ctx *c, int slot, Cloud &cl, const llb_point *src, int n)
 {
     upload_cloud(c, slot, src, n, cl.pts);
+    cl.view = cl.pts.p;
     cl.n_host = n; cl.exact = true;
 }
 
@@ -266,9 +268,9 @@ void downsample_scan(llb_ctx *c)
     c->cornerLastDS.ensure(std::max(nc, 1)); c->surfLastDS.ensure(std::max(ns, 1));
     c->outlierLastDS.ensure(std::max(no, 1)); c->surfTotalLastDS.ensure(std::max(ns + no, 1));
     VoxelInput in[3];
-    in[0].a = c->cornerLast.pts.p; in[0].na = nc;
-    in[1].a = c->surfLast.pts.p; in[1].na = ns;
-    in[2].a = c->outlierLast.pts.p; in[2].na = no;
+    in[0].a = c->cornerLast.view; in[0].na = nc;
+    in[1].a = c->surfLast.view; in[1].na = ns;
+    in[2].a = c->outlierLast.view; in[2].na = no;
     const float leaf[3] = { c->prm.corner_leaf, c->prm.surf_leaf, c->prm.outlier_leaf };
     float4 *out[3] = { c->cornerLastDS.p, c->surfLastDS.p, c->outlierLastDS.p };
     int *cnt[3] = { c->counts.p + llb_ctx::C_CORNER_DS, c->counts.p + llb_ctx::C_SURF_DS, c->counts.p + llb_ctx::C_OUTLIER_DS };
@@ -509,9 +511,10 @@ int llb_scan_set_dev(llb_ctx *c, const void *corner, int nc, const void *surf, i
 {
     return guarded(c, [&]() {
         if (nc < 0 || ns < 0 || no < 0) return (int)LLB_ERR_INVALID;
+        // device-resident sweeps are BORROWED (no copy): the pointers must stay valid and unchanged until the next
+        // llb_scan_set* / the end of the registration that uses them
         auto cp = [&](Cloud &cl, const void *src, int n) {
-            cl.pts.ensure(std::max(n, 1));
-            if (n > 0) LLB_CUDA(cudaMemcpyAsync(cl.pts.p, src, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            cl.view = (const float4 *)src;
             cl.n_host = n; cl.exact = true;
         };
         cp(c->cornerLast, corner, nc); cp(c->surfLast, surf, ns); cp(c->outlierLast, outlier, no);

@@ -298,3 +298,26 @@ def test_odometry_guard(ctx):
     T0 = np.array([0.001, 0.002, 0.003, 0.01, 0.02, 0.03], np.float32)
     T, s0, s1 = ctx.odom_optimize(T0)
     assert s0.skipped == 1 and np.array_equal(T, T0)
+
+
+def test_device_resident_family_matches_host_path(ctx):
+    """llb_scan_set_dev (borrowed device sweeps) + llb_map_set_ds_dev + llb_s2m_optimize_dev give the bits of the host-cloud
+    calls."""
+    import torch
+    case = data.mapping_case(3)
+    ctx.map_set_raw(case["map_corner_raw"], case["map_surf_raw"])
+    mc_ds, ms_ds = ctx.map_get_ds(0), ctx.map_get_ds(1)
+    ctx.map_set_ds(mc_ds, ms_ds); ctx.scan_set(case["corner"], case["surf"], case["outlier"])
+    counts = ctx.downsample_current_scan()
+    T_host, st = ctx.s2m_optimize(case["init"])
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v, np.float32)).to(dev)
+         for k, v in (("c", case["corner"]), ("s", case["surf"]), ("o", case["outlier"]), ("mc", mc_ds), ("ms", ms_ds))}
+    d_T = torch.from_numpy(np.asarray(case["init"], np.float32).copy()).to(dev)
+    torch.cuda.synchronize()
+    ctx.scan_set_dev(d["c"].data_ptr(), d["c"].shape[0], d["s"].data_ptr(), d["s"].shape[0], d["o"].data_ptr(), d["o"].shape[0])
+    assert ctx.downsample_current_scan() == counts
+    ctx.map_set_ds_dev(d["mc"].data_ptr(), d["mc"].shape[0], d["ms"].data_ptr(), d["ms"].shape[0])
+    ctx.s2m_optimize_dev(d_T.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(d_T.cpu().numpy().view(np.uint32), T_host.view(np.uint32))

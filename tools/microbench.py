@@ -48,7 +48,7 @@ def main():
     with torch.cuda.stream(stream):
         ctx.scan_set_dev(d_c.data_ptr(), d_c.shape[0], d_s.data_ptr(), d_s.shape[0], d_o.data_ptr(), d_o.shape[0])
         rows = []
-        rows.append(("scan_set_dev (3 D2D copies)", timed(stream, lambda: ctx.scan_set_dev(
+        rows.append(("scan_set_dev (borrowed pointers)", timed(stream, lambda: ctx.scan_set_dev(
             d_c.data_ptr(), d_c.shape[0], d_s.data_ptr(), d_s.shape[0], d_o.data_ptr(), d_o.shape[0]))))
         rows.append(("downsampleCurrentScan (4 voxel filters)", timed(stream, lambda: ctx.downsample_current_scan(False))))
         rows.append(("map_set_ds_dev (2 index builds)", timed(stream, lambda: ctx.map_set_ds_dev(
