@@ -67,6 +67,8 @@ struct llb_ctx {
     VoxelFilter vox2;             // second set of voxel scratch: the two map filters MO:1057-1064 run concurrently
     cudaStream_t stream2 = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    cudaEvent_t ds_fork_ev = nullptr, ds_ev = nullptr;   // downsampleCurrentScan on the forked stream (small sweeps)
+    bool ds_pending = false;
     // scan side (MO:109-118)
     Cloud cornerLast, surfLast, outlierLast;
     DevBuf<float4> cornerLastDS, surfLastDS, outlierLastDS, surfTotalLastDS;
@@ -217,8 +219,19 @@ void download_cloud(llb_ctx *c, const float4 *src, int n, llb_point *dst)
     }
 }
 
+// downsampleCurrentScan of small sweeps runs on the forked stream beside whatever the caller enqueues next (normally
+// the index build of the map); every consumer of the DS clouds / their counts and every producer that would overwrite
+// the sweep joins here first
+void join_scan_ds(llb_ctx *c)
+{
+    if (!c->ds_pending) return;
+    LLB_CUDA(cudaStreamWaitEvent(c->stream, c->ds_ev, 0));
+    c->ds_pending = false;
+}
+
 int read_count(llb_ctx *c, int which)
 {
+    join_scan_ds(c);
     LLB_CUDA(cudaMemcpyAsync(c->pin_counts.p, c->counts.p, sizeof(int) * llb_ctx::C_N, cudaMemcpyDeviceToHost, c->stream));
     LLB_CUDA(cudaStreamSynchronize(c->stream));
     return c->pin_counts.p[which];
@@ -255,6 +268,7 @@ void voxel_map_raw(llb_ctx *c, const float4 *corner, int rc, const float4 *surf,
 
 S2mQueries s2m_queries(llb_ctx *c)
 {
+    join_scan_ds(c);
     S2mQueries q;
     q.corner = c->cornerLastDS.p; q.nc_dev = c->counts.p + llb_ctx::C_CORNER_DS; q.nc_upper = c->cornerLast.n_host;
     q.surf = c->surfTotalLastDS.p; q.ns_dev = c->counts.p + llb_ctx::C_SURFTOTAL_DS;
@@ -264,6 +278,7 @@ S2mQueries s2m_queries(llb_ctx *c)
 
 void downsample_scan(llb_ctx *c)
 {
+    join_scan_ds(c);
     const int nc = c->cornerLast.n_host, ns = c->surfLast.n_host, no = c->outlierLast.n_host;
     c->cornerLastDS.ensure(std::max(nc, 1)); c->surfLastDS.ensure(std::max(ns, 1));
     c->outlierLastDS.ensure(std::max(no, 1)); c->surfTotalLastDS.ensure(std::max(ns + no, 1));
@@ -274,11 +289,21 @@ void downsample_scan(llb_ctx *c)
     const float leaf[3] = { c->prm.corner_leaf, c->prm.surf_leaf, c->prm.outlier_leaf };
     float4 *out[3] = { c->cornerLastDS.p, c->surfLastDS.p, c->outlierLastDS.p };
     int *cnt[3] = { c->counts.p + llb_ctx::C_CORNER_DS, c->counts.p + llb_ctx::C_SURF_DS, c->counts.p + llb_ctx::C_OUTLIER_DS };
-    c->launches += c->vox.run_batch(in, leaf, out, cnt, 3, c->stream);                 // MO:1069-1082
+    // sweeps that fit the cluster kernel need no scratch: their four filters run on the forked stream and overlap the
+    // map side of the registration (index build / map voxel filters) that the caller enqueues next
+    const bool forked = std::max(nc, std::max(ns, no)) <= VoxelFilter::SMALL_MAX && ns + no <= VoxelFilter::SMALL_MAX;
+    cudaStream_t vs = c->stream;
+    if (forked) {
+        LLB_CUDA(cudaEventRecord(c->ds_fork_ev, c->stream));
+        LLB_CUDA(cudaStreamWaitEvent(c->stream2, c->ds_fork_ev, 0));
+        vs = c->stream2;
+    }
+    c->launches += c->vox.run_batch(in, leaf, out, cnt, 3, vs);                        // MO:1069-1082
     VoxelInput tot;                                                                    // MO:1084-1090 (C12)
     tot.a = c->surfLastDS.p; tot.na_dev = cnt[1]; tot.na = ns;
     tot.b = c->outlierLastDS.p; tot.nb_dev = cnt[2]; tot.nb = no;
-    c->launches += c->vox.run(tot, c->prm.surf_leaf, c->surfTotalLastDS.p, c->counts.p + llb_ctx::C_SURFTOTAL_DS, c->stream);
+    c->launches += c->vox.run(tot, c->prm.surf_leaf, c->surfTotalLastDS.p, c->counts.p + llb_ctx::C_SURFTOTAL_DS, vs);
+    if (forked) { LLB_CUDA(cudaEventRecord(c->ds_ev, c->stream2)); c->ds_pending = true; }
     c->scan_ds_done = true;
 }
 
@@ -337,6 +362,8 @@ int llb_create(const llb_params *p, int device, llb_ctx **out)
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         LLB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
         LLB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+        LLB_CUDA(cudaEventCreateWithFlags(&c->ds_fork_ev, cudaEventDisableTiming));
+        LLB_CUDA(cudaEventCreateWithFlags(&c->ds_ev, cudaEventDisableTiming));
         c->gridCorner.init(c->prm.max_grid_cells);
         c->gridSurf.init(c->prm.max_grid_cells);
         c->s2m.init(s2m_params(c->prm));
@@ -362,6 +389,8 @@ int llb_destroy(llb_ctx *c)
     c->counts.release(); c->vox.release(); c->vox2.release();
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->join_ev) cudaEventDestroy(c->join_ev);
+    if (c->ds_fork_ev) cudaEventDestroy(c->ds_fork_ev);
+    if (c->ds_ev) cudaEventDestroy(c->ds_ev);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     c->cornerLast.pts.release(); c->surfLast.pts.release(); c->outlierLast.pts.release();
     c->cornerLastDS.release(); c->surfLastDS.release(); c->outlierLastDS.release(); c->surfTotalLastDS.release();
@@ -385,7 +414,7 @@ long long llb_launch_count(const llb_ctx *c) { return c ? c->launches : 0; }
 
 int llb_synchronize(llb_ctx *c)
 {
-    return guarded(c, [&]() { LLB_CUDA(cudaStreamSynchronize(c->stream)); return (int)LLB_OK; });
+    return guarded(c, [&]() { join_scan_ds(c); LLB_CUDA(cudaStreamSynchronize(c->stream)); return (int)LLB_OK; });
 }
 
 int llb_reserve(llb_ctx *c, int max_scan_points, int max_raw_map_points, int max_keyframes)
@@ -499,6 +528,7 @@ int llb_scan_set(llb_ctx *c, const llb_point *corner, int nc, const llb_point *s
     return guarded(c, [&]() {
         if (nc < 0 || ns < 0 || no < 0 || (nc > 0 && !corner) || (ns > 0 && !surf) || (no > 0 && !outlier))
             return (int)LLB_ERR_INVALID;
+        join_scan_ds(c);
         set_cloud(c, 0, c->cornerLast, corner, nc);
         set_cloud(c, 1, c->surfLast, surf, ns);
         set_cloud(c, 2, c->outlierLast, outlier, no);
@@ -511,6 +541,7 @@ int llb_scan_set_dev(llb_ctx *c, const void *corner, int nc, const void *surf, i
 {
     return guarded(c, [&]() {
         if (nc < 0 || ns < 0 || no < 0) return (int)LLB_ERR_INVALID;
+        join_scan_ds(c);
         // device-resident sweeps are BORROWED (no copy): the pointers must stay valid and unchanged until the next
         // llb_scan_set* / the end of the registration that uses them
         auto cp = [&](Cloud &cl, const void *src, int n) {
