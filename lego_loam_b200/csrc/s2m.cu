@@ -146,6 +146,8 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             }
             __syncthreads();
             // ---------------- phase A2: warp per query: candidates -> in-gate list -> 5 smallest
+            // (a thread-per-query walk, the throughput form of batch.cu, was measured here too: with one or two warps
+            // per SM nothing hides its dependent loads - 70k cycles per tile instead of 14k)
             for (int s = w; s < tn; s += S2M_NW) {
                 const int qi = rank + world * (j0 + t0 + s);
                 const bool is_corner = qi < nc;
@@ -228,8 +230,21 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
         // ---- CTA 0: deterministic grid reduction (16 interleaved slices, fixed order) + LM step
         if (blockIdx.x == 0) {
             double s = 0.0;
-            if (lane < S2M_ACC)
-                for (int b = w; b < (int)gridDim.x; b += S2M_NW) s += __ldcg(&partials[(size_t)b * S2M_ACC + lane]);
+            if (lane < S2M_ACC) {
+                // the (up to 10) partials of this warp's slice are fetched together - one L2 round trip instead of ten
+                // dependent ones - and added in the same fixed order as before
+                constexpr int RMAX = 10;                     // ceil(148 CTAs / 16 warps)
+                for (int b0 = w; b0 < (int)gridDim.x; b0 += S2M_NW * RMAX) {
+                    double v[RMAX];
+#pragma unroll
+                    for (int k = 0; k < RMAX; k++) {
+                        const int b = b0 + k * S2M_NW;
+                        v[k] = b < (int)gridDim.x ? __ldcg(&partials[(size_t)b * S2M_ACC + lane]) : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < RMAX; k++) if (b0 + k * S2M_NW < (int)gridDim.x) s += v[k];
+                }
+            }
             s_acc[w][lane] = s;
             __syncthreads();
             if (tid < S2M_ACC) {
