@@ -68,6 +68,9 @@ __global__ void batch_prepare_kernel(const BatchReg *__restrict__ regs, const fl
 // the order stays good for the whole registration; it only affects speed, never results.
 constexpr int QS_THREADS = 512;
 constexpr int QS_ITEMS = 4;
+#ifndef LLB_QS_SHIFT
+#define LLB_QS_SHIFT 1      // cost bucket = 2 candidates (8 measured the same)
+#endif
 
 __global__ void __launch_bounds__(QS_THREADS)
 batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap, int by_count)
@@ -121,7 +124,7 @@ batch_qsort_kernel(const BatchReg *__restrict__ regs, int cap, int by_count)
                 const int c0 = __ldg(&cell_begin[ry * dimx + x0]), c1 = __ldg(&cell_begin[ry * dimx + x1 + 1]);
                 tot += (r1 > r0) ? (c1 - c0) : 0;
             }
-            key = (unsigned)min(tot >> 1, 255);               // one 8-bit radix pass is enough to equalise warps
+            key = (unsigned)min(tot >> LLB_QS_SHIFT, 255);    // one 8-bit radix pass is enough to equalise warps
         }
         kin[i] = key;
         vin[i] = (unsigned short)i;
