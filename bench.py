@@ -366,7 +366,8 @@ def odometry_arm(api, local, reps, cpu_sample):
             "batched": {"pairs_per_launch": NBO, "ms_per_launch_device": batch_dev_ms,
                         "pairs_per_s_e2e_host": NBO / (float(np.median(bt_wall)) * 1e-3),
                         "equal_to_single": batch_equal},
-            "note": "updateTransformation (FA:1666-1695) of one VLP-16 sweep pair: one persistent CTA on the device"}
+            "note": "updateTransformation (FA:1666-1695) of one VLP-16 sweep pair: one persistent 8-CTA cluster on the device "
+                    "(redundant iteration loop, correspondence search split by feature); batched: one CTA per pair"}
 
 
 def main():

@@ -7,6 +7,11 @@
 // semantics, and lane k accumulates the k-th product of the 3x3 normal equations in fp64.
 #include "odom.cuh"
 #include "linalg.cuh"
+#include "grid_index.cuh"
+#include <cmath>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace llb {
 
@@ -21,6 +26,7 @@ struct OdomData {
     int nsharp, nflat, ncl, nsl;
     float *cInd1, *cInd2, *sInd1, *sInd2, *sInd3;
     float4 *dbg_coeff; int *dbg_valid;
+    MapIndexView cgrid, sgrid;          // uniform-grid indices of the previous sweep's clouds (sorted == nullptr: none)
 };
 
 __device__ __forceinline__ float sqdist_ref(const float4 &a, float x, float y, float z)
@@ -68,6 +74,50 @@ __device__ __forceinline__ void nn1_warp(const float4 *__restrict__ pts, int n, 
     best_d = __uint_as_float(mind);
 }
 
+// The same through the uniform-grid index of the cloud (cells slightly larger than the gate radius sqrt(25) = 5 m,
+// UT:125): the 3x3x3 cells around the query contain every point the reference could accept (FA:1057: d2 < 25), so the
+// exact nearest neighbour among them is the kd-tree's answer whenever the answer is used; otherwise best_d >= gate.
+// Ties: smaller ORIGINAL index, as nn1_warp.
+__device__ __forceinline__ void nn1_grid_warp(const MapIndexView &m, float x, float y, float z, int lane,
+                                              float &best_d, int &best_i)
+{
+    const GridDesc *g = m.desc;
+    const int dimx = g->dim[0], dimy = g->dim[1], dimz = g->dim[2];
+    const float inv = g->inv_cell;
+    const int cx = grid_coord(x, g->org[0], inv), cy = grid_coord(y, g->org[1], inv), cz = grid_coord(z, g->org[2], inv);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dimx - 1);
+    int b0 = 0, e0 = 0;
+    {
+        const int k = lane < 9 ? lane : 0;
+        const int yy = cy + (k % 3) - 1, zz = cz + (k / 3) - 1;
+        if (lane < 9 && yy >= 0 && yy < dimy && zz >= 0 && zz < dimz && x0 <= x1) {
+            const int ry = zz * dimy + yy;
+            if (__ldg(&m.row_begin[ry + 1]) > __ldg(&m.row_begin[ry])) {
+                b0 = __ldg(&m.cell_begin[ry * dimx + x0]);
+                e0 = __ldg(&m.cell_begin[ry * dimx + x1 + 1]);
+            }
+        }
+    }
+    float bd = __int_as_float(0x7f800000); int bi = INT_MAX;
+#pragma unroll 1
+    for (int r = 0; r < 9; r++) {
+        const int rb = __shfl_sync(FULL, b0, r), re = __shfl_sync(FULL, e0, r);
+        for (int j = rb + lane; j < re; j += 32) {
+            const float4 p = __ldg(&m.sorted[j]);
+            float diff = x - p.x; float d = diff * diff;
+            diff = y - p.y; d += diff * diff;
+            diff = z - p.z; d += diff * diff;
+            const int oi = __float_as_int(p.w);
+            if (d < bd || (d == bd && oi < bi)) { bd = d; bi = oi; }
+        }
+    }
+    const unsigned db = __float_as_uint(bd);
+    const unsigned mind = __reduce_min_sync(FULL, db);
+    const unsigned ci = (db == mind) ? (unsigned)bi : 0xffffffffu;
+    best_i = (int)__reduce_min_sync(FULL, ci);
+    best_d = __uint_as_float(mind);
+}
+
 // One direction of the neighbour scan.  Visits j = start, start+step, ... while in [lo, hi)
 // and until the first element whose ring violates the bound; among visited elements with
 // cls(j) == k (k = 0, 1) keeps the first strict minimum below bd[k].
@@ -77,41 +127,68 @@ __device__ __forceinline__ void window_scan(const float4 *__restrict__ pts, int 
                                             int closestScan, float x, float y, float z, int lane,
                                             float (&bd)[2], int (&bj)[2])
 {
-    for (int base = start;; base += 32 * step) {
-        const int j = base + lane * step;
-        const bool in = (j >= lo) && (j < hi);
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) p = __ldg(&pts[j]);
-        const int ring = (int)p.w;
-        const bool brk = !in || (step > 0 ? ring >= closestScan + 3 : ring <= closestScan - 3);
-        const unsigned bmask = __ballot_sync(FULL, brk);
-        const int fb = bmask ? (__ffs(bmask) - 1) : 32;
-        const bool vis = lane < fb;
-        const float d = sqdist_ref(p, x, y, z);
-        int cls;
-        if (SURF) cls = (step > 0) ? ((ring <= closestScan) ? 0 : 1) : ((ring >= closestScan) ? 0 : 1);
-        else cls = (step > 0) ? ((ring > closestScan) ? 0 : -1) : ((ring < closestScan) ? 0 : -1);
+    // lane-local running minima over the chunks (strict "<": within a lane the earlier visited element wins); ONE
+    // ballot per chunk finds the first break; the warp-wide choice is made once, after the loop
+    float lbd[2] = { bd[0], bd[1] };
+    int lbj[2] = { -1, -1 };
+    // the walk is a chain of dependent "load 32 candidates -> look for the break" steps (a surf window spans ~2500
+    // points = 80 steps of one load latency each): the loads of four steps are issued together; the ones behind the
+    // break are simply not used
+    constexpr int U = 4;
+    bool done = false;
+    for (int base = start; !done; base += 32 * U * step) {
+        float4 pv[U]; bool inv[U];
 #pragma unroll
-        for (int k = 0; k < (SURF ? 2 : 1); k++) {
-            const bool cand = vis && cls == k && d < bd[k];
-            const unsigned cm = __ballot_sync(FULL, cand);
-            if (cm) {
-                const unsigned db = cand ? __float_as_uint(d) : 0xffffffffu;
-                const unsigned mind = __reduce_min_sync(FULL, db);
-                const unsigned wm = __ballot_sync(FULL, cand && db == mind);
-                const int src = __ffs(wm) - 1;                     // earliest visited among equals
-                bd[k] = __uint_as_float(mind);
-                bj[k] = __shfl_sync(FULL, j, src);
-            }
+        for (int u = 0; u < U; u++) {
+            const int j = base + (u * 32 + lane) * step;
+            inv[u] = (j >= lo) && (j < hi);
+            pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inv[u]) pv[u] = __ldg(&pts[j]);
         }
-        if (bmask) break;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (done) break;
+            const int j = base + (u * 32 + lane) * step;
+            const float4 p = pv[u];
+            const bool in = inv[u];
+            const int ring = (int)p.w;
+            const bool brk = !in || (step > 0 ? ring >= closestScan + 3 : ring <= closestScan - 3);
+            const unsigned bmask = __ballot_sync(FULL, brk);
+            const int fb = bmask ? (__ffs(bmask) - 1) : 32;
+            const bool vis = lane < fb;
+            const float d = sqdist_ref(p, x, y, z);
+            int cls;
+            if (SURF) cls = (step > 0) ? ((ring <= closestScan) ? 0 : 1) : ((ring >= closestScan) ? 0 : 1);
+            else cls = (step > 0) ? ((ring > closestScan) ? 0 : -1) : ((ring < closestScan) ? 0 : -1);
+#pragma unroll
+            for (int k = 0; k < (SURF ? 2 : 1); k++)
+                if (vis && cls == k && d < lbd[k]) { lbd[k] = d; lbj[k] = j; }
+            if (bmask) done = true;
+        }
+    }
+    // the sequential loop keeps the FIRST strict minimum below the incoming bd[k]: smallest distance, and among equal
+    // distances the element visited first (smallest j going forward, largest j going backward)
+#pragma unroll
+    for (int k = 0; k < (SURF ? 2 : 1); k++) {
+        const bool cand = lbj[k] >= 0;
+        const unsigned db = cand ? __float_as_uint(lbd[k]) : 0xffffffffu;       // distances are >= 0: bit order == value order
+        const unsigned mind = __reduce_min_sync(FULL, db);
+        if (mind != 0xffffffffu) {                                               // warp-uniform
+            const bool win = cand && db == mind;
+            const unsigned order = win ? (unsigned)(step > 0 ? lbj[k] : (INT_MAX - lbj[k])) : 0xffffffffu;
+            const unsigned first = __reduce_min_sync(FULL, order);
+            bd[k] = __uint_as_float(mind);
+            bj[k] = step > 0 ? (int)first : INT_MAX - (int)first;
+        }
     }
 }
-
 struct Trig { float srx, crx, sry, cry, srz, crz, tx, ty, tz; };
 
 // 3x3 LM step shared by both solvers (FA:1324-1376 / FA:1425-1477).  Returns `more`.
-__device__ int solve3(OdomState *st, const double *sum, int iter, int which, const OdomParams &prm)
+// T, deg and matP are the CTA's shared-memory copies of the persistent state (loaded once per launch, mirrored to the
+// global OdomState with plain stores): the sequential iterations never wait for a global load of their own results
+__device__ int solve3(OdomState *st, bool writer, float *T, int *deg_s, float *matP, const double *sum, int iter, int which,
+                      const OdomParams &prm)
 {
     float AtA[9], AtB[3], A[9], B[3], X[3];
     AtA[0] = (float)sum[0]; AtA[1] = AtA[3] = (float)sum[1]; AtA[2] = AtA[6] = (float)sum[2];
@@ -131,29 +208,30 @@ __device__ int solve3(OdomState *st, const double *sum, int iter, int which, con
                 deg = 1;
             } else break;
         }
-        st->is_degenerate = deg;
+        *deg_s = deg; if (writer) st->is_degenerate = deg;
         cv_inv3(V, Vinv);
-        cv_gemm<3, 3, 3>(Vinv, V2, st->matP);
+        cv_gemm<3, 3, 3>(Vinv, V2, matP);
+        if (writer) for (int i = 0; i < 9; i++) st->matP[i] = matP[i];
     }
-    if (st->is_degenerate) {
+    if (*deg_s) {
         float X2[3] = { X[0], X[1], X[2] };
-        cv_gemm<3, 3, 1>(st->matP, X2, X);
+        cv_gemm<3, 3, 1>(matP, X2, X);
     }
     float deltaR, deltaT;
     if (which == 0) {                 // surf: rx, rz, ty
-        st->T[0] += X[0]; st->T[2] += X[1]; st->T[4] += X[2];
+        T[0] += X[0]; T[2] += X[1]; T[4] += X[2];
         double r0 = (double)X[0] * 180.0 / 3.14159265358979323846, r1 = (double)X[1] * 180.0 / 3.14159265358979323846;
         double t0 = (double)(X[2] * 100);
         deltaR = (float)sqrt(r0 * r0 + r1 * r1);
         deltaT = (float)sqrt(t0 * t0);
     } else {                          // corner: ry, tx, tz
-        st->T[1] += X[0]; st->T[3] += X[1]; st->T[5] += X[2];
+        T[1] += X[0]; T[3] += X[1]; T[5] += X[2];
         double r0 = (double)X[0] * 180.0 / 3.14159265358979323846;
         double t0 = (double)(X[1] * 100), t1 = (double)(X[2] * 100);
         deltaR = (float)sqrt(r0 * r0);
         deltaT = (float)sqrt(t0 * t0 + t1 * t1);
     }
-    for (int i = 0; i < 6; i++) if (isnan(st->T[i])) st->T[i] = 0.f;          // C14
+    for (int i = 0; i < 6; i++) { if (isnan(T[i])) T[i] = 0.f; if (writer) st->T[i] = T[i]; }   // C14
     if ((double)deltaR < (double)prm.converge_deg && (double)deltaT < (double)prm.converge_cm) return 0;
     return 1;
 }
@@ -166,12 +244,23 @@ __device__ int solve3(OdomState *st, const double *sum, int iter, int which, con
 //   P3 thread/feature : line / plane coefficients from the stored indices, weight, Jacobian row -> shared memory
 //   P4 lane k of warp w accumulates product k of the 10 normal-equation terms over rows w, w+32, ...
 // then a fixed-order reduction and the 3x3 LM step by thread 0.
+// CL > 1: the kernel runs as a thread-block CLUSTER of CL CTAs.  Every CTA executes the whole (deterministic) iteration
+// loop redundantly on its own shared-memory copy of the state, so all control flow stays in lockstep without any
+// communication; only the correspondence SEARCH of the refresh iterations (P2: 1-NN + ring-window scans, issue-bound
+// on one SM: 200k cycles for 192 surf features) is split by feature over the CTAs, its results go to the global
+// index arrays every CTA reads in P3 anyway, and one cluster barrier makes them visible.  CTA 0 alone writes OdomState.
+template <int CL>
 __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData &dat, OdomState *__restrict__ st, int mode,
                                           int iter0)
 {
+    int crank = 0;
+    if (CL > 1) crank = (int)cg::this_cluster().block_rank();
+    const bool writer = crank == 0;
     __shared__ double s_acc[OD_NW][OD_ACC];
     __shared__ double s_tot[OD_ACC];
     __shared__ float s_T[6];
+    __shared__ float s_matP[9];
+    __shared__ int s_deg;
     __shared__ Trig s_trig;
     __shared__ int s_more;
     __shared__ float s_sel[3][OD_THREADS];                  // de-skewed feature of the tile
@@ -179,12 +268,18 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
-    if (tid == 0) {
+    if (tid == 0 && writer) {
         st->skipped = (dat.ncl < 10 || dat.nsl < 100) ? 1 : 0;               // FA:1668
         if (mode == 0) { st->iters[0] = st->iters[1] = 0; st->converged[0] = st->converged[1] = 0; }
         st->n_corr = 0; st->more = 1;
     }
     if (dat.ncl < 10 || dat.nsl < 100) return;
+    if (tid == 0) {                                                          // persistent state -> shared memory, once
+        for (int i = 0; i < 6; i++) s_T[i] = st->T[i];
+        for (int i = 0; i < 9; i++) s_matP[i] = st->matP[i];
+        s_deg = st->is_degenerate;
+    }
+    if (CL > 1) cg::this_cluster().sync();                                   // nobody overwrites the state before all have read it
 
     const int ia_tab[10] = { 0, 0, 0, 1, 1, 2, 0, 1, 2, 4 };
     const int ib_tab[10] = { 0, 1, 2, 1, 2, 2, 3, 3, 3, 4 };
@@ -202,10 +297,7 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
         const int it_begin = mode == 0 ? 0 : iter0, it_end = mode == 0 ? prm.max_iter : iter0 + 1;
         for (int iter = it_begin; iter < it_end; iter++) {
             __syncthreads();
-            if (tid == 0) {
-                for (int i = 0; i < 6; i++) s_T[i] = st->T[i];
-                s_trig.tx = s_T[3]; s_trig.ty = s_T[4]; s_trig.tz = s_T[5];
-            }
+            if (tid == 0) { s_trig.tx = s_T[3]; s_trig.ty = s_T[4]; s_trig.tz = s_T[5]; }
             __syncthreads();
             if (tid < 6) {                                                   // six threads, one fp64 libm call each
                 const double a = (double)s_T[tid >> 1];
@@ -232,11 +324,15 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
                 __syncthreads();
                 // ---- P2
                 if (iter % 5 == 0) {                                          // C4
-                    for (int s = w; s < tn; s += OD_NW) {
+                    // no CTA may overwrite indices another CTA is still reading in P3 of an earlier iteration
+                    if (CL > 1) cg::this_cluster().sync();
+                    for (int s = w + OD_NW * crank; s < tn; s += OD_NW * CL) {
                         const int i = t0 + s;
                         const float x0 = s_sel[0][s], y0 = s_sel[1][s], z0 = s_sel[2][s];
                         float d1; int closest;
-                        nn1_warp(last, nlast, x0, y0, z0, lane, d1, closest);
+                        const MapIndexView &gv = which == 0 ? dat.sgrid : dat.cgrid;
+                        if (gv.sorted) nn1_grid_warp(gv, x0, y0, z0, lane, d1, closest);
+                        else nn1_warp(last, nlast, x0, y0, z0, lane, d1, closest);
                         float bd[2] = { prm.nearest_sqdist, prm.nearest_sqdist };
                         int bj[2] = { -1, -1 };
                         if (d1 < prm.nearest_sqdist) {
@@ -254,7 +350,8 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
                             else { dat.cInd1[i] = (float)closest; dat.cInd2[i] = (float)bj[0]; }
                         }
                     }
-                    __syncthreads();
+                    if (CL > 1) { __threadfence(); cg::this_cluster().sync(); }   // every CTA's share of the indices is visible
+                    else __syncthreads();
                 }
                 // ---- P3
                 {
@@ -357,14 +454,13 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
             __syncthreads();
             if (tid == 0) {
                 const int n_corr = (int)s_tot[9];
-                st->n_corr = n_corr;
-                st->iters[which] = iter + 1;
+                if (writer) { st->n_corr = n_corr; st->iters[which] = iter + 1; }
                 int more = 1;
                 if (n_corr >= prm.min_corr) {                                 // FA:1677 / FA:1690
-                    more = solve3(st, s_tot, iter, which, prm);
-                    if (!more) st->converged[which] = 1;
+                    more = solve3(st, writer, s_T, &s_deg, s_matP, s_tot, iter, which, prm);
+                    if (!more && writer) st->converged[which] = 1;
                 }
-                st->more = more;
+                if (writer) st->more = more;
                 s_more = more;
             }
             __syncthreads();
@@ -374,10 +470,11 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
 }
 
 // one sweep pair (llb_ctx)
-__global__ void __launch_bounds__(OD_THREADS, 1)
+constexpr int OD_CLUSTER = 8;
+__global__ void __cluster_dims__(OD_CLUSTER, 1, 1) __launch_bounds__(OD_THREADS, 1)
 odom_kernel(OdomParams prm, OdomData dat, OdomState *__restrict__ st, int mode, int iter0)
 {
-    odom_body(prm, dat, st, mode, iter0);
+    odom_body<OD_CLUSTER>(prm, dat, st, mode, iter0);
 }
 
 // B independent sweep pairs, one CTA each (llb_batch): the <= 50 sequential iterations of a pair cannot be spread
@@ -392,7 +489,8 @@ odom_batch_kernel(OdomParams prm, const OdomBatchJob *__restrict__ jobs)
     dat.cInd1 = jb.ind; dat.cInd2 = jb.ind + jb.cap; dat.sInd1 = jb.ind + 2 * jb.cap; dat.sInd2 = jb.ind + 3 * jb.cap;
     dat.sInd3 = jb.ind + 4 * jb.cap;
     dat.dbg_coeff = nullptr; dat.dbg_valid = nullptr;
-    odom_body(prm, dat, jb.st, 0, 0);
+    dat.cgrid = MapIndexView{ nullptr, nullptr, nullptr, nullptr }; dat.sgrid = dat.cgrid;   // brute-force 1-NN
+    odom_body<1>(prm, dat, jb.st, 0, 0);
 }
 
 __global__ void odom_state_init_kernel(OdomState *st)
@@ -455,12 +553,20 @@ void OdomSolver::release()
 {
     state_.release(); cornerLast_.release(); surfLast_.release(); sharp_.release(); flat_.release();
     ind_.release(); dbg_coeff_.release(); dbg_valid_.release();
+    if (grids_init_) { gridCorner_.release(); gridSurf_.release(); grids_init_ = false; grids_built_ = false; }
 }
 
-int OdomSolver::set_last(int ncl, int nsl, cudaStream_t)
+int OdomSolver::set_last(int ncl, int nsl, cudaStream_t s)
 {
     ncl_ = ncl; nsl_ = nsl; last_set_ = true;
-    return 0;
+    // spatial index of the previous sweep's clouds (the reference rebuilds its two kd-trees here, FA:1615-1616 /
+    // FA:1786-1787): cells of the gate radius, so the 27-cell neighbourhood holds every acceptable nearest neighbour
+    if (!grids_init_) { gridCorner_.init(1 << 18); gridSurf_.init(1 << 18); grids_init_ = true; }
+    if (ncl <= 0 || nsl <= 0) { grids_built_ = false; return 0; }
+    const int n = GridIndex::build_pair(gridCorner_, cornerLast_.p, nullptr, ncl, gridSurf_, surfLast_.p, nullptr, nsl,
+                                        std::sqrt(prm_.nearest_sqdist), s);
+    grids_built_ = true;
+    return n;
 }
 
 void OdomSolver::ensure_work()
@@ -487,6 +593,7 @@ static OdomData make_data(const float4 *sharp, const float4 *flat, const float4 
                           int nflat, int ncl, int nsl, float *ind, int cap, float4 *dbg_coeff, int *dbg_valid)
 {
     OdomData d;
+    d.cgrid = MapIndexView{ nullptr, nullptr, nullptr, nullptr }; d.sgrid = d.cgrid;
     d.sharp = sharp; d.flat = flat; d.cornerLast = cl; d.surfLast = sl;
     d.nsharp = nsharp; d.nflat = nflat; d.ncl = ncl; d.nsl = nsl;
     d.cInd1 = ind; d.cInd2 = ind + cap; d.sInd1 = ind + 2 * cap; d.sInd2 = ind + 3 * cap; d.sInd3 = ind + 4 * cap;
@@ -499,7 +606,8 @@ int OdomSolver::optimize(const float *T, cudaStream_t s)
     LLB_CUDA(cudaMemcpyAsync(state_.p, T, 6 * sizeof(float), cudaMemcpyHostToDevice, s));   // OdomState starts with T[6]
     OdomData d = make_data(sharp_.p, flat_.p, cornerLast_.p, surfLast_.p, nsharp_, nflat_, ncl_, nsl_, ind_.p, cap_,
                            nullptr, nullptr);
-    odom_kernel<<<1, OD_THREADS, 0, s>>>(prm_, d, state_.p, 0, 0);
+    if (grids_built_) { d.cgrid = gridCorner_.view(); d.sgrid = gridSurf_.view(); }
+    odom_kernel<<<OD_CLUSTER, OD_THREADS, 0, s>>>(prm_, d, state_.p, 0, 0);
     LLB_CUDA(cudaGetLastError());
     dbg_which_ = -1;
     return 1;
@@ -510,7 +618,8 @@ int OdomSolver::iterate(int which, const float *T, int iter, cudaStream_t s)
     LLB_CUDA(cudaMemcpyAsync(state_.p, T, 6 * sizeof(float), cudaMemcpyHostToDevice, s));
     OdomData d = make_data(sharp_.p, flat_.p, cornerLast_.p, surfLast_.p, nsharp_, nflat_, ncl_, nsl_, ind_.p, cap_,
                            dbg_coeff_.p, dbg_valid_.p);
-    odom_kernel<<<1, OD_THREADS, 0, s>>>(prm_, d, state_.p, which == 0 ? 1 : 2, iter);
+    if (grids_built_) { d.cgrid = gridCorner_.view(); d.sgrid = gridSurf_.view(); }
+    odom_kernel<<<OD_CLUSTER, OD_THREADS, 0, s>>>(prm_, d, state_.p, which == 0 ? 1 : 2, iter);
     LLB_CUDA(cudaGetLastError());
     dbg_which_ = which;
     return 1;

@@ -7,6 +7,7 @@
 // between iterations).
 #pragma once
 #include "common.cuh"
+#include "grid_index.cuh"
 #include <vector>
 
 namespace llb {
@@ -70,6 +71,8 @@ private:
     int ncl_ = 0, nsl_ = 0, nsharp_ = 0, nflat_ = 0, cap_ = 0;
     int dbg_which_ = -1;
     bool last_set_ = false, feat_set_ = false;
+    GridIndex gridCorner_, gridSurf_;   // uniform grids over the previous sweep's clouds (cell = gate radius)
+    bool grids_init_ = false, grids_built_ = false;
 };
 
 }  // namespace llb
