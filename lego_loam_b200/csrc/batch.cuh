@@ -5,7 +5,10 @@
 // spatial index and persistent LM state (isDegenerate / matP).  ONE step registers all B
 // slots with a FIXED number of launches that does not depend on B:
 //     1   unpack of every host cloud uploaded this step (PCL 32 B stride -> float4)
-//     2   downsampleCurrentScan, MO:1067-1091: 3B filters in one cluster launch, then the B "total" filters
+//     2   downsampleCurrentScan, MO:1067-1091: 3B filters (one CTA each, radix sort in shared memory), then the B
+//         "total" filters - on a forked stream beside the map side of the step
+//   1+19  slots with a key-frame request: assembly of their raw local maps (one launch) + their 2 map voxel filters
+//         each (one set of 19 launches, job table); key-frames saved since the last step are copied first (1)
 //     5   spatial-index build of every map that changed (replaces 2B kdtree->setInputCloud, MO:1333-1334)
 //     2   prepare (pose, sin/cos, guard MO:1331) + ordering of the queries by kNN cost (speed only)
 //   2xI   per LM iteration (MO:1336-1346): kNN (thread per query, cost-balanced warps), then fit + Jacobian rows + fp64
