@@ -6,6 +6,7 @@
 #include "odom.cuh"
 
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -34,6 +35,8 @@ struct StepLayout {
         bytes = o;
     }
 };
+
+struct StepSig { int nunp, unp_max, ncopy, copy_max, nseg, seg_max, nvox, raw_max, ngrid, map_n_max, vox_cap1, vox_cap2; };
 
 constexpr int RING = 3;
 constexpr int PROF_N = 6;      // unpack+copies, downsample, index, knn, fit, solve(+prepare/collect)
@@ -115,6 +118,9 @@ struct llb_batch {
     std::vector<int> od_n;                   // [B][4] lengths; -1 = not set
     std::vector<BatchUnpack> od_pending; int od_pending_max = 0;
 
+    struct GraphEntry { StepSig sig; cudaGraphExec_t exec; long long launches; };
+    std::vector<GraphEntry> graphs;          // captured steps, one per launch geometry
+    bool use_graph = true;
     cudaStream_t stream2 = nullptr;          // forked stream of the step (downsampleCurrentScan beside the map side)
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -293,13 +299,18 @@ int enqueue_step(llb_batch *c, const float *T)
     const int nunp = (int)c->pending_unpack.size();
     if (nunp > 5 * B) return LLB_ERR_STATE;
     for (int i = 0; i < nunp; i++) h_unp[i] = c->pending_unpack[i];
-    const int unp_max = c->pending_unpack_max;
+    // launch-geometry upper bounds are rounded up so that steps of similar size share one captured graph
+    auto round_up = [](int v, int g) { return (v + g - 1) / g * g; };
+    const int unp_max = round_up(c->pending_unpack_max, 2048);
     c->pending_unpack.clear(); c->pending_unpack_max = 0;
     const int ncopy = (int)c->pending_copy.size();
     if (ncopy > 3 * B) return LLB_ERR_STATE;
     for (int i = 0; i < ncopy; i++) h_copy[i] = c->pending_copy[i];
-    const int copy_max = c->pending_copy_max;
+    const int copy_max = round_up(c->pending_copy_max, 2048);
     c->pending_copy.clear(); c->pending_copy_max = 0;
+    seg_max = round_up(seg_max, 2048);
+    map_n_max = round_up(map_n_max, 4096);
+    raw_max = std::min(round_up(raw_max, 16384), std::max(c->cap_raw, raw_max));
 
     // ---- enqueue
     c->n_pev = 0;
@@ -308,55 +319,87 @@ int enqueue_step(llb_batch *c, const float *T)
     LLB_CUDA(cudaMemcpyAsync(dp, hp, L.bytes, cudaMemcpyHostToDevice, c->stream));
     LLB_CUDA(cudaEventRecord(c->step_ev[rp], c->stream));
     c->step_busy[rp] = true;
-    if (nunp > 0) {
-        launch_batch_unpack((const BatchUnpack *)(dp + L.off_unpack), nunp, unp_max, c->stream);
-        c->launches++;
-    }
-    if (ncopy > 0) {                                         // key-frames saved since the last step: DS clouds -> arenas,
-        launch_batch_copy((const BatchCopy *)(dp + L.off_copy), ncopy, copy_max, c->stream);   // before they are overwritten
-        c->launches++;
-    }
-    // downsampleCurrentScan only depends on the sweeps: it runs on a forked stream beside the map side of the step
-    // (key-frame assembly, map voxel filters, index build) and is joined before the registrations start
-    LLB_CUDA(cudaEventRecord(c->fork_ev, c->stream));
-    LLB_CUDA(cudaStreamWaitEvent(c->stream2, c->fork_ev, 0));
-    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream2);
-    launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream2);
-    c->launches += 2;
-    LLB_CUDA(cudaEventRecord(c->join_ev, c->stream2));
-    if (nseg > 0) {
+    if (nseg > 0)
         LLB_CUDA(cudaMemcpyAsync(c->seg_dev.p, h_seg, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
-        launch_kf_assemble(c->seg_dev.p, nseg, seg_max, c->stream);
-        c->launches++;
+    // every kernel launch of the step; all arguments are device-resident tables or the counts of `sig`
+    auto enqueue_kernels = [&]() -> long long {
+        long long nl = 0;
+        if (nunp > 0) {
+            launch_batch_unpack((const BatchUnpack *)(dp + L.off_unpack), nunp, unp_max, c->stream);
+            nl++;
+        }
+        if (ncopy > 0) {                                         // key-frames saved since the last step: DS clouds -> arenas,
+            launch_batch_copy((const BatchCopy *)(dp + L.off_copy), ncopy, copy_max, c->stream);   // before they are overwritten
+            nl++;
+        }
+        // downsampleCurrentScan only depends on the sweeps: it runs on a forked stream beside the map side of the step
+        // (key-frame assembly, map voxel filters, index build) and is joined before the registrations start
+        LLB_CUDA(cudaEventRecord(c->fork_ev, c->stream));
+        LLB_CUDA(cudaStreamWaitEvent(c->stream2, c->fork_ev, 0));
+        launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small1), 3 * B, c->vox_cap1, c->stream2);
+        launch_voxel_cta_jobs((const SmallJob *)(dp + L.off_small2), B, c->vox_cap2, c->stream2);
+        nl += 2;
+        LLB_CUDA(cudaEventRecord(c->join_ev, c->stream2));
+        if (nseg > 0) {
+            launch_kf_assemble(c->seg_dev.p, nseg, seg_max, c->stream);
+            nl++;
+        }
+        if (nvox > 0)
+            nl += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
+                                                     raw_max, c->stream);      // scratch is sized for cap_raw >= raw_max
+        prof_mark(c, 0);
+        if (ngrid > 0)
+            nl += GridIndex::build_table((const GridJob *)(dp + L.off_grid), ngrid, map_n_max,
+                                                  std::sqrt(c->prm.knn_max_sqdist), c->grids[0].max_cells(), c->grid_ctas, c->stream);
+        prof_mark(c, 2);
+        LLB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+        prof_mark(c, 1);                                         // what is left of downsampleCurrentScan after the overlap
+        const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
+        launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
+        nl++;
+        if (batch_knn_variant() >= 2) {                          // kNN variants 2 / 3: queries ordered by cell / by cost
+            launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);
+            nl++;
+        }
+        prof_mark(c, 5);
+        for (int it = 0; it < c->prm.s2m_max_iterations; it++) {
+            launch_batch_knn(regs, B, c->knn_ctas, c->sprm, c->stream);
+            prof_mark(c, 3);
+            launch_batch_fit(regs, B, c->fit_blocks, it, c->sprm, c->stream);
+            prof_mark(c, 4);
+            nl += 2;
+        }
+        launch_batch_collect(regs, B, c->results.p, c->stream);
+        nl++;
+        prof_mark(c, 5);
+        return nl;
+    };
+    // The ~30 dependent launches of a step are replayed as ONE CUDA graph (forked stream included): a step in steady
+    // state has the same launch geometry every time - its tables live in the device block refreshed above - so the
+    // graph is captured once per geometry and the host pays one launch instead of thirty (LLB_BATCH_GRAPH=0 disables).
+    const StepSig sig{ nunp, unp_max, ncopy, copy_max, nseg, seg_max, nvox, raw_max, ngrid, map_n_max, c->vox_cap1, c->vox_cap2 };
+    if (c->use_graph && !c->profile) {
+        llb_batch::GraphEntry *ge = nullptr;
+        for (auto &g : c->graphs) if (std::memcmp(&g.sig, &sig, sizeof(sig)) == 0) { ge = &g; break; }
+        if (!ge) {
+            if (c->graphs.size() >= 16) { cudaGraphExecDestroy(c->graphs[0].exec); c->graphs.erase(c->graphs.begin()); }
+            cudaGraph_t graph = nullptr;
+            LLB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            long long nl = 0;
+            try { nl = enqueue_kernels(); } catch (...) { cudaStreamEndCapture(c->stream, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+            LLB_CUDA(cudaStreamEndCapture(c->stream, &graph));
+            llb_batch::GraphEntry e{};
+            e.sig = sig; e.launches = nl;
+            LLB_CUDA(cudaGraphInstantiate(&e.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            c->graphs.push_back(e);
+            ge = &c->graphs.back();
+        }
+        LLB_CUDA(cudaGraphLaunch(ge->exec, c->stream));
+        c->launches += ge->launches;
+    } else {
+        c->launches += enqueue_kernels();
     }
-    if (nvox > 0)
-        c->launches += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
-                                                 raw_max, c->stream);      // scratch is sized for cap_raw >= raw_max
-    prof_mark(c, 0);
-    if (ngrid > 0)
-        c->launches += GridIndex::build_table((const GridJob *)(dp + L.off_grid), ngrid, map_n_max,
-                                              std::sqrt(c->prm.knn_max_sqdist), c->grids[0].max_cells(), c->grid_ctas, c->stream);
-    prof_mark(c, 2);
-    LLB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
-    prof_mark(c, 1);                                         // what is left of downsampleCurrentScan after the overlap
-    const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
-    launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
-    c->launches++;
-    if (batch_knn_variant() >= 2) {                          // kNN variants 2 / 3: queries ordered by cell / by cost
-        launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);
-        c->launches++;
-    }
-    prof_mark(c, 5);
-    for (int it = 0; it < c->prm.s2m_max_iterations; it++) {
-        launch_batch_knn(regs, B, c->knn_ctas, c->sprm, c->stream);
-        prof_mark(c, 3);
-        launch_batch_fit(regs, B, c->fit_blocks, it, c->sprm, c->stream);
-        prof_mark(c, 4);
-        c->launches += 2;
-    }
-    launch_batch_collect(regs, B, c->results.p, c->stream);
-    c->launches++;
-    prof_mark(c, 5);
     LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
     LLB_CUDA(cudaMemcpyAsync(c->pin_results.p, c->results.p, sizeof(BatchResult) * B, cudaMemcpyDeviceToHost, c->stream));
     c->pending = true;
@@ -424,6 +467,7 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         LLB_CUDA(cudaEventCreate(&c->ev0)); LLB_CUDA(cudaEventCreate(&c->ev1));
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        c->use_graph = !(getenv("LLB_BATCH_GRAPH") && atoi(getenv("LLB_BATCH_GRAPH")) == 0);
         LLB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
         LLB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
         for (int i = 0; i < 64; i++) LLB_CUDA(cudaEventCreate(&c->pev[i]));
@@ -485,6 +529,8 @@ int llb_batch_destroy(llb_batch *c)
     for (int i = 0; i < 64; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     if (c->join_ev) cudaEventDestroy(c->join_ev);
     if (c->stream2) cudaStreamDestroy(c->stream2);
