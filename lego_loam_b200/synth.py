@@ -370,3 +370,83 @@ def make_odometry_pair(world: World, sensor: Sensor, pose_start, cur_true, seed:
     inten = ring + SCAN_PERIOD * s
     return OdometryPair(_pack(p1[sharp], inten[sharp]), _pack(p1[flat], inten[flat]),
                         corner_last, surf_last, cur.astype(np.float32))
+
+
+@dataclasses.dataclass
+class SegmentedSweep:
+    """What imageProjection publishes for one sweep (IP:312-368, cloud_msgs/cloud_info): the input of FA's
+    adjustDistortion / calculateSmoothness / markOccludedPoints / extractFeatures."""
+    cloud: np.ndarray          # (n,4) float32, LIDAR frame (x fwd, y left, z up), intensity = row + col/10000
+    start_ring: np.ndarray     # (n_scan,) int32
+    end_ring: np.ndarray       # (n_scan,) int32
+    start_ori: float
+    end_ori: float
+    ori_diff: float
+    ground: np.ndarray         # (n,) uint8
+    col: np.ndarray            # (n,) uint32
+    range: np.ndarray          # (n,) float32
+    outlier: np.ndarray        # (m,4) float32
+
+
+def make_segmented_sweep(world: World, sensor: Sensor, pose, seed: int, noise: float = 0.02,
+                         dropout: float = 0.02, clutter: float = 0.03) -> SegmentedSweep:
+    """One sweep ray-cast at `pose` and packed the way imageProjection packs its segmented cloud (IP:318-356).
+
+    Ground marking and segmentation stand in for IP:260-310 / IP:370-460 (out of scope): ground = ground
+    hits on the rings up to ground_scan_ind, a random `clutter` share of the other hits plays the clusters that
+    segmentation rejects (label 999999 -> outliers on every 5th column above the ground rings)."""
+    rng = np.random.default_rng(seed)
+    pose = np.asarray(pose, np.float64)
+    d, ring, col = sensor_dirs(sensor)
+    R = rot_zxy(pose[0], pose[1], pose[2])
+    r, kind, _, _ = raycast(world, pose[3:6], d @ R.T, sensor.max_range)
+    ok = np.isfinite(r) & (rng.random(r.shape[0]) > dropout)
+    r = np.where(ok, r + rng.normal(0, noise, r.shape[0]), 0.0)
+    cam = (d * r[:, None]).astype(np.float32)
+    lid = np.stack([cam[:, 2], cam[:, 0], cam[:, 1]], 1)          # x_l = z_c, y_l = x_c, z_l = y_c
+    rngf = np.sqrt(lid[:, 0] * lid[:, 0] + lid[:, 1] * lid[:, 1] + lid[:, 2] * lid[:, 2]).astype(np.float32)
+    # column as IP:236-242 computes it from the point
+    ha = np.arctan2(lid[:, 0], lid[:, 1]).astype(np.float32) * np.float32(180.0) / np.pi
+    cidx = (-np.round((ha - 90.0) / (360.0 / sensor.horizon)) + sensor.horizon / 2).astype(np.int64)
+    cidx = np.where(cidx >= sensor.horizon, cidx - sensor.horizon, cidx)
+    ok &= (cidx >= 0) & (cidx < sensor.horizon) & (rngf >= 1.0)
+    H, N = sensor.horizon, sensor.n_scan
+    img_ok = np.zeros((N, H), bool); img_pt = np.zeros((N, H, 3), np.float32); img_r = np.zeros((N, H), np.float32)
+    img_g = np.zeros((N, H), bool); img_rej = np.zeros((N, H), bool)
+    sel = np.where(ok)[0]
+    img_ok[ring[sel], cidx[sel]] = True
+    img_pt[ring[sel], cidx[sel]] = lid[sel]
+    img_r[ring[sel], cidx[sel]] = rngf[sel]
+    img_g[ring[sel], cidx[sel]] = (kind[sel] == 1) & (ring[sel] <= sensor.ground_scan_ind)
+    img_rej[ring[sel], cidx[sel]] = (~img_g[ring[sel], cidx[sel]]) & (rng.random(sel.size) < clutter)
+    pts, grd, cols, rngs, outl = [], [], [], [], []
+    start_ring = np.zeros(N, np.int32); end_ring = np.zeros(N, np.int32)
+    size = 0
+    jj = np.arange(H)
+    for i in range(N):
+        start_ring[i] = size - 1 + 5
+        rej = img_ok[i] & img_rej[i]
+        if i > sensor.ground_scan_ind:
+            o = rej & (jj % 5 == 0)
+            outl.append(np.concatenate([img_pt[i][o], (i + jj[o] / 10000.0).astype(np.float32)[:, None]], 1))
+        keep = img_ok[i] & ~rej
+        keep &= ~(img_g[i] & (jj % 5 != 0) & (jj > 5) & (jj < H - 5))
+        k = np.where(keep)[0]
+        pts.append(np.concatenate([img_pt[i][k], (np.float32(i) + (k.astype(np.float32) / np.float32(10000.0)))[:, None]], 1))
+        grd.append(img_g[i][k]); cols.append(k); rngs.append(img_r[i][k])
+        size += k.size
+        end_ring[i] = size - 1 - 5
+    cloud = np.concatenate(pts).astype(np.float32)
+    first = lid[sel[0]]; last = lid[sel[-1]]
+    # IP:199-211 on the first / last point of the raw cloud (float members of the message)
+    start_ori = np.float32(-np.arctan2(first[1], first[0]))
+    end_ori = np.float32(-np.arctan2(last[1], last[0]) + 2 * np.pi)
+    if float(end_ori) - float(start_ori) > 3 * np.pi:
+        end_ori = np.float32(float(end_ori) - 2 * np.pi)
+    elif float(end_ori) - float(start_ori) < np.pi:
+        end_ori = np.float32(float(end_ori) + 2 * np.pi)
+    ori_diff = np.float32(end_ori - start_ori)
+    return SegmentedSweep(cloud, start_ring, end_ring, float(start_ori), float(end_ori), float(ori_diff),
+                          np.concatenate(grd).astype(np.uint8), np.concatenate(cols).astype(np.uint32),
+                          np.concatenate(rngs).astype(np.float32),
+                          np.concatenate(outl).astype(np.float32) if outl else np.zeros((0, 4), np.float32))

@@ -275,3 +275,52 @@ class FeatureAssociation:
 def set_trig_mode(mode: int):
     """0 = host libm sinf/cosf (reference-faithful on this machine), 1 = correctly rounded."""
     lib().llo_set_trig_mode(int(mode))
+
+
+# ------------------------------------------------------------------ feature extraction (SURVEY 8(f)-2)
+
+def std_sort_by_value(value, ind, depth_limit=-1):
+    """Restatement of libstdc++ std::sort on (value, ind) records compared by value only (FA:699)."""
+    v = np.ascontiguousarray(value, np.float32).copy(); i = np.ascontiguousarray(ind, np.uint32).copy()
+    lib().llo_std_sort_by_value(_fp(v), i.ctypes.data_as(ctypes.c_void_p), v.shape[0], int(depth_limit))
+    return v, i
+
+
+class FeatureExtraction:
+    """adjustDistortion (no IMU) + calculateSmoothness + markOccludedPoints + extractFeatures, FA:491-784, with the
+    state the reference keeps between sweeps."""
+
+    def __init__(self, n_scan=16, horizon=1800):
+        L = lib()
+        L.llo_features_create.restype = ctypes.c_void_p
+        self.n_scan, self.horizon = n_scan, horizon
+        self._h = ctypes.c_void_p(L.llo_features_create(n_scan, horizon))
+        self._n = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().llo_features_destroy(self._h); self._h = None
+
+    def extract(self, sw):
+        """sw: SegmentedSweep fields. -> (sharp, less_sharp, flat, less_flat, adjusted cloud)"""
+        cap = self.n_scan * self.horizon
+        cloud = _pts(sw.cloud).copy(); n = cloud.shape[0]
+        g = np.zeros(cap, np.uint8); g[:n] = sw.ground
+        col = np.zeros(cap, np.uint32); col[:n] = sw.col
+        rg = np.zeros(cap, np.float32); rg[:n] = sw.range
+        sr = np.ascontiguousarray(sw.start_ring, np.int32); er = np.ascontiguousarray(sw.end_ring, np.int32)
+        outs = [np.zeros((max(n, 1), 4), np.float32) for _ in range(4)]
+        optr = (ctypes.c_void_p * 4)(*[o.ctypes.data for o in outs])
+        cnt = (ctypes.c_int * 4)()
+        lib().llo_features_extract(self._h, _fp(cloud), n, sr.ctypes.data_as(ctypes.c_void_p), er.ctypes.data_as(ctypes.c_void_p),
+                                   ctypes.c_float(sw.start_ori), ctypes.c_float(sw.end_ori), ctypes.c_float(sw.ori_diff),
+                                   g.ctypes.data_as(ctypes.c_void_p), col.ctypes.data_as(ctypes.c_void_p), _fp(rg), optr, cnt)
+        self._n = n
+        return tuple(outs[k][:cnt[k]].copy() for k in range(4)) + (cloud,)
+
+    def point_state(self):
+        n = self._n
+        curv = np.zeros(n, np.float32); picked = np.zeros(n, np.int32); label = np.zeros(n, np.int32)
+        lib().llo_features_get_state(self._h, n, _fp(curv), picked.ctypes.data_as(ctypes.c_void_p),
+                                     label.ctypes.data_as(ctypes.c_void_p))
+        return curv, picked, label

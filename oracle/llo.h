@@ -153,6 +153,22 @@ int  llo_featassoc_get_correspondences(const llo_featassoc *f, llo_point *ori, l
 int  llo_featassoc_get_search_ind(const llo_featassoc *f, int which /*0 corner,1 surf*/,
                                   float *ind1, float *ind2, float *ind3, int cap);
 
+/* ---------------- feature extraction (llo_features.c) ---------------- */
+typedef struct llo_features llo_features;
+llo_features *llo_features_create(int n_scan, int horizon);
+void llo_features_destroy(llo_features *f);
+/* adjustDistortion (no IMU), calculateSmoothness, markOccludedPoints, extractFeatures (FA:491-784) on one segmented
+ * sweep; cloud is adjusted in place; ground/col/range hold n_scan*horizon entries (zero beyond n).
+ * out[0..3] = cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat, surfPointsLessFlat (room for n each). */
+void llo_features_extract(llo_features *f, llo_point *cloud, int n, const int *start_ring, const int *end_ring,
+                          float start_ori, float end_ori, float ori_diff,
+                          const uint8_t *ground, const uint32_t *col, const float *range,
+                          llo_point *const out[4], int n_out[4]);
+void llo_features_get_state(const llo_features *f, int n, float *curv, int *picked, int *label);
+void llo_adjust_distortion(llo_point *cloud, int n, float start_ori, float end_ori, float ori_diff, float scan_period);
+/* libstdc++ std::sort of (value, ind) records compared by value only (FA:57-61, FA:699); depth_limit < 0 = std::sort's own */
+void llo_std_sort_by_value(float *value, uint32_t *ind, int n, int depth_limit);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,6 +184,40 @@ class FeatureAssociation:
         self.L.ref_fa_get_degenerate(self._h, ctypes.byref(d), _fp(P)); return bool(d.value), P
 
     def clear_correspondences(self): self.L.ref_fa_clear_correspondences(self._h)
+
+    # ---- feature extraction (FA:491-784)
+    def n_scan(self): return self.L.ref_fa_n_scan()
+
+    def set_segmented(self, sw):
+        """sw: lego_loam_b200.synth.SegmentedSweep (or anything with its fields)."""
+        pts = _pts(sw.cloud)
+        sr = np.ascontiguousarray(sw.start_ring, np.int32); er = np.ascontiguousarray(sw.end_ring, np.int32)
+        assert sr.shape[0] == self.n_scan()
+        g = np.ascontiguousarray(sw.ground, np.uint8); col = np.ascontiguousarray(sw.col, np.uint32)
+        rg = np.ascontiguousarray(sw.range, np.float32)
+        self._n_seg = pts.shape[0]
+        self.L.ref_fa_set_segmented(self._h, _fp(pts), pts.shape[0], sr.ctypes.data_as(ctypes.c_void_p),
+                                    er.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(sw.start_ori),
+                                    ctypes.c_float(sw.end_ori), ctypes.c_float(sw.ori_diff),
+                                    g.ctypes.data_as(ctypes.c_void_p), col.ctypes.data_as(ctypes.c_void_p), _fp(rg))
+
+    def extract_features(self):
+        """adjustDistortion, calculateSmoothness, markOccludedPoints, extractFeatures (FA:1827-1833)."""
+        self.L.ref_fa_extract_features(self._h)
+
+    def feature_cloud(self, which, cap=40000):
+        """0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud."""
+        out = np.zeros((cap, 4), np.float32)
+        n = self.L.ref_fa_get_cloud(self._h, int(which), _fp(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def point_state(self):
+        n = self._n_seg
+        curv = np.zeros(n, np.float32); picked = np.zeros(n, np.int32); label = np.zeros(n, np.int32)
+        self.L.ref_fa_get_point_state(self._h, n, _fp(curv), picked.ctypes.data_as(ctypes.c_void_p),
+                                      label.ctypes.data_as(ctypes.c_void_p))
+        return curv, picked, label
     def findCorrespondingCornerFeatures(self, it): self.L.ref_fa_findCorrespondingCornerFeatures(self._h, it)
     def findCorrespondingSurfFeatures(self, it): self.L.ref_fa_findCorrespondingSurfFeatures(self._h, it)
     def calculateTransformationSurf(self, it) -> bool: return bool(self.L.ref_fa_calculateTransformationSurf(self._h, it))
@@ -201,3 +235,11 @@ class FeatureAssociation:
         a = np.zeros(max(n, 1), np.float32); b = a.copy(); c = a.copy()
         self.L.ref_fa_get_search_ind(self._h, which, _fp(a), _fp(b), _fp(c), n)
         return a[:n].copy(), b[:n].copy(), c[:n].copy()
+
+
+def std_sort(value, ind, depth_limit=-1):
+    """libstdc++ std::sort of (value, ind) records by value (FA:699); depth_limit >= 0: its introsort loop with that limit."""
+    L = _lib(_FA, "ref_fa_create")
+    v = np.ascontiguousarray(value, np.float32).copy(); i = np.ascontiguousarray(ind, np.uint64).copy()
+    L.ref_fa_std_sort(_fp(v), i.ctypes.data_as(ctypes.c_void_p), v.shape[0], int(depth_limit))
+    return v, i

@@ -28,7 +28,20 @@ int dump(const pcl::PointCloud<PointType>::Ptr &c, llo_point *out, int cap)
 }  // namespace
 
 extern "C" {
-void *ref_fa_create() { return new FeatureAssociation(); }
+void *ref_fa_create()
+{
+    FeatureAssociation *f = new FeatureAssociation();
+    // the reference reads cloudCurvature / cloudNeighborPicked / cloudLabel at indices its calculateSmoothness never
+    // writes (index 0..4, FA:624 vs FA:688): `new T[]` leaves them uninitialised, the harness defines them as zero
+    memset(f->cloudCurvature, 0, sizeof(float) * N_SCAN * Horizon_SCAN);
+    // ... and it writes cloudNeighborPicked[-1..-5] when the stale smoothness record {0, 0} is picked (FA:766-773 with
+    // ind = 0): give the array 16 entries of slack in front so that this stays inside the harness's own memory
+    delete[] f->cloudNeighborPicked;
+    f->cloudNeighborPicked = (new int[N_SCAN * Horizon_SCAN + 16]) + 16;
+    memset(f->cloudNeighborPicked - 16, 0, sizeof(int) * (N_SCAN * Horizon_SCAN + 16));
+    memset(f->cloudLabel, 0, sizeof(int) * N_SCAN * Horizon_SCAN);
+    return f;
+}
 void ref_fa_destroy(void *h) { delete (FeatureAssociation *)h; }
 // laserCloudCornerLast / SurfLast + the statements of FA:1615-1619 (force) or FA:1782-1788
 void ref_fa_set_last(void *h, const llo_point *c, int nc, const llo_point *s, int ns, int force)
@@ -80,6 +93,60 @@ int ref_fa_get_search_ind(void *h, int which, float *i1, float *i2, float *i3, i
     }
     return n;
 }
+// ---- feature extraction: segmentedCloud + segInfo in (as laserCloudHandler / laserCloudInfoHandler
+// leave them, FA:461-489), then the statements of runFeatureAssociation FA:1827-1833
+int ref_fa_n_scan() { return N_SCAN; }
+int ref_fa_horizon_scan() { return Horizon_SCAN; }
+void ref_fa_set_segmented(void *h, const llo_point *pts, int n, const int *start_ring, const int *end_ring,
+                          float start_ori, float end_ori, float ori_diff,
+                          const unsigned char *ground, const unsigned *col, const float *range)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    fill(f->segmentedCloud, pts, n);
+    cloud_msgs::cloud_info &s = f->segInfo;
+    s.startRingIndex.assign(start_ring, start_ring + N_SCAN);
+    s.endRingIndex.assign(end_ring, end_ring + N_SCAN);
+    s.startOrientation = start_ori; s.endOrientation = end_ori; s.orientationDiff = ori_diff;
+    s.segmentedCloudGroundFlag.assign(N_SCAN * Horizon_SCAN, 0);     // sized as IP:141-143 sizes them
+    s.segmentedCloudColInd.assign(N_SCAN * Horizon_SCAN, 0);
+    s.segmentedCloudRange.assign(N_SCAN * Horizon_SCAN, 0);
+    for (int i = 0; i < n; i++) { s.segmentedCloudGroundFlag[i] = ground[i]; s.segmentedCloudColInd[i] = col[i]; s.segmentedCloudRange[i] = range[i]; }
+}
+void ref_fa_extract_features(void *h)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    f->adjustDistortion(); f->calculateSmoothness(); f->markOccludedPoints(); f->extractFeatures();
+}
+int ref_fa_get_cloud(void *h, int which, llo_point *out, int cap)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    switch (which) {
+    case 0: return dump(f->cornerPointsSharp, out, cap);
+    case 1: return dump(f->cornerPointsLessSharp, out, cap);
+    case 2: return dump(f->surfPointsFlat, out, cap);
+    case 3: return dump(f->surfPointsLessFlat, out, cap);
+    default: return dump(f->segmentedCloud, out, cap);
+    }
+}
+void ref_fa_get_point_state(void *h, int n, float *curv, int *picked, int *label)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    for (int i = 0; i < n; i++) { curv[i] = f->cloudCurvature[i]; picked[i] = f->cloudNeighborPicked[i]; label[i] = f->cloudLabel[i]; }
+}
+// libstdc++'s own sort of (value, ind) records by value, as FA:699 calls it; depth_limit >= 0 drives the internal
+// introsort loop with that limit so that tests reach its heap-sort branch
+void ref_fa_std_sort(float *value, unsigned long long *ind, int n, int depth_limit)
+{
+    std::vector<smoothness_t> v(n);
+    for (int i = 0; i < n; i++) { v[i].value = value[i]; v[i].ind = ind[i]; }
+    if (depth_limit < 0) std::sort(v.begin(), v.end(), by_value());
+    else if (n > 0) {
+        std::__introsort_loop(v.begin(), v.end(), (long)depth_limit, __gnu_cxx::__ops::__iter_comp_iter(by_value()));
+        std::__final_insertion_sort(v.begin(), v.end(), __gnu_cxx::__ops::__iter_comp_iter(by_value()));
+    }
+    for (int i = 0; i < n; i++) { value[i] = v[i].value; ind[i] = v[i].ind; }
+}
+
 // the per-sweep bookkeeping around the matcher, for sequence replays (FA:1639-1725, FA:1759-1788)
 void ref_fa_integrateTransformation(void *h) { ((FeatureAssociation *)h)->integrateTransformation(); }
 void ref_fa_get_transform_sum(void *h, float *t) { memcpy(t, ((FeatureAssociation *)h)->transformSum, 24); }

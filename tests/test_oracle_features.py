@@ -1,0 +1,70 @@
+"""Feature-extraction oracle: the C restatement (oracle/llo_features.c) against the UNMODIFIED reference
+featureAssociation.cpp compiled in oracle/_ref (adjustDistortion, calculateSmoothness, markOccludedPoints,
+extractFeatures, FA:491-784) and the std::sort restatement against libstdc++ itself."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref_harness as rh
+from lego_loam_b200 import synth
+
+needs_ref = pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+
+
+def sweeps(n, quantize=None, seed=3):
+    w = synth.make_world()
+    out = []
+    for k in range(n):
+        pose = [0.002 * k, 0.05 + 0.01 * k, 0.001 * k, 3 + 0.4 * k, 0, 5 + 0.2 * k]
+        sw = synth.make_segmented_sweep(w, synth.VLP16, pose, seed + k)
+        if quantize:
+            sw = dataclasses.replace(sw, range=(np.round(sw.range / quantize) * quantize).astype(np.float32))
+        out.append(sw)
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("n,depth", [(0, -1), (1, -1), (2, -1), (16, -1), (17, -1), (300, -1), (1000, -1), (300, 0), (300, 1),
+                                     (300, 3), (1000, 2), (33, 0)])
+def test_std_sort_restatement_matches_libstdcxx(n, depth):
+    rng = np.random.default_rng(n * 7 + depth + 1)
+    for levels in (3, 17, 1000, 0):
+        for shape in ("random", "sorted", "reverse", "pipe"):
+            if levels:
+                v = rng.integers(0, levels, n).astype(np.float32) * np.float32(0.25)
+            else:
+                v = rng.random(n).astype(np.float32)
+            if shape == "sorted": v = np.sort(v)
+            if shape == "reverse": v = np.sort(v)[::-1].copy()
+            if shape == "pipe": v = np.concatenate([np.sort(v[: n // 2]), np.sort(v[n // 2:])[::-1]])
+            ind = np.arange(n)
+            rv, ri = rh.std_sort(v, ind, depth)
+            ov, oi = oracle.std_sort_by_value(v, ind, depth)
+            assert np.array_equal(rv, ov)
+            assert np.array_equal(ri.astype(np.int64), oi.astype(np.int64))     # same order among equal values
+            assert np.all(np.diff(ov) >= 0)
+
+
+@needs_ref
+@pytest.mark.parametrize("quantize", [None, 0.02, 0.1])
+def test_feature_extraction_restatement_matches_reference(quantize):
+    """Five consecutive sweeps through ONE reference object and ONE restatement object (state survives between sweeps):
+    every cloud bit-identical, in the reference's order; quantised ranges make equal curvatures (sort ties) common."""
+    fa = rh.FeatureAssociation(); fe = oracle.FeatureExtraction(16, 1800)
+    ties = 0
+    for sw in sweeps(5, quantize):
+        fa.set_segmented(sw); fa.extract_features()
+        got = fe.extract(sw)
+        for k in range(5):
+            ref = fa.feature_cloud(k)
+            assert ref.shape == got[k].shape, (k, ref.shape, got[k].shape)
+            assert np.array_equal(ref.view(np.uint32), got[k].view(np.uint32)), k
+        for a, b in zip(fa.point_state(), fe.point_state()):
+            assert np.array_equal(a, b)
+        curv = fe.point_state()[0]
+        ties += curv.size - np.unique(curv).size
+        assert got[0].shape[0] > 50 and got[2].shape[0] > 50 and got[3].shape[0] > 2000
+    if quantize:
+        assert ties > 1000
