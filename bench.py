@@ -370,6 +370,55 @@ def odometry_arm(api, local, reps, cpu_sample):
                     "(redundant iteration loop, correspondence search split by feature); batched: one CTA per pair"}
 
 
+def feature_extraction_arm(api, local, reps, cpu_sample):
+    """Secondary arm for the next row of the path: adjustDistortion + calculateSmoothness +
+    markOccludedPoints + extractFeatures (FA:491-784) of one segmented VLP-16 sweep: device time, wall time through the
+    C ABI with host buffers (segmented cloud + cloud_info in, four feature clouds out), and the reference's own
+    functions on one core."""
+    from lego_loam_b200 import synth
+    w = synth.make_world(synth.SEED0)
+    sws = [synth.make_segmented_sweep(w, synth.VLP16, [0, 0.05 + 0.01 * k, 0, 3 + 0.4 * k, 0, 5], 11 + k) for k in range(4)]
+    c = api.Context(local); c.features_init(16, 1800)
+    dev_ms, wall_ms = [], []
+    for i in range(reps + 3):
+        t0 = time.perf_counter()
+        counts, ms = c.features_extract(sws[i % 4])
+        if i >= 3:
+            wall_ms.append((time.perf_counter() - t0) * 1e3); dev_ms.append(ms)
+    got = [c.features_get(k) for k in range(4)]
+    last = sws[(reps + 2) % 4]
+    c.close()
+    kind, fa = "port", None
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            kind = "reference"; fa = ref_harness.FeatureAssociation()
+    except Exception:
+        pass
+    if fa is None:
+        import oracle
+        fe = oracle.FeatureExtraction(16, 1800)
+        run = lambda sw: fe.extract(sw)[:4]
+    else:
+        def run(sw):
+            fa.set_segmented(sw); fa.extract_features()
+            return [fa.feature_cloud(k) for k in range(4)]
+    # same sweep sequence through ONE CPU object (state survives between sweeps, as on the device)
+    cpu_t = []
+    for i in range(reps + 3):
+        t0 = time.perf_counter(); ref = run(sws[i % 4]); cpu_t.append((time.perf_counter() - t0) * 1e3)
+    same_xyz = all(g.shape == r.shape and np.array_equal(g[:, :3].view(np.uint32), np.asarray(r)[:, :3].view(np.uint32))
+                   for g, r in zip(got, ref))
+    dint = max(float(np.max(np.abs(g[:, 3] - np.asarray(r)[:, 3]))) if g.size and g.shape == r.shape else 0.0 for g, r in zip(got, ref))
+    return {"ms_per_sweep_device": float(np.median(dev_ms)), "ms_per_sweep_e2e_host": float(np.median(wall_ms)),
+            "points": int(last.cloud.shape[0]), "counts": [int(x) for x in counts],
+            "cpu_1core": {"ms_per_sweep": float(np.median(cpu_t[3:])), "kind": kind,
+                          "sample": f"{reps} sweeps (includes the harness copies of the clouds in and out)"},
+            "selection_and_xyz_identical_to_cpu": bool(same_xyz), "intensity_max_abs_diff_vs_cpu": dint,
+            "note": "5 launches per sweep: per-point kernels, one CTA per ring (sector sorts = libstdc++ std::sort move "
+                    "for move, greedy picks 32 candidates per step), per-ring VoxelGrid(0.2), concatenation"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -590,6 +639,12 @@ def main():
             od_arm = odometry_arm(api, local, 20, 10)
         except Exception as e:
             od_arm = {"error": repr(e)}
+    fe_arm = None
+    if rank == 0:
+        try:
+            fe_arm = feature_extraction_arm(api, local, 20, 10)
+        except Exception as e:
+            fe_arm = {"error": repr(e)}
     if world > 1:
         dist.barrier()
 
@@ -680,6 +735,7 @@ def main():
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
             "mapping_cycle": mc_arm,
             "odometry": od_arm,
+            "feature_extraction": fe_arm,
         }
         print(json.dumps(line))
     if world > 1:

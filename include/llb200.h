@@ -174,6 +174,33 @@ int llb_map_assemble(llb_ctx *ctx, const int *ids, const float *poses, int n);
 /* laserCloudCornerFromMap (0) / laserCloudSurfFromMap (1) of the last llb_map_assemble (parity checks) */
 int llb_map_get_raw(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
 
+/* ---- featureAssociation: feature extraction ----
+ * What laserCloudHandler / laserCloudInfoHandler leave in the node (FA:461-489): segmentedCloud in the LIDAR frame with
+ * intensity = row + col / 10000 (IP:253), and cloud_msgs::cloud_info. */
+typedef struct {
+    const llb_point *cloud; int n;          /* segmentedCloud */
+    const int *start_ring, *end_ring;       /* startRingIndex / endRingIndex, n_scan entries each (IP:318, IP:358) */
+    float start_orientation, end_orientation, orientation_diff;   /* IP:199-211 */
+    const unsigned char *ground_flag;       /* segmentedCloudGroundFlag[n] */
+    const unsigned *col_ind;                /* segmentedCloudColInd[n] */
+    const float *range;                     /* segmentedCloudRange[n] */
+} llb_segmented_cloud;
+/* N_SCAN / Horizon_SCAN (UT:63-84); allocates the per-point state the reference keeps between sweeps (FA:210-223) */
+int llb_features_init(llb_ctx *ctx, int n_scan, int horizon_scan);
+/* adjustDistortion (no IMU data: imuPointerLast < 0, FA:525), calculateSmoothness, markOccludedPoints, extractFeatures
+ * = runFeatureAssociation FA:1827-1833.  counts = sizes of cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat,
+ * surfPointsLessFlat.  Selection, order and coordinates are bit-identical to the reference (std::sort's order of equal
+ * curvatures included); the time part of the intensity goes through atan2, taken correctly rounded here. */
+int llb_features_extract(llb_ctx *ctx, const llb_segmented_cloud *seg, int counts[4], float *device_ms);
+/* which: 0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud after
+ * adjustDistortion */
+int llb_features_get(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+/* cloudCurvature / cloudNeighborPicked / cloudLabel of the last sweep (parity checks) */
+int llb_features_get_state(llb_ctx *ctx, float *curvature, int *neighbor_picked, int *label, int capacity);
+/* cornerPointsSharp / surfPointsFlat of the last extraction become the odometry's features without leaving the device
+ * (= llb_odom_set_features on them) */
+int llb_features_to_odometry(llb_ctx *ctx);
+
 /* ---- featureAssociation ---- */
 /* laserCloudCornerLast / laserCloudSurfLast + kdtree rebuild (FA:1615-1619, FA:1774-1788) */
 int llb_odom_set_last(llb_ctx *ctx, const llb_point *corner_last, int ncl, const llb_point *surf_last, int nsl);

@@ -67,6 +67,7 @@ EXPORTS = [
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
+    "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry",
     "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
     "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
@@ -107,6 +108,14 @@ def lib() -> ctypes.CDLL:
             getattr(L, name)   # raises AttributeError if a declared symbol is missing
         _lib = L
     return _lib
+
+
+class SegmentedCloud(ctypes.Structure):
+    """llb_segmented_cloud"""
+    _fields_ = [("cloud", ctypes.c_void_p), ("n", ctypes.c_int), ("start_ring", ctypes.c_void_p),
+                ("end_ring", ctypes.c_void_p), ("start_orientation", ctypes.c_float), ("end_orientation", ctypes.c_float),
+                ("orientation_diff", ctypes.c_float), ("ground_flag", ctypes.c_void_p), ("col_ind", ctypes.c_void_p),
+                ("range", ctypes.c_void_p)]
 
 
 def to_pcl(pts) -> np.ndarray:
@@ -322,6 +331,40 @@ class Context:
     def odom_set_last(self, corner_last, surf_last):
         c = to_pcl(corner_last); s = to_pcl(surf_last)
         self._ck(lib().llb_odom_set_last(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    # ---- feature extraction (FA:491-784)
+    def features_init(self, n_scan: int, horizon_scan: int):
+        self._ck(lib().llb_features_init(self._h, int(n_scan), int(horizon_scan)))
+
+    def features_extract(self, sw):
+        """sw: a SegmentedSweep (lego_loam_b200.synth) or anything with its fields.  -> (counts[4], device_ms)"""
+        seg = SegmentedCloud()
+        keep = [to_pcl(sw.cloud), np.ascontiguousarray(sw.start_ring, np.int32), np.ascontiguousarray(sw.end_ring, np.int32),
+                np.ascontiguousarray(sw.ground, np.uint8), np.ascontiguousarray(sw.col, np.uint32),
+                np.ascontiguousarray(sw.range, np.float32)]
+        seg.cloud = _vp(keep[0]); seg.n = keep[0].shape[0]
+        seg.start_ring = _vp(keep[1]); seg.end_ring = _vp(keep[2])
+        seg.start_orientation = sw.start_ori; seg.end_orientation = sw.end_ori; seg.orientation_diff = sw.ori_diff
+        seg.ground_flag = _vp(keep[3]); seg.col_ind = _vp(keep[4]); seg.range = _vp(keep[5])
+        counts = (ctypes.c_int * 4)(); ms = ctypes.c_float(0)
+        self._ck(lib().llb_features_extract(self._h, ctypes.byref(seg), counts, ctypes.byref(ms)))
+        return list(counts), float(ms.value)
+
+    def features_get(self, which: int):
+        """0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 adjusted segmentedCloud"""
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_features_get(self._h, int(which), None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_features_get(self._h, int(which), _vp(out), out.shape[0], ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    def features_get_state(self, n: int):
+        curv = np.zeros(max(n, 1), np.float32); picked = np.zeros(max(n, 1), np.int32); label = np.zeros(max(n, 1), np.int32)
+        self._ck(lib().llb_features_get_state(self._h, _vp(curv), _vp(picked), _vp(label), curv.shape[0]))
+        return curv[:n], picked[:n], label[:n]
+
+    def features_to_odometry(self):
+        self._ck(lib().llb_features_to_odometry(self._h))
 
     def odom_set_features(self, sharp, flat):
         c = to_pcl(sharp); s = to_pcl(flat)

@@ -9,6 +9,7 @@
 #include "s2m.cuh"
 #include "odom.cuh"
 #include "keyframes.cuh"
+#include "features.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -89,6 +90,9 @@ struct llb_ctx {
     DevBuf<float4> tmp_vox;
 
     OdomSolver odom;
+    FeatureExtractor features;
+    bool features_done = false;
+    float features_ms = 0.f;
 
     // device-resident key-frame store + assembled raw local map
     KeyFrameStore kfs;
@@ -399,6 +403,7 @@ int llb_destroy(llb_ctx *c)
     c->dbg_coeff.release(); c->dbg_valid.release(); c->dbg_knn.release(); c->dbg_d2.release(); c->tmp_vox.release();
     for (int r = 0; r < S2M_MAX_PEERS; r++) if (c->p2p_opened[r]) cudaIpcCloseMemHandle(c->p2p_opened[r]);
     if (c->p2p_mem) cudaFree(c->p2p_mem);
+    c->features.release();
     c->kfs.release(); c->asmCorner.release(); c->asmSurf.release(); c->asm_segs.release(); c->pin_segs.release();
     if (c->asm_ev) cudaEventDestroy(c->asm_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1081,6 +1086,86 @@ int llb_odom_set_features(llb_ctx *c, const llb_point *sharp, int nsharp, const 
         upload_cloud(c, 0, sharp, nsharp, c->odom.sharp());
         upload_cloud(c, 1, flat, nflat, c->odom.flat());
         c->odom.set_features(nsharp, nflat);
+        return (int)LLB_OK;
+    });
+}
+
+// ---------------------------------------------------------------- feature extraction
+int llb_features_init(llb_ctx *c, int n_scan, int horizon_scan)
+{
+    return guarded(c, [&]() {
+        if (n_scan <= 0 || n_scan > FE_MAX_RINGS || horizon_scan < 16 || horizon_scan > 4096) return (int)LLB_ERR_INVALID;
+        c->features.init(n_scan, horizon_scan, c->stream);
+        c->features_done = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_extract(llb_ctx *c, const llb_segmented_cloud *seg, int counts[4], float *device_ms)
+{
+    return guarded(c, [&]() {
+        if (!seg || seg->n < 0) return (int)LLB_ERR_INVALID;
+        if (!c->features.ready()) return (int)LLB_ERR_STATE;
+        if (seg->n > c->features.n_scan() * c->features.horizon()) return (int)LLB_ERR_CAPACITY;
+        if (!seg->start_ring || !seg->end_ring) return (int)LLB_ERR_INVALID;
+        if (seg->n > 0 && (!seg->cloud || !seg->ground_flag || !seg->col_ind || !seg->range)) return (int)LLB_ERR_INVALID;
+        // ring bounds must stay inside the cloud (IP:318, IP:358): the kernels index with them
+        for (int r = 0; r < c->features.n_scan(); r++)
+            if (seg->start_ring[r] < 4 || seg->end_ring[r] > seg->n - 6 || seg->end_ring[r] - seg->start_ring[r] > c->features.horizon())
+                return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->features.extract(reinterpret_cast<const float *>(seg->cloud), seg->n, seg->start_ring, seg->end_ring,
+                                           seg->start_orientation, seg->end_orientation, seg->orientation_diff,
+                                           seg->ground_flag, seg->col_ind, seg->range, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        LLB_CUDA(cudaEventElapsedTime(&c->features_ms, c->ev0, c->ev1));
+        c->features_done = true;
+        if (counts) for (int k = 0; k < 4; k++) counts[k] = c->features.counts()[k];
+        if (device_ms) *device_ms = c->features_ms;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_get(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 4) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        const int cnt = which == 4 ? c->features.n_points() : c->features.counts()[which];
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        if (which == 4) { download_cloud(c, c->features.dev_cloud(4), cnt, out); return (int)LLB_OK; }
+        const float4 *src = c->features.host_cloud(which);
+        for (int i = 0; i < cnt; i++) {
+            out[i].x = src[i].x; out[i].y = src[i].y; out[i].z = src[i].z; out[i].w = 1.0f;
+            out[i].intensity = src[i].w; out[i].c1 = out[i].c2 = out[i].c3 = 0.f;
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_get_state(llb_ctx *c, float *curvature, int *neighbor_picked, int *label, int cap)
+{
+    return guarded(c, [&]() {
+        if (!curvature || !neighbor_picked || !label) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        if (c->features.n_points() > cap) return (int)LLB_ERR_CAPACITY;
+        c->features.get_state(curvature, neighbor_picked, label, c->features.n_points(), c->stream);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_to_odometry(llb_ctx *c)
+{
+    return guarded(c, [&]() {
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        const int ns = c->features.counts()[0], nf = c->features.counts()[2];
+        c->odom.sharp().ensure(std::max(ns, 1)); c->odom.flat().ensure(std::max(nf, 1));
+        if (ns > 0) LLB_CUDA(cudaMemcpyAsync(c->odom.sharp().p, c->features.dev_cloud(0), sizeof(float4) * ns, cudaMemcpyDeviceToDevice, c->stream));
+        if (nf > 0) LLB_CUDA(cudaMemcpyAsync(c->odom.flat().p, c->features.dev_cloud(2), sizeof(float4) * nf, cudaMemcpyDeviceToDevice, c->stream));
+        c->odom.set_features(ns, nf);
         return (int)LLB_OK;
     });
 }

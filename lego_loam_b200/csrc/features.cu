@@ -1,0 +1,396 @@
+// features.cu — see features.cuh.  Every statement cites the reference line it restates; arithmetic types follow the
+// reference's C++ promotion rules (float members compared against double M_PI expressions, FA:506-519).
+#include "features.cuh"
+#include "std_sort.cuh"
+#include <climits>
+#include <cstring>
+#include <cstddef>
+#include <vector>
+#include <algorithm>
+
+namespace llb {
+
+namespace {
+
+constexpr int FE_TPB = 256;
+constexpr int FE_RING_THREADS = 192;      // 6 warps: one per sector for the sorts
+constexpr double FE_PI = 3.14159265358979323846;
+
+__device__ __forceinline__ float fe_range(const FeView &v, int i) { return (i >= 0 && i < v.n) ? __ldg(v.range + i) : 0.f; }
+__device__ __forceinline__ unsigned fe_col(const FeView &v, int i) { return (i >= 0 && i < v.n) ? __ldg(v.col + i) : 0u; }
+__device__ __forceinline__ int fe_ground(const FeView &v, int i) { return (i >= 0 && i < v.n) ? (int)__ldg(v.ground + i) : 0; }
+__device__ __forceinline__ int fe_col_diff(const FeView &v, int a, int b)
+{   // std::abs(int(ColInd[a] - ColInd[b])) on uint32 members, FA:651
+    return abs((int)(fe_col(v, a) - fe_col(v, b)));
+}
+
+// orientation of a point before the half-sweep test, FA:504-509
+__device__ __forceinline__ float fe_ori_first_half(float ori, float start_ori)
+{
+    if ((double)ori < (double)start_ori - FE_PI / 2) ori = (float)((double)ori + 2 * FE_PI);
+    else if ((double)ori > (double)start_ori + FE_PI * 3 / 2) ori = (float)((double)ori - 2 * FE_PI);
+    return ori;
+}
+
+__global__ void __launch_bounds__(FE_TPB) fe_point_kernel(FeView v)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+        const float4 q = __ldg(v.cloud_in + i);
+        // point.x = y, point.z = x; ori = -atan2(point.x, point.z) (float overload), FA:500-504
+        const float ori = -(float)atan2((double)q.y, (double)q.x);
+        v.ori[i] = ori;
+        const float a = fe_ori_first_half(ori, v.start_ori);
+        if ((double)(a - v.start_ori) > FE_PI) atomicMin(&v.hdr->first_half, i);      // FA:511-512
+        if (i >= 5 && i < v.n - 5) {                                                    // FA:624-640
+            const float r0 = __ldg(v.range + i);
+            float d = __ldg(v.range + i - 5) + __ldg(v.range + i - 4);
+            d = d + __ldg(v.range + i - 3); d = d + __ldg(v.range + i - 2); d = d + __ldg(v.range + i - 1);
+            d = d - r0 * 10;
+            d = d + __ldg(v.range + i + 1); d = d + __ldg(v.range + i + 2); d = d + __ldg(v.range + i + 3);
+            d = d + __ldg(v.range + i + 4); d = d + __ldg(v.range + i + 5);
+            const float c = d * d;
+            v.curv[i] = c; v.picked[i] = 0; v.label[i] = 0;
+            v.smooth[i] = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(FeView v)
+{
+    const int half = v.hdr->first_half;       // the point at which halfPassed becomes true still takes the first branch
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+        const float4 q = __ldg(v.cloud_in + i);
+        float ori = v.ori[i];
+        if (i <= half) ori = fe_ori_first_half(ori, v.start_ori);
+        else {                                                                          // FA:514-520
+            ori = (float)((double)ori + 2 * FE_PI);
+            if ((double)ori < (double)v.end_ori - FE_PI * 3 / 2) ori = (float)((double)ori + 2 * FE_PI);
+            else if ((double)ori > (double)v.end_ori + FE_PI / 2) ori = (float)((double)ori - 2 * FE_PI);
+        }
+        const float rel = (ori - v.start_ori) / v.ori_diff;                            // FA:522
+        float4 p;
+        p.x = q.y; p.y = q.z; p.z = q.x;                                               // FA:500-502
+        p.w = (float)(int)q.w + v.prm.scan_period * rel;                               // FA:523
+        v.cloud_adj[i] = p;
+        if (i >= 5 && i < v.n - 6) {                                                    // FA:647-677
+            const float d1 = __ldg(v.range + i), d2 = __ldg(v.range + i + 1);
+            if (fe_col_diff(v, i + 1, i) < 10) {
+                if ((double)(d1 - d2) > 0.3) { for (int k = -5; k <= 0; k++) v.picked[i + k] = 1; }
+                else if ((double)(d2 - d1) > 0.3) { for (int k = 1; k <= 6; k++) v.picked[i + k] = 1; }
+            }
+            const float f1 = fabsf(__ldg(v.range + i - 1) - d1), f2 = fabsf(d2 - d1);
+            if ((double)f1 > 0.02 * (double)d1 && (double)f2 > 0.02 * (double)d1) v.picked[i] = 1;
+        }
+    }
+}
+
+struct PickWindow { unsigned char *s; int w0, w1; volatile int *g; int cap; };
+__device__ __forceinline__ int pk_get(const PickWindow &w, int i)
+{
+    if (i >= w.w0 && i < w.w1) return w.s[i - w.w0];
+    return (i >= 0 && i < w.cap) ? w.g[i] : 1;
+}
+__device__ __forceinline__ void pk_set(const PickWindow &w, int i)
+{
+    if (i >= w.w0 && i < w.w1) w.s[i - w.w0] = 1;
+    else if (i >= 0 && i < w.cap) w.g[i] = 1;
+}
+// FA:727-740 == FA:758-773
+__device__ void fe_mark_neighbors(const FeView &v, const PickWindow &w, int ind)
+{
+    pk_set(w, ind);
+    for (int l = 1; l <= 5; l++) {
+        if (fe_col_diff(v, ind + l, ind + l - 1) > 10) break;
+        pk_set(w, ind + l);
+    }
+    for (int l = -1; l >= -5; l--) {
+        if (ind + l < 0) break;      // only reachable through the stale record {0, 0}: the reference is undefined there
+        if (fe_col_diff(v, ind + l, ind + l + 1) > 10) break;
+        pk_set(w, ind + l);
+    }
+}
+
+__device__ __forceinline__ void fe_sector(int st, int en, int j, int &sp, int &ep)
+{   // FA:693-694
+    sp = (st * (6 - j) + en * j) / 6;
+    ep = (st * (5 - j) + en * (j + 1)) / 6 - 1;
+}
+
+__global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
+{
+    extern __shared__ __align__(16) unsigned long long s_rec[];                       // [horizon + 8]
+    unsigned char *s_pk = reinterpret_cast<unsigned char *>(s_rec + v.horizon + 8);    // [horizon + 32]
+    __shared__ int s_tot[FE_RING_THREADS / 32];
+    __shared__ int s_owner, s_late;
+    const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int st = __ldg(v.start_ring + ring), en = __ldg(v.end_ring + ring);
+    // the record at position 4 is never rewritten by calculateSmoothness (FA:624 starts at 5) while sector 0 of the
+    // first populated ring starts there (IP:318): it is state from earlier sweeps and may name a point of another
+    // ring.  The ring that sorts it ("owner") then finishes its picks before the other rings read their flags.
+    if (tid == 0) {
+        int owner = -1;
+        for (int r = 0; r < v.n_scan; r++) {
+            int sp, ep; fe_sector(__ldg(v.start_ring + r), __ldg(v.end_ring + r), 0, sp, ep);
+            if (sp == 4 && sp < ep) { owner = r; break; }
+        }
+        s_owner = owner; s_late = 0;
+    }
+    const int w0 = max(0, st - 6), w1 = max(w0, min(v.cap, en + 7));
+    const int nrec = max(0, en - st);                    // positions [st, en - 1] = [sp_0, ep_5]
+    for (int k = tid; k < nrec; k += FE_RING_THREADS) s_rec[k] = v.smooth[st + k];
+    __syncthreads();
+    const int owner = s_owner;
+    if (owner == ring && tid == 0) {
+        const int stale = (int)(unsigned)s_rec[0];
+        if (stale >= w0 && stale < w1) { __threadfence(); atomicExch(&v.hdr->release_seq, v.seq); }
+        else s_late = 1;
+    }
+    // ---- the six sorts, one warp each (single thread: the order of equal keys is defined by the sequential algorithm)
+    if (warp < 6 && lane == 0) {
+        int sp, ep; fe_sector(st, en, warp, sp, ep);
+        if (sp < ep) stdsort::sort(s_rec + (sp - st), ep - sp);                         // FA:699: [sp, ep)
+    }
+    if (owner >= 0 && owner != ring && tid == 0) {
+        volatile int *flag = &v.hdr->release_seq;
+        while (*flag != v.seq) __nanosleep(100);
+        __threadfence();
+    }
+    __syncthreads();
+    for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) s_pk[k - w0] = (unsigned char)(((volatile int *)v.picked)[k] != 0);
+    __syncthreads();
+    PickWindow w{ s_pk, w0, w1, (volatile int *)v.picked, v.cap };
+    // ---- greedy picks, sectors in order (a pick of sector j may block neighbours that belong to sector j+1)
+    if (warp == 0) {
+        int nsharp = 0, nls = 0, nflat = 0;
+        for (int j = 0; j < 6; j++) {
+            int sp, ep; fe_sector(st, en, j, sp, ep);
+            if (sp >= ep) continue;
+            int cnt = 0;
+            for (int khi = ep; khi >= sp && cnt < 20; khi -= 32) {                       // FA:701-742
+                const int k = khi - lane;
+                const bool valid = k >= sp;
+                const int ind = valid ? (int)(unsigned)s_rec[k - st] : 0;
+                bool stat = valid && v.curv[ind] > v.prm.edge_threshold && fe_ground(v, ind) == 0;
+                for (;;) {
+                    const bool el = stat && pk_get(w, ind) == 0;
+                    const unsigned b = __ballot_sync(FULL, el);
+                    if (!b) break;
+                    const int f = __ffs(b) - 1;
+                    if (lane == f) {
+                        const float4 p = v.cloud_adj[ind];
+                        v.label[ind] = cnt < 2 ? 2 : 1;
+                        if (cnt < 2) v.r_sharp[ring * FE_SHARP_PER_RING + nsharp] = p;
+                        v.r_lsharp[ring * FE_LSHARP_PER_RING + nls] = p;
+                        fe_mark_neighbors(v, w, ind);
+                    }
+                    __syncwarp();
+                    if (cnt < 2) nsharp++;
+                    nls++; cnt++;
+                    if (cnt >= 20) break;
+                    if (lane <= f) stat = false;
+                }
+            }
+            cnt = 0;
+            bool done = false;
+            for (int klo = sp; klo <= ep && !done; klo += 32) {                          // FA:744-775
+                const int k = klo + lane;
+                const bool valid = k <= ep;
+                const int ind = valid ? (int)(unsigned)s_rec[k - st] : 0;
+                bool stat = valid && v.curv[ind] < v.prm.surf_threshold && fe_ground(v, ind) != 0;
+                for (;;) {
+                    const bool el = stat && pk_get(w, ind) == 0;
+                    const unsigned b = __ballot_sync(FULL, el);
+                    if (!b) break;
+                    const int f = __ffs(b) - 1;
+                    if (lane == f) {
+                        v.label[ind] = -1;
+                        v.r_flat[ring * FE_FLAT_PER_RING + nflat] = v.cloud_adj[ind];
+                        if (cnt + 1 < 4) fe_mark_neighbors(v, w, ind);               // the 4th pick breaks before the marks
+                    }
+                    __syncwarp();
+                    nflat++; cnt++;
+                    if (cnt >= 4) { done = true; break; }
+                    if (lane <= f) stat = false;
+                }
+            }
+        }
+        if (lane == 0) { v.r_cnt[ring * 4 + 0] = nsharp; v.r_cnt[ring * 4 + 1] = nls; v.r_cnt[ring * 4 + 2] = nflat; }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0 && owner == ring && s_late) atomicExch(&v.hdr->release_seq, v.seq);
+    }
+    __syncthreads();
+    // state back: flags set by this ring, records in sorted order
+    for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) if (s_pk[k - w0]) v.picked[k] = 1;
+    for (int k = tid; k < nrec; k += FE_RING_THREADS) v.smooth[st + k] = s_rec[k];
+    // ---- surfPointsLessFlatScan: points with label <= 0 of the sectors that were processed, in index order, FA:777-781
+    int base = 0;
+    for (int j = 0; j < 6; j++) {
+        int sp, ep; fe_sector(st, en, j, sp, ep);
+        if (sp >= ep) continue;
+        for (int k0 = sp; k0 <= ep; k0 += FE_RING_THREADS) {
+            const int k = k0 + tid;
+            const bool flag = k <= ep && v.label[k] <= 0;
+            const unsigned b = __ballot_sync(FULL, flag);
+            if (lane == 0) s_tot[warp] = __popc(b);
+            __syncthreads();
+            int off = 0, tot = 0;
+#pragma unroll
+            for (int q = 0; q < FE_RING_THREADS / 32; q++) { if (q < warp) off += s_tot[q]; tot += s_tot[q]; }
+            if (flag) v.r_lf_scan[(size_t)ring * v.horizon + base + off + __popc(b & ((1u << lane) - 1))] = v.cloud_adj[k];
+            base += tot;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) v.r_cnt[ring * 4 + 3] = base;
+}
+
+__global__ void __launch_bounds__(1024) fe_concat_kernel(FeView v)
+{
+    __shared__ int s_off[4][FE_MAX_RINGS + 1];
+    const int tid = threadIdx.x;
+    if (tid < 4) {
+        int acc = 0;
+        for (int r = 0; r < v.n_scan; r++) {
+            s_off[tid][r] = acc;
+            acc += tid < 3 ? v.r_cnt[r * 4 + tid] : v.r_lf_ds_cnt[r];
+        }
+        s_off[tid][v.n_scan] = acc;
+        v.hdr->counts[tid] = acc;
+    }
+    __syncthreads();
+    const float4 *src[4] = { v.r_sharp, v.r_lsharp, v.r_flat, v.r_lf_ds };
+    const int stride[4] = { FE_SHARP_PER_RING, FE_LSHARP_PER_RING, FE_FLAT_PER_RING, v.horizon };
+    for (int which = 0; which < 4; which++) {
+        const int total = s_off[which][v.n_scan];
+        for (int i = tid; i < total; i += blockDim.x) {
+            int lo = 0, hi = v.n_scan;                    // last ring with offset <= i
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[which][mid] <= i) lo = mid; else hi = mid; }
+            v.out[which][i] = src[which][(size_t)lo * stride[which] + (i - s_off[which][lo])];
+        }
+    }
+    if (tid == 0) v.hdr->first_half = INT_MAX;             // ready for the next sweep
+}
+
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+}  // namespace
+
+void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
+{
+    release();
+    n_scan_ = n_scan; horizon_ = horizon; cap_ = n_scan * horizon;
+    const size_t cap = (size_t)cap_;
+    cloud_adj_.ensure(cap); ori_.ensure(cap); curv_.ensure(cap); picked_.ensure(cap); label_.ensure(cap); smooth_.ensure(cap);
+    r_sharp_.ensure((size_t)n_scan * FE_SHARP_PER_RING); r_lsharp_.ensure((size_t)n_scan * FE_LSHARP_PER_RING);
+    r_flat_.ensure((size_t)n_scan * FE_FLAT_PER_RING); r_lf_scan_.ensure(cap); r_lf_ds_.ensure(cap);
+    r_cnt_.ensure((size_t)n_scan * 4); r_lf_ds_cnt_.ensure(n_scan); hdr_.ensure(1); jobs_.ensure(n_scan);
+    out_[0].ensure((size_t)n_scan * FE_SHARP_PER_RING); out_[1].ensure((size_t)n_scan * FE_LSHARP_PER_RING);
+    out_[2].ensure((size_t)n_scan * FE_FLAT_PER_RING); out_[3].ensure(cap);
+    // the reference's arrays start as whatever `new` returns (FA:210-212); zero, as the oracle harness defines them
+    LLB_CUDA(cudaMemsetAsync(curv_.p, 0, sizeof(float) * cap, s));
+    LLB_CUDA(cudaMemsetAsync(picked_.p, 0, sizeof(int) * cap, s));
+    LLB_CUDA(cudaMemsetAsync(label_.p, 0, sizeof(int) * cap, s));
+    LLB_CUDA(cudaMemsetAsync(smooth_.p, 0, sizeof(unsigned long long) * cap, s));       // FA:223: {0, 0}
+    FeHeader h{}; h.first_half = INT_MAX; h.release_seq = 0;
+    LLB_CUDA(cudaMemcpyAsync(hdr_.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    std::vector<SmallJob> jobs(n_scan);
+    for (int r = 0; r < n_scan; r++) {
+        SmallJob &j = jobs[r];
+        j.in.a = r_lf_scan_.p + (size_t)r * horizon; j.in.na_dev = r_cnt_.p + r * 4 + 3; j.in.na = horizon;
+        j.in.b = nullptr; j.in.nb_dev = nullptr; j.in.nb = 0;
+        j.leaf = prm.leaf; j.out = r_lf_ds_.p + (size_t)r * horizon; j.n_out = r_lf_ds_cnt_.p + r;
+    }
+    LLB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), sizeof(SmallJob) * n_scan, cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 2; k++) LLB_CUDA(cudaEventCreateWithFlags(&in_ev_[k], cudaEventDisableTiming));
+    out_off_[0] = 64;
+    out_off_[1] = out_off_[0] + sizeof(float4) * n_scan * FE_SHARP_PER_RING;
+    out_off_[2] = out_off_[1] + sizeof(float4) * n_scan * FE_LSHARP_PER_RING;
+    out_off_[3] = out_off_[2] + sizeof(float4) * n_scan * FE_FLAT_PER_RING;
+    pin_out_.ensure(out_off_[3] + sizeof(float4) * cap);
+    const int smem = (horizon + 8) * 8 + horizon + 32;
+    if (smem > 48 * 1024)
+        LLB_CUDA(cudaFuncSetAttribute(fe_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    seq_ = 0; n_ = 0;
+}
+
+void FeatureExtractor::release()
+{
+    for (int k = 0; k < 2; k++) { if (in_ev_[k]) cudaEventDestroy(in_ev_[k]); in_ev_[k] = nullptr; in_busy_[k] = false; pin_in_[k].release(); }
+    in_dev_.release(); cloud_adj_.release(); r_sharp_.release(); r_lsharp_.release(); r_flat_.release(); r_lf_scan_.release();
+    r_lf_ds_.release(); for (auto &o : out_) o.release();
+    ori_.release(); curv_.release(); picked_.release(); label_.release(); r_cnt_.release(); r_lf_ds_cnt_.release();
+    smooth_.release(); hdr_.release(); jobs_.release(); pin_out_.release();
+    n_scan_ = 0;
+}
+
+const float4 *FeatureExtractor::host_cloud(int which) const
+{
+    return reinterpret_cast<const float4 *>(pin_out_.p + out_off_[which]);
+}
+
+int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
+                              float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
+                              const float *range, cudaStream_t s)
+{
+    // ---- one pinned block, one H2D
+    const size_t o_cloud = 0, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
+                 o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan_),
+                 o_ground = align16(o_end + 4 * (size_t)n_scan_), total = align16(o_ground + (size_t)n + 16);
+    const int rb = ring_; ring_ ^= 1;
+    if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
+    pin_in_[rb].ensure(total); in_dev_.ensure(total);
+    unsigned char *hp = pin_in_[rb].p, *dp = in_dev_.p;
+    float *hc = reinterpret_cast<float *>(hp + o_cloud);
+    for (int i = 0; i < n; i++) {
+        const float *q = cloud32 + 8 * (size_t)i;
+        hc[4 * i] = q[0]; hc[4 * i + 1] = q[1]; hc[4 * i + 2] = q[2]; hc[4 * i + 3] = q[4];
+    }
+    std::memcpy(hp + o_range, range, 4 * (size_t)n);
+    std::memcpy(hp + o_col, col, 4 * (size_t)n);
+    std::memcpy(hp + o_start, start_ring, 4 * (size_t)n_scan_);
+    std::memcpy(hp + o_end, end_ring, 4 * (size_t)n_scan_);
+    std::memcpy(hp + o_ground, ground, (size_t)n);
+    LLB_CUDA(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaEventRecord(in_ev_[rb], s)); in_busy_[rb] = true;
+
+    FeView v{};
+    v.cloud_in = reinterpret_cast<const float4 *>(dp + o_cloud); v.cloud_adj = cloud_adj_.p;
+    v.n = n; v.n_scan = n_scan_; v.horizon = horizon_; v.cap = cap_;
+    v.start_ring = reinterpret_cast<const int *>(dp + o_start); v.end_ring = reinterpret_cast<const int *>(dp + o_end);
+    v.ground = dp + o_ground; v.col = reinterpret_cast<const unsigned *>(dp + o_col);
+    v.range = reinterpret_cast<const float *>(dp + o_range);
+    v.start_ori = start_ori; v.end_ori = end_ori; v.ori_diff = ori_diff;
+    v.ori = ori_.p; v.curv = curv_.p; v.picked = picked_.p; v.label = label_.p; v.smooth = smooth_.p; v.hdr = hdr_.p;
+    v.r_sharp = r_sharp_.p; v.r_lsharp = r_lsharp_.p; v.r_flat = r_flat_.p; v.r_lf_scan = r_lf_scan_.p; v.r_lf_ds = r_lf_ds_.p;
+    v.r_cnt = r_cnt_.p; v.r_lf_ds_cnt = r_lf_ds_cnt_.p;
+    for (int k = 0; k < 4; k++) v.out[k] = out_[k].p;
+    v.prm = prm; v.seq = ++seq_;
+    n_ = n;
+    const int grid = std::max(1, std::min(div_up(n, FE_TPB), 148 * 4));
+    fe_point_kernel<<<grid, FE_TPB, 0, s>>>(v);
+    fe_mark_kernel<<<grid, FE_TPB, 0, s>>>(v);
+    fe_ring_kernel<<<n_scan_, FE_RING_THREADS, (horizon_ + 8) * 8 + horizon_ + 32, s>>>(v);
+    launch_voxel_cta_jobs(jobs_.p, n_scan_, (horizon_ + 1023) & ~1023, s);
+    fe_concat_kernel<<<1, 1024, 0, s>>>(v);
+    LLB_CUDA(cudaGetLastError());
+    // ---- results: counts + the four clouds (the less-flat cloud is bounded by n)
+    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, reinterpret_cast<unsigned char *>(hdr_.p) + offsetof(FeHeader, counts), 16,
+                             cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 3; k++)
+        LLB_CUDA(cudaMemcpyAsync(pin_out_.p + out_off_[k], out_[k].p, out_off_[k + 1] - out_off_[k], cudaMemcpyDeviceToHost, s));
+    if (n > 0)
+        LLB_CUDA(cudaMemcpyAsync(pin_out_.p + out_off_[3], out_[3].p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    return 5;
+}
+
+void FeatureExtractor::get_state(float *curv, int *picked, int *label, int n, cudaStream_t s)
+{
+    LLB_CUDA(cudaMemcpyAsync(curv, curv_.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    LLB_CUDA(cudaMemcpyAsync(picked, picked_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    LLB_CUDA(cudaMemcpyAsync(label, label_.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    LLB_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace llb

@@ -1,0 +1,74 @@
+// features.cuh — feature extraction of one segmented sweep on the device: adjustDistortion (no-IMU
+// branch, FA:491-619), calculateSmoothness (FA:621-641), markOccludedPoints (FA:643-678), extractFeatures (FA:680-784).
+//
+// Launches per sweep: 1 H2D (one pinned block: cloud, range, column, ground flag, ring bounds) ->
+//   fe_point_kernel  per point: azimuth, first "half passed" point (atomicMin), curvature, state reset, sort records
+//   fe_mark_kernel   per point: relative time -> intensity, axis swap; occlusion / parallel-beam marks
+//   fe_ring_kernel   one CTA per ring: its 6 sectors sorted by 6 warps (libstdc++ std::sort move for move, std_sort.cuh),
+//                    then the greedy picks of the sectors in order by one warp (32 candidates evaluated per step),
+//                    then the ordered gather of the ring's less-flat points
+//   voxel_cta_kernel one CTA per ring: VoxelGrid(0.2) of surfPointsLessFlatScan (FA:778-782), K1 as it is
+//   fe_concat_kernel ring-major concatenation into the four output clouds
+// -> 1 D2H (counts + four clouds).  Per-point work is HBM-trivial (30k points); the step is bound by the dependent
+// chain of one sector sort (~300 records, one thread) + ~24 sequential picks per sector.
+#pragma once
+#include "common.cuh"
+#include "voxel_dev.cuh"
+
+namespace llb {
+
+constexpr int FE_MAX_RINGS = 128;
+constexpr int FE_SHARP_PER_RING = 12, FE_LSHARP_PER_RING = 120, FE_FLAT_PER_RING = 24;   // 6 sectors x (2, 20, 4)
+
+struct FeParams { float edge_threshold, surf_threshold, scan_period, leaf; };   // UT:116-117, UT:107, FA:214
+
+struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; };
+
+struct FeView {
+    const float4 *cloud_in; float4 *cloud_adj;
+    int n, n_scan, horizon, cap;
+    const int *start_ring, *end_ring;
+    const unsigned char *ground; const unsigned *col; const float *range;
+    float start_ori, end_ori, ori_diff;
+    float *ori; float *curv; int *picked; int *label; unsigned long long *smooth;
+    FeHeader *hdr;
+    float4 *r_sharp, *r_lsharp, *r_flat, *r_lf_scan, *r_lf_ds;
+    int *r_cnt;          // [n_scan][4]: sharp, less sharp, flat, less-flat-scan
+    int *r_lf_ds_cnt;    // [n_scan]
+    float4 *out[4];
+    FeParams prm;
+    int seq;
+};
+
+class FeatureExtractor {
+public:
+    void init(int n_scan, int horizon, cudaStream_t s);
+    bool ready() const { return n_scan_ > 0; }
+    int n_scan() const { return n_scan_; }
+    int horizon() const { return horizon_; }
+    void release();
+    // stages the sweep (host pointers, cloud with a 32 B stride), enqueues everything; returns kernel launches
+    int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
+                float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
+    // after the stream has been synchronised
+    const int *counts() const { return reinterpret_cast<const int *>(pin_out_.p); }
+    const float4 *host_cloud(int which) const;
+    const float4 *dev_cloud(int which) const { return which == 4 ? cloud_adj_.p : out_[which].p; }
+    int n_points() const { return n_; }
+    void get_state(float *curv, int *picked, int *label, int n, cudaStream_t s);
+    FeParams prm{ 0.1f, 0.1f, 0.1f, 0.2f };
+private:
+    int n_scan_ = 0, horizon_ = 0, cap_ = 0, n_ = 0, seq_ = 0;
+    PinnedBuf<unsigned char> pin_in_[2]; cudaEvent_t in_ev_[2] = { nullptr, nullptr }; bool in_busy_[2] = { false, false };
+    int ring_ = 0;
+    DevBuf<unsigned char> in_dev_;
+    DevBuf<float4> cloud_adj_, r_sharp_, r_lsharp_, r_flat_, r_lf_scan_, r_lf_ds_, out_[4];
+    DevBuf<float> ori_, curv_; DevBuf<int> picked_, label_, r_cnt_, r_lf_ds_cnt_;
+    DevBuf<unsigned long long> smooth_;
+    DevBuf<FeHeader> hdr_;
+    DevBuf<SmallJob> jobs_;
+    PinnedBuf<unsigned char> pin_out_;
+    size_t out_off_[4] = { 0, 0, 0, 0 };
+};
+
+}  // namespace llb
