@@ -197,6 +197,9 @@ int llb_features_extract(llb_ctx *ctx, const llb_segmented_cloud *seg, int count
 int llb_features_get(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
 /* cloudCurvature / cloudNeighborPicked / cloudLabel of the last sweep (parity checks) */
 int llb_features_get_state(llb_ctx *ctx, float *curvature, int *neighbor_picked, int *label, int capacity);
+/* SM cycles of the slowest ring of the last sweep (profiling): [0] sort phase, [1] picks; then the slowest warp / ring
+ * per part: [2] partitions, [3] leaf ranges, [4] edge picks, [5] flat picks, [6..9] reserved */
+int llb_features_get_profile(llb_ctx *ctx, int cycles[10]);
 /* cornerPointsSharp / surfPointsFlat of the last extraction become the odometry's features without leaving the device
  * (= llb_odom_set_features on them) */
 int llb_features_to_odometry(llb_ctx *ctx);

@@ -1157,6 +1157,16 @@ int llb_features_get_state(llb_ctx *c, float *curvature, int *neighbor_picked, i
     });
 }
 
+int llb_features_get_profile(llb_ctx *c, int cycles[10])
+{
+    return guarded(c, [&]() {
+        if (!cycles) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        for (int k = 0; k < 10; k++) cycles[k] = c->features.phase_cycles()[k];
+        return (int)LLB_OK;
+    });
+}
+
 int llb_features_to_odometry(llb_ctx *c)
 {
     return guarded(c, [&]() {

@@ -34,6 +34,7 @@ __device__ __forceinline__ float fe_ori_first_half(float ori, float start_ori)
 
 __global__ void __launch_bounds__(FE_TPB) fe_point_kernel(FeView v)
 {
+    if (blockIdx.x == 0 && threadIdx.x < 10) v.hdr->pad[threadIdx.x] = 0;      // pad[2] + prof[8]
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const float4 q = __ldg(v.cloud_in + i);
         // point.x = y, point.z = x; ori = -atan2(point.x, point.z) (float overload), FA:500-504
@@ -84,30 +85,146 @@ __global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(FeView v)
     }
 }
 
-struct PickWindow { unsigned char *s; int w0, w1; volatile int *g; int cap; };
-__device__ __forceinline__ int pk_get(const PickWindow &w, int i)
+// the ring's slice of the per-point arrays in shared memory; a stale record (see fe_ring_kernel) may name a point outside
+// of it, which goes to global memory
+struct RingWin {
+    unsigned char *pk, *gr; unsigned short *col; float *curv;
+    int w0, w1; volatile int *g_picked; int cap;
+};
+__device__ __forceinline__ int pk_get(const RingWin &w, int i)
 {
-    if (i >= w.w0 && i < w.w1) return w.s[i - w.w0];
-    return (i >= 0 && i < w.cap) ? w.g[i] : 1;
+    if (i >= w.w0 && i < w.w1) return w.pk[i - w.w0];
+    return (i >= 0 && i < w.cap) ? w.g_picked[i] : 1;
 }
-__device__ __forceinline__ void pk_set(const PickWindow &w, int i)
+__device__ __forceinline__ void pk_set(const RingWin &w, int i)
 {
-    if (i >= w.w0 && i < w.w1) w.s[i - w.w0] = 1;
-    else if (i >= 0 && i < w.cap) w.g[i] = 1;
+    if (i >= w.w0 && i < w.w1) w.pk[i - w.w0] = 1;
+    else if (i >= 0 && i < w.cap) w.g_picked[i] = 1;
 }
-// FA:727-740 == FA:758-773
-__device__ void fe_mark_neighbors(const FeView &v, const PickWindow &w, int ind)
+__device__ __forceinline__ int win_col_diff(const FeView &v, const RingWin &w, int a, int b)
 {
-    pk_set(w, ind);
-    for (int l = 1; l <= 5; l++) {
-        if (fe_col_diff(v, ind + l, ind + l - 1) > 10) break;
-        pk_set(w, ind + l);
+    const unsigned ca = (a >= w.w0 && a < w.w1) ? (unsigned)w.col[a - w.w0] : fe_col(v, a);
+    const unsigned cb = (b >= w.w0 && b < w.w1) ? (unsigned)w.col[b - w.w0] : fe_col(v, b);
+    return abs((int)(ca - cb));
+}
+__device__ __forceinline__ float win_curv(const FeView &v, const RingWin &w, int i)
+{
+    return (i >= w.w0 && i < w.w1) ? w.curv[i - w.w0] : v.curv[i];
+}
+__device__ __forceinline__ int win_ground(const FeView &v, const RingWin &w, int i)
+{
+    return (i >= w.w0 && i < w.w1) ? (int)w.gr[i - w.w0] : fe_ground(v, i);
+}
+// FA:727-740 == FA:758-773 by the whole warp: lanes 0-4 test the forward steps l = 1..5, lanes 5-9 the backward steps
+// l = -1..-5; a step is marked only if no earlier step of its direction broke off.  nf / nb: steps marked per direction.
+__device__ __forceinline__ void fe_mark_neighbors(const FeView &v, const RingWin &w, int ind, int lane, int &nf, int &nb)
+{
+    const bool fw = lane < 5, act = lane < 10;
+    const int pos = act ? (fw ? ind + lane + 1 : ind - (lane - 4)) : ind;
+    const int prev = fw ? pos - 1 : pos + 1;
+    bool brk = false;
+    if (act) brk = pos < 0 || win_col_diff(v, w, pos, prev) > 10;   // pos < 0: only through the stale record {0, 0}
+    const unsigned b = __ballot_sync(FULL, brk);
+    const unsigned fwd = b & 0x1fu, bwd = (b >> 5) & 0x1fu;
+    nf = fwd ? __ffs(fwd) - 1 : 5; nb = bwd ? __ffs(bwd) - 1 : 5;
+    if (lane < nf || (lane >= 5 && lane - 5 < nb) || lane == 31) pk_set(w, pos);
+}
+
+// ---- libstdc++ std::sort by one warp (std_sort.cuh: closed-form partitions + independent leaf ranges; checked on the
+// ---- host against libstdc++ in tests/test_host_std_sort.py).  All lanes call with identical arguments.
+__device__ int warp_partition(stdsort::rec_t *a, int first, int last, int pivot, unsigned short *Lbuf, unsigned short *Rbuf, int lane)
+{
+    const stdsort::rec_t pv = a[pivot];
+    const int m = last - first;
+    const unsigned lt = (1u << lane) - 1;
+    int nL = 0, nR = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool fl = i < m && !stdsort::less(a[first + i], pv);              // left stoppers, increasing position
+        const unsigned bl = __ballot_sync(FULL, fl);
+        if (fl) Lbuf[nL + __popc(bl & lt)] = (unsigned short)i;
+        nL += __popc(bl);
+        const int j = m - 1 - i;
+        const bool fr = i < m && !stdsort::less(pv, a[first + j]);              // right stoppers, decreasing position
+        const unsigned br = __ballot_sync(FULL, fr);
+        if (fr) Rbuf[nR + __popc(br & lt)] = (unsigned short)j;
+        nR += __popc(br);
     }
-    for (int l = -1; l >= -5; l--) {
-        if (ind + l < 0) break;      // only reachable through the stale record {0, 0}: the reference is undefined there
-        if (fe_col_diff(v, ind + l, ind + l + 1) > 10) break;
-        pk_set(w, ind + l);
+    __syncwarp();
+    const int mm = min(nL, nR);
+    int K = 0;
+    for (int base = 0; base < mm; base += 32) {
+        const int k = base + lane;
+        const unsigned b = __ballot_sync(FULL, k < mm && Lbuf[k] < Rbuf[k]);
+        K += __popc(b);
+        if (b != FULL) break;                                                   // the condition is monotone in k
     }
+    for (int k = lane; k < K; k += 32) stdsort::swp(a + first + Lbuf[k], a + first + Rbuf[k]);
+    int cut;
+    if (K == 0) cut = first + Lbuf[0];
+    else {
+        const int rk = first + Rbuf[K - 1];
+        cut = (K < nL && first + Lbuf[K] < rk) ? first + Lbuf[K] : rk;
+    }
+    __syncwarp();
+    return cut;
+}
+
+__device__ void warp_std_sort(stdsort::rec_t *a, stdsort::rec_t *tmp, int n, unsigned short *Lbuf, unsigned short *Rbuf,
+                              unsigned char *bound, int lane, int *prof)
+{
+    if (n <= 1) return;
+    const long long t0 = clock64();
+    int depth = 0;
+    for (int m = n; m > 1; m >>= 1) depth += 2;
+    int stk_first[40], stk_last[40], stk_depth[40];       // <= 2 * log2(n) pending right parts
+    int sp = 0, first = 0, last = n;
+    for (;;) {
+        while (last - first > 16) {
+            if (depth == 0) {
+                if (lane == 0) stdsort::heap_sort(a + first, last - first);
+                for (int p = first + lane; p < last; p += 32) { Lbuf[p] = (unsigned short)p; Rbuf[p] = (unsigned short)(p + 1); }   // in order already
+                __syncwarp();
+                last = first;
+                break;
+            }
+            --depth;
+            if (lane == 0) stdsort::median_to_first(a + first, a + first + 1, a + first + (last - first) / 2, a + last - 1);
+            __syncwarp();
+            const int cut = warp_partition(a, first + 1, last, first, Lbuf + first + 1, Rbuf + first + 1, lane);
+            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
+            last = cut;
+        }
+        // a terminal range: its records remember its bounds (the partition scratch of a range stays inside that range)
+        for (int p = first + lane; p < last; p += 32) { Lbuf[p] = (unsigned short)first; Rbuf[p] = (unsigned short)last; }
+        if (sp == 0) break;
+        sp--;
+        first = stk_first[sp]; last = stk_last[sp]; depth = stk_depth[sp];
+    }
+    __syncwarp();
+    const long long t1 = clock64();
+    // __final_insertion_sort = a stable sort of every terminal range on its own (std_sort.cuh): one record per lane, its
+    // place inside the range by counting the records that go before it
+    for (int base = 0; base < n; base += 32) {
+        const int p = base + lane;
+        if (p < n) {
+            const stdsort::rec_t rec = a[p];
+            const int s = Lbuf[p], e = Rbuf[p];
+            int r = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {           // terminal ranges hold at most 16 records
+                const int q = s + i;
+                const stdsort::rec_t x = a[min(q, n - 1)];
+                r += (q < e && (stdsort::less(x, rec) || (!stdsort::less(rec, x) && q < p))) ? 1 : 0;
+            }
+            const int dest = s + r;
+            tmp[dest] = rec;
+        }
+    }
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) a[p] = tmp[p];
+    __syncwarp();
+    if (lane == 0) { atomicMax(prof + 0, (int)(t1 - t0)); atomicMax(prof + 1, (int)(clock64() - t1)); }
 }
 
 __device__ __forceinline__ void fe_sector(int st, int en, int j, int &sp, int &ep)
@@ -119,8 +236,14 @@ __device__ __forceinline__ void fe_sector(int st, int en, int j, int &sp, int &e
 __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
 {
     extern __shared__ __align__(16) unsigned long long s_rec[];                       // [horizon + 8]
-    unsigned char *s_pk = reinterpret_cast<unsigned char *>(s_rec + v.horizon + 8);    // [horizon + 32]
+    const int wcap = v.horizon + 32;
+    unsigned long long *s_tmp = s_rec + v.horizon + 8;                                 // [horizon + 8]
+    float *s_curv = reinterpret_cast<float *>(s_tmp + v.horizon + 8);                  // [wcap] each
+    unsigned short *s_col = reinterpret_cast<unsigned short *>(s_curv + wcap);
+    unsigned char *s_pk = reinterpret_cast<unsigned char *>(s_col + wcap);
+    unsigned char *s_gr = s_pk + wcap;
     __shared__ int s_tot[FE_RING_THREADS / 32];
+    __shared__ int s_sharp[FE_SHARP_PER_RING], s_lsharp[FE_LSHARP_PER_RING], s_flat[FE_FLAT_PER_RING], s_n[3];
     __shared__ int s_owner, s_late;
     const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int st = __ldg(v.start_ring + ring), en = __ldg(v.end_ring + ring);
@@ -145,10 +268,13 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
         if (stale >= w0 && stale < w1) { __threadfence(); atomicExch(&v.hdr->release_seq, v.seq); }
         else s_late = 1;
     }
-    // ---- the six sorts, one warp each (single thread: the order of equal keys is defined by the sequential algorithm)
-    if (warp < 6 && lane == 0) {
+    const long long t_start = clock64();
+    // ---- the six sorts, one warp each
+    if (warp < 6) {      // scratch: the shared arrays of the ring slice, which are filled only after the sorts
         int sp, ep; fe_sector(st, en, warp, sp, ep);
-        if (sp < ep) stdsort::sort(s_rec + (sp - st), ep - sp);                         // FA:699: [sp, ep)
+        if (sp < ep)                                                                     // FA:699: [sp, ep)
+            warp_std_sort(s_rec + (sp - st), s_tmp + (sp - st), ep - sp, s_col + (sp - st), reinterpret_cast<unsigned short *>(s_curv) + (sp - st),
+                          s_pk + (sp - st), lane, v.hdr->prof);
     }
     if (owner >= 0 && owner != ring && tid == 0) {
         volatile int *flag = &v.hdr->release_seq;
@@ -156,74 +282,102 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
         __threadfence();
     }
     __syncthreads();
-    for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) s_pk[k - w0] = (unsigned char)(((volatile int *)v.picked)[k] != 0);
+    const long long t_sorted = clock64();
+    for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) {
+        s_pk[k - w0] = (unsigned char)(((volatile int *)v.picked)[k] != 0);
+        s_curv[k - w0] = v.curv[k];
+        s_col[k - w0] = (unsigned short)fe_col(v, k);
+        s_gr[k - w0] = (unsigned char)fe_ground(v, k);
+    }
     __syncthreads();
-    PickWindow w{ s_pk, w0, w1, (volatile int *)v.picked, v.cap };
+    RingWin w{ s_pk, s_gr, s_col, s_curv, w0, w1, (volatile int *)v.picked, v.cap };
     // ---- greedy picks, sectors in order (a pick of sector j may block neighbours that belong to sector j+1)
     if (warp == 0) {
         int nsharp = 0, nls = 0, nflat = 0;
+        long long c_large = 0, c_flat = 0;
         for (int j = 0; j < 6; j++) {
             int sp, ep; fe_sector(st, en, j, sp, ep);
             if (sp >= ep) continue;
             int cnt = 0;
+            const long long tl0 = clock64();
             for (int khi = ep; khi >= sp && cnt < 20; khi -= 32) {                       // FA:701-742
                 const int k = khi - lane;
                 const bool valid = k >= sp;
-                const int ind = valid ? (int)(unsigned)s_rec[k - st] : 0;
-                bool stat = valid && v.curv[ind] > v.prm.edge_threshold && fe_ground(v, ind) == 0;
+                const int ind = valid ? (int)(unsigned)s_rec[k - st] : w0;
+                bool stat = valid && win_curv(v, w, ind) > v.prm.edge_threshold && win_ground(v, w, ind) == 0;
+                // flags set by earlier chunks / sectors come from shared memory once; inside the chunk every lane follows
+                // the marks of the picks in registers
+                bool el = stat && pk_get(w, ind) == 0;
                 for (;;) {
-                    const bool el = stat && pk_get(w, ind) == 0;
                     const unsigned b = __ballot_sync(FULL, el);
                     if (!b) break;
                     const int f = __ffs(b) - 1;
-                    if (lane == f) {
-                        const float4 p = v.cloud_adj[ind];
-                        v.label[ind] = cnt < 2 ? 2 : 1;
-                        if (cnt < 2) v.r_sharp[ring * FE_SHARP_PER_RING + nsharp] = p;
-                        v.r_lsharp[ring * FE_LSHARP_PER_RING + nls] = p;
-                        fe_mark_neighbors(v, w, ind);
+                    const int pind = __shfl_sync(FULL, ind, f);
+                    if (lane == f) {      // labels and the points themselves are written after the picks, by all threads
+                        if (cnt < 2) s_sharp[nsharp] = ind;
+                        s_lsharp[nls] = ind;
                     }
-                    __syncwarp();
+                    int nf, nb;
+                    fe_mark_neighbors(v, w, pind, lane, nf, nb);
                     if (cnt < 2) nsharp++;
                     nls++; cnt++;
                     if (cnt >= 20) break;
-                    if (lane <= f) stat = false;
+                    if (lane <= f || (ind >= pind - nb && ind <= pind + nf)) el = false;
                 }
+                __syncwarp();
             }
             cnt = 0;
+            const long long tl1 = clock64();
+            c_large += tl1 - tl0;
             bool done = false;
             for (int klo = sp; klo <= ep && !done; klo += 32) {                          // FA:744-775
                 const int k = klo + lane;
                 const bool valid = k <= ep;
-                const int ind = valid ? (int)(unsigned)s_rec[k - st] : 0;
-                bool stat = valid && v.curv[ind] < v.prm.surf_threshold && fe_ground(v, ind) != 0;
+                const int ind = valid ? (int)(unsigned)s_rec[k - st] : w0;
+                bool stat = valid && win_curv(v, w, ind) < v.prm.surf_threshold && win_ground(v, w, ind) != 0;
+                bool el = stat && pk_get(w, ind) == 0;
                 for (;;) {
-                    const bool el = stat && pk_get(w, ind) == 0;
                     const unsigned b = __ballot_sync(FULL, el);
                     if (!b) break;
                     const int f = __ffs(b) - 1;
-                    if (lane == f) {
-                        v.label[ind] = -1;
-                        v.r_flat[ring * FE_FLAT_PER_RING + nflat] = v.cloud_adj[ind];
-                        if (cnt + 1 < 4) fe_mark_neighbors(v, w, ind);               // the 4th pick breaks before the marks
-                    }
-                    __syncwarp();
+                    const int pind = __shfl_sync(FULL, ind, f);
+                    if (lane == f) s_flat[nflat] = ind;
                     nflat++; cnt++;
-                    if (cnt >= 4) { done = true; break; }
-                    if (lane <= f) stat = false;
+                    if (cnt >= 4) { done = true; break; }                 // the 4th pick breaks before the marks, FA:752-756
+                    int nf, nb;
+                    fe_mark_neighbors(v, w, pind, lane, nf, nb);
+                    if (lane <= f || (ind >= pind - nb && ind <= pind + nf)) el = false;
                 }
+                __syncwarp();
             }
+            c_flat += clock64() - tl1;
         }
-        if (lane == 0) { v.r_cnt[ring * 4 + 0] = nsharp; v.r_cnt[ring * 4 + 1] = nls; v.r_cnt[ring * 4 + 2] = nflat; }
+        if (lane == 0) { atomicMax(v.hdr->prof + 2, (int)c_large); atomicMax(v.hdr->prof + 3, (int)c_flat); }
+        if (lane == 0) {
+            v.r_cnt[ring * 4 + 0] = nsharp; v.r_cnt[ring * 4 + 1] = nls; v.r_cnt[ring * 4 + 2] = nflat;
+            s_n[0] = nsharp; s_n[1] = nls; s_n[2] = nflat;
+        }
         __threadfence();
         __syncwarp();
         if (lane == 0 && owner == ring && s_late) atomicExch(&v.hdr->release_seq, v.seq);
+        if (lane == 0) {        // slowest ring: cycles of the sort phase (incl. the wait for the owner ring) and of the picks
+            atomicMax(&v.hdr->pad[0], (int)(t_sorted - t_start)); atomicMax(&v.hdr->pad[1], (int)(clock64() - t_sorted));
+        }
     }
     __syncthreads();
+    // cloudLabel: 1 for every edge pick, then 2 for the first two of each sector, -1 for the flat picks (FA:708-750)
+    for (int i = tid; i < s_n[1]; i += FE_RING_THREADS) v.label[s_lsharp[i]] = 1;
+    __syncthreads();
+    for (int i = tid; i < s_n[0]; i += FE_RING_THREADS) v.label[s_sharp[i]] = 2;
+    for (int i = tid; i < s_n[2]; i += FE_RING_THREADS) v.label[s_flat[i]] = -1;
+    for (int i = tid; i < s_n[0]; i += FE_RING_THREADS) v.r_sharp[ring * FE_SHARP_PER_RING + i] = v.cloud_adj[s_sharp[i]];
+    for (int i = tid; i < s_n[1]; i += FE_RING_THREADS) v.r_lsharp[ring * FE_LSHARP_PER_RING + i] = v.cloud_adj[s_lsharp[i]];
+    for (int i = tid; i < s_n[2]; i += FE_RING_THREADS) v.r_flat[ring * FE_FLAT_PER_RING + i] = v.cloud_adj[s_flat[i]];
     // state back: flags set by this ring, records in sorted order
     for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) if (s_pk[k - w0]) v.picked[k] = 1;
     for (int k = tid; k < nrec; k += FE_RING_THREADS) v.smooth[st + k] = s_rec[k];
     // ---- surfPointsLessFlatScan: points with label <= 0 of the sectors that were processed, in index order, FA:777-781
+    __syncthreads();                 // labels of this ring are in place
     int base = 0;
     for (int j = 0; j < 6; j++) {
         int sp, ep; fe_sector(st, en, j, sp, ep);
@@ -249,12 +403,15 @@ __global__ void __launch_bounds__(1024) fe_concat_kernel(FeView v)
 {
     __shared__ int s_off[4][FE_MAX_RINGS + 1];
     const int tid = threadIdx.x;
+    __shared__ int s_c[4][FE_MAX_RINGS];
+    for (int i = tid; i < 4 * v.n_scan; i += blockDim.x) {
+        const int which = i & 3, r = i >> 2;
+        s_c[which][r] = which < 3 ? v.r_cnt[r * 4 + which] : v.r_lf_ds_cnt[r];
+    }
+    __syncthreads();
     if (tid < 4) {
         int acc = 0;
-        for (int r = 0; r < v.n_scan; r++) {
-            s_off[tid][r] = acc;
-            acc += tid < 3 ? v.r_cnt[r * 4 + tid] : v.r_lf_ds_cnt[r];
-        }
+        for (int r = 0; r < v.n_scan; r++) { s_off[tid][r] = acc; acc += s_c[tid][r]; }
         s_off[tid][v.n_scan] = acc;
         v.hdr->counts[tid] = acc;
     }
@@ -269,7 +426,11 @@ __global__ void __launch_bounds__(1024) fe_concat_kernel(FeView v)
             v.out[which][i] = src[which][(size_t)lo * stride[which] + (i - s_off[which][lo])];
         }
     }
-    if (tid == 0) v.hdr->first_half = INT_MAX;             // ready for the next sweep
+    __syncthreads();
+    if (tid == 0) {
+        *v.out_hdr = *v.hdr;                               // counts + cycle counters travel with the clouds: one D2H
+        v.hdr->first_half = INT_MAX;                       // ready for the next sweep
+    }
 }
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -285,8 +446,6 @@ void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
     r_sharp_.ensure((size_t)n_scan * FE_SHARP_PER_RING); r_lsharp_.ensure((size_t)n_scan * FE_LSHARP_PER_RING);
     r_flat_.ensure((size_t)n_scan * FE_FLAT_PER_RING); r_lf_scan_.ensure(cap); r_lf_ds_.ensure(cap);
     r_cnt_.ensure((size_t)n_scan * 4); r_lf_ds_cnt_.ensure(n_scan); hdr_.ensure(1); jobs_.ensure(n_scan);
-    out_[0].ensure((size_t)n_scan * FE_SHARP_PER_RING); out_[1].ensure((size_t)n_scan * FE_LSHARP_PER_RING);
-    out_[2].ensure((size_t)n_scan * FE_FLAT_PER_RING); out_[3].ensure(cap);
     // the reference's arrays start as whatever `new` returns (FA:210-212); zero, as the oracle harness defines them
     LLB_CUDA(cudaMemsetAsync(curv_.p, 0, sizeof(float) * cap, s));
     LLB_CUDA(cudaMemsetAsync(picked_.p, 0, sizeof(int) * cap, s));
@@ -309,7 +468,8 @@ void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
     out_off_[2] = out_off_[1] + sizeof(float4) * n_scan * FE_LSHARP_PER_RING;
     out_off_[3] = out_off_[2] + sizeof(float4) * n_scan * FE_FLAT_PER_RING;
     pin_out_.ensure(out_off_[3] + sizeof(float4) * cap);
-    const int smem = (horizon + 8) * 8 + horizon + 32;
+    out_block_.ensure(out_off_[3] + sizeof(float4) * cap);
+    const int smem = (horizon + 8) * 16 + (horizon + 32) * 8;
     if (smem > 48 * 1024)
         LLB_CUDA(cudaFuncSetAttribute(fe_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     seq_ = 0; n_ = 0;
@@ -319,7 +479,7 @@ void FeatureExtractor::release()
 {
     for (int k = 0; k < 2; k++) { if (in_ev_[k]) cudaEventDestroy(in_ev_[k]); in_ev_[k] = nullptr; in_busy_[k] = false; pin_in_[k].release(); }
     in_dev_.release(); cloud_adj_.release(); r_sharp_.release(); r_lsharp_.release(); r_flat_.release(); r_lf_scan_.release();
-    r_lf_ds_.release(); for (auto &o : out_) o.release();
+    r_lf_ds_.release(); out_block_.release();
     ori_.release(); curv_.release(); picked_.release(); label_.release(); r_cnt_.release(); r_lf_ds_cnt_.release();
     smooth_.release(); hdr_.release(); jobs_.release(); pin_out_.release();
     n_scan_ = 0;
@@ -365,23 +525,19 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
     v.ori = ori_.p; v.curv = curv_.p; v.picked = picked_.p; v.label = label_.p; v.smooth = smooth_.p; v.hdr = hdr_.p;
     v.r_sharp = r_sharp_.p; v.r_lsharp = r_lsharp_.p; v.r_flat = r_flat_.p; v.r_lf_scan = r_lf_scan_.p; v.r_lf_ds = r_lf_ds_.p;
     v.r_cnt = r_cnt_.p; v.r_lf_ds_cnt = r_lf_ds_cnt_.p;
-    for (int k = 0; k < 4; k++) v.out[k] = out_[k].p;
+    for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_block_.p + out_off_[k]);
+    v.out_hdr = reinterpret_cast<FeHeader *>(out_block_.p);
     v.prm = prm; v.seq = ++seq_;
     n_ = n;
     const int grid = std::max(1, std::min(div_up(n, FE_TPB), 148 * 4));
     fe_point_kernel<<<grid, FE_TPB, 0, s>>>(v);
     fe_mark_kernel<<<grid, FE_TPB, 0, s>>>(v);
-    fe_ring_kernel<<<n_scan_, FE_RING_THREADS, (horizon_ + 8) * 8 + horizon_ + 32, s>>>(v);
+    fe_ring_kernel<<<n_scan_, FE_RING_THREADS, (horizon_ + 8) * 16 + (horizon_ + 32) * 8, s>>>(v);
     launch_voxel_cta_jobs(jobs_.p, n_scan_, (horizon_ + 1023) & ~1023, s);
     fe_concat_kernel<<<1, 1024, 0, s>>>(v);
     LLB_CUDA(cudaGetLastError());
-    // ---- results: counts + the four clouds (the less-flat cloud is bounded by n)
-    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, reinterpret_cast<unsigned char *>(hdr_.p) + offsetof(FeHeader, counts), 16,
-                             cudaMemcpyDeviceToHost, s));
-    for (int k = 0; k < 3; k++)
-        LLB_CUDA(cudaMemcpyAsync(pin_out_.p + out_off_[k], out_[k].p, out_off_[k + 1] - out_off_[k], cudaMemcpyDeviceToHost, s));
-    if (n > 0)
-        LLB_CUDA(cudaMemcpyAsync(pin_out_.p + out_off_[3], out_[3].p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    // ---- results: header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
+    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, out_block_.p, out_off_[3] + sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s));
     return 5;
 }
 

@@ -22,7 +22,7 @@ constexpr int FE_SHARP_PER_RING = 12, FE_LSHARP_PER_RING = 120, FE_FLAT_PER_RING
 
 struct FeParams { float edge_threshold, surf_threshold, scan_period, leaf; };   // UT:116-117, UT:107, FA:214
 
-struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; };
+struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; int prof[8]; };
 
 struct FeView {
     const float4 *cloud_in; float4 *cloud_adj;
@@ -35,7 +35,7 @@ struct FeView {
     float4 *r_sharp, *r_lsharp, *r_flat, *r_lf_scan, *r_lf_ds;
     int *r_cnt;          // [n_scan][4]: sharp, less sharp, flat, less-flat-scan
     int *r_lf_ds_cnt;    // [n_scan]
-    float4 *out[4];
+    float4 *out[4]; FeHeader *out_hdr;
     FeParams prm;
     int seq;
 };
@@ -51,9 +51,13 @@ public:
     int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
     // after the stream has been synchronised
-    const int *counts() const { return reinterpret_cast<const int *>(pin_out_.p); }
+    const int *counts() const { return reinterpret_cast<const FeHeader *>(pin_out_.p)->counts; }
+    const int *phase_cycles() const { return reinterpret_cast<const FeHeader *>(pin_out_.p)->pad; }   // sort, picks (slowest ring), then prof[8]
     const float4 *host_cloud(int which) const;
-    const float4 *dev_cloud(int which) const { return which == 4 ? cloud_adj_.p : out_[which].p; }
+    const float4 *dev_cloud(int which) const
+    {
+        return which == 4 ? cloud_adj_.p : reinterpret_cast<const float4 *>(out_block_.p + out_off_[which]);
+    }
     int n_points() const { return n_; }
     void get_state(float *curv, int *picked, int *label, int n, cudaStream_t s);
     FeParams prm{ 0.1f, 0.1f, 0.1f, 0.2f };
@@ -62,7 +66,8 @@ private:
     PinnedBuf<unsigned char> pin_in_[2]; cudaEvent_t in_ev_[2] = { nullptr, nullptr }; bool in_busy_[2] = { false, false };
     int ring_ = 0;
     DevBuf<unsigned char> in_dev_;
-    DevBuf<float4> cloud_adj_, r_sharp_, r_lsharp_, r_flat_, r_lf_scan_, r_lf_ds_, out_[4];
+    DevBuf<float4> cloud_adj_, r_sharp_, r_lsharp_, r_flat_, r_lf_scan_, r_lf_ds_;
+    DevBuf<unsigned char> out_block_;   // [FeHeader, 64 B][sharp][less sharp][flat][less flat]
     DevBuf<float> ori_, curv_; DevBuf<int> picked_, label_, r_cnt_, r_lf_ds_cnt_;
     DevBuf<unsigned long long> smooth_;
     DevBuf<FeHeader> hdr_;

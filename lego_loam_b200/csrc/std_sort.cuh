@@ -144,5 +144,57 @@ LLB_HD void sort(rec_t *a, int n, int depth_limit = -1)
     } else insertion_sort(a, 0, n);
 }
 
+// ---- the same result from data-parallel steps (what the kernel's warps execute; this sequential form exists so that the
+// ---- formulas can be checked on the host against libstdc++)
+//
+// __unguarded_partition in closed form.  With the pivot value pv, call position i a LEFT stopper if !(a[i] < pv) and a
+// RIGHT stopper if !(pv < a[i]); L_0 < L_1 < ... are the left stoppers of [first, last) in increasing order, R_0 > R_1 >
+// ... the right stoppers in decreasing order, both taken on the array as it is BEFORE the partition.  The sequential
+// loop swaps L_k with R_k for k = 0 .. K-1, K = number of k with L_k < R_k (swaps only touch positions both pointers have
+// passed, so the untouched stretch between them still shows the original stoppers), and returns
+// cut = L_0 if K == 0, else min(L_K, R_{K-1}) (position R_{K-1} now holds a left stopper).
+// Lbuf / Rbuf: scratch for the stopper positions.
+LLB_HD int partition_closed(rec_t *a, int first, int last, int pivot, unsigned short *Lbuf, unsigned short *Rbuf)
+{
+    const rec_t pv = a[pivot];
+    int nL = 0, nR = 0;
+    for (int i = first; i < last; i++) if (!less(a[i], pv)) Lbuf[nL++] = (unsigned short)(i - first);
+    for (int i = last - 1; i >= first; i--) if (!less(pv, a[i])) Rbuf[nR++] = (unsigned short)(i - first);
+    int K = 0;
+    const int m = nL < nR ? nL : nR;
+    for (int k = 0; k < m; k++) if (Lbuf[k] < Rbuf[k]) K++;          // monotone: true for k < K only
+    for (int k = 0; k < K; k++) swp(a + first + Lbuf[k], a + first + Rbuf[k]);
+    if (K == 0) return first + Lbuf[0];
+    const int rk = first + Rbuf[K - 1];
+    return (K < nL && first + Lbuf[K] < rk) ? first + Lbuf[K] : rk;
+}
+
+// std::sort as: partitions (closed form) down to ranges of <= 16 records, then every such range sorted on its own.
+// The final insertion sort of libstdc++ is a stable sort of the whole array; after the partitions the ranges are weakly
+// ordered among themselves (left part <= pivot <= right part), so a stable sort of the whole = a stable sort of each.
+LLB_HD void sort_closed(rec_t *a, int n, unsigned short *Lbuf, unsigned short *Rbuf, int depth_limit = -1)
+{
+    if (n <= 0) return;
+    if (depth_limit < 0) { int lg = 0; for (int m = n; m > 1; m >>= 1) lg++; depth_limit = 2 * lg; }
+    int stk_first[64], stk_last[64], stk_depth[64];
+    int sp = 0;
+    int first = 0, last = n, depth = depth_limit;
+    for (;;) {
+        while (last - first > 16) {
+            if (depth == 0) { heap_sort(a + first, last - first); last = first; break; }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            median_to_first(a + first, a + first + 1, a + mid, a + last - 1);
+            const int cut = partition_closed(a, first + 1, last, first, Lbuf, Rbuf);
+            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; sp++;
+            last = cut;
+        }
+        if (last - first > 1) insertion_sort(a, first, last);          // a leaf range
+        if (sp == 0) break;
+        sp--;
+        first = stk_first[sp]; last = stk_last[sp]; depth = stk_depth[sp];
+    }
+}
+
 }  // namespace stdsort
 }  // namespace llb

@@ -21,9 +21,9 @@ def host_sort(tmp_path_factory):
                            os.path.join(ROOT, "tests", "host_std_sort_test.cpp")])
     L = ctypes.CDLL(so)
 
-    def run(v, ind, depth=-1):
+    def run(v, ind, depth=-1, closed=0):
         v = np.ascontiguousarray(v, np.float32).copy(); i = np.ascontiguousarray(ind, np.uint32).copy()
-        L.host_std_sort(v.ctypes.data_as(ctypes.c_void_p), i.ctypes.data_as(ctypes.c_void_p), v.shape[0], int(depth))
+        L.host_std_sort(v.ctypes.data_as(ctypes.c_void_p), i.ctypes.data_as(ctypes.c_void_p), v.shape[0], int(depth), int(closed))
         return v, i
     return run
 
@@ -42,6 +42,8 @@ def test_device_std_sort_on_host(host_sort, n, depth):
             gv, gi = host_sort(v, ind, depth)
             ov, oi = oracle.std_sort_by_value(v, ind, depth)
             assert np.array_equal(gv, ov) and np.array_equal(gi, oi)
+            cv, ci = host_sort(v, ind, depth, closed=1)          # the data-parallel formulation the kernel executes
+            assert np.array_equal(cv, ov) and np.array_equal(ci, oi)
             if rh.available():
                 rv, ri = rh.std_sort(v, ind, depth)
                 assert np.array_equal(gv, rv) and np.array_equal(gi.astype(np.int64), ri.astype(np.int64))

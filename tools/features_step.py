@@ -20,5 +20,6 @@ for i in range(reps):
     t0 = time.perf_counter(); counts, d = c.features_extract(sws[i % 2]); ms.append(((time.perf_counter() - t0) * 1e3, d))
 print(sensor.name, "points", [s.cloud.shape[0] for s in sws], "counts", counts)
 print("wall ms", np.round([m[0] for m in ms], 3).tolist())
+print("slowest ring", c.features_get_profile())
 print("device ms", np.round([m[1] for m in ms], 3).tolist())
 c.close()
