@@ -202,13 +202,26 @@ private:
     int staged_ = 0;
 };
 
+// cloud_msgs::cloud_info (cloud_msgs/msg/cloud_info.msg) as imageProjection fills it (IP:312-368)
+struct cloud_info {
+    std::vector<int32_t> startRingIndex, endRingIndex;
+    float startOrientation = 0, endOrientation = 0, orientationDiff = 0;
+    std::vector<uint8_t> segmentedCloudGroundFlag;
+    std::vector<uint32_t> segmentedCloudColInd;
+    std::vector<float> segmentedCloudRange;
+};
+
 // ---------------------------------------------------------------------------------------------
-// FeatureAssociation: findCorresponding{Corner,Surf}Features / calculateTransformation{Surf,Corner}
+// FeatureAssociation: adjustDistortion / calculateSmoothness / markOccludedPoints / extractFeatures (FA:491-784),
+// findCorresponding{Corner,Surf}Features / calculateTransformation{Surf,Corner}
 // / updateTransformation (FA:1044-1478, FA:1666-1695)
 // ---------------------------------------------------------------------------------------------
 class FeatureAssociation {
 public:
+    Cloud::Ptr segmentedCloud;                                     // FA:52
+    cloud_info segInfo;                                            // FA:75
     Cloud::Ptr cornerPointsSharp, surfPointsFlat;                  // FA:56-58
+    Cloud::Ptr cornerPointsLessSharp, surfPointsLessFlat;          // FA:57-59
     Cloud::Ptr laserCloudCornerLast, laserCloudSurfLast;           // FA:161-162
     Cloud::Ptr laserCloudOri, coeffSel;                            // FA:163-164
     float transformCur[6];                                         // FA:154
@@ -220,7 +233,8 @@ public:
 
     explicit FeatureAssociation(int device = 0, const llb_params *params = nullptr)
     {
-        for (Cloud::Ptr *p : { &cornerPointsSharp, &surfPointsFlat, &laserCloudCornerLast, &laserCloudSurfLast, &laserCloudOri, &coeffSel })
+        for (Cloud::Ptr *p : { &cornerPointsSharp, &surfPointsFlat, &laserCloudCornerLast, &laserCloudSurfLast, &laserCloudOri, &coeffSel,
+                               &segmentedCloud, &cornerPointsLessSharp, &surfPointsLessFlat })
             p->reset(new Cloud());
         for (int i = 0; i < 6; i++) transformCur[i] = 0;
         laserCloudCornerLastNum = laserCloudSurfLastNum = 0;
@@ -233,6 +247,36 @@ public:
     ~FeatureAssociation() { llb_destroy(ctx_); }
     FeatureAssociation(const FeatureAssociation &) = delete;
     FeatureAssociation &operator=(const FeatureAssociation &) = delete;
+
+    // N_SCAN / Horizon_SCAN of the sensor (UT:63-84); allocates the per-point state FA:210-223 on the device
+    void initFeatureExtraction(int n_scan, int horizon_scan) { last_status = llb_features_init(ctx_, n_scan, horizon_scan); }
+    // runFeatureAssociation FA:1827-1833: the four steps run as one device pass when extractFeatures() is reached
+    void adjustDistortion() { fe_staged_ |= 1; }                   // FA:491 (no IMU data: imuPointerLast < 0)
+    void calculateSmoothness() { fe_staged_ |= 2; }                // FA:621
+    void markOccludedPoints() { fe_staged_ |= 4; }                 // FA:643
+    void extractFeatures()                                         // FA:680
+    {
+        if (fe_staged_ != 7) { last_status = LLB_ERR_STATE; return; }
+        fe_staged_ = 0;
+        llb_segmented_cloud seg;
+        seg.cloud = as_llb(*segmentedCloud); seg.n = (int)segmentedCloud->size();
+        seg.start_ring = segInfo.startRingIndex.data(); seg.end_ring = segInfo.endRingIndex.data();
+        seg.start_orientation = segInfo.startOrientation; seg.end_orientation = segInfo.endOrientation;
+        seg.orientation_diff = segInfo.orientationDiff;
+        seg.ground_flag = segInfo.segmentedCloudGroundFlag.data(); seg.col_ind = segInfo.segmentedCloudColInd.data();
+        seg.range = segInfo.segmentedCloudRange.data();
+        int counts[4] = { 0, 0, 0, 0 };
+        last_status = llb_features_extract(ctx_, &seg, counts, nullptr);
+        if (last_status != LLB_OK) return;
+        Cloud *out[5] = { cornerPointsSharp.get(), cornerPointsLessSharp.get(), surfPointsFlat.get(), surfPointsLessFlat.get(),
+                          segmentedCloud.get() };
+        for (int k = 0; k < 5; k++) {
+            int n = k < 4 ? counts[k] : seg.n;
+            out[k]->resize(n);
+            if (n > 0) last_status = llb_features_get(ctx_, k, as_llb(*out[k]), n, &n);
+        }
+        features_on_device_ = true;
+    }
 
     // replaces the two kdtree->setInputCloud calls of FA:1615-1616 / FA:1786-1787
     void setLastClouds()
@@ -263,6 +307,7 @@ public:
 private:
     void push_features()
     {
+        if (features_on_device_) { last_status = llb_features_to_odometry(ctx_); features_on_device_ = false; return; }
         last_status = llb_odom_set_features(ctx_, as_llb(*cornerPointsSharp), (int)cornerPointsSharp->size(),
                                             as_llb(*surfPointsFlat), (int)surfPointsFlat->size());
     }
@@ -282,6 +327,8 @@ private:
     }
     llb_ctx *ctx_ = nullptr;
     int staged_which_ = 0, staged_iter_ = 0;
+    int fe_staged_ = 0;
+    bool features_on_device_ = false;   // cornerPointsSharp / surfPointsFlat of the last extractFeatures() are still on the device
 };
 
 }  // namespace lego_loam_b200

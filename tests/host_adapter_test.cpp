@@ -4,6 +4,7 @@
 #include "../lego_loam_b200/host/lego_loam_b200.hpp"
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 
 using namespace lego_loam_b200;
@@ -46,6 +47,32 @@ int main(int argc, char **argv)
     FA.updateTransformation();                  // FA:1853
     printf("FA %d %d", FA.stats_surf.iterations, FA.stats_corner.iterations);
     for (int i = 0; i < 6; i++) printf(" %.9g", FA.transformCur[i]);
+    printf("\n");
+    // feature extraction: segmentedCloud + segInfo -> the four feature clouds (FA:1827-1833)
+    int n_scan = 0, horizon = 0;
+    f.read((char *)&n_scan, 4); f.read((char *)&horizon, 4);
+    if (!f) return 0;
+    FeatureAssociation FE;
+    FE.initFeatureExtraction(n_scan, horizon);
+    read_cloud(f, *FE.segmentedCloud);
+    const size_t n = FE.segmentedCloud->size();
+    FE.segInfo.startRingIndex.resize(n_scan); FE.segInfo.endRingIndex.resize(n_scan);
+    f.read((char *)FE.segInfo.startRingIndex.data(), 4 * n_scan); f.read((char *)FE.segInfo.endRingIndex.data(), 4 * n_scan);
+    f.read((char *)&FE.segInfo.startOrientation, 4); f.read((char *)&FE.segInfo.endOrientation, 4); f.read((char *)&FE.segInfo.orientationDiff, 4);
+    FE.segInfo.segmentedCloudGroundFlag.resize(n); FE.segInfo.segmentedCloudColInd.resize(n); FE.segInfo.segmentedCloudRange.resize(n);
+    f.read((char *)FE.segInfo.segmentedCloudGroundFlag.data(), n); f.read((char *)FE.segInfo.segmentedCloudColInd.data(), 4 * n);
+    f.read((char *)FE.segInfo.segmentedCloudRange.data(), 4 * n);
+    FE.adjustDistortion(); FE.calculateSmoothness(); FE.markOccludedPoints(); FE.extractFeatures();
+    const Cloud *out[4] = { FE.cornerPointsSharp.get(), FE.cornerPointsLessSharp.get(), FE.surfPointsFlat.get(), FE.surfPointsLessFlat.get() };
+    printf("FE %d", FE.last_status);
+    for (int k = 0; k < 4; k++) {
+        unsigned h = 2166136261u;                      // FNV-1a over the x, y, z words
+        for (const PointType &p : out[k]->points) {
+            const float v[3] = { p.x, p.y, p.z };
+            for (int a = 0; a < 3; a++) { unsigned w; memcpy(&w, &v[a], 4); h = (h ^ w) * 16777619u; }
+        }
+        printf(" %zu %u", out[k]->size(), h);
+    }
     printf("\n");
     return 0;
 }

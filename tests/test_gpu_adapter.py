@@ -40,6 +40,13 @@ def test_adapter_matches_oracle(tmp_path):
         f.write(np.ascontiguousarray(case["init"], np.float32).tobytes())
         for c in (od.corner_last, od.surf_last, od.corner_sharp, od.surf_flat):
             w(c)
+        from lego_loam_b200 import synth
+        sw = synth.make_segmented_sweep(synth.make_world(), synth.VLP16, [0, 0.05, 0, 3, 0, 5], 3)
+        f.write(struct.pack("ii", 16, 1800)); w(sw.cloud)
+        f.write(sw.start_ring.astype(np.int32).tobytes()); f.write(sw.end_ring.astype(np.int32).tobytes())
+        f.write(struct.pack("fff", sw.start_ori, sw.end_ori, sw.ori_diff))
+        f.write(sw.ground.astype(np.uint8).tobytes()); f.write(sw.col.astype(np.uint32).tobytes())
+        f.write(sw.range.astype(np.float32).tobytes())
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
     mo_line = out[0].split(); fa_line = out[1].split()
 
@@ -63,3 +70,17 @@ def test_adapter_matches_oracle(tmp_path):
     assert (int(fa_line[1]), int(fa_line[2])) == (it1, it2)
     assert np.allclose(np.array(fa_line[3:9], np.float32), fa.transformCur, atol=1e-5)
     oracle.set_trig_mode(0)
+
+    # extractFeatures through the adapter: sizes and the x, y, z words of the four clouds (FNV-1a) as the oracle has them
+    fe_line = out[2].split()
+    assert fe_line[0] == "FE" and int(fe_line[1]) == 0
+    want = oracle.FeatureExtraction(16, 1800).extract(sw)
+
+    def fnv(cloud):
+        h = 2166136261
+        for wd in np.ascontiguousarray(cloud[:, :3], np.float32).view(np.uint32).ravel().tolist():
+            h = ((h ^ wd) * 16777619) & 0xFFFFFFFF
+        return h
+    for k in range(4):
+        assert int(fe_line[2 + 2 * k]) == want[k].shape[0]
+        assert int(fe_line[3 + 2 * k]) == fnv(want[k])
