@@ -193,10 +193,15 @@ int llb_features_init(llb_ctx *ctx, int n_scan, int horizon_scan);
  * curvatures included); the time part of the intensity goes through atan2, taken correctly rounded here. */
 int llb_features_extract(llb_ctx *ctx, const llb_segmented_cloud *seg, int counts[4], float *device_ms);
 /* which: 0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud after
- * adjustDistortion */
+ * adjustDistortion, 5 / 6 laserCloudCornerLast / laserCloudSurfLast after llb_features_publish_last */
 int llb_features_get(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
 /* cloudCurvature / cloudNeighborPicked / cloudLabel of the last sweep (parity checks) */
 int llb_features_get_state(llb_ctx *ctx, float *curvature, int *neighbor_picked, int *label, int capacity);
+/* cloud part of publishCloudsLast (FA:1759-1788) after updateTransformation: TransformToEnd (FA:885-953, no IMU data) of
+ * cornerPointsLessSharp / surfPointsLessFlat with transformCur, the results become laserCloudCornerLast /
+ * laserCloudSurfLast of the odometry (= llb_odom_set_last on them, without leaving the device; the clouds are always
+ * indexed, see llb_odom_set_last).  llb_features_get(which = 5 / 6) reads them back. */
+int llb_features_publish_last(llb_ctx *ctx, const float transformCur[6]);
 /* SM cycles of the slowest ring of the last sweep (profiling): [0] sort phase, [1] picks; then the slowest warp / ring
  * per part: [2] partitions, [3] leaf ranges, [4] edge picks, [5] flat picks, [6..9] reserved */
 int llb_features_get_profile(llb_ctx *ctx, int cycles[10]);

@@ -67,7 +67,7 @@ EXPORTS = [
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
-    "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile",
+    "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
     "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
     "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
@@ -362,6 +362,11 @@ class Context:
         curv = np.zeros(max(n, 1), np.float32); picked = np.zeros(max(n, 1), np.int32); label = np.zeros(max(n, 1), np.int32)
         self._ck(lib().llb_features_get_state(self._h, _vp(curv), _vp(picked), _vp(label), curv.shape[0]))
         return curv[:n], picked[:n], label[:n]
+
+    def features_publish_last(self, transformCur):
+        """TransformToEnd of the less-sharp / less-flat clouds -> laserCloudCornerLast / laserCloudSurfLast (FA:1759-1788)"""
+        t = np.ascontiguousarray(transformCur, np.float32)
+        self._ck(lib().llb_features_publish_last(self._h, _fp(t)))
 
     def features_get_profile(self):
         cyc = (ctypes.c_int * 10)()

@@ -93,6 +93,7 @@ struct llb_ctx {
     FeatureExtractor features;
     bool features_done = false;
     float features_ms = 0.f;
+    int features_last_n[2] = { -1, -1 };   // sizes of laserCloudCornerLast / laserCloudSurfLast set by llb_features_publish_last
 
     // device-resident key-frame store + assembled raw local map
     KeyFrameStore kfs;
@@ -1130,8 +1131,16 @@ int llb_features_extract(llb_ctx *c, const llb_segmented_cloud *seg, int counts[
 int llb_features_get(llb_ctx *c, int which, llb_point *out, int cap, int *n)
 {
     return guarded(c, [&]() {
-        if (!n || which < 0 || which > 4) return (int)LLB_ERR_INVALID;
+        if (!n || which < 0 || which > 6) return (int)LLB_ERR_INVALID;
         if (!c->features_done) return (int)LLB_ERR_STATE;
+        if (which >= 5) {
+            if (c->features_last_n[which - 5] < 0) return (int)LLB_ERR_STATE;
+            *n = c->features_last_n[which - 5];
+            if (!out) return (int)LLB_OK;
+            if (*n > cap) return (int)LLB_ERR_CAPACITY;
+            download_cloud(c, which == 5 ? c->odom.cornerLast().p : c->odom.surfLast().p, *n, out);
+            return (int)LLB_OK;
+        }
         const int cnt = which == 4 ? c->features.n_points() : c->features.counts()[which];
         *n = cnt;
         if (!out) return (int)LLB_OK;
@@ -1153,6 +1162,20 @@ int llb_features_get_state(llb_ctx *c, float *curvature, int *neighbor_picked, i
         if (!c->features_done) return (int)LLB_ERR_STATE;
         if (c->features.n_points() > cap) return (int)LLB_ERR_CAPACITY;
         c->features.get_state(curvature, neighbor_picked, label, c->features.n_points(), c->stream);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_publish_last(llb_ctx *c, const float transformCur[6])
+{
+    return guarded(c, [&]() {
+        if (!transformCur) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        const int ncl = c->features.counts()[1], nsl = c->features.counts()[3];
+        c->odom.cornerLast().ensure(std::max(ncl, 1)); c->odom.surfLast().ensure(std::max(nsl, 1));
+        c->launches += c->features.transform_to_end(transformCur, c->odom.cornerLast().p, c->odom.surfLast().p, c->stream);
+        c->launches += c->odom.set_last(ncl, nsl, c->stream);
+        c->features_last_n[0] = ncl; c->features_last_n[1] = nsl;
         return (int)LLB_OK;
     });
 }

@@ -433,6 +433,73 @@ __global__ void __launch_bounds__(1024) fe_concat_kernel(FeView v)
     }
 }
 
+struct FeEndJob { const float4 *in[2]; float4 *out[2]; int n[2]; float T[6]; };
+
+__device__ __forceinline__ float fe_cosf(float x) { return (float)cos((double)x); }   // correctly rounded, as K5 takes them
+__device__ __forceinline__ float fe_sinf(float x) { return (float)sin((double)x); }
+
+// TransformToEnd FA:885-953 with the IMU terms of a node that never received an IMU message (angles and shifts 0; the
+// factors stay in the expressions so that signed zeros come out as in the reference)
+__global__ void __launch_bounds__(FE_TPB) fe_to_end_kernel(FeEndJob jb)
+{
+    const float *T = jb.T;
+    const float zero = 0.f;
+    const float cosImuRollStart = fe_cosf(zero), cosImuPitchStart = fe_cosf(zero), cosImuYawStart = fe_cosf(zero);
+    const float sinImuRollStart = fe_sinf(zero), sinImuPitchStart = fe_sinf(zero), sinImuYawStart = fe_sinf(zero);
+    const float cYawL = fe_cosf(zero), sYawL = fe_sinf(zero), cPitchL = fe_cosf(zero), sPitchL = fe_sinf(zero);
+    const float cRollL = fe_cosf(zero), sRollL = fe_sinf(zero);
+    const float cRy = fe_cosf(T[1]), sRy = fe_sinf(T[1]), cRx = fe_cosf(T[0]), sRx = fe_sinf(T[0]);
+    const float cRz = fe_cosf(T[2]), sRz = fe_sinf(T[2]);
+    const int total = jb.n[0] + jb.n[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int which = i < jb.n[0] ? 0 : 1, k = which ? i - jb.n[0] : i;
+        const float4 pi = jb.in[which][k];
+        const float s = 10 * (pi.w - (int)pi.w);
+        float rx = s * T[0], ry = s * T[1], rz = s * T[2], tx = s * T[3], ty = s * T[4], tz = s * T[5];
+        const float crz = fe_cosf(rz), srz = fe_sinf(rz), crx = fe_cosf(rx), srx = fe_sinf(rx), cry = fe_cosf(ry), sry = fe_sinf(ry);
+        const float x1 = crz * (pi.x - tx) + srz * (pi.y - ty);
+        const float y1 = -srz * (pi.x - tx) + crz * (pi.y - ty);
+        const float z1 = (pi.z - tz);
+        const float x2 = x1;
+        const float y2 = crx * y1 + srx * z1;
+        const float z2 = -srx * y1 + crx * z1;
+        const float x3 = cry * x2 - sry * z2;
+        const float y3 = y2;
+        const float z3 = sry * x2 + cry * z2;
+        tx = T[3]; ty = T[4]; tz = T[5];
+        const float x4 = cRy * x3 + sRy * z3;
+        const float y4 = y3;
+        const float z4 = -sRy * x3 + cRy * z3;
+        const float x5 = x4;
+        const float y5 = cRx * y4 - sRx * z4;
+        const float z5 = sRx * y4 + cRx * z4;
+        const float x6 = cRz * x5 - sRz * y5 + tx;
+        const float y6 = sRz * x5 + cRz * y5 + ty;
+        const float z6 = z5 + tz;
+        const float x7 = cosImuRollStart * (x6 - zero) - sinImuRollStart * (y6 - zero);
+        const float y7 = sinImuRollStart * (x6 - zero) + cosImuRollStart * (y6 - zero);
+        const float z7 = z6 - zero;
+        const float x8 = x7;
+        const float y8 = cosImuPitchStart * y7 - sinImuPitchStart * z7;
+        const float z8 = sinImuPitchStart * y7 + cosImuPitchStart * z7;
+        const float x9 = cosImuYawStart * x8 + sinImuYawStart * z8;
+        const float y9 = y8;
+        const float z9 = -sinImuYawStart * x8 + cosImuYawStart * z8;
+        const float x10 = cYawL * x9 - sYawL * z9;
+        const float y10 = y9;
+        const float z10 = sYawL * x9 + cYawL * z9;
+        const float x11 = x10;
+        const float y11 = cPitchL * y10 + sPitchL * z10;
+        const float z11 = -sPitchL * y10 + cPitchL * z10;
+        float4 po;
+        po.x = cRollL * x11 + sRollL * y11;
+        po.y = -sRollL * x11 + cRollL * y11;
+        po.z = z11;
+        po.w = (float)(int)pi.w;
+        jb.out[which][k] = po;
+    }
+}
+
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 }  // namespace
@@ -539,6 +606,19 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
     // ---- results: header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
     LLB_CUDA(cudaMemcpyAsync(pin_out_.p, out_block_.p, out_off_[3] + sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s));
     return 5;
+}
+
+int FeatureExtractor::transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s)
+{
+    FeEndJob jb;
+    jb.in[0] = dev_cloud(1); jb.in[1] = dev_cloud(3); jb.out[0] = corner_out; jb.out[1] = surf_out;
+    jb.n[0] = counts()[1]; jb.n[1] = counts()[3];
+    for (int i = 0; i < 6; i++) jb.T[i] = T[i];
+    const int total = jb.n[0] + jb.n[1];
+    if (total <= 0) return 0;
+    fe_to_end_kernel<<<std::min(div_up(total, FE_TPB), 148 * 4), FE_TPB, 0, s>>>(jb);
+    LLB_CUDA(cudaGetLastError());
+    return 1;
 }
 
 void FeatureExtractor::get_state(float *curv, int *picked, int *label, int n, cudaStream_t s)

@@ -59,6 +59,8 @@ public:
         return which == 4 ? cloud_adj_.p : reinterpret_cast<const float4 *>(out_block_.p + out_off_[which]);
     }
     int n_points() const { return n_; }
+    // TransformToEnd (FA:885-953) of cornerPointsLessSharp / surfPointsLessFlat into the given device clouds
+    int transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s);
     void get_state(float *curv, int *picked, int *label, int n, cudaStream_t s);
     FeParams prm{ 0.1f, 0.1f, 0.1f, 0.2f };
 private:

@@ -278,6 +278,22 @@ public:
         features_on_device_ = true;
     }
 
+    // cloud part of publishCloudsLast (FA:1759-1788): TransformToEnd of the less-sharp / less-flat clouds with transformCur,
+    // which become laserCloudCornerLast / laserCloudSurfLast (indexed on the device); fetch = copy them to the members too
+    void publishCloudsLast(bool fetch = true)
+    {
+        last_status = llb_features_publish_last(ctx_, transformCur);
+        if (last_status != LLB_OK) return;
+        Cloud *out[2] = { laserCloudCornerLast.get(), laserCloudSurfLast.get() };
+        int n[2] = { 0, 0 };
+        for (int k = 0; k < 2; k++) {
+            last_status = llb_features_get(ctx_, 5 + k, nullptr, 0, &n[k]);
+            if (last_status != LLB_OK) return;
+            if (fetch) { out[k]->resize(n[k]); if (n[k] > 0) last_status = llb_features_get(ctx_, 5 + k, as_llb(*out[k]), n[k], &n[k]); }
+        }
+        laserCloudCornerLastNum = n[0]; laserCloudSurfLastNum = n[1];
+    }
+
     // replaces the two kdtree->setInputCloud calls of FA:1615-1616 / FA:1786-1787
     void setLastClouds()
     {

@@ -324,3 +324,10 @@ class FeatureExtraction:
         lib().llo_features_get_state(self._h, n, _fp(curv), picked.ctypes.data_as(ctypes.c_void_p),
                                      label.ctypes.data_as(ctypes.c_void_p))
         return curv, picked, label
+
+
+def transform_to_end(T, cloud):
+    """TransformToEnd FA:885-953 on every point (no IMU messages); sin/cos per set_trig_mode."""
+    t = np.ascontiguousarray(T, np.float32); c = _pts(cloud).copy()
+    lib().llo_transform_to_end(_fp(t), _fp(c), c.shape[0])
+    return c

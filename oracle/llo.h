@@ -166,6 +166,8 @@ void llo_features_extract(llo_features *f, llo_point *cloud, int n, const int *s
                           llo_point *const out[4], int n_out[4]);
 void llo_features_get_state(const llo_features *f, int n, float *curv, int *picked, int *label);
 void llo_adjust_distortion(llo_point *cloud, int n, float start_ori, float end_ori, float ori_diff, float scan_period);
+/* TransformToEnd FA:885-953 (no IMU messages received) on every point, in place */
+void llo_transform_to_end(const float T[6], llo_point *cloud, int n);
 /* libstdc++ std::sort of (value, ind) records compared by value only (FA:57-61, FA:699); depth_limit < 0 = std::sort's own */
 void llo_std_sort_by_value(float *value, uint32_t *ind, int n, int depth_limit);
 

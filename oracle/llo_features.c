@@ -285,3 +285,60 @@ void llo_features_extract(llo_features *f, llo_point *cloud, int n, const int *s
     }
     free(scan);
 }
+
+/* TransformToEnd FA:885-953 for every point of a cloud, in place, with the IMU terms of a node that never received an
+ * IMU message (imuRollStart = ... = 0, shifts 0: cos -> 1, sin -> 0, kept in the expressions as the reference has them).
+ * sin/cos through llo_sinf/llo_cosf (llo_set_trig_mode). */
+void llo_transform_to_end(const float T[6], llo_point *cloud, int n)
+{
+    const float zero = 0.f;
+    const float cosImuRollStart = llo_cosf(zero), cosImuPitchStart = llo_cosf(zero), cosImuYawStart = llo_cosf(zero);
+    const float sinImuRollStart = llo_sinf(zero), sinImuPitchStart = llo_sinf(zero), sinImuYawStart = llo_sinf(zero);
+    const float imuShiftFromStartX = 0.f, imuShiftFromStartY = 0.f, imuShiftFromStartZ = 0.f;
+    const float imuYawLast = 0.f, imuPitchLast = 0.f, imuRollLast = 0.f;
+    for (int i = 0; i < n; i++) {
+        const llo_point *pi = &cloud[i];
+        float s = 10 * (pi->intensity - (int)pi->intensity);
+        float rx = s * T[0], ry = s * T[1], rz = s * T[2], tx = s * T[3], ty = s * T[4], tz = s * T[5];
+        float x1 = llo_cosf(rz) * (pi->x - tx) + llo_sinf(rz) * (pi->y - ty);
+        float y1 = -llo_sinf(rz) * (pi->x - tx) + llo_cosf(rz) * (pi->y - ty);
+        float z1 = (pi->z - tz);
+        float x2 = x1;
+        float y2 = llo_cosf(rx) * y1 + llo_sinf(rx) * z1;
+        float z2 = -llo_sinf(rx) * y1 + llo_cosf(rx) * z1;
+        float x3 = llo_cosf(ry) * x2 - llo_sinf(ry) * z2;
+        float y3 = y2;
+        float z3 = llo_sinf(ry) * x2 + llo_cosf(ry) * z2;
+        rx = T[0]; ry = T[1]; rz = T[2]; tx = T[3]; ty = T[4]; tz = T[5];
+        float x4 = llo_cosf(ry) * x3 + llo_sinf(ry) * z3;
+        float y4 = y3;
+        float z4 = -llo_sinf(ry) * x3 + llo_cosf(ry) * z3;
+        float x5 = x4;
+        float y5 = llo_cosf(rx) * y4 - llo_sinf(rx) * z4;
+        float z5 = llo_sinf(rx) * y4 + llo_cosf(rx) * z4;
+        float x6 = llo_cosf(rz) * x5 - llo_sinf(rz) * y5 + tx;
+        float y6 = llo_sinf(rz) * x5 + llo_cosf(rz) * y5 + ty;
+        float z6 = z5 + tz;
+        float x7 = cosImuRollStart * (x6 - imuShiftFromStartX) - sinImuRollStart * (y6 - imuShiftFromStartY);
+        float y7 = sinImuRollStart * (x6 - imuShiftFromStartX) + cosImuRollStart * (y6 - imuShiftFromStartY);
+        float z7 = z6 - imuShiftFromStartZ;
+        float x8 = x7;
+        float y8 = cosImuPitchStart * y7 - sinImuPitchStart * z7;
+        float z8 = sinImuPitchStart * y7 + cosImuPitchStart * z7;
+        float x9 = cosImuYawStart * x8 + sinImuYawStart * z8;
+        float y9 = y8;
+        float z9 = -sinImuYawStart * x8 + cosImuYawStart * z8;
+        float x10 = llo_cosf(imuYawLast) * x9 - llo_sinf(imuYawLast) * z9;
+        float y10 = y9;
+        float z10 = llo_sinf(imuYawLast) * x9 + llo_cosf(imuYawLast) * z9;
+        float x11 = x10;
+        float y11 = llo_cosf(imuPitchLast) * y10 + llo_sinf(imuPitchLast) * z10;
+        float z11 = -llo_sinf(imuPitchLast) * y10 + llo_cosf(imuPitchLast) * z10;
+        llo_point po;
+        po.x = llo_cosf(imuRollLast) * x11 + llo_sinf(imuRollLast) * y11;
+        po.y = -llo_sinf(imuRollLast) * x11 + llo_cosf(imuRollLast) * y11;
+        po.z = z11;
+        po.intensity = (int)pi->intensity;
+        cloud[i] = po;
+    }
+}

@@ -206,11 +206,16 @@ class FeatureAssociation:
         self.L.ref_fa_extract_features(self._h)
 
     def feature_cloud(self, which, cap=40000):
-        """0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud."""
+        """0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud,
+        5 laserCloudCornerLast, 6 laserCloudSurfLast."""
         out = np.zeros((cap, 4), np.float32)
         n = self.L.ref_fa_get_cloud(self._h, int(which), _fp(out), cap)
         assert n <= cap
         return out[:n].copy()
+
+    def publishCloudsLast(self):
+        """FA:1759-1815; afterwards feature_cloud(5) / feature_cloud(6) = laserCloudCornerLast / laserCloudSurfLast."""
+        self.L.ref_fa_publishCloudsLast(self._h)
 
     def point_state(self):
         n = self._n_seg

@@ -125,9 +125,14 @@ int ref_fa_get_cloud(void *h, int which, llo_point *out, int cap)
     case 1: return dump(f->cornerPointsLessSharp, out, cap);
     case 2: return dump(f->surfPointsFlat, out, cap);
     case 3: return dump(f->surfPointsLessFlat, out, cap);
+    case 5: return dump(f->laserCloudCornerLast, out, cap);
+    case 6: return dump(f->laserCloudSurfLast, out, cap);
     default: return dump(f->segmentedCloud, out, cap);
     }
 }
+// publishCloudsLast FA:1759-1815: TransformToEnd on cornerPointsLessSharp / surfPointsLessFlat, swap into
+// laserCloudCornerLast / laserCloudSurfLast, kd-tree rebuild
+void ref_fa_publishCloudsLast(void *h) { ((FeatureAssociation *)h)->publishCloudsLast(); }
 void ref_fa_get_point_state(void *h, int n, float *curv, int *picked, int *label)
 {
     FeatureAssociation *f = (FeatureAssociation *)h;
