@@ -410,11 +410,43 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
     same_xyz = all(g.shape == r.shape and np.array_equal(g[:, :3].view(np.uint32), np.asarray(r)[:, :3].view(np.uint32))
                    for g, r in zip(got, ref))
     dint = max(float(np.max(np.abs(g[:, 3] - np.asarray(r)[:, 3]))) if g.size and g.shape == r.shape else 0.0 for g, r in zip(got, ref))
+    # FA side of a node cycle, device-resident: extractFeatures -> updateTransformation -> publishCloudsLast; only the
+    # segmented cloud goes up, only the pose comes back
+    cyc = api.Context(local); cyc.features_init(16, 1800)
+    cyc_wall, T = [], np.zeros(6, np.float32)
+    for i in range(reps + 3):
+        t0 = time.perf_counter()
+        cyc.features_extract(sws[i % 4])
+        if i > 0:
+            cyc.features_to_odometry()
+            T, s0, s1 = cyc.odom_optimize(np.zeros(6, np.float32))
+        cyc.features_publish_last(T)
+        cyc.synchronize()
+        if i >= 3:
+            cyc_wall.append((time.perf_counter() - t0) * 1e3)
+    cyc.close()
+    cpu_cyc = None
+    if fa is not None:
+        fa2 = ref_harness.FeatureAssociation()
+        t_cpu = []
+        for i in range(reps + 3):
+            t0 = time.perf_counter()
+            fa2.set_segmented(sws[i % 4]); fa2.extract_features()
+            fa2.transformCur = np.zeros(6, np.float32)
+            if i > 0:
+                fa2.updateTransformation()
+            fa2.publishCloudsLast()
+            t_cpu.append((time.perf_counter() - t0) * 1e3)
+        cpu_cyc = {"ms_per_sweep": float(np.median(t_cpu[3:])), "kind": "reference",
+                   "pose_max_abs_diff": float(np.max(np.abs(np.asarray(fa2.transformCur) - np.asarray(T))))}
     return {"ms_per_sweep_device": float(np.median(dev_ms)), "ms_per_sweep_e2e_host": float(np.median(wall_ms)),
             "points": int(last.cloud.shape[0]), "counts": [int(x) for x in counts],
             "cpu_1core": {"ms_per_sweep": float(np.median(cpu_t[3:])), "kind": kind,
                           "sample": f"{reps} sweeps (includes the harness copies of the clouds in and out)"},
             "selection_and_xyz_identical_to_cpu": bool(same_xyz), "intensity_max_abs_diff_vs_cpu": dint,
+            "fa_cycle": {"ms_per_sweep_e2e_host": float(np.median(cyc_wall)), "cpu_1core": cpu_cyc,
+                         "what": "extractFeatures + updateTransformation + publishCloudsLast (TransformToEnd, last clouds, index) "
+                                 "per sweep; device: one upload (segmented cloud + cloud_info), pose back"},
             "note": "5 launches per sweep: per-point kernels, one CTA per ring (sector sorts = libstdc++ std::sort move "
                     "for move, greedy picks 32 candidates per step), per-ring VoxelGrid(0.2), concatenation"}
 
