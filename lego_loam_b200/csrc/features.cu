@@ -115,19 +115,14 @@ __device__ __forceinline__ int win_ground(const FeView &v, const RingWin &w, int
 {
     return (i >= w.w0 && i < w.w1) ? (int)w.gr[i - w.w0] : fe_ground(v, i);
 }
-// FA:727-740 == FA:758-773 by the whole warp: lanes 0-4 test the forward steps l = 1..5, lanes 5-9 the backward steps
-// l = -1..-5; a step is marked only if no earlier step of its direction broke off.  nf / nb: steps marked per direction.
-__device__ __forceinline__ void fe_mark_neighbors(const FeView &v, const RingWin &w, int ind, int lane, int &nf, int &nb)
+// FA:727-740 == FA:758-773: a pick at point i marks i, the forward steps i+1 .. i+nf and the backward steps i-1 .. i-nb,
+// each direction up to 5 steps or the first column gap above 10.  nf | nb << 4 per point is a property of the sweep.
+__device__ __forceinline__ int fe_reach(const FeView &v, const RingWin &w, int i)
 {
-    const bool fw = lane < 5, act = lane < 10;
-    const int pos = act ? (fw ? ind + lane + 1 : ind - (lane - 4)) : ind;
-    const int prev = fw ? pos - 1 : pos + 1;
-    bool brk = false;
-    if (act) brk = pos < 0 || win_col_diff(v, w, pos, prev) > 10;   // pos < 0: only through the stale record {0, 0}
-    const unsigned b = __ballot_sync(FULL, brk);
-    const unsigned fwd = b & 0x1fu, bwd = (b >> 5) & 0x1fu;
-    nf = fwd ? __ffs(fwd) - 1 : 5; nb = bwd ? __ffs(bwd) - 1 : 5;
-    if (lane < nf || (lane >= 5 && lane - 5 < nb) || lane == 31) pk_set(w, pos);
+    int nf = 0, nb = 0;
+    while (nf < 5 && win_col_diff(v, w, i + nf + 1, i + nf) <= 10) nf++;
+    while (nb < 5 && i - nb - 1 >= 0 && win_col_diff(v, w, i - nb - 1, i - nb) <= 10) nb++;   // i - nb - 1 < 0: see fe_ring_kernel
+    return nf | (nb << 4);
 }
 
 // ---- libstdc++ std::sort by one warp (std_sort.cuh: closed-form partitions + independent leaf ranges; checked on the
@@ -244,7 +239,7 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
     unsigned char *s_gr = s_pk + wcap;
     __shared__ int s_tot[FE_RING_THREADS / 32];
     __shared__ int s_sharp[FE_SHARP_PER_RING], s_lsharp[FE_LSHARP_PER_RING], s_flat[FE_FLAT_PER_RING], s_n[3];
-    __shared__ int s_owner, s_late;
+    __shared__ int s_owner, s_late, s_walk[6];
     const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int st = __ldg(v.start_ring + ring), en = __ldg(v.end_ring + ring);
     // the record at position 4 is never rewritten by calculateSmoothness (FA:624 starts at 5) while sector 0 of the
@@ -291,6 +286,18 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
     }
     __syncthreads();
     RingWin w{ s_pk, s_gr, s_col, s_curv, w0, w1, (volatile int *)v.picked, v.cap };
+    unsigned char *s_reach = reinterpret_cast<unsigned char *>(s_tmp);        // [wcap]; the sort scratch is free again
+    for (int k = w0 + tid; k < w1; k += FE_RING_THREADS) s_reach[k - w0] = (unsigned char)fe_reach(v, w, k);
+    // a sector without non-ground (ground) points has no edge (flat) candidates: its loop is not walked at all.  The
+    // sector that holds the stale record is always walked (the record may name a point outside the sector).
+    if (warp < 6) {
+        int sp, ep; fe_sector(st, en, warp, sp, ep);
+        bool any_g = false, any_ng = false;
+        for (int k = sp + lane; k <= ep && sp < ep; k += 32) { const bool g = s_gr[k - w0] != 0; any_g |= g; any_ng |= !g; }
+        any_g = __any_sync(FULL, any_g); any_ng = __any_sync(FULL, any_ng);
+        if (lane == 0) s_walk[warp] = (owner == ring && warp == 0) ? 3 : ((any_ng ? 1 : 0) | (any_g ? 2 : 0));
+    }
+    __syncthreads();
     // ---- greedy picks, sectors in order (a pick of sector j may block neighbours that belong to sector j+1)
     if (warp == 0) {
         int nsharp = 0, nls = 0, nflat = 0;
@@ -300,7 +307,8 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
             if (sp >= ep) continue;
             int cnt = 0;
             const long long tl0 = clock64();
-            for (int khi = ep; khi >= sp && cnt < 20; khi -= 32) {                       // FA:701-742
+            const int walk = s_walk[j];
+            for (int khi = ep; khi >= sp && cnt < 20 && (walk & 1); khi -= 32) {         // FA:701-742
                 const int k = khi - lane;
                 const bool valid = k >= sp;
                 const int ind = valid ? (int)(unsigned)s_rec[k - st] : w0;
@@ -308,17 +316,18 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
                 // flags set by earlier chunks / sectors come from shared memory once; inside the chunk every lane follows
                 // the marks of the picks in registers
                 bool el = stat && pk_get(w, ind) == 0;
+                const int my_reach = !stat ? 0 : (ind >= w0 && ind < w1) ? (int)s_reach[ind - w0] : fe_reach(v, w, ind);
                 for (;;) {
                     const unsigned b = __ballot_sync(FULL, el);
                     if (!b) break;
                     const int f = __ffs(b) - 1;
-                    const int pind = __shfl_sync(FULL, ind, f);
+                    const int pind = __shfl_sync(FULL, ind, f), pr = __shfl_sync(FULL, my_reach, f);
+                    const int nf = pr & 15, nb = pr >> 4;
                     if (lane == f) {      // labels and the points themselves are written after the picks, by all threads
                         if (cnt < 2) s_sharp[nsharp] = ind;
                         s_lsharp[nls] = ind;
                     }
-                    int nf, nb;
-                    fe_mark_neighbors(v, w, pind, lane, nf, nb);
+                    if (lane <= nf + nb) pk_set(w, pind - nb + lane);
                     if (cnt < 2) nsharp++;
                     nls++; cnt++;
                     if (cnt >= 20) break;
@@ -330,22 +339,23 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
             const long long tl1 = clock64();
             c_large += tl1 - tl0;
             bool done = false;
-            for (int klo = sp; klo <= ep && !done; klo += 32) {                          // FA:744-775
+            for (int klo = sp; klo <= ep && !done && (walk & 2); klo += 32) {            // FA:744-775
                 const int k = klo + lane;
                 const bool valid = k <= ep;
                 const int ind = valid ? (int)(unsigned)s_rec[k - st] : w0;
                 bool stat = valid && win_curv(v, w, ind) < v.prm.surf_threshold && win_ground(v, w, ind) != 0;
                 bool el = stat && pk_get(w, ind) == 0;
+                const int my_reach = !stat ? 0 : (ind >= w0 && ind < w1) ? (int)s_reach[ind - w0] : fe_reach(v, w, ind);
                 for (;;) {
                     const unsigned b = __ballot_sync(FULL, el);
                     if (!b) break;
                     const int f = __ffs(b) - 1;
-                    const int pind = __shfl_sync(FULL, ind, f);
+                    const int pind = __shfl_sync(FULL, ind, f), pr = __shfl_sync(FULL, my_reach, f);
+                    const int nf = pr & 15, nb = pr >> 4;
                     if (lane == f) s_flat[nflat] = ind;
                     nflat++; cnt++;
                     if (cnt >= 4) { done = true; break; }                 // the 4th pick breaks before the marks, FA:752-756
-                    int nf, nb;
-                    fe_mark_neighbors(v, w, pind, lane, nf, nb);
+                    if (lane <= nf + nb) pk_set(w, pind - nb + lane);
                     if (lane <= f || (ind >= pind - nb && ind <= pind + nf)) el = false;
                 }
                 __syncwarp();
