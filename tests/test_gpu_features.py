@@ -175,3 +175,20 @@ def test_device_resident_odometry_loop_matches_reference_functions():
     finally:
         oracle.set_trig_mode(0)
     ctx.close()
+
+
+def test_features_match_committed_reference_vectors():
+    """The device path against the golden vectors made from the compiled reference (tests/golden/ref_features_golden.npz)."""
+    from tests.test_oracle_features import golden_sweeps, assert_cloud_matches_golden
+    sweeps_, T = golden_sweeps()
+    ctx = api.Context(0); ctx.features_init(16, 1800)
+    for sw, want in sweeps_:
+        ctx.features_extract(sw)
+        for k, n in enumerate(("sharp", "less_sharp", "flat", "less_flat")):
+            assert_cloud_matches_golden(ctx.features_get(k), want[n], n)
+        curv, picked, label = ctx.features_get_state(sw.cloud.shape[0])
+        assert np.array_equal(label, want["label"].astype(np.int32)) and np.array_equal(picked, want["picked"].astype(np.int32))
+        ctx.features_publish_last(T)
+        assert_cloud_matches_golden(ctx.features_get(5), want["corner_last"], "corner_last", xyz_tol=2e-5)
+        assert_cloud_matches_golden(ctx.features_get(6), want["surf_last"], "surf_last", xyz_tol=2e-5)
+    ctx.close()

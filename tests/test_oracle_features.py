@@ -68,3 +68,45 @@ def test_feature_extraction_restatement_matches_reference(quantize):
         assert got[0].shape[0] > 50 and got[2].shape[0] > 50 and got[3].shape[0] > 2000
     if quantize:
         assert ties > 1000
+
+
+def golden_sweeps():
+    """Inputs and reference outputs committed under tests/golden (made by tests/golden/make_ref_golden.py from the compiled
+    reference): a 2-sweep sequence through one FeatureAssociation object, ranges quantised to 2 cm."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_features_golden.npz"))
+    out = []
+    for k in range(int(g["n_sweeps"])):
+        o = g[f"in_ori_{k}"]
+        sw = synth.SegmentedSweep(g[f"in_cloud_{k}"], g[f"in_start_ring_{k}"], g[f"in_end_ring_{k}"], float(o[0]), float(o[1]),
+                                  float(o[2]), g[f"in_ground_{k}"], g[f"in_col_{k}"], g[f"in_range_{k}"], np.zeros((0, 4), np.float32))
+        want = {n: g[f"out_{n}_{k}"] for n in ("sharp", "less_sharp", "flat", "less_flat", "adjusted_intensity", "label", "picked",
+                                               "corner_last", "surf_last")}
+        out.append((sw, want))
+    return out, g["T"]
+
+
+def assert_cloud_matches_golden(got, ref, name, xyz_tol=0.0):
+    """x, y, z identical (or within xyz_tol where sin/cos flavours enter); intensity within 2 ulp (atan2 flavour)."""
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    if xyz_tol == 0.0:
+        assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32)), name
+    else:
+        assert np.max(np.abs(got[:, :3] - ref[:, :3])) <= xyz_tol, name
+    tol = 2 * np.spacing(np.maximum(np.abs(ref[:, 3]), np.float32(1)))
+    assert np.all(np.abs(got[:, 3] - ref[:, 3]) <= tol), name
+
+
+def test_feature_extraction_restatement_matches_committed_reference_vectors():
+    """Pins the restatement without /root/reference and without oracle/_ref."""
+    sweeps_, T = golden_sweeps()
+    fe = oracle.FeatureExtraction(16, 1800)
+    for sw, want in sweeps_:
+        got = fe.extract(sw)
+        for k, n in enumerate(("sharp", "less_sharp", "flat", "less_flat")):
+            assert_cloud_matches_golden(got[k], want[n], n)
+        assert np.all(np.abs(got[4][:, 3] - want["adjusted_intensity"]) <= 2 * np.spacing(np.maximum(np.abs(want["adjusted_intensity"]), 1)))
+        curv, picked, label = fe.point_state()
+        assert np.array_equal(label, want["label"].astype(np.int32)) and np.array_equal(picked, want["picked"].astype(np.int32))
+        assert_cloud_matches_golden(oracle.transform_to_end(T, got[1]), want["corner_last"], "corner_last", xyz_tol=2e-5)
+        assert_cloud_matches_golden(oracle.transform_to_end(T, got[3]), want["surf_last"], "surf_last", xyz_tol=2e-5)
