@@ -425,6 +425,24 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
         if i >= 3:
             cyc_wall.append((time.perf_counter() - t0) * 1e3)
     cyc.close()
+    # throughput form: 64 sequences, one sweep each per step, on the batched engine (one set of five launches per step)
+    NBF = 64
+
+    class Held:          # a sweep with its 32 B-stride cloud built once (the caller's PCL cloud)
+        def __init__(self, sw):
+            self.__dict__.update(sw.__dict__); self.cloud32 = api.to_pcl(sw.cloud)
+    held = [Held(s) for s in sws]
+    fb = api.Batch(local, NBF, 4096, 4096); fb.features_init(16, 1800)
+    packs = [fb.features_pack([held[(s + i) % 4] for s in range(NBF)]) for i in range(2)]
+    fb_dev, fb_wall = [], []
+    for i in range(reps + 3):
+        t0 = time.perf_counter(); bcounts, bms = fb.features_extract(packs[i % 2]); t1 = time.perf_counter()
+        if i >= 3:
+            fb_dev.append(bms); fb_wall.append((t1 - t0) * 1e3)
+    fb.close()
+    batched = {"sweeps_per_step": NBF, "ms_per_step_device": float(np.median(fb_dev)),
+               "sweeps_per_s_e2e_host": NBF / (float(np.median(fb_wall)) * 1e-3),
+               "note": "segmented clouds + cloud_info of all slots in from host buffers, four feature clouds per slot out"}
     cpu_cyc = None
     if fa is not None:
         fa2 = ref_harness.FeatureAssociation()
@@ -444,6 +462,7 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
             "cpu_1core": {"ms_per_sweep": float(np.median(cpu_t[3:])), "kind": kind,
                           "sample": f"{reps} sweeps (includes the harness copies of the clouds in and out)"},
             "selection_and_xyz_identical_to_cpu": bool(same_xyz), "intensity_max_abs_diff_vs_cpu": dint,
+            "batched": batched,
             "fa_cycle": {"ms_per_sweep_e2e_host": float(np.median(cyc_wall)), "cpu_1core": cpu_cyc,
                          "what": "extractFeatures + updateTransformation + publishCloudsLast (TransformToEnd, last clouds, index) "
                                  "per sweep; device: one upload (segmented cloud + cloud_info), pose back"},

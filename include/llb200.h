@@ -323,6 +323,11 @@ int  llb_batch_keyframe_count(llb_batch *b, int slot, int *n);
 int  llb_batch_map_assemble(llb_batch *b, int slot, const int *ids, const float *poses, int n);
 /* which: 0 / 1 raw corner / surf map, 2 / 3 DS corner / surf map of the slot's last assembled map (parity checks) */
 int  llb_batch_map_get(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
+/* ---- feature extraction of the slots: llb_features_init / _extract / _get with one sweep per slot (segs[slots],
+ * counts[slots][4]); all slots share ONE set of five launches per step, every slot keeps its own per-point state */
+int  llb_batch_features_init(llb_batch *b, int n_scan, int horizon_scan);
+int  llb_batch_features_extract(llb_batch *b, const llb_segmented_cloud *segs, int *counts, float *device_ms);
+int  llb_batch_features_get(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
 /* ---- featureAssociation of the slots: llb_odom_set_last + llb_odom_set_features + llb_odom_optimize with a leading slot
  * index; updateTransformation (FA:1666-1695) of ALL slots is one launch (one persistent CTA per slot).  T: n_slots x 6
  * transformCur in/out; stats arrays of n_slots entries or NULL.  isDegenerate / matP and the neighbour indices kept

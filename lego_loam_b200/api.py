@@ -68,6 +68,7 @@ EXPORTS = [
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
     "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
+    "llb_batch_features_init", "llb_batch_features_extract", "llb_batch_features_get",
     "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
     "llb_map_get_raw",
     "llb_batch_create", "llb_batch_destroy", "llb_batch_last_error", "llb_batch_stream", "llb_batch_slots",
@@ -116,6 +117,19 @@ class SegmentedCloud(ctypes.Structure):
                 ("end_ring", ctypes.c_void_p), ("start_orientation", ctypes.c_float), ("end_orientation", ctypes.c_float),
                 ("orientation_diff", ctypes.c_float), ("ground_flag", ctypes.c_void_p), ("col_ind", ctypes.c_void_p),
                 ("range", ctypes.c_void_p)]
+
+
+def segmented_struct(sw, seg=None):
+    """SegmentedSweep-like object -> (llb_segmented_cloud, arrays that must stay alive during the call)"""
+    seg = SegmentedCloud() if seg is None else seg
+    keep = [sw.cloud32 if hasattr(sw, "cloud32") else to_pcl(sw.cloud), np.ascontiguousarray(sw.start_ring, np.int32),
+            np.ascontiguousarray(sw.end_ring, np.int32), np.ascontiguousarray(sw.ground, np.uint8),
+            np.ascontiguousarray(sw.col, np.uint32), np.ascontiguousarray(sw.range, np.float32)]
+    seg.cloud = _vp(keep[0]); seg.n = keep[0].shape[0]
+    seg.start_ring = _vp(keep[1]); seg.end_ring = _vp(keep[2])
+    seg.start_orientation = sw.start_ori; seg.end_orientation = sw.end_ori; seg.orientation_diff = sw.ori_diff
+    seg.ground_flag = _vp(keep[3]); seg.col_ind = _vp(keep[4]); seg.range = _vp(keep[5])
+    return seg, keep
 
 
 def to_pcl(pts) -> np.ndarray:
@@ -338,14 +352,7 @@ class Context:
 
     def features_extract(self, sw):
         """sw: a SegmentedSweep (lego_loam_b200.synth) or anything with its fields.  -> (counts[4], device_ms)"""
-        seg = SegmentedCloud()
-        keep = [to_pcl(sw.cloud), np.ascontiguousarray(sw.start_ring, np.int32), np.ascontiguousarray(sw.end_ring, np.int32),
-                np.ascontiguousarray(sw.ground, np.uint8), np.ascontiguousarray(sw.col, np.uint32),
-                np.ascontiguousarray(sw.range, np.float32)]
-        seg.cloud = _vp(keep[0]); seg.n = keep[0].shape[0]
-        seg.start_ring = _vp(keep[1]); seg.end_ring = _vp(keep[2])
-        seg.start_orientation = sw.start_ori; seg.end_orientation = sw.end_ori; seg.orientation_diff = sw.ori_diff
-        seg.ground_flag = _vp(keep[3]); seg.col_ind = _vp(keep[4]); seg.range = _vp(keep[5])
+        seg, keep = segmented_struct(sw)
         counts = (ctypes.c_int * 4)(); ms = ctypes.c_float(0)
         self._ck(lib().llb_features_extract(self._h, ctypes.byref(seg), counts, ctypes.byref(ms)))
         return list(counts), float(ms.value)
@@ -627,6 +634,29 @@ class Batch:
         for a in arrs:
             args += [_vp(a), a.shape[0]]
         self._ck(lib().llb_batch_odom_set(self._h, slot, *args))
+
+    # ---- feature extraction of the slots
+    def features_init(self, n_scan: int, horizon_scan: int):
+        self._ck(lib().llb_batch_features_init(self._h, int(n_scan), int(horizon_scan)))
+
+    def features_pack(self, sweeps):
+        """Builds the llb_segmented_cloud array for one sweep per slot (reusable across steps)."""
+        arr = (SegmentedCloud * len(sweeps))()
+        keep = [segmented_struct(sw, arr[i])[1] for i, sw in enumerate(sweeps)]
+        return arr, keep
+
+    def features_extract(self, packed):
+        arr, keep = packed
+        counts = np.zeros((len(arr), 4), np.int32); ms = ctypes.c_float(0)
+        self._ck(lib().llb_batch_features_extract(self._h, arr, _vp(counts), ctypes.byref(ms)))
+        return counts, float(ms.value)
+
+    def features_get(self, slot: int, which: int):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_batch_features_get(self._h, int(slot), int(which), None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_batch_features_get(self._h, int(slot), int(which), _vp(out), out.shape[0], ctypes.byref(n)))
+        return from_pcl(out[:n.value])
 
     def odom_optimize(self, T):
         """T: (n_slots, 6) transformCur -> (poses, [surf Stats], [corner Stats])"""

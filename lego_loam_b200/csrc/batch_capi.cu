@@ -3,6 +3,7 @@
 // No CPU fallback: llb_batch_create fails with LLB_ERR_NO_DEVICE without an sm_100 device.
 #include "../../include/llb200.h"
 #include "batch.cuh"
+#include "features.cuh"
 #include "odom.cuh"
 
 #include <cstring>
@@ -50,6 +51,8 @@ struct llb_batch {
     S2mParams sprm{};
     std::string err;
     long long launches = 0;
+    FeatureBatch features;               // feature extraction of the slots
+    bool features_done = false;
     int vox_cap1 = 1024, vox_cap2 = 1024;
     int B = 0, cap_scan = 0, cap_map = 0, qcap = 0, fit_blocks = 0, knn_ctas = 0, grid_ctas = 0;
     StepLayout lay{ 1 };
@@ -512,6 +515,7 @@ int llb_batch_destroy(llb_batch *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
+    c->features.release();
     c->scan_in.release(); c->scan_raw.release(); c->scan_ds.release(); c->map_in.release(); c->map_raw.release();
     c->ds_n.release(); c->states.release(); c->nn.release(); c->qperm.release(); c->d5.release(); c->partials.release();
     c->results.release(); c->pin_results.release(); c->step_dev.release();
@@ -917,6 +921,66 @@ int llb_batch_get_profile(llb_batch *c, float ms[6], int geometry[4])
     if (ms) for (int k = 0; k < PROF_N; k++) ms[k] = c->prof_ms[k];
     if (geometry) { geometry[0] = c->knn_ctas; geometry[1] = c->fit_blocks; geometry[2] = c->grid_ctas; geometry[3] = c->qcap; }
     return LLB_OK;
+}
+
+// ---------------------------------------------------------------- feature extraction of the slots
+int llb_batch_features_init(llb_batch *c, int n_scan, int horizon_scan)
+{
+    return guarded(c, [&]() {
+        if (n_scan <= 0 || n_scan > FE_MAX_RINGS || horizon_scan < 16 || horizon_scan > 4096) return (int)LLB_ERR_INVALID;
+        c->features.init(c->B, n_scan, horizon_scan, c->stream);
+        c->features_done = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_features_extract(llb_batch *c, const llb_segmented_cloud *segs, int *counts, float *device_ms)
+{
+    return guarded(c, [&]() {
+        if (!segs) return (int)LLB_ERR_INVALID;
+        if (!c->features.ready() || c->pending) return (int)LLB_ERR_STATE;
+        const int B = c->B;
+        std::vector<FeSweepHost> sw(B);
+        for (int s = 0; s < B; s++) {
+            const llb_segmented_cloud &g = segs[s];
+            FeatureExtractor &e = c->features.slot(s);
+            if (g.n < 0 || !g.start_ring || !g.end_ring) return (int)LLB_ERR_INVALID;
+            if (g.n > e.n_scan() * e.horizon()) return (int)LLB_ERR_CAPACITY;
+            if (g.n > 0 && (!g.cloud || !g.ground_flag || !g.col_ind || !g.range)) return (int)LLB_ERR_INVALID;
+            for (int r = 0; r < e.n_scan(); r++)
+                if (g.start_ring[r] < 4 || g.end_ring[r] > g.n - 6 || g.end_ring[r] - g.start_ring[r] > e.horizon())
+                    return (int)LLB_ERR_INVALID;
+            sw[s] = FeSweepHost{ reinterpret_cast<const float *>(g.cloud), g.n, g.start_ring, g.end_ring, g.start_orientation,
+                                 g.end_orientation, g.orientation_diff, g.ground_flag, g.col_ind, g.range };
+        }
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->features.extract(sw.data(), c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        c->features_done = true;
+        if (counts) for (int s = 0; s < B; s++) for (int k = 0; k < 4; k++) counts[4 * s + k] = c->features.slot(s).counts()[k];
+        if (device_ms) LLB_CUDA(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_batch_features_get(llb_batch *c, int slot, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || slot < 0 || slot >= c->B || which < 0 || which > 3) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        FeatureExtractor &e = c->features.slot(slot);
+        const int cnt = e.counts()[which];
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        const float4 *src = e.host_cloud(which);
+        for (int i = 0; i < cnt; i++) {
+            out[i].x = src[i].x; out[i].y = src[i].y; out[i].z = src[i].z; out[i].w = 1.0f;
+            out[i].intensity = src[i].w; out[i].c1 = out[i].c2 = out[i].c3 = 0.f;
+        }
+        return (int)LLB_OK;
+    });
 }
 
 }  // extern "C"

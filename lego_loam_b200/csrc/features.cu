@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <vector>
 #include <algorithm>
+#include <stdexcept>
 
 namespace llb {
 
@@ -32,9 +33,14 @@ __device__ __forceinline__ float fe_ori_first_half(float ori, float start_ori)
     return ori;
 }
 
-__global__ void __launch_bounds__(FE_TPB) fe_point_kernel(FeView v)
+// every kernel of the step reads its sweep from a device table: blockIdx.y = sweep (one entry for a single context, one per
+// slot for a batch)
+__global__ void __launch_bounds__(FE_TPB) fe_point_kernel(const FeView *__restrict__ table)
 {
-    if (blockIdx.x == 0 && threadIdx.x < 10) v.hdr->pad[threadIdx.x] = 0;      // pad[2] + prof[8]
+    const FeView v = table[blockIdx.y];
+    if (blockIdx.x == 0 && threadIdx.x < 9) v.hdr->pad[threadIdx.x] = 0;       // pad[2] + prof[7]
+    // the record calculateSmoothness never rewrites (see fe_ring_kernel), as it is before this sweep's sorts
+    if (blockIdx.x == 0 && threadIdx.x == 0) v.hdr->stale_ind = (int)(unsigned)v.smooth[4];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const float4 q = __ldg(v.cloud_in + i);
         // point.x = y, point.z = x; ori = -atan2(point.x, point.z) (float overload), FA:500-504
@@ -56,8 +62,9 @@ __global__ void __launch_bounds__(FE_TPB) fe_point_kernel(FeView v)
     }
 }
 
-__global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(FeView v)
+__global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(const FeView *__restrict__ table)
 {
+    const FeView v = table[blockIdx.y];
     const int half = v.hdr->first_half;       // the point at which halfPassed becomes true still takes the first branch
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const float4 q = __ldg(v.cloud_in + i);
@@ -228,8 +235,9 @@ __device__ __forceinline__ void fe_sector(int st, int en, int j, int &sp, int &e
     ep = (st * (5 - j) + en * (j + 1)) / 6 - 1;
 }
 
-__global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
+__global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(const FeView *__restrict__ table)
 {
+    const FeView v = table[blockIdx.y];
     extern __shared__ __align__(16) unsigned long long s_rec[];                       // [horizon + 8]
     const int wcap = v.horizon + 32;
     unsigned long long *s_tmp = s_rec + v.horizon + 8;                                 // [horizon + 8]
@@ -244,25 +252,27 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
     const int st = __ldg(v.start_ring + ring), en = __ldg(v.end_ring + ring);
     // the record at position 4 is never rewritten by calculateSmoothness (FA:624 starts at 5) while sector 0 of the
     // first populated ring starts there (IP:318): it is state from earlier sweeps and may name a point of another
-    // ring.  The ring that sorts it ("owner") then finishes its picks before the other rings read their flags.
+    // ring.  Only then (every ring can tell from the copy fe_point_kernel took of the record) the ring that sorts it
+    // ("owner") finishes its picks before the other rings read their flags.
     if (tid == 0) {
-        int owner = -1;
+        int owner = -1, late = 0;
         for (int r = 0; r < v.n_scan; r++) {
-            int sp, ep; fe_sector(__ldg(v.start_ring + r), __ldg(v.end_ring + r), 0, sp, ep);
-            if (sp == 4 && sp < ep) { owner = r; break; }
+            const int rs = __ldg(v.start_ring + r), re = __ldg(v.end_ring + r);
+            int sp, ep; fe_sector(rs, re, 0, sp, ep);
+            if (sp == 4 && sp < ep) {
+                owner = r;
+                const int stale = v.hdr->stale_ind, ow0 = max(0, rs - 6), ow1 = max(ow0, min(v.cap, re + 7));
+                late = (stale >= ow0 && stale < ow1) ? 0 : 1;
+                break;
+            }
         }
-        s_owner = owner; s_late = 0;
+        s_owner = owner; s_late = late;
     }
     const int w0 = max(0, st - 6), w1 = max(w0, min(v.cap, en + 7));
     const int nrec = max(0, en - st);                    // positions [st, en - 1] = [sp_0, ep_5]
     for (int k = tid; k < nrec; k += FE_RING_THREADS) s_rec[k] = v.smooth[st + k];
     __syncthreads();
     const int owner = s_owner;
-    if (owner == ring && tid == 0) {
-        const int stale = (int)(unsigned)s_rec[0];
-        if (stale >= w0 && stale < w1) { __threadfence(); atomicExch(&v.hdr->release_seq, v.seq); }
-        else s_late = 1;
-    }
     const long long t_start = clock64();
     // ---- the six sorts, one warp each
     if (warp < 6) {      // scratch: the shared arrays of the ring slice, which are filled only after the sorts
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
             warp_std_sort(s_rec + (sp - st), s_tmp + (sp - st), ep - sp, s_col + (sp - st), reinterpret_cast<unsigned short *>(s_curv) + (sp - st),
                           s_pk + (sp - st), lane, v.hdr->prof);
     }
-    if (owner >= 0 && owner != ring && tid == 0) {
+    if (owner >= 0 && owner != ring && s_late && tid == 0) {
         volatile int *flag = &v.hdr->release_seq;
         while (*flag != v.seq) __nanosleep(100);
         __threadfence();
@@ -409,8 +419,9 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(FeView v)
     if (tid == 0) v.r_cnt[ring * 4 + 3] = base;
 }
 
-__global__ void __launch_bounds__(1024) fe_concat_kernel(FeView v)
+__global__ void __launch_bounds__(1024) fe_concat_kernel(const FeView *__restrict__ table)
 {
+    const FeView v = table[blockIdx.y];
     __shared__ int s_off[4][FE_MAX_RINGS + 1];
     const int tid = threadIdx.x;
     __shared__ int s_c[4][FE_MAX_RINGS];
@@ -530,7 +541,8 @@ void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
     LLB_CUDA(cudaMemsetAsync(smooth_.p, 0, sizeof(unsigned long long) * cap, s));       // FA:223: {0, 0}
     FeHeader h{}; h.first_half = INT_MAX; h.release_seq = 0;
     LLB_CUDA(cudaMemcpyAsync(hdr_.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    std::vector<SmallJob> jobs(n_scan);
+    jobs_host_.assign(n_scan, SmallJob{});
+    std::vector<SmallJob> &jobs = jobs_host_;
     for (int r = 0; r < n_scan; r++) {
         SmallJob &j = jobs[r];
         j.in.a = r_lf_scan_.p + (size_t)r * horizon; j.in.na_dev = r_cnt_.p + r * 4 + 3; j.in.na = horizon;
@@ -567,12 +579,14 @@ const float4 *FeatureExtractor::host_cloud(int which) const
     return reinterpret_cast<const float4 *>(pin_out_.p + out_off_[which]);
 }
 
-int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
-                              float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
-                              const float *range, cudaStream_t s)
+// the sweep goes into one pinned block: [FeView, 256 B][cloud as float4][range][column][ring bounds][ground flags];
+// copy_in() sends it with one H2D, the view at its head is this sweep's entry of the kernels' table
+FeView FeatureExtractor::stage(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
+                               float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
+                               const float *range)
 {
-    // ---- one pinned block, one H2D
-    const size_t o_cloud = 0, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
+    static_assert(sizeof(FeView) <= 256, "FeView must fit the head of the input block");
+    const size_t o_cloud = 256, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
                  o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan_),
                  o_ground = align16(o_end + 4 * (size_t)n_scan_), total = align16(o_ground + (size_t)n + 16);
     const int rb = ring_; ring_ ^= 1;
@@ -589,8 +603,6 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
     std::memcpy(hp + o_start, start_ring, 4 * (size_t)n_scan_);
     std::memcpy(hp + o_end, end_ring, 4 * (size_t)n_scan_);
     std::memcpy(hp + o_ground, ground, (size_t)n);
-    LLB_CUDA(cudaMemcpyAsync(dp, hp, total, cudaMemcpyHostToDevice, s));
-    LLB_CUDA(cudaEventRecord(in_ev_[rb], s)); in_busy_[rb] = true;
 
     FeView v{};
     v.cloud_in = reinterpret_cast<const float4 *>(dp + o_cloud); v.cloud_adj = cloud_adj_.p;
@@ -605,17 +617,84 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
     for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_block_.p + out_off_[k]);
     v.out_hdr = reinterpret_cast<FeHeader *>(out_block_.p);
     v.prm = prm; v.seq = ++seq_;
-    n_ = n;
-    const int grid = std::max(1, std::min(div_up(n, FE_TPB), 148 * 4));
-    fe_point_kernel<<<grid, FE_TPB, 0, s>>>(v);
-    fe_mark_kernel<<<grid, FE_TPB, 0, s>>>(v);
-    fe_ring_kernel<<<n_scan_, FE_RING_THREADS, (horizon_ + 8) * 16 + (horizon_ + 32) * 8, s>>>(v);
-    launch_voxel_cta_jobs(jobs_.p, n_scan_, (horizon_ + 1023) & ~1023, s);
-    fe_concat_kernel<<<1, 1024, 0, s>>>(v);
+    std::memcpy(hp, &v, sizeof(v));
+    n_ = n; staged_ = rb; staged_bytes_ = total;
+    return v;
+}
+
+void FeatureExtractor::copy_in(cudaStream_t s)
+{
+    LLB_CUDA(cudaMemcpyAsync(in_dev_.p, pin_in_[staged_].p, staged_bytes_, cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaEventRecord(in_ev_[staged_], s)); in_busy_[staged_] = true;
+}
+
+void FeatureExtractor::copy_out(cudaStream_t s)
+{   // header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
+    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, out_block_.p, out_off_[3] + sizeof(float4) * (size_t)n_, cudaMemcpyDeviceToHost, s));
+}
+
+int FeatureExtractor::launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
+                             cudaStream_t s)
+{
+    const int gx = std::max(1, std::min(div_up(n_max, FE_TPB), std::max(8, 148 * 4 / std::max(count, 1))));
+    fe_point_kernel<<<dim3(gx, count), FE_TPB, 0, s>>>(table_dev);
+    fe_mark_kernel<<<dim3(gx, count), FE_TPB, 0, s>>>(table_dev);
+    fe_ring_kernel<<<dim3(n_scan, count), FE_RING_THREADS, (horizon + 8) * 16 + (horizon + 32) * 8, s>>>(table_dev);
+    launch_voxel_cta_jobs(jobs_dev, n_scan * count, (horizon + 1023) & ~1023, s);
+    fe_concat_kernel<<<dim3(1, count), 1024, 0, s>>>(table_dev);
     LLB_CUDA(cudaGetLastError());
-    // ---- results: header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
-    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, out_block_.p, out_off_[3] + sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, s));
     return 5;
+}
+
+int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
+                              float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
+                              const float *range, cudaStream_t s)
+{
+    stage(cloud32, n, start_ring, end_ring, start_ori, end_ori, ori_diff, ground, col, range);
+    copy_in(s);
+    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s);
+    copy_out(s);
+    return launches;
+}
+
+// ---------------------------------------------------------------- batch: one sweep per slot, the same five launches
+void FeatureBatch::init(int slots, int n_scan, int horizon, cudaStream_t s)
+{
+    release();
+    ext_.resize(slots);
+    std::vector<SmallJob> jobs;
+    for (auto &e : ext_) { e.init(n_scan, horizon, s); jobs.insert(jobs.end(), e.jobs_host().begin(), e.jobs_host().end()); }
+    jobs_.ensure(jobs.size());
+    LLB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), sizeof(SmallJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaStreamSynchronize(s));
+    table_.ensure(slots); pin_table_.ensure(slots);
+    n_scan_ = n_scan; horizon_ = horizon;
+}
+
+void FeatureBatch::release()
+{
+    for (auto &e : ext_) e.release();
+    ext_.clear(); jobs_.release(); table_.release(); pin_table_.release(); n_scan_ = 0;
+}
+
+int FeatureBatch::extract(const FeSweepHost *sweeps, cudaStream_t s)
+{
+    const int S = (int)ext_.size();
+    int n_max = 1;
+    // staging (repacking a sweep into its pinned block, ~15 us) and the copy calls of the slots are host work and set the
+    // pace of a step (2.3 ms for 64 slots; sharing the staging between threads did not pay: 3.3 ms); each slot's H2D
+    // is issued as soon as its block is ready so that the copies overlap the staging of the next slot
+    for (int i = 0; i < S; i++) {
+        const FeSweepHost &h = sweeps[i];
+        pin_table_.p[i] = ext_[i].stage(h.cloud32, h.n, h.start_ring, h.end_ring, h.start_ori, h.end_ori, h.ori_diff, h.ground,
+                                        h.col, h.range);
+        ext_[i].copy_in(s);
+        n_max = std::max(n_max, h.n);
+    }
+    LLB_CUDA(cudaMemcpyAsync(table_.p, pin_table_.p, sizeof(FeView) * S, cudaMemcpyHostToDevice, s));
+    const int launches = FeatureExtractor::launch(table_.p, S, n_max, n_scan_, horizon_, jobs_.p, s);
+    for (int i = 0; i < S; i++) ext_[i].copy_out(s);
+    return launches;
 }
 
 int FeatureExtractor::transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s)

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "voxel_dev.cuh"
+#include <vector>
 
 namespace llb {
 
@@ -22,7 +23,7 @@ constexpr int FE_SHARP_PER_RING = 12, FE_LSHARP_PER_RING = 120, FE_FLAT_PER_RING
 
 struct FeParams { float edge_threshold, surf_threshold, scan_period, leaf; };   // UT:116-117, UT:107, FA:214
 
-struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; int prof[8]; };
+struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; int prof[7]; int stale_ind; };
 
 struct FeView {
     const float4 *cloud_in; float4 *cloud_adj;
@@ -47,6 +48,15 @@ public:
     int n_scan() const { return n_scan_; }
     int horizon() const { return horizon_; }
     void release();
+    // the pieces of extract(), for the batch: fill the pinned input block (returns the sweep's table entry), send it,
+    // the five launches over a device table of sweeps, fetch the result block
+    FeView stage(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
+                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range);
+    void copy_in(cudaStream_t s);
+    void copy_out(cudaStream_t s);
+    static int launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
+                      cudaStream_t s);
+    const std::vector<SmallJob> &jobs_host() const { return jobs_host_; }
     // stages the sweep (host pointers, cloud with a 32 B stride), enqueues everything; returns kernel launches
     int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
@@ -64,7 +74,9 @@ public:
     void get_state(float *curv, int *picked, int *label, int n, cudaStream_t s);
     FeParams prm{ 0.1f, 0.1f, 0.1f, 0.2f };
 private:
-    int n_scan_ = 0, horizon_ = 0, cap_ = 0, n_ = 0, seq_ = 0;
+    int n_scan_ = 0, horizon_ = 0, cap_ = 0, n_ = 0, seq_ = 0, staged_ = 0;
+    size_t staged_bytes_ = 0;
+    std::vector<SmallJob> jobs_host_;
     PinnedBuf<unsigned char> pin_in_[2]; cudaEvent_t in_ev_[2] = { nullptr, nullptr }; bool in_busy_[2] = { false, false };
     int ring_ = 0;
     DevBuf<unsigned char> in_dev_;
@@ -76,6 +88,27 @@ private:
     DevBuf<SmallJob> jobs_;
     PinnedBuf<unsigned char> pin_out_;
     size_t out_off_[4] = { 0, 0, 0, 0 };
+};
+
+struct FeSweepHost {     // one sweep as the caller holds it (llb_segmented_cloud)
+    const float *cloud32; int n; const int *start_ring, *end_ring; float start_ori, end_ori, ori_diff;
+    const unsigned char *ground; const unsigned *col; const float *range;
+};
+
+// S independent sequences: one FeatureExtractor state per slot, ONE set of five launches per step (blockIdx.y = slot)
+class FeatureBatch {
+public:
+    void init(int slots, int n_scan, int horizon, cudaStream_t s);
+    void release();
+    bool ready() const { return n_scan_ > 0; }
+    int slots() const { return (int)ext_.size(); }
+    int extract(const FeSweepHost *sweeps, cudaStream_t s);      // returns kernel launches
+    FeatureExtractor &slot(int i) { return ext_[i]; }
+private:
+    std::vector<FeatureExtractor> ext_;
+    DevBuf<SmallJob> jobs_;
+    DevBuf<FeView> table_; PinnedBuf<FeView> pin_table_;
+    int n_scan_ = 0, horizon_ = 0;
 };
 
 }  // namespace llb

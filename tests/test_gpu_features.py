@@ -192,3 +192,29 @@ def test_features_match_committed_reference_vectors():
         assert_cloud_matches_golden(ctx.features_get(5), want["corner_last"], "corner_last", xyz_tol=2e-5)
         assert_cloud_matches_golden(ctx.features_get(6), want["surf_last"], "surf_last", xyz_tol=2e-5)
     ctx.close()
+
+
+def test_batch_features_equal_single_contexts():
+    """One sweep per slot through the batched form (one set of five launches for all slots) == each sequence through its
+    own context, over 3 steps (every slot keeps its own state); slots see different sweeps, one slot an empty one."""
+    import dataclasses as dc
+    S = 5
+    seqs = [sweeps(3, quantize=(0.02 if s % 2 else None), seed=3 + 10 * s) for s in range(S - 1)]
+    sw0 = seqs[0][0]
+    empty = dc.replace(sw0, cloud=sw0.cloud[:0], ground=sw0.ground[:0], col=sw0.col[:0], range=sw0.range[:0],
+                       start_ring=np.full(16, 4, np.int32), end_ring=np.full(16, -6, np.int32))
+    seqs.append([empty, seqs[1][1], empty])
+    b = api.Batch(0, S, 4096, 4096); b.features_init(16, 1800)
+    ctxs = [api.Context(0) for _ in range(S)]
+    for c in ctxs:
+        c.features_init(16, 1800)
+    for step in range(3):
+        counts, ms = b.features_extract(b.features_pack([seqs[s][step] for s in range(S)]))
+        for s in range(S):
+            cs, _ = ctxs[s].features_extract(seqs[s][step])
+            assert list(counts[s]) == cs, (step, s)
+            for k in range(4):
+                assert np.array_equal(b.features_get(s, k).view(np.uint32), ctxs[s].features_get(k).view(np.uint32)), (step, s, k)
+    for c in ctxs:
+        c.close()
+    b.close()
