@@ -8,6 +8,9 @@
 #include <vector>
 #include <algorithm>
 #include <stdexcept>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace llb {
 
@@ -17,7 +20,6 @@ constexpr int FE_TPB = 256;
 constexpr int FE_RING_THREADS = 192;      // 6 warps: one per sector for the sorts
 constexpr double FE_PI = 3.14159265358979323846;
 
-__device__ __forceinline__ float fe_range(const FeView &v, int i) { return (i >= 0 && i < v.n) ? __ldg(v.range + i) : 0.f; }
 __device__ __forceinline__ unsigned fe_col(const FeView &v, int i) { return (i >= 0 && i < v.n) ? __ldg(v.col + i) : 0u; }
 __device__ __forceinline__ int fe_ground(const FeView &v, int i) { return (i >= 0 && i < v.n) ? (int)__ldg(v.ground + i) : 0; }
 __device__ __forceinline__ int fe_col_diff(const FeView &v, int a, int b)
@@ -173,7 +175,7 @@ __device__ int warp_partition(stdsort::rec_t *a, int first, int last, int pivot,
 }
 
 __device__ void warp_std_sort(stdsort::rec_t *a, stdsort::rec_t *tmp, int n, unsigned short *Lbuf, unsigned short *Rbuf,
-                              unsigned char *bound, int lane, int *prof)
+                              int lane, int *prof)
 {
     if (n <= 1) return;
     const long long t0 = clock64();
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(FE_RING_THREADS) fe_ring_kernel(const FeView *
         int sp, ep; fe_sector(st, en, warp, sp, ep);
         if (sp < ep)                                                                     // FA:699: [sp, ep)
             warp_std_sort(s_rec + (sp - st), s_tmp + (sp - st), ep - sp, s_col + (sp - st), reinterpret_cast<unsigned short *>(s_curv) + (sp - st),
-                          s_pk + (sp - st), lane, v.hdr->prof);
+                          lane, v.hdr->prof);
     }
     if (owner >= 0 && owner != ring && s_late && tid == 0) {
         volatile int *flag = &v.hdr->release_seq;
@@ -522,10 +524,43 @@ __global__ void __launch_bounds__(FE_TPB) fe_to_end_kernel(FeEndJob jb)
 }
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+// pcl::PointXYZI (32 B: x y z _ intensity _ _ _) -> float4 {x, y, z, intensity}; this repacking is the host cost of a sweep
+void fe_pack_cloud(const float *cloud32, int n, float *out16)
+{
+#if defined(__SSE2__)
+    for (int i = 0; i < n; i++) {
+        const float *q = cloud32 + 8 * (size_t)i;
+        const __m128 a = _mm_loadu_ps(q), b = _mm_load_ss(q + 4);
+        const __m128 t = _mm_shuffle_ps(a, b, _MM_SHUFFLE(0, 0, 2, 2));             // z z i i
+        _mm_store_ps(out16 + 4 * (size_t)i, _mm_shuffle_ps(a, t, _MM_SHUFFLE(2, 0, 1, 0)));   // x y z i
+    }
+#else
+    for (int i = 0; i < n; i++) {
+        const float *q = cloud32 + 8 * (size_t)i;
+        out16[4 * i] = q[0]; out16[4 * i + 1] = q[1]; out16[4 * i + 2] = q[2]; out16[4 * i + 3] = q[4];
+    }
+#endif
+}
+
+size_t fe_input_bytes(int n, int n_scan)
+{   // must match the layout of FeatureExtractor::stage
+    const size_t o_cloud = 256, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
+                 o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan),
+                 o_ground = align16(o_end + 4 * (size_t)n_scan);
+    return align16(o_ground + (size_t)n + 16);
+}
 
 }  // namespace
 
-void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
+size_t FeatureExtractor::input_bytes(int n, int n_scan) { return fe_input_bytes(n, n_scan); }
+
+size_t FeatureExtractor::out_block_bytes(int n_scan, int horizon)
+{
+    return 64 + sizeof(float4) * (size_t)n_scan * (FE_SHARP_PER_RING + FE_LSHARP_PER_RING + FE_FLAT_PER_RING)
+         + sizeof(float4) * (size_t)n_scan * horizon;
+}
+
+void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s, unsigned char *out_dev_ext)
 {
     release();
     n_scan_ = n_scan; horizon_ = horizon; cap_ = n_scan * horizon;
@@ -556,8 +591,11 @@ void FeatureExtractor::init(int n_scan, int horizon, cudaStream_t s)
     out_off_[1] = out_off_[0] + sizeof(float4) * n_scan * FE_SHARP_PER_RING;
     out_off_[2] = out_off_[1] + sizeof(float4) * n_scan * FE_LSHARP_PER_RING;
     out_off_[3] = out_off_[2] + sizeof(float4) * n_scan * FE_FLAT_PER_RING;
-    pin_out_.ensure(out_off_[3] + sizeof(float4) * cap);
-    out_block_.ensure(out_off_[3] + sizeof(float4) * cap);
+    if (out_dev_ext) { out_dev_ = out_dev_ext; out_pin_ = nullptr; }
+    else {
+        pin_out_.ensure(out_off_[3] + sizeof(float4) * cap); out_block_.ensure(out_off_[3] + sizeof(float4) * cap);
+        out_dev_ = out_block_.p; out_pin_ = pin_out_.p;
+    }
     const int smem = (horizon + 8) * 16 + (horizon + 32) * 8;
     if (smem > 48 * 1024)
         LLB_CUDA(cudaFuncSetAttribute(fe_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -576,28 +614,29 @@ void FeatureExtractor::release()
 
 const float4 *FeatureExtractor::host_cloud(int which) const
 {
-    return reinterpret_cast<const float4 *>(pin_out_.p + out_off_[which]);
+    return reinterpret_cast<const float4 *>(out_pin_ + out_off_[which]);
 }
 
 // the sweep goes into one pinned block: [FeView, 256 B][cloud as float4][range][column][ring bounds][ground flags];
 // copy_in() sends it with one H2D, the view at its head is this sweep's entry of the kernels' table
 FeView FeatureExtractor::stage(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
                                float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
-                               const float *range)
+                               const float *range, unsigned char *hp_ext, unsigned char *dp_ext)
 {
     static_assert(sizeof(FeView) <= 256, "FeView must fit the head of the input block");
     const size_t o_cloud = 256, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
                  o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan_),
                  o_ground = align16(o_end + 4 * (size_t)n_scan_), total = align16(o_ground + (size_t)n + 16);
-    const int rb = ring_; ring_ ^= 1;
-    if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
-    pin_in_[rb].ensure(total); in_dev_.ensure(total);
-    unsigned char *hp = pin_in_[rb].p, *dp = in_dev_.p;
-    float *hc = reinterpret_cast<float *>(hp + o_cloud);
-    for (int i = 0; i < n; i++) {
-        const float *q = cloud32 + 8 * (size_t)i;
-        hc[4 * i] = q[0]; hc[4 * i + 1] = q[1]; hc[4 * i + 2] = q[2]; hc[4 * i + 3] = q[4];
+    int rb = 0;
+    unsigned char *hp = hp_ext, *dp = dp_ext;
+    if (!hp_ext) {
+        rb = ring_; ring_ ^= 1;
+        if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
+        pin_in_[rb].ensure(total); in_dev_.ensure(total);
+        hp = pin_in_[rb].p; dp = in_dev_.p;
     }
+    float *hc = reinterpret_cast<float *>(hp + o_cloud);
+    fe_pack_cloud(cloud32, n, hc);
     std::memcpy(hp + o_range, range, 4 * (size_t)n);
     std::memcpy(hp + o_col, col, 4 * (size_t)n);
     std::memcpy(hp + o_start, start_ring, 4 * (size_t)n_scan_);
@@ -614,8 +653,8 @@ FeView FeatureExtractor::stage(const float *cloud32, int n, const int *start_rin
     v.ori = ori_.p; v.curv = curv_.p; v.picked = picked_.p; v.label = label_.p; v.smooth = smooth_.p; v.hdr = hdr_.p;
     v.r_sharp = r_sharp_.p; v.r_lsharp = r_lsharp_.p; v.r_flat = r_flat_.p; v.r_lf_scan = r_lf_scan_.p; v.r_lf_ds = r_lf_ds_.p;
     v.r_cnt = r_cnt_.p; v.r_lf_ds_cnt = r_lf_ds_cnt_.p;
-    for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_block_.p + out_off_[k]);
-    v.out_hdr = reinterpret_cast<FeHeader *>(out_block_.p);
+    for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_dev_ + out_off_[k]);
+    v.out_hdr = reinterpret_cast<FeHeader *>(out_dev_);
     v.prm = prm; v.seq = ++seq_;
     std::memcpy(hp, &v, sizeof(v));
     n_ = n; staged_ = rb; staged_bytes_ = total;
@@ -630,7 +669,7 @@ void FeatureExtractor::copy_in(cudaStream_t s)
 
 void FeatureExtractor::copy_out(cudaStream_t s)
 {   // header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
-    LLB_CUDA(cudaMemcpyAsync(pin_out_.p, out_block_.p, out_off_[3] + sizeof(float4) * (size_t)n_, cudaMemcpyDeviceToHost, s));
+    LLB_CUDA(cudaMemcpyAsync(out_pin_, out_dev_, out_bytes_used(n_), cudaMemcpyDeviceToHost, s));
 }
 
 int FeatureExtractor::launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
@@ -661,39 +700,62 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
 void FeatureBatch::init(int slots, int n_scan, int horizon, cudaStream_t s)
 {
     release();
+    out_stride_ = (FeatureExtractor::out_block_bytes(n_scan, horizon) + 255) & ~(size_t)255;
+    out_dev_.ensure(out_stride_ * slots); pin_out_.ensure(out_stride_ * slots);
     ext_.resize(slots);
     std::vector<SmallJob> jobs;
-    for (auto &e : ext_) { e.init(n_scan, horizon, s); jobs.insert(jobs.end(), e.jobs_host().begin(), e.jobs_host().end()); }
+    for (int i = 0; i < slots; i++) {
+        ext_[i].init(n_scan, horizon, s, out_dev_.p + out_stride_ * i);
+        jobs.insert(jobs.end(), ext_[i].jobs_host().begin(), ext_[i].jobs_host().end());
+    }
     jobs_.ensure(jobs.size());
     LLB_CUDA(cudaMemcpyAsync(jobs_.p, jobs.data(), sizeof(SmallJob) * jobs.size(), cudaMemcpyHostToDevice, s));
     LLB_CUDA(cudaStreamSynchronize(s));
-    table_.ensure(slots); pin_table_.ensure(slots);
+    for (int k = 0; k < 2; k++) LLB_CUDA(cudaEventCreateWithFlags(&in_ev_[k], cudaEventDisableTiming));
     n_scan_ = n_scan; horizon_ = horizon;
 }
 
 void FeatureBatch::release()
 {
     for (auto &e : ext_) e.release();
-    ext_.clear(); jobs_.release(); table_.release(); pin_table_.release(); n_scan_ = 0;
+    ext_.clear(); jobs_.release(); in_dev_.release(); out_dev_.release(); pin_out_.release();
+    for (int k = 0; k < 2; k++) { pin_in_[k].release(); if (in_ev_[k]) cudaEventDestroy(in_ev_[k]); in_ev_[k] = nullptr; in_busy_[k] = false; }
+    n_scan_ = 0;
 }
 
 int FeatureBatch::extract(const FeSweepHost *sweeps, cudaStream_t s)
 {
     const int S = (int)ext_.size();
+    // ---- one input block: the table of the sweeps at its head, then every slot's sweep; one H2D
+    std::vector<size_t> off(S + 1);
+    off[0] = (sizeof(FeView) * (size_t)S + 255) & ~(size_t)255;
     int n_max = 1;
-    // staging (repacking a sweep into its pinned block, ~15 us) and the copy calls of the slots are host work and set the
-    // pace of a step (2.3 ms for 64 slots; sharing the staging between threads did not pay: 3.3 ms); each slot's H2D
-    // is issued as soon as its block is ready so that the copies overlap the staging of the next slot
     for (int i = 0; i < S; i++) {
-        const FeSweepHost &h = sweeps[i];
-        pin_table_.p[i] = ext_[i].stage(h.cloud32, h.n, h.start_ring, h.end_ring, h.start_ori, h.end_ori, h.ori_diff, h.ground,
-                                        h.col, h.range);
-        ext_[i].copy_in(s);
-        n_max = std::max(n_max, h.n);
+        off[i + 1] = off[i] + ((FeatureExtractor::input_bytes(sweeps[i].n, n_scan_) + 255) & ~(size_t)255);
+        n_max = std::max(n_max, sweeps[i].n);
     }
-    LLB_CUDA(cudaMemcpyAsync(table_.p, pin_table_.p, sizeof(FeView) * S, cudaMemcpyHostToDevice, s));
-    const int launches = FeatureExtractor::launch(table_.p, S, n_max, n_scan_, horizon_, jobs_.p, s);
-    for (int i = 0; i < S; i++) ext_[i].copy_out(s);
+    const int rb = ring_; ring_ ^= 1;
+    if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
+    pin_in_[rb].ensure(off[S]); in_dev_.ensure(off[S]);
+    unsigned char *hp = pin_in_[rb].p, *dp = in_dev_.p;
+    FeView *table = reinterpret_cast<FeView *>(hp);
+    size_t sent = off[0];                   // the table at the head goes last
+    for (int i = 0; i < S; i++) {           // host work: the repacking of the sweep; the copies of 8 slots at a time overlap it
+        const FeSweepHost &h = sweeps[i];
+        table[i] = ext_[i].stage(h.cloud32, h.n, h.start_ring, h.end_ring, h.start_ori, h.end_ori, h.ori_diff, h.ground, h.col,
+                                 h.range, hp + off[i], dp + off[i]);
+        if ((i & 7) == 7 || i == S - 1) {
+            LLB_CUDA(cudaMemcpyAsync(dp + sent, hp + sent, off[i + 1] - sent, cudaMemcpyHostToDevice, s));
+            sent = off[i + 1];
+        }
+    }
+    LLB_CUDA(cudaMemcpyAsync(dp, hp, off[0], cudaMemcpyHostToDevice, s));
+    LLB_CUDA(cudaEventRecord(in_ev_[rb], s)); in_busy_[rb] = true;
+    const int launches = FeatureExtractor::launch(reinterpret_cast<const FeView *>(dp), S, n_max, n_scan_, horizon_, jobs_.p, s);
+    // ---- one 2-D D2H: the used part (header, three fixed clouds, n_max less-flat points) of every slot's result block
+    const size_t used = ext_[0].out_bytes_used(n_max);
+    LLB_CUDA(cudaMemcpy2DAsync(pin_out_.p, used, out_dev_.p, out_stride_, used, S, cudaMemcpyDeviceToHost, s));
+    for (int i = 0; i < S; i++) ext_[i].set_host_out(pin_out_.p + used * i);
     return launches;
 }
 

@@ -43,7 +43,12 @@ struct FeView {
 
 class FeatureExtractor {
 public:
-    void init(int n_scan, int horizon, cudaStream_t s);
+    // out_dev_ext: result block of this sweep inside a batch's block (own allocation when null)
+    void init(int n_scan, int horizon, cudaStream_t s, unsigned char *out_dev_ext = nullptr);
+    static size_t out_block_bytes(int n_scan, int horizon);     // [FeHeader][sharp][less sharp][flat][less flat, n_scan * horizon]
+    static size_t input_bytes(int n, int n_scan);
+    size_t out_bytes_used(int n) const { return out_off_[3] + sizeof(float4) * (size_t)n; }
+    void set_host_out(unsigned char *p) { out_pin_ = p; }      // where the batch's D2H put this sweep's result block
     bool ready() const { return n_scan_ > 0; }
     int n_scan() const { return n_scan_; }
     int horizon() const { return horizon_; }
@@ -51,7 +56,8 @@ public:
     // the pieces of extract(), for the batch: fill the pinned input block (returns the sweep's table entry), send it,
     // the five launches over a device table of sweeps, fetch the result block
     FeView stage(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
-                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range);
+                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range,
+                 unsigned char *hp_ext = nullptr, unsigned char *dp_ext = nullptr);     // ext: the sweep's place in a batch block
     void copy_in(cudaStream_t s);
     void copy_out(cudaStream_t s);
     static int launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
@@ -61,12 +67,12 @@ public:
     int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
     // after the stream has been synchronised
-    const int *counts() const { return reinterpret_cast<const FeHeader *>(pin_out_.p)->counts; }
-    const int *phase_cycles() const { return reinterpret_cast<const FeHeader *>(pin_out_.p)->pad; }   // sort, picks (slowest ring), then prof[8]
+    const int *counts() const { return reinterpret_cast<const FeHeader *>(out_pin_)->counts; }
+    const int *phase_cycles() const { return reinterpret_cast<const FeHeader *>(out_pin_)->pad; }   // sort, picks (slowest ring), then prof[8]
     const float4 *host_cloud(int which) const;
     const float4 *dev_cloud(int which) const
     {
-        return which == 4 ? cloud_adj_.p : reinterpret_cast<const float4 *>(out_block_.p + out_off_[which]);
+        return which == 4 ? cloud_adj_.p : reinterpret_cast<const float4 *>(out_dev_ + out_off_[which]);
     }
     int n_points() const { return n_; }
     // TransformToEnd (FA:885-953) of cornerPointsLessSharp / surfPointsLessFlat into the given device clouds
@@ -87,6 +93,7 @@ private:
     DevBuf<FeHeader> hdr_;
     DevBuf<SmallJob> jobs_;
     PinnedBuf<unsigned char> pin_out_;
+    unsigned char *out_dev_ = nullptr, *out_pin_ = nullptr;     // own buffers or the batch's
     size_t out_off_[4] = { 0, 0, 0, 0 };
 };
 
@@ -107,7 +114,13 @@ public:
 private:
     std::vector<FeatureExtractor> ext_;
     DevBuf<SmallJob> jobs_;
-    DevBuf<FeView> table_; PinnedBuf<FeView> pin_table_;
+    // one input block per step: [table of FeView][slot 0 input][slot 1 input]..., one H2D; one result block
+    // [slots][stride], fetched with one 2-D D2H of the used part of every slot
+    PinnedBuf<unsigned char> pin_in_[2]; cudaEvent_t in_ev_[2] = { nullptr, nullptr }; bool in_busy_[2] = { false, false };
+    int ring_ = 0;
+    DevBuf<unsigned char> in_dev_, out_dev_;
+    PinnedBuf<unsigned char> pin_out_;
+    size_t out_stride_ = 0;
     int n_scan_ = 0, horizon_ = 0;
 };
 
