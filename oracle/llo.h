@@ -18,6 +18,9 @@
  *     exact-kNN is cross-checked against scipy.cKDTree and cv2.flann).
  *   - control flow / thresholds / Jacobians are pinned against the UNMODIFIED
  *     reference sources compiled against shim headers (oracle/_ref).
+ *   - feature extraction (llo_features.c) incl. its restatement of libstdc++'s
+ *     std::sort: pinned bit-for-bit against oracle/_ref and against libstdc++
+ *     itself (tests/test_oracle_features.py), golden vectors committed.
  *
  * Numerics contract: IEEE float32 with the double-promoted sub-expressions the
  * C++ reference has.  Build with -O2 -ffp-contract=off
