@@ -450,3 +450,25 @@ def make_segmented_sweep(world: World, sensor: Sensor, pose, seed: int, noise: f
                           np.concatenate(grd).astype(np.uint8), np.concatenate(cols).astype(np.uint32),
                           np.concatenate(rngs).astype(np.float32),
                           np.concatenate(outl).astype(np.float32) if outl else np.zeros((0, 4), np.float32))
+
+
+def make_raw_sweep(world: World, sensor: Sensor, pose, seed: int, noise: float = 0.02, dropout: float = 0.02,
+                   quantize: float = 0.002):
+    """One raw sweep as the driver publishes it: points in the LIDAR frame (x fwd, y left, z up) in firing order (all
+    rings of an azimuth step, then the next step, clockwise as a Velodyne spins), with the ring channel.
+    -> (cloud (n,4) float32 with intensity 0, ring (n,) uint16).  Ranges are quantised (2 mm, the sensor's resolution)."""
+    rng = np.random.default_rng(seed)
+    pose = np.asarray(pose, np.float64)
+    d, ring, col = sensor_dirs(sensor)
+    R = rot_zxy(pose[0], pose[1], pose[2])
+    r, kind, _, _ = raycast(world, pose[3:6], d @ R.T, sensor.max_range)
+    ok = np.isfinite(r) & (rng.random(r.shape[0]) > dropout)
+    r = np.where(ok, r + rng.normal(0, noise, r.shape[0]), 0.0)
+    if quantize:
+        r = np.round(r / quantize) * quantize
+    cam = d * r[:, None]
+    lid = np.stack([cam[:, 2], cam[:, 0], cam[:, 1]], 1).astype(np.float32)
+    order = np.lexsort((ring, -col))          # azimuth steps in decreasing column (clockwise), rings inside a step
+    order = order[ok[order]]
+    cloud = np.zeros((order.size, 4), np.float32); cloud[:, :3] = lid[order]
+    return cloud, ring[order].astype(np.uint16)

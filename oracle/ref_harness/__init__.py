@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _OUT = os.path.join(os.path.dirname(_HERE), "_ref")
 _MO = os.path.join(_OUT, "libref_mo.so")
 _FA = os.path.join(_OUT, "libref_fa.so")
+_IP = os.path.join(_OUT, "libref_ip.so")
 _libs = {}
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -29,7 +30,7 @@ def build() -> bool:
 
 
 def available() -> bool:
-    return os.path.exists(_MO) and os.path.exists(_FA)
+    return os.path.exists(_MO) and os.path.exists(_FA) and os.path.exists(_IP)
 
 
 def _lib(path, create):
@@ -240,6 +241,43 @@ class FeatureAssociation:
         a = np.zeros(max(n, 1), np.float32); b = a.copy(); c = a.copy()
         self.L.ref_fa_get_search_ind(self._h, which, _fp(a), _fp(b), _fp(c), n)
         return a[:n].copy(), b[:n].copy(), c[:n].copy()
+
+
+class ImageProjection:
+    """class ImageProjection of the reference (imageProjection.cpp:37): raw sweep -> segmented cloud + cloud_info +
+    outlier cloud, through its own member functions (cloudHandler IP:181-197 without publishing)."""
+
+    def __init__(self):
+        self.L = _lib(_IP, "ref_ip_create")
+        self._h = ctypes.c_void_p(self.L.ref_ip_create())
+        self.n_scan = self.L.ref_ip_n_scan(); self.horizon = self.L.ref_ip_horizon_scan()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_ip_destroy(self._h); self._h = None
+
+    def process(self, cloud, ring):
+        """cloud (n,4) in the LIDAR frame in firing order, ring (n,) -> lego_loam_b200.synth.SegmentedSweep"""
+        from lego_loam_b200 import synth
+        pts = _pts(cloud); rg = np.ascontiguousarray(ring, np.uint16)
+        assert rg.shape[0] == pts.shape[0]
+        self.L.ref_ip_process(self._h, _fp(pts), rg.ctypes.data_as(ctypes.c_void_p), pts.shape[0])
+        cap = self.n_scan * self.horizon
+        seg = np.zeros((cap, 4), np.float32); n = self.L.ref_ip_get_cloud(self._h, 0, _fp(seg), cap); seg = seg[:n].copy()
+        out = np.zeros((cap, 4), np.float32); m = self.L.ref_ip_get_cloud(self._h, 1, _fp(out), cap); out = out[:m].copy()
+        sr = np.zeros(self.n_scan, np.int32); er = np.zeros(self.n_scan, np.int32); ori = np.zeros(3, np.float32)
+        g = np.zeros(max(n, 1), np.uint8); col = np.zeros(max(n, 1), np.uint32); r = np.zeros(max(n, 1), np.float32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.L.ref_ip_get_info(self._h, vp(sr), vp(er), _fp(ori), vp(g), vp(col), _fp(r), n)
+        return synth.SegmentedSweep(seg, sr, er, float(ori[0]), float(ori[1]), float(ori[2]), g[:n], col[:n], r[:n], out)
+
+    def images(self):
+        n = self.n_scan * self.horizon
+        rm = np.zeros(n, np.float32); gm = np.zeros(n, np.int8); lm = np.zeros(n, np.int32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.L.ref_ip_get_images(self._h, _fp(rm), vp(gm), vp(lm))
+        shp = (self.n_scan, self.horizon)
+        return rm.reshape(shp), gm.reshape(shp), lm.reshape(shp)
 
 
 def std_sort(value, ind, depth_limit=-1):

@@ -119,6 +119,7 @@ namespace sensor_msgs {
 struct PointCloud2 {
     std_msgs::Header header;
     std::vector<float> xyzi;                 // shim payload: x y z intensity per point
+    std::vector<uint16_t> ring;              // ... and the "ring" channel when the sender has one
     typedef std::shared_ptr<PointCloud2> Ptr;
     typedef std::shared_ptr<const PointCloud2> ConstPtr;
 };
@@ -211,16 +212,29 @@ struct TransformBroadcaster { void sendTransform(const StampedTransform &) {} };
 
 // ============================================================ OpenCV (CV_32F small dense only)
 #define CV_32F 5
+#define CV_8S 1
+#define CV_32S 4
 namespace cv {
 struct Scalar { double v; static Scalar all(double x) { Scalar s; s.v = x; return s; } };
 enum { DECOMP_LU = 0, DECOMP_SVD = 1, DECOMP_EIG = 2, DECOMP_CHOLESKY = 3, DECOMP_QR = 4, DECOMP_NORMAL = 16 };
 struct Mat {
-    int rows = 0, cols = 0;
-    std::vector<float> d;
+    int rows = 0, cols = 0, type = CV_32F;
+    std::vector<float> d;                    // CV_32F
+    std::vector<int32_t> di;                 // CV_32S
+    std::vector<int8_t> db;                  // CV_8S (imageProjection's label / ground images)
     Mat() {}
-    Mat(int r, int c, int /*type*/, const Scalar &s = Scalar::all(0)) : rows(r), cols(c), d((size_t)r * c, (float)s.v) {}
-    template <typename T> T &at(int i, int j) { return d[(size_t)i * cols + j]; }
-    template <typename T> const T &at(int i, int j) const { return d[(size_t)i * cols + j]; }
+    Mat(int r, int c, int t, const Scalar &s = Scalar::all(0)) : rows(r), cols(c), type(t)
+    {
+        if (t == CV_32S) di.assign((size_t)r * c, (int32_t)s.v);
+        else if (t == CV_8S) db.assign((size_t)r * c, (int8_t)s.v);
+        else d.assign((size_t)r * c, (float)s.v);
+    }
+    float &el(float *, size_t k) { return d[k]; }
+    int32_t &el(int32_t *, size_t k) { return di[k]; }
+    int8_t &el(int8_t *, size_t k) { return db[k]; }
+    const float &el(float *, size_t k) const { return d[k]; }
+    template <typename T> T &at(int i, int j) { return el((T *)nullptr, (size_t)i * cols + j); }
+    template <typename T> const T &at(int i, int j) const { return el((T *)nullptr, (size_t)i * cols + j); }
     void copyTo(Mat &o) const { o = *this; }
     Mat inv(int = DECOMP_LU) const
     {
@@ -309,6 +323,8 @@ inline void copyPointCloud(const PointCloud<A> &in, PointCloud<B> &out)
     }
 }
 
+template <typename T> inline auto shim_set_ring(T &p, uint16_t r, int) -> decltype(p.ring, void()) { p.ring = r; }
+template <typename T> inline void shim_set_ring(T &, uint16_t, long) {}
 template <typename T>
 inline void fromROSMsg(const sensor_msgs::PointCloud2 &msg, PointCloud<T> &cloud)
 {
@@ -317,9 +333,25 @@ inline void fromROSMsg(const sensor_msgs::PointCloud2 &msg, PointCloud<T> &cloud
     for (size_t i = 0; i < n; i++) {
         T p;
         p.x = msg.xyzi[4 * i]; p.y = msg.xyzi[4 * i + 1]; p.z = msg.xyzi[4 * i + 2]; p.intensity = msg.xyzi[4 * i + 3];
+        shim_set_ring(p, i < msg.ring.size() ? msg.ring[i] : (uint16_t)0, 0);
         cloud.points[i] = p;
     }
     cloud.width = (uint32_t)n; cloud.height = 1; cloud.is_dense = true;
+}
+// pcl::removeNaNFromPointCloud (pcl/filters/filter.h): keeps the points whose x, y, z are all finite, in order
+template <typename T>
+inline void removeNaNFromPointCloud(const PointCloud<T> &in, PointCloud<T> &out, std::vector<int> &index)
+{
+    std::vector<T> kept; kept.reserve(in.points.size());
+    index.clear();
+    for (size_t i = 0; i < in.points.size(); i++) {
+        const T &p = in.points[i];
+        if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+        kept.push_back(p); index.push_back((int)i);
+    }
+    out.header = in.header;
+    out.points.swap(kept);
+    out.width = (uint32_t)out.points.size(); out.height = 1; out.is_dense = true;
 }
 template <typename T>
 inline void toROSMsg(const PointCloud<T> &cloud, sensor_msgs::PointCloud2 &msg)

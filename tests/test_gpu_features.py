@@ -218,3 +218,20 @@ def test_batch_features_equal_single_contexts():
     for c in ctxs:
         c.close()
     b.close()
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+def test_features_on_reference_image_projection_output():
+    """Raw sweeps -> the reference's own imageProjection (oracle/_ref) -> feature extraction on the device vs the
+    reference's featureAssociation: the node's real data path in front of the device kernels."""
+    from tests.test_oracle_features import reference_front_end_sweeps
+    ctx = api.Context(0); ctx.features_init(16, 1800)
+    fa = rh.FeatureAssociation()
+    for sw in reference_front_end_sweeps(3):
+        counts, _ = ctx.features_extract(sw)
+        fa.set_segmented(sw); fa.extract_features()
+        for k in range(5):
+            check_cloud(ctx.features_get(k), fa.feature_cloud(k), f"cloud {k}")
+        for a, b in zip(ctx.features_get_state(sw.cloud.shape[0]), fa.point_state()):
+            assert np.array_equal(a, b)
+    ctx.close()

@@ -110,3 +110,31 @@ def test_feature_extraction_restatement_matches_committed_reference_vectors():
         assert np.array_equal(label, want["label"].astype(np.int32)) and np.array_equal(picked, want["picked"].astype(np.int32))
         assert_cloud_matches_golden(oracle.transform_to_end(T, got[1]), want["corner_last"], "corner_last", xyz_tol=2e-5)
         assert_cloud_matches_golden(oracle.transform_to_end(T, got[3]), want["surf_last"], "surf_last", xyz_tol=2e-5)
+
+
+def reference_front_end_sweeps(n, seed=40):
+    """Raw sweeps (firing order, ring channel) through the UNMODIFIED reference imageProjection.cpp (oracle/_ref/libref_ip.so):
+    the segmented clouds and cloud_info messages featureAssociation receives in the node."""
+    w = synth.make_world()
+    ip = rh.ImageProjection()
+    out = []
+    for k in range(n):
+        cloud, ring = synth.make_raw_sweep(w, synth.VLP16, [0.002 * k, 0.05 + 0.01 * k, 0, 3 + 0.4 * k, 0, 5 + 0.1 * k], seed + k)
+        out.append(ip.process(cloud, ring))
+    return out
+
+
+@needs_ref
+def test_feature_extraction_on_reference_image_projection_output():
+    """imageProjection (reference) -> feature extraction: restatement == reference, sweep after sweep through one object;
+    the segmented clouds have the node's structure (ground rings thinned to every 5th column, small clusters removed)."""
+    fa = rh.FeatureAssociation(); fe = oracle.FeatureExtraction(16, 1800)
+    for sw in reference_front_end_sweeps(3):
+        assert 5000 < sw.cloud.shape[0] < 16 * 1800 and sw.ground.sum() > 1000 and sw.outlier.shape[0] > 0
+        assert abs(sw.ori_diff - 2 * np.pi) < 0.05
+        fa.set_segmented(sw); fa.extract_features()
+        got = fe.extract(sw)
+        for k in range(5):
+            ref = fa.feature_cloud(k)
+            assert ref.shape == got[k].shape and np.array_equal(ref.view(np.uint32), got[k].view(np.uint32)), k
+        assert got[0].shape[0] > 50 and got[2].shape[0] > 50
