@@ -331,3 +331,41 @@ def transform_to_end(T, cloud):
     t = np.ascontiguousarray(T, np.float32); c = _pts(cloud).copy()
     lib().llo_transform_to_end(_fp(t), _fp(c), c.shape[0])
     return c
+
+
+# ------------------------------------------------------------------ imageProjection
+
+class ImageProjection:
+    """Restatement of the reference's imageProjection node (IP:181-368): raw sweep -> segmented cloud + cloud_info."""
+
+    def __init__(self, n_scan=16, horizon=1800, ang_res_x=0.2, ang_res_y=2.0, ground_scan_ind=7):
+        L = lib()
+        L.llo_projection_create.restype = ctypes.c_void_p
+        self.n_scan, self.horizon = n_scan, horizon
+        self._h = ctypes.c_void_p(L.llo_projection_create(n_scan, horizon, ctypes.c_float(ang_res_x), ctypes.c_float(ang_res_y),
+                                                          ground_scan_ind))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().llo_projection_destroy(self._h); self._h = None
+
+    def process(self, cloud, ring):
+        from lego_loam_b200 import synth
+        pts = _pts(cloud); rg = np.ascontiguousarray(ring, np.uint16)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        lib().llo_projection_process(self._h, _fp(pts), vp(rg), pts.shape[0])
+        cap = self.n_scan * self.horizon
+        seg = np.zeros((cap, 4), np.float32); n = lib().llo_projection_get_cloud(self._h, 0, _fp(seg), cap); seg = seg[:n].copy()
+        out = np.zeros((cap, 4), np.float32); m = lib().llo_projection_get_cloud(self._h, 1, _fp(out), cap); out = out[:m].copy()
+        sr = np.zeros(self.n_scan, np.int32); er = np.zeros(self.n_scan, np.int32); ori = np.zeros(3, np.float32)
+        g = np.zeros(max(n, 1), np.uint8); col = np.zeros(max(n, 1), np.uint32); r = np.zeros(max(n, 1), np.float32)
+        lib().llo_projection_get_info(self._h, vp(sr), vp(er), _fp(ori), vp(g), vp(col), _fp(r), n)
+        return synth.SegmentedSweep(seg, sr, er, float(ori[0]), float(ori[1]), float(ori[2]), g[:n], col[:n], r[:n], out)
+
+    def images(self):
+        n = self.n_scan * self.horizon
+        rm = np.zeros(n, np.float32); gm = np.zeros(n, np.int8); lm = np.zeros(n, np.int32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        lib().llo_projection_get_images(self._h, _fp(rm), vp(gm), vp(lm))
+        shp = (self.n_scan, self.horizon)
+        return rm.reshape(shp), gm.reshape(shp), lm.reshape(shp)

@@ -156,6 +156,18 @@ int  llo_featassoc_get_correspondences(const llo_featassoc *f, llo_point *ori, l
 int  llo_featassoc_get_search_ind(const llo_featassoc *f, int which /*0 corner,1 surf*/,
                                   float *ind1, float *ind2, float *ind3, int cap);
 
+/* ---------------- imageProjection (llo_projection.c) ---------------- */
+typedef struct llo_projection llo_projection;
+llo_projection *llo_projection_create(int n_scan, int horizon, float ang_res_x, float ang_res_y, int ground_scan_ind);
+void llo_projection_destroy(llo_projection *p);
+/* cloudHandler IP:181-197 without publishing: raw sweep (lidar frame, firing order, ring channel) -> range / ground / label
+ * images, segmented cloud + cloud_info, outlier cloud */
+void llo_projection_process(llo_projection *p, const llo_point *cloud, const uint16_t *ring, int n);
+int llo_projection_get_cloud(const llo_projection *p, int which /* 0 segmented, 1 outlier */, llo_point *out, int cap);
+void llo_projection_get_info(const llo_projection *p, int *start_ring, int *end_ring, float ori[3], uint8_t *ground,
+                             uint32_t *col, float *range, int n);
+void llo_projection_get_images(const llo_projection *p, float *range_mat, int8_t *ground_mat, int32_t *label_mat);
+
 /* ---------------- feature extraction (llo_features.c) ---------------- */
 typedef struct llo_features llo_features;
 llo_features *llo_features_create(int n_scan, int horizon);
