@@ -190,7 +190,7 @@ int llb_features_init(llb_ctx *ctx, int n_scan, int horizon_scan);
 /* adjustDistortion (no IMU data: imuPointerLast < 0, FA:525), calculateSmoothness, markOccludedPoints, extractFeatures
  * = runFeatureAssociation FA:1827-1833.  counts = sizes of cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat,
  * surfPointsLessFlat.  Selection, order and coordinates are bit-identical to the reference (std::sort's order of equal
- * curvatures included); the time part of the intensity goes through atan2, taken correctly rounded here. */
+ * curvatures included), and so are the intensities: the kernel restates glibc's atan2f operation by operation. */
 int llb_features_extract(llb_ctx *ctx, const llb_segmented_cloud *seg, int counts[4], float *device_ms);
 /* which: 0 cornerPointsSharp, 1 cornerPointsLessSharp, 2 surfPointsFlat, 3 surfPointsLessFlat, 4 segmentedCloud after
  * adjustDistortion, 5 / 6 laserCloudCornerLast / laserCloudSurfLast after llb_features_publish_last */

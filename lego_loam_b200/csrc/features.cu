@@ -2,6 +2,7 @@
 // reference's C++ promotion rules (float members compared against double M_PI expressions, FA:506-519).
 #include "features.cuh"
 #include "std_sort.cuh"
+#include "glibc_atan2f.cuh"
 #include <climits>
 #include <cstring>
 #include <cstddef>
@@ -45,8 +46,8 @@ __global__ void __launch_bounds__(FE_TPB) fe_point_kernel(const FeView *__restri
     if (blockIdx.x == 0 && threadIdx.x == 0) v.hdr->stale_ind = (int)(unsigned)v.smooth[4];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
         const float4 q = __ldg(v.cloud_in + i);
-        // point.x = y, point.z = x; ori = -atan2(point.x, point.z) (float overload), FA:500-504
-        const float ori = -(float)atan2((double)q.y, (double)q.x);
+        // point.x = y, point.z = x; ori = -atan2(point.x, point.z) (float overload = glibc's atan2f, restated), FA:500-504
+        const float ori = -glibcm::atan2f_(q.y, q.x);
         v.ori[i] = ori;
         const float a = fe_ori_first_half(ori, v.start_ori);
         if ((double)(a - v.start_ori) > FE_PI) atomicMin(&v.hdr->first_half, i);      // FA:511-512

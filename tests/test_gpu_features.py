@@ -3,8 +3,9 @@ extractFeatures, FA:491-784) through the C ABI against the oracle restatement an
 snapshot, against the UNMODIFIED reference featureAssociation.cpp.
 
 Bar: which points are picked, their order, labels, flags, curvatures and coordinates bit-identical (std::sort's order
-of equal curvatures included); the relative-time part of the intensity goes through atan2 (glibc's atan2f in the
-reference, a correctly rounded value on the device): within 2 ulp of the intensity value."""
+of equal curvatures included); the relative-time part of the intensity goes through glibc's atan2f, which the kernel
+restates operation by operation: observed bit-identical, asserted within 2 ulp of the intensity value so that a host
+with another libm does not fail the suite."""
 import dataclasses
 
 import numpy as np
@@ -65,6 +66,12 @@ def test_features_match_oracle_and_reference(quantize):
         assert counts[0] > 50 and counts[2] > 50 and counts[3] > 2000
         print(f"n={n} counts={counts} device_ms={ms:.3f}")
     print(f"intensity words differing from glibc atan2f path: {ulp_diffs} of {total}")
+    # the kernel restates glibc's atan2f operation by operation (csrc/glibc_atan2f.cuh): on a host with that libm the
+    # intensities are bit-identical too (the 2-ulp bar above stays for hosts whose libm computes atan2f differently)
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/features_intensity_diff_{quantize}.json", "w") as f:
+        json.dump({"differing_words": ulp_diffs, "of": total}, f)
     ctx.close()
 
 
