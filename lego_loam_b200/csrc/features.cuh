@@ -9,8 +9,11 @@
 //                    then the ordered gather of the ring's less-flat points
 //   voxel_cta_kernel one CTA per ring: VoxelGrid(0.2) of surfPointsLessFlatScan (FA:778-782), K1 as it is
 //   fe_concat_kernel ring-major concatenation into the four output clouds
-// -> 1 D2H (counts + four clouds).  Per-point work is HBM-trivial (30k points); the step is bound by the dependent
-// chain of one sector sort (~300 records, one thread) + ~24 sequential picks per sector.
+// -> 1 D2H (counts + four clouds).  Every kernel reads its sweep from a device table (blockIdx.y = sweep): a single
+// context has one entry, FeatureBatch one per slot - the same five launches serve 64 sequences.  Per-point work is
+// HBM-trivial (30k points); the step is bound by the dependent chains of a ring's CTA: ~22 warp-wide partitions per
+// sector sort (std_sort.cuh, closed-form Hoare partition) and the <= 24 picks per sector, each of which can block the
+// candidates next to it.  transform_to_end(): TransformToEnd (FA:885-953) of the less-sharp / less-flat clouds.
 #pragma once
 #include "common.cuh"
 #include "voxel_dev.cuh"
