@@ -3,6 +3,7 @@
 #include "features.cuh"
 #include "std_sort.cuh"
 #include "glibc_atan2f.cuh"
+#include "glibc_sincosf.cuh"
 #include <climits>
 #include <cstring>
 #include <cstddef>
@@ -459,8 +460,9 @@ __global__ void __launch_bounds__(1024) fe_concat_kernel(const FeView *__restric
 
 struct FeEndJob { const float4 *in[2]; float4 *out[2]; int n[2]; float T[6]; };
 
-__device__ __forceinline__ float fe_cosf(float x) { return (float)cos((double)x); }   // correctly rounded, as K5 takes them
-__device__ __forceinline__ float fe_sinf(float x) { return (float)sin((double)x); }
+// glibc's sinf / cosf restated (glibc_sincosf.cuh): the transformed clouds come out as the reference's own, bit for bit
+__device__ __forceinline__ float fe_cosf(float x) { return glibcm::cosf_(x); }
+__device__ __forceinline__ float fe_sinf(float x) { return glibcm::sinf_(x); }
 
 // TransformToEnd FA:885-953 with the IMU terms of a node that never received an IMU message (angles and shifts 0; the
 // factors stay in the expressions so that signed zeros come out as in the reference)
