@@ -153,11 +153,21 @@ class MapOptimization:
         return out[:n].copy()
 
 
+def _sensor_lib(base, sensor):
+    """libref_<node>.so is the reference as shipped (VLP-16, UT:62-68); libref_<node>_<sensor>.so the same sources with
+    the sensor block of utility.h switched the way the reference's README prescribes (Makefile: select_sensor.awk)."""
+    return base if sensor in (None, "vlp16") else base[:-3] + "_" + sensor + ".so"
+
+
+def sensor_available(sensor) -> bool:
+    return os.path.exists(_sensor_lib(_FA, sensor)) and os.path.exists(_sensor_lib(_IP, sensor))
+
+
 class FeatureAssociation:
     """class FeatureAssociation of the reference (FA:37)."""
 
-    def __init__(self):
-        self.L = _lib(_FA, "ref_fa_create")
+    def __init__(self, sensor=None):
+        self.L = _lib(_sensor_lib(_FA, sensor), "ref_fa_create")
         self._h = ctypes.c_void_p(self.L.ref_fa_create())
 
     def __del__(self):
@@ -247,8 +257,8 @@ class ImageProjection:
     """class ImageProjection of the reference (imageProjection.cpp:37): raw sweep -> segmented cloud + cloud_info +
     outlier cloud, through its own member functions (cloudHandler IP:181-197 without publishing)."""
 
-    def __init__(self):
-        self.L = _lib(_IP, "ref_ip_create")
+    def __init__(self, sensor=None):
+        self.L = _lib(_sensor_lib(_IP, sensor), "ref_ip_create")
         self._h = ctypes.c_void_p(self.L.ref_ip_create())
         self.n_scan = self.L.ref_ip_n_scan(); self.horizon = self.L.ref_ip_horizon_scan()
 

@@ -138,3 +138,34 @@ def test_feature_extraction_on_reference_image_projection_output():
             ref = fa.feature_cloud(k)
             assert ref.shape == got[k].shape and np.array_equal(ref.view(np.uint32), got[k].view(np.uint32)), k
         assert got[0].shape[0] > 50 and got[2].shape[0] > 50
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["hdl32e", "vls128"])
+def test_other_sensors_front_end_and_features_match_reference(name):
+    """The reference built for HDL-32E / VLS-128 (its utility.h sensor block switched by the harness recipe): raw sweep ->
+    imageProjection -> feature extraction, restatements == reference for both steps, two sweeps through the same objects."""
+    if not rh.sensor_available(name):
+        pytest.skip("oracle/_ref has no build for this sensor")
+    sensor = synth.SENSORS[name]
+    ang_res_x = 360.0 / sensor.horizon if name == "hdl32e" else 0.2            # UT:73, UT:81
+    ang_res_y = 41.33 / (sensor.n_scan - 1) if name == "hdl32e" else 0.3       # UT:74, UT:82
+    w = synth.make_world()
+    rip = rh.ImageProjection(name); oip = oracle.ImageProjection(sensor.n_scan, sensor.horizon, ang_res_x, ang_res_y,
+                                                                 sensor.ground_scan_ind)
+    rfa = rh.FeatureAssociation(name); ofe = oracle.FeatureExtraction(sensor.n_scan, sensor.horizon)
+    assert rip.n_scan == sensor.n_scan and rfa.n_scan() == sensor.n_scan
+    for k in range(2):
+        cloud, ring = synth.make_raw_sweep(w, sensor, [0, 0.05 + 0.02 * k, 0, 3 + 0.5 * k, 0, 5], 70 + k)
+        a = rip.process(cloud, ring); b = oip.process(cloud, ring)
+        for x, y in zip(rip.images(), oip.images()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a.cloud.view(np.uint32), b.cloud.view(np.uint32)) and np.array_equal(a.col, b.col)
+        assert np.array_equal(a.start_ring, b.start_ring) and np.array_equal(a.end_ring, b.end_ring)
+        assert np.array_equal(a.ground, b.ground) and np.array_equal(a.range.view(np.uint32), b.range.view(np.uint32))
+        rfa.set_segmented(a); rfa.extract_features()
+        got = ofe.extract(a)
+        for which in range(5):
+            ref = rfa.feature_cloud(which, cap=sensor.n_scan * sensor.horizon)
+            assert ref.shape == got[which].shape and np.array_equal(ref.view(np.uint32), got[which].view(np.uint32)), which
+        assert got[0].shape[0] > sensor.n_scan and got[3].shape[0] > 1000
