@@ -519,8 +519,7 @@ batch_fit_kernel(const BatchReg *__restrict__ regs, int iter, S2mParams prm)
         if (lane == 0) { stw->ticket = 0; lm_solve(stw, s_tot, iter, prm, false); }
         __syncwarp();
         if (lane < 6) {                                      // sin/cos of the new pose, one per lane
-            const double a = (double)stw->T[lane >> 1];
-            stw->cs[lane] = (lane & 1) ? (float)sin(a) : (float)cos(a);
+            stw->cs[lane] = pose_trig(stw->T, lane);
         }
     }
 }

@@ -7,6 +7,7 @@
 // semantics, and lane k accumulates the k-th product of the 3x3 normal equations in fp64.
 #include "odom.cuh"
 #include "linalg.cuh"
+#include "glibc_sincosf.cuh"
 #include "grid_index.cuh"
 #include <cmath>
 #include <cooperative_groups.h>
@@ -35,15 +36,15 @@ __device__ __forceinline__ float sqdist_ref(const float4 &a, float x, float y, f
     return (a.x - x) * (a.x - x) + (a.y - y) * (a.y - y) + (a.z - z) * (a.z - z);
 }
 
-// TransformToStart FA:860-883; the six sin/cos are correctly-rounded floats
+// TransformToStart FA:860-883; sin / cos of the float angles are glibc's sinf / cosf (glibc_sincosf.cuh), as in the reference build
 __device__ __forceinline__ void transform_to_start(const float *T, const float4 &pi, float &ox, float &oy, float &oz)
 {
     const float s = 10 * (pi.w - (int)pi.w);
     const float rx = s * T[0], ry = s * T[1], rz = s * T[2];
     const float tx = s * T[3], ty = s * T[4], tz = s * T[5];
-    const float crz = (float)cos((double)rz), srz = (float)sin((double)rz);
-    const float crx = (float)cos((double)rx), srx = (float)sin((double)rx);
-    const float cry = (float)cos((double)ry), sry = (float)sin((double)ry);
+    const float crz = glibcm::cosf_(rz), srz = glibcm::sinf_(rz);
+    const float crx = glibcm::cosf_(rx), srx = glibcm::sinf_(rx);
+    const float cry = glibcm::cosf_(ry), sry = glibcm::sinf_(ry);
 
     const float x1 = crz * (pi.x - tx) + srz * (pi.y - ty);
     const float y1 = -srz * (pi.x - tx) + crz * (pi.y - ty);
@@ -299,9 +300,9 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
             __syncthreads();
             if (tid == 0) { s_trig.tx = s_T[3]; s_trig.ty = s_T[4]; s_trig.tz = s_T[5]; }
             __syncthreads();
-            if (tid < 6) {                                                   // six threads, one fp64 libm call each
-                const double a = (double)s_T[tid >> 1];
-                const float v = (tid & 1) ? (float)cos(a) : (float)sin(a);
+            if (tid < 6) {                                                   // six threads, one sinf / cosf each
+                const float a = s_T[tid >> 1];
+                const float v = (tid & 1) ? glibcm::cosf_(a) : glibcm::sinf_(a);
                 if (tid == 0) s_trig.srx = v; if (tid == 1) s_trig.crx = v;
                 if (tid == 2) s_trig.sry = v; if (tid == 3) s_trig.cry = v;
                 if (tid == 4) s_trig.srz = v; if (tid == 5) s_trig.crz = v;

@@ -291,10 +291,9 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             if (prof) st->prof[iter % 10][5] = clock64();
             if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm, false);
             __syncthreads();
-            // the six sin/cos of the new pose, one per thread (fp64 libm calls are the long pole of the step)
+            // the six sin/cos of the new pose, one per thread (glibc's sinf / cosf restated)
             if (tid < 6 && do_solve) {
-                const double a = (double)st->T[tid >> 1];
-                st->cs[tid] = (tid & 1) ? (float)sin(a) : (float)cos(a);
+                st->cs[tid] = pose_trig(st->T, tid);
             }
             if (prof) st->prof[iter % 10][6] = clock64();
         }

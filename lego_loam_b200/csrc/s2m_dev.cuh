@@ -5,6 +5,7 @@
 #pragma once
 #include "s2m.cuh"
 #include "linalg.cuh"
+#include "glibc_sincosf.cuh"
 
 namespace llb {
 // cornerOptimization body for one query (MO:1102-1170).  Returns true when the row is accepted.
@@ -77,11 +78,18 @@ __device__ __forceinline__ bool surf_fit(const float (&nx)[5], const float (&ny)
     return (double)s > 0.1;
 }
 
+// sin / cos of a float pose angle as the reference build gets them (MO:498-506, MO:1241-1246: sin(float) is glibc's
+// sinf, which is NOT always the correctly rounded value): glibc's operation sequence restated (glibc_sincosf.cuh), so the
+// poses are the reference's bit for bit.
+__device__ __forceinline__ float ref_sinf(float x) { return glibcm::sinf_(x); }
+__device__ __forceinline__ float ref_cosf(float x) { return glibcm::cosf_(x); }
+// entry k of S2mState::cs (cRoll sRoll cPitch sPitch cYaw sYaw) for the pose T
+__device__ __forceinline__ float pose_trig(const float *T, int k) { return (k & 1) ? ref_sinf(T[k >> 1]) : ref_cosf(T[k >> 1]); }
+
 __device__ inline void update_sincos(S2mState *st)
 {
-    st->cs[0] = (float)cos((double)st->T[0]); st->cs[1] = (float)sin((double)st->T[0]);
-    st->cs[2] = (float)cos((double)st->T[1]); st->cs[3] = (float)sin((double)st->T[1]);
-    st->cs[4] = (float)cos((double)st->T[2]); st->cs[5] = (float)sin((double)st->T[2]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) st->cs[k] = pose_trig(st->T, k);
 }
 
 // LMOptimization tail MO:1273-1326 on the 28 reduced sums (one thread)

@@ -50,7 +50,7 @@ def test_adapter_matches_oracle(tmp_path):
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
     mo_line = out[0].split(); fa_line = out[1].split()
 
-    oracle.set_trig_mode(1)
+    oracle.set_trig_mode(0)
     mo = oracle.MapOptimization()
     mo.set_map_raw(case["map_corner_raw"], case["map_surf_raw"])
     mo.set_scan(case["corner"], case["surf"], case["outlier"])

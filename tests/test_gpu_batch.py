@@ -46,7 +46,7 @@ def test_batch_matches_oracle_and_single(ctx, cases):
         b.map_set_ds(s, c["mc_ds"], c["ms_ds"])
     T, st = b.register(np.stack([c["init"] for c in cases]))
     for s, c in enumerate(cases):
-        Tr, iters, ds = _oracle_registration(c, c["mc_ds"], c["ms_ds"], 1)        # correctly rounded sin/cos
+        Tr, iters, ds = _oracle_registration(c, c["mc_ds"], c["ms_ds"], 0)        # the reference's arithmetic (libm sinf / cosf)
         for which in range(4):
             got = b.scan_get_ds(s, which)
             assert got.shape == ds[which].shape
@@ -54,8 +54,7 @@ def test_batch_matches_oracle_and_single(ctx, cases):
         assert st[s].iterations == iters, (s, st[s].as_dict(), iters)
         assert st[s].skipped == 0 and st[s].n_corner_ds == ds[0].shape[0] and st[s].n_surf_ds == ds[3].shape[0]
         assert np.array_equal(T[s].view(np.uint32), Tr.astype(np.float32).view(np.uint32)), (s, T[s], Tr)
-        Tl, _, _ = _oracle_registration(c, c["mc_ds"], c["ms_ds"], 0)             # host libm sinf/cosf
-        assert np.max(np.abs(T[s] - Tl)) < POSE_TOL
+        assert np.max(np.abs(T[s] - Tr)) < POSE_TOL                                # north-star bar (implied by the line above)
         # the single-registration path on the same inputs
         ctx.map_set_ds(c["mc_ds"], c["ms_ds"]); ctx.scan_set(c["corner"], c["surf"], c["outlier"])
         ctx.downsample_current_scan()
@@ -254,7 +253,7 @@ def test_batch_odometry_matches_single_and_oracle(ctx):
             assert np.array_equal(T[s].view(np.uint32), Ts.view(np.uint32)), (rep, s, T[s], Ts)
             assert (s0[s].iterations, s1[s].iterations) == (t0.iterations, t1.iterations)
             if rep == 0:
-                oracle.set_trig_mode(1)
+                oracle.set_trig_mode(0)
                 fa = oracle.FeatureAssociation()
                 fa.set_last(od.corner_last, od.surf_last, force=True); fa.set_features(od.corner_sharp, od.surf_flat)
                 fa.transformCur = np.zeros(6, np.float32)
