@@ -32,11 +32,19 @@ struct BatchReg {                    // device-resident record of one slot, read
     const int *nc_dev, *ns_dev;
     MapIndexView cmap, smap;
     S2mState *st;
-    int *nn;                         // [5][cap] positions of the 5 neighbours in the map's sorted array
     int *qperm;                      // [cap] cell-ordered query permutation (corner part, then surf part)
-    float *d5;                       // [cap] 5th squared distance, -1 when fewer than 5 candidates inside the gate
-    double *partials;                // [fit blocks][S2M_ACC]
-    int cap;                         // query slots of nn / d5
+    double *partials;                // [chunks of 32 queries][S2M_ACC]
+    float4 *qprev;                   // [cap] per query: its map-frame position and 5th squared distance (-1: none) of the
+                                     // previous LM iteration (seeds the bound of the next search)
+    int cap;                         // query capacity of qperm / qprev
+};
+
+struct BatchSlotInfo { int nc, ns, done, n_chunks; };   // done: skipped by the guard MO:1331 (or no iterations asked for)
+struct BatchQueue {                  // device-resident work hand-out of the registration kernel of one step
+    int live;                        // slots that still have iterations to run
+    unsigned *ctl;                   // [B] per slot: (LM iteration << 16) | next chunk to hand out; 0xffffffff = done
+    BatchSlotInfo *slot;             // [B] what a warp needs to know about a slot, one 16-byte load
+    long long *prof;                 // debug (LLB_ITER_PROF): per-warp cycles by phase, [warps][12]; nullptr = off
 };
 
 struct BatchUnpack {                 // one host cloud to compact: raw PCL points -> float4
@@ -53,18 +61,18 @@ struct BatchCopy {                   // float4 cloud copy (DS clouds of a sweep 
     const float4 *src; float4 *dst; int n;
 };
 
-constexpr int BATCH_FIT_THREADS = 256;
-constexpr int BATCH_KNN_THREADS = 256;
+constexpr int BATCH_ITER_THREADS = 128;     // 4 autonomous warps; shared memory (candidate staging) sets the CTAs per SM
+constexpr int BATCH_ITER_CTAS_PER_SM = 4;
 
 // kernels (batch.cu)
 void launch_batch_copy(const BatchCopy *jobs_dev, int count, int n_max, cudaStream_t s);
 void launch_batch_unpack(const BatchUnpack *jobs_dev, int count, int n_max, cudaStream_t s);
-void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, cudaStream_t s);
-int batch_knn_variant();   // 3 (default): cost-ordered queries + flattened walk; 1: row-by-row walk in scan order; 2: two-phase list
+void launch_batch_prepare(const BatchReg *regs, const float *poses_dev, int B, const S2mParams &prm, int max_iter, BatchQueue *queue,
+                          cudaStream_t s);
 void launch_batch_qsort(const BatchReg *regs, int B, int cap, cudaStream_t s);
-void launch_batch_knn(const BatchReg *regs, int B, int ctas_per_slot, const S2mParams &prm, cudaStream_t s);
-void launch_batch_fit(const BatchReg *regs, int B, int fit_blocks, int iter, const S2mParams &prm, cudaStream_t s);
-void launch_batch_collect(const BatchReg *regs, int B, BatchResult *out, cudaStream_t s);
+int batch_lm_grid();       // CTAs of the persistent registration kernel (all co-resident)
+void launch_batch_lm(const BatchReg *regs, int B, int grid, const S2mParams &prm, int max_iter, BatchQueue *queue, cudaStream_t s);
+void launch_batch_collect(const BatchReg *regs, int B, BatchResult *out, BatchQueue *queue, cudaStream_t s);
 void launch_batch_state_init(S2mState *st, int B, cudaStream_t s);
 
 }  // namespace llb

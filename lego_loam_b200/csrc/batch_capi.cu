@@ -54,7 +54,7 @@ struct llb_batch {
     FeatureBatch features;               // feature extraction of the slots
     bool features_done = false;
     int vox_cap1 = 1024, vox_cap2 = 1024;
-    int B = 0, cap_scan = 0, cap_map = 0, qcap = 0, fit_blocks = 0, knn_ctas = 0, grid_ctas = 0;
+    int B = 0, cap_scan = 0, cap_map = 0, qcap = 0, grid_ctas = 0;
     StepLayout lay{ 1 };
 
     // per-slot device buffers, sliced out of big allocations
@@ -66,7 +66,10 @@ struct llb_batch {
     DevBuf<int> ds_n;            // [B][4]
     std::vector<GridIndex> grids;   // 2B
     DevBuf<S2mState> states;
-    DevBuf<int> nn; DevBuf<int> qperm; DevBuf<float> d5; DevBuf<double> partials;
+    DevBuf<int> qperm; DevBuf<double> partials; DevBuf<float4> qprev; DevBuf<BatchQueue> queue; DevBuf<unsigned> ctl;
+    int lm_grid = 0, part_stride = 0;
+    DevBuf<long long> iter_prof;         // debug: LLB_ITER_PROF
+    DevBuf<BatchSlotInfo> slot_info;
     DevBuf<BatchResult> results;
     PinnedBuf<BatchResult> pin_results;
     DevBuf<unsigned char> step_dev;
@@ -291,9 +294,9 @@ int enqueue_step(llb_batch *c, const float *T)
         r.corner = ds_out[0]; r.surf = ds_out[3]; r.nc_dev = dsn + 0; r.ns_dev = dsn + 3;
         r.cmap = c->grids[2 * s].view(); r.smap = c->grids[2 * s + 1].view();
         r.st = c->states.p + s;
-        r.nn = c->nn.p + (size_t)s * 5 * c->qcap; r.d5 = c->d5.p + (size_t)s * c->qcap;
         r.qperm = c->qperm.p + (size_t)s * c->qcap;
-        r.partials = c->partials.p + (size_t)s * c->fit_blocks * S2M_ACC;
+        r.qprev = c->qprev.p + (size_t)s * c->qcap;
+        r.partials = c->partials.p + (size_t)s * c->part_stride * S2M_ACC;
         r.cap = c->qcap;
         for (int i = 0; i < 6; i++) h_poses[6 * s + i] = T[6 * s + i];
     }
@@ -358,21 +361,16 @@ int enqueue_step(llb_batch *c, const float *T)
         LLB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
         prof_mark(c, 1);                                         // what is left of downsampleCurrentScan after the overlap
         const BatchReg *regs = (const BatchReg *)(dp + L.off_regs);
-        launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->stream);
+        launch_batch_prepare(regs, (const float *)(dp + L.off_poses), B, c->sprm, c->prm.s2m_max_iterations, c->queue.p, c->stream);
         nl++;
-        if (batch_knn_variant() >= 2) {                          // kNN variants 2 / 3: queries ordered by cell / by cost
-            launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);
-            nl++;
-        }
+        launch_batch_qsort(regs, B, std::max(c->vox_cap1, c->vox_cap2), c->stream);   // queries ordered by search cost
+        nl++;
         prof_mark(c, 5);
-        for (int it = 0; it < c->prm.s2m_max_iterations; it++) {
-            launch_batch_knn(regs, B, c->knn_ctas, c->sprm, c->stream);
-            prof_mark(c, 3);
-            launch_batch_fit(regs, B, c->fit_blocks, it, c->sprm, c->stream);
-            prof_mark(c, 4);
-            nl += 2;
-        }
-        launch_batch_collect(regs, B, c->results.p, c->stream);
+        // scan2MapOptimization of every slot: ONE persistent launch for all LM iterations (batch.cu)
+        launch_batch_lm(regs, B, c->lm_grid, c->sprm, c->prm.s2m_max_iterations, c->queue.p, c->stream);
+        nl++;
+        prof_mark(c, 4);
+        launch_batch_collect(regs, B, c->results.p, c->queue.p, c->stream);
         nl++;
         prof_mark(c, 5);
         return nl;
@@ -487,12 +485,25 @@ int llb_batch_create(const llb_params *p, int device, int n_slots, int max_scan_
         c->ds_n.ensure((size_t)B * 4);
         LLB_CUDA(cudaMemset(c->ds_n.p, 0, sizeof(int) * 4 * B));
         c->states.ensure(B);
-        c->nn.ensure((size_t)B * 5 * c->qcap); c->d5.ensure((size_t)B * c->qcap); c->qperm.ensure((size_t)B * c->qcap);
+        c->qperm.ensure((size_t)B * c->qcap); c->qprev.ensure((size_t)B * c->qcap);
         // launch geometry: enough CTAs to fill 148 SMs several times over, independent of B
-        c->fit_blocks = std::max(1, std::min(div_up(c->qcap, BATCH_FIT_THREADS), std::max(2, 148 * 8 / B)));
-        c->knn_ctas = std::max(1, std::min(div_up(c->qcap, BATCH_KNN_THREADS), std::max(2, 148 * 12 / B)));
         c->grid_ctas = std::max(2, std::min(148 * 4, 148 * 8 / (2 * B)));
-        c->partials.ensure((size_t)B * c->fit_blocks * S2M_ACC);
+        c->part_stride = c->qcap / 32 + 2;                               // one partial per chunk of 32 queries
+        c->partials.ensure((size_t)B * c->part_stride * S2M_ACC);
+        c->queue.ensure(1);
+        c->slot_info.ensure(B); c->ctl.ensure(B);
+        LLB_CUDA(cudaMemset(c->slot_info.p, 0, sizeof(BatchSlotInfo) * B));
+        { std::vector<unsigned> done((size_t)B, 0xffff8000u); LLB_CUDA(cudaMemcpy(c->ctl.p, done.data(), sizeof(unsigned) * B, cudaMemcpyHostToDevice)); }
+        c->lm_grid = batch_lm_grid();
+        BatchQueue bq{};
+        bq.slot = c->slot_info.p; bq.ctl = c->ctl.p;
+        if (getenv("LLB_ITER_PROF")) {                           // debug: per-warp cycles by phase of the registration kernel
+            const size_t n = (size_t)c->lm_grid * (BATCH_ITER_THREADS / 32) * 12;
+            c->iter_prof.ensure(n);
+            LLB_CUDA(cudaMemset(c->iter_prof.p, 0, n * sizeof(long long)));
+            bq.prof = c->iter_prof.p;
+        }
+        LLB_CUDA(cudaMemcpy(c->queue.p, &bq, sizeof(bq), cudaMemcpyHostToDevice));
         c->results.ensure(B); c->pin_results.ensure(B);
         const int cells = std::min(c->prm.max_grid_cells, 1 << 22);
         c->grids.resize(2 * (size_t)B);
@@ -514,10 +525,30 @@ int llb_batch_destroy(llb_batch *c)
     if (!c) return LLB_ERR_INVALID;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->iter_prof.p) {                                        // debug: phase durations (cycles) of the last profiled launch
+        const int nw = c->lm_grid * (BATCH_ITER_THREADS / 32);
+        std::vector<long long> h((size_t)nw * 12);
+        cudaMemcpy(h.data(), c->iter_prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        static const char *names[10] = { "fetch item + slot record", "query + transform + bound", "A own row", "B neighbour index",
+                                         "C rank runs", "gather 5", "fit + Jacobian", "products + partial", "fence + ticket", "LM step" };
+        std::vector<long long> col(nw);
+        auto stat = [&](int k, const char *name) {
+            int n = 0;
+            for (int w = 0; w < nw; w++) if (h[(size_t)w * 12 + 11] > 0 || k >= 10) col[n++] = h[(size_t)w * 12 + k];
+            if (n == 0) return;
+            std::sort(col.begin(), col.begin() + n);
+            double sum = 0; for (int i = 0; i < n; i++) sum += (double)col[i];
+            fprintf(stderr, "  %-28s mean %9.0f  p50 %9lld  p90 %9lld  max %9lld  (%d warps)\n", name, sum / n, col[n / 2], col[n * 9 / 10], col[n - 1], n);
+        };
+        fprintf(stderr, "LLB_ITER_PROF: cycles per warp summed over its items, by phase\n");
+        for (int k = 0; k < 10; k++) stat(k, names[k]);
+        stat(10, "warp lifetime"); stat(11, "items per warp");
+        c->iter_prof.release();
+    }
     for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
     c->features.release();
     c->scan_in.release(); c->scan_raw.release(); c->scan_ds.release(); c->map_in.release(); c->map_raw.release();
-    c->ds_n.release(); c->states.release(); c->nn.release(); c->qperm.release(); c->d5.release(); c->partials.release();
+    c->ds_n.release(); c->states.release(); c->qperm.release(); c->partials.release(); c->qprev.release(); c->queue.release(); c->slot_info.release(); c->ctl.release();
     c->results.release(); c->pin_results.release(); c->step_dev.release();
     for (int i = 0; i < RING; i++) { c->step_pin[i].release(); if (c->step_ev[i]) cudaEventDestroy(c->step_ev[i]); }
     for (auto &g : c->grids) g.release();
@@ -919,7 +950,7 @@ int llb_batch_get_profile(llb_batch *c, float ms[6], int geometry[4])
 {
     if (!c) return LLB_ERR_INVALID;
     if (ms) for (int k = 0; k < PROF_N; k++) ms[k] = c->prof_ms[k];
-    if (geometry) { geometry[0] = c->knn_ctas; geometry[1] = c->fit_blocks; geometry[2] = c->grid_ctas; geometry[3] = c->qcap; }
+    if (geometry) { geometry[0] = c->lm_grid; geometry[1] = BATCH_ITER_THREADS; geometry[2] = c->grid_ctas; geometry[3] = c->qcap; }
     return LLB_OK;
 }
 

@@ -182,7 +182,10 @@ grid_row_scan_kernel(GridJobs jobs, const GridJob *__restrict__ table)
     if (threadIdx.x == 0) jb.row_begin[nrows] = s_carry;
 }
 
-// cell_begin of every row: one warp per row
+// cell_begin of every occupied row: one warp per row.  Lane l owns 8 CONSECUTIVE cells of a 256-cell stretch (its loads
+// fill whole 32-byte sectors), adds them up, ONE warp scan over the 32 lane sums gives every lane its base: ~45
+// instructions per stretch (the first version scanned 8 interleaved strips with 8 warp scans: ~150, and this kernel
+// was a quarter of all instructions of a batch step, profiles/r02_knnfit.md).
 __global__ void __launch_bounds__(TPB)
 grid_row_apply_kernel(GridJobs jobs, const GridJob *__restrict__ table)
 {
@@ -197,17 +200,22 @@ grid_row_apply_kernel(GridJobs jobs, const GridJob *__restrict__ table)
         int *__restrict__ cb = jb.cell_begin + (size_t)r * dx;
         const int *__restrict__ cnt = jb.counts + (size_t)r * dx;
         int run = rb;
-        for (int x0 = 0; x0 < dx; x0 += 256) {              // 8 independent loads per lane, then 8 warp scans
+        for (int x0 = 0; x0 < dx; x0 += 256) {
+            const int xl = x0 + lane * 8;
             int v[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) { const int x = x0 + j * 32 + lane; v[j] = x < dx ? cnt[x] : 0; }
+            for (int j = 0; j < 8; j++) v[j] = xl + j < dx ? cnt[xl + j] : 0;
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) s += v[j];
+            const int inc = warp_incl_scan(s);
+            int o = run + inc - s;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int x = x0 + j * 32 + lane;
-                const int inc = warp_incl_scan(v[j]);
-                if (x < dx) cb[x] = run + inc - v[j];
-                run += __shfl_sync(FULL, inc, 31);
+                if (xl + j < dx) cb[xl + j] = o;
+                o += v[j];
             }
+            run += __shfl_sync(FULL, inc, 31);
         }
         if (lane == 0) cb[dx] = run;                         // end of the row's last cell (= next row's first entry)
     }
@@ -250,7 +258,7 @@ __global__ void grid_zero_kernel(int *p, int n)
 
 }  // namespace
 
-void GridIndex::init(int max_cells)
+void GridIndex::init(int max_cells, cudaStream_t s)
 {
     max_cells_ = max_cells > 4096 ? max_cells : 4096;
     desc_.ensure(1);
@@ -258,9 +266,9 @@ void GridIndex::init(int max_cells)
     cell_begin_.ensure((size_t)max_cells_ + 1);
     row_cnt_.ensure((size_t)max_cells_ + 1);
     row_begin_.ensure((size_t)max_cells_ + 2);
-    grid_desc_init_kernel<<<1, 1>>>(desc_.p);
-    grid_zero_kernel<<<148 * 4, 256>>>(counts_.p, max_cells_ + 1);
-    grid_zero_kernel<<<148 * 4, 256>>>(row_cnt_.p, max_cells_ + 1);
+    grid_desc_init_kernel<<<1, 1, 0, s>>>(desc_.p);
+    grid_zero_kernel<<<148 * 4, 256, 0, s>>>(counts_.p, max_cells_ + 1);
+    grid_zero_kernel<<<148 * 4, 256, 0, s>>>(row_cnt_.p, max_cells_ + 1);
     LLB_CUDA(cudaGetLastError());
 }
 

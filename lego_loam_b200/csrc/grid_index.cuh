@@ -43,7 +43,9 @@ struct GridJob {             // one index build: input cloud + the buffers of th
 
 class GridIndex {
 public:
-    void init(int max_cells);
+    // the tables are zeroed by kernels on `s`: pass the stream the builds will run on (a non-blocking stream does not
+    // wait for work on the default stream)
+    void init(int max_cells, cudaStream_t s = nullptr);
     void release();
     // Builds the indices of two maps with one set of five launches.  n_upper is a host upper
     // bound, n_dev (optional) the device-resident length.  Returns the number of launches.

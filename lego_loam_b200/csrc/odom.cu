@@ -562,7 +562,9 @@ int OdomSolver::set_last(int ncl, int nsl, cudaStream_t s)
     ncl_ = ncl; nsl_ = nsl; last_set_ = true;
     // spatial index of the previous sweep's clouds (the reference rebuilds its two kd-trees here, FA:1615-1616 /
     // FA:1786-1787): cells of the gate radius, so the 27-cell neighbourhood holds every acceptable nearest neighbour
-    if (!grids_init_) { gridCorner_.init(1 << 18); gridSurf_.init(1 << 18); grids_init_ = true; }
+    // (first call: the tables are zeroed on the same stream the build runs on - on the default stream the build on a
+    // non-blocking stream raced with them: an intermittently wrong first index, seen as a flaky first odometry test)
+    if (!grids_init_) { gridCorner_.init(1 << 18, s); gridSurf_.init(1 << 18, s); grids_init_ = true; }
     if (ncl <= 0 || nsl <= 0) { grids_built_ = false; return 0; }
     const int n = GridIndex::build_pair(gridCorner_, cornerLast_.p, nullptr, ncl, gridSurf_, surfLast_.p, nullptr, nsl,
                                         std::sqrt(prm_.nearest_sqdist), s);

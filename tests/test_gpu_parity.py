@@ -192,6 +192,63 @@ def test_scan2map_pose_parity(ctx, seed):
     assert err1 < err0
 
 
+# ------------------------------------------------------------------ BASELINE configs 1 / 3 / 4 (sensor + map size)
+
+@pytest.mark.parametrize("workload", ["vlp16_50k", "hdl32e_300k", "vls128_2m"])
+def test_scan2map_parity_baseline_configs(workload):
+    """BASELINE.json configs[0] (VLP-16 vs a 50k map), [2] (HDL-32E vs 300k), [3] (VLS-128 vs 2M) on bench.py's own generators:
+    DS maps / DS scans bit-exact, first-iteration kNN sets + rows bit-exact against the restatement, final pose
+    bit-identical to the restatement and to the compiled reference (tier B)."""
+    import bench
+    from lego_loam_b200 import api
+    mc, ms, scans = bench.make_inputs(workload, 0, 1)
+    sc, init = scans[0]
+    case = dict(map_corner_raw=mc, map_surf_raw=ms, corner=sc.corner_last, surf=sc.surf_last, outlier=sc.outlier_last, init=init)
+    ctx = api.Context(0)
+    try:
+        mo, counts = _setup(ctx, case, 0)
+        for which in range(4):
+            assert_clouds_bitexact(ctx.scan_get_ds(which), mo.scan_ds(which), f"{workload} scan ds {which}")
+        for which in range(2):
+            assert_clouds_bitexact(ctx.map_get_ds(which), mo.map_ds(which), f"{workload} map ds {which}")
+        # one iteration: kNN sets and rows
+        mo.build_kdtrees()
+        mo.transformTobeMapped = init
+        mo.clear_correspondences()
+        mo.cornerOptimization(0); mo.surfOptimization(0)
+        mo.LMOptimization(0)
+        T1, conv, n_corr = ctx.s2m_iterate(init, 0)
+        for which in range(2):
+            ri, rd = mo.knn(which); gi, gd = ctx.get_knn(which)
+            used = rd[:, 4] < 1.0
+            assert np.array_equal(used, (gi[:, 4] >= 0) & (gd[:, 4] < 1.0))
+            assert np.array_equal(ri[used], gi[used]) and np.array_equal(rd[used].view(np.uint32), gd[used].view(np.uint32))
+        ori_r, co_r = mo.correspondences(); ori_g, co_g = ctx.get_correspondences()
+        assert n_corr == ori_r.shape[0] > 50
+        assert_clouds_bitexact(ori_g, ori_r, "laserCloudOri"); assert_clouds_bitexact(co_g, co_r, "coeffSel")
+        # the whole registration
+        mo.transformTobeMapped = init
+        it_ref = mo.scan2MapOptimization()
+        T_gpu, st = ctx.s2m_optimize(init)
+        assert st.iterations == it_ref and not st.skipped
+        assert np.array_equal(T_gpu.view(np.uint32), np.asarray(mo.transformTobeMapped, np.float32).view(np.uint32)), \
+            (T_gpu, mo.transformTobeMapped)
+        T_b = _ref_pose(case)
+        if T_b is not None:
+            assert np.array_equal(T_gpu.view(np.uint32), T_b.view(np.uint32)), (T_gpu, T_b)
+        # the batched engine on the same registration (one slot)
+        mc_ds, ms_ds = ctx.map_get_ds(0), ctx.map_get_ds(1)
+        cap_scan = 1 << int(np.ceil(np.log2(max(sc.corner_last.shape[0], sc.surf_last.shape[0] + sc.outlier_last.shape[0], 1024))))
+        if cap_scan <= 16384:                                # scan capacity of a batch slot
+            b = api.Batch(0, 1, cap_scan, max(mc_ds.shape[0], ms_ds.shape[0]) + 64)
+            b.scan_set(0, sc.corner_last, sc.surf_last, sc.outlier_last); b.map_set_ds(0, mc_ds, ms_ds)
+            Tb, stb = b.register(np.stack([init]))
+            b.close()
+            assert np.array_equal(Tb[0].view(np.uint32), T_gpu.view(np.uint32)) and stb[0].iterations == st.iterations
+    finally:
+        ctx.close()
+
+
 def test_scan2map_guard_small_map(ctx):
     """MO:1331: with <= 10 corner or <= 100 surf map points nothing runs and the pose is untouched."""
     case = data.mapping_case(1)
