@@ -1,26 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- scan-to-map registrations/s on B200 (BASELINE.json metric).
+"""bench.py -- scan-to-map registrations/s on B200 (BASELINE.json metric, config 5: 64 independent VLP-16 sequences).
 
-Workload (BASELINE configs[1]/[4]): VLP-16 synthetic sequences replayed against their ~100k-point
-voxel-DS local maps.  A registration = downsampleCurrentScan (MO:1067-1091) + scan2MapOptimization
-(MO:1329-1350, including the spatial-index build that replaces the two kdtree->setInputCloud calls).
-One registration is ~0.2 ms of latency-bound device work, so -- exactly like the reference arm, which
-runs one registration stream per host core -- the GPU arm registers S independent sequences per step
-with the batched engine (llb_batch_*: every kernel launch covers all slots; NB batches of S/NB slots
-alternate so that the host work / H2D of one overlaps the kernels of the other).  A "step" = one
-registration for each of the S sequences; ranks are replicas (weak scaling, no data-path collective).
+A REGISTRATION is one mapping cycle of the reference node for one sequence (the north-star path end to end):
+    local map of the sequence assembled from its key-frames     (transformPointCloud + concatenation, MO:1033-1056)
+    two map voxel filters                                        (MO:1057-1064)
+    spatial index of the two voxel-DS maps                       (replaces kdtree->setInputCloud x2, MO:1333-1334)
+    downsampleCurrentScan                                        (MO:1067-1091)
+    scan2MapOptimization                                         (MO:1329-1350: <= 10 LM iterations)
+A STEP registers one new sweep for each of the S sequences of a GPU with the batched engine (llb_batch_*: every kernel
+launch covers all slots, NB batches alternate so that the host work of one overlaps the kernels of the other); the
+key-frame clouds of every sequence are device-resident (llb_batch_keyframe_add: each was uploaded once, when it was the
+current sweep).  Ranks are replicas (weak scaling, no data-path collective).
 
-  value : device-resident inputs, CUDA events (first start -> last end over the NB batch streams),
-          max over ranks.  The resident maps + indices exceed the 126 MB L2 (config.l2), no flush needed.
-  e2e   : the same steps through the C ABI with HOST clouds in pcl::PointXYZI layout (H2D of scan + DS
-          map and D2H of pose + stats inside the timed region), wall clock, one host thread per batch.
-  latency : single sequence through the single-registration path (one persistent kernel), L2 flushed
-          between registrations (ms/scan of the metric).
-  roofline : the kNN + fit kernels of one LM iteration over all slots (K3+K4), 96 algorithmic bytes per
-          query-iteration, timed with CUDA events on the batch stream.
-  cpu_baseline : the reference-linked harness (oracle/_ref, kind "reference"; else the oracle port)
-          on a bounded sample of the same workload, 1 core.
-  --impl reference : the reference's CPU path on all host cores (one registration stream per core).
+  value : the new sweeps already in HBM; CUDA events (first start -> last end over the NB batch streams), max over ranks.
+  e2e   : the same steps through the C ABI with HOST sweeps in pcl::PointXYZI layout: H2D of the sweep and D2H of pose +
+          stats inside the timed region, wall clock, one host thread per batch, on EVERY rank.
+  roofline : the registration kernel (kNN + fits + LM steps of all iterations, ONE launch per step), 96 algorithmic bytes
+          per query-iteration, timed with CUDA events on the batch stream; roofline_stages: index build
+          and map voxel filters against their own algorithmic bytes.
+  cpu_baseline : the reference's own statements for the same cycle (oracle/_ref: the unmodified mapOptmization.cpp; kind
+          "reference") on a bounded sample, 1 core.
+  registration_only : secondary (rank 0): the drop-in signature alone - DS map handed over, downsampleCurrentScan +
+          scan2MapOptimization - device-resident and with host clouds (scan AND DS map over PCIe), as round 1 reported.
+  latency : one sequence alone on the single-registration path (one persistent kernel), L2 flushed.
+  --impl reference : the same cycle with the reference's CPU implementation on all host cores (one stream per core).
 """
 from __future__ import annotations
 
@@ -122,34 +125,132 @@ def cpu_registration_factory(mc_ds, ms_ds, scans):
     return run, kind
 
 
-def _ref_worker(args):
-    workload, seq_id, n_scans, n_regs, start_at = args
+_T0 = time.time()
+
+
+def _log(msg):
+    print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def make_cycle_sequence(args):
+    """One synthetic sequence of the mapping cycle: n_kf key-frame sweeps ~1 m apart along a gently turning path (the
+    reference thins key poses to 1 m, MO:1011-1012) and n_new further sweeps beside the path -> (key poses (n_kf, 6) f32,
+    [(corner, surf, outlier)] key-frame sweeps, [(corner, surf, outlier, true pose)] new sweeps)."""
+    seq_id, n_kf, n_new, sensor = args
+    from lego_loam_b200 import synth
+    w = synth.make_world(synth.SEED0 + 500 + seq_id)
+    rng = np.random.default_rng(8000 + seq_id)
+    yaw0 = rng.uniform(-3.0, 3.0)
+    x0, z0 = rng.uniform(-25, 25, 2)
+    poses, kf, new = [], [], []
+    for k in range(n_kf + n_new):
+        j = k if k < n_kf else n_kf // 2 + 3 * (k - n_kf)
+        yaw = yaw0 + 0.01 * j
+        pose = np.array([0.004 * np.sin(0.3 * j), yaw, 0.004 * np.cos(0.2 * j),
+                         x0 + 1.0 * j * np.sin(yaw0 + 0.005 * j), 0.0, z0 + 1.0 * j * np.cos(yaw0 + 0.005 * j)])
+        if k >= n_kf:
+            pose[3] += 0.35; pose[5] += 0.2                  # the new sweeps are not on a key-frame
+        sc = synth.make_mapping_scan(w, synth.SENSORS[sensor], pose, seed=9000 + 1000 * seq_id + k)
+        if k < n_kf:
+            poses.append(pose.astype(np.float32)); kf.append((sc.corner_last, sc.surf_last, sc.outlier_last))
+        else:
+            new.append((sc.corner_last, sc.surf_last, sc.outlier_last, pose))
+    return np.stack(poses), kf, new
+
+
+def make_cycle_sequences(ids, n_kf, n_new, sensor):
+    """the sequences are ray-cast on the host (0.25 s per sweep): all cores, untimed set-up"""
+    import multiprocessing as mp
+    jobs = [(i, n_kf, n_new, sensor) for i in ids]
+    cores = max(1, min(len(jobs), len(os.sched_getaffinity(0))))
+    if cores == 1:
+        return [make_cycle_sequence(j) for j in jobs]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        return pool.map(make_cycle_sequence, jobs)
+
+
+def cpu_raw_map(key_poses, kf):
+    """Raw local map of a sequence on the host (reference arm / cpu_baseline without a device): every key-frame's DS
+    clouds (downsampleCurrentScan of the sweep, what saveKeyFramesAndFactor stores, MO:1443-1453) moved by its key pose
+    (transformPointCloud MO:545-575) and concatenated (MO:1050-1054)."""
     import oracle
-    mc, ms, scans = make_inputs(workload, seq_id, n_scans)
-    mc_ds, _ = oracle.voxel_grid(mc, 0.2); ms_ds, _ = oracle.voxel_grid(ms, 0.4)
-    run, kind = cpu_registration_factory(mc_ds, ms_ds, scans)
-    run(0)                                                   # warm-up
-    while time.time() < start_at:
-        time.sleep(0.001)
+    from lego_loam_b200 import synth
+    oracle.set_trig_mode(0)
+    mo = oracle.MapOptimization()
+    rc, rs = [], []
+    for pose, (c, s, o) in zip(key_poses, kf):
+        mo.set_scan(c, s, o); mo.downsampleCurrentScan()
+        for cloud, dst in ((mo.scan_ds(0), rc), (mo.scan_ds(1), rs), (mo.scan_ds(2), rs)):
+            out = cloud.copy()
+            out[:, :3] = synth.apply_pose(pose.astype(np.float64), cloud[:, :3].astype(np.float64)).astype(np.float32)
+            dst.append(out)
+    return np.ascontiguousarray(np.concatenate(rc)), np.ascontiguousarray(np.concatenate(rs))
+
+
+def cpu_cycle_factory(raw_c, raw_s, new, inits):
+    """-> (fn(i) -> pose, kind): the reference's statements for one mapping cycle on the CPU (raw local map given)"""
+    kind, mo = "port", None
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            kind = "reference"; mo = ref_harness.MapOptimization()
+    except Exception:
+        mo = None
+    if mo is None:
+        import oracle
+        oracle.set_trig_mode(0); mo = oracle.MapOptimization()
+
+    def run(i):
+        c, s_, o, _ = new[i % len(new)]
+        mo.set_map_raw(raw_c, raw_s)                         # MO:1057-1064: the two map voxel filters
+        mo.set_scan(c, s_, o)
+        mo.transformTobeMapped = inits[i % len(new)]
+        mo.downsampleCurrentScan()
+        mo.scan2MapOptimization()
+        return mo.transformTobeMapped
+    return run, kind
+
+
+_REF_BARRIER = None
+
+
+def _ref_init(barrier):
+    global _REF_BARRIER
+    _REF_BARRIER = barrier
+
+
+def _ref_worker(args):
+    seq_id, n_kf, n_new, sensor, n_warm, n_regs = args
+    from lego_loam_b200 import synth
+    key_poses, kf, new = make_cycle_sequence((seq_id, n_kf, n_new, sensor))
+    raw_c, raw_s = cpu_raw_map(key_poses, kf)
+    rng = np.random.default_rng(100 + seq_id)
+    inits = [synth.perturb_pose(np.asarray(x[3], np.float64), rng).astype(np.float32) for x in new]
+    run, kind = cpu_cycle_factory(raw_c, raw_s, new, inits)
+    for i in range(max(n_warm, 1)):
+        run(i)
+    _REF_BARRIER.wait()                                      # every worker has built its inputs
     t0 = time.perf_counter()
     for i in range(n_regs):
         run(i)
-    return time.perf_counter() - t0, kind
+    return time.perf_counter() - t0, kind, int(raw_c.shape[0] + raw_s.shape[0])
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path, one registration stream per host core."""
+    """--impl reference: the reference's CPU path for the same mapping cycle, one registration stream per host core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    per_core = 3                                             # registrations per core per step
+    per_core = 1                                             # registrations per core per step
     K, W = args.steps, args.warmup
+    sensor = WORKLOADS[args.workload][0]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        start_at = time.time() + 30.0                        # every worker builds its inputs first
-        res = pool.map(_ref_worker, [(args.workload, 0, 2, per_core * K, start_at)] * cores)
+    barrier = ctx.Barrier(cores)
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(barrier,)) as pool:
+        res = pool.map(_ref_worker, [(c % max(args.distinct, 1), args.key_frames, args.scans, sensor, min(W, 2), per_core * K)
+                                     for c in range(cores)], chunksize=1)
     wall = max(r[0] for r in res)
     kind = res[0][1]
     total = cores * per_core * K
@@ -158,8 +259,8 @@ def run_reference(args):
         "impl": "reference", "metric": "scan-to-map registrations/s", "value": value, "unit": "registrations/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": wall / K * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: VLP-16 sweep vs ~100k-pt DS local map, downsampleCurrentScan+"
-                               f"scan2MapOptimization, {per_core} registrations/core/step on {cores} cores"},
+        "config": {"workload": cycle_workload_text(args.workload, args.key_frames, res[0][2], None) +
+                               f"; {per_core} registration/core/step on {cores} cores"},
         "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": kind,
                          "sample": f"{total} registrations ({per_core}/core/step x {K} steps x {cores} cores)"},
         "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,136 +270,167 @@ def run_reference(args):
     return 0
 
 
-def mapping_cycle_arm(api, local, n_slots, n_batches, n_keyframes, steps, warm, cpu_sample):
-    """Secondary arm (SURVEY 8(f)-1 + row a2): the mapping cycle with DEVICE-RESIDENT key-frame stores on the batched
-    engine.  Per registration only the new sweep crosses PCIe; the raw local map of every slot is assembled from its
-    resident key-frames (transformPointCloud + concatenation, MO:1033-1056) by one launch, the 2 x slots map voxel
-    filters (MO:1057-1064) share one set of 18 launches, then index build + downsampleCurrentScan +
-    scan2MapOptimization as in the main arm.  The CPU figure runs the reference's own statements for the same cycle
-    (its two map voxel filters + downsampleCurrentScan + scan2MapOptimization) on 1 core."""
-    from lego_loam_b200 import synth
-    D = 2
-    seq = []
+def cycle_workload_text(workload, n_kf, raw_pts, ds_pts):
+    sensor = WORKLOADS[workload][0]
+    t = (f"{workload}: independent {sensor.upper()} synthetic sequences, registration = one mapping cycle: local map from "
+         f"{n_kf} key-frames (~{raw_pts} raw points")
+    if ds_pts:
+        t += f" -> ~{ds_pts}-pt voxel-DS map"
+    return t + ") + 2 map voxel filters + index + downsampleCurrentScan + scan2MapOptimization"
+
+
+def registration_only_arm(api, torch, local, workload, S, NB, D, n_scans, K, W):
+    """Secondary arm (rank 0): the drop-in signature alone, as round 1 reported it.  The voxel-DS map is handed over
+    (MO:1057-1064 is the caller's tail), a registration = downsampleCurrentScan + scan2MapOptimization (index build
+    included); device-resident inputs (CUDA events) and host clouds through the C ABI (scan AND DS map cross PCIe for
+    every registration: PCIe-bound)."""
+    dev = torch.device("cuda", local)
+    base = []
+    setup_ctx = api.Context(local)
     for d in range(D):
-        w = synth.make_world(synth.SEED0 + 500 + d)
-        yaw0 = 0.4 + 0.9 * d
-        poses, scans = [], []
-        for k in range(n_keyframes + 2):
-            # key-frames every ~1 m along a gently turning path (the reference thins key poses to 1 m, MO:1011-1012)
-            j = k if k < n_keyframes else n_keyframes // 2 + (k - n_keyframes)
-            yaw = yaw0 + 0.01 * j
-            pose = np.array([0.004 * np.sin(0.3 * j), yaw, 0.004 * np.cos(0.2 * j),
-                             -20.0 + 1.0 * j * np.sin(yaw0 + 0.005 * j), 0.0, -25.0 + 1.0 * j * np.cos(yaw0 + 0.005 * j)])
-            if k >= n_keyframes:
-                pose[3] += 0.35; pose[5] += 0.2                    # the new sweeps are not on a key-frame
-            poses.append(pose.astype(np.float32))
-            sc = synth.make_mapping_scan(w, synth.VLP16, pose, seed=9000 + 100 * d + k)
-            scans.append((api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), sc))
-        seq.append((poses, scans))
+        mc, ms, scans = make_inputs(workload, d, n_scans)
+        setup_ctx.map_set_raw(mc, ms)
+        base.append((setup_ctx.map_get_ds(0), setup_ctx.map_get_ds(1), scans))
+    setup_ctx.close()
+    seqs = []
+    for s in range(S):
+        mc_ds, ms_ds, scans = base[s % D]
+        seqs.append({"scans": scans, "mc_ds": mc_ds, "ms_ds": ms_ds, "mc32": api.to_pcl(mc_ds), "ms32": api.to_pcl(ms_ds),
+                     "scans32": [(api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), init)
+                                 for sc, init in scans],
+                     "d_mc": torch.from_numpy(mc_ds).to(dev), "d_ms": torch.from_numpy(ms_ds).to(dev),
+                     "d_scans": [(torch.from_numpy(sc.corner_last).to(dev), torch.from_numpy(sc.surf_last).to(dev),
+                                  torch.from_numpy(sc.outlier_last).to(dev)) for sc, init in scans]})
+    torch.cuda.synchronize()
+    max_map = max(max(q["mc_ds"].shape[0], q["ms_ds"].shape[0]) for q in seqs) + 1024
+    max_scan = max(max(c.shape[0] for c in sc[:3]) for q in seqs for sc in q["scans32"]) + 256
     prm = api.default_params(); prm.pin_host_clouds = 1
     P = api.Batch.pack
-    per = n_slots // n_batches
-    bts = []
-    for bi in range(n_batches):
-        b = api.Batch(local, per, 8192, 4096, prm)
-        b.enable_keyframes(400000, n_keyframes)
-        slot_seq = [(bi * per + s) % D for s in range(per)]
-        dummy = api.to_pcl(np.zeros((16, 4), np.float32))          # placeholder map for the key-frame collection steps
-        for s in range(per):
-            b.map_set_ds_pcl(s, dummy, dummy)
-        tabs = [tuple(P([seq[d][1][k][j].ctypes.data for d in slot_seq], [seq[d][1][k][j].shape[0] for d in slot_seq])
-                      for j in range(3)) for k in range(n_keyframes + 2)]
-        for k in range(n_keyframes):                              # saveKeyFramesAndFactor's cloud part, MO:1443-1453
-            b.scan_set_all(*tabs[k], dev=False)
-            b.register(np.zeros((per, 6), np.float32))             # (skipped by the guard MO:1331: only the DS clouds matter)
-            for s in range(per):
-                b.keyframe_add(s)
-        kposes = [np.stack(seq[d][0][:n_keyframes]).astype(np.float32) for d in slot_seq]
-        rng = np.random.default_rng(100 + bi)
-        init = [np.stack([synth.perturb_pose(seq[d][0][n_keyframes + i].astype(np.float64), rng) for d in slot_seq]).astype(np.float32)
-                for i in range(2)]
-        bts.append({"b": b, "tabs": tabs, "kposes": kposes, "init": init, "slot_seq": slot_seq, "dummy": dummy})
-    ids = np.arange(n_keyframes, dtype=np.int32)
+    batches = []
+    for g in [list(range(b, S, NB)) for b in range(NB)]:
+        b = api.Batch(local, len(g), min(max_scan, 16384), max_map, prm)
+        tabs = {"T": [np.stack([seqs[s]["scans"][i][1] for s in g]).astype(np.float32) for i in range(n_scans)]}
+        for kind, dev_side in (("dev", True), ("host", False)):
+            ptr = (lambda a: a.data_ptr()) if dev_side else (lambda a: a.ctypes.data)
+            mk, sk = ("d_mc", "d_ms") if dev_side else ("mc32", "ms32")
+            tabs[kind + "_map"] = (P([ptr(seqs[s][mk]) for s in g], [seqs[s][mk].shape[0] for s in g]),
+                                   P([ptr(seqs[s][sk]) for s in g], [seqs[s][sk].shape[0] for s in g]))
+            sckey = "d_scans" if dev_side else "scans32"
+            tabs[kind + "_scan"] = [tuple(P([ptr(seqs[s][sckey][i][k]) for s in g], [seqs[s][sckey][i][k].shape[0] for s in g])
+                                          for k in range(3)) for i in range(n_scans)]
+        batches.append({"b": b, "g": g, "tabs": tabs, "stream": torch.cuda.ExternalStream(b.stream, device=local)})
 
-    def cycle(bt, i):
-        b = bt["b"]
-        b.scan_set_all(*bt["tabs"][n_keyframes + i % 2], dev=False)    # H2D: the new sweeps only
-        for s in range(per):
-            b.map_assemble(s, ids, bt["kposes"][s])               # resident key-frames -> raw map -> DS map -> index
-        b.register_async(bt["init"][i % 2])
+    def enqueue(bt, i, kind):
+        b, tabs = bt["b"], bt["tabs"]
+        c, s_, o = tabs[kind + "_scan"][i % n_scans]
+        b.scan_set_all(c, s_, o, dev=(kind == "dev"))
+        mc, ms = tabs[kind + "_map"]
+        b.map_set_ds_all(mc, ms, dev=(kind == "dev"))        # index rebuilt every registration, like the kd-trees MO:1333-1334
+        b.register_async(tabs["T"][i % n_scans])
 
-    barrier = threading.Barrier(n_batches + 1)
-    out = {}
+    def run_steps(kind, n):
+        for i in range(n):
+            for bt in batches:
+                if bt.get("pending"):
+                    bt["b"].result(); bt["pending"] = False
+                enqueue(bt, i, kind); bt["pending"] = True
+        for bt in batches:
+            if bt.get("pending"):
+                bt["b"].result(); bt["pending"] = False
+
+    run_steps("dev", W)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1s = [torch.cuda.Event(enable_timing=True) for _ in batches]
+    e0.record(batches[0]["stream"])
+    run_steps("dev", K)
+    for bt, e in zip(batches, e1s):
+        e.record(bt["stream"])
+    torch.cuda.synchronize()
+    dev_ms = max(e0.elapsed_time(e) for e in e1s)
+    barrier = threading.Barrier(NB + 1)
 
     def worker(k):
-        bt = bts[k]
-        for i in range(warm):
-            cycle(bt, i); bt["b"].result()
+        torch.cuda.set_device(local)
+        bt = batches[k]
+        for i in range(W):
+            enqueue(bt, i, "host"); bt["b"].result()
         barrier.wait()
-        for i in range(steps):
-            cycle(bt, i); res = bt["b"].result()
-        if k == 0:
-            out["T"], out["st"] = res
+        for i in range(K):
+            enqueue(bt, i, "host"); bt["b"].result()
         barrier.wait()
 
-    ths = [threading.Thread(target=worker, args=(k,)) for k in range(n_batches)]
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(NB)]
     for x in ths:
         x.start()
     barrier.wait()
     t0 = time.perf_counter()
     barrier.wait()
-    wall = time.perf_counter() - t0
+    host_s = time.perf_counter() - t0
     for x in ths:
         x.join()
-    b0 = bts[0]["b"]
-    b0.set_profile(True)
-    cycle(bts[0], steps - 1); b0.result()
-    prof, _ = b0.get_profile()
-    b0.set_profile(False)
-    # the reference's own statements for the same cycle on 1 core (bounded sample) + pose check of slot 0
-    raw_c, raw_s = b0.map_get(0, 0), b0.map_get(0, 1)
-    ds_sizes = (int(b0.map_get(0, 2).shape[0]), int(b0.map_get(0, 3).shape[0]))
-    kind, mo = "port", None
-    try:
-        from oracle import ref_harness
-        if ref_harness.available():
-            kind = "reference"; mo = ref_harness.MapOptimization()
-    except Exception:
-        pass
-    if mo is None:
-        import oracle
-        oracle.set_trig_mode(0); mo = oracle.MapOptimization()
-    d0 = bts[0]["slot_seq"][0]
-
-    def cpu_cycle(i):
-        sc = seq[d0][1][n_keyframes + i % 2][3]
-        mo.set_map_raw(raw_c, raw_s)                              # MO:1057-1064: the two map voxel filters
-        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
-        mo.transformTobeMapped = bts[0]["init"][i % 2][0]
-        mo.downsampleCurrentScan()
-        mo.scan2MapOptimization()
-        return mo.transformTobeMapped
-    cpu_cycle(0)
-    t0 = time.perf_counter()
-    for i in range(cpu_sample):
-        cpu_cycle(i)
-    cpu_s = time.perf_counter() - t0
-    diff = float(np.max(np.abs(out["T"][0] - cpu_cycle(steps - 1)))) if "T" in out else None
-    h2d = int(sum(seq[d0][1][n_keyframes][j].nbytes for j in range(3)) + n_keyframes * 28 + 24)
-    st0 = out["st"][0].as_dict() if "st" in out else None
-    for bt in bts:
+    h2d = int(np.mean([sum(a.nbytes for a in q["scans32"][0][:3]) + q["mc32"].nbytes + q["ms32"].nbytes + 24 for q in seqs]))
+    for bt in batches:
         bt["b"].close()
-    return {"value": n_slots * steps / wall, "unit": "registrations/s", "slots": n_slots, "batches": n_batches,
-            "host_threads": n_batches, "key_frames": n_keyframes,
-            "raw_map_points": [int(raw_c.shape[0]), int(raw_s.shape[0])], "ds_map_points": list(ds_sizes),
-            "h2d_bytes_per_registration": h2d, "ms_per_step_wall": wall / steps * 1e3,
-            "stage_ms_per_step": prof, "last_stats_slot0": st0,
-            "cpu_1core": {"value": cpu_sample / cpu_s, "ms_per_registration": cpu_s / cpu_sample * 1e3, "kind": kind,
-                          "sample": f"{cpu_sample} cycles"},
-            "pose_check_max_abs_diff_vs_cpu": diff,
-            "note": "registration = local-map assembly from device-resident key-frames + map voxel filters + index + "
-                    "downsampleCurrentScan + scan2MapOptimization on the batched engine; host clouds in (new sweep only), "
-                    "pose out, wall clock; stage_ms: 'unpack' = key-frame copies + assembly + map voxel filters"}
+    return {"value_device_resident": S * K / (dev_ms * 1e-3), "e2e_host_clouds": S * K / host_s, "unit": "registrations/s",
+            "sequences": S, "batches": NB, "steps": K, "h2d_bytes_per_registration": h2d,
+            "map_points": int(np.mean([q["mc_ds"].shape[0] + q["ms_ds"].shape[0] for q in seqs])),
+            "note": "downsampleCurrentScan + scan2MapOptimization with the voxel-DS map handed over (round-1 main arms); the "
+                    "host-cloud form moves scan AND DS map over PCIe for every registration"}
+
+
+def latency_arm(api, torch, local, workload, W):
+    """One sequence alone on the single-registration path (one persistent kernel), L2 flushed before every registration."""
+    dev = torch.device("cuda", local)
+    mc, ms, scans = make_inputs(workload, 0, 2)
+    setup = api.Context(local); setup.map_set_raw(mc, ms)
+    mc_ds, ms_ds = setup.map_get_ds(0), setup.map_get_ds(1)
+    setup.close()
+    mc32, ms32 = api.to_pcl(mc_ds), api.to_pcl(ms_ds)
+    scans32 = [(api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), init) for sc, init in scans]
+    d_mc, d_ms = torch.from_numpy(mc_ds).to(dev), torch.from_numpy(ms_ds).to(dev)
+    d_scans = [(torch.from_numpy(sc.corner_last).to(dev), torch.from_numpy(sc.surf_last).to(dev),
+                torch.from_numpy(sc.outlier_last).to(dev)) for sc, init in scans]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lat_prm = api.default_params(); lat_prm.pin_host_clouds = 1   # one CTA per SM; host clouds DMA'd in place (long-lived members)
+    lat_ctx = api.Context(local, lat_prm)
+    lat_stream = torch.cuda.ExternalStream(lat_ctx.stream, device=local)
+    d_T = torch.zeros(6, dtype=torch.float32, device=dev)
+    d_init = [torch.from_numpy(np.asarray(init, np.float32).copy()).to(dev) for _, init in scans]
+    lat, lat_host = [], []
+
+    def step_single(i):
+        c, s_, o = d_scans[i % 2]
+        with torch.cuda.stream(lat_stream):
+            d_T.copy_(d_init[i % 2], non_blocking=True)
+        lat_ctx.scan_set_dev(c.data_ptr(), c.shape[0], s_.data_ptr(), s_.shape[0], o.data_ptr(), o.shape[0])
+        lat_ctx.downsample_current_scan(want_counts=False)
+        lat_ctx.map_set_ds_dev(d_mc.data_ptr(), d_mc.shape[0], d_ms.data_ptr(), d_ms.shape[0])
+        lat_ctx.s2m_optimize_dev(d_T.data_ptr())
+
+    with torch.cuda.stream(lat_stream):
+        for i in range(W + 20):
+            flush.zero_()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(lat_stream); step_single(i); b.record(lat_stream)
+            lat_stream.synchronize()
+            if i >= W:
+                lat.append(a.elapsed_time(b))
+        for i in range(W + 20):                              # the same through the C ABI with host clouds, wall clock
+            c, s_, o, init = scans32[i % 2]
+            flush.zero_(); lat_stream.synchronize()
+            t0 = time.perf_counter()
+            lat_ctx.scan_set_pcl(c, s_, o); lat_ctx.downsample_current_scan(want_counts=False)
+            lat_ctx.map_set_ds_pcl(mc32, ms32); lat_ctx.s2m_optimize(init)
+            if i >= W:
+                lat_host.append((time.perf_counter() - t0) * 1e3)
+    del flush
+    lat_ctx.close()
+    return {"ms_per_scan_device": float(np.median(lat)), "ms_per_scan_device_max": float(np.max(lat)),
+            "ms_per_scan_e2e_host": float(np.median(lat_host)), "ms_per_scan_e2e_host_max": float(np.max(lat_host)),
+            "map_points": int(mc_ds.shape[0] + ms_ds.shape[0]),
+            "note": "one sequence alone on the single-registration path (one persistent kernel, one CTA per SM), DS map "
+                    "handed over, L2 flushed before each registration; e2e_host = host PCL clouds in (page-locked once, DMA "
+                    "in place), pose out, wall clock"}
 
 
 def odometry_arm(api, local, reps, cpu_sample):
@@ -473,24 +605,24 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vlp16_100k", choices=sorted(WORKLOADS))
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences registered per step per GPU")
     ap.add_argument("--batches", type=int, default=2, help="batch objects (streams) the sequences are split over")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic sequences generated (slots beyond copy them)")
-    ap.add_argument("--scans", type=int, default=2, help="distinct sweeps per sequence rotated through the steps")
-    ap.add_argument("--cpu-sample", type=int, default=12, help="registrations timed for cpu_baseline")
-    ap.add_argument("--mapping-cycle", type=int, default=1, help="1: also run the key-frame-store mapping-cycle arm (rank 0)")
-    ap.add_argument("--key-frames", type=int, default=50)
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences generated per GPU (slots beyond reuse them with their own initial guesses)")
+    ap.add_argument("--scans", type=int, default=8, help="distinct new sweeps per sequence rotated through the steps")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="registrations timed for cpu_baseline")
+    ap.add_argument("--key-frames", type=int, default=100, help="resident key-frames the local map of a sequence is assembled from")
+    ap.add_argument("--secondary", type=int, default=1, help="1: also run the secondary arms on rank 0 (registration_only, latency, odometry, feature_extraction)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from lego_loam_b200 import api
+    from lego_loam_b200 import api, synth
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -501,62 +633,59 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W, S = args.steps, max(args.warmup, 3), args.seqs
     NB = max(1, min(args.batches, S))
+    KF, NS = args.key_frames, max(args.scans, 1)
     dev = torch.device("cuda", local)
+    sensor = WORKLOADS[args.workload][0]
 
-    # ---------------- S independent sequences: own DS map, own sweeps, own slot (own resident index + LM state)
+    # ---------------- D distinct sequences per rank (ray-cast on the host, all cores, untimed); slot s replays
+    # sequence s % D with its own device copies of the sweeps and its own initial guesses
     D = max(1, min(args.distinct, S))
-    base = []
-    setup_ctx = api.Context(local)                           # one-off set-up work (untimed)
-    for d in range(D):
-        mc, ms, scans = make_inputs(args.workload, 1000 * rank + d, args.scans)
-        setup_ctx.map_set_raw(mc, ms)                        # DS map = what the drop-in signature receives (MO:1057-1064
-        base.append((setup_ctx.map_get_ds(0), setup_ctx.map_get_ds(1), scans))   # is the caller's tail); once, untimed
-    setup_ctx.close()
-    seqs = []
-    for s in range(S):
-        mc_ds, ms_ds, scans = base[s % D]
-        q = {"scans": scans, "mc_ds": mc_ds, "ms_ds": ms_ds,
-             # every slot gets its OWN host and device copies: no artificial sharing in L2 or over PCIe
-             "mc32": api.to_pcl(mc_ds), "ms32": api.to_pcl(ms_ds),
-             "scans32": [(api.to_pcl(sc.corner_last), api.to_pcl(sc.surf_last), api.to_pcl(sc.outlier_last), init)
-                         for sc, init in scans],
-             "d_mc": torch.from_numpy(mc_ds).to(dev), "d_ms": torch.from_numpy(ms_ds).to(dev),
-             "d_scans": [(torch.from_numpy(sc.corner_last).to(dev), torch.from_numpy(sc.surf_last).to(dev),
-                          torch.from_numpy(sc.outlier_last).to(dev)) for sc, init in scans]}
-        seqs.append(q)
-    torch.cuda.synchronize()
-    map_pts = int(np.mean([q["mc_ds"].shape[0] + q["ms_ds"].shape[0] for q in seqs]))
-    max_map = max(max(q["mc_ds"].shape[0], q["ms_ds"].shape[0]) for q in seqs) + 1024
-    max_scan = max(max(c.shape[0] for c in sc[:3]) for q in seqs for sc in q["scans32"]) + 256
-    # resident bytes a step touches: per slot the DS map + its re-ordered copy + cell/row tables (estimate)
-    ws_mb = S * (map_pts * 16 * 2 + 2 * 4 * 1.2e6) / 1e6
-
-    prm = api.default_params()
-    prm.pin_host_clouds = 1                                  # e2e: DMA straight from the (long-lived) host clouds
-    groups = [list(range(b, S, NB)) for b in range(NB)]
+    seq = make_cycle_sequences([1000 * rank + d for d in range(D)], KF, NS, sensor)
+    _log("sequences generated")
+    host32 = [[tuple(api.to_pcl(x) for x in sw[:3]) for sw in seq[d][2]] for d in range(D)]      # the caller's PCL clouds
+    kf32 = [[tuple(api.to_pcl(x) for x in f) for f in seq[d][1]] for d in range(D)]
+    max_scan = max(max(x.shape[0] for f in seq[d][1] + [sw[:3] for sw in seq[d][2]] for x in f) for d in range(D)) + 256
+    prm = api.default_params(); prm.pin_host_clouds = 0      # host sweeps are packed into one pinned block per step: ONE copy
+    P = api.Batch.pack
+    per = S // NB
+    ids = np.arange(KF, dtype=np.int32)
     batches = []
-    for g in groups:
-        b = api.Batch(local, len(g), min(max_scan, 16384), max_map, prm)
-        P = api.Batch.pack
-        tabs = {"T": [np.stack([seqs[s]["scans"][i][1] for s in g]).astype(np.float32) for i in range(args.scans)]}
-        for kind, dev_side in (("dev", True), ("host", False)):
-            ptr = (lambda a: a.data_ptr()) if dev_side else (lambda a: a.ctypes.data)
-            mk, sk = ("d_mc", "d_ms") if dev_side else ("mc32", "ms32")
-            tabs[kind + "_map"] = (P([ptr(seqs[s][mk]) for s in g], [seqs[s][mk].shape[0] for s in g]),
-                                   P([ptr(seqs[s][sk]) for s in g], [seqs[s][sk].shape[0] for s in g]))
-            sckey = "d_scans" if dev_side else "scans32"
-            tabs[kind + "_scan"] = [tuple(P([ptr(seqs[s][sckey][i][k]) for s in g], [seqs[s][sckey][i][k].shape[0] for s in g])
-                                          for k in range(3)) for i in range(args.scans)]
-        batches.append({"b": b, "g": g, "tabs": tabs, "stream": torch.cuda.ExternalStream(b.stream, device=local)})
+    for bi in range(NB):
+        g = list(range(bi, S, NB))[:per]
+        b = api.Batch(local, per, min(max_scan, 16384), 4096, prm)
+        b.enable_keyframes(int(KF * 9000 * (2.0 if sensor != "vlp16" else 1.0)), KF)
+        sd = [s % D for s in g]
+        dummy = api.to_pcl(np.zeros((16, 4), np.float32))    # placeholder map while the key-frames are collected
+        for s in range(per):
+            b.map_set_ds_pcl(s, dummy, dummy)
+        for k in range(KF):                                  # saveKeyFramesAndFactor's cloud part, MO:1443-1453
+            tab = tuple(P([kf32[d][k][j].ctypes.data for d in sd], [kf32[d][k][j].shape[0] for d in sd]) for j in range(3))
+            b.scan_set_all(*tab, dev=False)
+            b.register(np.zeros((per, 6), np.float32))       # (skipped by the guard MO:1331: only the DS clouds matter)
+            for s in range(per):
+                b.keyframe_add(s)
+        rng = np.random.default_rng(100 + 1000 * rank + bi)
+        init = [np.stack([synth.perturb_pose(np.asarray(seq[d][2][i][3], np.float64), rng) for d in sd]).astype(np.float32)
+                for i in range(NS)]
+        d_sw = [[tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in seq[d][2][i][:3]) for i in range(NS)] for d in sd]
+        tabs = {"host": [tuple(P([host32[d][i][j].ctypes.data for d in sd], [host32[d][i][j].shape[0] for d in sd]) for j in range(3))
+                         for i in range(NS)],
+                "dev": [tuple(P([d_sw[s][i][j].data_ptr() for s in range(per)], [d_sw[s][i][j].shape[0] for s in range(per)])
+                              for j in range(3)) for i in range(NS)]}
+        batches.append({"b": b, "g": g, "sd": sd, "tabs": tabs, "init": init, "keep": d_sw, "dummy": dummy,
+                        "asm": api.Batch.pack_assemble([ids] * per, [seq[d][0] for d in sd]),
+                        "stream": torch.cuda.ExternalStream(b.stream, device=local)})
+    # (kf32 stays alive: with pin_host_clouds the library page-locks the caller's buffers in place, and freed-but-registered
+    # memory handed out again by malloc breaks later copies)
+    torch.cuda.synchronize()
+    _log(f"set-up done: {D} sequences x ({KF} key-frames + {NS} sweeps), {NB} batches x {per} slots")
 
     def enqueue(bt, i, kind):
-        """one step of one batch: hand-over of every slot's sweep + DS map, then all registrations, asynchronously"""
-        b, tabs = bt["b"], bt["tabs"]
-        c, s_, o = tabs[kind + "_scan"][i % args.scans]
-        b.scan_set_all(c, s_, o, dev=(kind == "dev"))
-        mc, ms = tabs[kind + "_map"]
-        b.map_set_ds_all(mc, ms, dev=(kind == "dev"))        # index rebuilt every registration, like the kd-trees MO:1333-1334
-        b.register_async(tabs["T"][i % args.scans])
+        """one step of one batch: the new sweep of every slot, its local map from the resident key-frames, registration"""
+        b = bt["b"]
+        b.scan_set_all(*bt["tabs"][kind][i % NS], dev=(kind == "dev"))
+        b.map_assemble_all(bt["asm"])                        # resident key-frames -> raw map -> 2 voxel filters -> index
+        b.register_async(bt["init"][i % NS])
 
     def run_steps(kind, n):
         """n steps of every batch, software-pipelined from one host thread: while batch A computes, B is prepared"""
@@ -592,12 +721,13 @@ def main():
     if world > 1:
         dist.barrier()
     total_ms = max(e_start.elapsed_time(e) for e in e_ends)
+    _log(f"value arm done: {total_ms / K:.3f} ms per step")
 
-    # ---------------- roofline of the dominant kernels (kNN + fit of the LM iterations), timed with CUDA events on the
-    # batch stream during extra steps after the timed region (per-stage events perturb the pipelining)
+    # ---------------- stage times and the roofline of the registration kernel, with CUDA events on the batch stream
+    # during extra steps after the timed region (per-stage events perturb the pipelining)
     b0 = batches[0]
     b0["b"].set_profile(True)
-    prof_acc, geo, qi_acc, it_max_acc = {}, None, 0, 0
+    prof_acc, geo, qi_acc = {}, None, 0
     NPROF = 5
     for i in range(NPROF):
         enqueue(b0, i, "dev"); Tp, stp = b0["b"].result()
@@ -605,49 +735,13 @@ def main():
         for k, v in pr.items():
             prof_acc[k] = prof_acc.get(k, 0.0) + v / NPROF
         qi_acc += sum((x.n_corner_ds + x.n_surf_ds) * x.iterations for x in stp) / NPROF
-        it_max_acc += max(x.iterations for x in stp) / NPROF
     b0["b"].set_profile(False)
+    raw_n = [(int(b0["b"].map_get(s, 0).shape[0]), int(b0["b"].map_get(s, 1).shape[0])) for s in range(min(per, D))]
+    ds_n = [(int(b0["b"].map_get(s, 2).shape[0]), int(b0["b"].map_get(s, 3).shape[0])) for s in range(min(per, D))]
+    raw_c0, raw_s0 = b0["b"].map_get(0, 0), b0["b"].map_get(0, 1)
 
-    # ---------------- single-sequence latency (single-registration path, one persistent kernel), L2 flushed
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    lat_prm = api.default_params(); lat_prm.pin_host_clouds = 1   # one CTA per SM; host clouds DMA'd in place (long-lived members)
-    lat_ctx = api.Context(local, lat_prm)
-    lat_stream = torch.cuda.ExternalStream(lat_ctx.stream, device=local)
-    q0 = seqs[0]
-    d_T = torch.zeros(6, dtype=torch.float32, device=dev)
-    d_init = [torch.from_numpy(init.copy()).to(dev) for _, init in q0["scans"]]
-    lat, lat_host = [], []
-
-    def step_single(i):
-        c, s_, o = q0["d_scans"][i % args.scans]
-        with torch.cuda.stream(lat_stream):
-            d_T.copy_(d_init[i % args.scans], non_blocking=True)
-        lat_ctx.scan_set_dev(c.data_ptr(), c.shape[0], s_.data_ptr(), s_.shape[0], o.data_ptr(), o.shape[0])
-        lat_ctx.downsample_current_scan(want_counts=False)
-        lat_ctx.map_set_ds_dev(q0["d_mc"].data_ptr(), q0["d_mc"].shape[0], q0["d_ms"].data_ptr(), q0["d_ms"].shape[0])
-        lat_ctx.s2m_optimize_dev(d_T.data_ptr())
-
-    with torch.cuda.stream(lat_stream):
-        for i in range(W + 20):
-            flush.zero_()
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(lat_stream); step_single(i); b.record(lat_stream)
-            lat_stream.synchronize()
-            if i >= W:
-                lat.append(a.elapsed_time(b))
-        for i in range(W + 20):                              # the same through the C ABI with host clouds, wall clock
-            c, s_, o, init = q0["scans32"][i % args.scans]
-            flush.zero_(); lat_stream.synchronize()
-            t0 = time.perf_counter()
-            lat_ctx.scan_set_pcl(c, s_, o); lat_ctx.downsample_current_scan(want_counts=False)
-            lat_ctx.map_set_ds_pcl(q0["mc32"], q0["ms32"]); lat_ctx.s2m_optimize(init)
-            if i >= W:
-                lat_host.append((time.perf_counter() - t0) * 1e3)
-    del flush
-    lat_ctx.close()
-
-    # ---------------- end-to-end arm: host clouds through the C ABI, one host thread per batch (the H2D of one batch
-    # overlaps the kernels of the other)
+    # ---------------- end-to-end arm on every rank: host sweeps through the C ABI, one host thread per batch (the H2D
+    # and host work of one batch overlap the kernels of the other)
     barrier = threading.Barrier(NB + 1)
     last = {}
 
@@ -657,9 +751,16 @@ def main():
         for i in range(W):
             enqueue(bt, i, "host"); bt["b"].result()
         barrier.wait()
+        # the next sweeps are handed over while the current registrations run (the library packs them into one pinned block
+        # and sends it with one copy on its own stream): host packing and PCIe overlap the kernels of the step in flight
+        b = bt["b"]
+        b.scan_set_all(*bt["tabs"]["host"][0], dev=False)
         for i in range(K):
-            enqueue(bt, i, "host")
-            res = bt["b"].result()
+            b.map_assemble_all(bt["asm"])
+            b.register_async(bt["init"][i % NS])
+            if i + 1 < K:
+                b.scan_set_all(*bt["tabs"]["host"][(i + 1) % NS], dev=False)
+            res = b.result()
         if k == 0:
             last["T"], last["st"] = res
         barrier.wait()
@@ -678,24 +779,21 @@ def main():
     if world > 1:
         dist.barrier()
     stop_evt.set(); th.join()
-    mc_arm = None
-    if args.mapping_cycle and rank == 0:
-        try:
-            mc_arm = mapping_cycle_arm(api, local, 64, 2, args.key_frames, max(4, K // 2), 2, 4)
-        except Exception as e:                                # secondary arm: never hides the main line
-            mc_arm = {"error": repr(e)}
-    od_arm = None
-    if rank == 0:
-        try:
-            od_arm = odometry_arm(api, local, 20, 10)
-        except Exception as e:
-            od_arm = {"error": repr(e)}
-    fe_arm = None
-    if rank == 0:
-        try:
-            fe_arm = feature_extraction_arm(api, local, 20, 10)
-        except Exception as e:
-            fe_arm = {"error": repr(e)}
+    _log(f"e2e arm done: {e2e_s / K * 1e3:.3f} ms per step")
+    for bt in batches[1:]:
+        bt["b"].close()
+
+    sec = {}
+    if args.secondary and rank == 0:
+        for name, fn in (("registration_only", lambda: registration_only_arm(api, torch, local, args.workload, S, NB, min(D, 8), 2, min(K, 40), W)),
+                         ("latency", lambda: latency_arm(api, torch, local, args.workload, W)),
+                         ("odometry", lambda: odometry_arm(api, local, 20, 10)),
+                         ("feature_extraction", lambda: feature_extraction_arm(api, local, 20, 10))):
+            try:
+                sec[name] = fn()
+            except Exception as e:                            # secondary arms never hide the main line
+                sec[name] = {"error": repr(e)}
+            _log(f"secondary arm {name} done")
     if world > 1:
         dist.barrier()
 
@@ -707,92 +805,100 @@ def main():
     if rank == 0:
         ms_per_step = total_ms / K
         value = world * S * K / (total_ms / 1e3)
-        h2d_reg = [sum(a.nbytes for a in q["scans32"][0][:3]) + q["mc32"].nbytes + q["ms32"].nbytes + 24 for q in seqs]
+        h2d_step = int(sum(sum(a.nbytes for a in host32[d][0]) for bt in batches for d in bt["sd"]) + S * (KF * 28 + 24))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # K3+K4 of one LM iteration over all slots of a batch = one kNN launch + one fit launch
-        nb0 = len(b0["g"])
-        kern_ms = prof_acc["knn"] + prof_acc["fit"]
-        ms_launch = kern_ms / max(it_max_acc, 1e-9)
-        alg_bytes_launch = ALG_BYTES_PER_QUERY * qi_acc / max(it_max_acc, 1e-9)
-        achieved = ALG_BYTES_PER_QUERY * qi_acc / (kern_ms * 1e-3) / 1e9
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"
+        # registration kernel: ONE launch per step and batch covers every LM iteration of its slots
+        kern_ms = prof_acc["fit"] + prof_acc["knn"]
+        alg_bytes = ALG_BYTES_PER_QUERY * qi_acc
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
-        try:                                                 # dram bytes per launch pair from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_traffic.json")))
-            if args.workload == "vlp16_100k":
-                traffic = int(tj["dram_bytes_per_launch"] * nb0 / tj["slots"])
+        try:                                                 # dram bytes per launch from the committed ncu capture (same workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if args.workload == tj.get("workload"):
+                traffic = int(tj["dram_bytes_per_launch"] * per / tj["slots"])
         except Exception:
             pass
-        # bounded CPU sample on this box's host cores, 1 core; also the pose check of the e2e result
-        g0 = batches[0]["g"]
+        raw_tot = float(np.mean([a + b for a, b in raw_n])); ds_tot = float(np.mean([a + b for a, b in ds_n]))
+        stages = {
+            "index_build": {"algorithmic_bytes": 32.0 * ds_tot * per, "ms": prof_acc["index_build"],
+                            "what": "read + write re-ordered float4 of every DS map point (SURVEY 8(d)), 2 maps per slot"},
+            "map_assembly_and_voxel": {"algorithmic_bytes": (32.0 * raw_tot + 16.0 * (raw_tot + ds_tot)) * per, "ms": prof_acc["unpack"],
+                                       "what": "transform + concatenate the key-frame clouds (32 B per raw point), then 16 B per raw "
+                                               "point in and per DS point out of the two voxel filters"},
+        }
+        for v in stages.values():
+            v["achieved_gbs"] = v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None
+            v["frac"] = v["achieved_gbs"] / peak if v["achieved_gbs"] else None
+        # bounded CPU sample on this box's host cores, 1 core (the reference's statements for the same cycle, raw map of
+        # slot 0 as the device assembled it); also the pose check of the e2e result against the CPU
+        sd0 = b0["sd"]
         n_cpu = max(args.cpu_sample, 1)
-        run_cpu, kind = cpu_registration_factory(seqs[g0[0]]["mc_ds"], seqs[g0[0]]["ms_ds"], seqs[g0[0]]["scans"])
+        run_cpu, kind = cpu_cycle_factory(raw_c0, raw_s0, seq[sd0[0]][2], [b0["init"][i][0] for i in range(NS)])
         run_cpu(0)
         t0 = time.perf_counter()
         for i in range(n_cpu):
             run_cpu(i)
         cpu_s = time.perf_counter() - t0
         pose_diff = None
-        if "T" in last:                                      # every DISTINCT sequence of batch 0 against the CPU reference
+        if "T" in last:                                      # the distinct sequences of batch 0 against the CPU reference
             pose_diff = 0.0
-            for j, s in enumerate(g0[:D]):
-                rc, _ = cpu_registration_factory(seqs[s]["mc_ds"], seqs[s]["ms_ds"], seqs[s]["scans"])
+            for j in range(min(per, D, 4)):
+                rc, _ = cpu_cycle_factory(b0["b"].map_get(j, 0), b0["b"].map_get(j, 1), seq[sd0[j]][2], [b0["init"][i][j] for i in range(NS)])
                 pose_diff = max(pose_diff, float(np.max(np.abs(last["T"][j] - rc(K - 1)))))
         line = {
             "metric": "scan-to-map registrations/s", "value": value, "unit": "registrations/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {S} independent VLP-16 (16x1800) synthetic sequences per GPU, each "
-                                   f"sweep vs its own ~{map_pts}-pt voxel-DS local map; registration = "
-                                   f"downsampleCurrentScan + scan2MapOptimization (index build + <=10 LM iterations); "
-                                   f"step = one registration per sequence, batched engine ({NB} batches x {S // NB} slots)",
-                       "sequences_per_gpu": S, "batches": NB, "distinct_sequences": D,
-                       "registrations_per_step": S * world, "queries_per_registration": int(np.mean([x.n_corner_ds + x.n_surf_ds for x in stp])),
-                       "map_points": map_pts,
-                       "l2": f"no flush in the throughput arms: every slot has its own map, index and clouds, ~{ws_mb:.0f} MB "
-                             f"touched per step (> 126 MB L2); the latency arm flushes L2 (256 MiB write) before every registration",
-                       "timing": "CUDA events, first start to last end over the batch streams (host gaps included), max over ranks",
-                       "e2e_host_threads": NB, "pin_host_clouds": 1},
+            "config": {"workload": cycle_workload_text(args.workload, KF, int(raw_tot), int(ds_tot)) +
+                                   f"; step = one registration for each of {S} sequences per GPU, batched engine "
+                                   f"({NB} batches x {per} slots), key-frame clouds device-resident",
+                       "sequences_per_gpu": S, "batches": NB, "distinct_sequences": D, "sweeps_per_sequence": NS, "key_frames": KF,
+                       "registrations_per_step": S * world,
+                       "queries_per_registration": int(np.mean([x.n_corner_ds + x.n_surf_ds for x in stp])),
+                       "raw_map_points": int(raw_tot), "map_points": int(ds_tot),
+                       "l2": f"no flush: every slot has its own key-frames, raw map, DS map, index and sweeps, "
+                             f"~{S * (raw_tot * 48 + ds_tot * 64) / 1e6:.0f} MB touched per step (> 126 MB L2); the latency arm flushes "
+                             f"L2 (256 MiB write) before every registration",
+                       "timing": "value: CUDA events, first start to last end over the batch streams (host gaps included), max "
+                                 "over ranks; e2e: wall clock on every rank, max over ranks",
+                       "e2e_host_threads": NB, "pin_host_clouds": 0},
             "e2e": {"value": world * S * K / e2e_s, "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(sum(h2d_reg)), "d2h_bytes_per_step": int(72 * S),
-                    "ms_per_step": e2e_s / K * 1e3,
-                    "note": "scan AND voxel-DS map cross PCIe for every registration (the drop-in signature hands both over); "
-                            "PCIe-bound"},
-            "latency": {"ms_per_scan_device": float(np.median(lat)), "ms_per_scan_device_max": float(np.max(lat)),
-                        "ms_per_scan_e2e_host": float(np.median(lat_host)), "ms_per_scan_e2e_host_max": float(np.max(lat_host)),
-                        "note": "one sequence alone on the single-registration path (one persistent kernel, one CTA per SM), L2 "
-                                "flushed before each registration; e2e_host = host PCL clouds in (page-locked once, DMA in "
-                                "place), pose out, wall clock"},
+                    "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": int(72 * S),
+                    "ms_per_step": e2e_s / K * 1e3, "h2d_gbs_per_rank": h2d_step / (e2e_s / K) / 1e9,
+                    "note": "host sweeps (pcl::PointXYZI, 32 B per point) in, pose + stats out through the C ABI on every rank; "
+                            "the key-frame clouds are device-resident (each crossed PCIe once, as the sweep it was)"},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk_samples),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "traffic_source": "ncu --set full captures of both kernels, profiles/r01c_traffic.json (same workload)",
-                         "kernel": "batch_knn3_kernel + batch_fit_kernel (K3+K4 of one LM iteration over all slots of a batch)",
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "ms_per_launch": ms_launch, "alg_bytes_per_launch": alg_bytes_launch,
-                         "slots_per_launch": nb0, "stage_ms_per_step": prof_acc, "geometry": geo,
-                         "note": "instruction/latency-bound, not bandwidth-bound: ~1.8k thread instructions per query-iteration "
-                                 "for 96 algorithmic bytes (DESIGN.md section 3)"},
+                         "traffic_source": "ncu --set full capture of the kernel, profiles/r02_traffic.json (same workload)",
+                         "kernel": "batch_lm_kernel (kNN + line/plane fits + Jacobian rows + fp64 products + LM steps of ALL "
+                                   "iterations of a batch's slots: one launch per step and batch)",
+                         "peak_source": peak_src,
+                         "ms_per_launch": kern_ms, "alg_bytes_per_launch": alg_bytes,
+                         "slots_per_launch": per, "query_iterations_per_launch": qi_acc,
+                         "stage_ms_per_step": prof_acc, "geometry": geo,
+                         "note": "latency/issue-bound, not bandwidth-bound: ~5k warp instructions per 32 query-iterations for "
+                                 "3 kB of algorithmic bytes (DESIGN.md section 3, profiles/r02_knnfit.md)"},
+            "roofline_stages": stages,
             "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "registrations/s", "cores": 1, "kind": kind,
-                             "sample": f"{n_cpu} registrations of the same workload, 1 core",
+                             "sample": f"{n_cpu} mapping cycles of sequence 0 (same raw map, same sweeps), 1 core",
                              "ms_per_registration": cpu_s / n_cpu * 1e3},
             "wall_s_timed_region": t_wall,
             "last_stats": last["st"][0].as_dict() if "st" in last else None,
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
-            "mapping_cycle": mc_arm,
-            "odometry": od_arm,
-            "feature_extraction": fe_arm,
         }
+        line.update(sec)
         print(json.dumps(line))
+    b0["b"].close()
     if world > 1:
         dist.destroy_process_group()
-    for bt in batches:
-        bt["b"].close()
     return 0
 
 

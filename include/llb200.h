@@ -222,6 +222,7 @@ int llb_odom_optimize(llb_ctx *ctx, float T[6], llb_stats *stats_surf, llb_stats
  * skipped when it is < 10 (FA:1677) */
 int llb_odom_iterate(llb_ctx *ctx, int which, float T[6], int iter, int *more, int *n_correspondences);
 int llb_odom_get_correspondences(llb_ctx *ctx, llb_point *ori, llb_point *coeff, int capacity, int *n);
+/* which: 0 = surf (pointSearchSurfInd1 / 2 / 3, FA:148-152), 1 = corner (pointSearchCornerInd1 / 2; ind3 untouched) */
 int llb_odom_get_search_ind(llb_ctx *ctx, int which, float *ind1, float *ind2, float *ind3, int capacity, int *n);
 int llb_odom_get_degeneracy(llb_ctx *ctx, int *is_degenerate, float matP[9]);
 
@@ -321,6 +322,9 @@ int  llb_batch_enable_keyframes(llb_batch *b, int max_raw_map_points, int max_ke
 int  llb_batch_keyframe_add(llb_batch *b, int slot, int *id);
 int  llb_batch_keyframe_count(llb_batch *b, int slot, int *n);
 int  llb_batch_map_assemble(llb_batch *b, int slot, const int *ids, const float *poses, int n);
+/* the same for every slot with one call: slot s takes ids[offset[s] .. offset[s+1]) and the poses at the same positions
+ * (offset: n_slots + 1 entries, offset[0] = 0); slots with an empty range keep their map */
+int  llb_batch_map_assemble_all(llb_batch *b, const int *ids, const float *poses, const int *offset);
 /* which: 0 / 1 raw corner / surf map, 2 / 3 DS corner / surf map of the slot's last assembled map (parity checks) */
 int  llb_batch_map_get(llb_batch *b, int slot, int which, llb_point *out, int capacity, int *n);
 /* ---- feature extraction of the slots: llb_features_init / _extract / _get with one sweep per slot (segs[slots],

@@ -75,7 +75,7 @@ EXPORTS = [
     "llb_batch_launch_count", "llb_batch_scan_set", "llb_batch_map_set_ds", "llb_batch_scan_set_dev",
     "llb_batch_map_set_ds_dev", "llb_batch_scan_set_all", "llb_batch_map_set_ds_all", "llb_batch_scan_set_dev_all",
     "llb_batch_map_set_ds_dev_all", "llb_batch_register", "llb_batch_register_async", "llb_batch_result",
-    "llb_batch_enable_keyframes", "llb_batch_keyframe_add", "llb_batch_keyframe_count", "llb_batch_map_assemble",
+    "llb_batch_enable_keyframes", "llb_batch_keyframe_add", "llb_batch_keyframe_count", "llb_batch_map_assemble", "llb_batch_map_assemble_all",
     "llb_batch_map_get", "llb_batch_odom_set", "llb_batch_odom_optimize", "llb_batch_scan_get_ds", "llb_batch_get_degeneracy", "llb_batch_set_profile", "llb_batch_get_profile",
 ]
 
@@ -171,11 +171,18 @@ class Context:
             self._h = ctypes.c_void_p()
             raise LlbError(rc, "llb_create failed (no CPU fallback exists)")
         self.device = device
+        # converted host clouds of the convenience setters: the library may page-lock them in place (pin_host_clouds) and
+        # copy from them after the call has returned, so they live until the next cloud of the same kind replaces them
+        self._held = {}
+
+    def _hold(self, kind: str, arrays):
+        self._held[kind] = arrays
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             lib().llb_destroy(self._h)
             self._h = ctypes.c_void_p()
+        self._held = {}
 
     def __del__(self):
         try:
@@ -212,6 +219,7 @@ class Context:
     # ---- map
     def map_set_ds(self, corner_ds, surf_ds):
         c = to_pcl(corner_ds); s = to_pcl(surf_ds)
+        self._hold("map_ds", (c, s))
         self._ck(lib().llb_map_set_ds(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
 
     def map_set_ds_pcl(self, c32: np.ndarray, s32: np.ndarray):
@@ -219,6 +227,7 @@ class Context:
 
     def map_set_raw(self, corner, surf):
         c = to_pcl(corner); s = to_pcl(surf)
+        self._hold("map_raw", (c, s))
         self._ck(lib().llb_map_set_raw(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
 
     def map_set_raw_pcl(self, c32: np.ndarray, s32: np.ndarray):
@@ -269,6 +278,7 @@ class Context:
     # ---- scan
     def scan_set(self, corner_last, surf_last, outlier_last):
         c = to_pcl(corner_last); s = to_pcl(surf_last); o = to_pcl(outlier_last)
+        self._hold("scan", (c, s, o))                       # the library may page-lock / DMA from these after the call returns
         self.scan_set_pcl(c, s, o)
 
     def scan_set_pcl(self, c32, s32, o32):
@@ -344,6 +354,7 @@ class Context:
     # ---- odometry
     def odom_set_last(self, corner_last, surf_last):
         c = to_pcl(corner_last); s = to_pcl(surf_last)
+        self._hold("odom_last", (c, s))
         self._ck(lib().llb_odom_set_last(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
 
     # ---- feature extraction (FA:491-784)
@@ -386,6 +397,7 @@ class Context:
 
     def odom_set_features(self, sharp, flat):
         c = to_pcl(sharp); s = to_pcl(flat)
+        self._hold("odom_features", (c, s))
         self._ck(lib().llb_odom_set_features(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
 
     def odom_optimize(self, T):
@@ -618,6 +630,22 @@ class Batch:
         assert p.shape[0] == i.shape[0]
         self._ck(lib().llb_batch_map_assemble(self._h, slot, i.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(p),
                                               int(i.shape[0])))
+
+    @staticmethod
+    def pack_assemble(ids_per_slot, poses_per_slot):
+        """-> (ids, poses, offset) arrays for map_assemble_all (build once while the surrounding key-frames do not change)"""
+        off = np.zeros(len(ids_per_slot) + 1, np.int32)
+        off[1:] = np.cumsum([len(i) for i in ids_per_slot])
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(i, np.int32).reshape(-1) for i in ids_per_slot]), np.int32)
+        poses = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 6) for p in poses_per_slot]), np.float32)
+        assert poses.shape[0] == ids.shape[0]
+        return ids, poses, off
+
+    def map_assemble_all(self, packed):
+        ids, poses, off = packed
+        assert off.shape[0] == self.n_slots + 1
+        self._ck(lib().llb_batch_map_assemble_all(self._h, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(poses),
+                                                  off.ctypes.data_as(ctypes.POINTER(ctypes.c_int))))
 
     def map_get(self, slot: int, which: int) -> np.ndarray:
         n = ctypes.c_int(0)

@@ -89,7 +89,13 @@ struct llb_batch {
     int pending_unpack_max = 0;
     struct Reg { const void *p; size_t bytes; bool ours; };
     std::vector<Reg> regs;
-    std::vector<PinnedBuf<float>> stage;     // [B*5] lazily allocated staging (pin_host_clouds == 0)
+    std::vector<PinnedBuf<float>> stage;     // [B*5] lazily allocated staging (pin_host_clouds == 0: maps, odometry clouds)
+    // host sweeps with pin_host_clouds == 0: packed back to back into ONE pinned block per step (two alternate) and sent
+    // with ONE copy on its own stream - ~100 cudaMemcpyAsync calls per step cost 2.4 ms of host time (bench.py e2e)
+    PinnedBuf<unsigned char> up_pin[2]; DevBuf<unsigned char> up_dev[2];
+    size_t up_cap = 0, up_off = 0, up_sent = 0; int up_cur = 0;
+    cudaEvent_t up_ev[2] = {}; bool up_busy[2] = {};
+    cudaStream_t up_stream = nullptr;
     std::vector<cudaEvent_t> stage_ev; std::vector<char> stage_busy;
 
     // device-resident key-frame stores (llb_batch_enable_keyframes): per slot an arena of key-frame clouds, the assembled
@@ -103,7 +109,12 @@ struct llb_batch {
     DevBuf<int> ds_map_n;                    // [B][2]
     DevBuf<AsmSeg> seg_dev;
     PinnedBuf<AsmSeg> seg_pin[RING];
-    struct AsmReq { std::vector<int> ids; std::vector<float> poses; bool pending = false; int rc = 0, rs = 0; };
+    struct AsmReq {
+        std::vector<int> ids; std::vector<float> poses; bool pending = false; int rc = 0, rs = 0;
+        // the segment table of the last assembly: reused while the same key-frames are asked for with the same poses (the
+        // sin / cos of 6 angles per key-frame cloud are most of the host cost of a step with 100 key-frames per slot)
+        std::vector<int> c_ids; std::vector<float> c_poses; std::vector<AsmSeg> c_seg; size_t c_oc = 0, c_os = 0;
+    };
     std::vector<AsmReq> asm_req;
     std::vector<char> map_from_kf;           // the slot's current map is the assembled one (counts live on the device)
     std::vector<BatchCopy> pending_copy;
@@ -199,6 +210,42 @@ void upload(llb_batch *c, int stage_id, const llb_point *src, int n, float *raw_
     c->pending_unpack_max = std::max(c->pending_unpack_max, n);
 }
 
+// packed staging of a host sweep cloud (pin_host_clouds == 0); false = no room, take the per-cloud path
+bool upload_packed(llb_batch *c, const llb_point *src, int n, float4 *dst)
+{
+    if (n <= 0) return true;
+    if (!c->up_stream) {
+        c->up_cap = (size_t)c->B * 3 * c->cap_scan * sizeof(llb_point) + 256 * 3 * (size_t)c->B;
+        for (int k = 0; k < 2; k++) {
+            c->up_pin[k].ensure(c->up_cap); c->up_dev[k].ensure(c->up_cap);
+            LLB_CUDA(cudaEventCreateWithFlags(&c->up_ev[k], cudaEventDisableTiming));
+        }
+        LLB_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    }
+    const size_t bytes = (size_t)n * sizeof(llb_point);
+    if (c->up_off + bytes > c->up_cap) return false;
+    if (c->up_off == 0 && c->up_busy[c->up_cur]) {           // the copy that last read this pinned block (two steps ago)
+        LLB_CUDA(cudaEventSynchronize(c->up_ev[c->up_cur])); c->up_busy[c->up_cur] = false;
+    }
+    std::memcpy(c->up_pin[c->up_cur].p + c->up_off, src, bytes);
+    c->pending_unpack.push_back(BatchUnpack{ reinterpret_cast<const float *>(c->up_dev[c->up_cur].p + c->up_off), dst, n });
+    c->pending_unpack_max = std::max(c->pending_unpack_max, n);
+    c->up_off = (c->up_off + bytes + 255) & ~(size_t)255;
+    return true;
+}
+
+// sends what has been packed since the last call (one copy, own stream: it overlaps the kernels of a step in flight)
+void upload_flush(llb_batch *c)
+{
+    if (!c->up_stream || c->up_off <= c->up_sent) return;
+    const int k = c->up_cur;
+    LLB_CUDA(cudaMemcpyAsync(c->up_dev[k].p + c->up_sent, c->up_pin[k].p + c->up_sent, c->up_off - c->up_sent,
+                             cudaMemcpyHostToDevice, c->up_stream));
+    LLB_CUDA(cudaEventRecord(c->up_ev[k], c->up_stream));
+    c->up_busy[k] = true;
+    c->up_sent = c->up_off;
+}
+
 void prof_mark(llb_batch *c, int kind)
 {
     if (!c->profile || c->n_pev >= 64) return;
@@ -212,6 +259,8 @@ int enqueue_step(llb_batch *c, const float *T)
     const int B = c->B;
     for (int s = 0; s < B; s++)
         if (!c->slots[s].scan_set || !(c->slots[s].map_set || (c->kf_enabled && c->asm_req[s].pending))) return LLB_ERR_STATE;
+    // capacity of the step's job tables, checked BEFORE anything is consumed: a refused step leaves the batch as it was
+    if ((int)c->pending_unpack.size() > 5 * B || (int)c->pending_copy.size() > 3 * B) return LLB_ERR_STATE;
     // ---- build this step's tables in the next pinned block
     const int rp = c->ring_pos;
     c->ring_pos = (rp + 1) % RING;
@@ -257,18 +306,26 @@ int enqueue_step(llb_batch *c, const float *T)
             float4 *rawc = c->raw_map.p + (size_t)(2 * s) * c->cap_raw, *raws = rawc + c->cap_raw;
             float4 *dsc = c->ds_map.p + (size_t)(2 * s) * c->cap_raw, *dss = dsc + c->cap_raw;
             size_t oc = 0, os = 0;
-            for (size_t k = 0; k < rq.ids.size(); k++) {
-                const KeyFrameRec &kr = c->kfs[s].rec(rq.ids[k]);
-                const float *p = rq.poses.data() + 6 * k;
-                AsmSeg sg{};
-                sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]); sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
-                sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]); sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
-                sg.src = kr.cloud[0]; sg.n = kr.n[0]; sg.dst = rawc + oc; oc += kr.n[0];
-                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
-                sg.src = kr.cloud[1]; sg.n = kr.n[1]; sg.dst = raws + os; os += kr.n[1];
-                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
-                sg.src = kr.cloud[2]; sg.n = kr.n[2]; sg.dst = raws + os; os += kr.n[2];
-                if (sg.n > 0) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
+            if (rq.c_ids == rq.ids && rq.c_poses == rq.poses && !rq.c_seg.empty()) {
+                for (const AsmSeg &sg : rq.c_seg) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); }
+                oc = rq.c_oc; os = rq.c_os;
+            } else {
+                rq.c_seg.clear();
+                auto put = [&](const AsmSeg &sg) { h_seg[nseg++] = sg; seg_max = std::max(seg_max, sg.n); rq.c_seg.push_back(sg); };
+                for (size_t k = 0; k < rq.ids.size(); k++) {
+                    const KeyFrameRec &kr = c->kfs[s].rec(rq.ids[k]);
+                    const float *p = rq.poses.data() + 6 * k;
+                    AsmSeg sg{};
+                    sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]); sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
+                    sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]); sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
+                    sg.src = kr.cloud[0]; sg.n = kr.n[0]; sg.dst = rawc + oc; oc += kr.n[0];
+                    if (sg.n > 0) put(sg);
+                    sg.src = kr.cloud[1]; sg.n = kr.n[1]; sg.dst = raws + os; os += kr.n[1];
+                    if (sg.n > 0) put(sg);
+                    sg.src = kr.cloud[2]; sg.n = kr.n[2]; sg.dst = raws + os; os += kr.n[2];
+                    if (sg.n > 0) put(sg);
+                }
+                rq.c_ids = rq.ids; rq.c_poses = rq.poses; rq.c_oc = oc; rq.c_os = os;
             }
             VoxelInput vc; vc.a = rawc; vc.na = (int)oc;
             VoxelInput vs; vs.a = raws; vs.na = (int)os;
@@ -303,14 +360,12 @@ int enqueue_step(llb_batch *c, const float *T)
     // shared-memory capacity of the two voxel launches: this step's largest filter, rounded to 1024 points
     c->vox_cap1 = (vmax1 + 1023) & ~1023; c->vox_cap2 = (vmax2 + 1023) & ~1023;
     const int nunp = (int)c->pending_unpack.size();
-    if (nunp > 5 * B) return LLB_ERR_STATE;
     for (int i = 0; i < nunp; i++) h_unp[i] = c->pending_unpack[i];
     // launch-geometry upper bounds are rounded up so that steps of similar size share one captured graph
     auto round_up = [](int v, int g) { return (v + g - 1) / g * g; };
     const int unp_max = round_up(c->pending_unpack_max, 2048);
     c->pending_unpack.clear(); c->pending_unpack_max = 0;
     const int ncopy = (int)c->pending_copy.size();
-    if (ncopy > 3 * B) return LLB_ERR_STATE;
     for (int i = 0; i < ncopy; i++) h_copy[i] = c->pending_copy[i];
     const int copy_max = round_up(c->pending_copy_max, 2048);
     c->pending_copy.clear(); c->pending_copy_max = 0;
@@ -320,13 +375,18 @@ int enqueue_step(llb_batch *c, const float *T)
 
     // ---- enqueue
     c->n_pev = 0;
+    if (c->up_stream && c->up_off > 0) {                     // packed host sweeps of this step: sent (if not yet), then awaited
+        upload_flush(c);
+        LLB_CUDA(cudaStreamWaitEvent(c->stream, c->up_ev[c->up_cur], 0));
+        c->up_cur ^= 1; c->up_off = 0; c->up_sent = 0;
+    }
     LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
     prof_mark(c, -1);
     LLB_CUDA(cudaMemcpyAsync(dp, hp, L.bytes, cudaMemcpyHostToDevice, c->stream));
-    LLB_CUDA(cudaEventRecord(c->step_ev[rp], c->stream));
-    c->step_busy[rp] = true;
     if (nseg > 0)
         LLB_CUDA(cudaMemcpyAsync(c->seg_dev.p, h_seg, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
+    LLB_CUDA(cudaEventRecord(c->step_ev[rp], c->stream));    // after the LAST copy that reads ring slot rp (step block + segments)
+    c->step_busy[rp] = true;
     // every kernel launch of the step; all arguments are device-resident tables or the counts of `sig`
     auto enqueue_kernels = [&]() -> long long {
         long long nl = 0;
@@ -546,6 +606,8 @@ int llb_batch_destroy(llb_batch *c)
         c->iter_prof.release();
     }
     for (auto &r : c->regs) if (r.ours) cudaHostUnregister(const_cast<void *>(r.p));
+    for (int k = 0; k < 2; k++) { c->up_pin[k].release(); c->up_dev[k].release(); if (c->up_ev[k]) cudaEventDestroy(c->up_ev[k]); }
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
     c->features.release();
     c->scan_in.release(); c->scan_raw.release(); c->scan_ds.release(); c->map_in.release(); c->map_raw.release();
     c->ds_n.release(); c->states.release(); c->qperm.release(); c->partials.release(); c->qprev.release(); c->queue.release(); c->slot_info.release(); c->ctl.release();
@@ -592,7 +654,8 @@ int llb_batch_scan_set(llb_batch *c, int slot, const llb_point *corner, int nc, 
         llb_batch::Slot &sl = c->slots[slot];
         for (int k = 0; k < 3; k++) {
             float4 *dst = c->scan_in.p + ((size_t)slot * 3 + k) * c->cap_scan;
-            upload(c, slot * 5 + k, src[k], n[k], c->scan_raw.p + ((size_t)slot * 3 + k) * c->cap_scan * 8, dst);
+            if (c->prm.pin_host_clouds || !upload_packed(c, src[k], n[k], dst))
+                upload(c, slot * 5 + k, src[k], n[k], c->scan_raw.p + ((size_t)slot * 3 + k) * c->cap_scan * 8, dst);
             sl.scan[k] = dst; sl.scan_n[k] = n[k];
         }
         sl.scan_set = true;
@@ -658,7 +721,7 @@ int llb_batch_scan_set_all(llb_batch *c, const llb_point *const *corner, const i
         const int rc = llb_batch_scan_set(c, s, corner[s], nc[s], surf[s], ns[s], outlier[s], no[s]);
         if (rc != LLB_OK) return rc;
     }
-    return LLB_OK;
+    return guarded(c, [&]() { upload_flush(c); return (int)LLB_OK; });   // the sweeps start crossing PCIe now
 }
 
 int llb_batch_map_set_ds_all(llb_batch *c, const llb_point *const *corner_ds, const int *mc, const llb_point *const *surf_ds,
@@ -817,6 +880,19 @@ int llb_batch_map_assemble(llb_batch *c, int slot, const int *ids, const float *
         rq.rc = (int)rc; rq.rs = (int)rs; rq.pending = true;
         return (int)LLB_OK;
     });
+}
+
+int llb_batch_map_assemble_all(llb_batch *c, const int *ids, const float *poses, const int *offset)
+{
+    if (!c || !ids || !poses || !offset) return LLB_ERR_INVALID;
+    for (int s = 0; s < c->B; s++) {
+        const int n = offset[s + 1] - offset[s];
+        if (n < 0) return LLB_ERR_INVALID;
+        if (n == 0) continue;
+        const int rc = llb_batch_map_assemble(c, s, ids + offset[s], poses + 6 * (size_t)offset[s], n);
+        if (rc != LLB_OK) return rc;
+    }
+    return LLB_OK;
 }
 
 // which: 0 raw corner map, 1 raw surf map, 2 DS corner map, 3 DS surf map of the slot's last assembled map

@@ -1273,7 +1273,7 @@ int llb_odom_get_search_ind(llb_ctx *c, int which, float *i1, float *i2, float *
         if (!i1 || !i2) return (int)LLB_OK;
         if ((int)a.size() > cap) return (int)LLB_ERR_CAPACITY;
         std::copy(a.begin(), a.end(), i1); std::copy(b.begin(), b.end(), i2);
-        if (i3 && which == 1) std::copy(d.begin(), d.end(), i3);
+        if (i3 && which == 0) std::copy(d.begin(), d.end(), i3);
         return (int)LLB_OK;
     });
 }

@@ -336,7 +336,7 @@ __device__ __forceinline__ void odom_body(const OdomParams &prm, const OdomData 
                         else nn1_warp(last, nlast, x0, y0, z0, lane, d1, closest);
                         float bd[2] = { prm.nearest_sqdist, prm.nearest_sqdist };
                         int bj[2] = { -1, -1 };
-                        if (d1 < prm.nearest_sqdist) {
+                        if (d1 < prm.nearest_sqdist && closest < nlast) {         // (closest >= nlast: stale index, C20)
                             const int closestScan = (int)__ldg(&last[closest]).w;
                             if (which == 0) {
                                 window_scan<true>(last, closest + 1, +1, 0, fwdEnd, closestScan, x0, y0, z0, lane, bd, bj);
@@ -565,7 +565,13 @@ int OdomSolver::set_last(int ncl, int nsl, cudaStream_t s)
     // (first call: the tables are zeroed on the same stream the build runs on - on the default stream the build on a
     // non-blocking stream raced with them: an intermittently wrong first index, seen as a flaky first odometry test)
     if (!grids_init_) { gridCorner_.init(1 << 18, s); gridSurf_.init(1 << 18, s); grids_init_ = true; }
-    if (ncl <= 0 || nsl <= 0) { grids_built_ = false; return 0; }
+    // Quirk C20: the reference rebuilds its two kd-trees only when the new clouds have MORE than 10 / 100 points
+    // (FA:1785-1788) while updateTransformation runs from 10 / 100 points on (FA:1668): with exactly 10 corner or 100
+    // surf points (or a smaller cloud on the other side) the next matcher searches the PREVIOUS sweep's trees - which
+    // hold their own copy of that sweep's points - and uses the returned indices in the NEW clouds.  The grid indices
+    // keep a copy of their points too, so "do not rebuild" reproduces it; an index that points beyond the new cloud
+    // (undefined behaviour in the reference) counts as "no neighbour" in the kernel.
+    if (!(ncl > 10 && nsl > 100)) return 0;
     const int n = GridIndex::build_pair(gridCorner_, cornerLast_.p, nullptr, ncl, gridSurf_, surfLast_.p, nullptr, nsl,
                                         std::sqrt(prm_.nearest_sqdist), s);
     grids_built_ = true;
@@ -646,14 +652,15 @@ void OdomSolver::download_correspondences(std::vector<float4> &ori, std::vector<
 void OdomSolver::download_search_ind(int which, std::vector<float> &i1, std::vector<float> &i2, std::vector<float> &i3,
                                      cudaStream_t s)
 {
-    const int n = which == 0 ? nsharp_ : nflat_;
+    // which: 0 = surf (pointSearchSurfInd1/2/3), 1 = corner (pointSearchCornerInd1/2), as everywhere else in the C ABI
+    const int n = which == 0 ? nflat_ : nsharp_;
     i1.assign(n, -1.f); i2.assign(n, -1.f); i3.assign(n, -1.f);
     if (n <= 0) return;
-    const float *b1 = which == 0 ? ind_.p : ind_.p + 2 * cap_;
-    const float *b2 = which == 0 ? ind_.p + cap_ : ind_.p + 3 * cap_;
+    const float *b1 = which == 0 ? ind_.p + 2 * cap_ : ind_.p;
+    const float *b2 = which == 0 ? ind_.p + 3 * cap_ : ind_.p + cap_;
     LLB_CUDA(cudaMemcpyAsync(i1.data(), b1, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
     LLB_CUDA(cudaMemcpyAsync(i2.data(), b2, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-    if (which == 1) LLB_CUDA(cudaMemcpyAsync(i3.data(), ind_.p + 4 * cap_, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    if (which == 0) LLB_CUDA(cudaMemcpyAsync(i3.data(), ind_.p + 4 * cap_, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
     LLB_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -136,6 +136,9 @@ public:
     void surfOptimization(int /*iterCount*/) { staged_ |= 2; }      // MO:1176
     bool LMOptimization(int iterCount)                              // MO:1229, returns true when converged
     {
+        // the device iteration is the fusion of the three reference calls: it needs BOTH searches staged (the reference
+        // order MO:1339-1343); laserCloudOri / coeffSel are filled here, not by the two stagers
+        if (staged_ != 3) { staged_ = 0; last_status = LLB_ERR_STATE; return false; }
         staged_ = 0;
         if (!ensure_map()) return false;
         int conv = 0, n = 0;
@@ -249,7 +252,11 @@ public:
     FeatureAssociation &operator=(const FeatureAssociation &) = delete;
 
     // N_SCAN / Horizon_SCAN of the sensor (UT:63-84); allocates the per-point state FA:210-223 on the device
-    void initFeatureExtraction(int n_scan, int horizon_scan) { last_status = llb_features_init(ctx_, n_scan, horizon_scan); }
+    void initFeatureExtraction(int n_scan, int horizon_scan)
+    {
+        last_status = llb_features_init(ctx_, n_scan, horizon_scan);
+        n_scan_ = last_status == LLB_OK ? n_scan : 0;
+    }
     // runFeatureAssociation FA:1827-1833: the four steps run as one device pass when extractFeatures() is reached
     void adjustDistortion() { fe_staged_ |= 1; }                   // FA:491 (no IMU data: imuPointerLast < 0)
     void calculateSmoothness() { fe_staged_ |= 2; }                // FA:621
@@ -258,6 +265,11 @@ public:
     {
         if (fe_staged_ != 7) { last_status = LLB_ERR_STATE; return; }
         fe_staged_ = 0;
+        // the library reads n_scan ring bounds and one flag / column / range per point: refuse short vectors here
+        const size_t np = segmentedCloud->size();
+        if (n_scan_ <= 0 || (int)segInfo.startRingIndex.size() < n_scan_ || (int)segInfo.endRingIndex.size() < n_scan_ ||
+            segInfo.segmentedCloudGroundFlag.size() < np || segInfo.segmentedCloudColInd.size() < np ||
+            segInfo.segmentedCloudRange.size() < np) { last_status = LLB_ERR_INVALID; return; }
         llb_segmented_cloud seg;
         seg.cloud = as_llb(*segmentedCloud); seg.n = (int)segmentedCloud->size();
         seg.start_ring = segInfo.startRingIndex.data(); seg.end_ring = segInfo.endRingIndex.data();
@@ -276,6 +288,7 @@ public:
             if (n > 0) last_status = llb_features_get(ctx_, k, as_llb(*out[k]), n, &n);
         }
         features_on_device_ = true;
+        features_pushed_ = false;
     }
 
     // cloud part of publishCloudsLast (FA:1759-1788): TransformToEnd of the less-sharp / less-flat clouds with transformCur,
@@ -303,6 +316,8 @@ public:
                                         as_llb(*laserCloudSurfLast), laserCloudSurfLastNum);
     }
 
+    // call when cornerPointsSharp / surfPointsFlat were (re)filled on the host by the caller
+    void featuresChanged() { features_pushed_ = false; features_on_device_ = false; }
     void findCorrespondingSurfFeatures(int iterCount) { staged_which_ = 0; staged_iter_ = iterCount; push_features(); }     // FA:1155
     void findCorrespondingCornerFeatures(int iterCount) { staged_which_ = 1; staged_iter_ = iterCount; push_features(); }   // FA:1044
     // return value as in the reference: FALSE when converged (C8)
@@ -312,6 +327,7 @@ public:
     void updateTransformation()                                                          // FA:1666
     {
         if (laserCloudCornerLastNum < 10 || laserCloudSurfLastNum < 100) return;
+        features_pushed_ = false;                            // one call per sweep: the members are (re)sent
         push_features();
         last_status = llb_odom_optimize(ctx_, transformCur, &stats_surf, &stats_corner);
         if (last_status != LLB_OK) return;
@@ -321,17 +337,19 @@ public:
     llb_ctx *context() { return ctx_; }
 
 private:
-    void push_features()
+    void push_features()                 // once per sweep: the step-wise calls (<= 50 per sweep) do not upload again
     {
-        if (features_on_device_) { last_status = llb_features_to_odometry(ctx_); features_on_device_ = false; return; }
-        last_status = llb_odom_set_features(ctx_, as_llb(*cornerPointsSharp), (int)cornerPointsSharp->size(),
-                                            as_llb(*surfPointsFlat), (int)surfPointsFlat->size());
+        if (features_pushed_) return;
+        if (features_on_device_) { last_status = llb_features_to_odometry(ctx_); features_on_device_ = false; }
+        else last_status = llb_odom_set_features(ctx_, as_llb(*cornerPointsSharp), (int)cornerPointsSharp->size(),
+                                                 as_llb(*surfPointsFlat), (int)surfPointsFlat->size());
+        features_pushed_ = last_status == LLB_OK;
     }
     bool step(int which, int iterCount)
     {
         int more = 1, n = 0;
         last_status = llb_odom_iterate(ctx_, which, transformCur, iterCount, &more, &n);
-        if (last_status != LLB_OK) return true;
+        if (last_status != LLB_OK) return false;             // a dead context must end the caller's loop, not spin it
         int m = 0;
         if (llb_odom_get_correspondences(ctx_, nullptr, nullptr, 0, &m) == LLB_OK) {
             laserCloudOri->resize(m); coeffSel->resize(m);
@@ -343,7 +361,8 @@ private:
     }
     llb_ctx *ctx_ = nullptr;
     int staged_which_ = 0, staged_iter_ = 0;
-    int fe_staged_ = 0;
+    int fe_staged_ = 0, n_scan_ = 0;
+    bool features_pushed_ = false;      // cornerPointsSharp / surfPointsFlat of this sweep are in the odometry's buffers
     bool features_on_device_ = false;   // cornerPointsSharp / surfPointsFlat of the last extractFeatures() are still on the device
 };
 

@@ -329,7 +329,7 @@ def test_odometry_single_steps_bitexact(ctx, seed):
             more_ref = calc(it) if ori_r.shape[0] >= 10 else True
             T_gpu, more, n_corr = ctx.odom_iterate(which, T, it)
             i1r, i2r, i3r = fa.search_ind(1 - which)          # oracle: 0 corner, 1 surf
-            i1g, i2g, i3g = ctx.odom_get_search_ind(1 - which)
+            i1g, i2g, i3g = ctx.odom_get_search_ind(which)        # C ABI: 0 surf, 1 corner
             assert np.array_equal(i1r, i1g) and np.array_equal(i2r, i2g)
             if which == 0:
                 assert np.array_equal(i3r, i3g)
@@ -365,6 +365,49 @@ def test_odometry_update_transformation_parity(ctx, seed):
         rfa.transformCur = np.zeros(6, np.float32)
         rfa.updateTransformation()
         assert np.array_equal(T.view(np.uint32), rfa.transformCur.view(np.uint32)), (T, rfa.transformCur)
+
+
+def test_odometry_stale_trees_quirk_c20(ctx):
+    """C20 (FA:1668 vs FA:1785): with exactly 10 corner points in the new last-sweep cloud updateTransformation still
+    runs (>= 10 / >= 100) but the kd-trees were NOT rebuilt (> 10 / > 100): the 1-NN search runs in the PREVIOUS sweep's
+    trees and its indices are used in the NEW clouds.  Constructed so that every stale index stays inside the new
+    clouds (anything else is undefined behaviour in the reference): previous corner cloud = 10 real points + 1 far-away
+    point, new corner cloud = 10 other points; the new surf cloud is at least as long as the previous one."""
+    od_a, od_b = _odom_case(4), _odom_case(5)
+    corner_a = np.vstack([od_a.corner_last[:10], np.array([[900.0, 900.0, 900.0, 3.0]], np.float32)]).astype(np.float32)
+    surf_a, surf_b = od_a.surf_last, od_b.surf_last
+    n = min(surf_a.shape[0], surf_b.shape[0])
+    surf_a = np.ascontiguousarray(surf_a[:n]); surf_b = np.ascontiguousarray(surf_b)      # |surf_b| >= |surf_a|
+    corner_b = np.ascontiguousarray(od_a.corner_last[10:20] + np.float32(0.01))            # exactly 10 points
+    oracle.set_trig_mode(0)
+    fa = oracle.FeatureAssociation()
+    fa.set_last(corner_a, surf_a)                       # 11 / n points: trees built (FA:1785)
+    fa.set_last(corner_b, surf_b)                       # 10 corner points: trees stay those of sweep A
+    fa.set_features(od_a.corner_sharp, od_a.surf_flat)
+    fa.transformCur = np.zeros(6, np.float32)
+    it1, it2 = fa.updateTransformation()
+    ctx.odom_set_last(corner_a, surf_a)
+    ctx.odom_set_last(corner_b, surf_b)
+    ctx.odom_set_features(od_a.corner_sharp, od_a.surf_flat)
+    T, s0, s1 = ctx.odom_optimize(np.zeros(6, np.float32))
+    assert s0.skipped == 0 and (s0.iterations, s1.iterations) == (it1, it2)
+    assert np.array_equal(T.view(np.uint32), np.asarray(fa.transformCur, np.float32).view(np.uint32)), (T, fa.transformCur)
+    # and it is NOT what fresh trees give (the quirk is observable)
+    fa2 = oracle.FeatureAssociation()
+    fa2.set_last(corner_b, surf_b, force=True)
+    fa2.set_features(od_a.corner_sharp, od_a.surf_flat)
+    fa2.transformCur = np.zeros(6, np.float32)
+    fa2.updateTransformation()
+    assert not np.array_equal(np.asarray(fa2.transformCur, np.float32), T)
+    from oracle import ref_harness as rh
+    if rh.available():                                       # the compiled reference itself
+        rfa = rh.FeatureAssociation()
+        rfa.set_last(corner_a, surf_a); rfa.set_last(corner_b, surf_b)
+        rfa.set_features(od_a.corner_sharp, od_a.surf_flat)
+        rfa.transformCur = np.zeros(6, np.float32)
+        rfa.updateTransformation()
+        assert np.array_equal(T.view(np.uint32), rfa.transformCur.view(np.uint32)), (T, rfa.transformCur)
+    ctx.odom_set_last(od_a.corner_last, od_a.surf_last)      # leave the shared context with fresh indices
 
 
 def test_odometry_guard(ctx):
