@@ -265,6 +265,30 @@ int llb_s2m_get_profile(llb_ctx *ctx, int iter, long long stamps[8]);
  * last run: out[4*cta + k]; *n_ctas receives the grid size (diagnostics for profiles/) */
 int llb_s2m_get_cta_profile(llb_ctx *ctx, double *out, int capacity_ctas, int *n_ctas);
 
+/* ---- imageProjection on the device (IP = LeGO-LOAM/src/imageProjection.cpp) ----
+ * llb_projection_init: the sensor block of utility.h (UT:62-84): N_SCAN, Horizon_SCAN, ang_res_x, ang_res_y,
+ * groundScanInd.  llb_projection_process replaces cloudHandler IP:181-197 without the publishing: findStartEndAngle
+ * (IP:199-211), projectPointCloud (IP:213-257, useCloudRing: the row of a point is its ring), groundRemoval
+ * (IP:259-310), cloudSegmentation (IP:312-368) with labelComponents (IP:370-448) as connected-component labelling.
+ * cloud: the sweep in firing order without NaN points (IP:170), pcl::PointXYZI layout; ring: its ring channel.
+ * Results stay on the device: llb_projection_get_* copy them out (segmentedCloud + cloud_msgs::cloud_info fields,
+ * outlierCloud, the three images for parity checks), llb_projection_to_features hands them to the feature extraction
+ * (llb_features_init with the same N_SCAN / Horizon_SCAN) without leaving the device: raw sweep -> features with one
+ * upload per sweep. */
+int llb_projection_init(llb_ctx *ctx, int n_scan, int horizon_scan, float ang_res_x, float ang_res_y, int ground_scan_ind);
+int llb_projection_process(llb_ctx *ctx, const llb_point *cloud, const uint16_t *ring, int n, int *n_segmented,
+                           int *n_outlier, float *device_ms /* may be NULL */);
+/* which: 0 segmentedCloud, 1 outlierCloud */
+int llb_projection_get_cloud(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+/* cloud_info of the last sweep: start / end ring index (N_SCAN each), {startOrientation, endOrientation,
+ * orientationDiff}, per segmented point: ground flag, column index, range (capacity entries each; any may be NULL) */
+int llb_projection_get_info(llb_ctx *ctx, int32_t *start_ring, int32_t *end_ring, float orientation[3],
+                            uint8_t *ground_flag, uint32_t *col_ind, float *range, int capacity);
+/* rangeMat (FLT_MAX: no return), groundMat, labelMat of the last sweep, N_SCAN x Horizon_SCAN each (parity checks) */
+int llb_projection_get_images(llb_ctx *ctx, float *range_mat, int8_t *ground_mat, int32_t *label_mat);
+/* adjustDistortion .. extractFeatures (llb_features_extract) on the segmented cloud of the last llb_projection_process */
+int llb_projection_to_features(llb_ctx *ctx, int counts[4], float *device_ms /* may be NULL */);
+
 /* number of kernels launched by this context since creation (bench.py gpu_launches) */
 long long llb_launch_count(const llb_ctx *ctx);
 

@@ -68,6 +68,8 @@ EXPORTS = [
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
     "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
+    "llb_projection_init", "llb_projection_process", "llb_projection_get_cloud", "llb_projection_get_info",
+    "llb_projection_get_images", "llb_projection_to_features",
     "llb_batch_features_init", "llb_batch_features_extract", "llb_batch_features_get",
     "llb_keyframe_add", "llb_keyframe_add_clouds", "llb_keyframe_count", "llb_keyframe_clear", "llb_map_assemble",
     "llb_map_get_raw",
@@ -356,6 +358,51 @@ class Context:
         c = to_pcl(corner_last); s = to_pcl(surf_last)
         self._hold("odom_last", (c, s))
         self._ck(lib().llb_odom_set_last(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0]))
+
+    # ---- imageProjection (IP:181-460)
+    def projection_init(self, n_scan: int, horizon_scan: int, ang_res_x: float, ang_res_y: float, ground_scan_ind: int):
+        self._ip_shape = (int(n_scan), int(horizon_scan))
+        self._ck(lib().llb_projection_init(self._h, int(n_scan), int(horizon_scan), ctypes.c_float(ang_res_x),
+                                           ctypes.c_float(ang_res_y), int(ground_scan_ind)))
+
+    def projection_process(self, cloud, ring):
+        """cloud (n, 4) in firing order, ring (n,) uint16 -> (n_segmented, n_outlier, device ms)"""
+        c32 = to_pcl(cloud); rg = np.ascontiguousarray(ring, np.uint16)
+        assert rg.shape[0] == c32.shape[0]
+        ns = ctypes.c_int(0); no = ctypes.c_int(0); ms = ctypes.c_float(0)
+        self._ck(lib().llb_projection_process(self._h, _vp(c32), rg.ctypes.data_as(ctypes.c_void_p), c32.shape[0],
+                                              ctypes.byref(ns), ctypes.byref(no), ctypes.byref(ms)))
+        return ns.value, no.value, ms.value
+
+    def projection_get_cloud(self, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_projection_get_cloud(self._h, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_projection_get_cloud(self._h, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    def projection_get_sweep(self):
+        """-> lego_loam_b200.synth.SegmentedSweep of the last projection_process (segmentedCloud + cloud_info + outliers)"""
+        from . import synth
+        seg = self.projection_get_cloud(0); out = self.projection_get_cloud(1)
+        n = seg.shape[0]; N = self._ip_shape[0]
+        sr = np.zeros(N, np.int32); er = np.zeros(N, np.int32); ori = np.zeros(3, np.float32)
+        g = np.zeros(max(n, 1), np.uint8); col = np.zeros(max(n, 1), np.uint32); r = np.zeros(max(n, 1), np.float32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self._ck(lib().llb_projection_get_info(self._h, vp(sr), vp(er), _fp(ori), vp(g), vp(col), _fp(r), max(n, 1)))
+        return synth.SegmentedSweep(seg, sr, er, float(ori[0]), float(ori[1]), float(ori[2]), g[:n], col[:n], r[:n], out)
+
+    def projection_get_images(self):
+        N, H = self._ip_shape
+        rm = np.zeros((N, H), np.float32); gm = np.zeros((N, H), np.int8); lm = np.zeros((N, H), np.int32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self._ck(lib().llb_projection_get_images(self._h, _fp(rm), vp(gm), vp(lm)))
+        return rm, gm, lm
+
+    def projection_to_features(self):
+        cnt = (ctypes.c_int * 4)(); ms = ctypes.c_float(0)
+        self._ck(lib().llb_projection_to_features(self._h, cnt, ctypes.byref(ms)))
+        return list(cnt), ms.value
 
     # ---- feature extraction (FA:491-784)
     def features_init(self, n_scan: int, horizon_scan: int):

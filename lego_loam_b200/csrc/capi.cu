@@ -10,6 +10,7 @@
 #include "odom.cuh"
 #include "keyframes.cuh"
 #include "features.cuh"
+#include "projection.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -91,6 +92,8 @@ struct llb_ctx {
 
     OdomSolver odom;
     FeatureExtractor features;
+    ImageProjector projection;
+    bool projection_done = false;
     bool features_done = false;
     float features_ms = 0.f;
     int features_last_n[2] = { -1, -1 };   // sizes of laserCloudCornerLast / laserCloudSurfLast set by llb_features_publish_last
@@ -405,6 +408,7 @@ int llb_destroy(llb_ctx *c)
     for (int r = 0; r < S2M_MAX_PEERS; r++) if (c->p2p_opened[r]) cudaIpcCloseMemHandle(c->p2p_opened[r]);
     if (c->p2p_mem) cudaFree(c->p2p_mem);
     c->features.release();
+    c->projection.release();
     c->kfs.release(); c->asmCorner.release(); c->asmSurf.release(); c->asm_segs.release(); c->pin_segs.release();
     if (c->asm_ev) cudaEventDestroy(c->asm_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1087,6 +1091,108 @@ int llb_odom_set_features(llb_ctx *c, const llb_point *sharp, int nsharp, const 
         upload_cloud(c, 0, sharp, nsharp, c->odom.sharp());
         upload_cloud(c, 1, flat, nflat, c->odom.flat());
         c->odom.set_features(nsharp, nflat);
+        return (int)LLB_OK;
+    });
+}
+
+// ---------------------------------------------------------------- imageProjection
+int llb_projection_init(llb_ctx *c, int n_scan, int horizon_scan, float ang_res_x, float ang_res_y, int ground_scan_ind)
+{
+    return guarded(c, [&]() {
+        if (n_scan <= 0 || n_scan > FE_MAX_RINGS || horizon_scan < 16 || horizon_scan > 4096 || !(ang_res_x > 0.f) || !(ang_res_y > 0.f) ||
+            ground_scan_ind < 0 || ground_scan_ind >= n_scan) return (int)LLB_ERR_INVALID;
+        c->projection.init(n_scan, horizon_scan, ang_res_x, ang_res_y, ground_scan_ind, c->stream);
+        c->projection_done = false;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_projection_process(llb_ctx *c, const llb_point *cloud, const uint16_t *ring, int n, int *n_seg, int *n_out, float *device_ms)
+{
+    return guarded(c, [&]() {
+        if (n < 0 || (n > 0 && (!cloud || !ring))) return (int)LLB_ERR_INVALID;
+        if (!c->projection.ready()) return (int)LLB_ERR_STATE;
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->projection.process(reinterpret_cast<const float *>(cloud), ring, n, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        c->projection_done = true;
+        if (n_seg) *n_seg = c->projection.header().n_seg;
+        if (n_out) *n_out = c->projection.header().n_outlier;
+        if (device_ms) LLB_CUDA(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_projection_get_cloud(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 1) return (int)LLB_ERR_INVALID;
+        if (!c->projection_done) return (int)LLB_ERR_STATE;
+        const int cnt = which == 0 ? c->projection.header().n_seg : c->projection.header().n_outlier;
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        if (cnt > 0) download_cloud(c, which == 0 ? c->projection.seg_dev() : c->projection.outlier_dev(), cnt, out);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_projection_get_info(llb_ctx *c, int32_t *start_ring, int32_t *end_ring, float ori[3], uint8_t *ground, uint32_t *col,
+                            float *range, int cap)
+{
+    return guarded(c, [&]() {
+        if (!c->projection_done) return (int)LLB_ERR_STATE;
+        const ImageProjector &ip = c->projection;
+        const int ns = ip.params().n_scan, n = ip.header().n_seg;
+        if ((ground || col || range) && n > cap) return (int)LLB_ERR_CAPACITY;
+        if (start_ring) std::memcpy(start_ring, ip.start_ring_host(), sizeof(int) * ns);
+        if (end_ring) std::memcpy(end_ring, ip.end_ring_host(), sizeof(int) * ns);
+        if (ori) { ori[0] = ip.header().start_ori; ori[1] = ip.header().end_ori; ori[2] = ip.header().ori_diff; }
+        if (n > 0) {
+            if (ground) LLB_CUDA(cudaMemcpyAsync(ground, ip.ground_flag_dev(), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            if (col) LLB_CUDA(cudaMemcpyAsync(col, ip.col_ind_dev(), sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+            if (range) LLB_CUDA(cudaMemcpyAsync(range, ip.seg_range_dev(), sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+            LLB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_projection_get_images(llb_ctx *c, float *range_mat, int8_t *ground_mat, int32_t *label_mat)
+{
+    return guarded(c, [&]() {
+        if (!c->projection_done) return (int)LLB_ERR_STATE;
+        const ImageProjector &ip = c->projection;
+        const size_t np = (size_t)ip.params().n_scan * ip.params().horizon;
+        if (range_mat) LLB_CUDA(cudaMemcpyAsync(range_mat, ip.range_mat_dev(), sizeof(float) * np, cudaMemcpyDeviceToHost, c->stream));
+        if (ground_mat) LLB_CUDA(cudaMemcpyAsync(ground_mat, ip.ground_mat_dev(), np, cudaMemcpyDeviceToHost, c->stream));
+        if (label_mat) LLB_CUDA(cudaMemcpyAsync(label_mat, ip.label_mat_dev(), sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_projection_to_features(llb_ctx *c, int counts[4], float *device_ms)
+{
+    return guarded(c, [&]() {
+        if (!c->projection_done || !c->features.ready()) return (int)LLB_ERR_STATE;
+        const ImageProjector &ip = c->projection;
+        if (ip.params().n_scan != c->features.n_scan() || ip.params().horizon != c->features.horizon()) return (int)LLB_ERR_STATE;
+        const IpHeader &h = ip.header();
+        // ring bounds must stay inside the cloud (IP:318, IP:358): the feature kernels index with them
+        for (int r = 0; r < ip.params().n_scan; r++)
+            if (ip.start_ring_host()[r] < 4 || ip.end_ring_host()[r] > h.n_seg - 6 ||
+                ip.end_ring_host()[r] - ip.start_ring_host()[r] > ip.params().horizon) return (int)LLB_ERR_INVALID;
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->features.extract_dev(ip.seg_dev(), h.n_seg, ip.start_ring_dev(), ip.end_ring_dev(), h.start_ori, h.end_ori,
+                                               h.ori_diff, ip.ground_flag_dev(), ip.col_ind_dev(), ip.seg_range_dev(), c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        LLB_CUDA(cudaEventElapsedTime(&c->features_ms, c->ev0, c->ev1));
+        c->features_done = true;
+        if (counts) for (int k = 0; k < 4; k++) counts[k] = c->features.counts()[k];
+        if (device_ms) *device_ms = c->features_ms;
         return (int)LLB_OK;
     });
 }

@@ -699,6 +699,33 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
     return launches;
 }
 
+int FeatureExtractor::extract_dev(const float4 *cloud_dev, int n, const int *start_ring_dev, const int *end_ring_dev, float start_ori,
+                                  float end_ori, float ori_diff, const unsigned char *ground_dev, const unsigned *col_dev,
+                                  const float *range_dev, cudaStream_t s)
+{
+    const int rb = ring_; ring_ ^= 1;
+    if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
+    pin_in_[rb].ensure(256); in_dev_.ensure(256);
+    FeView v{};
+    v.cloud_in = cloud_dev; v.cloud_adj = cloud_adj_.p;
+    v.n = n; v.n_scan = n_scan_; v.horizon = horizon_; v.cap = cap_;
+    v.start_ring = start_ring_dev; v.end_ring = end_ring_dev;
+    v.ground = ground_dev; v.col = col_dev; v.range = range_dev;
+    v.start_ori = start_ori; v.end_ori = end_ori; v.ori_diff = ori_diff;
+    v.ori = ori_.p; v.curv = curv_.p; v.picked = picked_.p; v.label = label_.p; v.smooth = smooth_.p; v.hdr = hdr_.p;
+    v.r_sharp = r_sharp_.p; v.r_lsharp = r_lsharp_.p; v.r_flat = r_flat_.p; v.r_lf_scan = r_lf_scan_.p; v.r_lf_ds = r_lf_ds_.p;
+    v.r_cnt = r_cnt_.p; v.r_lf_ds_cnt = r_lf_ds_cnt_.p;
+    for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_dev_ + out_off_[k]);
+    v.out_hdr = reinterpret_cast<FeHeader *>(out_dev_);
+    v.prm = prm; v.seq = ++seq_;
+    std::memcpy(pin_in_[rb].p, &v, sizeof(v));
+    n_ = n; staged_ = rb; staged_bytes_ = 256;
+    copy_in(s);
+    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s);
+    copy_out(s);
+    return launches;
+}
+
 // ---------------------------------------------------------------- batch: one sweep per slot, the same five launches
 void FeatureBatch::init(int slots, int n_scan, int horizon, cudaStream_t s)
 {

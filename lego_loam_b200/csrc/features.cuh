@@ -69,6 +69,9 @@ public:
     // stages the sweep (host pointers, cloud with a 32 B stride), enqueues everything; returns kernel launches
     int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
+    // the same for a sweep that is already on the device (output of projection.cu): only the 256-byte table entry goes up
+    int extract_dev(const float4 *cloud_dev, int n, const int *start_ring_dev, const int *end_ring_dev, float start_ori, float end_ori,
+                    float ori_diff, const unsigned char *ground_dev, const unsigned *col_dev, const float *range_dev, cudaStream_t s);
     // after the stream has been synchronised
     const int *counts() const { return reinterpret_cast<const FeHeader *>(out_pin_)->counts; }
     const int *phase_cycles() const { return reinterpret_cast<const FeHeader *>(out_pin_)->pad; }   // sort, picks (slowest ring), then prof[8]

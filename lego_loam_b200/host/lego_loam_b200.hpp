@@ -215,6 +215,66 @@ struct cloud_info {
 };
 
 // ---------------------------------------------------------------------------------------------
+// ImageProjection: cloudHandler's steps (IP:181-197): findStartEndAngle, projectPointCloud, groundRemoval,
+// cloudSegmentation (imageProjection.cpp:199-368 with labelComponents :370-448).  The reference's members keep their
+// names; the four steps run as one device pass when cloudSegmentation() is reached (they only communicate through the
+// images, which stay on the device).  laserCloudInRing: the ring channel of the sweep (useCloudRing, UT:60).
+// ---------------------------------------------------------------------------------------------
+class ImageProjection {
+public:
+    Cloud::Ptr laserCloudIn;                                       // IP:48 (NaN-free, IP:170)
+    std::vector<uint16_t> laserCloudInRing;                        // IP:49: points[i].ring
+    Cloud::Ptr segmentedCloud, outlierCloud;                       // IP:55, IP:57
+    cloud_info segMsg;                                             // IP:68
+    int last_status = LLB_OK;
+
+    // sensor block of utility.h (UT:62-84): N_SCAN, Horizon_SCAN, ang_res_x, ang_res_y, groundScanInd
+    ImageProjection(int n_scan, int horizon_scan, float ang_res_x, float ang_res_y, int ground_scan_ind, int device = 0,
+                    const llb_params *params = nullptr)
+    {
+        for (Cloud::Ptr *p : { &laserCloudIn, &segmentedCloud, &outlierCloud }) p->reset(new Cloud());
+        if (llb_create(params, device, &ctx_) != LLB_OK)
+            throw std::runtime_error("lego_loam_b200: llb_create failed (no CUDA device / no CPU fallback)");
+        last_status = llb_projection_init(ctx_, n_scan, horizon_scan, ang_res_x, ang_res_y, ground_scan_ind);
+        n_scan_ = n_scan;
+    }
+    ~ImageProjection() { llb_destroy(ctx_); }
+    ImageProjection(const ImageProjection &) = delete;
+    ImageProjection &operator=(const ImageProjection &) = delete;
+
+    void findStartEndAngle() { staged_ |= 1; }                     // IP:199
+    void projectPointCloud() { staged_ |= 2; }                     // IP:213
+    void groundRemoval() { staged_ |= 4; }                         // IP:259
+    // fetch = copy segmentedCloud / outlierCloud / segMsg to the members (not needed when the next stage is
+    // llb_projection_to_features on the same context)
+    void cloudSegmentation(bool fetch = true)                      // IP:312
+    {
+        if (staged_ != 7 || laserCloudInRing.size() < laserCloudIn->size()) { staged_ = 0; last_status = LLB_ERR_STATE; return; }
+        staged_ = 0;
+        int ns = 0, no = 0;
+        last_status = llb_projection_process(ctx_, as_llb(*laserCloudIn), laserCloudInRing.data(), (int)laserCloudIn->size(),
+                                             &ns, &no, nullptr);
+        if (last_status != LLB_OK || !fetch) return;
+        segmentedCloud->resize(ns); outlierCloud->resize(no);
+        if (ns > 0) last_status = llb_projection_get_cloud(ctx_, 0, as_llb(*segmentedCloud), ns, &ns);
+        if (no > 0 && last_status == LLB_OK) last_status = llb_projection_get_cloud(ctx_, 1, as_llb(*outlierCloud), no, &no);
+        segMsg.startRingIndex.assign(n_scan_, 0); segMsg.endRingIndex.assign(n_scan_, 0);
+        segMsg.segmentedCloudGroundFlag.assign(ns, 0); segMsg.segmentedCloudColInd.assign(ns, 0); segMsg.segmentedCloudRange.assign(ns, 0.f);
+        float ori[3] = { 0, 0, 0 };
+        if (last_status == LLB_OK)
+            last_status = llb_projection_get_info(ctx_, segMsg.startRingIndex.data(), segMsg.endRingIndex.data(), ori,
+                                                  segMsg.segmentedCloudGroundFlag.data(), segMsg.segmentedCloudColInd.data(),
+                                                  segMsg.segmentedCloudRange.data(), ns > 0 ? ns : 1);
+        segMsg.startOrientation = ori[0]; segMsg.endOrientation = ori[1]; segMsg.orientationDiff = ori[2];
+    }
+    llb_ctx *context() { return ctx_; }
+
+private:
+    llb_ctx *ctx_ = nullptr;
+    int staged_ = 0, n_scan_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
 // FeatureAssociation: adjustDistortion / calculateSmoothness / markOccludedPoints / extractFeatures (FA:491-784),
 // findCorresponding{Corner,Surf}Features / calculateTransformation{Surf,Corner}
 // / updateTransformation (FA:1044-1478, FA:1666-1695)
