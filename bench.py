@@ -602,6 +602,59 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
                     "for move, greedy picks 32 candidates per step), per-ring VoxelGrid(0.2), concatenation"}
 
 
+def sharded_arm(api, torch, dist, local, rank, world, workload="vls128_2m"):
+    """BASELINE config 4 (only with WORLD_SIZE > 1): ONE registration of a VLS-128 sweep against a ~2M-point voxel-DS map
+    with the queries sharded over the ranks (qi = rank + world * j) and the 28 fp64 sums of every LM iteration exchanged
+    (a) by P2P stores over NVLink fused into the persistent kernel, (b) by an NCCL all-reduce driven from the host.  The
+    voxel-DS map and its index are REPLICATED on every rank (each rank filters and indexes the whole map): what shards
+    is the kNN + fit + accumulation work.  Poses must be bit-identical across ranks and equal the single-GPU pose."""
+    from lego_loam_b200 import multi_gpu
+    mc, ms, scans = make_inputs(workload, 0, 1)              # identical inputs on every rank (same seeds)
+    sc, init = scans[0]
+    ctx = api.Context(local)
+    ctx.map_set_raw(mc, ms); ctx.synchronize()               # (first call: workspace allocation)
+    mc32, ms32 = api.to_pcl(mc), api.to_pcl(ms)
+    t0 = time.perf_counter()
+    ctx.map_set_raw_pcl(mc32, ms32)
+    ctx.synchronize()
+    map_ms = (time.perf_counter() - t0) * 1e3                # H2D + map voxel filters + index build (replicated, not sharded)
+    ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
+    counts = ctx.downsample_current_scan()
+    single = []
+    for _ in range(5):
+        T_single, st = ctx.s2m_optimize(init); single.append(st.device_ms)
+    nccl = []
+    for _ in range(4):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        T_nccl, it_nccl = multi_gpu.sharded_scan2map(ctx, init, rank, world)
+        torch.cuda.synchronize()
+        nccl.append((time.perf_counter() - t0) * 1e3)
+    multi_gpu.setup_fused_exchange(ctx, rank, world)
+    fused_dev, fused_wall = [], []
+    for _ in range(8):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        T_fused, st_f = multi_gpu.sharded_scan2map_fused(ctx, init)
+        fused_wall.append((time.perf_counter() - t0) * 1e3); fused_dev.append(st_f.device_ms)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (np.asarray(T_fused, np.float32).tobytes(), float(np.median(fused_dev[2:]))))
+    same = all(g[0] == gathered[0][0] for g in gathered)
+    out = {"workload": workload, "world": world, "queries": int(counts[0] + counts[3]),
+           "map_points": [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])], "raw_map_points": int(mc.shape[0] + ms.shape[0]),
+           "iterations": int(st.iterations), "single_gpu_device_ms": float(np.median(single[1:])),
+           "fused_device_ms_max_over_ranks": float(max(g[1] for g in gathered)), "fused_wall_ms": float(np.median(fused_wall[2:])),
+           "nccl_wall_ms": float(np.median(nccl[1:])), "bytes_per_iteration_per_rank": 28 * 8 * (world - 1),
+           "pose_bit_identical_across_ranks": bool(same),
+           "pose_equals_single_gpu": bool(np.array_equal(np.asarray(T_fused, np.float32), np.asarray(T_single, np.float32))),
+           "fused_equals_nccl": bool(np.array_equal(np.asarray(T_fused, np.float32), np.asarray(T_nccl, np.float32))),
+           "replicated_map_upload_voxel_index_wall_ms": map_ms,
+           "note": "queries sharded, voxel-DS map + index replicated on every rank (the map-side work does not divide by the "
+                   "number of GPUs); exchange = 28 fp64 per rank and LM iteration"}
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -615,6 +668,7 @@ def main():
     ap.add_argument("--scans", type=int, default=8, help="distinct new sweeps per sequence rotated through the steps")
     ap.add_argument("--cpu-sample", type=int, default=8, help="registrations timed for cpu_baseline")
     ap.add_argument("--key-frames", type=int, default=100, help="resident key-frames the local map of a sequence is assembled from")
+    ap.add_argument("--sharded", type=int, default=1, help="1: with WORLD_SIZE > 1 also run the config-4 arm (one VLS-128 registration sharded over the ranks)")
     ap.add_argument("--secondary", type=int, default=1, help="1: also run the secondary arms on rank 0 (registration_only, latency, odometry, feature_extraction)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -794,6 +848,13 @@ def main():
             except Exception as e:                            # secondary arms never hide the main line
                 sec[name] = {"error": repr(e)}
             _log(f"secondary arm {name} done")
+    shard = None
+    if world > 1 and args.sharded:
+        try:
+            shard = sharded_arm(api, torch, dist, local, rank, world)
+        except Exception as e:
+            shard = {"error": repr(e)}
+        _log("sharded arm done")
     if world > 1:
         dist.barrier()
 
@@ -895,6 +956,8 @@ def main():
             "pose_check_max_abs_diff_vs_cpu": pose_diff,
         }
         line.update(sec)
+        if shard is not None:
+            line["sharded"] = shard
         print(json.dumps(line))
     b0["b"].close()
     if world > 1:

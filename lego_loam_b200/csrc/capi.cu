@@ -938,7 +938,6 @@ int llb_s2m_optimize_sharded(llb_ctx *c, float T[6], llb_stats *stats)
         c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
         c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg,
                                   c->peers.rank, c->peers.world, true, c->stream, &c->peers);
-        c->peers.seq_base += (unsigned long long)c->prm.s2m_max_iterations + 1ull;   // the same on every rank
         LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         read_count(c, 0);

@@ -64,7 +64,7 @@ __global__ void s2m_state_init_kernel(S2mState *st)
     for (int i = 0; i < 36; i++) { st->matP[i] = 0.f; st->AtA[i] = 0.f; st->AtA0[i] = 0.f; }
     st->matP_valid = 1;                                      // the reference starts with matP = 0 (MO:361)
     st->converged = 0; st->iters = 0; st->n_corr = 0; st->is_degenerate = 0; st->skipped = 0; st->ticket = 0;
-    st->queue = 0; st->peer_timeout = 0;
+    st->queue = 0; st->peer_timeout = 0; st->xchg = 0ull;
 }
 
 
@@ -259,10 +259,13 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 // ---- fused exchange of the 28 sums over NVLink (BASELINE config 4): one-shot all-to-all of P2P
                 // stores into every peer's mailbox + flag, then every rank adds the contributions in RANK ORDER, so
                 // all ranks hold bit-identical normal equations and take the identical LM step - no NCCL call, no host.
-                // Mailboxes are double-buffered by iteration parity: a rank can be at most one iteration ahead of a
-                // peer (it needs the peer's sums of iteration i to leave iteration i).
-                const int par = iter & 1;
-                const unsigned long long seq = peers.seq_base + (unsigned long long)iter + 1ull;
+                // Mailboxes are double-buffered by the parity of the EXCHANGE number: a rank can be at most one exchange
+                // ahead of a peer (it needs the peer's sums of exchange e to leave exchange e), and the number runs on
+                // over the registrations of the context - a registration that ended on an even iteration is not followed
+                // by one that starts in the same mailbox while a slow peer still reads it.
+                const unsigned long long xn = st->xchg;
+                const int par = (int)(xn & 1ull);
+                const unsigned long long seq = xn + 1ull;
                 if (tid < S2M_ACC)
                     for (int r = 0; r < peers.world; r++)
                         reinterpret_cast<volatile double *>(peers.box[r])[(par * S2M_MAX_PEERS + peers.rank) * 32 + tid] = s_tot[tid];
@@ -287,6 +290,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                     s_tot[tid] = tsum;
                 }
                 __syncthreads();
+                if (tid == 0) st->xchg = xn + 1ull;
             }
             if (prof) st->prof[iter % 10][5] = clock64();
             if (tid == 0 && do_solve) lm_solve(st, s_tot, iter, prm, false);

@@ -32,6 +32,8 @@ struct S2mState {                    // device-resident, persists across registr
     float AtA[36], AtB[6], X[6];     // last LM step (diagnostics)
     unsigned ticket;                 // last-block election
     int peer_timeout;                // fused multi-GPU exchange: a peer's sums did not arrive within ~2 s
+    unsigned long long xchg;         // exchanges performed so far: the same on every rank (identical LM steps), so it
+                                     // numbers the exchanges and alternates the mailboxes ACROSS registrations too
     unsigned queue;                  // chunk queue of the persistent kernel (zero between iterations)
     long long prof[10][8];           // clock64 stamps of CTA 0 per iteration: start, A, B, C, sync1, reduce, solve, sync2
 };
@@ -50,7 +52,6 @@ struct S2mPeers {
     double *box[S2M_MAX_PEERS];
     unsigned long long *flag[S2M_MAX_PEERS];
     int world, rank;
-    unsigned long long seq_base;     // flags carry seq_base + iteration + 1: monotonic over the context's lifetime
 };
 
 struct S2mQueries {

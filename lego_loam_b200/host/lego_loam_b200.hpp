@@ -160,10 +160,46 @@ public:
         }
     }
 
-    void transformUpdate()                                          // MO:463-496 without IMU messages (C15, C23)
+    // imuHandler MO:643-652 after the quaternion -> roll / pitch conversion (tf stays with the caller)
+    void imuHandler(double stamp, double roll, double pitch)
     {
+        imuPointerLast = (imuPointerLast + 1) % imuQueLength;
+        imuTime[imuPointerLast] = stamp;
+        imuRoll[imuPointerLast] = (float)roll;
+        imuPitch[imuPointerLast] = (float)pitch;
+    }
+
+    // MO:463-496: with IMU messages roll and pitch are pulled towards the IMU's (complementary blend 0.998 / 0.002,
+    // IMU values interpolated at the end of the sweep); host arithmetic, O(1)
+    void transformUpdate()
+    {
+        if (imuPointerLast >= 0) {
+            float imuRollLast = 0, imuPitchLast = 0;
+            while (imuPointerFront != imuPointerLast) {
+                if (timeLaserOdometry + scanPeriod < imuTime[imuPointerFront]) break;
+                imuPointerFront = (imuPointerFront + 1) % imuQueLength;
+            }
+            if (timeLaserOdometry + scanPeriod > imuTime[imuPointerFront]) {
+                imuRollLast = imuRoll[imuPointerFront];
+                imuPitchLast = imuPitch[imuPointerFront];
+            } else {
+                const int back = (imuPointerFront + imuQueLength - 1) % imuQueLength;
+                const float ratioFront = (float)((timeLaserOdometry + scanPeriod - imuTime[back]) / (imuTime[imuPointerFront] - imuTime[back]));
+                const float ratioBack = (float)((imuTime[imuPointerFront] - timeLaserOdometry - scanPeriod) / (imuTime[imuPointerFront] - imuTime[back]));
+                imuRollLast = imuRoll[imuPointerFront] * ratioFront + imuRoll[back] * ratioBack;
+                imuPitchLast = imuPitch[imuPointerFront] * ratioFront + imuPitch[back] * ratioBack;
+            }
+            transformTobeMapped[0] = (float)(0.998 * transformTobeMapped[0] + 0.002 * imuPitchLast);
+            transformTobeMapped[2] = (float)(0.998 * transformTobeMapped[2] + 0.002 * imuRollLast);
+        }
         for (int i = 0; i < 6; i++) { transformBefMapped[i] = transformSum[i]; transformAftMapped[i] = transformTobeMapped[i]; }
     }
+    static constexpr int imuQueLength = 200;                       // UT:109
+    static constexpr float scanPeriod = 0.1f;                      // UT:107 (a float: it is promoted to double in the time sums)
+    double timeLaserOdometry = 0;                                  // MO:160
+    double imuTime[imuQueLength] = {};                             // MO:184
+    float imuRoll[imuQueLength] = {}, imuPitch[imuQueLength] = {}; // MO:185-186
+    int imuPointerFront = 0, imuPointerLast = -1;                  // MO:181-182
 
     // call when laserCloud*FromMapDS were (re)filled on the host by the caller
     void mapChanged() { map_on_device_ = false; }

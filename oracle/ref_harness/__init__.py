@@ -124,6 +124,10 @@ class MapOptimization:
     def transformAssociateToMap(self): self.L.ref_mo_transformAssociateToMap(self._h)
     def transformUpdate(self): self.L.ref_mo_transformUpdate(self._h)
 
+    def push_imu(self, stamp: float, roll: float, pitch: float):
+        """imuHandler MO:643-652 after the quaternion -> roll / pitch conversion"""
+        self.L.ref_mo_push_imu(self._h, ctypes.c_double(stamp), ctypes.c_double(roll), ctypes.c_double(pitch))
+
     @property
     def transformAftMapped(self):
         t = np.zeros(6, np.float32); self.L.ref_mo_get_aft_mapped(self._h, _fp(t)); return t

@@ -124,6 +124,15 @@ void ref_mo_set_odometry(void *h, const float *sum, double stamp)
 }
 void ref_mo_transformAssociateToMap(void *h) { ((mapOptimization *)h)->transformAssociateToMap(); }
 void ref_mo_transformUpdate(void *h) { ((mapOptimization *)h)->transformUpdate(); }
+// imuHandler MO:643-652 after the quaternion -> roll / pitch conversion (tf is not part of the path)
+void ref_mo_push_imu(void *h, double stamp, double roll, double pitch)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    m->imuPointerLast = (m->imuPointerLast + 1) % imuQueLength;
+    m->imuTime[m->imuPointerLast] = stamp;
+    m->imuRoll[m->imuPointerLast] = roll;
+    m->imuPitch[m->imuPointerLast] = pitch;
+}
 void ref_mo_get_aft_mapped(void *h, float *t) { memcpy(t, ((mapOptimization *)h)->transformAftMapped, 24); }
 int ref_mo_map_ds_sizes(void *h, int *nc, int *ns)
 {

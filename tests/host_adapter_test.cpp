@@ -39,6 +39,21 @@ int main(int argc, char **argv)
            MO.laserCloudSurfTotalLastDSNum, MO.last_stats.iterations, (int)MO.isDegenerate);
     for (int i = 0; i < 6; i++) printf(" %.9g", MO.transformTobeMapped[i]);
     printf(" %zu\n", MO.laserCloudSurfTotalLastDS->size());
+    // transformUpdate with IMU messages (MO:463-496): K samples {stamp, roll, pitch}, then the odometry stamp and pose
+    int n_imu = 0;
+    f.read((char *)&n_imu, 4);
+    for (int k = 0; k < n_imu; k++) {
+        double v[3];
+        f.read((char *)v, 24);
+        MO.imuHandler(v[0], v[1], v[2]);
+    }
+    f.read((char *)&MO.timeLaserOdometry, 8);
+    f.read((char *)MO.transformSum, 24);
+    MO.transformUpdate();
+    printf("TU");
+    for (int i = 0; i < 6; i++) printf(" %.9g", MO.transformBefMapped[i]);
+    for (int i = 0; i < 6; i++) printf(" %.9g", MO.transformAftMapped[i]);
+    printf("\n");
 
     FeatureAssociation FA;
     read_cloud(f, *FA.laserCloudCornerLast); read_cloud(f, *FA.laserCloudSurfLast);

@@ -38,6 +38,12 @@ def test_adapter_matches_oracle(tmp_path):
         for c in (case["map_corner_raw"], case["map_surf_raw"], case["corner"], case["surf"], case["outlier"]):
             w(c)
         f.write(np.ascontiguousarray(case["init"], np.float32).tobytes())
+        rng = np.random.default_rng(9)
+        imu = np.stack([100.0 + 0.005 * np.arange(40), 0.02 * rng.standard_normal(40), 0.03 * rng.standard_normal(40)], 1)
+        t_odo = 100.0 + 0.005 * 17.3 - float(np.float32(0.1))     # the blend interpolates at timeLaserOdometry + scanPeriod
+        t_sum = np.array([0.01, 0.5, -0.02, 4.0, 0.1, -3.0], np.float32)
+        f.write(struct.pack("i", imu.shape[0])); f.write(np.ascontiguousarray(imu, np.float64).tobytes())
+        f.write(struct.pack("d", t_odo)); f.write(t_sum.tobytes())
         for c in (od.corner_last, od.surf_last, od.corner_sharp, od.surf_flat):
             w(c)
         from lego_loam_b200 import synth
@@ -48,7 +54,7 @@ def test_adapter_matches_oracle(tmp_path):
         f.write(sw.ground.astype(np.uint8).tobytes()); f.write(sw.col.astype(np.uint32).tobytes())
         f.write(sw.range.astype(np.float32).tobytes())
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
-    mo_line = out[0].split(); fa_line = out[1].split()
+    mo_line = out[0].split(); tu_line = out[1].split(); fa_line = out[2].split()
 
     oracle.set_trig_mode(0)
     mo = oracle.MapOptimization()
@@ -62,6 +68,21 @@ def test_adapter_matches_oracle(tmp_path):
     assert np.allclose(np.array(mo_line[7:13], np.float32), mo.transformTobeMapped, atol=1e-6)
     assert int(mo_line[13]) == mo.scan_ds(3).shape[0]
 
+    # transformUpdate with IMU messages against the compiled reference (MO:463-496), bit for bit
+    from oracle import ref_harness as rh
+    if rh.available():
+        rmo = rh.MapOptimization()
+        for st, ro, pi in imu:
+            rmo.push_imu(st, ro, pi)
+        rmo.set_odometry(t_sum, t_odo)
+        rmo.transformTobeMapped = np.array(mo_line[7:13], np.float32)
+        rmo.transformUpdate()
+        bef, aft = rmo.bef_aft()
+        assert tu_line[0] == "TU"
+        got = np.array(tu_line[1:13], np.float32)
+        assert np.array_equal(got[:6].view(np.uint32), bef.view(np.uint32)) and np.array_equal(got[6:].view(np.uint32), aft.view(np.uint32)), (got, bef, aft)
+        assert not np.array_equal(aft, np.array(mo_line[7:13], np.float32))        # the blend changed roll / pitch
+
     fa = oracle.FeatureAssociation()
     fa.set_last(od.corner_last, od.surf_last, force=True)
     fa.set_features(od.corner_sharp, od.surf_flat)
@@ -72,7 +93,7 @@ def test_adapter_matches_oracle(tmp_path):
     oracle.set_trig_mode(0)
 
     # extractFeatures through the adapter: sizes and the x, y, z words of the four clouds (FNV-1a) as the oracle has them
-    fe_line = out[2].split()
+    fe_line = out[3].split()
     assert fe_line[0] == "FE" and int(fe_line[1]) == 0
     want = oracle.FeatureExtraction(16, 1800).extract(sw)
 
