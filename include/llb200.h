@@ -187,7 +187,7 @@ typedef struct {
 } llb_segmented_cloud;
 /* N_SCAN / Horizon_SCAN (UT:63-84); allocates the per-point state the reference keeps between sweeps (FA:210-223) */
 int llb_features_init(llb_ctx *ctx, int n_scan, int horizon_scan);
-/* adjustDistortion (no IMU data: imuPointerLast < 0, FA:525), calculateSmoothness, markOccludedPoints, extractFeatures
+/* adjustDistortion (IMU branch FA:525-613 when llb_features_set_imu gave ring buffers), calculateSmoothness, markOccludedPoints, extractFeatures
  * = runFeatureAssociation FA:1827-1833.  counts = sizes of cornerPointsSharp, cornerPointsLessSharp, surfPointsFlat,
  * surfPointsLessFlat.  Selection, order and coordinates are bit-identical to the reference (std::sort's order of equal
  * curvatures included), and so are the intensities: the kernel restates glibc's atan2f operation by operation. */
@@ -202,6 +202,39 @@ int llb_features_get_state(llb_ctx *ctx, float *curvature, int *neighbor_picked,
  * laserCloudSurfLast of the odometry (= llb_odom_set_last on them, without leaving the device; the clouds are always
  * indexed, see llb_odom_set_last).  llb_features_get(which = 5 / 6) reads them back. */
 int llb_features_publish_last(llb_ctx *ctx, const float transformCur[6]);
+/* ---- IMU branches of featureAssociation (imuHandler FA:417-448 and AccumulateIMUShiftAndRotation
+ * FA:390-415 stay on the host: one message at a time, a few flops each — host/lego_loam_b200.hpp keeps the ring
+ * buffers; the per-point work, adjustDistortion's IMU branch FA:525-613 and TransformToEnd's IMU terms FA:927-950,
+ * runs on the device) ---- */
+#define LLB_IMU_QUEUE 200                   /* imuQueLength UT:109 */
+typedef struct llb_imu_queue {              /* the ring buffers FA:82-135 as they stand when the sweep arrives */
+    double time[LLB_IMU_QUEUE];             /* imuTime */
+    float roll[LLB_IMU_QUEUE], pitch[LLB_IMU_QUEUE], yaw[LLB_IMU_QUEUE];
+    float velo[3][LLB_IMU_QUEUE];           /* imuVeloX / Y / Z */
+    float shift[3][LLB_IMU_QUEUE];          /* imuShiftX / Y / Z */
+    float angular[3][LLB_IMU_QUEUE];        /* imuAngularRotationX / Y / Z */
+    double time_scan_cur;                   /* timeScanCur FA:453 */
+    int pointer_last;                       /* imuPointerLast; < 0: no message yet (FA:525 skips the branch) */
+    int pointer_last_iteration;             /* imuPointerLastIteration FA:489 / FA:616 */
+} llb_imu_queue;
+typedef struct llb_imu_sweep {              /* what adjustDistortion's IMU branch leaves in the members */
+    float start[9];                         /* imuRoll/Pitch/YawStart, imuVeloX/Y/ZStart, imuShiftX/Y/ZStart (point 0) */
+    float angular_cur[3];                   /* imuAngularRotationX/Y/ZCur (point 0, FA:580-594) */
+    float cur[3];                           /* imuRoll/Pitch/YawCur after the last point */
+    float velo_from_start_cur[3];           /* imuVeloFromStartX/Y/ZCur after the last point (valid when has_velo) */
+    int valid, has_velo;                    /* valid: the branch ran; has_velo: the sweep had a point after the first */
+} llb_imu_sweep;
+typedef struct llb_imu_end {                /* IMU terms of TransformToEnd FA:927-950 */
+    float cs_start[6];                      /* cos, sin of imuRollStart; of imuPitchStart; of imuYawStart (FA:317-324) */
+    float shift_from_start[3];              /* imuShiftFromStartX/Y/Z */
+    float last[3];                          /* imuRollLast, imuPitchLast, imuYawLast */
+} llb_imu_end;
+/* ring buffers for the NEXT llb_features_extract / llb_projection_to_features (copied; NULL: back to "no IMU data") */
+int llb_features_set_imu(llb_ctx *ctx, const llb_imu_queue *queue);
+/* members after the last extraction (out->valid = 0 when the branch did not run) */
+int llb_features_get_imu(llb_ctx *ctx, llb_imu_sweep *out);
+/* llb_features_publish_last with the IMU terms of TransformToEnd (NULL = llb_features_publish_last) */
+int llb_features_publish_last_imu(llb_ctx *ctx, const float transformCur[6], const llb_imu_end *imu);
 /* SM cycles of the slowest ring of the last sweep (profiling): [0] sort phase, [1] picks; then the slowest warp / ring
  * per part: [2] partitions, [3] leaf ranges, [4] edge picks, [5] flat picks, [6..9] reserved */
 int llb_features_get_profile(llb_ctx *ctx, int cycles[10]);

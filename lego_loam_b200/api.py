@@ -68,6 +68,7 @@ EXPORTS = [
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
     "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
+    "llb_features_set_imu", "llb_features_get_imu", "llb_features_publish_last_imu",
     "llb_projection_init", "llb_projection_process", "llb_projection_get_cloud", "llb_projection_get_info",
     "llb_projection_get_images", "llb_projection_to_features",
     "llb_batch_features_init", "llb_batch_features_extract", "llb_batch_features_get",
@@ -111,6 +112,41 @@ def lib() -> ctypes.CDLL:
             getattr(L, name)   # raises AttributeError if a declared symbol is missing
         _lib = L
     return _lib
+
+
+IMU_QUEUE = 200
+_LIBM = None
+
+
+def _libm():
+    """the C library's cosf / sinf (numpy's float32 cos is its own SIMD routine, not the reference's libm)"""
+    global _LIBM
+    if _LIBM is None:
+        import ctypes.util
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        for f in (_LIBM.cosf, _LIBM.sinf):
+            f.restype = ctypes.c_float; f.argtypes = [ctypes.c_float]
+    return _LIBM
+
+
+class ImuQueue(ctypes.Structure):
+    """llb_imu_queue: the IMU ring buffers of FeatureAssociation (FA:82-135) as they stand when a sweep arrives."""
+    _fields_ = [("time", ctypes.c_double * IMU_QUEUE),
+                ("roll", ctypes.c_float * IMU_QUEUE), ("pitch", ctypes.c_float * IMU_QUEUE), ("yaw", ctypes.c_float * IMU_QUEUE),
+                ("velo", (ctypes.c_float * IMU_QUEUE) * 3), ("shift", (ctypes.c_float * IMU_QUEUE) * 3),
+                ("angular", (ctypes.c_float * IMU_QUEUE) * 3),
+                ("time_scan_cur", ctypes.c_double), ("pointer_last", ctypes.c_int), ("pointer_last_iteration", ctypes.c_int)]
+
+
+class ImuSweep(ctypes.Structure):
+    """llb_imu_sweep: the members adjustDistortion's IMU branch leaves behind (FA:556-611)."""
+    _fields_ = [("start", ctypes.c_float * 9), ("angular_cur", ctypes.c_float * 3), ("cur", ctypes.c_float * 3),
+                ("velo_from_start_cur", ctypes.c_float * 3), ("valid", ctypes.c_int), ("has_velo", ctypes.c_int)]
+
+
+class ImuEnd(ctypes.Structure):
+    """llb_imu_end: IMU terms of TransformToEnd (FA:927-950)."""
+    _fields_ = [("cs_start", ctypes.c_float * 6), ("shift_from_start", ctypes.c_float * 3), ("last", ctypes.c_float * 3)]
 
 
 class SegmentedCloud(ctypes.Structure):
@@ -432,6 +468,26 @@ class Context:
         """TransformToEnd of the less-sharp / less-flat clouds -> laserCloudCornerLast / laserCloudSurfLast (FA:1759-1788)"""
         t = np.ascontiguousarray(transformCur, np.float32)
         self._ck(lib().llb_features_publish_last(self._h, _fp(t)))
+
+    def features_set_imu(self, queue):
+        """ring buffers (ImuQueue) for the next features_extract / projection_to_features; None: no IMU data"""
+        self._ck(lib().llb_features_set_imu(self._h, ctypes.byref(queue) if queue is not None else None))
+
+    def features_get_imu(self):
+        out = ImuSweep()
+        self._ck(lib().llb_features_get_imu(self._h, ctypes.byref(out)))
+        return out
+
+    def features_publish_last_imu(self, transformCur, start_rpy, shift_from_start, last_rpy):
+        """publishCloudsLast with the IMU terms of TransformToEnd: imuRoll/Pitch/YawStart, imuShiftFromStartX/Y/Z,
+        imuRoll/Pitch/YawLast (the cos / sin of the start angles are taken here, in float, as FA:317-324 does)"""
+        e = ImuEnd()
+        for k in range(3):
+            a = ctypes.c_float(float(np.float32(start_rpy[k])))
+            e.cs_start[2 * k] = _libm().cosf(a); e.cs_start[2 * k + 1] = _libm().sinf(a)
+            e.shift_from_start[k] = float(np.float32(shift_from_start[k])); e.last[k] = float(np.float32(last_rpy[k]))
+        t = np.ascontiguousarray(transformCur, np.float32)
+        self._ck(lib().llb_features_publish_last_imu(self._h, _fp(t), ctypes.byref(e)))
 
     def features_get_profile(self):
         cyc = (ctypes.c_int * 10)()

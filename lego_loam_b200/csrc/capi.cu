@@ -1271,14 +1271,45 @@ int llb_features_get_state(llb_ctx *c, float *curvature, int *neighbor_picked, i
     });
 }
 
+static_assert(sizeof(llb_imu_queue) == sizeof(FeImu) && LLB_IMU_QUEUE == FE_IMU_QUEUE, "llb_imu_queue mirrors FeImu");
+static_assert(sizeof(llb_imu_sweep) == sizeof(FeImuOut) && sizeof(llb_imu_end) == sizeof(FeEndImu), "IMU structs mirror the device ones");
+
+int llb_features_set_imu(llb_ctx *c, const llb_imu_queue *queue)
+{
+    return guarded(c, [&]() {
+        if (!c->features.ready()) return (int)LLB_ERR_STATE;
+        if (queue && (queue->pointer_last >= LLB_IMU_QUEUE || queue->pointer_last_iteration < 0 ||
+                      queue->pointer_last_iteration >= LLB_IMU_QUEUE)) return (int)LLB_ERR_INVALID;
+        c->features.set_imu(reinterpret_cast<const FeImu *>(queue));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_features_get_imu(llb_ctx *c, llb_imu_sweep *out)
+{
+    return guarded(c, [&]() {
+        if (!out) return (int)LLB_ERR_INVALID;
+        if (!c->features_done) return (int)LLB_ERR_STATE;
+        if (c->features.has_imu_out()) std::memcpy(out, &c->features.imu_out(), sizeof(*out));
+        else std::memset(out, 0, sizeof(*out));
+        return (int)LLB_OK;
+    });
+}
+
 int llb_features_publish_last(llb_ctx *c, const float transformCur[6])
+{
+    return llb_features_publish_last_imu(c, transformCur, nullptr);
+}
+
+int llb_features_publish_last_imu(llb_ctx *c, const float transformCur[6], const llb_imu_end *imu)
 {
     return guarded(c, [&]() {
         if (!transformCur) return (int)LLB_ERR_INVALID;
         if (!c->features_done) return (int)LLB_ERR_STATE;
         const int ncl = c->features.counts()[1], nsl = c->features.counts()[3];
         c->odom.cornerLast().ensure(std::max(ncl, 1)); c->odom.surfLast().ensure(std::max(nsl, 1));
-        c->launches += c->features.transform_to_end(transformCur, c->odom.cornerLast().p, c->odom.surfLast().p, c->stream);
+        c->launches += c->features.transform_to_end(transformCur, c->odom.cornerLast().p, c->odom.surfLast().p, c->stream,
+                                                    reinterpret_cast<const FeEndImu *>(imu));
         c->launches += c->odom.set_last(ncl, nsl, c->stream);
         c->features_last_n[0] = ncl; c->features_last_n[1] = nsl;
         return (int)LLB_OK;

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(const FeView *__restric
         p.x = q.y; p.y = q.z; p.z = q.x;                                               // FA:500-502
         p.w = (float)(int)q.w + v.prm.scan_period * rel;                               // FA:523
         v.cloud_adj[i] = p;
+        if (v.imu) v.ori[i] = rel;                                                      // relTime for fe_imu_kernel
         if (i >= 5 && i < v.n - 6) {                                                    // FA:647-677
             const float d1 = __ldg(v.range + i), d2 = __ldg(v.range + i + 1);
             if (fe_col_diff(v, i + 1, i) < 10) {
@@ -92,6 +93,100 @@ __global__ void __launch_bounds__(FE_TPB) fe_mark_kernel(const FeView *__restric
             }
             const float f1 = fabsf(__ldg(v.range + i - 1) - d1), f2 = fabsf(d2 - d1);
             if ((double)f1 > 0.02 * (double)d1 && (double)f2 > 0.02 * (double)d1) v.picked[i] = 1;
+        }
+    }
+}
+
+// ---- the IMU branch of adjustDistortion (FA:525-613).  glibc's sinf / cosf restated (glibc_sincosf.cuh).
+__device__ __forceinline__ float fe_cosf(float x) { return glibcm::cosf_(x); }
+__device__ __forceinline__ float fe_sinf(float x) { return glibcm::sinf_(x); }
+
+struct FeImuAt { float roll, pitch, yaw, velo[3], shift[3], ang[3]; };
+
+// IMU state at timeScanCur + pointTime: the reference's pointer walk from imuPointerLastIteration (it restarts for every
+// point, FA:527-533) and the linear interpolation between the two entries around that time (FA:535-565, FA:580-594)
+__device__ __forceinline__ void fe_imu_at(const FeImu &m, float pointTime, FeImuAt &o)
+{
+    const double t = m.time_scan_cur + pointTime;
+    int front = m.pointer_last_iteration;
+    while (front != m.pointer_last) {
+        if (t < m.time[front]) break;
+        front = (front + 1) % FE_IMU_QUEUE;
+    }
+    if (t > m.time[front]) {
+        o.roll = m.roll[front]; o.pitch = m.pitch[front]; o.yaw = m.yaw[front];
+#pragma unroll
+        for (int a = 0; a < 3; a++) { o.velo[a] = m.velo[a][front]; o.shift[a] = m.shift[a][front]; o.ang[a] = m.angular[a][front]; }
+    } else {
+        const int back = (front + FE_IMU_QUEUE - 1) % FE_IMU_QUEUE;
+        const float rf = (float)((t - m.time[back]) / (m.time[front] - m.time[back]));
+        const float rb = (float)((m.time[front] - m.time_scan_cur - pointTime) / (m.time[front] - m.time[back]));
+        o.roll = m.roll[front] * rf + m.roll[back] * rb;
+        o.pitch = m.pitch[front] * rf + m.pitch[back] * rb;
+        if ((double)(m.yaw[front] - m.yaw[back]) > FE_PI)
+            o.yaw = (float)((double)(m.yaw[front] * rf) + ((double)m.yaw[back] + 2 * FE_PI) * (double)rb);
+        else if ((double)(m.yaw[front] - m.yaw[back]) < -FE_PI)
+            o.yaw = (float)((double)(m.yaw[front] * rf) + ((double)m.yaw[back] - 2 * FE_PI) * (double)rb);
+        else
+            o.yaw = m.yaw[front] * rf + m.yaw[back] * rb;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            o.velo[a] = m.velo[a][front] * rf + m.velo[a][back] * rb;
+            o.shift[a] = m.shift[a][front] * rf + m.shift[a][back] * rb;
+            o.ang[a] = m.angular[a][front] * rf + m.angular[a][back] * rb;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FE_TPB) fe_imu_kernel(const FeView *__restrict__ table)
+{
+    const FeView v = table[blockIdx.y];
+    if (!v.imu || v.n <= 0) return;
+    const FeImu &m = *v.imu;
+    if (m.pointer_last < 0) return;                                                    // FA:525
+    // the first point defines the start state (FA:567-578); every thread derives it again (a few hundred instructions)
+    FeImuAt st;
+    fe_imu_at(m, v.ori[0] * v.prm.scan_period, st);
+    const float cRs = fe_cosf(st.roll), cPs = fe_cosf(st.pitch), cYs = fe_cosf(st.yaw);      // updateImuRollPitchYawStartSinCos
+    const float sRs = fe_sinf(st.roll), sPs = fe_sinf(st.pitch), sYs = fe_sinf(st.yaw);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+        FeImuOut *out = v.imu_out;
+        if (i == 0) {
+            out->start[0] = st.roll; out->start[1] = st.pitch; out->start[2] = st.yaw;
+            for (int a = 0; a < 3; a++) { out->start[3 + a] = st.velo[a]; out->start[6 + a] = st.shift[a]; out->angular_cur[a] = st.ang[a]; }
+            out->valid = 1;
+            if (v.n == 1) { out->cur[0] = st.roll; out->cur[1] = st.pitch; out->cur[2] = st.yaw; out->has_velo = 0; }
+            continue;
+        }
+        FeImuAt c;
+        fe_imu_at(m, v.ori[i] * v.prm.scan_period, c);
+        // VeloToStartIMU FA:346-363
+        float vx = c.velo[0] - st.velo[0], vy = c.velo[1] - st.velo[1], vz = c.velo[2] - st.velo[2];
+        {
+            const float x1 = cYs * vx - sYs * vz, y1 = vy, z1 = sYs * vx + cYs * vz;
+            const float x2 = x1, y2 = cPs * y1 + sPs * z1, z2 = -sPs * y1 + cPs * z1;
+            vx = cRs * x2 + sRs * y2; vy = -sRs * x2 + cRs * y2; vz = z2;
+        }
+        // TransformToStartIMU FA:365-388 (imuShiftFromStart*Cur stay 0: ShiftToStartIMU is never called in the reference)
+        float4 p = v.cloud_adj[i];
+        {
+            const float cr = fe_cosf(c.roll), sr = fe_sinf(c.roll), cp = fe_cosf(c.pitch), sp = fe_sinf(c.pitch);
+            const float cy = fe_cosf(c.yaw), sy = fe_sinf(c.yaw);
+            const float shx = 0.f, shy = 0.f, shz = 0.f;
+            const float x1 = cr * p.x - sr * p.y, y1 = sr * p.x + cr * p.y, z1 = p.z;
+            const float x2 = x1, y2 = cp * y1 - sp * z1, z2 = sp * y1 + cp * z1;
+            const float x3 = cy * x2 + sy * z2, y3 = y2, z3 = -sy * x2 + cy * z2;
+            const float x4 = cYs * x3 - sYs * z3, y4 = y3, z4 = sYs * x3 + cYs * z3;
+            const float x5 = x4, y5 = cPs * y4 + sPs * z4, z5 = -sPs * y4 + cPs * z4;
+            p.x = cRs * x5 + sRs * y5 + shx;
+            p.y = -sRs * x5 + cRs * y5 + shy;
+            p.z = z5 + shz;
+        }
+        v.cloud_adj[i] = p;
+        if (i == v.n - 1) {
+            out->cur[0] = c.roll; out->cur[1] = c.pitch; out->cur[2] = c.yaw;
+            out->velo_from_start_cur[0] = vx; out->velo_from_start_cur[1] = vy; out->velo_from_start_cur[2] = vz;
+            out->has_velo = 1;
         }
     }
 }
@@ -458,22 +553,19 @@ __global__ void __launch_bounds__(1024) fe_concat_kernel(const FeView *__restric
     }
 }
 
-struct FeEndJob { const float4 *in[2]; float4 *out[2]; int n[2]; float T[6]; };
+struct FeEndJob { const float4 *in[2]; float4 *out[2]; int n[2]; float T[6]; FeEndImu imu; };
 
-// glibc's sinf / cosf restated (glibc_sincosf.cuh): the transformed clouds come out as the reference's own, bit for bit
-__device__ __forceinline__ float fe_cosf(float x) { return glibcm::cosf_(x); }
-__device__ __forceinline__ float fe_sinf(float x) { return glibcm::sinf_(x); }
-
-// TransformToEnd FA:885-953 with the IMU terms of a node that never received an IMU message (angles and shifts 0; the
-// factors stay in the expressions so that signed zeros come out as in the reference)
+// TransformToEnd FA:885-953 (glibc's sinf / cosf restated: the clouds come out as the reference's own, bit for bit).  Without
+// IMU messages every IMU angle and shift is 0; the factors stay in the expressions so that signed zeros come out alike.
 __global__ void __launch_bounds__(FE_TPB) fe_to_end_kernel(FeEndJob jb)
 {
     const float *T = jb.T;
-    const float zero = 0.f;
-    const float cosImuRollStart = fe_cosf(zero), cosImuPitchStart = fe_cosf(zero), cosImuYawStart = fe_cosf(zero);
-    const float sinImuRollStart = fe_sinf(zero), sinImuPitchStart = fe_sinf(zero), sinImuYawStart = fe_sinf(zero);
-    const float cYawL = fe_cosf(zero), sYawL = fe_sinf(zero), cPitchL = fe_cosf(zero), sPitchL = fe_sinf(zero);
-    const float cRollL = fe_cosf(zero), sRollL = fe_sinf(zero);
+    const float cosImuRollStart = jb.imu.cs_start[0], sinImuRollStart = jb.imu.cs_start[1];
+    const float cosImuPitchStart = jb.imu.cs_start[2], sinImuPitchStart = jb.imu.cs_start[3];
+    const float cosImuYawStart = jb.imu.cs_start[4], sinImuYawStart = jb.imu.cs_start[5];
+    const float shX = jb.imu.shift_from_start[0], shY = jb.imu.shift_from_start[1], shZ = jb.imu.shift_from_start[2];
+    const float cYawL = fe_cosf(jb.imu.last[2]), sYawL = fe_sinf(jb.imu.last[2]), cPitchL = fe_cosf(jb.imu.last[1]), sPitchL = fe_sinf(jb.imu.last[1]);
+    const float cRollL = fe_cosf(jb.imu.last[0]), sRollL = fe_sinf(jb.imu.last[0]);
     const float cRy = fe_cosf(T[1]), sRy = fe_sinf(T[1]), cRx = fe_cosf(T[0]), sRx = fe_sinf(T[0]);
     const float cRz = fe_cosf(T[2]), sRz = fe_sinf(T[2]);
     const int total = jb.n[0] + jb.n[1];
@@ -502,9 +594,9 @@ __global__ void __launch_bounds__(FE_TPB) fe_to_end_kernel(FeEndJob jb)
         const float x6 = cRz * x5 - sRz * y5 + tx;
         const float y6 = sRz * x5 + cRz * y5 + ty;
         const float z6 = z5 + tz;
-        const float x7 = cosImuRollStart * (x6 - zero) - sinImuRollStart * (y6 - zero);
-        const float y7 = sinImuRollStart * (x6 - zero) + cosImuRollStart * (y6 - zero);
-        const float z7 = z6 - zero;
+        const float x7 = cosImuRollStart * (x6 - shX) - sinImuRollStart * (y6 - shY);
+        const float y7 = sinImuRollStart * (x6 - shX) + cosImuRollStart * (y6 - shY);
+        const float z7 = z6 - shZ;
         const float x8 = x7;
         const float y8 = cosImuPitchStart * y7 - sinImuPitchStart * z7;
         const float z8 = sinImuPitchStart * y7 + cosImuPitchStart * z7;
@@ -547,7 +639,7 @@ void fe_pack_cloud(const float *cloud32, int n, float *out16)
 
 size_t fe_input_bytes(int n, int n_scan)
 {   // must match the layout of FeatureExtractor::stage
-    const size_t o_cloud = 256, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
+    const size_t o_cloud = FE_HEAD, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
                  o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan),
                  o_ground = align16(o_end + 4 * (size_t)n_scan);
     return align16(o_ground + (size_t)n + 16);
@@ -620,14 +712,14 @@ const float4 *FeatureExtractor::host_cloud(int which) const
     return reinterpret_cast<const float4 *>(out_pin_ + out_off_[which]);
 }
 
-// the sweep goes into one pinned block: [FeView, 256 B][cloud as float4][range][column][ring bounds][ground flags];
+// the sweep goes into one pinned block: [FeView, FE_HEAD B][cloud as float4][range][column][ring bounds][ground flags];
 // copy_in() sends it with one H2D, the view at its head is this sweep's entry of the kernels' table
 FeView FeatureExtractor::stage(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
                                float end_ori, float ori_diff, const unsigned char *ground, const unsigned *col,
                                const float *range, unsigned char *hp_ext, unsigned char *dp_ext)
 {
-    static_assert(sizeof(FeView) <= 256, "FeView must fit the head of the input block");
-    const size_t o_cloud = 256, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
+    static_assert(sizeof(FeView) <= FE_HEAD, "FeView must fit the head of the input block");
+    const size_t o_cloud = FE_HEAD, o_range = align16(o_cloud + sizeof(float4) * n), o_col = align16(o_range + 4 * (size_t)n),
                  o_start = align16(o_col + 4 * (size_t)n), o_end = align16(o_start + 4 * (size_t)n_scan_),
                  o_ground = align16(o_end + 4 * (size_t)n_scan_), total = align16(o_ground + (size_t)n + 16);
     int rb = 0;
@@ -659,13 +751,23 @@ FeView FeatureExtractor::stage(const float *cloud32, int n, const int *start_rin
     for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_dev_ + out_off_[k]);
     v.out_hdr = reinterpret_cast<FeHeader *>(out_dev_);
     v.prm = prm; v.seq = ++seq_;
+    v.imu = imu_set_ ? imu_dev_.p : nullptr; v.imu_out = imu_out_dev_.p;
     std::memcpy(hp, &v, sizeof(v));
     n_ = n; staged_ = rb; staged_bytes_ = total;
     return v;
 }
 
+void FeatureExtractor::set_imu(const FeImu *imu_host)
+{
+    imu_dev_.ensure(1); pin_imu_.ensure(1); imu_out_dev_.ensure(1); pin_imu_out_.ensure(1);
+    imu_set_ = imu_host != nullptr && imu_host->pointer_last >= 0;
+    if (imu_set_) *pin_imu_.p = *imu_host;                   // (the previous sweep's copy has long been sent)
+}
+
 void FeatureExtractor::copy_in(cudaStream_t s)
 {
+    if (imu_set_) LLB_CUDA(cudaMemcpyAsync(imu_dev_.p, pin_imu_.p, sizeof(FeImu), cudaMemcpyHostToDevice, s));
+    if (imu_out_dev_.p) LLB_CUDA(cudaMemsetAsync(imu_out_dev_.p, 0, sizeof(FeImuOut), s));
     LLB_CUDA(cudaMemcpyAsync(in_dev_.p, pin_in_[staged_].p, staged_bytes_, cudaMemcpyHostToDevice, s));
     LLB_CUDA(cudaEventRecord(in_ev_[staged_], s)); in_busy_[staged_] = true;
 }
@@ -673,19 +775,21 @@ void FeatureExtractor::copy_in(cudaStream_t s)
 void FeatureExtractor::copy_out(cudaStream_t s)
 {   // header (counts) + the four clouds in one block, one D2H (the less-flat cloud is bounded by n)
     LLB_CUDA(cudaMemcpyAsync(out_pin_, out_dev_, out_bytes_used(n_), cudaMemcpyDeviceToHost, s));
+    if (imu_out_dev_.p) LLB_CUDA(cudaMemcpyAsync(pin_imu_out_.p, imu_out_dev_.p, sizeof(FeImuOut), cudaMemcpyDeviceToHost, s));
 }
 
 int FeatureExtractor::launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
-                             cudaStream_t s)
+                             cudaStream_t s, bool imu)
 {
     const int gx = std::max(1, std::min(div_up(n_max, FE_TPB), std::max(8, 148 * 4 / std::max(count, 1))));
     fe_point_kernel<<<dim3(gx, count), FE_TPB, 0, s>>>(table_dev);
     fe_mark_kernel<<<dim3(gx, count), FE_TPB, 0, s>>>(table_dev);
+    if (imu) fe_imu_kernel<<<dim3(gx, count), FE_TPB, 0, s>>>(table_dev);
     fe_ring_kernel<<<dim3(n_scan, count), FE_RING_THREADS, (horizon + 8) * 16 + (horizon + 32) * 8, s>>>(table_dev);
     launch_voxel_cta_jobs(jobs_dev, n_scan * count, (horizon + 1023) & ~1023, s);
     fe_concat_kernel<<<dim3(1, count), 1024, 0, s>>>(table_dev);
     LLB_CUDA(cudaGetLastError());
-    return 5;
+    return imu ? 6 : 5;
 }
 
 int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori,
@@ -694,7 +798,7 @@ int FeatureExtractor::extract(const float *cloud32, int n, const int *start_ring
 {
     stage(cloud32, n, start_ring, end_ring, start_ori, end_ori, ori_diff, ground, col, range);
     copy_in(s);
-    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s);
+    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s, imu_set_);
     copy_out(s);
     return launches;
 }
@@ -705,7 +809,7 @@ int FeatureExtractor::extract_dev(const float4 *cloud_dev, int n, const int *sta
 {
     const int rb = ring_; ring_ ^= 1;
     if (in_busy_[rb]) { LLB_CUDA(cudaEventSynchronize(in_ev_[rb])); in_busy_[rb] = false; }
-    pin_in_[rb].ensure(256); in_dev_.ensure(256);
+    pin_in_[rb].ensure(FE_HEAD); in_dev_.ensure(FE_HEAD);
     FeView v{};
     v.cloud_in = cloud_dev; v.cloud_adj = cloud_adj_.p;
     v.n = n; v.n_scan = n_scan_; v.horizon = horizon_; v.cap = cap_;
@@ -718,10 +822,11 @@ int FeatureExtractor::extract_dev(const float4 *cloud_dev, int n, const int *sta
     for (int k = 0; k < 4; k++) v.out[k] = reinterpret_cast<float4 *>(out_dev_ + out_off_[k]);
     v.out_hdr = reinterpret_cast<FeHeader *>(out_dev_);
     v.prm = prm; v.seq = ++seq_;
+    v.imu = imu_set_ ? imu_dev_.p : nullptr; v.imu_out = imu_out_dev_.p;
     std::memcpy(pin_in_[rb].p, &v, sizeof(v));
-    n_ = n; staged_ = rb; staged_bytes_ = 256;
+    n_ = n; staged_ = rb; staged_bytes_ = FE_HEAD;
     copy_in(s);
-    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s);
+    const int launches = launch(reinterpret_cast<const FeView *>(in_dev_.p), 1, n, n_scan_, horizon_, jobs_.p, s, imu_set_);
     copy_out(s);
     return launches;
 }
@@ -789,9 +894,14 @@ int FeatureBatch::extract(const FeSweepHost *sweeps, cudaStream_t s)
     return launches;
 }
 
-int FeatureExtractor::transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s)
+int FeatureExtractor::transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s, const FeEndImu *imu)
 {
     FeEndJob jb;
+    if (imu) jb.imu = *imu;
+    else {                                                   // a node that never received an IMU message: cos(0), sin(0), zeros
+        for (int k = 0; k < 6; k++) jb.imu.cs_start[k] = (k & 1) ? sinf(0.f) : cosf(0.f);
+        for (int k = 0; k < 3; k++) { jb.imu.shift_from_start[k] = 0.f; jb.imu.last[k] = 0.f; }
+    }
     jb.in[0] = dev_cloud(1); jb.in[1] = dev_cloud(3); jb.out[0] = corner_out; jb.out[1] = surf_out;
     jb.n[0] = counts()[1]; jb.n[1] = counts()[3];
     for (int i = 0; i < 6; i++) jb.T[i] = T[i];

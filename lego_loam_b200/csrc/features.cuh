@@ -28,6 +28,31 @@ struct FeParams { float edge_threshold, surf_threshold, scan_period, leaf; };   
 
 struct FeHeader { int first_half; int counts[4]; int release_seq; int pad[2]; int prof[7]; int stale_ind; };
 
+constexpr int FE_IMU_QUEUE = 200;                // imuQueLength UT:109
+constexpr size_t FE_HEAD = 512;                   // bytes reserved for the FeView at the head of a staged sweep
+
+struct FeImu {                   // the IMU ring buffers of FeatureAssociation (FA:82-135) for one sweep, device copy
+    double time[FE_IMU_QUEUE];
+    float roll[FE_IMU_QUEUE], pitch[FE_IMU_QUEUE], yaw[FE_IMU_QUEUE];
+    float velo[3][FE_IMU_QUEUE], shift[3][FE_IMU_QUEUE], angular[3][FE_IMU_QUEUE];
+    double time_scan_cur;
+    int pointer_last, pointer_last_iteration;
+};
+
+struct FeImuOut {                // what the IMU branch of adjustDistortion leaves behind (FA:556-611)
+    float start[9];              // imuRoll/Pitch/YawStart, imuVeloX/Y/ZStart, imuShiftX/Y/ZStart
+    float angular_cur[3];        // imuAngularRotationX/Y/ZCur (at the first point)
+    float cur[3];                // imuRoll/Pitch/YawCur of the last point
+    float velo_from_start_cur[3];// imuVeloFromStartX/Y/ZCur of the last point (points >= 1 only)
+    int valid, has_velo;
+};
+
+struct FeEndImu {                // IMU terms of TransformToEnd (FA:927-950); all zero angles / shifts without IMU messages
+    float cs_start[6];           // cos / sin of imuRollStart, imuPitchStart, imuYawStart
+    float shift_from_start[3];
+    float last[3];               // imuRollLast, imuPitchLast, imuYawLast
+};
+
 struct FeView {
     const float4 *cloud_in; float4 *cloud_adj;
     int n, n_scan, horizon, cap;
@@ -42,6 +67,7 @@ struct FeView {
     float4 *out[4]; FeHeader *out_hdr;
     FeParams prm;
     int seq;
+    const FeImu *imu; FeImuOut *imu_out;     // nullptr: no IMU data for this sweep
 };
 
 class FeatureExtractor {
@@ -64,12 +90,12 @@ public:
     void copy_in(cudaStream_t s);
     void copy_out(cudaStream_t s);
     static int launch(const FeView *table_dev, int count, int n_max, int n_scan, int horizon, const SmallJob *jobs_dev,
-                      cudaStream_t s);
+                      cudaStream_t s, bool imu = false);
     const std::vector<SmallJob> &jobs_host() const { return jobs_host_; }
     // stages the sweep (host pointers, cloud with a 32 B stride), enqueues everything; returns kernel launches
     int extract(const float *cloud32, int n, const int *start_ring, const int *end_ring, float start_ori, float end_ori,
                 float ori_diff, const unsigned char *ground, const unsigned *col, const float *range, cudaStream_t s);
-    // the same for a sweep that is already on the device (output of projection.cu): only the 256-byte table entry goes up
+    // the same for a sweep that is already on the device (output of projection.cu): only the table entry (FE_HEAD bytes) goes up
     int extract_dev(const float4 *cloud_dev, int n, const int *start_ring_dev, const int *end_ring_dev, float start_ori, float end_ori,
                     float ori_diff, const unsigned char *ground_dev, const unsigned *col_dev, const float *range_dev, cudaStream_t s);
     // after the stream has been synchronised
@@ -82,7 +108,12 @@ public:
     }
     int n_points() const { return n_; }
     // TransformToEnd (FA:885-953) of cornerPointsLessSharp / surfPointsLessFlat into the given device clouds
-    int transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s);
+    int transform_to_end(const float T[6], float4 *corner_out, float4 *surf_out, cudaStream_t s, const FeEndImu *imu = nullptr);
+    // IMU ring buffers for the NEXT extract / extract_dev (nullptr or pointer_last < 0: none); imu_out(): after the stream
+    // has been synchronised
+    void set_imu(const FeImu *imu_host);
+    const FeImuOut &imu_out() const { return *pin_imu_out_.p; }
+    bool has_imu_out() const { return pin_imu_out_.p != nullptr; }
     void get_state(float *curv, int *picked, int *label, int n, cudaStream_t s);
     FeParams prm{ 0.1f, 0.1f, 0.1f, 0.2f };
 private:
@@ -101,6 +132,8 @@ private:
     PinnedBuf<unsigned char> pin_out_;
     unsigned char *out_dev_ = nullptr, *out_pin_ = nullptr;     // own buffers or the batch's
     size_t out_off_[4] = { 0, 0, 0, 0 };
+    DevBuf<FeImu> imu_dev_; PinnedBuf<FeImu> pin_imu_; DevBuf<FeImuOut> imu_out_dev_; PinnedBuf<FeImuOut> pin_imu_out_;
+    bool imu_set_ = false;
 };
 
 struct FeSweepHost {     // one sweep as the caller holds it (llb_segmented_cloud)

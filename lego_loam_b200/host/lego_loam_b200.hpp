@@ -354,7 +354,7 @@ public:
         n_scan_ = last_status == LLB_OK ? n_scan : 0;
     }
     // runFeatureAssociation FA:1827-1833: the four steps run as one device pass when extractFeatures() is reached
-    void adjustDistortion() { fe_staged_ |= 1; }                   // FA:491 (no IMU data: imuPointerLast < 0)
+    void adjustDistortion() { fe_staged_ |= 1; }                   // FA:491 (IMU branch: when imuHandler has been fed)
     void calculateSmoothness() { fe_staged_ |= 2; }                // FA:621
     void markOccludedPoints() { fe_staged_ |= 4; }                 // FA:643
     void extractFeatures()                                         // FA:680
@@ -374,8 +374,15 @@ public:
         seg.ground_flag = segInfo.segmentedCloudGroundFlag.data(); seg.col_ind = segInfo.segmentedCloudColInd.data();
         seg.range = segInfo.segmentedCloudRange.data();
         int counts[4] = { 0, 0, 0, 0 };
+        if (imuPointerLast >= 0) {                           // FA:525: the IMU branch of adjustDistortion runs on the device
+            imu_.time_scan_cur = timeScanCur; imu_.pointer_last = imuPointerLast; imu_.pointer_last_iteration = imuPointerLastIteration;
+            last_status = llb_features_set_imu(ctx_, &imu_);
+            if (last_status != LLB_OK) return;
+        }
         last_status = llb_features_extract(ctx_, &seg, counts, nullptr);
         if (last_status != LLB_OK) return;
+        if (imuPointerLast >= 0) pull_imu_sweep();
+        imuPointerLastIteration = imuPointerLast;            // FA:616
         Cloud *out[5] = { cornerPointsSharp.get(), cornerPointsLessSharp.get(), surfPointsFlat.get(), surfPointsLessFlat.get(),
                           segmentedCloud.get() };
         for (int k = 0; k < 5; k++) {
@@ -391,7 +398,13 @@ public:
     // which become laserCloudCornerLast / laserCloudSurfLast (indexed on the device); fetch = copy them to the members too
     void publishCloudsLast(bool fetch = true)
     {
-        last_status = llb_features_publish_last(ctx_, transformCur);
+        llb_imu_end e;                                       // updateImuRollPitchYawStartSinCos FA:317-324 + the members FA:927-950 reads
+        e.cs_start[0] = std::cos(imuRollStart); e.cs_start[1] = std::sin(imuRollStart);
+        e.cs_start[2] = std::cos(imuPitchStart); e.cs_start[3] = std::sin(imuPitchStart);
+        e.cs_start[4] = std::cos(imuYawStart); e.cs_start[5] = std::sin(imuYawStart);
+        e.shift_from_start[0] = imuShiftFromStartX; e.shift_from_start[1] = imuShiftFromStartY; e.shift_from_start[2] = imuShiftFromStartZ;
+        e.last[0] = imuRollLast; e.last[1] = imuPitchLast; e.last[2] = imuYawLast;
+        last_status = llb_features_publish_last_imu(ctx_, transformCur, &e);
         if (last_status != LLB_OK) return;
         Cloud *out[2] = { laserCloudCornerLast.get(), laserCloudSurfLast.get() };
         int n[2] = { 0, 0 };
@@ -402,6 +415,80 @@ public:
         }
         laserCloudCornerLastNum = n[0]; laserCloudSurfLastNum = n[1];
     }
+
+    // ---- IMU.  imuHandler FA:417-448 after tf's quaternion -> roll / pitch / yaw (tf is the caller's):
+    // gravity compensation, ring-buffer entry, AccumulateIMUShiftAndRotation FA:390-415.  One message at a time and a few
+    // dozen flops each: host work; the per-point use of the buffers runs on the device (llb_features_set_imu).
+    void imuHandler(double stamp, double roll, double pitch, double yaw, const double linear_acceleration[3],
+                    const double angular_velocity[3])
+    {
+        const float accX = (float)(linear_acceleration[1] - std::sin(roll) * std::cos(pitch) * 9.81);
+        const float accY = (float)(linear_acceleration[2] - std::cos(roll) * std::cos(pitch) * 9.81);
+        const float accZ = (float)(linear_acceleration[0] + std::sin(pitch) * 9.81);
+        imuPointerLast = (imuPointerLast + 1) % imuQueLength;
+        const int l = imuPointerLast;
+        imu_.time[l] = stamp;
+        imu_.roll[l] = (float)roll; imu_.pitch[l] = (float)pitch; imu_.yaw[l] = (float)yaw;
+        imuAcc[0][l] = accX; imuAcc[1][l] = accY; imuAcc[2][l] = accZ;
+        for (int a = 0; a < 3; a++) imuAngularVelo[a][l] = (float)angular_velocity[a];
+        AccumulateIMUShiftAndRotation();
+    }
+    void AccumulateIMUShiftAndRotation()                     // FA:390
+    {
+        const int l = imuPointerLast;
+        const float roll = imu_.roll[l], pitch = imu_.pitch[l], yaw = imu_.yaw[l];
+        float accX = imuAcc[0][l], accY = imuAcc[1][l], accZ = imuAcc[2][l];
+        const float x1 = std::cos(roll) * accX - std::sin(roll) * accY;
+        const float y1 = std::sin(roll) * accX + std::cos(roll) * accY;
+        const float z1 = accZ;
+        const float x2 = x1;
+        const float y2 = std::cos(pitch) * y1 - std::sin(pitch) * z1;
+        const float z2 = std::sin(pitch) * y1 + std::cos(pitch) * z1;
+        accX = std::cos(yaw) * x2 + std::sin(yaw) * z2;
+        accY = y2;
+        accZ = -std::sin(yaw) * x2 + std::cos(yaw) * z2;
+        const float acc[3] = { accX, accY, accZ };
+        const int b = (l + imuQueLength - 1) % imuQueLength;
+        const double timeDiff = imu_.time[l] - imu_.time[b];
+        if (timeDiff < scanPeriod) {
+            for (int a = 0; a < 3; a++) {
+                imu_.shift[a][l] = (float)(imu_.shift[a][b] + imu_.velo[a][b] * timeDiff + acc[a] * timeDiff * timeDiff / 2);
+                imu_.velo[a][l] = (float)(imu_.velo[a][b] + acc[a] * timeDiff);
+                imu_.angular[a][l] = (float)(imu_.angular[a][b] + imuAngularVelo[a][b] * timeDiff);
+            }
+        }
+    }
+    void laserCloudHandlerStamp(double stamp) { timeScanCur = stamp; }         // FA:453
+    void updateInitialGuess()                                // FA:1639
+    {
+        imuPitchLast = imuPitchCur; imuYawLast = imuYawCur; imuRollLast = imuRollCur;
+        imuShiftFromStartX = imuShiftFromStartXCur; imuShiftFromStartY = imuShiftFromStartYCur; imuShiftFromStartZ = imuShiftFromStartZCur;
+        imuVeloFromStartX = imuVeloFromStartXCur; imuVeloFromStartY = imuVeloFromStartYCur; imuVeloFromStartZ = imuVeloFromStartZCur;
+        if (imuAngularFromStartX != 0 || imuAngularFromStartY != 0 || imuAngularFromStartZ != 0) {
+            transformCur[0] = -imuAngularFromStartY; transformCur[1] = -imuAngularFromStartZ; transformCur[2] = -imuAngularFromStartX;
+        }
+        if (imuVeloFromStartX != 0 || imuVeloFromStartY != 0 || imuVeloFromStartZ != 0) {
+            transformCur[3] -= imuVeloFromStartX * scanPeriod; transformCur[4] -= imuVeloFromStartY * scanPeriod;
+            transformCur[5] -= imuVeloFromStartZ * scanPeriod;
+        }
+    }
+    static constexpr int imuQueLength = LLB_IMU_QUEUE;       // UT:109
+    static constexpr float scanPeriod = 0.1f;                // UT:107
+    double timeScanCur = 0;                                  // FA:67
+    int imuPointerLast = -1, imuPointerLastIteration = 0;    // FA:84-85 (FA:268-269)
+    llb_imu_queue imu_ = {};                                 // imuTime, imuRoll/Pitch/Yaw, imuVelo*, imuShift*, imuAngularRotation* FA:105-127
+    float imuAcc[3][LLB_IMU_QUEUE] = {}, imuAngularVelo[3][LLB_IMU_QUEUE] = {};   // FA:112-114, FA:124-126 (host only)
+    float imuRollStart = 0, imuPitchStart = 0, imuYawStart = 0;                  // FA:87-90
+    float imuRollCur = 0, imuPitchCur = 0, imuYawCur = 0;
+    float imuVeloXStart = 0, imuVeloYStart = 0, imuVeloZStart = 0, imuShiftXStart = 0, imuShiftYStart = 0, imuShiftZStart = 0;
+    float imuShiftFromStartXCur = 0, imuShiftFromStartYCur = 0, imuShiftFromStartZCur = 0;   // never written: ShiftToStartIMU has no caller
+    float imuVeloFromStartXCur = 0, imuVeloFromStartYCur = 0, imuVeloFromStartZCur = 0;
+    float imuAngularRotationXCur = 0, imuAngularRotationYCur = 0, imuAngularRotationZCur = 0;
+    float imuAngularRotationXLast = 0, imuAngularRotationYLast = 0, imuAngularRotationZLast = 0;
+    float imuAngularFromStartX = 0, imuAngularFromStartY = 0, imuAngularFromStartZ = 0;
+    float imuRollLast = 0, imuPitchLast = 0, imuYawLast = 0;
+    float imuShiftFromStartX = 0, imuShiftFromStartY = 0, imuShiftFromStartZ = 0;
+    float imuVeloFromStartX = 0, imuVeloFromStartY = 0, imuVeloFromStartZ = 0;
 
     // replaces the two kdtree->setInputCloud calls of FA:1615-1616 / FA:1786-1787
     void setLastClouds()
@@ -433,6 +520,24 @@ public:
     llb_ctx *context() { return ctx_; }
 
 private:
+    void pull_imu_sweep()                // the members adjustDistortion's IMU branch writes (FA:556-611), from the device pass
+    {
+        llb_imu_sweep w;
+        last_status = llb_features_get_imu(ctx_, &w);
+        if (last_status != LLB_OK || !w.valid) return;
+        imuRollStart = w.start[0]; imuPitchStart = w.start[1]; imuYawStart = w.start[2];
+        imuVeloXStart = w.start[3]; imuVeloYStart = w.start[4]; imuVeloZStart = w.start[5];
+        imuShiftXStart = w.start[6]; imuShiftYStart = w.start[7]; imuShiftZStart = w.start[8];
+        imuAngularRotationXCur = w.angular_cur[0]; imuAngularRotationYCur = w.angular_cur[1]; imuAngularRotationZCur = w.angular_cur[2];
+        imuAngularFromStartX = imuAngularRotationXCur - imuAngularRotationXLast;           // FA:596-602
+        imuAngularFromStartY = imuAngularRotationYCur - imuAngularRotationYLast;
+        imuAngularFromStartZ = imuAngularRotationZCur - imuAngularRotationZLast;
+        imuAngularRotationXLast = imuAngularRotationXCur; imuAngularRotationYLast = imuAngularRotationYCur;
+        imuAngularRotationZLast = imuAngularRotationZCur;
+        imuRollCur = w.cur[0]; imuPitchCur = w.cur[1]; imuYawCur = w.cur[2];
+        if (w.has_velo) { imuVeloFromStartXCur = w.velo_from_start_cur[0]; imuVeloFromStartYCur = w.velo_from_start_cur[1];
+                          imuVeloFromStartZCur = w.velo_from_start_cur[2]; }
+    }
     void push_features()                 // once per sweep: the step-wise calls (<= 50 per sweep) do not upload again
     {
         if (features_pushed_) return;

@@ -228,6 +228,23 @@ class FeatureAssociation:
         assert n <= cap
         return out[:n].copy()
 
+    # ---- IMU (FA:417-448 and the IMU branches of adjustDistortion / TransformToEnd / updateInitialGuess)
+    def push_imu(self, stamp, roll, pitch, yaw, lin_acc, ang_vel):
+        """imuHandler after the quaternion -> roll / pitch / yaw conversion"""
+        la = (ctypes.c_double * 3)(*[float(x) for x in lin_acc]); av = (ctypes.c_double * 3)(*[float(x) for x in ang_vel])
+        self.L.ref_fa_push_imu(self._h, ctypes.c_double(stamp), ctypes.c_double(roll), ctypes.c_double(pitch), ctypes.c_double(yaw), la, av)
+
+    def set_time_scan_cur(self, t): self.L.ref_fa_set_time_scan_cur(self._h, ctypes.c_double(t))
+    def updateInitialGuess(self): self.L.ref_fa_updateInitialGuess(self._h)
+
+    def imu_state(self):
+        o = np.zeros(24, np.float32); self.L.ref_fa_get_imu_state(self._h, _fp(o)); return o
+
+    def imu_entry(self, idx=-1):
+        t = ctypes.c_double(0); o = np.zeros(12, np.float32)
+        i = self.L.ref_fa_get_imu_entry(self._h, int(idx), ctypes.byref(t), _fp(o))
+        return i, t.value, o
+
     def publishCloudsLast(self):
         """FA:1759-1815; afterwards feature_cloud(5) / feature_cloud(6) = laserCloudCornerLast / laserCloudSurfLast."""
         self.L.ref_fa_publishCloudsLast(self._h)

@@ -153,6 +153,55 @@ void ref_fa_std_sort(float *value, unsigned long long *ind, int n, int depth_lim
 }
 
 // the per-sweep bookkeeping around the matcher, for sequence replays (FA:1639-1725, FA:1759-1788)
+// ---- IMU (FA:417-448): imuHandler after the quaternion -> roll / pitch / yaw conversion (tf is not part of the path):
+// gravity compensation, ring-buffer entry, AccumulateIMUShiftAndRotation (the reference's own member function)
+void ref_fa_push_imu(void *h, double stamp, double roll, double pitch, double yaw, const double lin_acc[3], const double ang_vel[3])
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    float accX = lin_acc[1] - sin(roll) * cos(pitch) * 9.81;
+    float accY = lin_acc[2] - cos(roll) * cos(pitch) * 9.81;
+    float accZ = lin_acc[0] + sin(pitch) * 9.81;
+    f->imuPointerLast = (f->imuPointerLast + 1) % imuQueLength;
+    f->imuTime[f->imuPointerLast] = stamp;
+    f->imuRoll[f->imuPointerLast] = roll;
+    f->imuPitch[f->imuPointerLast] = pitch;
+    f->imuYaw[f->imuPointerLast] = yaw;
+    f->imuAccX[f->imuPointerLast] = accX;
+    f->imuAccY[f->imuPointerLast] = accY;
+    f->imuAccZ[f->imuPointerLast] = accZ;
+    f->imuAngularVeloX[f->imuPointerLast] = ang_vel[0];
+    f->imuAngularVeloY[f->imuPointerLast] = ang_vel[1];
+    f->imuAngularVeloZ[f->imuPointerLast] = ang_vel[2];
+    f->AccumulateIMUShiftAndRotation();
+}
+void ref_fa_set_time_scan_cur(void *h, double t) { ((FeatureAssociation *)h)->timeScanCur = t; }
+void ref_fa_updateInitialGuess(void *h) { ((FeatureAssociation *)h)->updateInitialGuess(); }
+// the IMU state a sweep leaves behind: {imuRoll/Pitch/YawStart, imuVeloX/Y/ZStart, imuShiftX/Y/ZStart, imuRoll/Pitch/YawCur,
+// imuVeloFromStartX/Y/ZCur, imuAngularFromStartX/Y/Z, imuAngularRotationX/Y/ZCur, imuRoll/Pitch/YawLast} (24 floats) and the
+// ring-buffer entry `idx`: {time (as double in out_d), roll, pitch, yaw, velo xyz, shift xyz, angular rotation xyz}
+void ref_fa_get_imu_state(void *h, float *o)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    const float v[24] = { f->imuRollStart, f->imuPitchStart, f->imuYawStart, f->imuVeloXStart, f->imuVeloYStart, f->imuVeloZStart,
+                          f->imuShiftXStart, f->imuShiftYStart, f->imuShiftZStart, f->imuRollCur, f->imuPitchCur, f->imuYawCur,
+                          f->imuVeloFromStartXCur, f->imuVeloFromStartYCur, f->imuVeloFromStartZCur,
+                          f->imuAngularFromStartX, f->imuAngularFromStartY, f->imuAngularFromStartZ,
+                          f->imuAngularRotationXCur, f->imuAngularRotationYCur, f->imuAngularRotationZCur,
+                          f->imuRollLast, f->imuPitchLast, f->imuYawLast };
+    memcpy(o, v, sizeof v);
+}
+int ref_fa_get_imu_entry(void *h, int idx, double *t, float *o)
+{
+    FeatureAssociation *f = (FeatureAssociation *)h;
+    if (idx < 0) idx = f->imuPointerLast;
+    if (idx < 0) return -1;
+    *t = f->imuTime[idx];
+    const float v[12] = { f->imuRoll[idx], f->imuPitch[idx], f->imuYaw[idx], f->imuVeloX[idx], f->imuVeloY[idx], f->imuVeloZ[idx],
+                          f->imuShiftX[idx], f->imuShiftY[idx], f->imuShiftZ[idx],
+                          f->imuAngularRotationX[idx], f->imuAngularRotationY[idx], f->imuAngularRotationZ[idx] };
+    memcpy(o, v, sizeof v);
+    return idx;
+}
 void ref_fa_integrateTransformation(void *h) { ((FeatureAssociation *)h)->integrateTransformation(); }
 void ref_fa_get_transform_sum(void *h, float *t) { memcpy(t, ((FeatureAssociation *)h)->transformSum, 24); }
 }  // extern "C"

@@ -24,6 +24,28 @@ static bool read_cloud(std::ifstream &f, Cloud &c)
     return (bool)f;
 }
 
+static void read_sweep(std::ifstream &f, FeatureAssociation &FE, int n_scan)
+{
+    read_cloud(f, *FE.segmentedCloud);
+    const size_t n = FE.segmentedCloud->size();
+    FE.segInfo.startRingIndex.resize(n_scan); FE.segInfo.endRingIndex.resize(n_scan);
+    f.read((char *)FE.segInfo.startRingIndex.data(), 4 * n_scan); f.read((char *)FE.segInfo.endRingIndex.data(), 4 * n_scan);
+    f.read((char *)&FE.segInfo.startOrientation, 4); f.read((char *)&FE.segInfo.endOrientation, 4); f.read((char *)&FE.segInfo.orientationDiff, 4);
+    FE.segInfo.segmentedCloudGroundFlag.resize(n); FE.segInfo.segmentedCloudColInd.resize(n); FE.segInfo.segmentedCloudRange.resize(n);
+    f.read((char *)FE.segInfo.segmentedCloudGroundFlag.data(), n); f.read((char *)FE.segInfo.segmentedCloudColInd.data(), 4 * n);
+    f.read((char *)FE.segInfo.segmentedCloudRange.data(), 4 * n);
+}
+
+static unsigned fnv_cloud(const Cloud &c, bool with_intensity)
+{
+    unsigned h = 2166136261u;                          // FNV-1a over the x, y, z (, intensity) words
+    for (const PointType &p : c.points) {
+        const float v[4] = { p.x, p.y, p.z, p.intensity };
+        for (int a = 0; a < (with_intensity ? 4 : 3); a++) { unsigned w; memcpy(&w, &v[a], 4); h = (h ^ w) * 16777619u; }
+    }
+    return h;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 2) return 2;
@@ -69,14 +91,7 @@ int main(int argc, char **argv)
     if (!f) return 0;
     FeatureAssociation FE;
     FE.initFeatureExtraction(n_scan, horizon);
-    read_cloud(f, *FE.segmentedCloud);
-    const size_t n = FE.segmentedCloud->size();
-    FE.segInfo.startRingIndex.resize(n_scan); FE.segInfo.endRingIndex.resize(n_scan);
-    f.read((char *)FE.segInfo.startRingIndex.data(), 4 * n_scan); f.read((char *)FE.segInfo.endRingIndex.data(), 4 * n_scan);
-    f.read((char *)&FE.segInfo.startOrientation, 4); f.read((char *)&FE.segInfo.endOrientation, 4); f.read((char *)&FE.segInfo.orientationDiff, 4);
-    FE.segInfo.segmentedCloudGroundFlag.resize(n); FE.segInfo.segmentedCloudColInd.resize(n); FE.segInfo.segmentedCloudRange.resize(n);
-    f.read((char *)FE.segInfo.segmentedCloudGroundFlag.data(), n); f.read((char *)FE.segInfo.segmentedCloudColInd.data(), 4 * n);
-    f.read((char *)FE.segInfo.segmentedCloudRange.data(), 4 * n);
+    read_sweep(f, FE, n_scan);
     FE.adjustDistortion(); FE.calculateSmoothness(); FE.markOccludedPoints(); FE.extractFeatures();
     const Cloud *out[4] = { FE.cornerPointsSharp.get(), FE.cornerPointsLessSharp.get(), FE.surfPointsFlat.get(), FE.surfPointsLessFlat.get() };
     printf("FE %d", FE.last_status);
@@ -89,5 +104,41 @@ int main(int argc, char **argv)
         printf(" %zu %u", out[k]->size(), h);
     }
     printf("\n");
+    // IMU branches (FA:417-448 imuHandler + AccumulateIMUShiftAndRotation on the host, adjustDistortion's IMU branch and
+    // TransformToEnd's IMU terms on the device, updateInitialGuess): two sweeps, each preceded by a block of messages
+    int n_sweeps = 0;
+    f.read((char *)&n_sweeps, 4);
+    if (!f) return 0;
+    FeatureAssociation FI;
+    FI.initFeatureExtraction(n_scan, horizon);
+    for (int sweep = 0; sweep < n_sweeps; sweep++) {
+        int n_msg = 0;
+        f.read((char *)&n_msg, 4);
+        for (int k = 0; k < n_msg; k++) {
+            double v[10];
+            f.read((char *)v, 80);
+            FI.imuHandler(v[0], v[1], v[2], v[3], v + 4, v + 7);
+        }
+        double stamp = 0;
+        f.read((char *)&stamp, 8);
+        FI.laserCloudHandlerStamp(stamp);
+        read_sweep(f, FI, n_scan);
+        FI.adjustDistortion(); FI.calculateSmoothness(); FI.markOccludedPoints(); FI.extractFeatures();
+        f.read((char *)FI.transformCur, 24);
+        FI.updateInitialGuess();
+        const float st[24] = { FI.imuRollStart, FI.imuPitchStart, FI.imuYawStart, FI.imuVeloXStart, FI.imuVeloYStart, FI.imuVeloZStart,
+                               FI.imuShiftXStart, FI.imuShiftYStart, FI.imuShiftZStart, FI.imuRollCur, FI.imuPitchCur, FI.imuYawCur,
+                               FI.imuVeloFromStartXCur, FI.imuVeloFromStartYCur, FI.imuVeloFromStartZCur,
+                               FI.imuAngularFromStartX, FI.imuAngularFromStartY, FI.imuAngularFromStartZ,
+                               FI.imuAngularRotationXCur, FI.imuAngularRotationYCur, FI.imuAngularRotationZCur,
+                               FI.imuRollLast, FI.imuPitchLast, FI.imuYawLast };
+        printf("IM %d", FI.last_status);
+        for (int k = 0; k < 24; k++) { unsigned w; memcpy(&w, &st[k], 4); printf(" %u", w); }
+        for (int k = 0; k < 6; k++) { unsigned w; memcpy(&w, &FI.transformCur[k], 4); printf(" %u", w); }
+        printf(" %zu %u", FI.segmentedCloud->size(), fnv_cloud(*FI.segmentedCloud, true));
+        FI.publishCloudsLast();
+        printf(" %zu %u %zu %u\n", FI.laserCloudCornerLast->size(), fnv_cloud(*FI.laserCloudCornerLast, true),
+               FI.laserCloudSurfLast->size(), fnv_cloud(*FI.laserCloudSurfLast, true));
+    }
     return 0;
 }

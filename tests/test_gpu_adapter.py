@@ -53,6 +53,27 @@ def test_adapter_matches_oracle(tmp_path):
         f.write(struct.pack("fff", sw.start_ori, sw.end_ori, sw.ori_diff))
         f.write(sw.ground.astype(np.uint8).tobytes()); f.write(sw.col.astype(np.uint32).tobytes())
         f.write(sw.range.astype(np.float32).tobytes())
+        # IMU block: two sweeps, each preceded by IMU messages (the second block wraps the 200-entry ring)
+        from tests.test_gpu_imu import imu_messages
+        imu_sweeps = []
+        t_msg, yaw0 = 2000.0, 3.02
+        f.write(struct.pack("i", 2))
+        for s_no, n_msg in enumerate((60, 170)):
+            msgs = imu_messages(n_msg, t_msg, 20 + s_no, yaw0)
+            t_msg = msgs[-1][0] + 0.005; yaw0 = msgs[-1][3] + 0.004
+            stamp = msgs[-1][0] - 0.15
+            swi = synth.make_segmented_sweep(synth.make_world(), synth.VLP16, [0, 0.05 + 0.1 * s_no, 0, 3, 0, 5 + s_no], 5 + s_no)
+            t_cur = np.array([0.002, 0.01, -0.001, 0.05, 0.01, 0.12], np.float32) * (1 + s_no)
+            f.write(struct.pack("i", n_msg))
+            for m in msgs:
+                f.write(struct.pack("10d", m[0], m[1], m[2], m[3], *m[4], *m[5]))
+            f.write(struct.pack("d", stamp)); w(swi.cloud)
+            f.write(swi.start_ring.astype(np.int32).tobytes()); f.write(swi.end_ring.astype(np.int32).tobytes())
+            f.write(struct.pack("fff", swi.start_ori, swi.end_ori, swi.ori_diff))
+            f.write(swi.ground.astype(np.uint8).tobytes()); f.write(swi.col.astype(np.uint32).tobytes())
+            f.write(swi.range.astype(np.float32).tobytes())
+            f.write(t_cur.tobytes())
+            imu_sweeps.append((msgs, stamp, swi, t_cur))
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
     mo_line = out[0].split(); tu_line = out[1].split(); fa_line = out[2].split()
 
@@ -105,3 +126,28 @@ def test_adapter_matches_oracle(tmp_path):
     for k in range(4):
         assert int(fe_line[2 + 2 * k]) == want[k].shape[0]
         assert int(fe_line[3 + 2 * k]) == fnv(want[k])
+
+    # IMU branches through the adapter (host ring buffers + device per-point work) against the compiled reference
+    if rh.available():
+        def fnv4(cloud):
+            h = 2166136261
+            for wd in np.ascontiguousarray(cloud, np.float32).view(np.uint32).ravel().tolist():
+                h = ((h ^ wd) * 16777619) & 0xFFFFFFFF
+            return h
+        rfa = rh.FeatureAssociation()
+        for s_no, (msgs, stamp, swi, t_cur) in enumerate(imu_sweeps):
+            for m in msgs:
+                rfa.push_imu(*m)
+            rfa.set_time_scan_cur(stamp); rfa.set_segmented(swi); rfa.extract_features()
+            rfa.transformCur = t_cur
+            rfa.updateInitialGuess()
+            line = out[4 + s_no].split()
+            assert line[0] == "IM" and int(line[1]) == 0
+            got = np.array([int(x) for x in line[2:32]], np.uint32)
+            want = np.concatenate([rfa.imu_state(), rfa.transformCur]).view(np.uint32)
+            assert np.array_equal(got, want), (s_no, got.view(np.float32), want.view(np.float32))
+            seg = rfa.feature_cloud(4)
+            assert (int(line[32]), int(line[33])) == (seg.shape[0], fnv4(seg))
+            rfa.publishCloudsLast()
+            cl, sl = rfa.feature_cloud(5), rfa.feature_cloud(6)
+            assert (int(line[34]), int(line[35]), int(line[36]), int(line[37])) == (cl.shape[0], fnv4(cl), sl.shape[0], fnv4(sl))
