@@ -260,6 +260,11 @@ class FeatureAssociation:
     def calculateTransformationSurf(self, it) -> bool: return bool(self.L.ref_fa_calculateTransformationSurf(self._h, it))
     def calculateTransformationCorner(self, it) -> bool: return bool(self.L.ref_fa_calculateTransformationCorner(self._h, it))
     def updateTransformation(self): self.L.ref_fa_updateTransformation(self._h)
+    def integrateTransformation(self): self.L.ref_fa_integrateTransformation(self._h)
+
+    @property
+    def transformSum(self):
+        t = np.zeros(6, np.float32); self.L.ref_fa_get_transform_sum(self._h, _fp(t)); return t
 
     def correspondences(self):
         n = self.L.ref_fa_get_correspondences(self._h, None, None, 0)
