@@ -603,54 +603,78 @@ def feature_extraction_arm(api, local, reps, cpu_sample):
 
 
 def sharded_arm(api, torch, dist, local, rank, world, workload="vls128_2m"):
-    """BASELINE config 4 (only with WORLD_SIZE > 1): ONE registration of a VLS-128 sweep against a ~2M-point voxel-DS map
-    with the queries sharded over the ranks (qi = rank + world * j) and the 28 fp64 sums of every LM iteration exchanged
-    (a) by P2P stores over NVLink fused into the persistent kernel, (b) by an NCCL all-reduce driven from the host.  The
-    voxel-DS map and its index are REPLICATED on every rank (each rank filters and indexes the whole map): what shards
-    is the kNN + fit + accumulation work.  Poses must be bit-identical across ranks and equal the single-GPU pose."""
+    """BASELINE config 4 (only with WORLD_SIZE > 1): ONE mapping cycle of a VLS-128 sweep against a ~2M-point voxel-DS map
+    (8M raw points, device-resident on every rank as replicated key-frame stores leave them).
+    map_sharded (preferred form): every rank voxel-filters and indexes only its slab of the raw map (on the
+    lattice of the whole map) and takes the queries inside its slab, so the map-side work AND the kNN + fit work divide by
+    the number of ranks; the 28 fp64 sums of every LM iteration are exchanged by P2P stores over NVLink fused into the
+    persistent kernel.  query_sharded (round 1): DS map + index replicated, queries dealt round-robin, exchange fused or
+    by an NCCL all-reduce driven from the host.  Poses must be bit-identical across ranks and equal the single-GPU pose."""
     from lego_loam_b200 import multi_gpu
     mc, ms, scans = make_inputs(workload, 0, 1)              # identical inputs on every rank (same seeds)
     sc, init = scans[0]
+    dev = torch.device("cuda", local)
+    mc_d = torch.as_tensor(np.ascontiguousarray(mc, np.float32), device=dev)
+    ms_d = torch.as_tensor(np.ascontiguousarray(ms, np.float32), device=dev)
+    ptrs = (mc_d.data_ptr(), int(mc.shape[0]), ms_d.data_ptr(), int(ms.shape[0]))
+    torch.cuda.synchronize()
     ctx = api.Context(local)
-    ctx.map_set_raw(mc, ms); ctx.synchronize()               # (first call: workspace allocation)
-    mc32, ms32 = api.to_pcl(mc), api.to_pcl(ms)
-    t0 = time.perf_counter()
-    ctx.map_set_raw_pcl(mc32, ms32)
-    ctx.synchronize()
-    map_ms = (time.perf_counter() - t0) * 1e3                # H2D + map voxel filters + index build (replicated, not sharded)
+
+    def timed(fn, reps, skip=1):
+        out = []
+        for _ in range(reps):
+            torch.cuda.synchronize(); dist.barrier()
+            t0 = time.perf_counter(); r = fn(); ctx.synchronize()
+            out.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(out[skip:])), r
+
+    # ---- one GPU alone: map voxel filters + index over the whole raw map, then the registration
+    map_single_ms, _ = timed(lambda: ctx.map_set_raw_dev(*ptrs), 4)
+    n_ds = [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])]
     ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last)
     counts = ctx.downsample_current_scan()
     single = []
     for _ in range(5):
         T_single, st = ctx.s2m_optimize(init); single.append(st.device_ms)
-    nccl = []
-    for _ in range(4):
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        T_nccl, it_nccl = multi_gpu.sharded_scan2map(ctx, init, rank, world)
-        torch.cuda.synchronize()
-        nccl.append((time.perf_counter() - t0) * 1e3)
+    # ---- query-sharded over the replicated DS map (round-1 form): NCCL-driven and fused exchange
+    nccl_ms, (T_nccl, it_nccl) = timed(lambda: multi_gpu.sharded_scan2map(ctx, init, rank, world), 4)
     multi_gpu.setup_fused_exchange(ctx, rank, world)
-    fused_dev, fused_wall = [], []
-    for _ in range(8):
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        T_fused, st_f = multi_gpu.sharded_scan2map_fused(ctx, init)
-        fused_wall.append((time.perf_counter() - t0) * 1e3); fused_dev.append(st_f.device_ms)
+    fused_dev = []
+    fused_wall, (T_fused, st_f) = timed(lambda: (lambda r: (fused_dev.append(r[1].device_ms), r)[1])(multi_gpu.sharded_scan2map_fused(ctx, init)), 8, 2)
+    # ---- map-sharded: slab of the raw map per rank (filters + index divide by the number of ranks), fused exchange
+    infos = []
+    map_shard_ms, _ = timed(lambda: infos.append(multi_gpu.set_sharded_map(ctx, None, None, rank, world, device_ptrs=ptrs)), 4)
+    info = infos[-1]
+    ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last); ctx.downsample_current_scan()
+    slab_dev = []
+    slab_wall, (T_slab, st_s) = timed(lambda: (lambda r: (slab_dev.append(r[1].device_ms), r)[1])(multi_gpu.sharded_scan2map_fused(ctx, init)), 8, 2)
     gathered = [None] * world
-    dist.all_gather_object(gathered, (np.asarray(T_fused, np.float32).tobytes(), float(np.median(fused_dev[2:]))))
-    same = all(g[0] == gathered[0][0] for g in gathered)
-    out = {"workload": workload, "world": world, "queries": int(counts[0] + counts[3]),
-           "map_points": [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])], "raw_map_points": int(mc.shape[0] + ms.shape[0]),
-           "iterations": int(st.iterations), "single_gpu_device_ms": float(np.median(single[1:])),
-           "fused_device_ms_max_over_ranks": float(max(g[1] for g in gathered)), "fused_wall_ms": float(np.median(fused_wall[2:])),
-           "nccl_wall_ms": float(np.median(nccl[1:])), "bytes_per_iteration_per_rank": 28 * 8 * (world - 1),
-           "pose_bit_identical_across_ranks": bool(same),
-           "pose_equals_single_gpu": bool(np.array_equal(np.asarray(T_fused, np.float32), np.asarray(T_single, np.float32))),
-           "fused_equals_nccl": bool(np.array_equal(np.asarray(T_fused, np.float32), np.asarray(T_nccl, np.float32))),
-           "replicated_map_upload_voxel_index_wall_ms": map_ms,
-           "note": "queries sharded, voxel-DS map + index replicated on every rank (the map-side work does not divide by the "
-                   "number of GPUs); exchange = 28 fp64 per rank and LM iteration"}
+    dist.all_gather_object(gathered, dict(fused=np.asarray(T_fused, np.float32).tobytes(), slab=np.asarray(T_slab, np.float32).tobytes(),
+                                          fused_dev=float(np.median(fused_dev[2:])), slab_dev=float(np.median(slab_dev[2:])),
+                                          map_shard_ms=map_shard_ms, map_single_ms=map_single_ms,
+                                          raw_kept=int(info.raw_kept[0] + info.raw_kept[1]), ds_local=int(info.ds_local[0] + info.ds_local[1])))
+    g0 = gathered[0]
+    t_single = np.asarray(T_single, np.float32).tobytes()
+    map_sh = max(g["map_shard_ms"] for g in gathered); slab_reg = max(g["slab_dev"] for g in gathered)
+    out = {"workload": workload, "world": world, "queries": int(counts[0] + counts[3]), "map_points": n_ds,
+           "raw_map_points": int(mc.shape[0] + ms.shape[0]), "iterations": int(st.iterations),
+           "single_gpu": {"map_voxel_index_ms": map_single_ms, "registration_device_ms": float(np.median(single[1:])),
+                          "cycle_ms": map_single_ms + float(np.median(single[1:]))},
+           "map_sharded": {"map_voxel_index_ms_max_over_ranks": map_sh, "registration_device_ms_max_over_ranks": slab_reg,
+                           "registration_wall_ms": slab_wall, "cycle_ms": map_sh + slab_reg,
+                           "raw_points_per_rank": [g["raw_kept"] for g in gathered], "ds_points_per_rank": [g["ds_local"] for g in gathered],
+                           "axis": int(info.axis), "iterations": int(st_s.iterations),
+                           "pose_bit_identical_across_ranks": all(g["slab"] == g0["slab"] for g in gathered),
+                           "pose_equals_single_gpu": g0["slab"] == t_single,
+                           "note": "map_voxel_index_ms = wall clock of the call incl. the slab planning (one small D2H + host sort) and "
+                                   "the all-reduce of the owned DS counts; raw map device-resident on every rank"},
+           "query_sharded": {"fused_device_ms_max_over_ranks": float(max(g["fused_dev"] for g in gathered)), "fused_wall_ms": fused_wall,
+                             "nccl_wall_ms": nccl_ms, "map_voxel_index_ms": max(g["map_single_ms"] for g in gathered),
+                             "pose_bit_identical_across_ranks": all(g["fused"] == g0["fused"] for g in gathered),
+                             "pose_equals_single_gpu": g0["fused"] == t_single,
+                             "fused_equals_nccl": bool(np.array_equal(np.asarray(T_fused, np.float32), np.asarray(T_nccl, np.float32)))},
+           "bytes_per_iteration_per_rank": 28 * 8 * (world - 1),
+           "speedup_cycle_vs_single_gpu": (map_single_ms + float(np.median(single[1:]))) / (map_sh + slab_reg)}
     ctx.close()
     return out
 

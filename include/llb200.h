@@ -174,6 +174,47 @@ int llb_map_assemble(llb_ctx *ctx, const int *ids, const float *poses, int n);
 /* laserCloudCornerFromMap (0) / laserCloudSurfFromMap (1) of the last llb_map_assemble (parity checks) */
 int llb_map_get_raw(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
 
+/* ---- loop closure + global map on the device (loopClosureEnableFlag is off by default, UT:104) ----
+ * The host keeps what it keeps in the reference: the radius search over the key poses (MO:824-837, MO:770-778), the 30 s
+ * test, the pose-graph factor (MO:919-944).  The device does the cloud work on its key-frame store. */
+typedef struct {
+    int    max_iterations;                  /* 100   MO:894 */
+    double max_correspondence_distance;     /* 100   MO:893 */
+    double transformation_epsilon;          /* 1e-6  MO:895 */
+    double euclidean_fitness_epsilon;       /* 1e-6  MO:896 */
+} llb_loop_params;
+typedef struct {
+    float  T[16];                           /* icp.getFinalTransformation(), row-major */
+    int    has_converged;                   /* icp.hasConverged() */
+    int    iterations;
+    int    convergence_state;               /* 0 too few correspondences, 1 iterations, 2 transformation epsilon, 3 absolute
+                                               MSE, 4 relative MSE (pcl::registration::DefaultConvergenceCriteria) */
+    int    n_correspondences;               /* of the last iteration */
+    double fitness_score;                   /* icp.getFitnessScore() */
+    double sums[17];                        /* of the last pass: n, sum p, sum q, sum q p^T, sum d^2 (parity checks) */
+    float  device_ms;
+    int    n_source, n_target;
+} llb_icp_result;
+void llb_loop_params_default(llb_loop_params *p);
+/* cloud part of detectLoopClosure MO:838-861: latestSurfKeyFrameCloud = corner + surf clouds of key-frame latest_id at
+ * latest_pose {roll, pitch, yaw, x, y, z} (points with (int)intensity >= 0, MO:845-849); nearHistorySurfKeyFrameCloud =
+ * corner + surf clouds of hist_ids[] (closestHistoryFrameID - 25 .. + 25 clipped, MO:853-858) at hist_poses[], then
+ * VoxelGrid(history_leaf) (0.4, MO:253).  counts = {latest, history DS} */
+int llb_loop_set_clouds(llb_ctx *ctx, int latest_id, const float latest_pose[6], const int *hist_ids, const float *hist_poses,
+                        int n_hist, float history_leaf, int counts[2]);
+/* the same two clouds handed over by a caller that built them itself (the drop-in members of the adapter) */
+int llb_loop_set_clouds_host(llb_ctx *ctx, const llb_point *latest, int n_latest, const llb_point *history_ds, int n_hist);
+/* pcl::IterativeClosestPoint<PointType, PointType>::align + getFitnessScore as performLoopClosure configures them
+ * (MO:892-904), PCL 1.8's algorithm: one persistent kernel for all iterations (p NULL = the reference's settings) */
+int llb_loop_icp(llb_ctx *ctx, const llb_loop_params *p, llb_icp_result *out);
+/* which: 0 latestSurfKeyFrameCloud, 1 nearHistorySurfKeyFrameCloud, 2 nearHistorySurfKeyFrameCloudDS, 3 globalMapKeyFramesDS */
+int llb_loop_get_cloud(llb_ctx *ctx, int which, llb_point *out, int capacity, int *n);
+/* nearest target index + squared distance of every source point in the last search of llb_loop_icp (the fitness pass) */
+int llb_loop_get_nn(llb_ctx *ctx, int *idx, float *sqdist, int capacity, int *n);
+/* cloud part of publishGlobalMap MO:780-788: corner + surf + outlier clouds of ids[] (globalMapKeyPosesDS order) at
+ * poses[], then VoxelGrid(leaf) (0.4, MO:257); read the result with llb_loop_get_cloud(which = 3) */
+int llb_global_map_assemble(llb_ctx *ctx, const int *ids, const float *poses, int n, float leaf, int *n_out);
+
 /* ---- featureAssociation: feature extraction ----
  * What laserCloudHandler / laserCloudInfoHandler leave in the node (FA:461-489): segmentedCloud in the LIDAR frame with
  * intensity = row + col / 10000 (IP:253), and cloud_msgs::cloud_info. */
@@ -281,6 +322,27 @@ int llb_s2m_solve(llb_ctx *ctx, int iter, int *converged);
 int llb_p2p_export(llb_ctx *ctx, unsigned char handle[64]);
 int llb_p2p_import(llb_ctx *ctx, int rank, int world, const unsigned char *handles /* world x 64 bytes */);
 int llb_s2m_optimize_sharded(llb_ctx *ctx, float T[6], llb_stats *stats);
+/* ---- the same registration with the MAP sharded (preferred form): every rank is given the same raw local
+ * map (its key-frame stores are replicas: each key-frame crossed PCIe once) but keeps, voxel-filters (MO:1057-1064) and
+ * indexes (MO:1333-1334) only a slab of it - the voxels that can hold a centroid within the kNN gate of a query inside
+ * the slab - on the lattice of the whole map, so voxel membership, order and centroids are those of the unsharded
+ * filter and the map-side work divides by the number of ranks.  The slab borders are quantiles of a deterministic
+ * sample of the raw map (one small D2H + host sort inside the call).  llb_s2m_optimize_sharded /
+ * llb_s2m_accumulate(rank 0, world 1) then take the queries whose mapped position lies inside the slab; the exchange
+ * per LM iteration stays the 28 fp64 sums.  The guard MO:1331 needs the sizes of the UNSHARDED DS maps: all-reduce
+ * llb_shard_info.ds_owned over the ranks (plumbing) and hand the sums to llb_map_shard_set_global; without that call
+ * the guard looks at this rank's part. */
+typedef struct {
+    int axis; float lo, hi;                 /* this rank owns mapped coordinates lo <= p[axis] < hi */
+    int rank, world;
+    int raw_kept[2];                        /* raw corner / surf points this rank filtered */
+    int ds_local[2];                        /* centroids it holds (slab + halo) */
+    int ds_owned[2];                        /* centroids inside the slab: sums over the ranks = sizes of the unsharded maps */
+} llb_shard_info;
+int llb_map_set_raw_sharded(llb_ctx *ctx, const llb_point *corner, int rc, const llb_point *surf, int rs, int rank, int world);
+int llb_map_set_raw_sharded_dev(llb_ctx *ctx, const void *corner_f4, int rc, const void *surf_f4, int rs, int rank, int world);
+int llb_map_shard_info(llb_ctx *ctx, llb_shard_info *out);
+int llb_map_shard_set_global(llb_ctx *ctx, const int global_ds[2]);
 int llb_s2m_pose_set(llb_ctx *ctx, const float T[6]);
 int llb_s2m_pose_get(llb_ctx *ctx, float T[6]);
 

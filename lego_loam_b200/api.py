@@ -67,6 +67,9 @@ EXPORTS = [
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
+    "llb_map_set_raw_sharded", "llb_map_set_raw_sharded_dev", "llb_map_shard_info", "llb_map_shard_set_global",
+    "llb_loop_params_default", "llb_loop_set_clouds", "llb_loop_set_clouds_host", "llb_loop_icp", "llb_loop_get_cloud",
+    "llb_loop_get_nn", "llb_global_map_assemble",
     "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
     "llb_features_set_imu", "llb_features_get_imu", "llb_features_publish_last_imu",
     "llb_projection_init", "llb_projection_process", "llb_projection_get_cloud", "llb_projection_get_info",
@@ -597,6 +600,67 @@ class Context:
         self._ck(lib().llb_s2m_optimize_sharded(self._h, _fp(t), ctypes.byref(st)))
         return t, st
 
+    # ---- loop closure + global map
+    def loop_set_clouds(self, latest_id: int, latest_pose, hist_ids, hist_poses, history_leaf: float = 0.4):
+        """cloud part of detectLoopClosure MO:838-861 on the device key-frame store -> (n latest, n history DS)"""
+        lp = np.ascontiguousarray(latest_pose, np.float32)
+        ids = np.ascontiguousarray(hist_ids, np.int32); hp = np.ascontiguousarray(hist_poses, np.float32).reshape(-1, 6)
+        cnt = (ctypes.c_int * 2)()
+        self._ck(lib().llb_loop_set_clouds(self._h, int(latest_id), _fp(lp), ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                           _fp(hp), ids.shape[0], ctypes.c_float(history_leaf), cnt))
+        return cnt[0], cnt[1]
+
+    def loop_set_clouds_host(self, latest, history_ds):
+        a = to_pcl(latest); b = to_pcl(history_ds)
+        self._hold("loop", (a, b))
+        self._ck(lib().llb_loop_set_clouds_host(self._h, _vp(a), a.shape[0], _vp(b), b.shape[0]))
+
+    def loop_icp(self, params: "LoopParams | None" = None) -> "IcpResult":
+        out = IcpResult()
+        self._ck(lib().llb_loop_icp(self._h, ctypes.byref(params) if params is not None else None, ctypes.byref(out)))
+        return out
+
+    def loop_get_cloud(self, which: int) -> np.ndarray:
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_loop_get_cloud(self._h, which, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(n.value, 1), 8), np.float32)
+        self._ck(lib().llb_loop_get_cloud(self._h, which, _vp(out), n.value, ctypes.byref(n)))
+        return from_pcl(out[:n.value])
+
+    def loop_get_nn(self):
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_loop_get_nn(self._h, None, None, 0, ctypes.byref(n)))
+        idx = np.zeros(max(n.value, 1), np.int32); d2 = np.zeros(max(n.value, 1), np.float32)
+        self._ck(lib().llb_loop_get_nn(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(d2), n.value, ctypes.byref(n)))
+        return idx[:n.value], d2[:n.value]
+
+    def global_map_assemble(self, ids, poses, leaf: float = 0.4) -> int:
+        """cloud part of publishGlobalMap MO:780-788; the cloud: loop_get_cloud(3)"""
+        i = np.ascontiguousarray(ids, np.int32); p = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        n = ctypes.c_int(0)
+        self._ck(lib().llb_global_map_assemble(self._h, i.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _fp(p), i.shape[0],
+                                               ctypes.c_float(leaf), ctypes.byref(n)))
+        return n.value
+
+    # ---- sharded local map (BASELINE config 4, map sharded)
+    def map_set_raw_sharded(self, corner, surf, rank: int, world: int):
+        c = to_pcl(corner); s = to_pcl(surf)
+        self._hold("map_raw", (c, s))
+        self._ck(lib().llb_map_set_raw_sharded(self._h, _vp(c), c.shape[0], _vp(s), s.shape[0], rank, world))
+
+    def map_set_raw_sharded_dev(self, corner_ptr: int, rc: int, surf_ptr: int, rs: int, rank: int, world: int):
+        self._ck(lib().llb_map_set_raw_sharded_dev(self._h, ctypes.c_void_p(corner_ptr), rc, ctypes.c_void_p(surf_ptr), rs,
+                                                   rank, world))
+
+    def map_shard_info(self) -> "ShardInfo":
+        out = ShardInfo()
+        self._ck(lib().llb_map_shard_info(self._h, ctypes.byref(out)))
+        return out
+
+    def map_shard_set_global(self, n_corner_ds: int, n_surf_ds: int):
+        g = (ctypes.c_int * 2)(int(n_corner_ds), int(n_surf_ds))
+        self._ck(lib().llb_map_shard_set_global(self._h, g))
+
     def s2m_accumulate(self, it: int, rank: int, world: int) -> int:
         p = ctypes.c_void_p()
         self._ck(lib().llb_s2m_accumulate(self._h, it, rank, world, ctypes.byref(p)))
@@ -606,6 +670,26 @@ class Context:
         conv = ctypes.c_int(0)
         self._ck(lib().llb_s2m_solve(self._h, it, ctypes.byref(conv) if want_converged else None))
         return bool(conv.value)
+
+
+class LoopParams(ctypes.Structure):
+    """llb_loop_params (defaults = MO:893-896)"""
+    _fields_ = [("max_iterations", ctypes.c_int), ("max_correspondence_distance", ctypes.c_double),
+                ("transformation_epsilon", ctypes.c_double), ("euclidean_fitness_epsilon", ctypes.c_double)]
+
+
+class IcpResult(ctypes.Structure):
+    """llb_icp_result"""
+    _fields_ = [("T", ctypes.c_float * 16), ("has_converged", ctypes.c_int), ("iterations", ctypes.c_int),
+                ("convergence_state", ctypes.c_int), ("n_correspondences", ctypes.c_int), ("fitness_score", ctypes.c_double),
+                ("sums", ctypes.c_double * 17), ("device_ms", ctypes.c_float), ("n_source", ctypes.c_int), ("n_target", ctypes.c_int)]
+
+
+class ShardInfo(ctypes.Structure):
+    """llb_shard_info"""
+    _fields_ = [("axis", ctypes.c_int), ("lo", ctypes.c_float), ("hi", ctypes.c_float), ("rank", ctypes.c_int),
+                ("world", ctypes.c_int), ("raw_kept", ctypes.c_int * 2), ("ds_local", ctypes.c_int * 2),
+                ("ds_owned", ctypes.c_int * 2)]
 
 
 class Batch:
@@ -810,6 +894,12 @@ class Batch:
         names = ["unpack", "downsample", "index_build", "knn", "fit", "lm_step"]
         return dict(zip(names, [float(x) for x in ms])), {"knn_ctas_per_slot": geo[0], "fit_ctas_per_slot": geo[1],
                                                           "index_ctas_per_map": geo[2], "query_capacity": geo[3]}
+
+
+def default_loop_params() -> "LoopParams":
+    p = LoopParams()
+    lib().llb_loop_params_default(ctypes.byref(p))
+    return p
 
 
 def default_params() -> Params:

@@ -11,6 +11,8 @@
 #include "keyframes.cuh"
 #include "features.cuh"
 #include "projection.cuh"
+#include "shard.cuh"
+#include "loop.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -63,7 +65,8 @@ struct llb_ctx {
     PinnedBuf<OdomState> pin_ostate;
 
     DevBuf<int> counts;           // device-resident lengths, see enum below
-    enum { C_CORNER_DS = 0, C_SURF_DS, C_OUTLIER_DS, C_SURFTOTAL_DS, C_MAP_CORNER_DS, C_MAP_SURF_DS, C_VOX_TMP, C_N };
+    enum { C_CORNER_DS = 0, C_SURF_DS, C_OUTLIER_DS, C_SURFTOTAL_DS, C_MAP_CORNER_DS, C_MAP_SURF_DS, C_VOX_TMP,
+           C_LOOP_LATEST, C_LOOP_HIST_DS, C_GLOBAL_DS, C_N };
 
     VoxelFilter vox;
     VoxelFilter vox2;             // second set of voxel scratch: the two map filters MO:1057-1064 run concurrently
@@ -106,6 +109,21 @@ struct llb_ctx {
     cudaEvent_t asm_ev = nullptr;
     bool asm_busy = false;
     int asm_rc = 0, asm_rs = 0;
+
+    // loop closure + global map (loop.cuh)
+    IcpSolver icp;
+    DevBuf<float4> loopLatestRaw, loopLatest, loopHistRaw, loopHistDS, globalRaw, globalDS;
+    VoxelFilter vox3;              // scratch of the history / global-map filters (kept apart from the map filters' scratch)
+    PinnedBuf<IcpState> pin_icp;
+    int loop_n_latest = -1, loop_n_hist_raw = 0, loop_n_hist = -1, global_n = -1, loop_n_latest_raw = 0;
+
+    // sharded local map (BASELINE config 4, shard.cuh): plan, this rank's part of the two raw maps, scratch
+    ShardPlan shard{};
+    DevBuf<float4> shardCorner, shardSurf;
+    DevBuf<int> shard_blk, shard_cnt;      // compaction scratch; {kept corner, kept surf, owned corner DS, owned surf DS}
+    DevBuf<float> shard_samp;
+    PinnedBuf<float> shard_samp_pin;
+    int shard_kept[2] = { 0, 0 }, shard_local[2] = { 0, 0 }, shard_owned[2] = { 0, 0 }, shard_global[2] = { -1, -1 };
 
     // fused multi-GPU exchange (sharded registration): this rank's mailbox + the peers' mailboxes mapped through cudaIpc
     unsigned char *p2p_mem = nullptr;
@@ -253,10 +271,14 @@ void build_indices(llb_ctx *c)
     c->launches += GridIndex::build_pair(c->gridCorner, c->mapCornerDS_view, nc, c->mapCornerDS_upper,
                                          c->gridSurf, c->mapSurfDS_view, ns, c->mapSurfDS_upper, radius, c->stream);
     c->map_set = true;
+    // every map setter ends here: the registration kernels learn whether this map is one rank's part of a sharded map
+    c->s2m.set_shard(c->shard.axis, c->shard.lo, c->shard.hi, c->shard.axis >= 0 ? c->shard_global[0] : -1,
+                     c->shard.axis >= 0 ? c->shard_global[1] : -1);
 }
 
 void voxel_map_raw(llb_ctx *c, const float4 *corner, int rc, const float4 *surf, int rs)
 {
+    c->shard = ShardPlan{};                                  // an unsharded map
     c->mapCornerDS.ensure(std::max(rc, 1)); c->mapSurfDS.ensure(std::max(rs, 1));
     VoxelInput a; a.a = corner; a.na = rc;
     VoxelInput b; b.a = surf; b.na = rs;
@@ -362,11 +384,12 @@ int llb_create(const llb_params *p, int device, llb_ctx **out)
         LLB_CUDA(cudaEventCreateWithFlags(&c->asm_ev, cudaEventDisableTiming));
         c->counts.ensure(llb_ctx::C_N);
         LLB_CUDA(cudaMemset(c->counts.p, 0, sizeof(int) * llb_ctx::C_N));
-        c->pin_counts.ensure(llb_ctx::C_N);
+        c->pin_counts.ensure(llb_ctx::C_N + 8);
         c->pin_state.ensure(1);
         c->pin_ostate.ensure(1);
         c->vox.init();
         c->vox2.init();
+        c->vox3.init();
         LLB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         LLB_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
         LLB_CUDA(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
@@ -409,6 +432,9 @@ int llb_destroy(llb_ctx *c)
     if (c->p2p_mem) cudaFree(c->p2p_mem);
     c->features.release();
     c->projection.release();
+    c->icp.release(); c->vox3.release(); c->pin_icp.release();
+    for (DevBuf<float4> *b : { &c->loopLatestRaw, &c->loopLatest, &c->loopHistRaw, &c->loopHistDS, &c->globalRaw, &c->globalDS, &c->shardCorner, &c->shardSurf }) b->release();
+    c->shard_blk.release(); c->shard_cnt.release(); c->shard_samp.release(); c->shard_samp_pin.release();
     c->kfs.release(); c->asmCorner.release(); c->asmSurf.release(); c->asm_segs.release(); c->pin_segs.release();
     if (c->asm_ev) cudaEventDestroy(c->asm_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -478,6 +504,7 @@ int llb_map_set_ds(llb_ctx *c, const llb_point *corner, int mc, const llb_point 
         c->mapCornerDS_view = c->mapCornerDS.p; c->mapSurfDS_view = c->mapSurfDS.p;
         c->mapCornerDS_upper = mc; c->mapSurfDS_upper = ms;
         c->map_counts_on_dev = false;
+        c->shard = ShardPlan{};
         build_indices(c);
         return (int)LLB_OK;
     });
@@ -490,6 +517,7 @@ int llb_map_set_ds_dev(llb_ctx *c, const void *corner, int mc, const void *surf,
         c->mapCornerDS_view = (const float4 *)corner; c->mapSurfDS_view = (const float4 *)surf;
         c->mapCornerDS_upper = mc; c->mapSurfDS_upper = ms;
         c->map_counts_on_dev = false;
+        c->shard = ShardPlan{};
         build_indices(c);
         return (int)LLB_OK;
     });
@@ -936,8 +964,12 @@ int llb_s2m_optimize_sharded(llb_ctx *c, float T[6], llb_stats *stats)
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
         c->launches += c->s2m.prepare(T, nullptr, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);
+        // replicated map: the queries are dealt round-robin (qi = rank + world * j); sharded map: a rank walks all queries
+        // and takes those inside its slab
+        const bool slab = c->shard.axis >= 0 && c->shard.world > 1;
+        if (slab && (c->shard.world != c->peers.world || c->shard.rank != c->peers.rank)) return (int)LLB_ERR_STATE;
         c->launches += c->s2m.run(0, c->prm.s2m_max_iterations, q, c->gridCorner.view(), c->gridSurf.view(), dbg,
-                                  c->peers.rank, c->peers.world, true, c->stream, &c->peers);
+                                  slab ? 0 : c->peers.rank, slab ? 1 : c->peers.world, true, c->stream, &c->peers);
         LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
         LLB_CUDA(cudaMemcpyAsync(c->pin_state.p, c->s2m.state_dev(), sizeof(S2mState), cudaMemcpyDeviceToHost, c->stream));
         read_count(c, 0);
@@ -949,6 +981,308 @@ int llb_s2m_optimize_sharded(llb_ctx *c, float T[6], llb_stats *stats)
         if (!s.skipped) for (int i = 0; i < 6; i++) T[i] = s.T[i];
         fill_stats(c, stats, s, ms);
         c->dbg_ready = false;
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ sharded local map (BASELINE config 4, shard.cuh)
+
+namespace {
+
+// the slab of this rank, from a deterministic sample of the raw surf map (every rank holds the same raw map and draws
+// the same sample): axis = the longer horizontal extent of the sample, borders = its quantiles
+void plan_shard(llb_ctx *c, const float4 *corner, int rc, const float4 *surf, int rs, int rank, int world)
+{
+    ShardPlan pl; pl.rank = rank; pl.world = world;
+    const float4 *src = rs > 0 ? surf : corner; const int n = rs > 0 ? rs : rc;
+    if (world <= 1 || n <= 0) { pl.axis = 0; c->shard = pl; return; }
+    const int nsamp = std::min(n, 8192), stride = std::max(1, n / nsamp);
+    c->shard_samp.ensure(3 * nsamp); c->shard_samp_pin.ensure(3 * nsamp);
+    c->launches += launch_shard_sample(src, n, stride, nsamp, c->shard_samp.p, c->stream);
+    LLB_CUDA(cudaMemcpyAsync(c->shard_samp_pin.p, c->shard_samp.p, sizeof(float) * 3 * nsamp, cudaMemcpyDeviceToHost, c->stream));
+    LLB_CUDA(cudaStreamSynchronize(c->stream));
+    const float *sp = c->shard_samp_pin.p;
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int k = 0; k < nsamp; k++)
+        for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], sp[3 * k + a]); mx[a] = std::max(mx[a], sp[3 * k + a]); }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
+    std::vector<float> v(nsamp);
+    for (int k = 0; k < nsamp; k++) v[k] = sp[3 * k + axis];
+    std::sort(v.begin(), v.end());
+    pl.axis = axis;
+    pl.lo = rank == 0 ? -FLT_MAX : v[(size_t)nsamp * rank / world];
+    pl.hi = rank == world - 1 ? FLT_MAX : v[(size_t)nsamp * (rank + 1) / world];
+    c->shard = pl;
+}
+
+// lattice range [ilo, ihi] on the plan's axis of the voxels (edge `leaf`) this rank must filter: every voxel that can
+// hold a centroid within `reach` of a point of the slab, plus one voxel of margin on both sides
+void slab_voxels(const ShardPlan &pl, float leaf, float reach, int &ilo, int &ihi)
+{
+    const float inv = 1.0f / leaf;
+    ilo = pl.lo <= -FLT_MAX ? INT_MIN / 2 : (int)std::floor((pl.lo - reach) * inv) - 1;
+    ihi = pl.hi >= FLT_MAX ? INT_MAX / 2 : (int)std::floor((pl.hi + reach) * inv) + 1;
+}
+
+int map_set_raw_sharded(llb_ctx *c, const float4 *corner, int rc, const float4 *surf, int rs, int rank, int world)
+{
+    if (world < 1 || world > S2M_MAX_PEERS || rank < 0 || rank >= world) return (int)LLB_ERR_INVALID;
+    plan_shard(c, corner, rc, surf, rs, rank, world);
+    const ShardPlan pl = c->shard;
+    const float reach = std::sqrt(c->prm.knn_max_sqdist);
+    c->shardCorner.ensure(std::max(rc, 1)); c->shardSurf.ensure(std::max(rs, 1));
+    c->shard_blk.ensure((size_t)div_up(std::max(rc, rs), 1024) + 2);
+    c->shard_cnt.ensure(4);
+    c->mapCornerDS.ensure(std::max(rc, 1)); c->mapSurfDS.ensure(std::max(rs, 1));
+    int ilo, ihi;
+    // this rank's part of the two raw maps (stable, whole voxels) ...
+    slab_voxels(pl, c->prm.corner_leaf, reach, ilo, ihi);
+    c->launches += launch_shard_compact(corner, rc, pl.axis, 1.0f / c->prm.corner_leaf, ilo, ihi, c->shardCorner.p,
+                                        c->shard_cnt.p + 0, c->shard_blk.p, c->stream);
+    slab_voxels(pl, c->prm.surf_leaf, reach, ilo, ihi);
+    c->launches += launch_shard_compact(surf, rs, pl.axis, 1.0f / c->prm.surf_leaf, ilo, ihi, c->shardSurf.p,
+                                        c->shard_cnt.p + 1, c->shard_blk.p, c->stream);
+    // ... voxel-filtered on the lattice of the WHOLE maps (MO:1057-1064 restricted to the slab) ...
+    VoxelInput a; a.a = c->shardCorner.p; a.na_dev = c->shard_cnt.p + 0; a.na = rc;
+    VoxelInput ab; ab.a = corner; ab.na = rc;
+    VoxelInput b; b.a = c->shardSurf.p; b.na_dev = c->shard_cnt.p + 1; b.na = rs;
+    VoxelInput bb; bb.a = surf; bb.na = rs;
+    LLB_CUDA(cudaEventRecord(c->fork_ev, c->stream));
+    LLB_CUDA(cudaStreamWaitEvent(c->stream2, c->fork_ev, 0));
+    c->launches += c->vox2.run_with_bounds(a, ab, c->prm.corner_leaf, c->mapCornerDS.p, c->counts.p + llb_ctx::C_MAP_CORNER_DS, c->stream2);
+    LLB_CUDA(cudaEventRecord(c->join_ev, c->stream2));
+    c->launches += c->vox.run_with_bounds(b, bb, c->prm.surf_leaf, c->mapSurfDS.p, c->counts.p + llb_ctx::C_MAP_SURF_DS, c->stream);
+    LLB_CUDA(cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+    c->mapCornerDS_view = c->mapCornerDS.p; c->mapSurfDS_view = c->mapSurfDS.p;
+    c->mapCornerDS_upper = rc; c->mapSurfDS_upper = rs;
+    c->map_counts_on_dev = true;
+    // ... the centroids this rank owns (halo excluded): their sum over the ranks is the size of the unsharded map
+    c->launches += launch_shard_count_owned(c->mapCornerDS.p, c->counts.p + llb_ctx::C_MAP_CORNER_DS, rc, pl.axis, pl.lo, pl.hi,
+                                            c->shard_cnt.p + 2, c->stream);
+    c->launches += launch_shard_count_owned(c->mapSurfDS.p, c->counts.p + llb_ctx::C_MAP_SURF_DS, rs, pl.axis, pl.lo, pl.hi,
+                                            c->shard_cnt.p + 3, c->stream);
+    c->shard_global[0] = c->shard_global[1] = -1;
+    build_indices(c);                                        // MO:1333-1334 on this rank's part only
+    return (int)LLB_OK;
+}
+
+}  // namespace
+
+int llb_map_set_raw_sharded(llb_ctx *c, const llb_point *corner, int rc, const llb_point *surf, int rs, int rank, int world)
+{
+    return guarded(c, [&]() {
+        if (rc < 0 || rs < 0 || (rc > 0 && !corner) || (rs > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        set_cloud(c, 0, c->mapCornerRaw, corner, rc);
+        set_cloud(c, 1, c->mapSurfRaw, surf, rs);
+        return map_set_raw_sharded(c, c->mapCornerRaw.pts.p, rc, c->mapSurfRaw.pts.p, rs, rank, world);
+    });
+}
+
+int llb_map_set_raw_sharded_dev(llb_ctx *c, const void *corner, int rc, const void *surf, int rs, int rank, int world)
+{
+    return guarded(c, [&]() {
+        if (rc < 0 || rs < 0 || (rc > 0 && !corner) || (rs > 0 && !surf)) return (int)LLB_ERR_INVALID;
+        return map_set_raw_sharded(c, (const float4 *)corner, rc, (const float4 *)surf, rs, rank, world);
+    });
+}
+
+int llb_map_shard_info(llb_ctx *c, llb_shard_info *out)
+{
+    return guarded(c, [&]() {
+        if (!out) return (int)LLB_ERR_INVALID;
+        if (c->shard.axis < 0) return (int)LLB_ERR_STATE;
+        const int dsn[2] = { read_count(c, llb_ctx::C_MAP_CORNER_DS), c->pin_counts.p[llb_ctx::C_MAP_SURF_DS] };
+        int *h = c->pin_counts.p + llb_ctx::C_N;
+        LLB_CUDA(cudaMemcpyAsync(h, c->shard_cnt.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        out->axis = c->shard.axis; out->lo = c->shard.lo; out->hi = c->shard.hi; out->rank = c->shard.rank; out->world = c->shard.world;
+        for (int k = 0; k < 2; k++) { out->raw_kept[k] = h[k]; out->ds_local[k] = dsn[k]; out->ds_owned[k] = h[2 + k]; }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_map_shard_set_global(llb_ctx *c, const int global_ds[2])
+{
+    return guarded(c, [&]() {
+        if (!global_ds || c->shard.axis < 0) return (int)(global_ds ? LLB_ERR_STATE : LLB_ERR_INVALID);
+        c->shard_global[0] = global_ds[0]; c->shard_global[1] = global_ds[1];
+        c->s2m.set_shard(c->shard.axis, c->shard.lo, c->shard.hi, global_ds[0], global_ds[1]);
+        return (int)LLB_OK;
+    });
+}
+
+// ------------------------------------------------------------------ loop closure + global map
+
+namespace {
+
+AsmSeg seg_for_pose(const float *p)
+{   // transformPointCloud(cloud, &pose) MO:577-606: cos / sin of the float members are the float overloads (utility.h:
+    // using namespace std), i.e. the host libm's cosf / sinf as in updateTransformPointCloudSinCos
+    AsmSeg sg{};
+    sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]);
+    sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
+    sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]);
+    sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
+    return sg;
+}
+
+// key-frame clouds `which` (bit k: cloud k of KeyFrameRec) of ids[] in order, transformed by poses[], back to back into dst
+size_t assemble_clouds(llb_ctx *c, const int *ids, const float *poses, int n, unsigned which, DevBuf<float4> &dst)
+{
+    size_t total = 0;
+    for (int k = 0; k < n; k++) {
+        const KeyFrameRec &r = c->kfs.rec(ids[k]);
+        for (int j = 0; j < 3; j++) if (which & (1u << j)) total += (size_t)r.n[j];
+    }
+    dst.ensure(std::max<size_t>(total, 1));
+    c->asm_segs.ensure(std::max(3 * n, 1));
+    if (c->asm_busy) { LLB_CUDA(cudaEventSynchronize(c->asm_ev)); c->asm_busy = false; }
+    c->pin_segs.ensure(std::max(3 * n, 1));
+    size_t off = 0; int nseg = 0, nmax = 1;
+    for (int k = 0; k < n; k++) {
+        const KeyFrameRec &r = c->kfs.rec(ids[k]);
+        AsmSeg sg = seg_for_pose(poses + 6 * k);
+        for (int j = 0; j < 3; j++) {
+            if (!(which & (1u << j))) continue;
+            sg.src = r.cloud[j]; sg.n = r.n[j]; sg.dst = dst.p + off; off += (size_t)r.n[j];
+            if (sg.n > 0) { c->pin_segs.p[nseg++] = sg; nmax = std::max(nmax, sg.n); }
+        }
+    }
+    if (nseg > 0) {
+        LLB_CUDA(cudaMemcpyAsync(c->asm_segs.p, c->pin_segs.p, sizeof(AsmSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
+        LLB_CUDA(cudaEventRecord(c->asm_ev, c->stream));
+        c->asm_busy = true;
+        launch_kf_assemble(c->asm_segs.p, nseg, nmax, c->stream);
+        c->launches++;
+    }
+    return total;
+}
+
+bool valid_ids(llb_ctx *c, const int *ids, int n)
+{
+    for (int k = 0; k < n; k++) if (ids[k] < 0 || ids[k] >= c->kfs.size()) return false;
+    return true;
+}
+
+}  // namespace
+
+void llb_loop_params_default(llb_loop_params *p)
+{
+    if (!p) return;
+    p->max_iterations = 100; p->max_correspondence_distance = 100.0;          // MO:893-894
+    p->transformation_epsilon = 1e-6; p->euclidean_fitness_epsilon = 1e-6;    // MO:895-896
+}
+
+int llb_loop_set_clouds(llb_ctx *c, int latest_id, const float latest_pose[6], const int *hist_ids, const float *hist_poses,
+                        int n_hist, float history_leaf, int counts[2])
+{
+    return guarded(c, [&]() {
+        if (!latest_pose || n_hist < 0 || (n_hist > 0 && (!hist_ids || !hist_poses)) || !(history_leaf > 0.f)) return (int)LLB_ERR_INVALID;
+        if (!valid_ids(c, &latest_id, 1) || !valid_ids(c, hist_ids, n_hist)) return (int)LLB_ERR_INVALID;
+        // MO:840-851: corner + surf clouds of the latest key-frame at its pose, points with (int)intensity >= 0
+        const size_t nl = assemble_clouds(c, &latest_id, latest_pose, 1, 3u, c->loopLatestRaw);
+        c->loopLatest.ensure(std::max<size_t>(nl, 1));
+        c->launches += launch_loop_filter_intensity(c->loopLatestRaw.p, (int)nl, c->loopLatest.p, c->counts.p + llb_ctx::C_LOOP_LATEST, c->stream);
+        c->loop_n_latest_raw = (int)nl;
+        // MO:853-861: corner + surf clouds of the history frames around the closest one, VoxelGrid(history_leaf)
+        const size_t nh = assemble_clouds(c, hist_ids, hist_poses, n_hist, 3u, c->loopHistRaw);
+        if (nh > (size_t)INT_MAX) return (int)LLB_ERR_CAPACITY;
+        c->loopHistDS.ensure(std::max<size_t>(nh, 1));
+        VoxelInput in; in.a = c->loopHistRaw.p; in.na = (int)nh;
+        c->launches += c->vox3.run(in, history_leaf, c->loopHistDS.p, c->counts.p + llb_ctx::C_LOOP_HIST_DS, c->stream);
+        c->loop_n_hist_raw = (int)nh;
+        c->loop_n_latest = read_count(c, llb_ctx::C_LOOP_LATEST);
+        c->loop_n_hist = c->pin_counts.p[llb_ctx::C_LOOP_HIST_DS];
+        if (counts) { counts[0] = c->loop_n_latest; counts[1] = c->loop_n_hist; }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_loop_set_clouds_host(llb_ctx *c, const llb_point *latest, int n_latest, const llb_point *history_ds, int n_hist)
+{
+    return guarded(c, [&]() {
+        if (n_latest < 0 || n_hist < 0 || (n_latest > 0 && !latest) || (n_hist > 0 && !history_ds)) return (int)LLB_ERR_INVALID;
+        upload_cloud(c, 0, latest, n_latest, c->loopLatest);
+        upload_cloud(c, 1, history_ds, n_hist, c->loopHistDS);
+        c->loop_n_latest = n_latest; c->loop_n_hist = n_hist; c->loop_n_latest_raw = 0; c->loop_n_hist_raw = 0;
+        return (int)LLB_OK;
+    });
+}
+
+int llb_loop_icp(llb_ctx *c, const llb_loop_params *prm, llb_icp_result *out)
+{
+    return guarded(c, [&]() {
+        if (!out) return (int)LLB_ERR_INVALID;
+        if (c->loop_n_latest < 0 || c->loop_n_hist < 0) return (int)LLB_ERR_STATE;
+        llb_loop_params p; llb_loop_params_default(&p);
+        if (prm) p = *prm;
+        if (p.max_iterations < 1 || !(p.max_correspondence_distance > 0)) return (int)LLB_ERR_INVALID;
+        IcpParams ip{ p.max_iterations, p.max_correspondence_distance, p.transformation_epsilon, p.euclidean_fitness_epsilon };
+        c->pin_icp.ensure(1);
+        LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        c->launches += c->icp.run(ip, c->loopLatest.p, c->loop_n_latest, c->loopHistDS.p, c->loop_n_hist, 0, c->stream);
+        LLB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        LLB_CUDA(cudaMemcpyAsync(c->pin_icp.p, c->icp.state_dev(), sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        const IcpState &s = *c->pin_icp.p;
+        for (int i = 0; i < 16; i++) out->T[i] = s.T[i];
+        out->has_converged = s.converged; out->iterations = s.iterations; out->convergence_state = s.state;
+        out->n_correspondences = s.n_corr; out->fitness_score = s.fitness;
+        out->n_source = c->loop_n_latest; out->n_target = c->loop_n_hist;
+        for (int i = 0; i < 17; i++) out->sums[i] = s.sums[i];
+        LLB_CUDA(cudaEventElapsedTime(&out->device_ms, c->ev0, c->ev1));
+        return (int)LLB_OK;
+    });
+}
+
+int llb_loop_get_cloud(llb_ctx *c, int which, llb_point *out, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n || which < 0 || which > 3) return (int)LLB_ERR_INVALID;
+        const int cnt = which == 0 ? c->loop_n_latest : which == 1 ? c->loop_n_hist_raw : which == 2 ? c->loop_n_hist : c->global_n;
+        if (cnt < 0) return (int)LLB_ERR_STATE;
+        *n = cnt;
+        if (!out) return (int)LLB_OK;
+        if (cnt > cap) return (int)LLB_ERR_CAPACITY;
+        download_cloud(c, which == 0 ? c->loopLatest.p : which == 1 ? c->loopHistRaw.p : which == 2 ? c->loopHistDS.p : c->globalDS.p, cnt, out);
+        return (int)LLB_OK;
+    });
+}
+
+int llb_loop_get_nn(llb_ctx *c, int *idx, float *sqdist, int cap, int *n)
+{
+    return guarded(c, [&]() {
+        if (!n) return (int)LLB_ERR_INVALID;
+        if (c->loop_n_latest < 0) return (int)LLB_ERR_STATE;
+        *n = c->loop_n_latest;
+        if (!idx && !sqdist) return (int)LLB_OK;
+        if (*n > cap) return (int)LLB_ERR_CAPACITY;
+        std::vector<unsigned long long> h((size_t)std::max(*n, 1));
+        LLB_CUDA(cudaMemcpyAsync(h.data(), c->icp.nn_dev(), sizeof(unsigned long long) * (size_t)*n, cudaMemcpyDeviceToHost, c->stream));
+        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < *n; i++) {
+            const unsigned hi = (unsigned)(h[i] >> 32);
+            if (idx) idx[i] = (int)(h[i] & 0xffffffffu);
+            if (sqdist) std::memcpy(&sqdist[i], &hi, 4);
+        }
+        return (int)LLB_OK;
+    });
+}
+
+int llb_global_map_assemble(llb_ctx *c, const int *ids, const float *poses, int n, float leaf, int *n_out)
+{
+    return guarded(c, [&]() {
+        if (n < 0 || (n > 0 && (!ids || !poses)) || !(leaf > 0.f)) return (int)LLB_ERR_INVALID;
+        if (!valid_ids(c, ids, n)) return (int)LLB_ERR_INVALID;
+        // MO:780-788: corner, surf and outlier clouds of every selected key-frame at its pose, then one VoxelGrid(leaf)
+        const size_t tot = assemble_clouds(c, ids, poses, n, 7u, c->globalRaw);
+        if (tot > (size_t)INT_MAX) return (int)LLB_ERR_CAPACITY;
+        c->globalDS.ensure(std::max<size_t>(tot, 1));
+        VoxelInput in; in.a = c->globalRaw.p; in.na = (int)tot;
+        c->launches += c->vox3.run(in, leaf, c->globalDS.p, c->counts.p + llb_ctx::C_GLOBAL_DS, c->stream);
+        c->global_n = read_count(c, llb_ctx::C_GLOBAL_DS);
+        if (n_out) *n_out = c->global_n;
         return (int)LLB_OK;
     });
 }

@@ -55,7 +55,8 @@ __global__ void s2m_prepare_kernel(S2mState *st, PoseArg pose, const float *T_de
     st->iters = 0;
     st->n_corr = 0;
     st->ticket = 0;
-    st->skipped = !(cd->n > prm.corner_map_min && sd->n > prm.surf_map_min);   // MO:1331
+    const int n_corner = prm.global_corner >= 0 ? prm.global_corner : cd->n, n_surf = prm.global_surf >= 0 ? prm.global_surf : sd->n;
+    st->skipped = !(n_corner > prm.corner_map_min && n_surf > prm.surf_map_min);   // MO:1331
 }
 
 __global__ void s2m_state_init_kernel(S2mState *st)
@@ -140,7 +141,15 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
                 s_q[0][s] = po.x; s_q[1][s] = po.y; s_q[2][s] = po.z;
                 s_q[3][s] = sx; s_q[4][s] = sy; s_q[5][s] = sz;
                 int rb[9], re[9];
-                knn_ranges(is_corner ? cmap : smap, sx, sy, sz, rb, re);
+                // sharded map: a query outside this rank's slab is another rank's (its runs stay empty: no neighbours,
+                // no row); every rank evaluates the same comparison on the same bits, so exactly one rank takes it
+                const float oc = prm.own_axis == 0 ? sx : (prm.own_axis == 1 ? sy : sz);
+                if (prm.own_axis < 0 || (oc >= prm.own_lo && oc < prm.own_hi)) {
+                    knn_ranges(is_corner ? cmap : smap, sx, sy, sz, rb, re);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 9; r++) { rb[r] = 0; re[r] = 0; }
+                }
 #pragma unroll
                 for (int r = 0; r < 9; r++) { s_rb[r][s] = rb[r]; s_re[r][s] = re[r]; }
             }

@@ -16,6 +16,12 @@ struct S2mParams {
     float converge_deg, converge_cm; // 0.05, 0.05
     int   corner_map_min, surf_map_min; // 10, 100
     int   max_ctas;                  // 0 = one per SM
+    // sharded map (shard.cuh): this rank handles the queries whose MAPPED coordinate on own_axis lies in
+    // [own_lo, own_hi); own_axis < 0: all queries.  global_corner / global_surf: sizes of the unsharded DS maps for the
+    // guard MO:1331 (< 0: the sizes of the maps this context holds)
+    int   own_axis = -1;
+    float own_lo = -FLT_MAX, own_hi = FLT_MAX;
+    int   global_corner = -1, global_surf = -1;
 };
 
 struct S2mState {                    // device-resident, persists across registrations
@@ -64,6 +70,8 @@ public:
     void init(const S2mParams &p);
     void release();
     S2mState *state_dev() { return state_.p; }
+    void set_shard(int axis, float lo, float hi, int global_corner, int global_surf)
+    { prm_.own_axis = axis; prm_.own_lo = lo; prm_.own_hi = hi; prm_.global_corner = global_corner; prm_.global_surf = global_surf; }
     double *acc_dev() { return acc_.p; }
     // upload T, compute its sin/cos on the device, evaluate the map-size guard, reset flags
     int prepare(const float *T_host, const float *T_dev, const GridDesc *corner_desc, const GridDesc *surf_desc,

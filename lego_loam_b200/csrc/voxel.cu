@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(LG_THREADS)
 voxel_minmax_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
-    const SegIn in = jb.in; VoxelDesc *__restrict__ d = jb.desc;
+    const SegIn in = jb.bounds; VoxelDesc *__restrict__ d = jb.desc;
     __shared__ float s_red[6][LG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int na = seg_len_a(in), n = na + seg_len_b(in);
@@ -350,12 +350,12 @@ int VoxelFilter::run_batch(const VoxelInput *in, const float *leaf, float4 *cons
     return 1;
 }
 
-LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev)
+LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, const VoxelInput *bounds)
 {
     const int n = std::max(in.upper(), 1);
     reserve(std::max(n, SMALL_MAX + 1));
     LargeVoxelJob j;
-    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p;
+    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in;
     j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
     j.hist = hist_.p; j.blk = blk_.p; j.psorted = psorted_.p; j.out = out; j.n_out = n_out_dev;
     return j;
@@ -397,9 +397,9 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     return launches;
 }
 
-int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s)
+int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s, const VoxelInput *bounds)
 {
-    const LargeVoxelJob j = large_job(in, leaf, out, n_out_dev);
+    const LargeVoxelJob j = large_job(in, leaf, out, n_out_dev, bounds);
     job_raw_.ensure(sizeof(LargeVoxelJob));
     job_pin_.ensure(sizeof(LargeVoxelJob));
     if (!job_ev_) LLB_CUDA(cudaEventCreateWithFlags(&job_ev_, cudaEventDisableTiming));
@@ -407,7 +407,7 @@ int VoxelFilter::run_large(const VoxelInput &in, float leaf, float4 *out, int *n
     std::memcpy(job_pin_.p, &j, sizeof(j));
     LLB_CUDA(cudaMemcpyAsync(job_raw_.p, job_pin_.p, sizeof(j), cudaMemcpyHostToDevice, s));
     LLB_CUDA(cudaEventRecord(job_ev_, s));
-    return launch_large(reinterpret_cast<const LargeVoxelJob *>(job_raw_.p), 1, in.upper(), s);
+    return launch_large(reinterpret_cast<const LargeVoxelJob *>(job_raw_.p), 1, std::max(in.upper(), bounds ? bounds->upper() : 0), s);
 }
 
 }  // namespace llb

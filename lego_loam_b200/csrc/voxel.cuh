@@ -35,19 +35,23 @@ public:
     void release();
     // batched form of the multi-kernel path: large_job() sizes this filter's scratch for the input's upper bound and
     // returns the job record; a device-resident table of such records is run by ONE set of 18 launches
-    LargeVoxelJob large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev);
+    LargeVoxelJob large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, const VoxelInput *bounds = nullptr);
     static int launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s);
     // pre-sizes the scratch of the multi-kernel path for inputs of up to n points (no allocation at run time below n)
     void reserve(int n);
     // out must have room for in.upper() points; n_out_dev receives the output count.
     // All work is enqueued on `stream`; nothing synchronises. Returns kernels launched.
     int run(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t stream);
+    // the same through the multi-kernel path whatever the size, with the lattice bounds taken from ANOTHER cloud (`bounds`,
+    // of which `in` is a part): a rank of a sharded map filters its share and numbers the voxels as the whole map does
+    int run_with_bounds(const VoxelInput &in, const VoxelInput &bounds, float leaf, float4 *out, int *n_out_dev,
+                        cudaStream_t stream) { return run_large(in, leaf, out, n_out_dev, stream, &bounds); }
     // `count` independent filters; when every one fits the single-CTA path they share ONE launch
     int run_batch(const VoxelInput *in, const float *leaf, float4 *const *out, int *const *n_out_dev,
                   int count, cudaStream_t stream);
 
 private:
-    int run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s);
+    int run_large(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, cudaStream_t s, const VoxelInput *bounds = nullptr);
     DevBuf<VoxelDesc> desc_;
     DevBuf<unsigned> keys_[2];
     DevBuf<int> vals_[2];

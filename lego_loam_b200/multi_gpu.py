@@ -2,9 +2,12 @@
 
 Two cases:
 * independent sequences / scans (BASELINE config 5): replicas, one process per GPU, no collective;
-* one registration against a large map (BASELINE config 4): the queries of the scan are sharded
-  round-robin over the ranks (query i belongs to rank i % world), every rank holds the whole
-  voxel-DS map (2M points = 32 MB), and the only exchange per LM iteration is an all-reduce(sum)
+* one registration against a large map (BASELINE config 4), two forms: (a) the MAP is sharded
+  (set_sharded_map: every rank voxel-filters and indexes a slab of the raw map on the lattice of
+  the whole map and takes the queries whose mapped position lies in its slab); (b) the queries
+  of the scan are sharded round-robin over the ranks (query i belongs to rank i % world) and
+  every rank holds the whole voxel-DS map (2M points = 32 MB).  In both the only exchange per LM
+  iteration is an all-reduce(sum)
   of 28 fp64 values (21 upper-triangular J^T J terms, 6 J^T r terms, the row count).  Every rank
   then performs the identical 6x6 LM step redundantly, so no broadcast is needed.
 """
@@ -92,6 +95,28 @@ def setup_fused_exchange(ctx, rank: int, world: int, group=None):
     else:
         handles = [mine]
     ctx.p2p_import(rank, world, handles)
+
+
+def set_sharded_map(ctx, corner_raw, surf_raw, rank: int, world: int, group=None, device_ptrs=None):
+    """Config 4 with the MAP sharded (preferred form): every rank is handed the same raw local map and keeps,
+    voxel-filters and indexes only its slab (+ 1 m halo) of it; the sizes of the unsharded DS maps (guard MO:1331) are the
+    all-reduced counts of the centroids each rank owns.  device_ptrs = (corner_ptr, rc, surf_ptr, rs) hands over float4
+    clouds already in HBM (replicated key-frame stores) instead of host arrays.  Returns the rank's ShardInfo."""
+    if device_ptrs is not None:
+        ctx.map_set_raw_sharded_dev(*device_ptrs, rank, world)
+    else:
+        ctx.map_set_raw_sharded(corner_raw, surf_raw, rank, world)
+    info = ctx.map_shard_info()
+    owned = np.array([info.ds_owned[0], info.ds_owned[1]], np.int64)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", ctx.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.as_tensor(owned, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        owned = t.cpu().numpy()
+    ctx.map_shard_set_global(int(owned[0]), int(owned[1]))
+    return info
 
 
 def sharded_scan2map_fused(ctx, T_init):

@@ -272,6 +272,32 @@ class FeatureAssociation:
         return a[:n].copy(), b[:n].copy(), c[:n].copy()
 
 
+def icp_align(src, tgt, max_iterations=100, max_corr_dist=100.0, transformation_epsilon=1e-6, euclidean_fitness_epsilon=1e-6):
+    """pcl::IterativeClosestPoint::align + getFitnessScore as MO:892-904 configures them (restated PCL 1.8, unpinned)."""
+    s = _pts(src); t = _pts(tgt)
+    T = np.zeros(16, np.float32); c = ctypes.c_int(0); it = ctypes.c_int(0); st = ctypes.c_int(0); f = ctypes.c_double(0)
+    lib().llo_icp_align(_fp(s), s.shape[0], _fp(t), t.shape[0], int(max_iterations), ctypes.c_double(max_corr_dist),
+                        ctypes.c_double(transformation_epsilon), ctypes.c_double(euclidean_fitness_epsilon), _fp(T),
+                        ctypes.byref(c), ctypes.byref(it), ctypes.byref(st), ctypes.byref(f))
+    return dict(T=T.reshape(4, 4), converged=bool(c.value), iterations=it.value, state=st.value, fitness=f.value)
+
+
+def icp_step(cur, tgt, max_corr_dist=100.0):
+    """one iteration on the CURRENT source cloud: (n, sums p[3], q[3], qp[9], mse, nn index per point, umeyama 4x4)"""
+    s = _pts(cur); t = _pts(tgt)
+    L = lib()
+    tree = ctypes.c_void_p(L.llo_kdtree_build(_fp(t), t.shape[0]))
+    sp = np.zeros(3); sq = np.zeros(3); sqp = np.zeros(9); mse = ctypes.c_double(0); nn = np.zeros(max(s.shape[0], 1), np.int32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    n = L.llo_icp_correspondence_sums(_fp(s), s.shape[0], tree, _fp(t), ctypes.c_double(max_corr_dist * max_corr_dist),
+                                      sp.ctypes.data_as(dp), sq.ctypes.data_as(dp), sqp.ctypes.data_as(dp), ctypes.byref(mse), _ip(nn))
+    L.llo_kdtree_free(tree)
+    Rt = np.zeros(16, np.float32)
+    if n >= 3:
+        L.llo_umeyama_from_sums(ctypes.c_double(n), sp.ctypes.data_as(dp), sq.ctypes.data_as(dp), sqp.ctypes.data_as(dp), _fp(Rt))
+    return dict(n=n, sp=sp, sq=sq, sqp=sqp.reshape(3, 3), mse=mse.value, nn=nn[:s.shape[0]], Rt=Rt.reshape(4, 4))
+
+
 def set_trig_mode(mode: int):
     """0 = host libm sinf/cosf (reference-faithful on this machine), 1 = correctly rounded."""
     lib().llo_set_trig_mode(int(mode))

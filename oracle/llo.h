@@ -85,6 +85,20 @@ int llo_kdtree_knn(const llo_kdtree *t, const float *q, int k, int *idx, float *
 /* brute-force definition of the same query (used to validate the tree) */
 int llo_knn_bruteforce(const llo_point *pts, int n, const float *q, int k, int *idx, float *d2);
 
+/* ---------------- loop closure (llo_loop.c; PARITY UNPINNED: PCL / Eigen absent) ----------------
+ * pcl::IterativeClosestPoint<PointXYZI,PointXYZI>::align + getFitnessScore as performLoopClosure configures them
+ * (MO:892-904), restated from PCL 1.8.  T_final: final_transformation_ (row-major 4x4); state: 0 too few
+ * correspondences (hasConverged() false), 1 iterations, 2 transform, 3 abs MSE, 4 rel MSE. */
+int llo_icp_align(const llo_point *src, int ns, const llo_point *tgt, int nt, int max_iterations, double max_corr_dist,
+                  double transformation_epsilon, double euclidean_fitness_epsilon, float T_final[16], int *converged,
+                  int *iterations, int *state, double *fitness);
+/* one step for per-function parity: correspondences of the CURRENT source cloud (exact 1-NN, kept when d^2 <= max_d2),
+ * the sums n (return value), sum p, sum q, sum q p^T, and the mean squared distance; nn_idx (may be NULL): target index or -1 */
+int llo_icp_correspondence_sums(const llo_point *cur, int ns, const llo_kdtree *tree, const llo_point *tgt, double max_d2,
+                                double sp[3], double sq[3], double sqp[9], double *mse, int *nn_idx);
+/* pcl::umeyama (no scaling) from those sums -> row-major 4x4 */
+void llo_umeyama_from_sums(double n, const double sp[3], const double sq[3], const double sqp[9], float Rt[16]);
+
 /* ---------------- mapOptimization hot path (MO:498-527, MO:1067-1350) ---------------- */
 
 typedef struct llo_mapopt llo_mapopt;

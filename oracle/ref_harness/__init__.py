@@ -156,6 +156,35 @@ class MapOptimization:
         self.L.ref_mo_get_keyframe_cloud(self._h, int(idx), which, _fp(out), n)
         return out[:n].copy()
 
+    # ---- loop closure + global map
+    def set_robot_pos(self, x, y, z): self.L.ref_mo_set_robot_pos(self._h, ctypes.c_float(x), ctypes.c_float(y), ctypes.c_float(z))
+    def set_time(self, stamp: float): self.L.ref_mo_set_time(self._h, ctypes.c_double(stamp))
+    def detectLoopClosure(self) -> bool: return bool(self.L.ref_mo_detectLoopClosure(self._h))
+
+    def loop_ids(self):
+        a = ctypes.c_int(0); b = ctypes.c_int(0)
+        self.L.ref_mo_loop_ids(self._h, ctypes.byref(a), ctypes.byref(b)); return a.value, b.value
+
+    def loop_cloud(self, which: int) -> np.ndarray:
+        """0 latestSurfKeyFrameCloud, 1 nearHistorySurfKeyFrameCloud, 2 nearHistorySurfKeyFrameCloudDS, 3 globalMapKeyFramesDS"""
+        return self._cloud(self.L.ref_mo_get_loop_cloud, which)
+
+    def performLoopClosure(self) -> bool: return bool(self.L.ref_mo_performLoopClosure(self._h))
+
+    def icp_last(self):
+        """-> dict of the last pcl::IterativeClosestPoint::align the reference ran (restated PCL, oracle/llo_loop.c)"""
+        T = np.zeros(16, np.float32); c = ctypes.c_int(0); it = ctypes.c_int(0); st = ctypes.c_int(0); f = ctypes.c_double(0)
+        calls = self.L.ref_mo_icp_last(_fp(T), ctypes.byref(c), ctypes.byref(it), ctypes.byref(st), ctypes.byref(f))
+        return dict(T=T.reshape(4, 4), converged=bool(c.value), iterations=it.value, state=st.value, fitness=f.value, calls=calls)
+
+    def publishGlobalMap(self) -> np.ndarray:
+        """runs publishGlobalMap (MO:758-800) with one subscriber; returns the key-frame ids it assembled, in order"""
+        n = self.L.ref_mo_publishGlobalMap(self._h, None, 0)
+        out = np.zeros(max(n, 1), np.int32)
+        # the function is idempotent on the same state: second call fills the ids
+        self.L.ref_mo_publishGlobalMap(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n)
+        return out[:n].copy()
+
 
 def _sensor_lib(base, sensor):
     """libref_<node>.so is the reference as shipped (VLP-16, UT:62-68); libref_<node>_<sensor>.so the same sources with

@@ -170,4 +170,62 @@ int ref_mo_get_map_raw(void *h, int which, llo_point *out, int cap)
     mapOptimization *m = (mapOptimization *)h;
     return dump(which == 0 ? m->laserCloudCornerFromMap : m->laserCloudSurfFromMap, out, cap);
 }
+// ---- loop closure + global map: the reference's own detectLoopClosure / performLoopClosure /
+// publishGlobalMap; pcl::IterativeClosestPoint is the restatement in oracle/llo_loop.c behind the shim class
+void ref_mo_set_robot_pos(void *h, float x, float y, float z)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    m->currentRobotPosPoint.x = x; m->currentRobotPosPoint.y = y; m->currentRobotPosPoint.z = z;
+}
+void ref_mo_set_time(void *h, double stamp) { ((mapOptimization *)h)->timeLaserOdometry = stamp; }
+int ref_mo_detectLoopClosure(void *h) { return ((mapOptimization *)h)->detectLoopClosure() ? 1 : 0; }
+void ref_mo_loop_ids(void *h, int *closest, int *latest)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    *closest = m->closestHistoryFrameID; *latest = m->latestFrameIDLoopCloure;
+}
+// which: 0 latestSurfKeyFrameCloud, 1 nearHistorySurfKeyFrameCloud, 2 nearHistorySurfKeyFrameCloudDS, 3 globalMapKeyFramesDS,
+// 4 globalMapKeyPosesDS
+int ref_mo_get_loop_cloud(void *h, int which, llo_point *out, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    return dump(which == 0 ? m->latestSurfKeyFrameCloud : which == 1 ? m->nearHistorySurfKeyFrameCloud
+              : which == 2 ? m->nearHistorySurfKeyFrameCloudDS : which == 3 ? m->globalMapKeyFramesDS : m->globalMapKeyPosesDS, out, cap);
+}
+// performLoopClosure MO:875-945 (returns aLoopIsClosed); the ICP it ran is read back with ref_mo_icp_last
+int ref_mo_performLoopClosure(void *h)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    m->aLoopIsClosed = false;
+    m->performLoopClosure();
+    return m->aLoopIsClosed ? 1 : 0;
+}
+int ref_mo_icp_last(float *T16, int *converged, int *iterations, int *state, double *fitness)
+{
+    const pcl::LlrefIcpRecord &r = pcl::llref_icp_last();
+    memcpy(T16, r.T, 64); *converged = r.converged; *iterations = r.iterations; *state = r.state; *fitness = r.fitness;
+    return r.calls;
+}
+// publishGlobalMap MO:758-800 with one subscriber; globalMapKeyPosesDS is cleared by the function, so its selection is
+// returned through ids (thisKeyInd of MO:781, in order)
+int ref_mo_publishGlobalMap(void *h, int *ids, int cap)
+{
+    mapOptimization *m = (mapOptimization *)h;
+    // the key-frame selection of MO:766-778 repeated on copies (the function clears its own), same objects, same order
+    int n = 0;
+    if (!m->cloudKeyPoses3D->points.empty()) {
+        std::vector<int> ind; std::vector<float> dis;
+        m->kdtreeGlobalMap->setInputCloud(m->cloudKeyPoses3D);
+        m->kdtreeGlobalMap->radiusSearch(m->currentRobotPosPoint, globalMapVisualizationSearchRadius, ind, dis, 0);
+        pcl::PointCloud<PointType>::Ptr kp(new pcl::PointCloud<PointType>()), kpds(new pcl::PointCloud<PointType>());
+        for (size_t i = 0; i < ind.size(); ++i) kp->points.push_back(m->cloudKeyPoses3D->points[ind[i]]);
+        m->downSizeFilterGlobalMapKeyPoses.setInputCloud(kp);
+        m->downSizeFilterGlobalMapKeyPoses.filter(*kpds);
+        for (size_t i = 0; i < kpds->points.size(); ++i) { if (n < cap) ids[n] = (int)kpds->points[i].intensity; n++; }
+    }
+    ros::llref_num_subscribers() = 1;
+    m->publishGlobalMap();
+    ros::llref_num_subscribers() = 0;
+    return n;
+}
 }  // extern "C"

@@ -81,9 +81,10 @@ struct Time {
 };
 struct Duration { double d; explicit Duration(double s = 0) : d(s) {} void sleep() const {} };
 struct Rate { explicit Rate(double) {} void sleep() {} };
+inline int &llref_num_subscribers() { static int n = 0; return n; }   // the harness raises it to let publishGlobalMap run
 struct Publisher {
     template <typename M> void publish(const M &) const {}
-    int getNumSubscribers() const { return 0; }
+    int getNumSubscribers() const { return llref_num_subscribers(); }
 };
 struct Subscriber {};
 struct NodeHandle {
@@ -441,17 +442,38 @@ private:
     llo_kdtree *tree_ = nullptr;
 };
 
-// loop closure is disabled in the reference (UT:104); compile-only stub
+// pcl::IterativeClosestPoint as performLoopClosure uses it (MO:892-904): the restatement of PCL 1.8's algorithm in
+// oracle/llo_loop.c ("parity unpinned": PCL itself is absent).  The object is a local of performLoopClosure, so the
+// harness reads what the last align() saw and produced from llref_icp_last().
+struct LlrefIcpRecord {
+    std::vector<llo_point> source, target;
+    float T[16]; int converged = 0, iterations = 0, state = 0, calls = 0; double fitness = 0;
+};
+inline LlrefIcpRecord &llref_icp_last() { static LlrefIcpRecord r; return r; }
 template <typename A, typename B>
 class IterativeClosestPoint {
 public:
-    void setMaxCorrespondenceDistance(double) {} void setMaximumIterations(int) {}
-    void setTransformationEpsilon(double) {} void setEuclideanFitnessEpsilon(double) {} void setRANSACIterations(int) {}
-    void setInputSource(const typename PointCloud<A>::ConstPtr &) {} void setInputTarget(const typename PointCloud<B>::ConstPtr &) {}
-    void align(PointCloud<A> &) {}
-    bool hasConverged() const { return false; }
-    double getFitnessScore() const { return 1e30; }
-    Eigen::Matrix4f getFinalTransformation() const { return Eigen::Matrix4f(); }
+    void setMaxCorrespondenceDistance(double d) { max_dist_ = d; } void setMaximumIterations(int n) { max_iter_ = n; }
+    void setTransformationEpsilon(double e) { teps_ = e; } void setEuclideanFitnessEpsilon(double e) { feps_ = e; }
+    void setRANSACIterations(int) {}
+    void setInputSource(const typename PointCloud<A>::ConstPtr &c) { src_ = c; }
+    void setInputTarget(const typename PointCloud<B>::ConstPtr &c) { tgt_ = c; }
+    void align(PointCloud<A> &)
+    {
+        LlrefIcpRecord &r = llref_icp_last();
+        r.source.resize(src_->points.size()); r.target.resize(tgt_->points.size());
+        for (size_t i = 0; i < r.source.size(); i++) r.source[i] = llo_point{ src_->points[i].x, src_->points[i].y, src_->points[i].z, src_->points[i].intensity };
+        for (size_t i = 0; i < r.target.size(); i++) r.target[i] = llo_point{ tgt_->points[i].x, tgt_->points[i].y, tgt_->points[i].z, tgt_->points[i].intensity };
+        llo_icp_align(r.source.data(), (int)r.source.size(), r.target.data(), (int)r.target.size(), max_iter_, max_dist_, teps_, feps_,
+                      r.T, &r.converged, &r.iterations, &r.state, &r.fitness);
+        r.calls++;
+    }
+    bool hasConverged() const { return llref_icp_last().converged != 0; }
+    double getFitnessScore() const { return llref_icp_last().fitness; }
+    Eigen::Matrix4f getFinalTransformation() const { Eigen::Matrix4f m; for (int i = 0; i < 16; i++) m.m[i] = llref_icp_last().T[i]; return m; }
+private:
+    typename PointCloud<A>::ConstPtr src_; typename PointCloud<B>::ConstPtr tgt_;
+    double max_dist_ = 1e30, teps_ = 0, feps_ = 0; int max_iter_ = 10;
 };
 inline Eigen::Affine3f getTransformation(float, float, float, float, float, float) { return Eigen::Affine3f(); }
 inline void getTranslationAndEulerAngles(const Eigen::Affine3f &, float &x, float &y, float &z, float &r, float &p, float &yw)

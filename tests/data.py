@@ -40,3 +40,43 @@ def random_cloud(n: int, seed: int, extent=(60.0, 8.0, 60.0), clustered: bool = 
     out[:, :3] = pts
     out[:, 3] = rng.integers(0, 16, n) + rng.random(n).astype(np.float32) * 0.1
     return out
+
+
+_LOOP_CASE = {}
+
+
+def loop_closure_case(n_out: int = 24, step: float = 0.7):
+    """A key-frame store the REFERENCE node logic (oracle/_ref, unmodified mapOptmization.cpp) builds over an out-and-back
+    drive: n_out key-frames away from the start, n_out back on a lane 1 m beside it, 2.5 s apart, with an odometry drift that
+    grows on the way back - so that at the end detectLoopClosure (MO:814-872) finds a history frame older than 30 s within
+    7 m and performLoopClosure (MO:875-945) aligns the latest key-frame against the 51-frame history sub-map.
+    -> dict(mo, n_kf, truth poses); cached (the harness object is reused read-only by the tests)."""
+    key = (n_out, step)
+    if key in _LOOP_CASE:
+        return _LOOP_CASE[key]
+    from oracle import ref_harness
+    w = world()
+    mo = ref_harness.MapOptimization()
+    truth = []
+    n = 2 * n_out
+    for k in range(n):
+        if k < n_out:
+            x, z, yaw = 2.0, -10.0 + step * k, 0.0
+        else:
+            x, z, yaw = 3.0, -10.0 + step * (n - 1 - k), np.pi
+        pose = np.array([0.004 * np.sin(0.3 * k), yaw + 0.01 * np.sin(0.2 * k), 0.004 * np.cos(0.2 * k), x, 0.0, z])
+        f = max(0.0, (k - n_out) / max(n_out - 1, 1))
+        odo = pose + f * np.array([0.002, 0.012, -0.002, 0.25, 0.03, -0.2])         # drift of the odometry on the way back
+        sc = synth.make_mapping_scan(w, synth.VLP16, pose, seed=4000 + k)
+        mo.set_odometry(odo.astype(np.float32), 2.5 * k)
+        mo.set_scan(sc.corner_last, sc.surf_last, sc.outlier_last)
+        mo.transformAssociateToMap()
+        mo.downsampleCurrentScan()
+        mo.transformUpdate()
+        mo.saveKeyFramesAndFactor()
+        mo.correctPoses()
+        mo.clearCloud()
+        truth.append(pose)
+    out = dict(mo=mo, n_kf=mo.num_keyframes(), truth=np.array(truth), last_odo=odo, t_last=2.5 * (n - 1))
+    _LOOP_CASE[key] = out
+    return out

@@ -49,17 +49,25 @@ def main():
         t0 = time.perf_counter()
         T_fused, st_f = multi_gpu.sharded_scan2map_fused(ctx, init)
         fused_wall.append((time.perf_counter() - t0) * 1e3); fused_dev.append(st_f.device_ms)
+    # MAP sharded (preferred form): every rank filters + indexes its slab of the raw map only; fused exchange
+    info = multi_gpu.set_sharded_map(ctx, mc, ms, rank, world)
+    ctx.scan_set(sc.corner_last, sc.surf_last, sc.outlier_last); ctx.downsample_current_scan()
+    T_slab, st_s = multi_gpu.sharded_scan2map_fused(ctx, init)
+    ok_slab = bool(np.array_equal(np.asarray(T_slab, np.float32).view(np.uint32), np.asarray(T_single, np.float32).view(np.uint32))) \
+        and st_s.iterations == st.iterations
     ok_fused = bool(np.array_equal(T_fused, T_shard)) and st_f.iterations == st.iterations
     ok = bool(np.allclose(T_shard, T_single, atol=1e-6)) and iters == st.iterations and ok_fused
     gathered = [None] * world
-    dist.all_gather_object(gathered, T_shard.tolist())
-    same = all(g == gathered[0] for g in gathered)          # the redundant LM steps stayed bit-identical
+    dist.all_gather_object(gathered, (T_shard.tolist(), np.asarray(T_slab).tolist(), ok_slab, int(info.raw_kept[0] + info.raw_kept[1])))
+    same = all(g[0] == gathered[0][0] and g[1] == gathered[0][1] for g in gathered)   # the redundant LM steps stayed bit-identical
+    ok = ok and all(g[2] for g in gathered)
     if rank == 0:
         print(json.dumps({"world": world, "queries": counts[0] + counts[3], "map_ds": [int(ctx.map_get_ds(0).shape[0]), int(ctx.map_get_ds(1).shape[0])],
                           "iterations_single": st.iterations, "iterations_sharded": iters, "pose_match": ok,
                           "bit_identical_across_ranks": same, "max_abs_diff": float(np.max(np.abs(T_shard - T_single))),
                           "single_gpu_device_ms": st.device_ms, "sharded_nccl_wall_ms_median": float(np.median(res)),
-                          "fused_matches_nccl_bitwise": ok_fused, "fused_wall_ms_median": float(np.median(fused_wall[2:])),
+                          "fused_matches_nccl_bitwise": ok_fused, "map_sharded_pose_equals_single_bitwise": all(g[2] for g in gathered),
+                          "map_sharded_raw_points_per_rank": [g[3] for g in gathered], "raw_points": int(mc.shape[0] + ms.shape[0]), "fused_wall_ms_median": float(np.median(fused_wall[2:])),
                           "fused_device_ms_median": float(np.median(fused_dev[2:]))}))
     dist.destroy_process_group()
     ctx.close()
