@@ -275,7 +275,6 @@ void IcpSolver::init()
     if (per_sm < 1) throw std::runtime_error("icp_kernel cannot be made resident");
     max_blocks_ = sms * std::min(per_sm, 2);
     partials_.ensure((size_t)max_blocks_ * ICP_NSUM);
-    LLB_CUDA(cudaMemset(state_.p, 0, sizeof(IcpState)));
 }
 
 void IcpSolver::release() { state_.release(); cur_.release(); nn_.release(); partials_.release(); }

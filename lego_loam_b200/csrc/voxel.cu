@@ -164,16 +164,21 @@ radix_scatter_kernel(const LargeVoxelJob *__restrict__ table, int shift)
     const int *vin = odd ? vB : vA; int *vout = odd ? vA : vB;
 
     constexpr int NW = LG_THREADS / 32;
-    __shared__ int s_base[256];
-    __shared__ int s_wcnt[NW][256];
+    constexpr int ITEMS = 8, SUB = LG_THREADS * ITEMS;
+    __shared__ int s_base[256];              // global position of the next key of digit d
+    __shared__ int s_wcnt[NW][256];          // per-warp digit counters -> per-warp offsets inside the digit's run of the sub-tile
+    __shared__ int s_lstart[257];            // start of digit d's run inside the sorted sub-tile
+    __shared__ int s_gdelta[256];            // global position of that run minus its local start
+    __shared__ int s_scan[33];
+    __shared__ unsigned s_k[SUB];            // the sub-tile in sorted order: each digit's run leaves as consecutive,
+    __shared__ int s_v[SUB];                 // coalesced stores instead of one 4-byte store per lane into up to 32 sectors
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     s_base[tid] = hist[tid * gridDim.x + blockIdx.x];
     int lo, hi;
     radix_tile(d->n, gridDim.x, blockIdx.x, lo, hi);
     // Sub-tiles of 2048 keys: warp w owns the contiguous keys [w*256, (w+1)*256) of the sub-tile and ranks them
-    // in 8 rounds of 32 against its PRIVATE digit counters (warp-level sync only), so a sub-tile costs two block
-    // barriers instead of three per 256 keys.  Order of ranks = (sub-tile, warp, round, lane) = input order: stable.
-    constexpr int ITEMS = 8, SUB = LG_THREADS * ITEMS;
+    // in 8 rounds of 32 against its PRIVATE digit counters (warp-level sync only).  Order of ranks = (sub-tile, warp,
+    // round, lane) = input order: stable.
     const unsigned lt = (1u << lane) - 1u;
     for (int sub = lo; sub < hi; sub += SUB) {
 #pragma unroll
@@ -200,19 +205,30 @@ radix_scatter_kernel(const LargeVoxelJob *__restrict__ table, int shift)
             __syncwarp();
         }
         __syncthreads();
-        {   // thread tid owns digit tid: turn per-warp counts into offsets
-            int run = s_base[tid];
+        int dtot = 0;
+        {   // thread tid owns digit tid: per-warp counts -> offsets inside the digit's run; dtot = keys of that digit
 #pragma unroll
-            for (int k = 0; k < NW; k++) { int c = s_wcnt[k][tid]; s_wcnt[k][tid] = run; run += c; }
-            s_base[tid] = run;
+            for (int k = 0; k < NW; k++) { const int c = s_wcnt[k][tid]; s_wcnt[k][tid] = dtot; dtot += c; }
         }
+        int stot;
+        const int lstart = block_excl_scan(dtot, s_scan, stot);          // (barriers inside)
+        s_lstart[tid] = lstart;
+        s_gdelta[tid] = s_base[tid] - lstart;
+        s_base[tid] += dtot;
+        if (tid == 0) s_lstart[256] = stot;
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) {
             if (dg[r] < 256u) {
-                const int pos = s_wcnt[w][dg[r]] + rk[r];
-                kout[pos] = key[r]; vout[pos] = val[r];
+                const int lp = s_lstart[dg[r]] + s_wcnt[w][dg[r]] + rk[r];
+                s_k[lp] = key[r]; s_v[lp] = val[r];
             }
+        }
+        __syncthreads();
+        for (int e = tid; e < stot; e += LG_THREADS) {
+            const unsigned kk = s_k[e];
+            const int pos = s_gdelta[(kk >> shift) & 255u] + e;
+            kout[pos] = kk; vout[pos] = s_v[e];
         }
         __syncthreads();
     }
@@ -230,67 +246,91 @@ __device__ __forceinline__ void sorted_bufs(const VoxelDesc *d, const unsigned *
 constexpr int HEAD_TILE = 1024;         // one filter alone: few, large CTAs (short block-count scan)
 constexpr int HEAD_TILE_BATCH = 256;    // batched: small CTAs, 8 resident per SM overlap the load -> scan -> walk chains
 
+constexpr int HEAD_GROUP = 8;           // tiles per CTA of the head count (the per-TILE counts feed the centroid kernel)
+
 template <int TILE>
 __global__ void __launch_bounds__(TILE)
-voxel_heads_kernel(const LargeVoxelJob *__restrict__ table)
+voxel_heads_kernel(const LargeVoxelJob *__restrict__ table, int nblk)
 {
     LG_JOB(table);
     const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB; int *__restrict__ blk = jb.blk;
     const unsigned *k; const int *v;
     sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
     const int n = d->n;
-    const int i = blockIdx.x * TILE + threadIdx.x;
-    int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
-    int cnt = __syncthreads_count(head);
-    if (threadIdx.x == 0) blk[blockIdx.x] = cnt;
+#pragma unroll 1
+    for (int r = 0; r < HEAD_GROUP; r++) {
+        const int tile = blockIdx.x * HEAD_GROUP + r;
+        if (tile >= nblk) break;                             // uniform over the CTA; tiles past n count 0 (the scan reads all nblk)
+        const int i = tile * TILE + threadIdx.x;
+        int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
+        int cnt = __syncthreads_count(head);
+        if (threadIdx.x == 0) blk[tile] = cnt;
+    }
 }
 
-// points in sorted order: psorted[i] = in[v[i]] (fully parallel gather, coalesced writes), so that the ordered per-voxel
-// sums below walk CONTIGUOUS memory instead of chasing one random 16-byte load per point
-__global__ void __launch_bounds__(LG_THREADS)
-voxel_gather_kernel(const LargeVoxelJob *__restrict__ table)
-{
-    LG_JOB(table);
-    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc;
-    const unsigned *k; const int *v;
-    sorted_bufs(d, jb.kA, jb.kB, jb.vA, jb.vB, k, v);
-    const int n = d->n;
-    const int na = seg_len_a(in);
-    for (int i = blockIdx.x * LG_THREADS + threadIdx.x; i < n; i += gridDim.x * LG_THREADS)
-        jb.psorted[i] = seg_load(in, na, __ldg(&v[i]));
-}
-
-// GATHERED: the points were put into sorted order by voxel_gather_kernel (batched launches: thousands of segment walks
-// in flight, contiguous reads pay); otherwise each walk fetches its points through the sorted index list (one filter
-// alone: one launch less on the latency path)
-template <bool GATHERED, int TILE>
+// One CTA per tile of TILE sorted positions: keys and points of the tile are staged in shared memory (the points are
+// fetched through the sorted index list: the gather is part of this kernel, nothing is written in between), heads are
+// ranked with the per-tile counts of voxel_heads_kernel, and the thread of every head walks its voxel IN shared memory
+// (the sums stay sequential in ascending input index, as PCL adds them); a voxel that runs past the tile is finished
+// from global memory.  The walk used to chase one dependent global load per point.
+template <int TILE>
 __global__ void __launch_bounds__(TILE)
 voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
-    const VoxelDesc *__restrict__ d = jb.desc; const unsigned *kA = jb.kA, *kB = jb.kB;
+    const VoxelDesc *__restrict__ d = jb.desc;
+    const int n = d->n;
+    const int i0 = blockIdx.x * TILE;
+    if (i0 >= n) return;                                     // the grid is sized for the longest job of the table
     const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
-    const float4 *__restrict__ ps = jb.psorted;
     const SegIn in = jb.in;
     const int na = seg_len_a(in);
     __shared__ int s_scan[33];
+    __shared__ unsigned s_key[TILE];
+    __shared__ float4 s_pt[TILE];
     const unsigned *k; const int *v;
-    sorted_bufs(d, kA, kB, jb.vA, jb.vB, k, v);
-    const int n = d->n;
-    const int i = blockIdx.x * TILE + threadIdx.x;
-    int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
+    sorted_bufs(d, jb.kA, jb.kB, jb.vA, jb.vB, k, v);
+    const int t = threadIdx.x, i = i0 + t;
+    unsigned key = 0u;
+    if (i < n) {
+        key = k[i];
+        s_key[t] = key;
+        s_pt[t] = seg_load(in, na, __ldg(&v[i]));
+    }
+    __syncthreads();
+    int head = 0;
+    if (i < n) head = (i == 0) ? 1 : (t == 0 ? (k[i - 1] != key) : (s_key[t - 1] != key));
     int total;
-    int rank = blk[blockIdx.x] + block_excl_scan(head, s_scan, total);
+    const int rank = blk[blockIdx.x] + block_excl_scan(head, s_scan, total);
     if (head) {
-        const unsigned cur = k[i];
+        const int tn = min(TILE, n - i0);
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-        int j = i;
-        while (j < n && k[j] == cur) {
-            const float4 p = GATHERED ? ps[j] : seg_load(in, na, v[j]);
+        int j = t;
+        // the keys are sorted: if the 4th key ahead still belongs to this voxel, so do the three before it.  Four
+        // points per trip: the loads are independent, only the four float chains stay sequential (PCL's order)
+        while (j + 4 <= tn && s_key[j + 3] == key) {
+            const float4 p0 = s_pt[j], p1 = s_pt[j + 1], p2 = s_pt[j + 2], p3 = s_pt[j + 3];
+            sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+            sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+            sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+            sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+            j += 4;
+        }
+        while (j < tn && s_key[j] == key) {
+            const float4 p = s_pt[j];
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             j++;
         }
-        float cnt = (float)(j - i);
+        int cntp = j - t;
+        if (j == TILE) {                                     // the voxel continues in the next tile(s)
+            int g = i0 + TILE;
+            while (g < n && k[g] == key) {
+                const float4 p = seg_load(in, na, v[g]);
+                sx += p.x; sy += p.y; sz += p.z; si += p.w;
+                g++; cntp++;
+            }
+        }
+        const float cnt = (float)cntp;
         out[rank] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
     }
 }
@@ -307,7 +347,7 @@ void VoxelFilter::init()
 void VoxelFilter::reserve(int n)
 {
     if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
-    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n); psorted_.ensure(n);
+    keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
     hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
     blk_.ensure(div_up(n, HEAD_TILE_BATCH) + 1);
 }
@@ -315,7 +355,7 @@ void VoxelFilter::reserve(int n)
 void VoxelFilter::release()
 {
     desc_.release(); keys_[0].release(); keys_[1].release(); vals_[0].release(); vals_[1].release();
-    hist_.release(); blk_.release(); job_raw_.release(); psorted_.release(); job_pin_.release();
+    hist_.release(); blk_.release(); job_raw_.release(); job_pin_.release();
     if (job_ev_) { cudaEventDestroy(job_ev_); job_ev_ = nullptr; }
 }
 
@@ -357,7 +397,7 @@ LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *o
     LargeVoxelJob j;
     j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in;
     j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
-    j.hist = hist_.p; j.blk = blk_.p; j.psorted = psorted_.p; j.out = out; j.n_out = n_out_dev;
+    j.hist = hist_.p; j.blk = blk_.p; j.out = out; j.n_out = n_out_dev;
     return j;
 }
 
@@ -383,16 +423,14 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
         radix_scatter_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
         launches += 3;
     }
-    if (count > 1) voxel_heads_kernel<HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev);
-    else voxel_heads_kernel<HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev);
+    const dim3 grid_heads(div_up(nblk_head, HEAD_GROUP), ny);
+    if (count > 1) voxel_heads_kernel<HEAD_TILE_BATCH><<<grid_heads, HEAD_TILE_BATCH, 0, s>>>(table_dev, nblk_head);
+    else voxel_heads_kernel<HEAD_TILE><<<grid_heads, HEAD_TILE, 0, s>>>(table_dev, nblk_head);
     launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
-    if (count > 1) {
-        voxel_gather_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
-        voxel_centroid_kernel<true, HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev); launches++;
-    } else {
-        voxel_centroid_kernel<false, HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev); launches++;
-    }
+    if (count > 1) voxel_centroid_kernel<HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev);
+    else voxel_centroid_kernel<HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev);
+    launches++;
     LLB_CUDA(cudaGetLastError());
     return launches;
 }

@@ -60,7 +60,6 @@ private:
     DevBuf<unsigned char> job_raw_;
     PinnedBuf<unsigned char> job_pin_;
     cudaEvent_t job_ev_ = nullptr;
-    DevBuf<float4> psorted_;    // points in sorted order (multi-kernel path)
     bool small_attr_set_ = false;
 };
 

@@ -111,6 +111,54 @@ public:
         map_on_device_ = true;
     }
 
+    // ---- loop closure + global map (loopClosureEnableFlag UT:104) ----
+    // Members with the reference's names (MO:140-146, MO:151-154).  The host keeps the key-pose searches and the pose
+    // graph (MO:822-837, MO:919-944); the device does the cloud work on its key-frame store.
+    Cloud::Ptr latestSurfKeyFrameCloud{ new Cloud() }, nearHistorySurfKeyFrameCloudDS{ new Cloud() }, globalMapKeyFramesDS{ new Cloud() };
+    int closestHistoryFrameID = -1, latestFrameIDLoopCloure = -1;
+    llb_icp_result last_icp{};
+    // cloud part of detectLoopClosure MO:838-861 once the caller has found closestHistoryFrameID (MO:822-837):
+    // poses6d(i) must return cloudKeyPoses6D[i] as {roll, pitch, yaw, x, y, z}; historyKeyframeSearchNum = 25 (UT:133)
+    template <typename PoseOf>
+    bool detectLoopClosureClouds(int closest_id, int latest_id, PoseOf poses6d, int history_num = 25, bool fetch = false)
+    {
+        closestHistoryFrameID = closest_id; latestFrameIDLoopCloure = latest_id;
+        std::vector<int> ids; std::vector<float> hp;
+        for (int j = -history_num; j <= history_num; ++j) {                         // MO:853-855
+            if (closest_id + j < 0 || closest_id + j > latest_id) continue;
+            ids.push_back(closest_id + j);
+            const float *p = poses6d(closest_id + j); hp.insert(hp.end(), p, p + 6);
+        }
+        int counts[2] = { 0, 0 };
+        last_status = llb_loop_set_clouds(ctx_, latest_id, poses6d(latest_id), ids.data(), hp.data(), (int)ids.size(), 0.4f, counts);
+        if (last_status != LLB_OK) return false;
+        if (fetch) {
+            fetch_cloud(&llb_loop_get_cloud, 0, *latestSurfKeyFrameCloud);
+            fetch_cloud(&llb_loop_get_cloud, 2, *nearHistorySurfKeyFrameCloudDS);
+        }
+        return true;
+    }
+    // the ICP of performLoopClosure MO:892-904: icp.align + hasConverged + getFitnessScore; true when the reference would
+    // go on to add the factor (MO:904); last_icp.T is icp.getFinalTransformation() (row-major)
+    bool performLoopClosureICP(bool clouds_from_members = false, float historyKeyframeFitnessScore = 0.3f)
+    {
+        if (clouds_from_members) {
+            last_status = llb_loop_set_clouds_host(ctx_, as_llb(*latestSurfKeyFrameCloud), (int)latestSurfKeyFrameCloud->size(),
+                                                   as_llb(*nearHistorySurfKeyFrameCloudDS), (int)nearHistorySurfKeyFrameCloudDS->size());
+            if (last_status != LLB_OK) return false;
+        }
+        last_status = llb_loop_icp(ctx_, nullptr, &last_icp);
+        if (last_status != LLB_OK) return false;
+        return last_icp.has_converged && !(last_icp.fitness_score > (double)historyKeyframeFitnessScore);
+    }
+    // cloud part of publishGlobalMap MO:780-788 for the key-frames the caller selected (MO:766-778)
+    void publishGlobalMapClouds(const std::vector<int> &ids, const std::vector<float> &poses6d)
+    {
+        int n = 0;
+        last_status = llb_global_map_assemble(ctx_, ids.data(), poses6d.data(), (int)ids.size(), 0.4f, &n);
+        if (last_status == LLB_OK) fetch_cloud(&llb_loop_get_cloud, 3, *globalMapKeyFramesDS);
+    }
+
     void downsampleCurrentScan()                                   // MO:1067
     {
         last_status = llb_scan_set(ctx_, as_llb(*laserCloudCornerLast), (int)laserCloudCornerLast->size(),

@@ -140,5 +140,11 @@ int main(int argc, char **argv)
         printf(" %zu %u %zu %u\n", FI.laserCloudCornerLast->size(), fnv_cloud(*FI.laserCloudCornerLast, true),
                FI.laserCloudSurfLast->size(), fnv_cloud(*FI.laserCloudSurfLast, true));
     }
+    // loop closure: the ICP of performLoopClosure MO:892-904 on the adapter's members
+    read_cloud(f, *MO.latestSurfKeyFrameCloud); read_cloud(f, *MO.nearHistorySurfKeyFrameCloudDS);
+    const bool closed = MO.performLoopClosureICP(true);
+    printf("LC %d %d %d %d %.17g", MO.last_status, (int)closed, MO.last_icp.iterations, MO.last_icp.convergence_state, MO.last_icp.fitness_score);
+    for (int k = 0; k < 16; k++) printf(" %.9g", MO.last_icp.T[k]);
+    printf("\n");
     return 0;
 }

@@ -74,6 +74,13 @@ def test_adapter_matches_oracle(tmp_path):
             f.write(swi.range.astype(np.float32).tobytes())
             f.write(t_cur.tobytes())
             imu_sweeps.append((msgs, stamp, swi, t_cur))
+        # loop closure: a source cloud = part of the target moved by a small rigid motion
+        rng = np.random.default_rng(12)
+        lc_tgt = np.zeros((12000, 4), np.float32); lc_tgt[:, :3] = rng.uniform(-25, 25, (12000, 3)) * [1, 0.1, 1]
+        a = 0.02; Rm = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        lc_src = lc_tgt[rng.choice(12000, 2500, replace=False)].copy()
+        lc_src[:, :3] = (lc_src[:, :3] @ Rm.T + np.array([0.25, 0.02, -0.2])).astype(np.float32)
+        w(lc_src); w(lc_tgt)
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.splitlines()
     mo_line = out[0].split(); tu_line = out[1].split(); fa_line = out[2].split()
 
@@ -151,3 +158,10 @@ def test_adapter_matches_oracle(tmp_path):
             rfa.publishCloudsLast()
             cl, sl = rfa.feature_cloud(5), rfa.feature_cloud(6)
             assert (int(line[34]), int(line[35]), int(line[36]), int(line[37])) == (cl.shape[0], fnv4(cl), sl.shape[0], fnv4(sl))
+
+    # loop-closure ICP through the adapter against the restated PCL algorithm
+    lc = [l for l in out if l.startswith("LC ")][0].split()
+    want_lc = oracle.icp_align(lc_src, lc_tgt)
+    assert int(lc[1]) == 0 and int(lc[2]) == 1 and int(lc[3]) == want_lc["iterations"] and int(lc[4]) == want_lc["state"]
+    assert abs(float(lc[5]) - want_lc["fitness"]) < 1e-9
+    assert np.abs(np.array(lc[6:22], np.float32).reshape(4, 4) - want_lc["T"]).max() < 1e-6
