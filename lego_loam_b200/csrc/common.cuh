@@ -81,6 +81,22 @@ __device__ __forceinline__ float ordered_to_float(int i)
     return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
 }
 
+// lanes of the warp that hold the same value in the low BITS bits of v (what __match_any_sync returns), from BITS
+// ballots: on sm_100 the result latency of MATCH.ANY dominated the radix ranking loops (half of all stall samples,
+// profiles/r02_voxel.md); the ballots of independent keys overlap
+template <int BITS>
+__device__ __forceinline__ unsigned match_low_bits(unsigned v)
+{
+    unsigned m = FULL;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (v >> b) & 1u;
+        const unsigned bal = __ballot_sync(FULL, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v)
 {
     const int lane = threadIdx.x & 31;

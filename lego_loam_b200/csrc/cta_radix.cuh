@@ -43,7 +43,7 @@ __device__ __forceinline__ void cta_radix_sort(unsigned *&kin, unsigned *&kout, 
             }
 #pragma unroll
             for (int r = 0; r < ITEMS; r++) {
-                const unsigned m = __match_any_sync(FULL, dg[r]);
+                const unsigned m = match_low_bits<9>(dg[r]);
                 const int pr = __popc(m & lt);
                 int cnt = 0;
                 if (dg[r] < 256u) cnt = s_wcnt[w][dg[r]];

@@ -195,7 +195,7 @@ radix_scatter_kernel(const LargeVoxelJob *__restrict__ table, int shift)
         }
 #pragma unroll
         for (int r = 0; r < ITEMS; r++) {
-            const unsigned m = __match_any_sync(FULL, dg[r]);
+            const unsigned m = match_low_bits<9>(dg[r]);      // digit, or 256 + lane for the lanes past the tile
             const int pr = __popc(m & lt);
             int cnt = 0;
             if (dg[r] < 256u) cnt = s_wcnt[w][dg[r]];
@@ -243,13 +243,14 @@ __device__ __forceinline__ void sorted_bufs(const VoxelDesc *d, const unsigned *
     v = (passes & 1) ? vB : vA;
 }
 
-constexpr int HEAD_TILE = 1024;         // one filter alone: few, large CTAs (short block-count scan)
-constexpr int HEAD_TILE_BATCH = 256;    // batched: small CTAs, 8 resident per SM overlap the load -> scan -> walk chains
+// heads + centroids work on tiles of HEAD_TILE sorted positions: HEAD_THREADS threads, HEAD_ITEMS positions each
+// (position r * HEAD_THREADS + t of the tile: coalesced, and all loads of a thread are in flight together)
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_ITEMS = 4;
+constexpr int HEAD_TILE = HEAD_THREADS * HEAD_ITEMS;
+constexpr int HEAD_GROUP = 2;           // tiles per CTA of the head count (the per-tile counts feed the centroid kernel)
 
-constexpr int HEAD_GROUP = 8;           // tiles per CTA of the head count (the per-TILE counts feed the centroid kernel)
-
-template <int TILE>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(HEAD_THREADS)
 voxel_heads_kernel(const LargeVoxelJob *__restrict__ table, int nblk)
 {
     LG_JOB(table);
@@ -258,80 +259,97 @@ voxel_heads_kernel(const LargeVoxelJob *__restrict__ table, int nblk)
     sorted_bufs(d, kA, kB, nullptr, nullptr, k, v);
     const int n = d->n;
 #pragma unroll 1
-    for (int r = 0; r < HEAD_GROUP; r++) {
-        const int tile = blockIdx.x * HEAD_GROUP + r;
+    for (int g = 0; g < HEAD_GROUP; g++) {
+        const int tile = blockIdx.x * HEAD_GROUP + g;
         if (tile >= nblk) break;                             // uniform over the CTA; tiles past n count 0 (the scan reads all nblk)
-        const int i = tile * TILE + threadIdx.x;
-        int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
-        int cnt = __syncthreads_count(head);
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < HEAD_ITEMS; r++) {
+            const int i = tile * HEAD_TILE + r * HEAD_THREADS + threadIdx.x;
+            const int head = (i < n) && (i == 0 || k[i - 1] != k[i]);
+            cnt += __syncthreads_count(head);
+        }
         if (threadIdx.x == 0) blk[tile] = cnt;
     }
 }
 
-// One CTA per tile of TILE sorted positions: keys and points of the tile are staged in shared memory (the points are
-// fetched through the sorted index list: the gather is part of this kernel, nothing is written in between), heads are
-// ranked with the per-tile counts of voxel_heads_kernel, and the thread of every head walks its voxel IN shared memory
-// (the sums stay sequential in ascending input index, as PCL adds them); a voxel that runs past the tile is finished
-// from global memory.  The walk used to chase one dependent global load per point.
-template <int TILE>
-__global__ void __launch_bounds__(TILE)
+// One CTA per tile of sorted positions: keys and points of the tile are staged in shared memory (the points are fetched
+// through the sorted index list: the gather is part of this kernel, nothing is written in between), heads are ranked
+// with the per-tile counts of voxel_heads_kernel, and the thread of every head walks its voxel IN shared memory (the
+// sums stay sequential in ascending input index, as PCL adds them); a voxel that runs past the tile is finished from
+// global memory.  The walk used to chase one dependent global load per point.
+__global__ void __launch_bounds__(HEAD_THREADS)
 voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
     const VoxelDesc *__restrict__ d = jb.desc;
     const int n = d->n;
-    const int i0 = blockIdx.x * TILE;
+    const int i0 = blockIdx.x * HEAD_TILE;
     if (i0 >= n) return;                                     // the grid is sized for the longest job of the table
     const int *__restrict__ blk = jb.blk; float4 *__restrict__ out = jb.out;
     const SegIn in = jb.in;
     const int na = seg_len_a(in);
     __shared__ int s_scan[33];
-    __shared__ unsigned s_key[TILE];
-    __shared__ float4 s_pt[TILE];
+    __shared__ unsigned s_key[HEAD_TILE];
+    __shared__ float4 s_pt[HEAD_TILE];
     const unsigned *k; const int *v;
     sorted_bufs(d, jb.kA, jb.kB, jb.vA, jb.vB, k, v);
-    const int t = threadIdx.x, i = i0 + t;
-    unsigned key = 0u;
-    if (i < n) {
-        key = k[i];
-        s_key[t] = key;
-        s_pt[t] = seg_load(in, na, __ldg(&v[i]));
+    const int t = threadIdx.x;
+    const int tn = min(HEAD_TILE, n - i0);
+    unsigned key[HEAD_ITEMS]; int src[HEAD_ITEMS];
+#pragma unroll
+    for (int r = 0; r < HEAD_ITEMS; r++) {
+        const int p = r * HEAD_THREADS + t;
+        key[r] = p < tn ? k[i0 + p] : 0u;
+        src[r] = p < tn ? __ldg(&v[i0 + p]) : 0;
+    }
+    const unsigned kprev = i0 > 0 ? k[i0 - 1] : 0u;
+#pragma unroll
+    for (int r = 0; r < HEAD_ITEMS; r++) {
+        const int p = r * HEAD_THREADS + t;
+        if (p < tn) { s_key[p] = key[r]; s_pt[p] = seg_load(in, na, src[r]); }
     }
     __syncthreads();
-    int head = 0;
-    if (i < n) head = (i == 0) ? 1 : (t == 0 ? (k[i - 1] != key) : (s_key[t - 1] != key));
-    int total;
-    const int rank = blk[blockIdx.x] + block_excl_scan(head, s_scan, total);
-    if (head) {
-        const int tn = min(TILE, n - i0);
-        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-        int j = t;
-        // the keys are sorted: if the 4th key ahead still belongs to this voxel, so do the three before it.  Four
-        // points per trip: the loads are independent, only the four float chains stay sequential (PCL's order)
-        while (j + 4 <= tn && s_key[j + 3] == key) {
-            const float4 p0 = s_pt[j], p1 = s_pt[j + 1], p2 = s_pt[j + 2], p3 = s_pt[j + 3];
-            sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
-            sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
-            sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
-            sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
-            j += 4;
-        }
-        while (j < tn && s_key[j] == key) {
-            const float4 p = s_pt[j];
-            sx += p.x; sy += p.y; sz += p.z; si += p.w;
-            j++;
-        }
-        int cntp = j - t;
-        if (j == TILE) {                                     // the voxel continues in the next tile(s)
-            int g = i0 + TILE;
-            while (g < n && k[g] == key) {
-                const float4 p = seg_load(in, na, v[g]);
-                sx += p.x; sy += p.y; sz += p.z; si += p.w;
-                g++; cntp++;
+    int base = blk[blockIdx.x];
+#pragma unroll 1
+    for (int r = 0; r < HEAD_ITEMS; r++) {
+        const int p = r * HEAD_THREADS + t;
+        int head = 0;
+        const unsigned kk = p < tn ? s_key[p] : 0u;
+        if (p < tn) head = (p == 0) ? (i0 == 0 || kprev != kk) : (s_key[p - 1] != kk);
+        int total;
+        const int rank = base + block_excl_scan(head, s_scan, total);
+        base += total;
+        if (head) {
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            int j = p;
+            // the keys are sorted: if the 4th key ahead still belongs to this voxel, so do the three before it.  Four
+            // points per trip: the loads are independent, only the four float chains stay sequential (PCL's order)
+            while (j + 4 <= tn && s_key[j + 3] == kk) {
+                const float4 p0 = s_pt[j], p1 = s_pt[j + 1], p2 = s_pt[j + 2], p3 = s_pt[j + 3];
+                sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+                sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+                sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+                sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+                j += 4;
             }
+            while (j < tn && s_key[j] == kk) {
+                const float4 q = s_pt[j];
+                sx += q.x; sy += q.y; sz += q.z; si += q.w;
+                j++;
+            }
+            int cntp = j - p;
+            if (j == HEAD_TILE) {                            // the voxel continues in the next tile(s)
+                int g = i0 + HEAD_TILE;
+                while (g < n && k[g] == kk) {
+                    const float4 q = seg_load(in, na, v[g]);
+                    sx += q.x; sy += q.y; sz += q.z; si += q.w;
+                    g++; cntp++;
+                }
+            }
+            const float cnt = (float)cntp;
+            out[rank] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
         }
-        const float cnt = (float)cntp;
-        out[rank] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
     }
 }
 
@@ -349,7 +367,7 @@ void VoxelFilter::reserve(int n)
     if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
     keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
     hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
-    blk_.ensure(div_up(n, HEAD_TILE_BATCH) + 1);
+    blk_.ensure(div_up(n, HEAD_TILE) + 1);
 }
 
 void VoxelFilter::release()
@@ -407,8 +425,7 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     const int n = std::max(n_upper, 1);
     // the histogram layout depends on the radix grid: it must be the same for sizing (reserve) and launching
     const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, 4096));
-    const int head_tile = count > 1 ? HEAD_TILE_BATCH : HEAD_TILE;
-    const int nblk_head = div_up(n, head_tile);
+    const int nblk_head = div_up(n, HEAD_TILE);
     const unsigned ny = (unsigned)std::max(count, 1);
     const int per = count > 1 ? std::max(8, 148 * 8 / count) : 148 * 8;
     const dim3 grid_stream(std::min(div_up(n, LG_THREADS), per), ny);
@@ -423,14 +440,9 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
         radix_scatter_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
         launches += 3;
     }
-    const dim3 grid_heads(div_up(nblk_head, HEAD_GROUP), ny);
-    if (count > 1) voxel_heads_kernel<HEAD_TILE_BATCH><<<grid_heads, HEAD_TILE_BATCH, 0, s>>>(table_dev, nblk_head);
-    else voxel_heads_kernel<HEAD_TILE><<<grid_heads, HEAD_TILE, 0, s>>>(table_dev, nblk_head);
-    launches++;
+    voxel_heads_kernel<<<dim3(div_up(nblk_head, HEAD_GROUP), ny), HEAD_THREADS, 0, s>>>(table_dev, nblk_head); launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
-    if (count > 1) voxel_centroid_kernel<HEAD_TILE_BATCH><<<dim3(nblk_head, ny), HEAD_TILE_BATCH, 0, s>>>(table_dev);
-    else voxel_centroid_kernel<HEAD_TILE><<<dim3(nblk_head, ny), HEAD_TILE, 0, s>>>(table_dev);
-    launches++;
+    voxel_centroid_kernel<<<dim3(nblk_head, ny), HEAD_THREADS, 0, s>>>(table_dev); launches++;
     LLB_CUDA(cudaGetLastError());
     return launches;
 }
