@@ -20,6 +20,12 @@ namespace {
 
 constexpr int LG_THREADS = 256;
 constexpr int RADIX_MAX_BLOCKS = 256;
+// keys per CTA of the radix kernels (histogram layout depends on it: the same value sizes the scratch and the launch)
+static int radix_keys_per_block()
+{
+    static const int v = getenv("LLB_RADIX_KEYS") ? std::max(2048, atoi(getenv("LLB_RADIX_KEYS"))) : 8192;
+    return v;
+}
 
 // every kernel of the large path serves job blockIdx.y of a device-resident table: one entry for a single filter
 // (llb_ctx), 2B entries when the map filters of a batched step share each launch
@@ -34,6 +40,7 @@ __global__ void __launch_bounds__(LG_THREADS)
 voxel_minmax_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
+    if (jb.bounds_ready) return;
     const SegIn in = jb.bounds; VoxelDesc *__restrict__ d = jb.desc;
     __shared__ float s_red[6][LG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -292,6 +299,7 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
     __shared__ int s_scan[33];
     __shared__ unsigned s_key[HEAD_TILE];
     __shared__ float4 s_pt[HEAD_TILE];
+    __shared__ int s_hp[HEAD_TILE];
     const unsigned *k; const int *v;
     sorted_bufs(d, jb.kA, jb.kB, jb.vA, jb.vB, k, v);
     const int t = threadIdx.x;
@@ -310,46 +318,53 @@ voxel_centroid_kernel(const LargeVoxelJob *__restrict__ table)
         if (p < tn) { s_key[p] = key[r]; s_pt[p] = seg_load(in, na, src[r]); }
     }
     __syncthreads();
-    int base = blk[blockIdx.x];
+    // heads of the tile in position order -> s_hp: the walks below then run on CONSECUTIVE threads (one per voxel)
+    // instead of on the scattered head lanes of every warp (a voxel has ~4.5 points: 7 of 32 lanes were active)
+    int nheads = 0;
 #pragma unroll 1
     for (int r = 0; r < HEAD_ITEMS; r++) {
         const int p = r * HEAD_THREADS + t;
-        int head = 0;
         const unsigned kk = p < tn ? s_key[p] : 0u;
+        int head = 0;
         if (p < tn) head = (p == 0) ? (i0 == 0 || kprev != kk) : (s_key[p - 1] != kk);
         int total;
-        const int rank = base + block_excl_scan(head, s_scan, total);
-        base += total;
-        if (head) {
-            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-            int j = p;
-            // the keys are sorted: if the 4th key ahead still belongs to this voxel, so do the three before it.  Four
-            // points per trip: the loads are independent, only the four float chains stay sequential (PCL's order)
-            while (j + 4 <= tn && s_key[j + 3] == kk) {
-                const float4 p0 = s_pt[j], p1 = s_pt[j + 1], p2 = s_pt[j + 2], p3 = s_pt[j + 3];
-                sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
-                sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
-                sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
-                sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
-                j += 4;
-            }
-            while (j < tn && s_key[j] == kk) {
-                const float4 q = s_pt[j];
-                sx += q.x; sy += q.y; sz += q.z; si += q.w;
-                j++;
-            }
-            int cntp = j - p;
-            if (j == HEAD_TILE) {                            // the voxel continues in the next tile(s)
-                int g = i0 + HEAD_TILE;
-                while (g < n && k[g] == kk) {
-                    const float4 q = seg_load(in, na, v[g]);
-                    sx += q.x; sy += q.y; sz += q.z; si += q.w;
-                    g++; cntp++;
-                }
-            }
-            const float cnt = (float)cntp;
-            out[rank] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        const int lr = nheads + block_excl_scan(head, s_scan, total);
+        nheads += total;
+        if (head) s_hp[lr] = p;
+    }
+    __syncthreads();
+    const int base = blk[blockIdx.x];
+    for (int q = t; q < nheads; q += HEAD_THREADS) {
+        const int p = s_hp[q];
+        const unsigned kk = s_key[p];
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        int j = p;
+        // the keys are sorted: if the 4th key ahead still belongs to this voxel, so do the three before it.  Four
+        // points per trip: the loads are independent, only the four float chains stay sequential (PCL's order)
+        while (j + 4 <= tn && s_key[j + 3] == kk) {
+            const float4 p0 = s_pt[j], p1 = s_pt[j + 1], p2 = s_pt[j + 2], p3 = s_pt[j + 3];
+            sx += p0.x; sy += p0.y; sz += p0.z; si += p0.w;
+            sx += p1.x; sy += p1.y; sz += p1.z; si += p1.w;
+            sx += p2.x; sy += p2.y; sz += p2.z; si += p2.w;
+            sx += p3.x; sy += p3.y; sz += p3.z; si += p3.w;
+            j += 4;
         }
+        while (j < tn && s_key[j] == kk) {
+            const float4 pq = s_pt[j];
+            sx += pq.x; sy += pq.y; sz += pq.z; si += pq.w;
+            j++;
+        }
+        int cntp = j - p;
+        if (j == HEAD_TILE) {                                // the voxel continues in the next tile(s)
+            int g = i0 + HEAD_TILE;
+            while (g < n && k[g] == kk) {
+                const float4 pq = seg_load(in, na, v[g]);
+                sx += pq.x; sy += pq.y; sz += pq.z; si += pq.w;
+                g++; cntp++;
+            }
+        }
+        const float cnt = (float)cntp;
+        out[base + q] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
     }
 }
 
@@ -366,7 +381,7 @@ void VoxelFilter::reserve(int n)
 {
     if (n <= SMALL_MAX) return;                              // the small paths need no global scratch
     keys_[0].ensure(n); keys_[1].ensure(n); vals_[0].ensure(n); vals_[1].ensure(n);
-    hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 4096)));
+    hist_.ensure((size_t)256 * std::min(RADIX_MAX_BLOCKS, div_up(n, 2048)));
     blk_.ensure(div_up(n, HEAD_TILE) + 1);
 }
 
@@ -413,24 +428,25 @@ LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *o
     const int n = std::max(in.upper(), 1);
     reserve(std::max(n, SMALL_MAX + 1));
     LargeVoxelJob j;
-    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in;
+    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in; j.bounds_ready = 0;
     j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
     j.hist = hist_.p; j.blk = blk_.p; j.out = out; j.n_out = n_out_dev;
     return j;
 }
 
 // `count` jobs of a device-resident table; n_upper bounds the input length of every job
-int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s)
+int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s, bool bounds_ready)
 {
     const int n = std::max(n_upper, 1);
     // the histogram layout depends on the radix grid: it must be the same for sizing (reserve) and launching
-    const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, 4096));
+    const int nblk_radix = std::min(RADIX_MAX_BLOCKS, div_up(n, radix_keys_per_block()));
     const int nblk_head = div_up(n, HEAD_TILE);
     const unsigned ny = (unsigned)std::max(count, 1);
     const int per = count > 1 ? std::max(8, 148 * 8 / count) : 148 * 8;
     const dim3 grid_stream(std::min(div_up(n, LG_THREADS), per), ny);
     int launches = 0;
-    voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
+    // bounds_ready: every job of the table had its bounds accumulated by the kernel that produced its input
+    if (!bounds_ready) { voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++; }
     voxel_setup_kernel<<<dim3(1, ny), 1, 0, s>>>(table_dev); launches++;
     voxel_keys_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     for (int pass = 0; pass < 4; pass++) {
