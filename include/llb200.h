@@ -342,6 +342,9 @@ typedef struct {
 int llb_map_set_raw_sharded(llb_ctx *ctx, const llb_point *corner, int rc, const llb_point *surf, int rs, int rank, int world);
 int llb_map_set_raw_sharded_dev(llb_ctx *ctx, const void *corner_f4, int rc, const void *surf_f4, int rs, int rank, int world);
 int llb_map_shard_info(llb_ctx *ctx, llb_shard_info *out);
+/* the slab planning alone (pure host function, no context): sample_xyz = nsamp x {x, y, z} map points; every rank must
+ * pass the same sample.  axis = longest extent of the sample, [lo, hi) = quantile interval of `rank` (open at the ends) */
+int llb_shard_plan(const float *sample_xyz, int nsamp, int rank, int world, int *axis, float *lo, float *hi);
 int llb_map_shard_set_global(llb_ctx *ctx, const int global_ds[2]);
 int llb_s2m_pose_set(llb_ctx *ctx, const float T[6]);
 int llb_s2m_pose_get(llb_ctx *ctx, float T[6]);

@@ -67,7 +67,7 @@ EXPORTS = [
     "llb_s2m_time_iteration", "llb_s2m_get_profile", "llb_s2m_get_cta_profile",
     "llb_s2m_optimize_async", "llb_s2m_result",
     "llb_p2p_export", "llb_p2p_import", "llb_s2m_optimize_sharded",
-    "llb_map_set_raw_sharded", "llb_map_set_raw_sharded_dev", "llb_map_shard_info", "llb_map_shard_set_global",
+    "llb_map_set_raw_sharded", "llb_map_set_raw_sharded_dev", "llb_map_shard_info", "llb_map_shard_set_global", "llb_shard_plan",
     "llb_loop_params_default", "llb_loop_set_clouds", "llb_loop_set_clouds_host", "llb_loop_icp", "llb_loop_get_cloud",
     "llb_loop_get_nn", "llb_global_map_assemble",
     "llb_features_init", "llb_features_extract", "llb_features_get", "llb_features_get_state", "llb_features_to_odometry", "llb_features_get_profile", "llb_features_publish_last",
@@ -894,6 +894,16 @@ class Batch:
         names = ["unpack", "downsample", "index_build", "knn", "fit", "lm_step"]
         return dict(zip(names, [float(x) for x in ms])), {"knn_ctas_per_slot": geo[0], "fit_ctas_per_slot": geo[1],
                                                           "index_ctas_per_map": geo[2], "query_capacity": geo[3]}
+
+
+def shard_plan(sample_xyz, rank: int, world: int):
+    """llb_shard_plan: (axis, lo, hi) of the slab of `rank` from a sample of map points (pure host function)"""
+    a = np.ascontiguousarray(sample_xyz, np.float32).reshape(-1, 3)
+    ax = ctypes.c_int(0); lo = ctypes.c_float(0); hi = ctypes.c_float(0)
+    rc = lib().llb_shard_plan(_fp(a), a.shape[0], rank, world, ctypes.byref(ax), ctypes.byref(lo), ctypes.byref(hi))
+    if rc != 0:
+        raise LlbError(rc, "llb_shard_plan")
+    return ax.value, lo.value, hi.value
 
 
 def default_loop_params() -> "LoopParams":

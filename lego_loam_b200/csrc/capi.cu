@@ -987,6 +987,26 @@ int llb_s2m_optimize_sharded(llb_ctx *c, float T[6], llb_stats *stats)
 
 // ------------------------------------------------------------------ sharded local map (BASELINE config 4, shard.cuh)
 
+// pure host function: the slab of `rank` from a sample of map points (nsamp x {x, y, z}): axis = the longest extent of the
+// sample, borders = its quantiles; rank 0 / world - 1 are open towards -inf / +inf
+int llb_shard_plan(const float *sample_xyz, int nsamp, int rank, int world, int *axis_out, float *lo_out, float *hi_out)
+{
+    if (!sample_xyz || nsamp < 1 || world < 1 || rank < 0 || rank >= world || !axis_out || !lo_out || !hi_out) return (int)LLB_ERR_INVALID;
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int k = 0; k < nsamp; k++)
+        for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], sample_xyz[3 * k + a]); mx[a] = std::max(mx[a], sample_xyz[3 * k + a]); }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
+    std::vector<float> v((size_t)nsamp);
+    for (int k = 0; k < nsamp; k++) v[k] = sample_xyz[3 * k + axis];
+    // the two order statistics that border this rank's slab (the values a full sort would put there)
+    auto order_stat = [&](size_t k) { std::nth_element(v.begin(), v.begin() + k, v.end()); return v[k]; };
+    *axis_out = axis;
+    *lo_out = rank == 0 ? -FLT_MAX : order_stat((size_t)nsamp * rank / world);
+    *hi_out = rank == world - 1 ? FLT_MAX : order_stat((size_t)nsamp * (rank + 1) / world);
+    return (int)LLB_OK;
+}
+
 namespace {
 
 // the slab of this rank, from a deterministic sample of the raw surf map (every rank holds the same raw map and draws
@@ -996,23 +1016,14 @@ void plan_shard(llb_ctx *c, const float4 *corner, int rc, const float4 *surf, in
     ShardPlan pl; pl.rank = rank; pl.world = world;
     const float4 *src = rs > 0 ? surf : corner; const int n = rs > 0 ? rs : rc;
     if (world <= 1 || n <= 0) { pl.axis = 0; c->shard = pl; return; }
-    const int nsamp = std::min(n, 8192), stride = std::max(1, n / nsamp);
+    const int nsamp = std::min(n, 2048), stride = std::max(1, n / nsamp);
     c->shard_samp.ensure(3 * nsamp); c->shard_samp_pin.ensure(3 * nsamp);
     c->launches += launch_shard_sample(src, n, stride, nsamp, c->shard_samp.p, c->stream);
     LLB_CUDA(cudaMemcpyAsync(c->shard_samp_pin.p, c->shard_samp.p, sizeof(float) * 3 * nsamp, cudaMemcpyDeviceToHost, c->stream));
     LLB_CUDA(cudaStreamSynchronize(c->stream));
-    const float *sp = c->shard_samp_pin.p;
-    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (int k = 0; k < nsamp; k++)
-        for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], sp[3 * k + a]); mx[a] = std::max(mx[a], sp[3 * k + a]); }
-    int axis = 0;
-    for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
-    std::vector<float> v(nsamp);
-    for (int k = 0; k < nsamp; k++) v[k] = sp[3 * k + axis];
-    std::sort(v.begin(), v.end());
-    pl.axis = axis;
-    pl.lo = rank == 0 ? -FLT_MAX : v[(size_t)nsamp * rank / world];
-    pl.hi = rank == world - 1 ? FLT_MAX : v[(size_t)nsamp * (rank + 1) / world];
+    int axis = 0; float lo = 0.f, hi = 0.f;
+    llb_shard_plan(c->shard_samp_pin.p, nsamp, rank, world, &axis, &lo, &hi);
+    pl.axis = axis; pl.lo = lo; pl.hi = hi;
     c->shard = pl;
 }
 
@@ -1092,10 +1103,9 @@ int llb_map_shard_info(llb_ctx *c, llb_shard_info *out)
     return guarded(c, [&]() {
         if (!out) return (int)LLB_ERR_INVALID;
         if (c->shard.axis < 0) return (int)LLB_ERR_STATE;
-        const int dsn[2] = { read_count(c, llb_ctx::C_MAP_CORNER_DS), c->pin_counts.p[llb_ctx::C_MAP_SURF_DS] };
         int *h = c->pin_counts.p + llb_ctx::C_N;
         LLB_CUDA(cudaMemcpyAsync(h, c->shard_cnt.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
-        LLB_CUDA(cudaStreamSynchronize(c->stream));
+        const int dsn[2] = { read_count(c, llb_ctx::C_MAP_CORNER_DS), c->pin_counts.p[llb_ctx::C_MAP_SURF_DS] };   // (one sync)
         out->axis = c->shard.axis; out->lo = c->shard.lo; out->hi = c->shard.hi; out->rank = c->shard.rank; out->world = c->shard.world;
         for (int k = 0; k < 2; k++) { out->raw_kept[k] = h[k]; out->ds_local[k] = dsn[k]; out->ds_owned[k] = h[2 + k]; }
         return (int)LLB_OK;

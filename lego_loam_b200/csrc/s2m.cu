@@ -103,8 +103,13 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
         const long long p = Wt * b / G;
         return p < CW * ncl ? (int)(p / CW) : (int)(ncl + (p - CW * ncl));
     };
-    const int j0 = boundary(bx), j1 = boundary(bx + 1);
+    // sharded map (own_axis >= 0): a rank handles the queries inside its slab, which are neighbours in the sweep; CTA b
+    // therefore takes the INTERLEAVED queries b, b + G, b + 2G, ... so that every CTA sees the same share of owned ones
+    const bool slab = prm.own_axis >= 0;
+    const int j0 = slab ? 0 : boundary(bx), j1 = slab ? (nq > bx ? (nq - bx + G - 1) / G : 0) : boundary(bx + 1);
     const int cnt = j1 - j0;
+    const int q_base = slab ? bx : rank, q_stride = slab ? G : world;
+    auto query_of = [&](int j) -> int { return q_base + q_stride * j; };
 
     int ia, ib;
     pair_of(lane, ia, ib);
@@ -122,11 +127,11 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
         for (int t0 = 0; t0 < cnt; t0 += S2M_TILE) {
             const int tn = min(S2M_TILE, cnt - t0);
             // slots [0, ncs) of this tile are corner queries, [ncs, tn) surf queries
-            const int ncs = max(0, min(tn, ncl - (j0 + t0)));
+            const int ncs = slab ? 0 : max(0, min(tn, ncl - (j0 + t0)));
             // ---------------- phase A1: thread per query: transform + the 9 cell-run ranges (18 independent loads)
             if (tid < tn) {
                 const int s = tid;
-                const int qi = rank + world * (j0 + t0 + s);
+                const int qi = query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float4 po = is_corner ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
                 // pointAssociateToMap MO:513-527
@@ -158,12 +163,18 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             // (a thread-per-query walk, the throughput form of batch.cu, was measured here too: with one or two warps
             // per SM nothing hides its dependent loads - 70k cycles per tile instead of 14k)
             for (int s = w; s < tn; s += S2M_NW) {
-                const int qi = rank + world * (j0 + t0 + s);
+                const int qi = query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float sx = s_q[3][s], sy = s_q[4][s], sz = s_q[5][s];
                 int rbv[9], rev[9];
+                bool any = false;
 #pragma unroll
-                for (int r = 0; r < 9; r++) { rbv[r] = s_rb[r][s]; rev[r] = s_re[r][s]; }
+                for (int r = 0; r < 9; r++) { rbv[r] = s_rb[r][s]; rev[r] = s_re[r][s]; any |= rev[r] > rbv[r]; }
+                if (!any && !dbg.knn_idx) {                  // another rank's query, or empty space: no row (warp-uniform)
+                    if (lane < 15) s_nn[lane][s] = 0.f;
+                    if (lane == 15) s_q[6][s] = -1.f;
+                    continue;
+                }
 
                 int npos[5]; float nd[5]; int ni[5];
                 const MapIndexView &mv = is_corner ? cmap : smap;
@@ -188,7 +199,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             const int c32 = min(ncs, 32);                    // corner slots beyond 32 ride with the surf warps
             const int s = tid < 32 ? (tid < c32 ? tid : -1) : (c32 + tid - 32);
             if (s >= 0 && s < tn) {
-                const int qi = rank + world * (j0 + t0 + s);
+                const int qi = query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float d5 = s_q[6][s];
                 bool ok = (d5 >= 0.f) && ((double)d5 < (double)prm.knn_max_sqdist);    // MO:1101 / MO:1183

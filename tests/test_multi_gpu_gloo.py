@@ -80,3 +80,65 @@ def test_shard_partition_is_exact_cover():
         for world in (1, 2, 3, 8):
             allq = np.concatenate([multi_gpu.shard_queries(n, r, world) for r in range(world)])
             assert np.array_equal(np.sort(allq), np.arange(n))
+
+
+def _worker_slab(rank, world, port, q):
+    """host logic of the MAP-sharded form: every rank plans its slab from the same sample (llb_shard_plan: pure host
+    code of the C ABI), the slabs tile the axis, and the sizes of the unsharded maps come out of an all-reduce of the
+    owned counts (multi_gpu.set_sharded_map with a stand-in context: the device work needs a GPU)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lego_loam_b200 import api, multi_gpu
+    rng = np.random.default_rng(42)                                  # the same "raw map" on every rank
+    pts = (rng.normal(0, 1, (50000, 3)) * [40.0, 2.0, 15.0]).astype(np.float32)
+    sample = pts[::7]
+    axis, lo, hi = api.shard_plan(sample, rank, world)
+
+    class StandIn:                                                   # what a context reports after filtering its slab
+        device = 0
+        def map_set_raw_sharded(self, c, s, r, w): self.args = (r, w)
+        def map_shard_info(self):
+            info = api.ShardInfo(); info.axis = axis; info.lo = lo; info.hi = hi; info.rank = rank; info.world = world
+            own = int(np.sum((pts[:, axis] >= lo) & (pts[:, axis] < hi)))
+            info.ds_owned[0] = own; info.ds_owned[1] = 2 * own
+            return info
+        def map_shard_set_global(self, a, b): self.glob = (a, b)
+    ctx = StandIn()
+    info = multi_gpu.set_sharded_map(ctx, None, None, rank, world)
+    q.put((rank, axis, lo, hi, ctx.glob, ctx.args, int(info.ds_owned[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_map_sharded_host_logic_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_slab, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, ax0, lo0, hi0, g0, a0, o0), (r1, ax1, lo1, hi1, g1, a1, o1) = res
+    assert ax0 == ax1 == 0                                           # the longest extent of the sample
+    assert lo0 < -1e30 and hi1 > 1e30 and hi0 == lo1                 # the slabs tile the axis, open at both ends
+    assert g0 == g1 == (50000, 100000) and o0 + o1 == 50000          # all-reduced owned counts = the unsharded sizes
+    assert abs(o0 - o1) < 2500                                       # quantile borders: balanced slabs
+    assert a0 == (0, 2) and a1 == (1, 2)
+
+
+def test_shard_plan_tiles_the_axis():
+    from lego_loam_b200 import api
+    rng = np.random.default_rng(1)
+    sample = (rng.uniform(-1, 1, (4096, 3)) * [10.0, 3.0, 80.0]).astype(np.float32)
+    for world in (1, 2, 3, 4, 8):
+        plans = [api.shard_plan(sample, r, world) for r in range(world)]
+        assert all(p[0] == 2 for p in plans)
+        assert plans[0][1] < -1e30 and plans[-1][2] > 1e30
+        for a, b in zip(plans[:-1], plans[1:]):
+            assert a[2] == b[1] and a[1] < a[2]
+    with __import__("pytest").raises(api.LlbError):
+        api.shard_plan(sample, 2, 2)
