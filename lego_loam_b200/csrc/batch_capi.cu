@@ -318,11 +318,8 @@ int enqueue_step(llb_batch *c, const float *T)
                     AsmSeg sg{};
                     sg.ctRoll = cosf(p[0]); sg.stRoll = sinf(p[0]); sg.ctPitch = cosf(p[1]); sg.stPitch = sinf(p[1]);
                     sg.ctYaw = cosf(p[2]); sg.stYaw = sinf(p[2]); sg.tx = p[3]; sg.ty = p[4]; sg.tz = p[5];
-                    // the assembly also accumulates the bounds of the two raw maps for their voxel filters (getMinMax3D)
-                    sg.bounds = c->vox[2 * s].bounds_accumulator();
                     sg.src = kr.cloud[0]; sg.n = kr.n[0]; sg.dst = rawc + oc; oc += kr.n[0];
                     if (sg.n > 0) put(sg);
-                    sg.bounds = c->vox[2 * s + 1].bounds_accumulator();
                     sg.src = kr.cloud[1]; sg.n = kr.n[1]; sg.dst = raws + os; os += kr.n[1];
                     if (sg.n > 0) put(sg);
                     sg.src = kr.cloud[2]; sg.n = kr.n[2]; sg.dst = raws + os; os += kr.n[2];
@@ -333,8 +330,8 @@ int enqueue_step(llb_batch *c, const float *T)
             VoxelInput vc; vc.a = rawc; vc.na = (int)oc;
             VoxelInput vs; vs.a = raws; vs.na = (int)os;
             int *dn = c->ds_map_n.p + 2 * s;
-            h_vox[nvox] = c->vox[2 * s].large_job(vc, c->prm.corner_leaf, dsc, dn); h_vox[nvox++].bounds_ready = 1;
-            h_vox[nvox] = c->vox[2 * s + 1].large_job(vs, c->prm.surf_leaf, dss, dn + 1); h_vox[nvox++].bounds_ready = 1;
+            h_vox[nvox++] = c->vox[2 * s].large_job(vc, c->prm.corner_leaf, dsc, dn);
+            h_vox[nvox++] = c->vox[2 * s + 1].large_job(vs, c->prm.surf_leaf, dss, dn + 1);
             raw_max = std::max(raw_max, (int)std::max(oc, os));
             sl.map[0] = dsc; sl.map[1] = dss; sl.map_n[0] = (int)oc; sl.map_n[1] = (int)os;   // upper bounds
             sl.map_set = true; sl.map_dirty = true;
@@ -415,8 +412,7 @@ int enqueue_step(llb_batch *c, const float *T)
         }
         if (nvox > 0)
             nl += VoxelFilter::launch_large((const LargeVoxelJob *)(dp + L.off_vox), nvox,
-                                                     raw_max, c->stream, true);   // scratch is sized for cap_raw >= raw_max;
-                                                                                  // bounds: accumulated by the assembly above
+                                                     raw_max, c->stream);      // scratch is sized for cap_raw >= raw_max
         prof_mark(c, 0);
         if (ngrid > 0)
             nl += GridIndex::build_table((const GridJob *)(dp + L.off_grid), ngrid, map_n_max,

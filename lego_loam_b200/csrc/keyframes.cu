@@ -11,7 +11,6 @@ __global__ void __launch_bounds__(256)
 kf_assemble_kernel(const AsmSeg *__restrict__ segs)
 {
     const AsmSeg sg = segs[blockIdx.y];
-    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
         const float4 p = __ldg(&sg.src[i]);
         const float x1 = sg.ctYaw * p.x - sg.stYaw * p.y;
@@ -26,29 +25,6 @@ kf_assemble_kernel(const AsmSeg *__restrict__ segs)
         o.z = -sg.stPitch * x2 + sg.ctPitch * z2 + sg.tz;
         o.w = p.w;
         sg.dst[i] = o;
-        mn[0] = fminf(mn[0], o.x); mx[0] = fmaxf(mx[0], o.x);
-        mn[1] = fminf(mn[1], o.y); mx[1] = fmaxf(mx[1], o.y);
-        mn[2] = fminf(mn[2], o.z); mx[2] = fmaxf(mx[2], o.z);
-    }
-    if (!sg.bounds || (int)(blockIdx.x * blockDim.x) >= sg.n) return;     // uniform over the CTA
-    // getMinMax3D of the map's voxel filter (voxel_minmax_kernel), folded into this pass: CTA reduce, 6 atomics
-    __shared__ float s_red[6][256 / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], off));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], off));
-        }
-        if (lane == 0) { s_red[a][w] = mn[a]; s_red[3 + a][w] = mx[a]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        float m0 = s_red[threadIdx.x][0], m1 = s_red[3 + threadIdx.x][0];
-        for (int k = 1; k < 256 / 32; k++) { m0 = fminf(m0, s_red[threadIdx.x][k]); m1 = fmaxf(m1, s_red[3 + threadIdx.x][k]); }
-        atomicMin(&sg.bounds[threadIdx.x], float_to_ordered(m0));
-        atomicMax(&sg.bounds[3 + threadIdx.x], float_to_ordered(m1));
     }
 }
 

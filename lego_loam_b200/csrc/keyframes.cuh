@@ -13,8 +13,6 @@ namespace llb {
 struct AsmSeg {                       // one key-frame cloud -> its slice of an assembled raw map
     const float4 *src; float4 *dst; int n;
     float ctRoll, stRoll, ctPitch, stPitch, ctYaw, stYaw, tx, ty, tz;   // updateTransformPointCloudSinCos MO:529-543
-    int *bounds;                      // optional: ordered-int min[3] / max[3] of the map this slice belongs to (VoxelDesc::mn):
-                                      // the bounds pass of the map's voxel filter is folded into the assembly
 };
 
 struct KeyFrameRec { const float4 *cloud[3]; int n[3]; };               // corner, surf, outlier (DS clouds)

@@ -40,7 +40,6 @@ __global__ void __launch_bounds__(LG_THREADS)
 voxel_minmax_kernel(const LargeVoxelJob *__restrict__ table)
 {
     LG_JOB(table);
-    if (jb.bounds_ready) return;
     const SegIn in = jb.bounds; VoxelDesc *__restrict__ d = jb.desc;
     __shared__ float s_red[6][LG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -428,14 +427,14 @@ LargeVoxelJob VoxelFilter::large_job(const VoxelInput &in, float leaf, float4 *o
     const int n = std::max(in.upper(), 1);
     reserve(std::max(n, SMALL_MAX + 1));
     LargeVoxelJob j;
-    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in; j.bounds_ready = 0;
+    j.in = to_seg(in); j.leaf = leaf; j.desc = desc_.p; j.bounds = bounds ? to_seg(*bounds) : j.in;
     j.kA = keys_[0].p; j.kB = keys_[1].p; j.vA = vals_[0].p; j.vB = vals_[1].p;
     j.hist = hist_.p; j.blk = blk_.p; j.out = out; j.n_out = n_out_dev;
     return j;
 }
 
 // `count` jobs of a device-resident table; n_upper bounds the input length of every job
-int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s, bool bounds_ready)
+int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s)
 {
     const int n = std::max(n_upper, 1);
     // the histogram layout depends on the radix grid: it must be the same for sizing (reserve) and launching
@@ -445,8 +444,7 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     const int per = count > 1 ? std::max(8, 148 * 8 / count) : 148 * 8;
     const dim3 grid_stream(std::min(div_up(n, LG_THREADS), per), ny);
     int launches = 0;
-    // bounds_ready: every job of the table had its bounds accumulated by the kernel that produced its input
-    if (!bounds_ready) { voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++; }
+    voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     voxel_setup_kernel<<<dim3(1, ny), 1, 0, s>>>(table_dev); launches++;
     voxel_keys_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     for (int pass = 0; pass < 4; pass++) {

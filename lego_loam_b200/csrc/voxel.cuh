@@ -36,9 +36,7 @@ public:
     // batched form of the multi-kernel path: large_job() sizes this filter's scratch for the input's upper bound and
     // returns the job record; a device-resident table of such records is run by ONE set of 18 launches
     LargeVoxelJob large_job(const VoxelInput &in, float leaf, float4 *out, int *n_out_dev, const VoxelInput *bounds = nullptr);
-    static int launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s, bool bounds_ready = false);
-    // where a producer kernel may accumulate the bounds of this filter's next input (ordered-int min[3], max[3])
-    int *bounds_accumulator() { return reinterpret_cast<int *>(desc_.p); }   // VoxelDesc starts with mn[3], mx[3]
+    static int launch_large(const LargeVoxelJob *table_dev, int count, int n_upper, cudaStream_t s);
     // pre-sizes the scratch of the multi-kernel path for inputs of up to n points (no allocation at run time below n)
     void reserve(int n);
     // out must have room for in.upper() points; n_out_dev receives the output count.

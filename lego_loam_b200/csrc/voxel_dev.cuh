@@ -20,7 +20,6 @@ struct LargeVoxelJob {       // one filter of the multi-kernel (radix) path: inp
     SegIn in; float leaf; VoxelDesc *desc;
     SegIn bounds;            // the cloud whose min / max define the lattice: `in` itself, or - sharded maps - the WHOLE raw
                              // map of which `in` is this rank's part, so that every rank numbers the voxels alike
-    int bounds_ready;        // the producer of `in` already accumulated the bounds into desc->mn / mx (kf_assemble_kernel)
     unsigned *kA, *kB; int *vA, *vB; int *hist; int *blk;
     float4 *out; int *n_out;
 };

@@ -39,7 +39,7 @@ def _rows_index(G):
     return {G[i].tobytes(): i for i in range(G.shape[0])}
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_map_virtual_ranks(world):
     """Config 4 with the MAP sharded, checked on ONE device: `world` contexts play the ranks.  Each keeps a slab of the raw
     map; its DS map must be a sub-sequence of the unsharded DS map (same bits, same order), the owned centroids must
