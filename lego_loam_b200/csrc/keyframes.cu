@@ -1,5 +1,6 @@
 // keyframes.cu — key-frame arena + the fused transformPointCloud / concatenation kernel (see keyframes.cuh).
 #include "keyframes.cuh"
+#include <cstdlib>
 
 namespace llb {
 
@@ -33,7 +34,9 @@ kf_assemble_kernel(const AsmSeg *__restrict__ segs)
 void launch_kf_assemble(const AsmSeg *segs_dev, int count, int n_max, cudaStream_t s)
 {
     if (count <= 0) return;
-    const dim3 grid(std::max(1, std::min(div_up(std::max(n_max, 1), 256), 32)), count);
+    // points per CTA: a key-frame cloud has ~1-4k points and a table thousands of segments; fewer, fuller CTAs
+    static const int per_cta = getenv("LLB_ASM_PTS_PER_CTA") ? std::max(256, atoi(getenv("LLB_ASM_PTS_PER_CTA"))) : 1024;
+    const dim3 grid(std::max(1, std::min(div_up(std::max(n_max, 1), per_cta), 32)), count);
     kf_assemble_kernel<<<grid, 256, 0, s>>>(segs_dev);
     LLB_CUDA(cudaGetLastError());
 }

@@ -41,7 +41,8 @@ constexpr int S2M_THREADS = 512;
 constexpr int S2M_CTAS_PER_SM = 1;
 constexpr int S2M_NW = S2M_THREADS / 32;
 constexpr int S2M_TILE = 64;             // queries a CTA stages per pass
-constexpr int S2M_QPB = S2M_NW;          // target queries per CTA when sizing the grid (one per warp)
+constexpr int S2M_QPB = S2M_NW;
+constexpr int S2M_LIST_CAP = 1024;       // candidates listed per pass in the sharded-map mode          // target queries per CTA when sizing the grid (one per warp)
 
 
 struct PoseArg { float T[6]; };
@@ -84,6 +85,8 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
     __shared__ unsigned long long s_wkey[S2M_NW][KNN_CAP];    // per-warp in-gate candidate lists (phase A)
     __shared__ int s_wpos[S2M_NW][KNN_CAP];
     __shared__ int s_rb[9][S2M_TILE], s_re[9][S2M_TILE];      // cell-run ranges per query (phase A1 -> A2)
+    __shared__ int s_list[S2M_LIST_CAP];                      // sharded map: this CTA's queries inside the slab
+    __shared__ int s_scan[33];
 
     if (__ldcg(&st->skipped)) return;                         // uniform over the grid (guard MO:1331)
 
@@ -124,14 +127,41 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
         const long long t_start = clock64();
         if (prof) st->prof[iter % 10][0] = t_start;
 
-        for (int t0 = 0; t0 < cnt; t0 += S2M_TILE) {
-            const int tn = min(S2M_TILE, cnt - t0);
+        // sharded map: the CTA first lists the queries of its share that lie inside this rank's slab at the current pose
+        // (order kept), S2M_LIST_CAP candidates at a time, and the tiles below run over that list only - a CTA of a
+        // 1/N slab stages 1/N of the tiles instead of mostly-empty ones
+        for (int c0 = 0; c0 < cnt; c0 += (slab ? S2M_LIST_CAP : cnt)) {
+        int cnt_eff = cnt;
+        if (slab) {
+            const int c1 = min(cnt, c0 + S2M_LIST_CAP);
+            int nl = 0;
+            for (int base = c0; base < c1; base += S2M_THREADS) {
+                const int j = base + tid;
+                int own = 0, qi = 0;
+                if (j < c1) {
+                    qi = query_of(j);
+                    const float4 po = qi < nc ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
+                    float sx, sy, sz;
+                    associate_to_map(crx, srx, cry, sry, crz, srz, tX, tY, tZ, po, sx, sy, sz);
+                    const float oc = prm.own_axis == 0 ? sx : (prm.own_axis == 1 ? sy : sz);
+                    own = (oc >= prm.own_lo && oc < prm.own_hi) ? 1 : 0;
+                }
+                int total;
+                const int pos = nl + block_excl_scan(own, s_scan, total);
+                if (own) s_list[pos] = qi;
+                nl += total;
+            }
+            __syncthreads();
+            cnt_eff = nl;
+        }
+        for (int t0 = 0; t0 < cnt_eff; t0 += S2M_TILE) {
+            const int tn = min(S2M_TILE, cnt_eff - t0);
             // slots [0, ncs) of this tile are corner queries, [ncs, tn) surf queries
             const int ncs = slab ? 0 : max(0, min(tn, ncl - (j0 + t0)));
             // ---------------- phase A1: thread per query: transform + the 9 cell-run ranges (18 independent loads)
             if (tid < tn) {
                 const int s = tid;
-                const int qi = query_of(j0 + t0 + s);
+                const int qi = slab ? s_list[t0 + s] : query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float4 po = is_corner ? __ldg(&q.corner[qi]) : __ldg(&q.surf[qi - nc]);
                 // pointAssociateToMap MO:513-527
@@ -163,7 +193,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             // (a thread-per-query walk, the throughput form of batch.cu, was measured here too: with one or two warps
             // per SM nothing hides its dependent loads - 70k cycles per tile instead of 14k)
             for (int s = w; s < tn; s += S2M_NW) {
-                const int qi = query_of(j0 + t0 + s);
+                const int qi = slab ? s_list[t0 + s] : query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float sx = s_q[3][s], sy = s_q[4][s], sz = s_q[5][s];
                 int rbv[9], rev[9];
@@ -199,7 +229,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             const int c32 = min(ncs, 32);                    // corner slots beyond 32 ride with the surf warps
             const int s = tid < 32 ? (tid < c32 ? tid : -1) : (c32 + tid - 32);
             if (s >= 0 && s < tn) {
-                const int qi = query_of(j0 + t0 + s);
+                const int qi = slab ? s_list[t0 + s] : query_of(j0 + t0 + s);
                 const bool is_corner = qi < nc;
                 const float d5 = s_q[6][s];
                 bool ok = (d5 >= 0.f) && ((double)d5 < (double)prm.knn_max_sqdist);    // MO:1101 / MO:1183
@@ -228,6 +258,7 @@ s2m_loop_kernel(S2mParams prm, int it_begin, int it_end, S2mQueries q, MapIndexV
             __syncthreads();
             if (tid == 0) pc = clock64();
         }
+        }   // candidates c0 ..
         if (prof) { st->prof[iter % 10][1] = pa; st->prof[iter % 10][2] = pb; st->prof[iter % 10][3] = pc; }
 
         // ---- CTA partial (fixed order over warps)

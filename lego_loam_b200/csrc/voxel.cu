@@ -90,24 +90,6 @@ __global__ void voxel_setup_kernel(const LargeVoxelJob *__restrict__ table)
     d->overflow = ovf; d->nbits = nb;
 }
 
-__global__ void __launch_bounds__(LG_THREADS)
-voxel_keys_kernel(const LargeVoxelJob *__restrict__ table)
-{
-    LG_JOB(table);
-    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc;
-    unsigned *__restrict__ keys = jb.kA; int *__restrict__ vals = jb.vA;
-    const int n = d->n;
-    const int na = seg_len_a(in);
-    const float inv = d->inv;
-    const int min_b[3] = { d->min_b[0], d->min_b[1], d->min_b[2] }, mul[3] = { d->mul[0], d->mul[1], d->mul[2] };
-    const int ovf = d->overflow;
-    for (int i = blockIdx.x * LG_THREADS + threadIdx.x; i < n; i += gridDim.x * LG_THREADS) {
-        float4 p = seg_load(in, na, i);
-        keys[i] = ovf ? (unsigned)i : voxel_key(p, inv, min_b, mul);
-        vals[i] = i;
-    }
-}
-
 // --- stable LSD radix sort, one 8-bit digit per pass.  Tile layout is a pure function of
 // (n, gridDim) so the histogram and scatter kernels agree.
 __device__ __forceinline__ void radix_tile(int n, int nblocks, int b, int &lo, int &hi)
@@ -117,6 +99,35 @@ __device__ __forceinline__ void radix_tile(int n, int nblocks, int b, int &lo, i
     long long l = (long long)b * tile;
     lo = (int)(l < n ? l : n);
     hi = (int)(l + tile < n ? l + tile : n);
+}
+
+// voxel keys of the points + the per-block histogram of the FIRST radix digit (same tile layout as the radix kernels: the
+// first pass needs no histogram launch).  The sort carries (key, input index) pairs; the index list of the first pass is
+// the identity and is never written: radix_scatter_kernel takes val = position when shift == 0.
+__global__ void __launch_bounds__(LG_THREADS)
+voxel_keys_kernel(const LargeVoxelJob *__restrict__ table)
+{
+    LG_JOB(table);
+    const SegIn in = jb.in; const VoxelDesc *__restrict__ d = jb.desc;
+    unsigned *__restrict__ keys = jb.kA; int *__restrict__ hist = jb.hist;
+    const int n = d->n;
+    const int na = seg_len_a(in);
+    const float inv = d->inv;
+    const int min_b[3] = { d->min_b[0], d->min_b[1], d->min_b[2] }, mul[3] = { d->mul[0], d->mul[1], d->mul[2] };
+    const int ovf = d->overflow;
+    __shared__ int s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    int lo, hi;
+    radix_tile(n, gridDim.x, blockIdx.x, lo, hi);
+    for (int i = lo + threadIdx.x; i < hi; i += LG_THREADS) {
+        float4 p = seg_load(in, na, i);
+        const unsigned key = ovf ? (unsigned)i : voxel_key(p, inv, min_b, mul);
+        keys[i] = key;
+        atomicAdd(&s_h[key & 255u], 1);
+    }
+    __syncthreads();
+    hist[threadIdx.x * gridDim.x + blockIdx.x] = s_h[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(LG_THREADS)
@@ -196,7 +207,7 @@ radix_scatter_kernel(const LargeVoxelJob *__restrict__ table, int shift)
             const int i = sub + w * (32 * ITEMS) + r * 32 + lane;
             const bool valid = i < hi;
             key[r] = valid ? kin[i] : 0u;
-            val[r] = valid ? vin[i] : 0;
+            val[r] = valid ? (shift == 0 ? i : vin[i]) : 0;                 // first pass: the index list is the identity
             dg[r] = valid ? ((key[r] >> shift) & 255u) : (256u + lane);    // invalid lanes never match
         }
 #pragma unroll
@@ -446,13 +457,13 @@ int VoxelFilter::launch_large(const LargeVoxelJob *table_dev, int count, int n_u
     int launches = 0;
     voxel_minmax_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
     voxel_setup_kernel<<<dim3(1, ny), 1, 0, s>>>(table_dev); launches++;
-    voxel_keys_kernel<<<grid_stream, LG_THREADS, 0, s>>>(table_dev); launches++;
+    voxel_keys_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev); launches++;     // + histogram of pass 0
     for (int pass = 0; pass < 4; pass++) {
         const int shift = pass * 8;
-        radix_hist_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
+        if (pass > 0) { radix_hist_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift); launches++; }
         scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 0, 256 * nblk_radix, shift);
         radix_scatter_kernel<<<dim3(nblk_radix, ny), LG_THREADS, 0, s>>>(table_dev, shift);
-        launches += 3;
+        launches += 2;
     }
     voxel_heads_kernel<<<dim3(div_up(nblk_head, HEAD_GROUP), ny), HEAD_THREADS, 0, s>>>(table_dev, nblk_head); launches++;
     scan_single_block_kernel<<<dim3(1, ny), 1024, 0, s>>>(table_dev, 1, nblk_head, -1); launches++;
