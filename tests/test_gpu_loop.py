@@ -113,3 +113,37 @@ def test_icp_guards_and_known_motion():
     with pytest.raises(api.LlbError):
         fresh.loop_icp()
     fresh.close(); ctx.close()
+
+
+def test_loop_argument_errors_and_empty_selection():
+    ctx = api.Context(0)
+    pose = np.zeros(6, np.float32)
+    with pytest.raises(api.LlbError) as e:
+        ctx.loop_set_clouds(0, pose, [0], [pose])             # empty key-frame store: id 0 does not exist
+    assert e.value.status == api.LLB_ERR_INVALID
+    rng = np.random.default_rng(1)
+    cl = [np.concatenate([rng.uniform(-5, 5, (n, 3)), rng.uniform(0, 15, (n, 1))], 1).astype(np.float32) for n in (300, 900, 500)]
+    assert ctx.keyframe_add_clouds(*cl) == 0
+    with pytest.raises(api.LlbError):
+        ctx.loop_set_clouds(0, pose, [0, 1], [pose, pose])    # id 1 does not exist
+    with pytest.raises(api.LlbError):
+        ctx.global_map_assemble([0], [pose], leaf=0.0)
+    assert ctx.global_map_assemble([], np.zeros((0, 6), np.float32)) == 0 and ctx.loop_get_cloud(3).shape[0] == 0
+    # one key-frame at the identity pose: the global map is the voxel filter of its three clouds, the latest cloud is
+    # corner + surf, the history cloud its VoxelGrid(0.4)
+    n = ctx.global_map_assemble([0], [pose])
+    want, _ = oracle.voxel_grid(np.concatenate(cl), 0.4)
+    assert n == want.shape[0] and np.array_equal(ctx.loop_get_cloud(3).view(np.uint32), want.view(np.uint32))
+    n_src, n_hist = ctx.loop_set_clouds(0, pose, [0], [pose])
+    assert n_src == 1200 and np.array_equal(ctx.loop_get_cloud(0).view(np.uint32), np.concatenate(cl[:2]).view(np.uint32))
+    want_h, _ = oracle.voxel_grid(np.concatenate(cl[:2]), 0.4)
+    assert n_hist == want_h.shape[0] and np.array_equal(ctx.loop_get_cloud(2).view(np.uint32), want_h.view(np.uint32))
+    # a negative intensity is dropped from the latest cloud (MO:845-849)
+    cl2 = [c.copy() for c in cl]; cl2[0][5, 3] = -2.0; cl2[1][7, 3] = -1.0
+    assert ctx.keyframe_add_clouds(*cl2) == 1
+    n_src, _ = ctx.loop_set_clouds(1, pose, [0], [pose])
+    keep = np.concatenate(cl2[:2]); keep = keep[keep[:, 3].astype(np.int32) >= 0]
+    assert n_src == 1198 and np.array_equal(ctx.loop_get_cloud(0).view(np.uint32), keep.view(np.uint32))
+    r = ctx.loop_icp()
+    assert r.has_converged == 1 and r.n_source == 1198
+    ctx.close()

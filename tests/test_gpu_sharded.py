@@ -108,3 +108,37 @@ def test_sharded_map_virtual_ranks(world):
     for ctx in ranks:
         ctx.close()
     ref.close()
+
+
+def test_sharded_map_edge_cases():
+    """world = 1: the slab is everything, the DS maps are the unsharded ones bit for bit; argument and call-order errors."""
+    import numpy as np
+    from lego_loam_b200 import api
+    from tests import data
+    c = data.mapping_case(seed=2, n_corner_raw=20000, n_surf_raw=90000)
+    ref = api.Context(0)
+    ref.map_set_raw(c["map_corner_raw"], c["map_surf_raw"])
+    one = api.Context(0)
+    with pytest.raises(api.LlbError) as e:
+        one.map_shard_info()                                  # no sharded map yet
+    assert e.value.status == api.LLB_ERR_STATE
+    one.map_set_raw_sharded(c["map_corner_raw"], c["map_surf_raw"], 0, 1)
+    info = one.map_shard_info()
+    assert info.world == 1 and info.lo < -1e30 and info.hi > 1e30
+    for k in range(2):
+        G, L = ref.map_get_ds(k), one.map_get_ds(k)
+        assert np.array_equal(G.view(np.uint32), L.view(np.uint32)) and info.ds_owned[k] == G.shape[0] == info.ds_local[k]
+    for rank, world in ((2, 2), (-1, 2), (0, 0), (0, 9)):
+        with pytest.raises(api.LlbError) as e:
+            one.map_set_raw_sharded(c["map_corner_raw"], c["map_surf_raw"], rank, world)
+        assert e.value.status == api.LLB_ERR_INVALID
+    # an unsharded setter ends the sharded mode
+    one.map_set_raw(c["map_corner_raw"], c["map_surf_raw"])
+    with pytest.raises(api.LlbError):
+        one.map_shard_info()
+    # empty raw maps: nothing to own, nothing crashes
+    z = np.zeros((0, 4), np.float32)
+    one.map_set_raw_sharded(z, z, 1, 2)
+    info = one.map_shard_info()
+    assert info.ds_owned[0] == 0 and info.ds_owned[1] == 0 and info.raw_kept[0] == 0
+    one.close(); ref.close()
