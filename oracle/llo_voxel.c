@@ -23,11 +23,23 @@
 
 typedef struct { int32_t idx; int32_t pt; } vox_pair;
 
-static int vox_cmp(const void *a, const void *b)
+/* (idx, input index) ascending = a STABLE sort by idx: LSD radix sort, 11-bit digits over the significant bits.
+ * PCL sorts with std::sort (inlined comparator); a qsort with a function-pointer comparator was ~2x slower than that and
+ * made the CPU baseline of the mapping cycle pessimistic (round-1 review) - the radix sort errs on the CPU's side. */
+static void vox_sort(vox_pair *v, int n, int32_t max_idx)
 {
-    const vox_pair *p = (const vox_pair *)a, *q = (const vox_pair *)b;
-    if (p->idx != q->idx) return p->idx < q->idx ? -1 : 1;
-    return p->pt < q->pt ? -1 : (p->pt > q->pt);   /* stable by input index */
+    vox_pair *tmp = (vox_pair *)malloc(sizeof(vox_pair) * (size_t)n);
+    vox_pair *src = v, *dst = tmp;
+    for (int shift = 0; shift < 32 && ((int64_t)max_idx >> shift) != 0; shift += 11) {
+        int cnt[2049];
+        memset(cnt, 0, sizeof(cnt));
+        for (int i = 0; i < n; i++) cnt[(((uint32_t)src[i].idx >> shift) & 2047u) + 1]++;
+        for (int k = 0; k < 2048; k++) cnt[k + 1] += cnt[k];
+        for (int i = 0; i < n; i++) dst[cnt[((uint32_t)src[i].idx >> shift) & 2047u]++] = src[i];
+        vox_pair *t = src; src = dst; dst = t;
+    }
+    if (src != v) memcpy(v, src, sizeof(vox_pair) * (size_t)n);
+    free(tmp);
 }
 
 int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *overflow)
@@ -67,7 +79,7 @@ int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *
         v[i].idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
         v[i].pt = i;
     }
-    qsort(v, (size_t)n, sizeof(vox_pair), vox_cmp);
+    vox_sort(v, n, (int32_t)((int64_t)div_b[0] * div_b[1] * div_b[2] - 1));
 
     int m = 0, i = 0;
     while (i < n) {
