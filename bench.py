@@ -688,7 +688,7 @@ def main():
     ap.add_argument("--workload", default="vlp16_100k", choices=sorted(WORKLOADS))
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences registered per step per GPU")
     ap.add_argument("--batches", type=int, default=2, help="batch objects (streams) the sequences are split over")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences generated per GPU (slots beyond reuse them with their own initial guesses)")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic sequences generated per GPU (slots beyond reuse them with their own initial guesses)")
     ap.add_argument("--scans", type=int, default=8, help="distinct new sweeps per sequence rotated through the steps")
     ap.add_argument("--cpu-sample", type=int, default=8, help="registrations timed for cpu_baseline")
     ap.add_argument("--key-frames", type=int, default=100, help="resident key-frames the local map of a sequence is assembled from")

@@ -8,6 +8,7 @@ mapOptimization for >= 200 sweeps, twice over the same synthetic drive:
 Bars of the north star: per-scan pose within 1e-4 m / 1e-4 rad, accumulated drift within 0.1 % of the path."""
 import json
 import os
+import time
 
 import numpy as np
 import pytest
@@ -46,6 +47,7 @@ class Mapping:
 
     def __init__(self, ctx):
         self.mo = rh.MapOptimization(); self.ctx = ctx; self.t_last = -1.0; self.traj = []; self.used = 0; self.ds_equal = True
+        self.lat_ms = []                                                  # device arm: wall clock of the registration calls
 
     def feed(self, stamp, transform_sum, corner, surf, outlier):
         if stamp - self.t_last < MAPPING_INTERVAL:                    # MO:1499
@@ -65,9 +67,11 @@ class Mapping:
                 ctx.map_set_raw(mo.map_raw(0), mo.map_raw(1))
                 self.ds_equal &= np.array_equal(ctx.map_get_ds(0).view(np.uint32), mo.map_ds(0).view(np.uint32))
                 self.ds_equal &= np.array_equal(ctx.map_get_ds(1).view(np.uint32), mo.map_ds(1).view(np.uint32))
+                t0 = time.perf_counter()
                 ctx.scan_set(corner, surf, outlier)
                 ctx.downsample_current_scan()
                 T, _ = ctx.s2m_optimize(mo.transformTobeMapped)
+                self.lat_ms.append((time.perf_counter() - t0) * 1e3)  # host sweep clouds in -> pose out (DS map resident)
                 mo.transformTobeMapped = T
                 mo.transformUpdate()
                 self.used += 1
@@ -103,8 +107,10 @@ def run_device(sweeps):
     odo = []
     frame = 1
     T = np.zeros(6, np.float32)
+    fa_ms = []                                                         # per sweep: raw sweep in -> odometry pose out + last clouds
     try:
         for k, (cloud, ring) in enumerate(sweeps):
+            t0 = time.perf_counter()
             fctx.projection_process(cloud, ring)
             fctx.projection_to_features()
             if k == 0:
@@ -115,6 +121,8 @@ def run_device(sweeps):
             T, _, _ = fctx.odom_optimize(T)                            # transformCur carries over as the initial guess
             book.transformCur = T; book.integrateTransformation()
             fctx.features_publish_last(T)
+            fctx.synchronize()
+            fa_ms.append((time.perf_counter() - t0) * 1e3)
             odo.append(book.transformSum.copy())
             frame += 1
             if frame >= 2:
@@ -123,14 +131,14 @@ def run_device(sweeps):
                         adjust_outlier(fctx.projection_get_cloud(1)))
     finally:
         fctx.close(); mctx.close()
-    return np.array(odo), np.array(mp.traj), mp.mo.num_keyframes(), mp.used, mp.ds_equal
+    return np.array(odo), np.array(mp.traj), mp.mo.num_keyframes(), mp.used, mp.ds_equal, np.array(fa_ms), np.array(mp.lat_ms)
 
 
 def test_full_pipeline_replay_200_sweeps():
     n = int(os.environ.get("LLB_PIPELINE_SWEEPS", "200"))
     poses, sweeps = make_drive(n)
     odo_ref, map_ref, kf_ref = run_reference(sweeps)
-    odo_gpu, map_gpu, kf_gpu, used, ds_equal = run_device(sweeps)
+    odo_gpu, map_gpu, kf_gpu, used, ds_equal, fa_ms, reg_ms = run_device(sweeps)
     assert odo_ref.shape == odo_gpu.shape == (n, 6) and map_ref.shape == map_gpu.shape and map_ref.shape[0] >= n // 4 - 2
     assert used >= map_ref.shape[0] - 2 and kf_ref == kf_gpu and ds_equal
     d_odo = np.abs(odo_gpu - odo_ref); d_map = np.abs(map_gpu - map_ref)
@@ -142,6 +150,12 @@ def test_full_pipeline_replay_200_sweeps():
            "mapping_max_abs_trans_diff_m": float(d_map[:, 3:].max()), "drift_vs_reference_over_path": drift,
            "odometry_sweeps_bit_identical": int(np.sum(np.all(odo_gpu.view(np.uint32) == odo_ref.view(np.uint32), axis=1))),
            "mapping_poses_bit_identical": int(np.sum(np.all(map_gpu.view(np.uint32) == map_ref.view(np.uint32), axis=1))),
+           "latency_ms_per_sweep_front_end_and_odometry": {"p50": float(np.percentile(fa_ms, 50)), "p99": float(np.percentile(fa_ms, 99)),
+                                                           "max": float(fa_ms.max()), "what": "raw sweep (host) in -> projection, features, "
+                                                           "updateTransformation, publishCloudsLast on the device -> pose, wall clock"},
+           "latency_ms_per_mapping_registration": {"p50": float(np.percentile(reg_ms, 50)), "p99": float(np.percentile(reg_ms, 99)),
+                                                   "max": float(reg_ms.max()), "what": "host sweep clouds in -> downsampleCurrentScan + "
+                                                   "scan2MapOptimization -> pose, wall clock (local map already voxel-filtered + indexed)"},
            "distance_from_start_m": {"truth": truth, "device": float(np.linalg.norm(map_gpu[-1, 3:])),
                                      "reference": float(np.linalg.norm(map_ref[-1, 3:]))}}
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
