@@ -118,7 +118,7 @@ public:
     int closestHistoryFrameID = -1, latestFrameIDLoopCloure = -1;
     llb_icp_result last_icp{};
     // cloud part of detectLoopClosure MO:838-861 once the caller has found closestHistoryFrameID (MO:822-837):
-    // poses6d(i) must return cloudKeyPoses6D[i] as {roll, pitch, yaw, x, y, z}; historyKeyframeSearchNum = 25 (UT:133)
+    // poses6d(i, out) must fill out[6] with cloudKeyPoses6D[i] as {roll, pitch, yaw, x, y, z}; historyKeyframeSearchNum = 25 (UT:133)
     template <typename PoseOf>
     bool detectLoopClosureClouds(int closest_id, int latest_id, PoseOf poses6d, int history_num = 25, bool fetch = false)
     {
@@ -127,10 +127,11 @@ public:
         for (int j = -history_num; j <= history_num; ++j) {                         // MO:853-855
             if (closest_id + j < 0 || closest_id + j > latest_id) continue;
             ids.push_back(closest_id + j);
-            const float *p = poses6d(closest_id + j); hp.insert(hp.end(), p, p + 6);
+            float p[6]; poses6d(closest_id + j, p); hp.insert(hp.end(), p, p + 6);
         }
         int counts[2] = { 0, 0 };
-        last_status = llb_loop_set_clouds(ctx_, latest_id, poses6d(latest_id), ids.data(), hp.data(), (int)ids.size(), 0.4f, counts);
+        float lp[6]; poses6d(latest_id, lp);
+        last_status = llb_loop_set_clouds(ctx_, latest_id, lp, ids.data(), hp.data(), (int)ids.size(), 0.4f, counts);
         if (last_status != LLB_OK) return false;
         if (fetch) {
             fetch_cloud(&llb_loop_get_cloud, 0, *latestSurfKeyFrameCloud);

@@ -146,5 +146,11 @@ int main(int argc, char **argv)
     printf("LC %d %d %d %d %.17g", MO.last_status, (int)closed, MO.last_icp.iterations, MO.last_icp.convergence_state, MO.last_icp.fitness_score);
     for (int k = 0; k < 16; k++) printf(" %.9g", MO.last_icp.T[k]);
     printf("\n");
+    // the device key-frame store behind the adapter: one key-frame, loop clouds from it (compiles the member template)
+    MO.fetch_downsampled_clouds = false;
+    MO.downsampleCurrentScan();
+    const int kf = MO.saveKeyFrameClouds();
+    const bool lc_ok = MO.detectLoopClosureClouds(kf, kf, [](int, float out[6]) { for (int k = 0; k < 6; k++) out[k] = 0.f; }, 25, true);
+    printf("LK %d %d %zu %zu\n", kf, (int)lc_ok, MO.latestSurfKeyFrameCloud->size(), MO.nearHistorySurfKeyFrameCloudDS->size());
     return 0;
 }

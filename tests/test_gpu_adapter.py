@@ -165,3 +165,6 @@ def test_adapter_matches_oracle(tmp_path):
     assert int(lc[1]) == 0 and int(lc[2]) == 1 and int(lc[3]) == want_lc["iterations"] and int(lc[4]) == want_lc["state"]
     assert abs(float(lc[5]) - want_lc["fitness"]) < 1e-9
     assert np.abs(np.array(lc[6:22], np.float32).reshape(4, 4) - want_lc["T"]).max() < 1e-6
+    # loop clouds from the adapter's device key-frame store: the latest cloud is cornerDS + surfDS of the sweep
+    lk = [l for l in out if l.startswith("LK ")][0].split()
+    assert int(lk[1]) == 0 and int(lk[2]) == 1 and int(lk[3]) == int(mo_line[1]) + int(mo_line[2]) and 0 < int(lk[4]) <= int(lk[3])
