@@ -147,3 +147,20 @@ def test_loop_argument_errors_and_empty_selection():
     r = ctx.loop_icp()
     assert r.has_converged == 1 and r.n_source == 1198
     ctx.close()
+
+
+def test_icp_against_committed_golden_vectors():
+    """tests/golden/ref_loop_golden.npz: the clouds of the reference's own detectLoopClosure and the alignment its
+    performLoopClosure ran (restated PCL behind the shim) - available on the GPU box without /root/reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loop_golden.npz"))
+    ctx = api.Context(0)
+    ctx.loop_set_clouds_host(g["source"], g["target_ds"])
+    r = ctx.loop_icp()
+    assert r.has_converged == int(g["converged"]) and r.iterations == int(g["iterations"]) and r.convergence_state == int(g["state"])
+    assert np.abs(np.array(r.T, np.float32).reshape(4, 4) - g["T"]).max() < 1e-4
+    assert abs(r.fitness_score - float(g["fitness"])) < 1e-4 * float(g["fitness"])
+    p1 = api.default_loop_params(); p1.max_iterations = 1
+    r1 = ctx.loop_icp(p1)
+    assert r1.n_correspondences == int(g["first_step_n"]) and np.abs(np.array(r1.T, np.float32).reshape(4, 4) - g["first_step_Rt"]).max() < 2e-7
+    ctx.close()

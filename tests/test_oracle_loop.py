@@ -81,3 +81,21 @@ def test_reference_global_map():
     assert ids.shape[0] >= 10 and len(set(ids.tolist())) == ids.shape[0]
     g = mo.loop_cloud(3)
     assert g.shape[0] > 5000
+
+
+def test_restated_icp_against_committed_golden_vectors():
+    """tests/golden/ref_loop_golden.npz (made by tests/golden/make_loop_golden.py from oracle/_ref): the clouds the
+    unmodified detectLoopClosure built and the alignment performLoopClosure ran.  Pins the restatement against
+    regressions on machines without /root/reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loop_golden.npz"))
+    src, tgt = g["source"], g["target_ds"]
+    st = oracle.icp_step(src, tgt)
+    assert st["n"] == int(g["first_step_n"]) and np.array_equal(st["nn"], g["first_step_nn"])
+    assert np.array_equal(st["Rt"], g["first_step_Rt"]) and st["mse"] == float(g["first_step_mse"])
+    r = oracle.icp_align(src, tgt)
+    assert r["iterations"] == int(g["iterations"]) and r["state"] == int(g["state"]) and r["converged"] == bool(g["converged"])
+    assert np.array_equal(r["T"], g["T"]) and r["fitness"] == float(g["fitness"])
+    # exact 1-NN of the first pass against the brute-force definition
+    nn = oracle.knn_bruteforce(tgt, src, 1)[0][:, 0]
+    assert np.array_equal(st["nn"], nn)
