@@ -331,7 +331,8 @@ int llb_s2m_optimize_sharded(llb_ctx *ctx, float T[6], llb_stats *stats);
  * llb_s2m_accumulate(rank 0, world 1) then take the queries whose mapped position lies inside the slab; the exchange
  * per LM iteration stays the 28 fp64 sums.  The guard MO:1331 needs the sizes of the UNSHARDED DS maps: all-reduce
  * llb_shard_info.ds_owned over the ranks (plumbing) and hand the sums to llb_map_shard_set_global; without that call
- * the guard looks at this rank's part. */
+ * the guard looks at this rank's part.  While a context holds a slab (world > 1) the single-rank entry points
+ * llb_s2m_optimize / _async / _dev / llb_s2m_iterate return LLB_ERR_STATE: they would see this rank's queries only. */
 typedef struct {
     int axis; float lo, hi;                 /* this rank owns mapped coordinates lo <= p[axis] < hi */
     int rank, world;

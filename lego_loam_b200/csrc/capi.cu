@@ -337,6 +337,18 @@ void downsample_scan(llb_ctx *c)
     c->scan_ds_done = true;
 }
 
+// a context that holds one rank's SLAB of a sharded map sees only its own queries: the single-rank entry points would
+// silently return a partial solution, so they refuse; llb_s2m_optimize_sharded / llb_s2m_accumulate + llb_s2m_solve go on
+bool holds_slab(llb_ctx *c)
+{
+    if (c->shard.axis >= 0 && c->shard.world > 1) {
+        c->err = "this context holds one rank's slab of a sharded map: use llb_s2m_optimize_sharded (or llb_s2m_accumulate / "
+                 "llb_s2m_solve with an all-reduce)";
+        return true;
+    }
+    return false;
+}
+
 void fill_stats(llb_ctx *c, llb_stats *st, const S2mState &s, float ms)
 {
     if (!st) return;
@@ -626,6 +638,7 @@ int llb_s2m_iterate(llb_ctx *c, float T[6], int iter, int *converged, int *n_cor
     return guarded(c, [&]() {
         if (!T || iter < 0) return (int)LLB_ERR_INVALID;
         if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        if (holds_slab(c)) return (int)LLB_ERR_STATE;
         S2mQueries q = s2m_queries(c);
         const int nq = q.nc_upper + q.ns_upper;
         c->dbg_coeff.ensure(std::max(nq, 1)); c->dbg_valid.ensure(std::max(nq, 1));
@@ -650,6 +663,7 @@ int llb_s2m_optimize(llb_ctx *c, float T[6], llb_stats *stats)
     return guarded(c, [&]() {
         if (!T) return (int)LLB_ERR_INVALID;
         if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        if (holds_slab(c)) return (int)LLB_ERR_STATE;
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
@@ -674,6 +688,7 @@ int llb_s2m_optimize_async(llb_ctx *c, const float T[6])
     return guarded(c, [&]() {
         if (!T) return (int)LLB_ERR_INVALID;
         if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        if (holds_slab(c)) return (int)LLB_ERR_STATE;
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         LLB_CUDA(cudaEventRecord(c->ev0, c->stream));
@@ -710,6 +725,7 @@ int llb_s2m_optimize_dev(llb_ctx *c, float *T_dev)
     return guarded(c, [&]() {
         if (!T_dev) return (int)LLB_ERR_INVALID;
         if (!c->map_set || !c->scan_ds_done) return (int)LLB_ERR_STATE;
+        if (holds_slab(c)) return (int)LLB_ERR_STATE;
         S2mQueries q = s2m_queries(c);
         S2mDebug dbg{ nullptr, nullptr, nullptr, nullptr };
         c->launches += c->s2m.prepare(nullptr, T_dev, c->gridCorner.desc_dev(), c->gridSurf.desc_dev(), c->stream);

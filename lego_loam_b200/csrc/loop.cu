@@ -164,6 +164,7 @@ icp_kernel(IcpParams prm, const float4 *__restrict__ src, int ns, const float4 *
             for (int k = 0; k < ICP_NSUM; k++) a[k] = 0.0;
             for (int q = gtid; q < ns; q += gsz) {
                 const unsigned long long key = nn[q];
+                if (key == ~0ull) continue;                                      // no neighbour was found (a non-finite point)
                 const float d2 = __uint_as_float((unsigned)(key >> 32));
                 if (!final_pass && (double)d2 > max_d2) continue;            // correspondence_estimation.hpp
                 const float4 p = cur[q], c = __ldg(&tgt[(unsigned)(key & 0xffffffffu)]);
