@@ -1,7 +1,9 @@
-// batch.cu — kernels of the batched multi-registration engine (see batch.cuh): every launch covers
-// ALL slots of the batch (blockIdx.y = slot), so a step costs the same number of launches for 1 or
-// 64 independent sequences.  The arithmetic is the single-registration path's (s2m_dev.cuh, knn.cuh):
-// same expressions, same association order, fp64 accumulation of exact float products in a fixed order.
+// batch.cu — kernels of the batched multi-registration engine (see batch.cuh): every launch covers ALL slots of the
+// batch, so a step costs the same number of launches for 1 or 64 independent sequences, and scan2MapOptimization of all
+// slots is ONE persistent kernel (batch_lm_kernel: chunks of 32 queries handed out through per-slot control words, the
+// warp that delivers the last chunk of a (slot, iteration) takes the LM step and releases the next iteration).  The
+// arithmetic is the single-registration path's (s2m_dev.cuh, knn.cuh): same expressions, same association order, fp64
+// accumulation of exact float products in a fixed order.  Measured history: profiles/r02_knnfit.md.
 #include "batch.cuh"
 #include "s2m_dev.cuh"
 #include "knn.cuh"

@@ -1,10 +1,12 @@
-// odom.cu — K5: one persistent CTA runs both LM loops of updateTransformation
-// (FA:1666-1695).  One warp per feature point: the 1-NN over the previous sweep's cloud
-// is a warp-strided brute-force scan (exact, lexicographic (distance, index) minimum,
-// the clouds are a few thousand points and stay in L1/L2), the +-2.5-ring neighbour
-// scans of FA:1061-1099 / FA:1172-1220 are evaluated 32 candidates at a time with ballot
-// logic that reproduces the sequential "first strict minimum before the first break"
-// semantics, and lane k accumulates the k-th product of the 3x3 normal equations in fp64.
+// odom.cu — K5: both LM loops of updateTransformation (FA:1666-1695) in ONE persistent launch: an 8-CTA thread-block
+// cluster (odom_kernel; every CTA runs the deterministic iteration loop redundantly on its own shared-memory copy of
+// the state, the correspondence search of the refresh iterations is split by feature over the CTAs between two cluster
+// barriers) or, batched, one CTA per slot (odom_batch_kernel).  One warp per feature point: the exact 1-NN over the
+// previous sweep goes through a uniform-grid index built at llb_odom_set_last (cells of the 5 m gate, lexicographic
+// (distance, index) minimum), the +-2.5-ring neighbour scans of FA:1061-1099 / FA:1172-1220 are evaluated 32 candidates
+// at a time with ballot logic that reproduces the sequential "first strict minimum before the first break" semantics,
+// and lane k accumulates the k-th product of the 3x3 normal equations in fp64.  Quirk C20 (stale trees when the last
+// sweep has exactly 10 / 100 points, FA:1668 vs FA:1785) is reproduced by keeping the previous index in that case.
 #include "odom.cuh"
 #include "linalg.cuh"
 #include "glibc_sincosf.cuh"

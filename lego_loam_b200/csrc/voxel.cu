@@ -1,10 +1,9 @@
-// voxel.cu — K1 kernels.  Two paths:
-//  * small (<= 16384 points, every current-scan cloud of a VLP-16/HDL-32E): ONE CTA does
-//    min/max, key generation, a bitonic sort of (voxel index << 32 | point index) in shared
-//    memory, head flags + scan, and the ordered per-voxel sums -> 1 launch per filter;
-//  * large (local maps, VLS-128 scans): min/max -> setup -> keys -> stable LSD radix sort
-//    (8-bit digits, per-block histograms, warp-match ranking) -> head count -> scan ->
-//    ordered per-voxel sums.
+// voxel.cu — K1, the multi-kernel path for clouds that do not fit one CTA / cluster (local maps, VLS-128 scans; the
+// small paths live in voxel_small.cu): min/max -> setup -> keys (+ first histogram) -> stable LSD radix sort of (key,
+// input index) pairs (8-bit digits over the significant bits, per-block histograms, ranking by ballots, sub-tiles put
+// into digit order in shared memory before they leave) -> per-tile head counts -> scan -> centroids (tile staged in
+// shared memory, one thread per voxel, sums sequential in ascending input index).  Every kernel serves job blockIdx.y
+// of a device-resident table.  Measured history: profiles/r02_voxel.md.
 // The float arithmetic that decides membership is written exactly as PCL does it
 // (float multiply, floorf, float subtract, int cast) and this file is compiled with
 // -fmad=false, so voxel membership, order and centroids are bit-identical to the oracle.
