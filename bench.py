@@ -249,7 +249,7 @@ def run_reference(args):
     ctx = mp.get_context("spawn")
     barrier = ctx.Barrier(cores)
     with ctx.Pool(cores, initializer=_ref_init, initargs=(barrier,)) as pool:
-        res = pool.map(_ref_worker, [(c % max(args.distinct, 1), args.key_frames, args.scans, sensor, min(W, 2), per_core * K)
+        res = pool.map(_ref_worker, [(c % max(args.distinct if args.distinct > 0 else 32, 1), args.key_frames, args.scans, sensor, min(W, 2), per_core * K)
                                      for c in range(cores)], chunksize=1)
     wall = max(r[0] for r in res)
     kind = res[0][1]
@@ -688,7 +688,8 @@ def main():
     ap.add_argument("--workload", default="vlp16_100k", choices=sorted(WORKLOADS))
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences registered per step per GPU")
     ap.add_argument("--batches", type=int, default=2, help="batch objects (streams) the sequences are split over")
-    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic sequences generated per GPU (slots beyond reuse them with their own initial guesses)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic sequences generated per GPU (slots beyond reuse them with their own initial guesses); "
+                    "0 = 32 on one GPU, 16 per GPU under torchrun (the ranks share the host cores that ray-cast them: untimed set-up)")
     ap.add_argument("--scans", type=int, default=8, help="distinct new sweeps per sequence rotated through the steps")
     ap.add_argument("--cpu-sample", type=int, default=8, help="registrations timed for cpu_baseline")
     ap.add_argument("--key-frames", type=int, default=100, help="resident key-frames the local map of a sequence is assembled from")
@@ -717,7 +718,7 @@ def main():
 
     # ---------------- D distinct sequences per rank (ray-cast on the host, all cores, untimed); slot s replays
     # sequence s % D with its own device copies of the sweeps and its own initial guesses
-    D = max(1, min(args.distinct, S))
+    D = max(1, min(args.distinct if args.distinct > 0 else (32 if world == 1 else 16), S))
     seq = make_cycle_sequences([1000 * rank + d for d in range(D)], KF, NS, sensor)
     _log("sequences generated")
     host32 = [[tuple(api.to_pcl(x) for x in sw[:3]) for sw in seq[d][2]] for d in range(D)]      # the caller's PCL clouds
