@@ -74,6 +74,9 @@ void llo_cv_gemm_f32(int m, int k, int n, const float *A, const float *B, float 
  * through unchanged (PCL prints a warning and copies input to output).
  * Points inside a voxel are summed in ascending input-index order (stable). */
 int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *overflow);
+/* the same on pcl::PointXYZI-layout clouds (8 floats per point: x y z _ intensity _ _ _), written in that layout (the
+ * untouched floats of an output point keep what they held); out32 must have room for n points and must not alias in32 */
+int llo_voxel_grid_pcl(const float *in32, int n, float leaf, float *out32, int *overflow);
 
 /* pcl::KdTreeFLANN<PointXYZI>: exact k-NN, squared L2 in float
  * (flann::L2_Simple), results ascending; ties broken by smaller index. */

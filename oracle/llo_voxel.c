@@ -42,15 +42,23 @@ static void vox_sort(vox_pair *v, int n, int32_t max_idx)
     free(tmp);
 }
 
-int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *overflow)
+/* points are read as base[i * stride + {0, 1, 2, off_i}] = x, y, z, intensity and written the same way: stride 4 / off 3
+ * for llo_point, stride 8 / off 4 for pcl::PointXYZI's 32-byte layout (the tier-B shim filters the caller's clouds in
+ * place, as PCL does, instead of converting them - two copies less per filter on the CPU baseline) */
+static int voxel_grid_core(const float *in, int stride, int off_i, int n, float leaf, float *out, int ostride, int ooff_i,
+                           int *overflow)
 {
+#define PX(i) in[(size_t)(i) * stride]
+#define PY(i) in[(size_t)(i) * stride + 1]
+#define PZ(i) in[(size_t)(i) * stride + 2]
+#define PI(i) in[(size_t)(i) * stride + off_i]
     if (overflow) *overflow = 0;
     if (n <= 0) return 0;
 
     const float inv = 1.0f / leaf;
-    float mn[3] = { in[0].x, in[0].y, in[0].z }, mx[3] = { in[0].x, in[0].y, in[0].z };
+    float mn[3] = { PX(0), PY(0), PZ(0) }, mx[3] = { PX(0), PY(0), PZ(0) };
     for (int i = 1; i < n; i++) {
-        const float p[3] = { in[i].x, in[i].y, in[i].z };
+        const float p[3] = { PX(i), PY(i), PZ(i) };
         for (int a = 0; a < 3; a++) {
             if (p[a] < mn[a]) mn[a] = p[a];
             if (p[a] > mx[a]) mx[a] = p[a];
@@ -59,7 +67,10 @@ int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *
     int64_t d[3];
     for (int a = 0; a < 3; a++) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
     if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {
-        memcpy(out, in, sizeof(llo_point) * (size_t)n);
+        for (int i = 0; i < n; i++) {
+            float *o = out + (size_t)i * ostride;
+            o[0] = PX(i); o[1] = PY(i); o[2] = PZ(i); o[ooff_i] = PI(i);
+        }
         if (overflow) *overflow = 1;
         return n;
     }
@@ -73,9 +84,9 @@ int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *
 
     vox_pair *v = (vox_pair *)malloc(sizeof(vox_pair) * (size_t)n);
     for (int i = 0; i < n; i++) {
-        int ijk0 = (int)(floorf(in[i].x * inv) - (float)min_b[0]);
-        int ijk1 = (int)(floorf(in[i].y * inv) - (float)min_b[1]);
-        int ijk2 = (int)(floorf(in[i].z * inv) - (float)min_b[2]);
+        int ijk0 = (int)(floorf(PX(i) * inv) - (float)min_b[0]);
+        int ijk1 = (int)(floorf(PY(i) * inv) - (float)min_b[1]);
+        int ijk2 = (int)(floorf(PZ(i) * inv) - (float)min_b[2]);
         v[i].idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
         v[i].pt = i;
     }
@@ -86,15 +97,31 @@ int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *
         int j = i;
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         while (j < n && v[j].idx == v[i].idx) {
-            const llo_point *p = &in[v[j].pt];
-            sx += p->x; sy += p->y; sz += p->z; si += p->intensity;
+            const int p = v[j].pt;
+            sx += PX(p); sy += PY(p); sz += PZ(p); si += PI(p);
             j++;
         }
         float cnt = (float)(j - i);
-        out[m].x = sx / cnt; out[m].y = sy / cnt; out[m].z = sz / cnt; out[m].intensity = si / cnt;
+        float *o = out + (size_t)m * ostride;
+        o[0] = sx / cnt; o[1] = sy / cnt; o[2] = sz / cnt; o[ooff_i] = si / cnt;
         m++;
         i = j;
     }
     free(v);
     return m;
+#undef PX
+#undef PY
+#undef PZ
+#undef PI
+}
+
+int llo_voxel_grid(const llo_point *in, int n, float leaf, llo_point *out, int *overflow)
+{
+    return voxel_grid_core((const float *)in, 4, 3, n, leaf, (float *)out, 4, 3, overflow);
+}
+
+/* the same on clouds in pcl::PointXYZI's layout (8 floats per point: x y z _ intensity _ _ _); out must not alias in */
+int llo_voxel_grid_pcl(const float *in32, int n, float leaf, float *out32, int *overflow)
+{
+    return voxel_grid_core(in32, 8, 4, n, leaf, out32, 8, 4, overflow);
 }

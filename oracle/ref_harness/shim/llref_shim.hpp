@@ -376,19 +376,15 @@ public:
     void setInputCloud(const typename PointCloud<T>::ConstPtr &c) { in_ = c; }
     void filter(PointCloud<T> &out)
     {
-        std::vector<llo_point> a(in_ ? in_->points.size() : 0), b(a.size() ? a.size() : 1);
-        for (size_t i = 0; i < a.size(); i++) {
-            a[i].x = in_->points[i].x; a[i].y = in_->points[i].y; a[i].z = in_->points[i].z;
-            a[i].intensity = in_->points[i].intensity;
-        }
+        // the caller's clouds are filtered where they lie (32-byte points), as PCL does: no conversion copies
+        static_assert(sizeof(T) == 32, "pcl::PointXYZI layout");
+        const size_t n = in_ ? in_->points.size() : 0;
+        std::vector<T> tmp(n ? n : 1);                                         // default points: data[3] = 1, padding 0
         int ovf = 0;
-        int m = llo_voxel_grid(a.data(), (int)a.size(), leaf_, b.data(), &ovf);
-        out.points.resize(m);
-        for (int i = 0; i < m; i++) {
-            T p;
-            p.x = b[i].x; p.y = b[i].y; p.z = b[i].z; p.intensity = b[i].intensity;
-            out.points[i] = p;
-        }
+        const int m = n ? llo_voxel_grid_pcl(reinterpret_cast<const float *>(in_->points.data()), (int)n, leaf_,
+                                             reinterpret_cast<float *>(tmp.data()), &ovf) : 0;
+        tmp.resize(m);
+        out.points.swap(tmp);
         out.width = (uint32_t)m; out.height = 1; out.is_dense = true;
         if (in_) out.header = in_->header;
     }
